@@ -1,0 +1,231 @@
+/* itm_b200.h - C ABI of the B200-native InfiniTAM dense-fusion engines (libitm_b200.so).
+ *
+ * This is the drop-in boundary.  The reference selects its engines with
+ * `switch (settings->deviceType)` in three places (ITMLib/Engine/ITMMainEngine.cpp:21-45,
+ * ITMLib/Engine/ITMDenseMapper.cpp:16-34, ITMLib/Engine/ITMTrackerFactory.h:182-235); each
+ * function below is what one virtual method of those engine interfaces forwards to - the
+ * adapter classes that do the forwarding are in include/itm_b200_adapter.hpp and the wiring is
+ * shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, POD structs; no CUDA or torch types in any signature
+ *     (a cudaStream_t is passed as void*).
+ *   - every pointer named *_dev is DEVICE memory owned by the caller (in the reference: by
+ *     ORUtils::MemoryBlock<T>, ORUtils/MemoryBlock.h:173-263); the library only borrows it for
+ *     the duration of the call.  The handle owns scratch memory only.
+ *   - matrices are the reference's column-major float[16] (ORUtils/Matrix.h:8-33).
+ *   - layouts are the reference's: ITMHashEntry 16 B, ITMVoxel_s 4 B, Vector4f / Vector2f /
+ *     Vector4u images (ITMLib/Utils/ITMLibDefines.h:71-82, 157-179).
+ *   - every function returns 0 on success, a negative ITM_B200_E* code otherwise;
+ *     itm_b200_last_error() gives the message (the adapter turns it into DIEWITHEXCEPTION,
+ *     ORUtils/PlatformIndependence.h:34-38).  Pool exhaustion is not an error (the reference
+ *     silently skips the block, ITMSceneReconstructionEngine_CPU.cpp:187-189); it is counted.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     ITM_B200_ENODEVICE.
+ */
+#ifndef ITM_B200_H
+#define ITM_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ITM_B200_OK 0
+#define ITM_B200_EINVAL (-1)
+#define ITM_B200_ECUDA (-2)
+#define ITM_B200_ENODEVICE (-3)
+#define ITM_B200_EUNSUPPORTED (-4)
+
+#define ITM_B200_MAX_LEVELS 8
+
+/* TrackerIterationType, ITMLib/Utils/ITMLibDefines.h:278-283 */
+#define ITM_B200_ITER_ROTATION 1
+#define ITM_B200_ITER_TRANSLATION 2
+#define ITM_B200_ITER_BOTH 3
+#define ITM_B200_ITER_NONE 4
+
+/* What ITMLibSettings + ITMSceneParams + ITMRGBDCalib + the hash #defines carry
+ * (ITMLib/Utils/ITMLibSettings.cpp:9-88, ITMLib/Objects/ITMSceneParams.h:14-70,
+ *  ITMLib/Utils/ITMLibDefines.h:37-62).  Pool sizes are run-time here. */
+typedef struct itm_b200_params {
+  int width, height;                 /* depth image size */
+  float fx, fy, cx, cy;              /* intrinsics_d.projectionParamsSimple.all */
+  float voxel_size;                  /* sceneParams.voxelSize      (0.005) */
+  float mu;                          /* sceneParams.mu             (0.02)  */
+  int max_w;                         /* sceneParams.maxW           (100)   */
+  float view_frustum_min;            /* sceneParams.viewFrustum_min (0.35) */
+  float view_frustum_max;            /* sceneParams.viewFrustum_max (3.0)  */
+  int stop_integrating_at_max_w;     /* sceneParams.stopIntegratingAtMaxW (0) */
+  float depth_calib_a, depth_calib_b;/* ITMDisparityCalib TRAFO_AFFINE params (1/1000, 0) */
+  int sdf_local_block_num;           /* SDF_LOCAL_BLOCK_NUM   (0x10000)  */
+  int sdf_bucket_num;                /* SDF_BUCKET_NUM        (0x100000), power of two */
+  int sdf_excess_list_size;          /* SDF_EXCESS_LIST_SIZE  (0x20000)  */
+  int no_hierarchy_levels;           /* settings.noHierarchyLevels (5) */
+  int tracking_regime[ITM_B200_MAX_LEVELS]; /* settings.trackingRegime, level 0 = full res */
+  int no_icp_run_till_level;         /* settings.noICPRunTillLevel (0) */
+  float depth_tracker_icp_threshold; /* settings.depthTrackerICPThreshold (0.1*0.1) */
+  float depth_tracker_termination_threshold; /* (1e-3) */
+  int device;                        /* CUDA device ordinal */
+} itm_b200_params;
+
+/* Fills *p with the reference's defaults (ICP tracker regime) for a width x height sensor;
+ * intrinsics default to ITMIntrinsics() = (580, 580, 320, 240) scaled by width/640. */
+void itm_b200_default_params(itm_b200_params *p, int width, int height);
+
+const char *itm_b200_last_error(void);
+/* number of CUDA devices visible, or a negative error */
+int itm_b200_device_count(void);
+/* total kernels launched by this library in the calling process so far */
+unsigned long long itm_b200_launch_count(void);
+
+/* ===================================================================================== *
+ *  Layer A - one function per engine method, on caller-owned device buffers.            *
+ *  All of these return after the work has completed (stream-synchronised), like the     *
+ *  reference's own device engines do at their host-visible outputs.                     *
+ * ===================================================================================== */
+
+typedef struct itm_b200_ctx itm_b200_ctx;
+
+/* stream: a cudaStream_t (or NULL for a private stream).  */
+int itm_b200_ctx_create(const itm_b200_params *params, void *stream, itm_b200_ctx **out);
+void itm_b200_ctx_destroy(itm_b200_ctx *ctx);
+
+/* ITMScene<ITMVoxel_s, ITMVoxelBlockHash>: index + localVBA (ITMLib/Objects/ITMScene.h:20-51) */
+typedef struct itm_b200_scene {
+  void *voxel_blocks_dev;            /* localVBA.GetVoxelBlocks():  ITMVoxel_s[local*512]      */
+  void *hash_entries_dev;            /* index.GetEntries():         ITMHashEntry[bucket+excess] */
+  int *vba_allocation_list_dev;      /* localVBA.GetAllocationList(): int[local]               */
+  int *excess_allocation_list_dev;   /* index.GetExcessAllocationList(): int[excess]           */
+  int last_free_block_id;            /* localVBA.lastFreeBlockId            (host, in/out)      */
+  int last_free_excess_list_id;      /* index.Get/SetLastFreeExcessListId() (host, in/out)      */
+} itm_b200_scene;
+
+/* ITMRenderState_VH (ITMLib/Objects/ITMRenderState_VH.h:18-70, ITMRenderState.h:20-85) */
+typedef struct itm_b200_render_state {
+  int *visible_entry_ids_dev;            /* int[local] */
+  unsigned char *entries_visible_type_dev; /* uchar[bucket+excess] */
+  int no_visible_entries;                /* host, in/out */
+  float *rendering_range_image_dev;      /* Vector2f[w*h] */
+  float *raycast_result_dev;             /* Vector4f[w*h] */
+  unsigned char *raycast_image_dev;      /* Vector4u[w*h] */
+} itm_b200_render_state;
+
+/* ITMTrackingState (ITMLib/Objects/ITMTrackingState.h:19-85) */
+typedef struct itm_b200_tracking_state {
+  float *points_map_dev;             /* pointCloud->locations: Vector4f[w*h] */
+  float *normals_map_dev;            /* pointCloud->colours:   Vector4f[w*h] */
+  float pose_d[16];                  /* pose_d->GetM()           (host, in/out) */
+  float pose_point_cloud[16];        /* pose_pointCloud->GetM()  (host, in/out) */
+  int age_point_cloud;               /* host, in/out */
+} itm_b200_tracking_state;
+
+/* ITMSceneReconstructionEngine::ResetScene (Engine/ITMSceneReconstructionEngine.h:35) */
+int itm_b200_reset_scene(itm_b200_ctx *ctx, itm_b200_scene *scene);
+
+/* ITMSceneReconstructionEngine::AllocateSceneFromDepth (Engine/ITMSceneReconstructionEngine.h:41-42)
+ * depth_dev = view->depth (float metres); pose_M = trackingState->pose_d->GetM(). */
+int itm_b200_allocate_scene_from_depth(itm_b200_ctx *ctx, itm_b200_scene *scene, itm_b200_render_state *rs,
+                                       const float *depth_dev, const float pose_M[16], int only_update_visible_list);
+
+/* ITMSceneReconstructionEngine::IntegrateIntoScene (Engine/ITMSceneReconstructionEngine.h:47-48) */
+int itm_b200_integrate_into_scene(itm_b200_ctx *ctx, itm_b200_scene *scene, const itm_b200_render_state *rs,
+                                  const float *depth_dev, const float pose_M[16]);
+
+/* IITMVisualisationEngine::CreateExpectedDepths (Engine/ITMVisualisationEngine.h:46-47) */
+int itm_b200_create_expected_depths(itm_b200_ctx *ctx, const itm_b200_scene *scene, itm_b200_render_state *rs,
+                                    const float pose_M[16], const float intrinsics[4]);
+
+/* IITMVisualisationEngine::CreateICPMaps (Engine/ITMVisualisationEngine.h:66-67): raycast at
+ * ts->pose_d, fill points/normals/grey maps, set ts->pose_point_cloud = ts->pose_d. */
+int itm_b200_create_icp_maps(itm_b200_ctx *ctx, const itm_b200_scene *scene, itm_b200_render_state *rs,
+                             itm_b200_tracking_state *ts);
+
+/* ITMViewBuilder::ConvertDepthAffineToFloat (Engine/ITMViewBuilder.h) */
+int itm_b200_convert_depth_affine_to_float(itm_b200_ctx *ctx, float *depth_out_dev, const short *depth_in_dev, int w, int h,
+                                           float a, float b);
+
+/* ITMLowLevelEngine::FilterSubsampleWithHoles(float) (Engine/ITMLowLevelEngine.h:22) */
+int itm_b200_filter_subsample_with_holes(itm_b200_ctx *ctx, float *out_dev, const float *in_dev, int w_in, int h_in);
+
+/* ITMDepthTracker::ComputeGandH (Engine/ITMDepthTracker.h:56): one evaluation of the
+ * point-to-plane error at approx_inv_pose.  hessian is the full 6x6 (column-major, r + c*6) as
+ * the reference returns it; returns noValidPoints through *no_valid_points. */
+int itm_b200_compute_g_and_h(itm_b200_ctx *ctx, const float *level_depth_dev, int w, int h, const float view_intrinsics[4],
+                             const float *points_map_dev, const float *normals_map_dev, int scene_w, int scene_h,
+                             const float scene_intrinsics[4], const float approx_inv_pose[16], const float scene_pose[16],
+                             float dist_thresh, int iteration_type, float *f, float nabla[6], float hessian[36],
+                             int *no_valid_points);
+
+/* ITMTracker::TrackCamera (Engine/ITMTracker.h:26) for the depth ICP tracker: builds the depth
+ * pyramid from depth_dev and runs the whole Levenberg-Marquardt loop on the device; ts->pose_d
+ * is updated.  The map/pose fields of *ts are the tracker's inputs. */
+int itm_b200_track_camera(itm_b200_ctx *ctx, const float *depth_dev, itm_b200_tracking_state *ts);
+
+/* ===================================================================================== *
+ *  Layer B - ITMMainEngine: owns scene, render state, tracking state and view in HBM    *
+ *  and runs ProcessFrame (ITMLib/Engine/ITMMainEngine.cpp:111-127) without host syncs.  *
+ * ===================================================================================== */
+
+typedef struct itm_b200_engine itm_b200_engine;
+
+int itm_b200_engine_create(const itm_b200_params *params, itm_b200_engine **out);
+void itm_b200_engine_destroy(itm_b200_engine *e);
+/* denseMapper->ResetScene + fresh tracking state */
+int itm_b200_engine_reset(itm_b200_engine *e);
+
+/* ITMMainEngine::ProcessFrame(rgbImage, rawDepthImage).  rgb_host (Vector4u[w*h]) may be NULL;
+ * raw_depth_host is short[w*h] in host memory (pinned memory avoids a staging copy).  Returns
+ * after the frame is complete; pose_out (may be NULL) receives trackingState->pose_d->GetM(). */
+int itm_b200_engine_process_frame(itm_b200_engine *e, const unsigned char *rgb_host, const short *raw_depth_host,
+                                  float pose_out[16]);
+
+/* Same frame, input already resident in HBM, enqueued asynchronously on the engine's stream. */
+int itm_b200_engine_enqueue_frame_dev(itm_b200_engine *e, const short *raw_depth_dev);
+/* Wait for everything enqueued; counters = {noVisibleEntries, lastFreeBlockId,
+ * lastFreeExcessListId, allocFailures, errorFlags, icpEvaluations of last frame}. */
+int itm_b200_engine_sync(itm_b200_engine *e, float pose_out[16], int counters[6]);
+
+/* Single stages on the engine's own state, for stage-by-stage parity tests ("teacher forcing"):
+ * 0 view (needs a frame uploaded with itm_b200_engine_upload_depth), 1 track, 2 allocate,
+ * 3 integrate, 4 expected depths, 5 raycast + ICP maps. */
+int itm_b200_engine_upload_depth(itm_b200_engine *e, const short *raw_depth_host);
+int itm_b200_engine_run_stage(itm_b200_engine *e, int stage);
+
+/* Device buffers of the engine's state (borrowed pointers, valid until destroy). */
+enum {
+  ITM_B200_BUF_VOXELS = 0, ITM_B200_BUF_HASH, ITM_B200_BUF_VBA_ALLOC_LIST, ITM_B200_BUF_EXCESS_ALLOC_LIST,
+  ITM_B200_BUF_VISIBLE_IDS, ITM_B200_BUF_VISIBLE_TYPES, ITM_B200_BUF_DEPTH, ITM_B200_BUF_MINMAX, ITM_B200_BUF_RAYCAST_RESULT,
+  ITM_B200_BUF_RAYCAST_IMAGE, ITM_B200_BUF_POINTS, ITM_B200_BUF_NORMALS, ITM_B200_BUF_RAW_DEPTH, ITM_B200_BUF_PYRAMID_1,
+  ITM_B200_BUF_PYRAMID_2, ITM_B200_BUF_PYRAMID_3, ITM_B200_BUF_PYRAMID_4, ITM_B200_BUF_COUNT
+};
+int itm_b200_engine_get_buffer(itm_b200_engine *e, int which, void **dev_ptr, size_t *bytes);
+/* Blocking copies between one of those buffers and host memory (the reference's
+ * MemoryBlock::UpdateHostFromDevice / UpdateDeviceFromHost, ORUtils/MemoryBlock.h:112-121). */
+int itm_b200_engine_read_buffer(itm_b200_engine *e, int which, void *host_dst, size_t bytes, size_t offset);
+int itm_b200_engine_write_buffer(itm_b200_engine *e, int which, const void *host_src, size_t bytes, size_t offset);
+
+/* Host-visible tracking / scene state: pose_d, pose_pointCloud (column-major), and
+ * state6 = {noVisibleEntries, lastFreeBlockId, lastFreeExcessListId, age_pointCloud, 0, 0}. */
+int itm_b200_engine_get_state(itm_b200_engine *e, float pose_d[16], float pose_point_cloud[16], int state6[6]);
+int itm_b200_engine_set_state(itm_b200_engine *e, const float pose_d[16], const float pose_point_cloud[16], const int state6[6]);
+
+/* Per-stage device times (CUDA events) of the last processed frame in milliseconds:
+ * {h2d+view, track, allocate, integrate, expected depths, raycast, icp maps, total}.
+ * Enabled by itm_b200_engine_set_profiling(e, 1) (adds event records to the stream). */
+int itm_b200_engine_set_profiling(itm_b200_engine *e, int on);
+int itm_b200_engine_stage_times(itm_b200_engine *e, float ms8[8]);
+
+/* ---- host-side pose arithmetic (no GPU needed; used by the adapter and by tests) ---------- */
+/* Matrix4f::inv (ORUtils/Matrix.h:162-218) */
+int itm_b200_mat4_inv(const float m[16], float out[16]);
+/* ITMPose::SetInvM + Coerce + GetM/GetInvM (ITMLib/Objects/ITMPose.cpp:309-326) */
+int itm_b200_pose_from_inv_m_coerced(const float inv_m[16], float m_out[16], float inv_out[16], float params_out[6]);
+/* ITMDepthTracker::ComputeDelta (ITMLib/Engine/ITMDepthTracker.cpp:85-102) */
+int itm_b200_compute_delta(const float nabla[6], const float hessian[36], int short_iteration, float step_out[6]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ITM_B200_H */

@@ -1,0 +1,930 @@
+// Host side of libitm_b200.so: the C ABI declared in include/itm_b200.h.
+//
+// Layer A forwards one reference engine method per call onto caller-owned device buffers;
+// Layer B composes them the way ITMMainEngine does (ITMLib/Engine/ITMMainEngine.cpp:17-127,
+// ITMLib/Engine/ITMDenseMapper.cpp:51-65, ITMLib/Engine/ITMTrackingController.cpp:11-46) with
+// all cross-frame state resident in HBM and no host synchronisation inside a frame.
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/itm_b200.h"
+#include "itm_common.cuh"
+#include "kernels.h"
+#include "pose_math.cuh"
+
+using namespace itm;
+
+namespace {
+
+thread_local std::string g_lastError;
+std::atomic<unsigned long long> g_launches{0};
+
+int fail(int code, const std::string &msg) {
+  g_lastError = msg;
+  return code;
+}
+
+#define CU(expr)                                                                                   \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return fail(_e == cudaErrorNoDevice || _e == cudaErrorInsufficientDriver ? ITM_B200_ENODEVICE : ITM_B200_ECUDA, \
+                  std::string(#expr) + ": " + cudaGetErrorString(_e));                             \
+  } while (0)
+
+struct LevelCfg {
+  int w, h;
+  float fx, fy, cx, cy;
+  float distThresh;
+  int iterationType;
+  int noIterations;
+};
+
+}  // namespace
+
+struct itm_b200_ctx {
+  itm_b200_params p;
+  SceneParams sp;
+  ViewParams vp;
+  cudaStream_t stream = nullptr;
+  bool ownStream = false;
+  // scratch
+  unsigned *allocKey = nullptr;
+  unsigned long long *scanTickets = nullptr;
+  unsigned long long *allocTileState = nullptr;
+  unsigned long long *visTileState = nullptr;
+  double *icpPartials = nullptr;
+  unsigned *icpCounter = nullptr;
+  float *icpOut = nullptr;     // 44 floats
+  float *icpPoseIn = nullptr;  // 16 floats
+  FrameState *st = nullptr;    // device
+  FrameState *hst = nullptr;   // pinned host mirror
+  float *pyramid[ITM_MAX_LEVELS] = {nullptr};  // levels 1.. (level 0 is the caller's depth image)
+  LevelCfg levels[ITM_MAX_LEVELS];
+  int nLevels = 0;
+};
+
+namespace {
+
+int validate_params(const itm_b200_params *p) {
+  if (!p) return fail(ITM_B200_EINVAL, "params is NULL");
+  if (p->width <= 0 || p->height <= 0) return fail(ITM_B200_EINVAL, "image size must be positive");
+  if (p->sdf_bucket_num <= 0 || (p->sdf_bucket_num & (p->sdf_bucket_num - 1))) return fail(ITM_B200_EINVAL, "sdf_bucket_num must be a power of two");
+  if (p->sdf_local_block_num <= 0 || p->sdf_excess_list_size <= 0) return fail(ITM_B200_EINVAL, "pool sizes must be positive");
+  if ((long long)p->sdf_bucket_num + p->sdf_excess_list_size >= (1 << 21) * 1024LL) return fail(ITM_B200_EUNSUPPORTED, "hash table too large");
+  if (p->no_hierarchy_levels < 1 || p->no_hierarchy_levels > ITM_MAX_LEVELS) return fail(ITM_B200_EINVAL, "no_hierarchy_levels out of range");
+  if (!(p->voxel_size > 0) || !(p->mu > 0)) return fail(ITM_B200_EINVAL, "voxel_size and mu must be positive");
+  return ITM_B200_OK;
+}
+
+void derive(itm_b200_ctx *c) {
+  const itm_b200_params &p = c->p;
+  c->sp.voxelSize = p.voxel_size;
+  c->sp.mu = p.mu;
+  c->sp.maxW = p.max_w;
+  c->sp.vfMin = p.view_frustum_min;
+  c->sp.vfMax = p.view_frustum_max;
+  c->sp.stopAtMaxW = p.stop_integrating_at_max_w;
+  c->sp.nLocal = p.sdf_local_block_num;
+  c->sp.nBuckets = p.sdf_bucket_num;
+  c->sp.nExcess = p.sdf_excess_list_size;
+  c->sp.nEntries = p.sdf_bucket_num + p.sdf_excess_list_size;
+  c->sp.hashMask = (unsigned)p.sdf_bucket_num - 1u;
+  c->vp.W = p.width;
+  c->vp.H = p.height;
+  c->vp.fx = p.fx;
+  c->vp.fy = p.fy;
+  c->vp.cx = p.cx;
+  c->vp.cy = p.cy;
+  // ITMDepthTracker constructor (ITMLib/Engine/ITMDepthTracker.cpp:11-36) and
+  // PrepareForEvaluation's intrinsics halving (:62-75)
+  c->nLevels = p.no_hierarchy_levels;
+  int w = p.width, h = p.height;
+  float fx = p.fx, fy = p.fy, cx = p.cx, cy = p.cy;
+  for (int l = 0; l < c->nLevels; ++l) {
+    LevelCfg &L = c->levels[l];
+    L.w = w; L.h = h; L.fx = fx; L.fy = fy; L.cx = cx; L.cy = cy;
+    L.iterationType = p.tracking_regime[l];
+    L.noIterations = 2 + 2 * l;
+    w /= 2; h /= 2;
+    fx = fx * 0.5f; fy = fy * 0.5f; cx = cx * 0.5f; cy = cy * 0.5f;
+  }
+  const float distThresh = p.depth_tracker_icp_threshold;
+  const float step = distThresh / c->nLevels;
+  c->levels[c->nLevels - 1].distThresh = distThresh;
+  for (int l = c->nLevels - 2; l >= 0; --l) c->levels[l].distThresh = c->levels[l + 1].distThresh - step;
+}
+
+int ctx_alloc(itm_b200_ctx *c, void *stream) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return fail(ITM_B200_ENODEVICE, "no CUDA device available: this library has no CPU fallback");
+  CU(cudaSetDevice(c->p.device));
+  if (stream) {
+    c->stream = (cudaStream_t)stream;
+  } else {
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->ownStream = true;
+  }
+  const int numTiles = (c->sp.nEntries + 1023) / 1024;
+  const long long maxKey = (long long)c->p.width * c->p.height * alloc_step_bound(c->sp);
+  if (maxKey >= 0xFFFFFFFFLL) return fail(ITM_B200_EUNSUPPORTED, "image size x ray-segment steps exceeds the 32-bit allocation key");
+  CU(cudaMalloc(&c->allocKey, (size_t)numTiles * 1024 * sizeof(unsigned)));
+  CU(cudaMemsetAsync(c->allocKey, 0, (size_t)numTiles * 1024 * sizeof(unsigned), c->stream));
+  CU(cudaMalloc(&c->scanTickets, 2 * sizeof(unsigned long long)));
+  CU(cudaMemsetAsync(c->scanTickets, 0, 2 * sizeof(unsigned long long), c->stream));
+  CU(cudaMalloc(&c->allocTileState, numTiles * sizeof(unsigned long long)));
+  CU(cudaMemsetAsync(c->allocTileState, 0, numTiles * sizeof(unsigned long long), c->stream));
+  CU(cudaMalloc(&c->visTileState, numTiles * sizeof(unsigned long long)));
+  CU(cudaMemsetAsync(c->visTileState, 0, numTiles * sizeof(unsigned long long), c->stream));
+  CU(cudaMalloc(&c->icpPartials, (size_t)icp_max_ctas() * 32 * sizeof(double)));
+  CU(cudaMalloc(&c->icpCounter, sizeof(unsigned)));
+  CU(cudaMemsetAsync(c->icpCounter, 0, sizeof(unsigned), c->stream));
+  CU(cudaMalloc(&c->icpOut, 44 * sizeof(float)));
+  CU(cudaMalloc(&c->icpPoseIn, 16 * sizeof(float)));
+  CU(cudaMalloc(&c->st, sizeof(FrameState)));
+  CU(cudaMemsetAsync(c->st, 0, sizeof(FrameState), c->stream));
+  CU(cudaMallocHost(&c->hst, sizeof(FrameState)));
+  memset(c->hst, 0, sizeof(FrameState));
+  for (int l = 1; l < c->nLevels; ++l) {
+    const size_t n = (size_t)c->levels[l].w * c->levels[l].h;
+    CU(cudaMalloc(&c->pyramid[l], (n ? n : 1) * sizeof(float)));
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  return ITM_B200_OK;
+}
+
+void ctx_free(itm_b200_ctx *c) {
+  if (!c) return;
+  cudaFree(c->allocKey);
+  cudaFree(c->scanTickets);
+  cudaFree(c->allocTileState);
+  cudaFree(c->visTileState);
+  cudaFree(c->icpPartials);
+  cudaFree(c->icpCounter);
+  cudaFree(c->icpOut);
+  cudaFree(c->icpPoseIn);
+  cudaFree(c->st);
+  if (c->hst) cudaFreeHost(c->hst);
+  for (int l = 1; l < ITM_MAX_LEVELS; ++l) cudaFree(c->pyramid[l]);
+  if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
+}
+
+// identity pose etc.
+void host_state_init(FrameState *h, const SceneParams &sp) {
+  memset(h, 0, sizeof(FrameState));
+  const float I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  memcpy(h->M_d, I, sizeof(I));
+  memcpy(h->invM_d, I, sizeof(I));
+  memcpy(h->scenePose, I, sizeof(I));
+  h->noVisibleEntries = 0;
+  h->lastFreeBlockId = sp.nLocal - 1;
+  h->lastFreeExcessId = sp.nExcess - 1;
+  h->agePointCloud = -1;
+}
+
+void set_pose_host(FrameState *h, const float *M) {
+  memcpy(h->M_d, M, 64);
+  mat4_inv(M, h->invM_d);
+  pose_M_to_params(M, h->poseParams);
+}
+
+int push_state(itm_b200_ctx *c) {
+  CU(cudaMemcpyAsync(c->st, c->hst, sizeof(FrameState), cudaMemcpyHostToDevice, c->stream));
+  return ITM_B200_OK;
+}
+int pull_state(itm_b200_ctx *c) {
+  CU(cudaMemcpyAsync(c->hst, c->st, sizeof(FrameState), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  return ITM_B200_OK;
+}
+
+AllocArgs make_alloc_args(itm_b200_ctx *c, const float *depth, void *hash, const int *vbaList, const int *exList, int *visIds,
+                          unsigned char *visType, int onlyVisible) {
+  AllocArgs a;
+  a.depth = depth;
+  a.hashTable = hash;
+  a.vbaAllocList = vbaList;
+  a.excessAllocList = exList;
+  a.visibleIds = visIds;
+  a.visType = visType;
+  a.visibleCapacity = c->sp.nLocal;
+  a.allocKey = c->allocKey;
+  a.scanTickets = c->scanTickets;
+  a.allocTileState = c->allocTileState;
+  a.visTileState = c->visTileState;
+  a.st = c->st;
+  a.vp = c->vp;
+  a.sp = c->sp;
+  a.onlyUpdateVisibleList = onlyVisible;
+  return a;
+}
+
+IcpLevelArgs make_level_args(const itm_b200_ctx *c, int l, const float *depth) {
+  const LevelCfg &L = c->levels[l];
+  IcpLevelArgs lv;
+  lv.depth = depth;
+  lv.w = L.w; lv.h = L.h;
+  lv.fx = L.fx; lv.fy = L.fy; lv.cx = L.cx; lv.cy = L.cy;
+  lv.distThresh = L.distThresh;
+  lv.iterationType = L.iterationType;
+  return lv;
+}
+
+// ITMDepthTracker::TrackCamera: pyramid (unless already built) + LM loop, all enqueued
+void enqueue_track(itm_b200_ctx *c, const float *depth0, const float *points, const float *normals, bool buildPyramid) {
+  cudaStream_t s = c->stream;
+  if (buildPyramid && c->nLevels > 1) {
+    float *lv[ITM_MAX_LEVELS];
+    lv[0] = const_cast<float *>(depth0);
+    for (int l = 1; l < c->nLevels; ++l) lv[l] = c->pyramid[l];
+    launch_view_pyramid(nullptr, 0.f, 0.f, lv, c->vp.W, c->vp.H, c->nLevels, s);
+    g_launches += 1 + (c->nLevels > 5 ? c->nLevels - 5 : 0);
+  }
+  IcpArgs a;
+  a.pointsMap = points;
+  a.normalsMap = normals;
+  a.sceneVp = c->vp;
+  a.st = c->st;
+  a.partials = c->icpPartials;
+  a.ctaCounter = c->icpCounter;
+  a.terminationThreshold = c->p.depth_tracker_termination_threshold;
+  launch_icp_begin_frame(c->st, s);
+  g_launches += 1;
+  for (int l = c->nLevels - 1; l >= c->p.no_icp_run_till_level; --l) {
+    if (c->levels[l].iterationType == ITM_ITER_NONE) continue;
+    const IcpLevelArgs lv = make_level_args(c, l, l == 0 ? depth0 : c->pyramid[l]);
+    for (int it = 0; it < c->levels[l].noIterations; ++it) {
+      launch_icp_eval(a, lv, it == 0, 0, nullptr, nullptr, s);
+      g_launches += 1;
+    }
+  }
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+void itm_b200_default_params(itm_b200_params *p, int width, int height) {
+  memset(p, 0, sizeof(*p));
+  p->width = width;
+  p->height = height;
+  const float s = (float)width / 640.0f;
+  p->fx = 580.0f * s;
+  p->fy = 580.0f * s;
+  p->cx = (float)width / 2.0f;
+  p->cy = (float)height / 2.0f;
+  p->voxel_size = 0.005f;
+  p->mu = 0.02f;
+  p->max_w = 100;
+  p->view_frustum_min = 0.35f;
+  p->view_frustum_max = 3.0f;
+  p->stop_integrating_at_max_w = 0;
+  p->depth_calib_a = 1.0f / 1000.0f;
+  p->depth_calib_b = 0.0f;
+  p->sdf_local_block_num = 0x10000;
+  p->sdf_bucket_num = 0x100000;
+  p->sdf_excess_list_size = 0x20000;
+  p->no_hierarchy_levels = 5;
+  p->tracking_regime[0] = ITM_B200_ITER_BOTH;
+  p->tracking_regime[1] = ITM_B200_ITER_BOTH;
+  p->tracking_regime[2] = ITM_B200_ITER_ROTATION;
+  p->tracking_regime[3] = ITM_B200_ITER_ROTATION;
+  p->tracking_regime[4] = ITM_B200_ITER_ROTATION;
+  p->no_icp_run_till_level = 0;
+  p->depth_tracker_icp_threshold = 0.1f * 0.1f;
+  p->depth_tracker_termination_threshold = 1e-3f;
+  p->device = 0;
+}
+
+const char *itm_b200_last_error(void) { return g_lastError.c_str(); }
+
+int itm_b200_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) return fail(ITM_B200_ENODEVICE, cudaGetErrorString(e));
+  return n;
+}
+
+unsigned long long itm_b200_launch_count(void) { return g_launches.load(); }
+
+int itm_b200_ctx_create(const itm_b200_params *params, void *stream, itm_b200_ctx **out) {
+  if (!out) return fail(ITM_B200_EINVAL, "out is NULL");
+  *out = nullptr;
+  int rc = validate_params(params);
+  if (rc) return rc;
+  itm_b200_ctx *c = new itm_b200_ctx();
+  c->p = *params;
+  derive(c);
+  rc = ctx_alloc(c, stream);
+  if (rc) {
+    ctx_free(c);
+    delete c;
+    return rc;
+  }
+  host_state_init(c->hst, c->sp);
+  *out = c;
+  return ITM_B200_OK;
+}
+
+void itm_b200_ctx_destroy(itm_b200_ctx *ctx) {
+  if (!ctx) return;
+  ctx_free(ctx);
+  delete ctx;
+}
+
+int itm_b200_reset_scene(itm_b200_ctx *c, itm_b200_scene *scene) {
+  if (!c || !scene) return fail(ITM_B200_EINVAL, "NULL argument");
+  launch_reset_scene(scene->voxel_blocks_dev, scene->vba_allocation_list_dev, scene->hash_entries_dev, scene->excess_allocation_list_dev,
+                     c->sp, c->stream);
+  g_launches += 1;
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  scene->last_free_block_id = c->sp.nLocal - 1;
+  scene->last_free_excess_list_id = c->sp.nExcess - 1;
+  return ITM_B200_OK;
+}
+
+int itm_b200_allocate_scene_from_depth(itm_b200_ctx *c, itm_b200_scene *scene, itm_b200_render_state *rs, const float *depth_dev,
+                                       const float pose_M[16], int only_update_visible_list) {
+  if (!c || !scene || !rs || !depth_dev || !pose_M) return fail(ITM_B200_EINVAL, "NULL argument");
+  set_pose_host(c->hst, pose_M);
+  c->hst->noVisibleEntries = rs->no_visible_entries;
+  c->hst->lastFreeBlockId = scene->last_free_block_id;
+  c->hst->lastFreeExcessId = scene->last_free_excess_list_id;
+  c->hst->errorFlags = 0;
+  int rc = push_state(c);
+  if (rc) return rc;
+  launch_allocate(make_alloc_args(c, depth_dev, scene->hash_entries_dev, scene->vba_allocation_list_dev, scene->excess_allocation_list_dev,
+                                  rs->visible_entry_ids_dev, rs->entries_visible_type_dev, only_update_visible_list),
+                  c->stream);
+  g_launches += 4;
+  rc = pull_state(c);
+  if (rc) return rc;
+  rs->no_visible_entries = c->hst->noVisibleEntries;
+  scene->last_free_block_id = c->hst->lastFreeBlockId;
+  scene->last_free_excess_list_id = c->hst->lastFreeExcessId;
+  if (c->hst->errorFlags & 1) return fail(ITM_B200_EUNSUPPORTED, "allocation ray segment longer than the supported step bound");
+  return ITM_B200_OK;
+}
+
+int itm_b200_integrate_into_scene(itm_b200_ctx *c, itm_b200_scene *scene, const itm_b200_render_state *rs, const float *depth_dev,
+                                  const float pose_M[16]) {
+  if (!c || !scene || !rs || !depth_dev || !pose_M) return fail(ITM_B200_EINVAL, "NULL argument");
+  set_pose_host(c->hst, pose_M);
+  c->hst->noVisibleEntries = rs->no_visible_entries;
+  int rc = push_state(c);
+  if (rc) return rc;
+  IntegrateArgs a;
+  a.depth = depth_dev;
+  a.voxels = scene->voxel_blocks_dev;
+  a.hashTable = scene->hash_entries_dev;
+  a.visibleIds = rs->visible_entry_ids_dev;
+  a.st = c->st;
+  a.vp = c->vp;
+  a.sp = c->sp;
+  launch_integrate(a, c->stream);
+  g_launches += 1;
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  return ITM_B200_OK;
+}
+
+int itm_b200_create_expected_depths(itm_b200_ctx *c, const itm_b200_scene *scene, itm_b200_render_state *rs, const float pose_M[16],
+                                    const float intrinsics[4]) {
+  if (!c || !scene || !rs || !pose_M || !intrinsics) return fail(ITM_B200_EINVAL, "NULL argument");
+  set_pose_host(c->hst, pose_M);
+  c->hst->noVisibleEntries = rs->no_visible_entries;
+  int rc = push_state(c);
+  if (rc) return rc;
+  RenderArgs a;
+  memset(&a, 0, sizeof(a));
+  a.hashTable = scene->hash_entries_dev;
+  a.visibleIds = rs->visible_entry_ids_dev;
+  a.minmax = rs->rendering_range_image_dev;
+  a.st = c->st;
+  a.vp = c->vp;
+  a.vp.fx = intrinsics[0]; a.vp.fy = intrinsics[1]; a.vp.cx = intrinsics[2]; a.vp.cy = intrinsics[3];
+  a.sp = c->sp;
+  launch_expected_depths(a, c->stream);
+  g_launches += 2;
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  return ITM_B200_OK;
+}
+
+int itm_b200_create_icp_maps(itm_b200_ctx *c, const itm_b200_scene *scene, itm_b200_render_state *rs, itm_b200_tracking_state *ts) {
+  if (!c || !scene || !rs || !ts) return fail(ITM_B200_EINVAL, "NULL argument");
+  set_pose_host(c->hst, ts->pose_d);
+  int rc = push_state(c);
+  if (rc) return rc;
+  RenderArgs a;
+  memset(&a, 0, sizeof(a));
+  a.voxels = scene->voxel_blocks_dev;
+  a.hashTable = scene->hash_entries_dev;
+  a.minmax = rs->rendering_range_image_dev;
+  a.raycastResult = rs->raycast_result_dev;
+  a.raycastImage = rs->raycast_image_dev;
+  a.pointsMap = ts->points_map_dev;
+  a.normalsMap = ts->normals_map_dev;
+  a.st = c->st;
+  a.vp = c->vp;
+  a.sp = c->sp;
+  launch_raycast(a, c->stream);
+  launch_icp_maps(a, c->stream);
+  g_launches += 2;
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  // trackingState->pose_pointCloud->SetFrom(trackingState->pose_d)  (ITMVisualisationEngine_CPU.cpp:273)
+  memcpy(ts->pose_point_cloud, ts->pose_d, 64);
+  return ITM_B200_OK;
+}
+
+int itm_b200_convert_depth_affine_to_float(itm_b200_ctx *c, float *out_dev, const short *in_dev, int w, int h, float a, float b) {
+  if (!c || !out_dev || !in_dev) return fail(ITM_B200_EINVAL, "NULL argument");
+  launch_convert_depth(in_dev, out_dev, w * h, a, b, c->stream);
+  g_launches += 1;
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  return ITM_B200_OK;
+}
+
+int itm_b200_filter_subsample_with_holes(itm_b200_ctx *c, float *out_dev, const float *in_dev, int w_in, int h_in) {
+  if (!c || !out_dev || !in_dev) return fail(ITM_B200_EINVAL, "NULL argument");
+  launch_subsample_holes(out_dev, in_dev, w_in, h_in, c->stream);
+  g_launches += 1;
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  return ITM_B200_OK;
+}
+
+int itm_b200_compute_g_and_h(itm_b200_ctx *c, const float *level_depth_dev, int w, int h, const float view_intrinsics[4],
+                             const float *points_map_dev, const float *normals_map_dev, int scene_w, int scene_h,
+                             const float scene_intrinsics[4], const float approx_inv_pose[16], const float scene_pose[16], float dist_thresh,
+                             int iteration_type, float *f, float nabla[6], float hessian[36], int *no_valid_points) {
+  if (!c || !level_depth_dev || !points_map_dev || !normals_map_dev) return fail(ITM_B200_EINVAL, "NULL argument");
+  if (iteration_type == ITM_ITER_NONE) {
+    if (no_valid_points) *no_valid_points = 0;
+    return ITM_B200_OK;
+  }
+  memcpy(c->hst->scenePose, scene_pose, 64);
+  int rc = push_state(c);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(c->icpPoseIn, approx_inv_pose, 64, cudaMemcpyHostToDevice, c->stream));
+  IcpArgs a;
+  a.pointsMap = points_map_dev;
+  a.normalsMap = normals_map_dev;
+  a.sceneVp.W = scene_w; a.sceneVp.H = scene_h;
+  a.sceneVp.fx = scene_intrinsics[0]; a.sceneVp.fy = scene_intrinsics[1]; a.sceneVp.cx = scene_intrinsics[2]; a.sceneVp.cy = scene_intrinsics[3];
+  a.st = c->st;
+  a.partials = c->icpPartials;
+  a.ctaCounter = c->icpCounter;
+  a.terminationThreshold = c->p.depth_tracker_termination_threshold;
+  IcpLevelArgs lv;
+  lv.depth = level_depth_dev;
+  lv.w = w; lv.h = h;
+  lv.fx = view_intrinsics[0]; lv.fy = view_intrinsics[1]; lv.cx = view_intrinsics[2]; lv.cy = view_intrinsics[3];
+  lv.distThresh = dist_thresh;
+  lv.iterationType = iteration_type;
+  launch_icp_eval(a, lv, 1, 1, c->icpOut, c->icpPoseIn, c->stream);
+  g_launches += 1;
+  float out[44];
+  CU(cudaMemcpyAsync(out, c->icpOut, sizeof(out), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  if (no_valid_points) *no_valid_points = (int)out[0];
+  if (f) *f = out[1];
+  if (nabla) memcpy(nabla, out + 2, 6 * sizeof(float));
+  if (hessian) memcpy(hessian, out + 8, 36 * sizeof(float));
+  return ITM_B200_OK;
+}
+
+int itm_b200_track_camera(itm_b200_ctx *c, const float *depth_dev, itm_b200_tracking_state *ts) {
+  if (!c || !depth_dev || !ts) return fail(ITM_B200_EINVAL, "NULL argument");
+  set_pose_host(c->hst, ts->pose_d);
+  memcpy(c->hst->scenePose, ts->pose_point_cloud, 64);
+  int rc = push_state(c);
+  if (rc) return rc;
+  enqueue_track(c, depth_dev, ts->points_map_dev, ts->normals_map_dev, true);
+  rc = pull_state(c);
+  if (rc) return rc;
+  memcpy(ts->pose_d, c->hst->M_d, 64);
+  return ITM_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host pose helpers
+int itm_b200_mat4_inv(const float m[16], float out[16]) { return mat4_inv(m, out) ? ITM_B200_OK : ITM_B200_EINVAL; }
+
+int itm_b200_pose_from_inv_m_coerced(const float inv_m[16], float m_out[16], float inv_out[16], float params_out[6]) {
+  pose_set_invM_coerce(inv_m, m_out, params_out);
+  mat4_inv(m_out, inv_out);
+  return ITM_B200_OK;
+}
+
+int itm_b200_compute_delta(const float nabla[6], const float hessian[36], int short_iteration, float step_out[6]) {
+  icp_compute_delta(step_out, nabla, hessian, short_iteration != 0);
+  return ITM_B200_OK;
+}
+
+}  // extern "C"
+
+// =============================================================================================
+// Layer B
+
+struct itm_b200_engine {
+  itm_b200_ctx *c = nullptr;
+  // scene
+  void *voxels = nullptr;
+  void *hash = nullptr;
+  int *vbaAllocList = nullptr;
+  int *excessAllocList = nullptr;
+  // render state
+  int *visibleIds = nullptr;
+  unsigned char *visType = nullptr;
+  float *minmax = nullptr;
+  float *raycastResult = nullptr;
+  unsigned char *raycastImage = nullptr;
+  // tracking state
+  float *points = nullptr;
+  float *normals = nullptr;
+  // view
+  short *rawDepth = nullptr;
+  unsigned char *rgb = nullptr;
+  float *depth = nullptr;
+  int agePointCloud = -1;  // host copy; its evolution does not depend on device results
+  bool profiling = false;
+  cudaEvent_t ev[9] = {nullptr};
+  float stageMs[8] = {0};
+  size_t bytes[ITM_B200_BUF_COUNT] = {0};
+};
+
+namespace {
+
+int engine_alloc(itm_b200_engine *e) {
+  itm_b200_ctx *c = e->c;
+  const size_t P = (size_t)c->vp.W * c->vp.H;
+  CU(cudaMalloc(&e->voxels, (size_t)c->sp.nLocal * ITM_BLOCK_SIZE3 * 4));
+  CU(cudaMalloc(&e->hash, (size_t)c->sp.nEntries * 16));
+  CU(cudaMalloc(&e->vbaAllocList, (size_t)c->sp.nLocal * 4));
+  CU(cudaMalloc(&e->excessAllocList, (size_t)c->sp.nExcess * 4));
+  CU(cudaMalloc(&e->visibleIds, (size_t)c->sp.nLocal * 4));
+  CU(cudaMalloc(&e->visType, (size_t)((c->sp.nEntries + 1023) / 1024) * 1024));
+  CU(cudaMalloc(&e->minmax, P * 8));
+  CU(cudaMalloc(&e->raycastResult, P * 16));
+  CU(cudaMalloc(&e->raycastImage, P * 4));
+  CU(cudaMalloc(&e->points, P * 16));
+  CU(cudaMalloc(&e->normals, P * 16));
+  CU(cudaMalloc(&e->rawDepth, P * 2));
+  CU(cudaMalloc(&e->rgb, P * 4));
+  CU(cudaMalloc(&e->depth, P * 4));
+  for (int i = 0; i < 9; ++i) CU(cudaEventCreate(&e->ev[i]));
+  e->bytes[ITM_B200_BUF_VOXELS] = (size_t)c->sp.nLocal * ITM_BLOCK_SIZE3 * 4;
+  e->bytes[ITM_B200_BUF_HASH] = (size_t)c->sp.nEntries * 16;
+  e->bytes[ITM_B200_BUF_VBA_ALLOC_LIST] = (size_t)c->sp.nLocal * 4;
+  e->bytes[ITM_B200_BUF_EXCESS_ALLOC_LIST] = (size_t)c->sp.nExcess * 4;
+  e->bytes[ITM_B200_BUF_VISIBLE_IDS] = (size_t)c->sp.nLocal * 4;
+  e->bytes[ITM_B200_BUF_VISIBLE_TYPES] = (size_t)c->sp.nEntries;
+  e->bytes[ITM_B200_BUF_DEPTH] = P * 4;
+  e->bytes[ITM_B200_BUF_MINMAX] = P * 8;
+  e->bytes[ITM_B200_BUF_RAYCAST_RESULT] = P * 16;
+  e->bytes[ITM_B200_BUF_RAYCAST_IMAGE] = P * 4;
+  e->bytes[ITM_B200_BUF_POINTS] = P * 16;
+  e->bytes[ITM_B200_BUF_NORMALS] = P * 16;
+  e->bytes[ITM_B200_BUF_RAW_DEPTH] = P * 2;
+  for (int l = 1; l <= 4; ++l)
+    e->bytes[ITM_B200_BUF_PYRAMID_1 + l - 1] = l < c->nLevels ? (size_t)c->levels[l].w * c->levels[l].h * 4 : 0;
+  return ITM_B200_OK;
+}
+
+void engine_free(itm_b200_engine *e) {
+  cudaFree(e->voxels); cudaFree(e->hash); cudaFree(e->vbaAllocList); cudaFree(e->excessAllocList);
+  cudaFree(e->visibleIds); cudaFree(e->visType); cudaFree(e->minmax); cudaFree(e->raycastResult);
+  cudaFree(e->raycastImage); cudaFree(e->points); cudaFree(e->normals); cudaFree(e->rawDepth);
+  cudaFree(e->rgb); cudaFree(e->depth);
+  for (int i = 0; i < 9; ++i)
+    if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+  if (e->c) {
+    ctx_free(e->c);
+    delete e->c;
+  }
+}
+
+int engine_reset(itm_b200_engine *e) {
+  itm_b200_ctx *c = e->c;
+  const size_t P = (size_t)c->vp.W * c->vp.H;
+  launch_reset_scene(e->voxels, e->vbaAllocList, e->hash, e->excessAllocList, c->sp, c->stream);
+  g_launches += 1;
+  // MemoryBlock constructors clear their memory (ORUtils/MemoryBlock.h:88-110)
+  CU(cudaMemsetAsync(e->visType, 0, (size_t)((c->sp.nEntries + 1023) / 1024) * 1024, c->stream));
+  CU(cudaMemsetAsync(e->visibleIds, 0, (size_t)c->sp.nLocal * 4, c->stream));
+  CU(cudaMemsetAsync(e->raycastResult, 0, P * 16, c->stream));
+  CU(cudaMemsetAsync(e->raycastImage, 0, P * 4, c->stream));
+  CU(cudaMemsetAsync(e->points, 0, P * 16, c->stream));
+  CU(cudaMemsetAsync(e->normals, 0, P * 16, c->stream));
+  CU(cudaMemsetAsync(e->minmax, 0, P * 8, c->stream));
+  CU(cudaMemsetAsync(e->depth, 0, P * 4, c->stream));
+  CU(cudaMemsetAsync(c->allocKey, 0, (size_t)((c->sp.nEntries + 1023) / 1024) * 1024 * sizeof(unsigned), c->stream));
+  host_state_init(c->hst, c->sp);
+  int rc = push_state(c);
+  if (rc) return rc;
+  e->agePointCloud = -1;
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  return ITM_B200_OK;
+}
+
+void stage_view(itm_b200_engine *e) {
+  itm_b200_ctx *c = e->c;
+  float *lv[ITM_MAX_LEVELS];
+  lv[0] = e->depth;
+  for (int l = 1; l < c->nLevels; ++l) lv[l] = c->pyramid[l];
+  launch_view_pyramid(e->rawDepth, c->p.depth_calib_a, c->p.depth_calib_b, lv, c->vp.W, c->vp.H, c->nLevels, c->stream);
+  g_launches += 1 + (c->nLevels > 5 ? c->nLevels - 5 : 0);
+}
+
+void stage_track(itm_b200_engine *e) {
+  // ITMTrackingController::Track (ITMTrackingController.cpp:11-16)
+  if (e->agePointCloud != -1) enqueue_track(e->c, e->depth, e->points, e->normals, false);
+}
+
+void stage_allocate(itm_b200_engine *e) {
+  itm_b200_ctx *c = e->c;
+  launch_allocate(make_alloc_args(c, e->depth, e->hash, e->vbaAllocList, e->excessAllocList, e->visibleIds, e->visType, 0), c->stream);
+  g_launches += 4;
+}
+
+void stage_integrate(itm_b200_engine *e) {
+  itm_b200_ctx *c = e->c;
+  IntegrateArgs a;
+  a.depth = e->depth;
+  a.voxels = e->voxels;
+  a.hashTable = e->hash;
+  a.visibleIds = e->visibleIds;
+  a.st = c->st;
+  a.vp = c->vp;
+  a.sp = c->sp;
+  launch_integrate(a, c->stream);
+  g_launches += 1;
+}
+
+RenderArgs engine_render_args(itm_b200_engine *e) {
+  itm_b200_ctx *c = e->c;
+  RenderArgs a;
+  a.voxels = e->voxels;
+  a.hashTable = e->hash;
+  a.visibleIds = e->visibleIds;
+  a.minmax = e->minmax;
+  a.raycastResult = e->raycastResult;
+  a.pointsMap = e->points;
+  a.normalsMap = e->normals;
+  a.raycastImage = e->raycastImage;
+  a.st = c->st;
+  a.vp = c->vp;
+  a.sp = c->sp;
+  return a;
+}
+
+void stage_expected_depths(itm_b200_engine *e) {
+  launch_expected_depths(engine_render_args(e), e->c->stream);
+  g_launches += 2;
+}
+void stage_raycast(itm_b200_engine *e) {
+  launch_raycast(engine_render_args(e), e->c->stream);
+  g_launches += 1;
+}
+void stage_icp_maps(itm_b200_engine *e) {
+  // CreateICPMaps + the bookkeeping of ITMTrackingController::Prepare (:33-39); the copy
+  // pose_pointCloud <- pose_d happens inside the kernel (FrameState::scenePose)
+  launch_icp_maps(engine_render_args(e), e->c->stream);
+  g_launches += 1;
+  if (e->agePointCloud == -1) e->agePointCloud = -2;
+  else e->agePointCloud = 0;
+}
+
+void enqueue_frame(itm_b200_engine *e) {
+  cudaStream_t s = e->c->stream;
+  const bool prof = e->profiling;
+  if (prof) cudaEventRecord(e->ev[1], s);
+  stage_view(e);
+  if (prof) cudaEventRecord(e->ev[2], s);
+  stage_track(e);
+  if (prof) cudaEventRecord(e->ev[3], s);
+  stage_allocate(e);
+  if (prof) cudaEventRecord(e->ev[4], s);
+  stage_integrate(e);
+  if (prof) cudaEventRecord(e->ev[5], s);
+  stage_expected_depths(e);
+  if (prof) cudaEventRecord(e->ev[6], s);
+  stage_raycast(e);
+  if (prof) cudaEventRecord(e->ev[7], s);
+  stage_icp_maps(e);
+  if (prof) cudaEventRecord(e->ev[8], s);
+}
+
+}  // namespace
+
+extern "C" {
+
+int itm_b200_engine_create(const itm_b200_params *params, itm_b200_engine **out) {
+  if (!out) return fail(ITM_B200_EINVAL, "out is NULL");
+  *out = nullptr;
+  itm_b200_ctx *c = nullptr;
+  int rc = itm_b200_ctx_create(params, nullptr, &c);
+  if (rc) return rc;
+  itm_b200_engine *e = new itm_b200_engine();
+  e->c = c;
+  rc = engine_alloc(e);
+  if (!rc) rc = engine_reset(e);
+  if (rc) {
+    engine_free(e);
+    delete e;
+    return rc;
+  }
+  *out = e;
+  return ITM_B200_OK;
+}
+
+void itm_b200_engine_destroy(itm_b200_engine *e) {
+  if (!e) return;
+  engine_free(e);
+  delete e;
+}
+
+int itm_b200_engine_reset(itm_b200_engine *e) {
+  if (!e) return fail(ITM_B200_EINVAL, "NULL engine");
+  return engine_reset(e);
+}
+
+int itm_b200_engine_upload_depth(itm_b200_engine *e, const short *raw_depth_host) {
+  if (!e || !raw_depth_host) return fail(ITM_B200_EINVAL, "NULL argument");
+  const size_t P = (size_t)e->c->vp.W * e->c->vp.H;
+  CU(cudaMemcpyAsync(e->rawDepth, raw_depth_host, P * 2, cudaMemcpyHostToDevice, e->c->stream));
+  return ITM_B200_OK;
+}
+
+int itm_b200_engine_sync(itm_b200_engine *e, float pose_out[16], int counters[6]) {
+  if (!e) return fail(ITM_B200_EINVAL, "NULL engine");
+  int rc = pull_state(e->c);
+  if (rc) return rc;
+  const FrameState *h = e->c->hst;
+  if (pose_out) memcpy(pose_out, h->M_d, 64);
+  if (counters) {
+    counters[0] = h->noVisibleEntries;
+    counters[1] = h->lastFreeBlockId;
+    counters[2] = h->lastFreeExcessId;
+    counters[3] = h->allocFailures;
+    counters[4] = h->errorFlags;
+    counters[5] = h->icp.evalCount;
+  }
+  if (h->errorFlags & 1) return fail(ITM_B200_EUNSUPPORTED, "allocation ray segment longer than the supported step bound");
+  return ITM_B200_OK;
+}
+
+int itm_b200_engine_process_frame(itm_b200_engine *e, const unsigned char *rgb_host, const short *raw_depth_host, float pose_out[16]) {
+  if (!e || !raw_depth_host) return fail(ITM_B200_EINVAL, "NULL argument");
+  cudaStream_t s = e->c->stream;
+  const size_t P = (size_t)e->c->vp.W * e->c->vp.H;
+  if (e->profiling) cudaEventRecord(e->ev[0], s);
+  // ITMViewBuilder::UpdateView: rgb + raw depth to the device (ITMViewBuilder_CUDA.cu:52-53)
+  CU(cudaMemcpyAsync(e->rawDepth, raw_depth_host, P * 2, cudaMemcpyHostToDevice, s));
+  if (rgb_host) CU(cudaMemcpyAsync(e->rgb, rgb_host, P * 4, cudaMemcpyHostToDevice, s));
+  enqueue_frame(e);
+  return itm_b200_engine_sync(e, pose_out, nullptr);
+}
+
+int itm_b200_engine_enqueue_frame_dev(itm_b200_engine *e, const short *raw_depth_dev) {
+  if (!e || !raw_depth_dev) return fail(ITM_B200_EINVAL, "NULL argument");
+  cudaStream_t s = e->c->stream;
+  const size_t P = (size_t)e->c->vp.W * e->c->vp.H;
+  if (e->profiling) cudaEventRecord(e->ev[0], s);
+  if (raw_depth_dev != e->rawDepth) CU(cudaMemcpyAsync(e->rawDepth, raw_depth_dev, P * 2, cudaMemcpyDeviceToDevice, s));
+  enqueue_frame(e);
+  CU(cudaGetLastError());
+  return ITM_B200_OK;
+}
+
+int itm_b200_engine_run_stage(itm_b200_engine *e, int stage) {
+  if (!e) return fail(ITM_B200_EINVAL, "NULL engine");
+  switch (stage) {
+    case 0: stage_view(e); break;
+    case 1: stage_track(e); break;
+    case 2: stage_allocate(e); break;
+    case 3: stage_integrate(e); break;
+    case 4: stage_expected_depths(e); break;
+    case 5: stage_raycast(e); stage_icp_maps(e); break;
+    default: return fail(ITM_B200_EINVAL, "unknown stage");
+  }
+  return itm_b200_engine_sync(e, nullptr, nullptr);
+}
+
+int itm_b200_engine_get_buffer(itm_b200_engine *e, int which, void **dev_ptr, size_t *bytes) {
+  if (!e || !dev_ptr) return fail(ITM_B200_EINVAL, "NULL argument");
+  void *p = nullptr;
+  switch (which) {
+    case ITM_B200_BUF_VOXELS: p = e->voxels; break;
+    case ITM_B200_BUF_HASH: p = e->hash; break;
+    case ITM_B200_BUF_VBA_ALLOC_LIST: p = e->vbaAllocList; break;
+    case ITM_B200_BUF_EXCESS_ALLOC_LIST: p = e->excessAllocList; break;
+    case ITM_B200_BUF_VISIBLE_IDS: p = e->visibleIds; break;
+    case ITM_B200_BUF_VISIBLE_TYPES: p = e->visType; break;
+    case ITM_B200_BUF_DEPTH: p = e->depth; break;
+    case ITM_B200_BUF_MINMAX: p = e->minmax; break;
+    case ITM_B200_BUF_RAYCAST_RESULT: p = e->raycastResult; break;
+    case ITM_B200_BUF_RAYCAST_IMAGE: p = e->raycastImage; break;
+    case ITM_B200_BUF_POINTS: p = e->points; break;
+    case ITM_B200_BUF_NORMALS: p = e->normals; break;
+    case ITM_B200_BUF_RAW_DEPTH: p = e->rawDepth; break;
+    case ITM_B200_BUF_PYRAMID_1: case ITM_B200_BUF_PYRAMID_2: case ITM_B200_BUF_PYRAMID_3: case ITM_B200_BUF_PYRAMID_4:
+      p = e->c->pyramid[which - ITM_B200_BUF_PYRAMID_1 + 1]; break;
+    default: return fail(ITM_B200_EINVAL, "unknown buffer id");
+  }
+  *dev_ptr = p;
+  if (bytes) *bytes = e->bytes[which];
+  return ITM_B200_OK;
+}
+
+int itm_b200_engine_read_buffer(itm_b200_engine *e, int which, void *host_dst, size_t bytes, size_t offset) {
+  void *p = nullptr;
+  size_t total = 0;
+  int rc = itm_b200_engine_get_buffer(e, which, &p, &total);
+  if (rc) return rc;
+  if (!host_dst || offset + bytes > total) return fail(ITM_B200_EINVAL, "read_buffer: range outside the buffer");
+  CU(cudaMemcpyAsync(host_dst, (const char *)p + offset, bytes, cudaMemcpyDeviceToHost, e->c->stream));
+  CU(cudaStreamSynchronize(e->c->stream));
+  return ITM_B200_OK;
+}
+
+int itm_b200_engine_write_buffer(itm_b200_engine *e, int which, const void *host_src, size_t bytes, size_t offset) {
+  void *p = nullptr;
+  size_t total = 0;
+  int rc = itm_b200_engine_get_buffer(e, which, &p, &total);
+  if (rc) return rc;
+  if (!host_src || offset + bytes > total) return fail(ITM_B200_EINVAL, "write_buffer: range outside the buffer");
+  CU(cudaMemcpyAsync((char *)p + offset, host_src, bytes, cudaMemcpyHostToDevice, e->c->stream));
+  CU(cudaStreamSynchronize(e->c->stream));
+  return ITM_B200_OK;
+}
+
+int itm_b200_engine_get_state(itm_b200_engine *e, float pose_d[16], float pose_point_cloud[16], int state6[6]) {
+  if (!e) return fail(ITM_B200_EINVAL, "NULL engine");
+  int rc = pull_state(e->c);
+  if (rc) return rc;
+  const FrameState *h = e->c->hst;
+  if (pose_d) memcpy(pose_d, h->M_d, 64);
+  if (pose_point_cloud) memcpy(pose_point_cloud, h->scenePose, 64);
+  if (state6) {
+    state6[0] = h->noVisibleEntries;
+    state6[1] = h->lastFreeBlockId;
+    state6[2] = h->lastFreeExcessId;
+    state6[3] = e->agePointCloud;
+    state6[4] = 0;
+    state6[5] = 0;
+  }
+  return ITM_B200_OK;
+}
+
+int itm_b200_engine_set_state(itm_b200_engine *e, const float pose_d[16], const float pose_point_cloud[16], const int state6[6]) {
+  if (!e) return fail(ITM_B200_EINVAL, "NULL engine");
+  int rc = pull_state(e->c);
+  if (rc) return rc;
+  FrameState *h = e->c->hst;
+  if (pose_d) set_pose_host(h, pose_d);
+  if (pose_point_cloud) memcpy(h->scenePose, pose_point_cloud, 64);
+  if (state6) {
+    h->noVisibleEntries = state6[0];
+    h->lastFreeBlockId = state6[1];
+    h->lastFreeExcessId = state6[2];
+    e->agePointCloud = state6[3];
+  }
+  rc = push_state(e->c);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(e->c->stream));
+  return ITM_B200_OK;
+}
+
+int itm_b200_engine_set_profiling(itm_b200_engine *e, int on) {
+  if (!e) return fail(ITM_B200_EINVAL, "NULL engine");
+  e->profiling = on != 0;
+  return ITM_B200_OK;
+}
+
+int itm_b200_engine_stage_times(itm_b200_engine *e, float ms8[8]) {
+  if (!e || !ms8) return fail(ITM_B200_EINVAL, "NULL argument");
+  if (!e->profiling) return fail(ITM_B200_EINVAL, "profiling is off");
+  // ev[0] frame start, ev[1] after H2D, ev[2] after view, ev[3] track, ev[4] allocate, ev[5] integrate,
+  // ev[6] expected depths, ev[7] raycast, ev[8] icp maps
+  float t;
+  cudaEventElapsedTime(&t, e->ev[0], e->ev[2]); ms8[0] = t;
+  for (int i = 1; i < 7; ++i) { cudaEventElapsedTime(&t, e->ev[i + 1], e->ev[i + 2]); ms8[i] = t; }
+  cudaEventElapsedTime(&t, e->ev[0], e->ev[8]); ms8[7] = t;
+  return ITM_B200_OK;
+}
+
+}  // extern "C"

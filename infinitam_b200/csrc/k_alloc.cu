@@ -1,0 +1,392 @@
+// Voxel-block hash allocation and visible-list construction.
+//
+// Replaces ITMSceneReconstructionEngine::AllocateSceneFromDepth
+//   CPU driver      ITMLib/Engine/DeviceSpecific/CPU/ITMSceneReconstructionEngine_CPU.cpp:117-291
+//   per pixel       buildHashAllocAndVisibleTypePP  ITMLib/Engine/DeviceAgnostic/ITMSceneReconstructionEngine.h:141-241
+//   visibility      checkBlockVisibility / checkPointVisibility  same file :244-342
+//
+// Determinism.  The reference's per-pixel pass is "last writer wins" per hash slot in raster
+// (pixel, step) order, and its allocation loop hands out free-list entries in ascending slot
+// order.  Both are reproduced exactly, without serial loops:
+//   1. k_alloc_pixels: every ray-segment step that misses the table does
+//      atomicMax(allocKey[slot], pixel * stepBound + step + 1) - the largest key IS the last
+//      writer of the serial loop.  The block coordinate is not stored; the winner's
+//      coordinate is recomputed from its key in step 2 by the same device function.
+//   2. k_alloc_scan: single-pass ordered scan over all slots (scan_util.cuh) gives every
+//      request its rank, hence exactly the VBA / excess-list entries the serial loop would
+//      pop.  The hash table (pos, offset, ptr) comes out bit-identical to the reference.
+//   3. k_visible_scan: same scan machinery over entriesVisibleType; visibleEntryIDs come out
+//      in ascending slot order like the reference's.
+// No counter is read back by the host; the free-list heads and the visible count live in
+// FrameState.
+#include "itm_common.cuh"
+#include "kernels.h"
+#include "scan_util.cuh"
+
+namespace {
+
+using namespace itm;
+
+struct RaySegment {
+  float px, py, pz;  // start point in block units
+  float dx, dy, dz;  // per-step increment
+  int noSteps;
+};
+
+// ITMSceneReconstructionEngine.h:153-185; returns false when the pixel is rejected
+__device__ __forceinline__ bool make_ray_segment(RaySegment &r, float depth_measure, int x, int y, const float *invM_d,
+                                                 float invFx, float invFy, float cx, float cy, float mu, float oneOverVoxelSize,
+                                                 float vfMin, float vfMax) {
+  if (depth_measure <= 0 || (depth_measure - mu) < 0 || (depth_measure - mu) < vfMin || (depth_measure + mu) > vfMax) return false;
+  const float cz = depth_measure;
+  const float cxx = cz * (((float)x - cx) * invFx);
+  const float cyy = cz * (((float)y - cy) * invFy);
+  float norm = sqrtf(cxx * cxx + cyy * cyy + cz * cz);
+  const float s0 = 1.0f - mu / norm;
+  const float s1 = 1.0f + mu / norm;
+  float ax, ay, az, bx, by, bz;
+  mat4_mul_vec4(invM_d, cxx * s0, cyy * s0, cz * s0, 1.0f, ax, ay, az);
+  ax *= oneOverVoxelSize; ay *= oneOverVoxelSize; az *= oneOverVoxelSize;
+  mat4_mul_vec4(invM_d, cxx * s1, cyy * s1, cz * s1, 1.0f, bx, by, bz);
+  bx *= oneOverVoxelSize; by *= oneOverVoxelSize; bz *= oneOverVoxelSize;
+  float dx = bx - ax, dy = by - ay, dz = bz - az;
+  norm = sqrtf(dx * dx + dy * dy + dz * dz);
+  const int noSteps = (int)ceilf(2.0f * norm);
+  const float div = (float)(noSteps - 1);
+  r.px = ax; r.py = ay; r.pz = az;
+  r.dx = dx / div; r.dy = dy / div; r.dz = dz / div;
+  r.noSteps = noSteps;
+  return true;
+}
+
+__device__ __forceinline__ void block_of(float px, float py, float pz, int &bx, int &by, int &bz) {
+  bx = (short)(int)floorf(px);
+  by = (short)(int)floorf(py);
+  bz = (short)(int)floorf(pz);
+}
+
+// marks last frame's visible entries as "3" (:159-160) and snapshots the free-list heads the
+// allocation scan will count down from
+__global__ void k_mark_prev_visible(const int *__restrict__ visibleIds, unsigned char *__restrict__ visType, FrameState *st) {
+  const int n = st->noVisibleEntries;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    st->allocBaseBlockId = st->lastFreeBlockId;
+    st->allocBaseExcessId = st->lastFreeExcessId;
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) visType[visibleIds[i]] = 3;
+}
+
+__global__ void __launch_bounds__(256) k_alloc_pixels(const float *__restrict__ depth, const HashEntry *__restrict__ table,
+                                                      unsigned char *__restrict__ visType, unsigned *__restrict__ allocKey,
+                                                      FrameState *st, ViewParams vp, SceneParams sp, float oneOverVoxelSize,
+                                                      int stepBound) {
+  __shared__ float sInvM[16];
+  if (threadIdx.x < 16) sInvM[threadIdx.x] = st->invM_d[threadIdx.x];
+  __syncthreads();
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= vp.W || y >= vp.H) return;
+  const int locId = x + y * vp.W;
+  RaySegment r;
+  // invProjParams: x,y are 1/fx, 1/fy computed by the host as float divisions (:131-133)
+  if (!make_ray_segment(r, __ldg(depth + locId), x, y, sInvM, 1.0f / vp.fx, 1.0f / vp.fy, vp.cx, vp.cy, sp.mu, oneOverVoxelSize, sp.vfMin,
+                        sp.vfMax))
+    return;
+  if (r.noSteps > stepBound) {
+    atomicOr(&st->errorFlags, 1);
+    r.noSteps = stepBound;
+  }
+  float px = r.px, py = r.py, pz = r.pz;
+  for (int i = 0; i < r.noSteps; ++i) {
+    int bx, by, bz;
+    block_of(px, py, pz, bx, by, bz);
+    int hashIdx = (int)hash_index(bx, by, bz, sp.hashMask);
+    HashEntry e = load_entry(table, hashIdx);
+    bool isFound = false;
+    if (e.px == bx && e.py == by && e.pz == bz && e.ptr >= -1) {
+      visType[hashIdx] = (e.ptr == -1) ? 2 : 1;
+      isFound = true;
+    }
+    if (!isFound) {
+      bool isExcess = false;
+      if (e.ptr >= -1) {
+        while (e.offset >= 1) {
+          hashIdx = sp.nBuckets + e.offset - 1;
+          e = load_entry(table, hashIdx);
+          if (e.px == bx && e.py == by && e.pz == bz && e.ptr >= -1) {
+            visType[hashIdx] = (e.ptr == -1) ? 2 : 1;
+            isFound = true;
+            break;
+          }
+        }
+        isExcess = true;
+      }
+      if (!isFound) {
+        atomicMax(allocKey + hashIdx, (unsigned)locId * (unsigned)stepBound + (unsigned)i + 1u);
+        if (!isExcess) visType[hashIdx] = 1;
+      }
+    }
+    px += r.dx; py += r.dy; pz += r.dz;
+  }
+}
+
+// 256 threads x 4 slots = 1024-slot tiles
+__global__ void __launch_bounds__(256) k_alloc_scan(unsigned *__restrict__ allocKey, HashEntry *__restrict__ table,
+                                                    unsigned char *__restrict__ visType, const int *__restrict__ vbaAllocList,
+                                                    const int *__restrict__ excessAllocList, const float *__restrict__ depth,
+                                                    FrameState *st, ViewParams vp, SceneParams sp, float oneOverVoxelSize,
+                                                    int stepBound, int doAllocate, unsigned long long *ticket,
+                                                    unsigned long long *tileState, int numTiles) {
+  __shared__ unsigned sWarp[8];
+  __shared__ unsigned sTotal;
+  __shared__ unsigned sExA, sExB;
+  __shared__ int sTile;
+  __shared__ unsigned sEpoch;
+  __shared__ float sInvM[16];
+  if (threadIdx.x == 0) {
+    const unsigned long long t = atomicAdd(ticket, 1ull);
+    sTile = (int)(t % (unsigned long long)numTiles);
+    sEpoch = (unsigned)((t / (unsigned long long)numTiles + 1ull) & 0xFFFFFull);
+  }
+  if (threadIdx.x < 16) sInvM[threadIdx.x] = st->invM_d[threadIdx.x];
+  __syncthreads();
+  const int tile = sTile;
+  const int slot0 = tile * 1024 + threadIdx.x * 4;
+  uint4 k4 = make_uint4(0, 0, 0, 0);
+  if (slot0 + 3 < sp.nEntries) {
+    k4 = *reinterpret_cast<const uint4 *>(allocKey + slot0);
+  } else {
+    if (slot0 + 0 < sp.nEntries) k4.x = allocKey[slot0 + 0];
+    if (slot0 + 1 < sp.nEntries) k4.y = allocKey[slot0 + 1];
+    if (slot0 + 2 < sp.nEntries) k4.z = allocKey[slot0 + 2];
+  }
+  const unsigned keys[4] = {k4.x, k4.y, k4.z, k4.w};
+  int type[4];
+  unsigned packed = 0;  // low 16: all requests, high 16: excess-list requests
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    type[j] = 0;
+    if (keys[j] != 0 && doAllocate) {
+      const int slot = slot0 + j;
+      int t = 2;
+      if (slot < sp.nBuckets && table[slot].ptr < -1) t = 1;
+      type[j] = t;
+      packed += 1u + (t == 2 ? 0x10000u : 0u);
+    }
+  }
+  const unsigned excl = block_exclusive_scan_256(packed, sWarp, &sTotal);
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    unsigned exA, exB;
+    scan_lookback(tileState, tile, sEpoch, sTotal & 0xFFFFu, sTotal >> 16, exA, exB);
+    if (threadIdx.x == 0) {
+      sExA = exA;
+      sExB = exB;
+      if (tile == numTiles - 1) {
+        // counters always count down by the number of requests, successful or not (:186, :204-205)
+        st->lastFreeBlockId = st->allocBaseBlockId - (int)(exA + (sTotal & 0xFFFFu));
+        st->lastFreeExcessId = st->allocBaseExcessId - (int)(exB + (sTotal >> 16));
+      }
+    }
+  }
+  __syncthreads();
+  if (packed == 0 && (k4.x | k4.y | k4.z | k4.w) == 0) return;
+  int rankA = (int)(sExA + (excl & 0xFFFFu));
+  int rankB = (int)(sExB + (excl >> 16));
+  const int baseVba = st->allocBaseBlockId, baseExl = st->allocBaseExcessId;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (keys[j] == 0) continue;
+    const int slot = slot0 + j;
+    allocKey[slot] = 0;  // leave the array clean for the next frame
+    if (type[j] == 0) continue;
+    // recompute the winning request's block coordinate from its (pixel, step) key
+    const unsigned key = keys[j] - 1u;
+    const int locId = (int)(key / (unsigned)stepBound), step = (int)(key % (unsigned)stepBound);
+    const int y = locId / vp.W, x = locId - y * vp.W;
+    RaySegment r;
+    make_ray_segment(r, __ldg(depth + locId), x, y, sInvM, 1.0f / vp.fx, 1.0f / vp.fy, vp.cx, vp.cy, sp.mu, oneOverVoxelSize, sp.vfMin,
+                     sp.vfMax);
+    float px = r.px, py = r.py, pz = r.pz;
+    for (int i = 0; i < step; ++i) { px += r.dx; py += r.dy; pz += r.dz; }
+    int bx, by, bz;
+    block_of(px, py, pz, bx, by, bz);
+    const int vbaIdx = baseVba - rankA;
+    rankA++;
+    if (type[j] == 1) {
+      if (vbaIdx >= 0) store_entry(table, slot, bx, by, bz, 0, vbaAllocList[vbaIdx]);
+      else atomicAdd(&st->allocFailures, 1);
+    } else {
+      const int exlIdx = baseExl - rankB;
+      rankB++;
+      if (vbaIdx >= 0 && exlIdx >= 0) {
+        const int exlOffset = excessAllocList[exlIdx];
+        table[slot].offset = exlOffset + 1;
+        store_entry(table, sp.nBuckets + exlOffset, bx, by, bz, 0, vbaAllocList[vbaIdx]);
+        visType[sp.nBuckets + exlOffset] = 1;
+      } else {
+        atomicAdd(&st->allocFailures, 1);
+      }
+    }
+  }
+}
+
+// checkPointVisibility<false>, ITMSceneReconstructionEngine.h:244-274
+__device__ __forceinline__ bool point_visible(const float *M, float x, float y, float z, const ViewParams &vp) {
+  float bx, by, bz;
+  mat4_mul_vec4(M, x, y, z, 1.0f, bx, by, bz);
+  if (bz < 1e-10f) return false;
+  bx = vp.fx * bx / bz + vp.cx;
+  by = vp.fy * by / bz + vp.cy;
+  return bx >= 0 && bx < (float)vp.W && by >= 0 && by < (float)vp.H;
+}
+
+// checkBlockVisibility<false>, :277-342 - the corner coordinates are built by the same chain of
+// += / -= as the reference so that they round identically
+__device__ bool block_visible(const float *M, int hx, int hy, int hz, float voxelSize, const ViewParams &vp) {
+  const float factor = (float)ITM_BLOCK_SIZE * voxelSize;
+  float x = (float)hx * factor, y = (float)hy * factor, z = (float)hz * factor;
+  if (point_visible(M, x, y, z, vp)) return true;  // 0 0 0
+  z += factor;
+  if (point_visible(M, x, y, z, vp)) return true;  // 0 0 1
+  y += factor;
+  if (point_visible(M, x, y, z, vp)) return true;  // 0 1 1
+  x += factor;
+  if (point_visible(M, x, y, z, vp)) return true;  // 1 1 1
+  z -= factor;
+  if (point_visible(M, x, y, z, vp)) return true;  // 1 1 0
+  y -= factor;
+  if (point_visible(M, x, y, z, vp)) return true;  // 1 0 0
+  x -= factor;
+  y += factor;
+  if (point_visible(M, x, y, z, vp)) return true;  // 0 1 0
+  x += factor;
+  y -= factor;
+  z += factor;
+  if (point_visible(M, x, y, z, vp)) return true;  // 1 0 1
+  return false;
+}
+
+__global__ void __launch_bounds__(256) k_visible_scan(unsigned char *__restrict__ visType, const HashEntry *__restrict__ table,
+                                                      int *__restrict__ visibleIds, FrameState *st, ViewParams vp, SceneParams sp,
+                                                      int visibleCapacity, unsigned long long *ticket, unsigned long long *tileState,
+                                                      int numTiles) {
+  __shared__ unsigned sWarp[8];
+  __shared__ unsigned sTotal;
+  __shared__ unsigned sExA;
+  __shared__ int sTile;
+  __shared__ unsigned sEpoch;
+  __shared__ float sM[16];
+  if (threadIdx.x == 0) {
+    const unsigned long long t = atomicAdd(ticket, 1ull);
+    sTile = (int)(t % (unsigned long long)numTiles);
+    sEpoch = (unsigned)((t / (unsigned long long)numTiles + 1ull) & 0xFFFFFull);
+  }
+  if (threadIdx.x < 16) sM[threadIdx.x] = st->M_d[threadIdx.x];
+  __syncthreads();
+  const int tile = sTile;
+  const int slot0 = tile * 1024 + threadIdx.x * 4;
+  unsigned v4 = 0;
+  if (slot0 + 3 < sp.nEntries) {
+    v4 = *reinterpret_cast<const unsigned *>(visType + slot0);
+  } else {
+    for (int j = 0; j < 4; ++j)
+      if (slot0 + j < sp.nEntries) v4 |= (unsigned)visType[slot0 + j] << (8 * j);
+  }
+  unsigned cnt = 0;
+  unsigned out4 = v4;
+  if (v4 != 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      unsigned t = (v4 >> (8 * j)) & 0xFFu;
+      if (t == 3) {
+        const HashEntry e = load_entry_cg(table, slot0 + j);
+        if (!block_visible(sM, e.px, e.py, e.pz, sp.voxelSize, vp)) {
+          t = 0;
+          out4 &= ~(0xFFu << (8 * j));
+        }
+      }
+      if (t > 0) cnt++;
+    }
+    if (out4 != v4) {
+      if (slot0 + 3 < sp.nEntries) *reinterpret_cast<unsigned *>(visType + slot0) = out4;
+      else
+        for (int j = 0; j < 4; ++j)
+          if (slot0 + j < sp.nEntries) visType[slot0 + j] = (unsigned char)(out4 >> (8 * j));
+    }
+  }
+  const unsigned excl = block_exclusive_scan_256(cnt, sWarp, &sTotal);
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    unsigned exA, exB;
+    scan_lookback(tileState, tile, sEpoch, sTotal, 0, exA, exB);
+    if (threadIdx.x == 0) {
+      sExA = exA;
+      if (tile == numTiles - 1) {
+        int total = (int)(exA + sTotal);
+        if (total > visibleCapacity) {
+          atomicOr(&st->errorFlags, 2);
+          total = visibleCapacity;
+        }
+        st->noVisibleEntries = total;
+      }
+    }
+  }
+  __syncthreads();
+  if (cnt == 0) return;
+  int pos = (int)(sExA + excl);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if ((out4 >> (8 * j)) & 0xFFu) {
+      if (pos < visibleCapacity) visibleIds[pos] = slot0 + j;
+      pos++;
+    }
+  }
+}
+
+// ResetScene, ITMSceneReconstructionEngine_CPU.cpp:25-45
+__global__ void k_reset_scene(uint32_t *__restrict__ voxels, size_t nVoxels, int *__restrict__ vbaAllocList, int nLocal,
+                              HashEntry *__restrict__ table, int nEntries, int *__restrict__ excessAllocList, int nExcess,
+                              uint32_t emptyVoxel) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint4 *v4 = reinterpret_cast<uint4 *>(voxels);
+  const uint4 ev = make_uint4(emptyVoxel, emptyVoxel, emptyVoxel, emptyVoxel);
+  for (size_t i = tid; i < nVoxels / 4; i += stride) v4[i] = ev;
+  for (size_t i = tid; i < (size_t)nLocal; i += stride) vbaAllocList[i] = (int)i;
+  for (size_t i = tid; i < (size_t)nEntries; i += stride) store_entry(table, (int)i, 0, 0, 0, 0, -2);
+  for (size_t i = tid; i < (size_t)nExcess; i += stride) excessAllocList[i] = (int)i;
+}
+
+}  // namespace
+
+namespace itm {
+
+int alloc_step_bound(const SceneParams &sp) {
+  // noSteps = ceil(2 * |segment| / blockSize); |segment| = 2*mu up to rounding
+  const float len = 2.0f * sp.mu / (sp.voxelSize * (float)ITM_BLOCK_SIZE);
+  return (int)ceilf(2.0f * len * 1.01f) + 2;
+}
+
+void launch_reset_scene(void *voxels, int *vbaAllocList, void *table, int *excessAllocList, const SceneParams &sp, cudaStream_t s) {
+  // ITMVoxel_s(): sdf = 32767, w_depth = 0 (ITMLibDefines.h:175-178)
+  const uint32_t emptyVoxel = 0x00007FFFu;
+  k_reset_scene<<<148 * 8, 256, 0, s>>>(reinterpret_cast<uint32_t *>(voxels), (size_t)sp.nLocal * ITM_BLOCK_SIZE3, vbaAllocList, sp.nLocal,
+                                       reinterpret_cast<HashEntry *>(table), sp.nEntries, excessAllocList, sp.nExcess, emptyVoxel);
+}
+
+void launch_allocate(const AllocArgs &a, cudaStream_t s) {
+  const float oneOverVoxelSize = 1.0f / (a.sp.voxelSize * ITM_BLOCK_SIZE);
+  const int stepBound = alloc_step_bound(a.sp);
+  HashEntry *table = reinterpret_cast<HashEntry *>(a.hashTable);
+  k_mark_prev_visible<<<64, 256, 0, s>>>(a.visibleIds, a.visType, a.st);
+  dim3 g((a.vp.W + 31) / 32, (a.vp.H + 7) / 8);
+  k_alloc_pixels<<<g, 256, 0, s>>>(a.depth, table, a.visType, a.allocKey, a.st, a.vp, a.sp, oneOverVoxelSize, stepBound);
+  const int numTiles = (a.sp.nEntries + 1023) / 1024;
+  k_alloc_scan<<<numTiles, 256, 0, s>>>(a.allocKey, table, a.visType, a.vbaAllocList, a.excessAllocList, a.depth, a.st, a.vp, a.sp,
+                                        oneOverVoxelSize, stepBound, a.onlyUpdateVisibleList ? 0 : 1, a.scanTickets, a.allocTileState, numTiles);
+  k_visible_scan<<<numTiles, 256, 0, s>>>(a.visType, table, a.visibleIds, a.st, a.vp, a.sp, a.visibleCapacity, a.scanTickets + 1,
+                                          a.visTileState, numTiles);
+}
+
+}  // namespace itm

@@ -1,0 +1,147 @@
+// View building: raw short depth -> float metres, and the tracker's depth pyramid.
+//
+// Replaces:
+//   convertDepthAffineToFloat   ITMLib/Engine/DeviceAgnostic/ITMViewBuilder.h:22-28
+//   filterSubsampleWithHoles    ITMLib/Engine/DeviceAgnostic/ITMLowLevelEngine.h:26-47
+//   ITMDepthTracker::PrepareForEvaluation   ITMLib/Engine/ITMDepthTracker.cpp:62-75
+//
+// B200 design: the reference launches one kernel for the conversion and one per
+// pyramid level (5 launches, each re-reading the previous level from memory).
+// Here one CTA owns a 32x32 tile of the full-resolution image, converts it, and
+// reduces it through shared memory to 16x16, 8x8, 4x4 and 2x2 - the raw frame is
+// read once (2 B/px) and every level written once, in a single launch.
+#include "itm_common.cuh"
+#include "kernels.h"
+
+namespace {
+
+__device__ __forceinline__ float convert_affine(short d, float a, float b) {
+  return ((d <= 0) || (d > 32000)) ? -1.0f : (float)d * a + b;
+}
+
+// mean of the >0 entries of a 2x2 quad, accumulation order (0,0) (1,0) (0,1) (1,1)
+__device__ __forceinline__ float subsample4(float p00, float p10, float p01, float p11) {
+  float out = 0.0f, n = 0.0f;
+  if (p00 > 0.0f) { out += p00; n++; }
+  if (p10 > 0.0f) { out += p10; n++; }
+  if (p01 > 0.0f) { out += p01; n++; }
+  if (p11 > 0.0f) { out += p11; n++; }
+  if (n > 0) out /= n;
+  return out;
+}
+
+struct PyramidArgs {
+  float *level[ITM_MAX_LEVELS];  // level[0] = full resolution
+  int w[ITM_MAX_LEVELS], h[ITM_MAX_LEVELS];
+  int nLevels;                   // <= 5 handled by the fused kernel
+};
+
+// One CTA (256 threads) per 32x32 full-res tile.  raw may be NULL (then level 0 is
+// taken as already converted and only the pyramid is built).
+__global__ void __launch_bounds__(256) k_convert_pyramid(const short *__restrict__ raw, float a, float b, PyramidArgs args) {
+  __shared__ float s0[32][33];
+  __shared__ float s1[16][17];
+  __shared__ float s2[8][9];
+  __shared__ float s3[4][5];
+  const int W = args.w[0], H = args.h[0];
+  const int tx0 = blockIdx.x * 32, ty0 = blockIdx.y * 32;
+  const int tid = threadIdx.x;
+  float *__restrict__ out0 = args.level[0];
+
+  // level 0: 4 pixels per thread, rows coalesced
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int lx = tid & 31, ly = (tid >> 5) + 8 * k;
+    const int x = tx0 + lx, y = ty0 + ly;
+    float v = 0.0f;
+    if (x < W && y < H) {
+      if (raw) {
+        v = convert_affine(__ldg(raw + x + y * W), a, b);
+        out0[x + y * W] = v;
+      } else {
+        v = out0[x + y * W];
+      }
+    }
+    s0[ly][lx] = v;
+  }
+  __syncthreads();
+  if (args.nLevels > 1) {
+    const int lx = tid & 15, ly = tid >> 4;
+    const float v = subsample4(s0[2 * ly][2 * lx], s0[2 * ly][2 * lx + 1], s0[2 * ly + 1][2 * lx], s0[2 * ly + 1][2 * lx + 1]);
+    s1[ly][lx] = v;
+    const int x = (tx0 >> 1) + lx, y = (ty0 >> 1) + ly;
+    if (x < args.w[1] && y < args.h[1]) args.level[1][x + y * args.w[1]] = v;
+  }
+  __syncthreads();
+  if (args.nLevels > 2 && tid < 64) {
+    const int lx = tid & 7, ly = tid >> 3;
+    const float v = subsample4(s1[2 * ly][2 * lx], s1[2 * ly][2 * lx + 1], s1[2 * ly + 1][2 * lx], s1[2 * ly + 1][2 * lx + 1]);
+    s2[ly][lx] = v;
+    const int x = (tx0 >> 2) + lx, y = (ty0 >> 2) + ly;
+    if (x < args.w[2] && y < args.h[2]) args.level[2][x + y * args.w[2]] = v;
+  }
+  __syncthreads();
+  if (args.nLevels > 3 && tid < 16) {
+    const int lx = tid & 3, ly = tid >> 2;
+    const float v = subsample4(s2[2 * ly][2 * lx], s2[2 * ly][2 * lx + 1], s2[2 * ly + 1][2 * lx], s2[2 * ly + 1][2 * lx + 1]);
+    s3[ly][lx] = v;
+    const int x = (tx0 >> 3) + lx, y = (ty0 >> 3) + ly;
+    if (x < args.w[3] && y < args.h[3]) args.level[3][x + y * args.w[3]] = v;
+  }
+  __syncthreads();
+  if (args.nLevels > 4 && tid < 4) {
+    const int lx = tid & 1, ly = tid >> 1;
+    const float v = subsample4(s3[2 * ly][2 * lx], s3[2 * ly][2 * lx + 1], s3[2 * ly + 1][2 * lx], s3[2 * ly + 1][2 * lx + 1]);
+    const int x = (tx0 >> 4) + lx, y = (ty0 >> 4) + ly;
+    if (x < args.w[4] && y < args.h[4]) args.level[4][x + y * args.w[4]] = v;
+  }
+}
+
+// stand-alone pieces for the stage-level C ABI
+__global__ void k_convert_only(const short *__restrict__ raw, float *__restrict__ out, int n, float a, float b) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = convert_affine(__ldg(raw + i), a, b);
+}
+
+__global__ void k_subsample_holes(float *__restrict__ out, const float *__restrict__ in, int wOut, int hOut, int wIn) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= wOut || y >= hOut) return;
+  const float *p = in + 2 * x + 2 * y * wIn;
+  out[x + y * wOut] = subsample4(__ldg(p), __ldg(p + 1), __ldg(p + wIn), __ldg(p + wIn + 1));
+}
+
+}  // namespace
+
+namespace itm {
+
+void launch_convert_depth(const short *raw, float *out, int n, float a, float b, cudaStream_t s) {
+  k_convert_only<<<(n + 255) / 256, 256, 0, s>>>(raw, out, n, a, b);
+}
+
+void launch_subsample_holes(float *out, const float *in, int wIn, int hIn, cudaStream_t s) {
+  const int wOut = wIn / 2, hOut = hIn / 2;
+  dim3 b(32, 8), g((wOut + 31) / 32, (hOut + 7) / 8);
+  k_subsample_holes<<<g, b, 0, s>>>(out, in, wOut, hOut, wIn);
+}
+
+// Fused conversion + pyramid.  levels[0] is the full-resolution float depth; levels 1.. are
+// the tracker's view hierarchy.  Falls back to per-level launches above 5 levels or when a
+// level's children would straddle tiles (never for even dims >= level count).
+void launch_view_pyramid(const short *raw, float a, float b, float *const *levels, int W, int H, int nLevels, cudaStream_t s) {
+  PyramidArgs args;
+  int w = W, h = H;
+  for (int l = 0; l < ITM_MAX_LEVELS; ++l) {
+    args.level[l] = l < nLevels ? levels[l] : nullptr;
+    args.w[l] = w;
+    args.h[l] = h;
+    w /= 2;
+    h /= 2;
+  }
+  const int fused = nLevels < 5 ? nLevels : 5;
+  args.nLevels = fused;
+  dim3 g((W + 31) / 32, (H + 31) / 32);
+  k_convert_pyramid<<<g, 256, 0, s>>>(raw, a, b, args);
+  for (int l = fused; l < nLevels; ++l) launch_subsample_holes(levels[l], levels[l - 1], args.w[l - 1], args.h[l - 1], s);
+}
+
+}  // namespace itm

@@ -1,0 +1,143 @@
+"""Host-side mirror of the reference's engine interface for the fusion hot path.
+
+Class and method names follow ITMLib so that parity tests read like the reference's own call
+sites (ITMLib/Engine/ITMMainEngine.cpp:111-127):
+
+    ITMMainEngine.ProcessFrame(rgb, rawDepth)
+    ITMMainEngine.GetTrackingState() -> pose_d
+
+Everything here forwards to the C ABI in libitm_b200.so; no arithmetic of the path is done in
+Python and there is no fallback when the library or the GPU is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+HASH_ENTRY_DTYPE = np.dtype(
+    {"names": ["pos", "offset", "ptr"], "formats": [("<i2", 3), "<i4", "<i4"], "offsets": [0, 8, 12], "itemsize": 16}
+)
+
+_BUF_DTYPES = {
+    capi.BUF_VOXELS: np.uint32, capi.BUF_HASH: HASH_ENTRY_DTYPE, capi.BUF_VBA_ALLOC_LIST: np.int32,
+    capi.BUF_EXCESS_ALLOC_LIST: np.int32, capi.BUF_VISIBLE_IDS: np.int32, capi.BUF_VISIBLE_TYPES: np.uint8,
+    capi.BUF_DEPTH: np.float32, capi.BUF_MINMAX: np.float32, capi.BUF_RAYCAST_RESULT: np.float32,
+    capi.BUF_RAYCAST_IMAGE: np.uint8, capi.BUF_POINTS: np.float32, capi.BUF_NORMALS: np.float32,
+    capi.BUF_RAW_DEPTH: np.int16, capi.BUF_PYRAMID_1: np.float32, capi.BUF_PYRAMID_2: np.float32,
+    capi.BUF_PYRAMID_3: np.float32, capi.BUF_PYRAMID_4: np.float32,
+}
+
+
+def _f32p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _i32p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+class ITMMainEngine:
+    """ITMLib/Engine/ITMMainEngine.h:50-130 - owns scene, tracking state, render state and view (all in HBM)."""
+
+    def __init__(self, params: capi.Params | None = None, width: int = 640, height: int = 480):
+        self.lib = capi.load()
+        self.params = params if params is not None else capi.default_params(width, height)
+        self.W, self.H = self.params.width, self.params.height
+        h = C.c_void_p()
+        capi.check(self.lib.itm_b200_engine_create(C.byref(self.params), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.itm_b200_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- ITMMainEngine API ---------------------------------------------------------------
+    def ProcessFrame(self, rgbImage, rawDepthImage):
+        """ITMMainEngine::ProcessFrame (ITMMainEngine.cpp:111).  rgbImage may be None; rawDepthImage is an
+        int16 host array (or a pinned torch tensor / raw address).  Returns pose_d->GetM() (column-major 16)."""
+        pose = np.zeros(16, dtype=np.float32)
+        capi.check(self.lib.itm_b200_engine_process_frame(self.h, _addr(rgbImage), _addr(rawDepthImage), _f32p(pose)))
+        return pose
+
+    def EnqueueFrameDevice(self, raw_depth_dev_ptr: int):
+        capi.check(self.lib.itm_b200_engine_enqueue_frame_dev(self.h, C.c_void_p(raw_depth_dev_ptr)))
+
+    def Sync(self):
+        pose = np.zeros(16, dtype=np.float32)
+        counters = np.zeros(6, dtype=np.int32)
+        capi.check(self.lib.itm_b200_engine_sync(self.h, _f32p(pose), _i32p(counters)))
+        return pose, counters
+
+    def ResetScene(self):
+        capi.check(self.lib.itm_b200_engine_reset(self.h))
+
+    # ---- stage-level access for teacher-forced parity tests ----------------------------------
+    def UploadDepth(self, rawDepthImage):
+        capi.check(self.lib.itm_b200_engine_upload_depth(self.h, _addr(rawDepthImage)))
+
+    def RunStage(self, stage: int):
+        capi.check(self.lib.itm_b200_engine_run_stage(self.h, stage))
+
+    def buffer_info(self, which):
+        p, n = C.c_void_p(), C.c_size_t()
+        capi.check(self.lib.itm_b200_engine_get_buffer(self.h, which, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def read(self, which, count=None):
+        _, nbytes = self.buffer_info(which)
+        dt = np.dtype(_BUF_DTYPES[which])
+        n = nbytes // dt.itemsize if count is None else count
+        out = np.empty(n, dtype=dt)
+        capi.check(self.lib.itm_b200_engine_read_buffer(self.h, which, out.ctypes.data, n * dt.itemsize, 0))
+        return out
+
+    def write(self, which, arr):
+        a = np.ascontiguousarray(arr)
+        capi.check(self.lib.itm_b200_engine_write_buffer(self.h, which, a.ctypes.data, a.nbytes, 0))
+
+    def read_image(self, which, channels=1):
+        a = self.read(which)
+        return a.reshape(self.H, self.W, channels) if channels > 1 else a.reshape(self.H, self.W)
+
+    def get_state(self):
+        pose, pc, st = np.zeros(16, np.float32), np.zeros(16, np.float32), np.zeros(6, np.int32)
+        capi.check(self.lib.itm_b200_engine_get_state(self.h, _f32p(pose), _f32p(pc), _i32p(st)))
+        return pose, pc, st
+
+    def set_state(self, pose_d=None, pose_point_cloud=None, state6=None):
+        p = None if pose_d is None else np.ascontiguousarray(pose_d, np.float32).reshape(16)
+        q = None if pose_point_cloud is None else np.ascontiguousarray(pose_point_cloud, np.float32).reshape(16)
+        s = None if state6 is None else np.ascontiguousarray(state6, np.int32).reshape(6)
+        capi.check(self.lib.itm_b200_engine_set_state(
+            self.h, None if p is None else _f32p(p), None if q is None else _f32p(q), None if s is None else _i32p(s)))
+
+    def set_profiling(self, on=True):
+        capi.check(self.lib.itm_b200_engine_set_profiling(self.h, int(on)))
+
+    def stage_times(self):
+        ms = np.zeros(8, np.float32)
+        capi.check(self.lib.itm_b200_engine_stage_times(self.h, _f32p(ms)))
+        return ms
+
+
+def _addr(x):
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return C.c_void_p(x)
+    if isinstance(x, np.ndarray):
+        assert x.flags["C_CONTIGUOUS"]
+        return C.c_void_p(x.ctypes.data)
+    if hasattr(x, "data_ptr"):  # torch tensor (pinned host memory)
+        return C.c_void_p(x.data_ptr())
+    raise TypeError(type(x))

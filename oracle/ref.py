@@ -1,0 +1,307 @@
+"""ctypes view of oracle/_ref/libitm_ref*.so (the REAL reference CPU engines).
+
+TEST INFRASTRUCTURE.  Only tests/, __graft_entry__.smoke() and bench.py's CPU
+legs may import this module; the product (infinitam_b200/) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_DIR = os.path.join(HERE, "_ref")
+
+_f32p = C.POINTER(C.c_float)
+_i32p = C.POINTER(C.c_int)
+
+HASH_ENTRY_DTYPE = np.dtype(
+    {"names": ["pos", "offset", "ptr"], "formats": [("<i2", 3), "<i4", "<i4"], "offsets": [0, 8, 12], "itemsize": 16}
+)
+VOXEL_S_DTYPE = np.dtype({"names": ["sdf", "w_depth"], "formats": ["<i2", "u1"], "offsets": [0, 2], "itemsize": 4})
+
+
+def lib_path(flavour: str = "parity") -> str:
+    name = {"parity": "libitm_ref.so", "fast": "libitm_ref_fast.so", "fast1": "libitm_ref_fast1.so"}[flavour]
+    return os.path.join(REF_DIR, name)
+
+
+def available(flavour: str = "parity") -> bool:
+    return os.path.exists(lib_path(flavour))
+
+
+_libs = {}
+
+
+def load(flavour: str = "parity"):
+    if flavour in _libs:
+        return _libs[flavour]
+    lib = C.CDLL(lib_path(flavour))
+    lib.ref_const.restype = C.c_int
+    lib.ref_const.argtypes = [C.c_char_p]
+    lib.ref_create.restype = C.c_void_p
+    lib.ref_create.argtypes = [C.c_int, C.c_int] + [C.c_float] * 6 + [C.c_int, C.c_float, C.c_float]
+    for name in ("ref_destroy", "ref_track", "ref_integrate", "ref_expected_depths", "ref_icp_maps", "ref_prepare",
+                 "ref_icp_prepare"):
+        getattr(lib, name).restype = None
+        getattr(lib, name).argtypes = [C.c_void_p]
+    lib.ref_update_view.argtypes = [C.c_void_p, C.c_void_p]
+    lib.ref_update_view.restype = None
+    lib.ref_process_frame.argtypes = [C.c_void_p, C.c_void_p]
+    lib.ref_process_frame.restype = None
+    lib.ref_process_frame_timed.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
+    lib.ref_process_frame_timed.restype = None
+    lib.ref_allocate.argtypes = [C.c_void_p, C.c_int]
+    lib.ref_allocate.restype = None
+    lib.ref_icp_gandh.argtypes = [C.c_void_p, C.c_int, _f32p, _f32p]
+    lib.ref_icp_gandh.restype = C.c_int
+    lib.ref_pyramid_level.argtypes = [C.c_void_p, C.c_int, C.POINTER(_f32p), _i32p, _i32p, _f32p]
+    lib.ref_icp_config.argtypes = [C.c_void_p, _i32p, _i32p, _f32p, _i32p]
+    for name in ("ref_get_pose", "ref_set_pose", "ref_get_pose_pointcloud", "ref_set_pose_pointcloud",
+                 "ref_get_pose_params"):
+        getattr(lib, name).argtypes = [C.c_void_p, _f32p]
+        getattr(lib, name).restype = None
+    lib.ref_get_age.argtypes = [C.c_void_p]
+    lib.ref_get_age.restype = C.c_int
+    lib.ref_set_age.argtypes = [C.c_void_p, C.c_int]
+    lib.ref_mat_inv.argtypes = [_f32p, _f32p]
+    lib.ref_pose_from_invm_coerced.argtypes = [_f32p, _f32p, _f32p, _f32p]
+    lib.ref_pose_from_params.argtypes = [_f32p, _f32p]
+    lib.ref_compute_delta.argtypes = [C.c_void_p, _f32p, _f32p, C.c_int, _f32p]
+    for name in ("ref_hash_entries", "ref_voxels", "ref_vba_alloc_list", "ref_excess_alloc_list", "ref_visible_ids",
+                 "ref_visible_types", "ref_depth", "ref_minmax", "ref_raycast_result", "ref_raycast_image",
+                 "ref_points", "ref_normals"):
+        getattr(lib, name).argtypes = [C.c_void_p]
+        getattr(lib, name).restype = C.c_void_p
+    lib.ref_get_counters.argtypes = [C.c_void_p, _i32p]
+    lib.ref_set_counters.argtypes = [C.c_void_p, _i32p]
+    _libs[flavour] = lib
+    return lib
+
+
+def _fp(a):
+    return a.ctypes.data_as(_f32p)
+
+
+def _view(ptr, dtype, count):
+    dtype = np.dtype(dtype)
+    buf = (C.c_char * (count * dtype.itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=count)
+
+
+class RefEngine:
+    """The reference CPU engines composed like ITMMainEngine (ITMLib/Engine/ITMMainEngine.cpp:17-127)."""
+
+    def __init__(self, width=640, height=480, intr=None, voxel_size=0.005, mu=0.02, max_w=100, vf_min=0.35,
+                 vf_max=3.0, flavour="parity"):
+        from infinitam_b200 import synth  # numpy-only helper
+
+        self.lib = load(flavour)
+        self.W, self.H = width, height
+        self.intr = tuple(float(x) for x in (intr or synth.intrinsics_for(width, height)))
+        self.voxel_size, self.mu, self.max_w, self.vf_min, self.vf_max = voxel_size, mu, max_w, vf_min, vf_max
+        self.h = self.lib.ref_create(width, height, *self.intr, voxel_size, mu, max_w, vf_min, vf_max)
+        c = self.const
+        self.n_local = c("SDF_LOCAL_BLOCK_NUM")
+        self.n_bucket = c("SDF_BUCKET_NUM")
+        self.n_excess = c("SDF_EXCESS_LIST_SIZE")
+        self.n_entries = self.n_bucket + self.n_excess
+
+    def const(self, name):
+        return self.lib.ref_const(name.encode())
+
+    def close(self):
+        if self.h:
+            self.lib.ref_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- stages -------------------------------------------------------------
+    def update_view(self, depth_i16):
+        d = np.ascontiguousarray(depth_i16, dtype=np.int16)
+        self.lib.ref_update_view(self.h, d.ctypes.data)
+
+    def track(self):
+        self.lib.ref_track(self.h)
+
+    def allocate(self, only_visible=False):
+        self.lib.ref_allocate(self.h, int(only_visible))
+
+    def integrate(self):
+        self.lib.ref_integrate(self.h)
+
+    def expected_depths(self):
+        self.lib.ref_expected_depths(self.h)
+
+    def icp_maps(self):
+        self.lib.ref_icp_maps(self.h)
+
+    def process_frame(self, depth_i16):
+        d = np.ascontiguousarray(depth_i16, dtype=np.int16)
+        self.lib.ref_process_frame(self.h, d.ctypes.data)
+
+    def process_frame_timed(self, depth_i16):
+        d = np.ascontiguousarray(depth_i16, dtype=np.int16)
+        ms = (C.c_double * 6)()
+        self.lib.ref_process_frame_timed(self.h, d.ctypes.data, ms)
+        return list(ms)
+
+    # ---- ICP ----------------------------------------------------------------
+    def icp_prepare(self):
+        self.lib.ref_icp_prepare(self.h)
+
+    def icp_gandh(self, level, approx_inv_pose16):
+        inv = np.ascontiguousarray(approx_inv_pose16, dtype=np.float32).reshape(16)
+        out = np.zeros(44, dtype=np.float32)
+        n = self.lib.ref_icp_gandh(self.h, level, _fp(inv), _fp(out))
+        return n, out
+
+    def pyramid_level(self, level):
+        p = _f32p()
+        w, h = C.c_int(), C.c_int()
+        intr = np.zeros(4, dtype=np.float32)
+        self.lib.ref_pyramid_level(self.h, level, C.byref(p), C.byref(w), C.byref(h), _fp(intr))
+        arr = np.ctypeslib.as_array(p, shape=(h.value, w.value))
+        return arr, intr
+
+    def icp_config(self):
+        n = C.c_int()
+        iters = np.zeros(8, dtype=np.int32)
+        thr = np.zeros(8, dtype=np.float32)
+        typ = np.zeros(8, dtype=np.int32)
+        self.lib.ref_icp_config(self.h, C.byref(n), iters.ctypes.data_as(_i32p), _fp(thr), typ.ctypes.data_as(_i32p))
+        k = n.value
+        return k, iters[:k].copy(), thr[:k].copy(), typ[:k].copy()
+
+    # ---- pose ---------------------------------------------------------------
+    def _get16(self, fn):
+        m = np.zeros(16, dtype=np.float32)
+        fn(self.h, _fp(m))
+        return m
+
+    @property
+    def pose_M(self):
+        """column-major 16 floats (ORUtils/Matrix.h:8-33)"""
+        return self._get16(self.lib.ref_get_pose)
+
+    @pose_M.setter
+    def pose_M(self, m):
+        m = np.ascontiguousarray(m, dtype=np.float32).reshape(16)
+        self.lib.ref_set_pose(self.h, _fp(m))
+
+    @property
+    def pose_pointcloud_M(self):
+        return self._get16(self.lib.ref_get_pose_pointcloud)
+
+    @pose_pointcloud_M.setter
+    def pose_pointcloud_M(self, m):
+        m = np.ascontiguousarray(m, dtype=np.float32).reshape(16)
+        self.lib.ref_set_pose_pointcloud(self.h, _fp(m))
+
+    @property
+    def pose_params(self):
+        p = np.zeros(6, dtype=np.float32)
+        self.lib.ref_get_pose_params(self.h, _fp(p))
+        return p
+
+    @property
+    def age(self):
+        return self.lib.ref_get_age(self.h)
+
+    @age.setter
+    def age(self, a):
+        self.lib.ref_set_age(self.h, int(a))
+
+    def mat_inv(self, m16):
+        a = np.ascontiguousarray(m16, dtype=np.float32).reshape(16)
+        o = np.zeros(16, dtype=np.float32)
+        self.lib.ref_mat_inv(_fp(a), _fp(o))
+        return o
+
+    def pose_from_invm_coerced(self, inv16):
+        a = np.ascontiguousarray(inv16, dtype=np.float32).reshape(16)
+        M, inv, p = np.zeros(16, np.float32), np.zeros(16, np.float32), np.zeros(6, np.float32)
+        self.lib.ref_pose_from_invm_coerced(_fp(a), _fp(M), _fp(inv), _fp(p))
+        return M, inv, p
+
+    def compute_delta(self, nabla6, hess36, short_iteration):
+        n = np.ascontiguousarray(nabla6, dtype=np.float32).reshape(6)
+        h = np.ascontiguousarray(hess36, dtype=np.float32).reshape(36)
+        s = np.zeros(6, np.float32)
+        self.lib.ref_compute_delta(self.h, _fp(n), _fp(h), int(short_iteration), _fp(s))
+        return s
+
+    # ---- raw state (numpy views onto the reference's own buffers) -------------
+    @property
+    def hash_entries(self):
+        return _view(self.lib.ref_hash_entries(self.h), HASH_ENTRY_DTYPE, self.n_entries)
+
+    @property
+    def voxels(self):
+        """raw uint32 view, one word per ITMVoxel_s (sdf | w_depth<<16 | pad<<24)"""
+        assert self.const("sizeof_voxel") == 4
+        return _view(self.lib.ref_voxels(self.h), np.uint32, self.n_local * 512)
+
+    @property
+    def vba_alloc_list(self):
+        return _view(self.lib.ref_vba_alloc_list(self.h), np.int32, self.n_local)
+
+    @property
+    def excess_alloc_list(self):
+        return _view(self.lib.ref_excess_alloc_list(self.h), np.int32, self.n_excess)
+
+    @property
+    def visible_ids(self):
+        return _view(self.lib.ref_visible_ids(self.h), np.int32, self.n_local)
+
+    @property
+    def visible_types(self):
+        return _view(self.lib.ref_visible_types(self.h), np.uint8, self.n_entries)
+
+    @property
+    def counters(self):
+        c = np.zeros(3, dtype=np.int32)
+        self.lib.ref_get_counters(self.h, c.ctypes.data_as(_i32p))
+        return c
+
+    @counters.setter
+    def counters(self, c):
+        c = np.ascontiguousarray(c, dtype=np.int32)
+        self.lib.ref_set_counters(self.h, c.ctypes.data_as(_i32p))
+
+    def _img(self, fn, dtype, ch):
+        p = fn(self.h)
+        if not p:
+            return None
+        a = _view(p, dtype, self.W * self.H * ch)
+        return a.reshape(self.H, self.W, ch) if ch > 1 else a.reshape(self.H, self.W)
+
+    @property
+    def depth(self):
+        return self._img(self.lib.ref_depth, np.float32, 1)
+
+    @property
+    def minmax(self):
+        return self._img(self.lib.ref_minmax, np.float32, 2)
+
+    @property
+    def raycast_result(self):
+        return self._img(self.lib.ref_raycast_result, np.float32, 4)
+
+    @property
+    def raycast_image(self):
+        return self._img(self.lib.ref_raycast_image, np.uint8, 4)
+
+    @property
+    def points(self):
+        return self._img(self.lib.ref_points, np.float32, 4)
+
+    @property
+    def normals(self):
+        return self._img(self.lib.ref_normals, np.float32, 4)
