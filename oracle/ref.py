@@ -34,14 +34,32 @@ def available(flavour: str = "parity") -> bool:
 _libs = {}
 
 
+class _Prefixed:
+    """view of a CDLL whose exported functions are named <prefix>_xxx, exposed as ref_xxx"""
+
+    def __init__(self, lib, prefix):
+        self._lib, self._prefix = lib, prefix
+
+    def __getattr__(self, name):
+        if name.startswith("ref_"):
+            return getattr(self._lib, self._prefix + name[3:])
+        return getattr(self._lib, name)
+
+
 def load(flavour: str = "parity"):
     if flavour in _libs:
         return _libs[flavour]
-    lib = C.CDLL(lib_path(flavour))
+    lib = _Prefixed(C.CDLL(lib_path(flavour)), "ref")
     lib.ref_const.restype = C.c_int
     lib.ref_const.argtypes = [C.c_char_p]
     lib.ref_create.restype = C.c_void_p
     lib.ref_create.argtypes = [C.c_int, C.c_int] + [C.c_float] * 6 + [C.c_int, C.c_float, C.c_float]
+    declare_common(lib)
+    _libs[flavour] = lib
+    return lib
+
+
+def declare_common(lib):
     for name in ("ref_destroy", "ref_track", "ref_integrate", "ref_expected_depths", "ref_icp_maps", "ref_prepare",
                  "ref_icp_prepare"):
         getattr(lib, name).restype = None
@@ -76,7 +94,6 @@ def load(flavour: str = "parity"):
         getattr(lib, name).restype = C.c_void_p
     lib.ref_get_counters.argtypes = [C.c_void_p, _i32p]
     lib.ref_set_counters.argtypes = [C.c_void_p, _i32p]
-    _libs[flavour] = lib
     return lib
 
 
@@ -97,16 +114,19 @@ class RefEngine:
                  vf_max=3.0, flavour="parity"):
         from infinitam_b200 import synth  # numpy-only helper
 
-        self.lib = load(flavour)
         self.W, self.H = width, height
         self.intr = tuple(float(x) for x in (intr or synth.intrinsics_for(width, height)))
         self.voxel_size, self.mu, self.max_w, self.vf_min, self.vf_max = voxel_size, mu, max_w, vf_min, vf_max
-        self.h = self.lib.ref_create(width, height, *self.intr, voxel_size, mu, max_w, vf_min, vf_max)
+        self._create(flavour)
+        self.n_entries = self.n_bucket + self.n_excess
+
+    def _create(self, flavour):
+        self.lib = load(flavour)
+        self.h = self.lib.ref_create(self.W, self.H, *self.intr, self.voxel_size, self.mu, self.max_w, self.vf_min, self.vf_max)
         c = self.const
         self.n_local = c("SDF_LOCAL_BLOCK_NUM")
         self.n_bucket = c("SDF_BUCKET_NUM")
         self.n_excess = c("SDF_EXCESS_LIST_SIZE")
-        self.n_entries = self.n_bucket + self.n_excess
 
     def const(self, name):
         return self.lib.ref_const(name.encode())
@@ -245,7 +265,6 @@ class RefEngine:
     @property
     def voxels(self):
         """raw uint32 view, one word per ITMVoxel_s (sdf | w_depth<<16 | pad<<24)"""
-        assert self.const("sizeof_voxel") == 4
         return _view(self.lib.ref_voxels(self.h), np.uint32, self.n_local * 512)
 
     @property

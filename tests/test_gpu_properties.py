@@ -1,0 +1,101 @@
+"""-m gpu: size-independent properties of the CUDA path at the full BASELINE size (640x480), plus edge cases."""
+import numpy as np
+import pytest
+
+import parity
+from infinitam_b200 import capi, synth
+from infinitam_b200.engines import ITMMainEngine
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+
+
+def _snapshot(eng):
+    pose, pc, st = eng.get_state()
+    return (pose.copy(), st.copy(), eng.read(capi.BUF_HASH).tobytes(), eng.read(capi.BUF_VOXELS).tobytes(),
+            eng.read(capi.BUF_VISIBLE_IDS)[: st[0]].tobytes(), eng.read(capi.BUF_POINTS).tobytes())
+
+
+def test_run_to_run_bitwise_determinism():
+    """two engines, same 8 frames -> identical pose, hash table, voxels, visible list, ICP maps (ordered allocation and
+    fixed-order reductions: no atomics-order dependence anywhere)"""
+    seq = synth.sequence(8, 640, 480)
+    snaps = []
+    for _ in range(2):
+        eng = ITMMainEngine(width=640, height=480)
+        for k in range(8):
+            eng.ProcessFrame(None, seq[k])
+        snaps.append(_snapshot(eng))
+        eng.close()
+    a, b = snaps
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert a[2] == b[2] and a[3] == b[3] and a[4] == b[4] and a[5] == b[5]
+
+
+def test_allocation_is_idempotent_and_weights_count_frames():
+    """re-allocating from the same depth and pose allocates nothing new; integrating the same frame n times makes every
+    touched voxel's weight n (until maxW) and leaves its sdf where one observation put it"""
+    seq = synth.sequence(1, 640, 480)
+    eng = ITMMainEngine(width=640, height=480)
+    eng.UploadDepth(seq[0])
+    eng.RunStage(capi.STAGE_VIEW)
+    eng.RunStage(capi.STAGE_ALLOCATE)
+    _, _, st1 = eng.get_state()
+    h1 = eng.read(capi.BUF_HASH).tobytes()
+    eng.RunStage(capi.STAGE_ALLOCATE)
+    _, _, st2 = eng.get_state()
+    assert list(st1[:3]) == list(st2[:3]) and eng.read(capi.BUF_HASH).tobytes() == h1
+    eng.RunStage(capi.STAGE_INTEGRATE)
+    v1 = eng.read(capi.BUF_VOXELS)
+    for _ in range(3):
+        eng.RunStage(capi.STAGE_INTEGRATE)
+    v4 = eng.read(capi.BUF_VOXELS)
+    w1, w4 = (v1 >> 16) & 0xFF, (v4 >> 16) & 0xFF
+    touched = w1 > 0
+    assert touched.sum() > 1_000_000
+    assert np.array_equal(w4[touched], 4 * w1[touched]) and not w4[~touched].any()
+    s1 = (v1 & 0xFFFF).astype(np.uint16).view(np.int16).astype(np.int32)
+    s4 = (v4 & 0xFFFF).astype(np.uint16).view(np.int16).astype(np.int32)
+    assert np.abs(s1 - s4)[touched].max() <= 3  # running mean of identical samples; only truncation noise
+    eng.close()
+
+
+def test_empty_and_invalid_depth_frames():
+    """all-zero depth (no valid pixel) and out-of-frustum depth allocate nothing and leave the scene untouched"""
+    o = port.PortEngine(320, 240)
+    eng = parity.make_cuda_engine(o)
+    zero = np.zeros((240, 320), np.int16)
+    far = np.full((240, 320), 3500, np.int16)  # beyond viewFrustum_max - mu
+    neg = np.full((240, 320), -5, np.int16)
+    for k, d in enumerate((zero, far, neg)):
+        r = parity.compare_frame(o, eng, d, k, strict=True)
+        assert r["counters_ref"][0] == 0
+    # and a normal frame afterwards still works
+    parity.compare_frame(o, eng, synth.sequence(1, 320, 240)[0], 3, strict=True)
+    eng.close(); o.close()
+
+
+def test_ragged_image_sizes():
+    """sizes that are not multiples of the tile sizes (32x32 view tiles, 16x16 raycast tiles, odd pyramid halves)"""
+    for (w, h) in ((200, 152), (176, 144)):
+        o = port.PortEngine(w, h)
+        eng = parity.make_cuda_engine(o)
+        seq = synth.sequence(3, w, h)
+        for k in range(3):
+            parity.compare_frame(o, eng, seq[k], k, strict=True)
+        eng.close(); o.close()
+
+
+def test_long_free_running_sequence_stays_close_to_reference():
+    """30 frames without teacher forcing: the trajectories may drift apart (ICP is chaotic in its rounding) but must stay
+    within 2 mm / 2 mrad, and both must stay near the ground truth"""
+    seq = synth.sequence(30, 320, 240)
+    o = port.PortEngine(320, 240)
+    eng = parity.make_cuda_engine(o)
+    rows = parity.compare_free_running(o, eng, seq)
+    assert max(r["rot"] for r in rows) < 2e-3 and max(r["trans"] for r in rows) < 2e-3
+    gt = synth.ground_truth_pose(29)
+    pose, _, _ = eng.get_state()
+    M = pose.reshape(4, 4).T
+    assert np.abs(M[:3, 3] - gt[:3, 3]).max() < 0.03
+    eng.close(); o.close()

@@ -1,0 +1,121 @@
+"""CPU (-m "not gpu"): pins the oracle.
+
+1. the C restatement (oracle/itm_oracle.c) against the golden vectors generated from the real reference;
+2. when oracle/_ref/libitm_ref.so exists (built from /root/reference in the dev container), the restatement against the
+   real reference engines, stage by stage, bit for bit.
+"""
+import numpy as np
+import pytest
+
+import golden_check
+from infinitam_b200 import synth
+from oracle import port, ref
+
+
+def _state(e):
+    return dict(pose=e.pose_M, counters=e.counters, hash_entries=e.hash_entries, visible_ids=e.visible_ids, voxels_u32=e.voxels,
+                minmax=e.minmax, raycast=e.raycast_result, points=e.points, normals=e.normals, image=e.raycast_image,
+                visible_types=e.visible_types, depth=e.depth)
+
+
+def test_port_reproduces_golden_vectors():
+    g = golden_check.load()
+    seq = golden_check.golden_sequence(g)
+    e = port.PortEngine(int(g["W"]), int(g["H"]))
+    for k in range(int(g["N"])):
+        e.update_view(seq[k])
+        if k == 1:
+            e.icp_prepare()
+            inv = e.mat_inv(e.pose_M)
+            for lvl in range(5):
+                _, o = e.icp_gandh(lvl, inv)
+                assert np.array_equal(o, g["f1_gandh_l%d" % lvl]), "ComputeGandH level %d differs from golden" % lvl
+        e.track()
+        e.allocate()
+        e.integrate()
+        e.expected_depths()
+        e.icp_maps()
+        golden_check.check_frame(g, k, **_state(e))
+    e.close()
+
+
+def _eq_engines(a, b, what=""):
+    ha, hb = a.hash_entries, b.hash_entries
+    assert np.array_equal(ha["pos"], hb["pos"]) and np.array_equal(ha["ptr"], hb["ptr"]) and np.array_equal(ha["offset"], hb["offset"]), what + " hash"
+    assert np.array_equal(a.counters, b.counters), what + " counters"
+    assert np.array_equal(a.visible_ids[: a.counters[0]], b.visible_ids[: b.counters[0]]), what + " visible ids"
+    assert np.array_equal(a.visible_types, b.visible_types), what + " visible types"
+    assert np.array_equal(a.voxels & 0x00FFFFFF, b.voxels & 0x00FFFFFF), what + " voxels"
+    assert np.array_equal(a.pose_M, b.pose_M), what + " pose"
+
+
+@pytest.mark.parametrize("size,voxel,noise", [((320, 240), 0.005, True), ((160, 120), 0.0025, False)])
+def test_port_matches_real_reference_stage_by_stage(size, voxel, noise):
+    if not ref.available("parity"):
+        pytest.skip("oracle/_ref/libitm_ref.so not present (needs /root/reference to build)")
+    W, H = size
+    a = ref.RefEngine(W, H, voxel_size=voxel)
+    b = port.PortEngine(W, H, voxel_size=voxel)
+    seq = synth.sequence(4, W, H, noise=noise)
+    for k in range(4):
+        a.update_view(seq[k]); b.update_view(seq[k])
+        assert np.array_equal(a.depth, b.depth)
+        a.icp_prepare(); b.icp_prepare()
+        for lvl in range(1, 5):
+            assert np.array_equal(a.pyramid_level(lvl)[0], b.pyramid_level(lvl)[0]), "pyramid level %d" % lvl
+            assert np.array_equal(a.pyramid_level(lvl)[1], b.pyramid_level(lvl)[1])
+        if k > 0:
+            inv = a.mat_inv(a.pose_M)
+            assert np.array_equal(inv, b.mat_inv(b.pose_M))
+            for lvl in range(5):
+                na, oa = a.icp_gandh(lvl, inv)
+                nb, ob = b.icp_gandh(lvl, inv)
+                assert na == nb and np.array_equal(oa, ob), "ComputeGandH level %d" % lvl
+        a.track(); b.track()
+        assert np.array_equal(a.pose_M, b.pose_M) and np.array_equal(a.pose_params, b.pose_params), "frame %d pose" % k
+        a.allocate(); b.allocate()
+        _eq_engines(a, b, "frame %d after allocate:" % k)
+        a.integrate(); b.integrate()
+        _eq_engines(a, b, "frame %d after integrate:" % k)
+        a.expected_depths(); b.expected_depths()
+        assert np.array_equal(a.minmax, b.minmax)
+        a.icp_maps(); b.icp_maps()
+        assert np.array_equal(a.raycast_result, b.raycast_result)
+        assert np.array_equal(a.points, b.points) and np.array_equal(a.normals, b.normals)
+        assert np.array_equal(a.raycast_image, b.raycast_image)
+        assert np.array_equal(a.pose_pointcloud_M, b.pose_pointcloud_M) and a.age == b.age
+    a.close(); b.close()
+
+
+def test_icp_config_matches_reference_constructor():
+    """ITMDepthTracker constructor: iterations {2,4,6,8,10}, distThresh 0.002 .. 0.01 (ITMDepthTracker.cpp:19-28)"""
+    b = port.PortEngine(64, 48)
+    n, iters, thr, typ = b.icp_config()
+    assert n == 5 and list(iters) == [2, 4, 6, 8, 10] and list(typ) == [3, 3, 1, 1, 1]
+    if ref.available("parity"):
+        a = ref.RefEngine(64, 48)
+        n2, iters2, thr2, typ2 = a.icp_config()
+        assert n2 == n and np.array_equal(iters, iters2) and np.array_equal(thr, thr2) and np.array_equal(typ, typ2)
+        a.close()
+    b.close()
+
+
+def test_pose_math_matches_reference():
+    rng = np.random.default_rng(7)
+    if not ref.available("parity"):
+        pytest.skip("needs oracle/_ref")
+    a = ref.RefEngine(64, 48)
+    b = port.PortEngine(64, 48)
+    for _ in range(200):
+        p = np.concatenate([rng.normal(0, 0.3, 3), rng.normal(0, 0.4, 3)]).astype(np.float32)
+        M = np.zeros(16, np.float32)
+        a.lib.ref_pose_from_params(p.ctypes.data_as(ref._f32p), M.ctypes.data_as(ref._f32p))
+        M2 = np.zeros(16, np.float32)
+        b.lib.ref_pose_from_params(p.ctypes.data_as(ref._f32p), M2.ctypes.data_as(ref._f32p))
+        assert np.array_equal(M, M2)
+        inv = a.mat_inv(M)
+        assert np.array_equal(inv, b.mat_inv(M))
+        ra, rb = a.pose_from_invm_coerced(inv), b.pose_from_invm_coerced(inv)
+        for x, y in zip(ra, rb):
+            assert np.array_equal(x, y)
+    a.close(); b.close()
