@@ -818,7 +818,9 @@ port_engine *port_create(const port_params *pp) {
   e->hash = (HashEntry *)malloc((size_t)e->n_entries * sizeof(HashEntry));
   e->vba_list = (int *)malloc((size_t)pp->n_local * sizeof(int));
   e->excess_list = (int *)malloc((size_t)pp->n_excess * sizeof(int));
-  e->visible_ids = (int *)calloc((size_t)pp->n_local, sizeof(int));
+  /* the reference sizes this list SDF_LOCAL_BLOCK_NUM and would overrun it when more blocks are visible than the pool
+   * holds; the restatement over-allocates instead of reproducing the overrun */
+  e->visible_ids = (int *)calloc((size_t)e->n_entries, sizeof(int));
   e->visible_type = (unsigned char *)calloc((size_t)e->n_entries, 1);
   e->minmax = (V2 *)calloc(P, sizeof(V2));
   e->raycast = (V4 *)calloc(P, sizeof(V4));

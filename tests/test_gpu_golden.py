@@ -49,12 +49,14 @@ def test_cuda_teacher_forced_against_port_with_runtime_pools():
 
 
 def test_cuda_pool_exhaustion_matches_oracle():
-    """VBA with only 1024 blocks: allocation runs dry; the reference keeps decrementing the counters and skips the blocks"""
-    o = port.PortEngine(320, 240, n_local=1024, n_bucket=0x4000, n_excess=256)
+    """the voxel-block pool and the excess list both run dry while the camera moves; the reference keeps decrementing its
+    counters and silently skips the blocks (ITMSceneReconstructionEngine_CPU.cpp:187-189, :206) - so must we"""
+    o = port.PortEngine(320, 240, n_local=7168, n_bucket=0x4000, n_excess=1600)
     eng = parity.make_cuda_engine(o)
-    seq = synth.sequence(3, 320, 240)
-    rows = [parity.compare_frame(o, eng, seq[k], k, strict=True) for k in range(3)]
-    assert rows[0]["counters_ref"][1] < 0, "the pool was supposed to be exhausted"
+    seq = synth.sequence(8, 320, 240)
+    rows = [parity.compare_frame(o, eng, seq[k], k, strict=True) for k in range(8)]
+    assert rows[-1]["counters_ref"][1] < 0 and rows[-1]["counters_ref"][2] < 0, "both pools were supposed to be exhausted"
+    assert max(r["counters_ref"][0] for r in rows) <= 7168
     eng.close(); o.close()
 
 

@@ -39,8 +39,15 @@ def test_allocation_is_idempotent_and_weights_count_frames():
     eng = ITMMainEngine(width=640, height=480)
     eng.UploadDepth(seq[0])
     eng.RunStage(capi.STAGE_VIEW)
-    eng.RunStage(capi.STAGE_ALLOCATE)
-    _, _, st1 = eng.get_state()
+    # blocks that lose a same-frame collision (two new blocks wanting the same bucket / chain tail) are allocated by the
+    # next pass (ITMSceneReconstructionEngine.h:232-235), so it takes a few passes to reach the fixed point
+    prev = None
+    for _ in range(8):
+        eng.RunStage(capi.STAGE_ALLOCATE)
+        _, _, st1 = eng.get_state()
+        if prev is not None and list(prev[:3]) == list(st1[:3]):
+            break
+        prev = st1.copy()
     h1 = eng.read(capi.BUF_HASH).tobytes()
     eng.RunStage(capi.STAGE_ALLOCATE)
     _, _, st2 = eng.get_state()
@@ -61,17 +68,24 @@ def test_allocation_is_idempotent_and_weights_count_frames():
 
 
 def test_empty_and_invalid_depth_frames():
-    """all-zero depth (no valid pixel) and out-of-frustum depth allocate nothing and leave the scene untouched"""
-    o = port.PortEngine(320, 240)
-    eng = parity.make_cuda_engine(o)
+    """all-zero depth (no valid pixel), out-of-frustum depth and negative raw values allocate nothing and leave the scene
+    untouched; every stage still matches the oracle"""
     zero = np.zeros((240, 320), np.int16)
     far = np.full((240, 320), 3500, np.int16)  # beyond viewFrustum_max - mu
     neg = np.full((240, 320), -5, np.int16)
-    for k, d in enumerate((zero, far, neg)):
-        r = parity.compare_frame(o, eng, d, k, strict=True)
+    for d in (zero, far, neg):
+        o = port.PortEngine(320, 240)
+        eng = parity.make_cuda_engine(o)
+        r = parity.compare_frame(o, eng, d, 0, strict=True)
         assert r["counters_ref"][0] == 0
-    # and a normal frame afterwards still works
-    parity.compare_frame(o, eng, synth.sequence(1, 320, 240)[0], 3, strict=True)
+        eng.close(); o.close()
+    # a frame with a large hole in it, followed by normal tracking
+    o = port.PortEngine(320, 240)
+    eng = parity.make_cuda_engine(o)
+    seq = synth.sequence(3, 320, 240).copy()
+    seq[:, 60:180, 100:220] = 0
+    for k in range(3):
+        parity.compare_frame(o, eng, seq[k], k, strict=True)
     eng.close(); o.close()
 
 
