@@ -59,6 +59,7 @@ struct itm_b200_ctx {
   unsigned long long *visTileState = nullptr;
   double *icpPartials = nullptr;
   unsigned *icpCounter = nullptr;
+  unsigned *icpBarrier = nullptr;  // [0] arrivals, [1] generation
   float *icpOut = nullptr;     // 44 floats
   float *icpPoseIn = nullptr;  // 16 floats
   FrameState *st = nullptr;    // device
@@ -144,6 +145,8 @@ int ctx_alloc(itm_b200_ctx *c, void *stream) {
   CU(cudaMalloc(&c->icpPartials, (size_t)icp_max_ctas() * 32 * sizeof(double)));
   CU(cudaMalloc(&c->icpCounter, sizeof(unsigned)));
   CU(cudaMemsetAsync(c->icpCounter, 0, sizeof(unsigned), c->stream));
+  CU(cudaMalloc(&c->icpBarrier, 2 * sizeof(unsigned)));
+  CU(cudaMemsetAsync(c->icpBarrier, 0, 2 * sizeof(unsigned), c->stream));
   CU(cudaMalloc(&c->icpOut, 44 * sizeof(float)));
   CU(cudaMalloc(&c->icpPoseIn, 16 * sizeof(float)));
   CU(cudaMalloc(&c->st, sizeof(FrameState)));
@@ -166,6 +169,7 @@ void ctx_free(itm_b200_ctx *c) {
   cudaFree(c->visTileState);
   cudaFree(c->icpPartials);
   cudaFree(c->icpCounter);
+  cudaFree(c->icpBarrier);
   cudaFree(c->icpOut);
   cudaFree(c->icpPoseIn);
   cudaFree(c->st);
@@ -254,16 +258,15 @@ void enqueue_track(itm_b200_ctx *c, const float *depth0, const float *points, co
   a.partials = c->icpPartials;
   a.ctaCounter = c->icpCounter;
   a.terminationThreshold = c->p.depth_tracker_termination_threshold;
-  launch_icp_begin_frame(c->st, s);
-  g_launches += 1;
-  for (int l = c->nLevels - 1; l >= c->p.no_icp_run_till_level; --l) {
-    if (c->levels[l].iterationType == ITM_ITER_NONE) continue;
-    const IcpLevelArgs lv = make_level_args(c, l, l == 0 ? depth0 : c->pyramid[l]);
-    for (int it = 0; it < c->levels[l].noIterations; ++it) {
-      launch_icp_eval(a, lv, it == 0, 0, nullptr, nullptr, s);
-      g_launches += 1;
-    }
+  IcpLevelArgs lv[ITM_MAX_LEVELS];
+  int iters[ITM_MAX_LEVELS];
+  for (int l = 0; l < c->nLevels; ++l) {
+    lv[l] = make_level_args(c, l, l == 0 ? depth0 : c->pyramid[l]);
+    iters[l] = c->levels[l].noIterations;
   }
+  const cudaError_t e = launch_icp_track(a, lv, iters, c->nLevels, c->p.no_icp_run_till_level, c->icpBarrier, s);
+  if (e != cudaSuccess) g_lastError = std::string("cooperative launch of the ICP tracker failed: ") + cudaGetErrorString(e);
+  g_launches += 1;
 }
 
 }  // namespace
@@ -492,7 +495,7 @@ int itm_b200_compute_g_and_h(itm_b200_ctx *c, const float *level_depth_dev, int 
   lv.fx = view_intrinsics[0]; lv.fy = view_intrinsics[1]; lv.cx = view_intrinsics[2]; lv.cy = view_intrinsics[3];
   lv.distThresh = dist_thresh;
   lv.iterationType = iteration_type;
-  launch_icp_eval(a, lv, 1, 1, c->icpOut, c->icpPoseIn, c->stream);
+  launch_icp_eval_single(a, lv, c->icpOut, c->icpPoseIn, c->stream);
   g_launches += 1;
   float out[44];
   CU(cudaMemcpyAsync(out, c->icpOut, sizeof(out), cudaMemcpyDeviceToHost, c->stream));

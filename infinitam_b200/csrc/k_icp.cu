@@ -6,16 +6,18 @@
 //   computePerPointGH_Depth(_Ab)          ITMLib/Engine/DeviceAgnostic/ITMDepthTracker.h:9-105
 //   interpolateBilinear_withHoles         ITMLib/Engine/DeviceAgnostic/ITMPixelUtils.h:41-71
 //
-// B200 design.  The reference CUDA tracker does memset + kernel + blocking 29-word D2H copy +
-// host Cholesky for each of up to 30 evaluations per frame.  Here one launch per evaluation
-// does everything on the device:
-//   * each thread accumulates its pixels' (count, b^2, b*A, A*A^T) in registers (fp32),
-//   * warps reduce with shuffles, the CTA combines its warps in fp64 and writes one 30-value
-//     partial, then takes a ticket;
-//   * the last CTA to finish sums the partials in CTA order (fp64, bit-reproducible run to
-//     run) and runs the accept/reject + Cholesky + SE(3) update of the LM loop (pose_math.cuh)
-//     on the pose kept in FrameState, including the early-exit flag of HasConverged().
-// So a whole TrackCamera is <= 30 back-to-back launches with no host involvement.
+// B200 design.  The reference CUDA tracker does memset + kernel + blocking 29-word D2H copy + host
+// Cholesky for each of up to 30 evaluations per frame; most of a frame at kHz rates is those round
+// trips.  Here the WHOLE TrackCamera is one persistent, cooperatively launched kernel:
+//   * the grid (<= 2 CTAs per SM, all co-resident) walks the pyramid levels and LM iterations itself;
+//   * per evaluation each thread accumulates its pixels' (count, b^2, b*A, A*A^T) in fp32 registers,
+//     warps reduce with shuffles, the CTA combines its warps in fp64 and writes one 32-value partial;
+//   * CTAs then meet at a grid barrier built from one atomic counter + a generation word.  The LAST
+//     CTA to arrive sums the partials in CTA order (fp64: bit-reproducible run to run), runs the
+//     accept/reject + Cholesky + SE(3) update of the LM loop (pose_math.cuh, everything in registers)
+//     on the pose kept in FrameState, and releases the barrier; the others spin on the generation.
+//   * HasConverged() simply ends the level's loop - nothing is launched for skipped iterations.
+// k_icp_eval_single is the stand-alone evaluation behind the stage-level ComputeGandH entry point.
 #include "itm_common.cuh"
 #include "kernels.h"
 #include "pose_math.cuh"
@@ -95,95 +97,23 @@ __device__ __forceinline__ bool per_point_Ab(float *A, float &b, int x, int y, f
   return true;
 }
 
-// The LM bookkeeping of one iteration, ITMDepthTracker.cpp:167-197.  Run by one thread.
-__device__ void lm_update(FrameState *st, const float *sums /*[0]=n [1]=sumF [2..7]=nabla [8..28]=hessian lower tri*/, int noPara,
-                          int iterationType, bool firstIterOfLevel, float terminationThreshold) {
-  IcpState &s = st->icp;
-  if (firstIterOfLevel) {
-    // approxInvPose = pose_d->GetInvM(); lastKnownGoodPose(*pose_d); f_old = 1e20f; lambda = 1.0  (:161-165)
-    mat4_inv(st->M_d, s.approxInvPose);
-    for (int i = 0; i < 16; ++i) s.lastGoodM[i] = st->M_d[i];
-    for (int i = 0; i < 6; ++i) s.lastGoodParams[i] = st->poseParams[i];
-    s.fOld = 1e20f;
-    s.lambda = 1.0f;
-    s.levelDone = 0;
-  }
-  const int noValid = (int)sums[0];
-  const float fNew = (noValid > 100) ? sqrtf(sums[1]) / (float)noValid : 1e5f;
-  float hessianNew[36], nablaNew[6];
-  for (int i = 0; i < 36; ++i) hessianNew[i] = 0.0f;
-  for (int i = 0; i < 6; ++i) nablaNew[i] = 0.0f;
-  for (int r = 0, counter = 0; r < noPara; r++)
-    for (int c = 0; c <= r; c++, counter++) hessianNew[r + c * 6] = sums[8 + counter];
-  for (int r = 0; r < noPara; ++r)
-    for (int c = r + 1; c < noPara; c++) hessianNew[r + c * 6] = hessianNew[c + r * 6];
-  for (int r = 0; r < noPara; ++r) nablaNew[r] = sums[2 + r];
-  s.lastNoValid = noValid;
-  s.lastF = fNew;
-  s.evalCount++;
-
-  float approxInvPose[16];
-  if ((noValid <= 0) || (fNew > s.fOld)) {
-    // revert
-    for (int i = 0; i < 16; ++i) st->M_d[i] = s.lastGoodM[i];
-    for (int i = 0; i < 6; ++i) st->poseParams[i] = s.lastGoodParams[i];
-    mat4_inv(st->M_d, approxInvPose);
-    s.lambda *= 10.0f;
-  } else {
-    for (int i = 0; i < 16; ++i) { s.lastGoodM[i] = st->M_d[i]; approxInvPose[i] = s.approxInvPose[i]; }
-    for (int i = 0; i < 6; ++i) s.lastGoodParams[i] = st->poseParams[i];
-    s.fOld = fNew;
-    for (int i = 0; i < 36; ++i) s.hessianGood[i] = hessianNew[i] / (float)noValid;
-    for (int i = 0; i < 6; ++i) s.nablaGood[i] = nablaNew[i] / (float)noValid;
-    s.lambda /= 10.0f;
-  }
-  float A[36];
-  for (int i = 0; i < 36; ++i) A[i] = s.hessianGood[i];
-  for (int i = 0; i < 6; ++i) A[i + i * 6] *= 1.0f + s.lambda;
-  float step[6];
-  icp_compute_delta(step, s.nablaGood, A, iterationType != ITM_ITER_BOTH);
-  icp_apply_delta(approxInvPose, step, iterationType, approxInvPose);
-  pose_set_invM_coerce(approxInvPose, st->M_d, st->poseParams);
-  mat4_inv(st->M_d, s.approxInvPose);
-  for (int i = 0; i < 16; ++i) st->invM_d[i] = s.approxInvPose[i];
-  if (icp_has_converged(step, terminationThreshold)) s.levelDone = 1;
-}
-
-// mode 0: tracking fast path (LM update on device).  mode 1: evaluate at the pose given in
-// out44[0..15] (approxInvPose, device memory) and leave [n, f, nabla6, hessian36] in out44.
+// Sums this CTA's share of one evaluation and writes it to partialOut[0..NV).  All threads take part.
+// Layout of a partial: [n, sum b^2, nabla(noPara), hessian lower triangle(noParaSQ)].
 template <bool shortIteration, bool rotationOnly>
-__global__ void __launch_bounds__(ICP_THREADS) k_icp_eval(IcpArgs a, IcpLevelArgs lv, int firstIterOfLevel, int mode,
-                                                          float *__restrict__ out44, const float *__restrict__ poseIn) {
+__device__ __forceinline__ void eval_to_partial(const IcpLevelArgs &lv, const ViewParams &sv, const IcpConsts &c,
+                                                const float4 *__restrict__ pointsMap, const float4 *__restrict__ normalsMap,
+                                                double (*sPart)[ICP_NVALS], double *__restrict__ partialOut, int nCtas) {
   constexpr int noPara = shortIteration ? 3 : 6;
   constexpr int noParaSQ = shortIteration ? 6 : 21;
   constexpr int NV = 2 + noPara + noParaSQ;
-  __shared__ IcpConsts c;
-  __shared__ double sPart[ICP_THREADS / 32][ICP_NVALS];
-  __shared__ bool sIsLast;
-  FrameState *st = a.st;
-  if (mode == 0 && !firstIterOfLevel && st->icp.levelDone) return;  // HasConverged() broke out of this level
-  if (threadIdx.x == 0) {
-    if (mode == 1) {
-      for (int i = 0; i < 16; ++i) c.approxInvPose[i] = poseIn[i];
-    } else if (firstIterOfLevel) {
-      mat4_inv(st->M_d, c.approxInvPose);  // approxInvPose = pose_d->GetInvM()  (:161)
-    } else {
-      for (int i = 0; i < 16; ++i) c.approxInvPose[i] = st->icp.approxInvPose[i];
-    }
-  }
-  if (threadIdx.x >= 32 && threadIdx.x < 48) c.scenePose[threadIdx.x - 32] = st->scenePose[threadIdx.x - 32];
-  __syncthreads();
-
   float acc[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) acc[i] = 0.0f;
-  const float4 *pointsMap = reinterpret_cast<const float4 *>(a.pointsMap);
-  const float4 *normalsMap = reinterpret_cast<const float4 *>(a.normalsMap);
   const int n = lv.w * lv.h;
-  for (int i = blockIdx.x * ICP_THREADS + threadIdx.x; i < n; i += gridDim.x * ICP_THREADS) {
+  for (int i = blockIdx.x * ICP_THREADS + threadIdx.x; i < n; i += nCtas * ICP_THREADS) {
     const int y = i / lv.w, x = i - y * lv.w;
     float A[noPara], b;
-    if (per_point_Ab<shortIteration, rotationOnly>(A, b, x, y, __ldg(lv.depth + i), lv, a.sceneVp, c, pointsMap, normalsMap)) {
+    if (per_point_Ab<shortIteration, rotationOnly>(A, b, x, y, __ldg(lv.depth + i), lv, sv, c, pointsMap, normalsMap)) {
       acc[0] += 1.0f;
       acc[1] += b * b;
 #pragma unroll
@@ -194,7 +124,6 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_eval(IcpArgs a, IcpLevelArg
       }
     }
   }
-  // warp reduce (fp32), CTA reduce (fp64)
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     float v = acc[i];
@@ -208,62 +137,261 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_eval(IcpArgs a, IcpLevelArg
     for (int i = 0; i < NV; ++i) sPart[warp][i] = (double)acc[i];
   }
   __syncthreads();
-  if (threadIdx.x < NV) {
+  if (threadIdx.x < ICP_NVALS) {
     double s = 0.0;
+    if (threadIdx.x < NV) {
 #pragma unroll
-    for (int w = 0; w < ICP_THREADS / 32; ++w) s += sPart[w][threadIdx.x];
-    a.partials[(size_t)blockIdx.x * ICP_NVALS + threadIdx.x] = s;
+      for (int w = 0; w < ICP_THREADS / 32; ++w) s += sPart[w][threadIdx.x];
+    }
+    partialOut[threadIdx.x] = s;
   }
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned t = atomicAdd(a.ctaCounter, 1u);
-    sIsLast = (t == gridDim.x - 1);
+  __syncthreads();  // sPart is reused by the caller
+}
+
+// Sum of the first nRows CTA partials (fp64) by the 8 warps of one CTA; result (float) in sSums[0..32).
+// Lane = value index, warp w owns a contiguous chunk of rows; loads are issued 8 deep so the chain of L2
+// round trips stays short.  The summation order is fixed (rows ascending inside a chunk, chunks ascending),
+// hence bit-reproducible run to run.
+__device__ __forceinline__ void reduce_partials(const double *__restrict__ partials, int nRows, double (*sPart)[ICP_NVALS], float *sSums) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int chunk = (nRows + 7) >> 3;
+  const int r0 = warp * chunk, r1 = min(nRows, r0 + chunk);
+  double s = 0.0;
+  int r = r0;
+  for (; r + 8 <= r1; r += 8) {
+    double v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = __ldcg(partials + (size_t)(r + k) * ICP_NVALS + lane);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += v[k];
   }
+  for (; r < r1; ++r) s += __ldcg(partials + (size_t)r * ICP_NVALS + lane);
+  sPart[warp][lane] = s;
   __syncthreads();
-  if (!sIsLast) return;
-  __threadfence();
-  __shared__ float sSums[ICP_NVALS];
-  if (threadIdx.x < NV) {
-    double s = 0.0;
-    for (unsigned cta = 0; cta < gridDim.x; ++cta) s += __ldcg(a.partials + (size_t)cta * ICP_NVALS + threadIdx.x);
-    sSums[threadIdx.x] = (float)s;
+  if (threadIdx.x < ICP_NVALS) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < ICP_THREADS / 32; ++w) t += sPart[w][threadIdx.x];
+    sSums[threadIdx.x] = (float)t;
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    *a.ctaCounter = 0;
-    // unpack to the common layout [n, sumF, nabla(6), hessian lower triangle(21)]
-    float sums[2 + 6 + 21];
-    for (int i = 0; i < 29; ++i) sums[i] = 0.0f;
-    sums[0] = sSums[0];
-    sums[1] = sSums[1];
-    for (int r = 0; r < noPara; ++r) sums[2 + r] = sSums[2 + r];
-    for (int i = 0; i < noParaSQ; ++i) sums[8 + i] = sSums[2 + noPara + i];
-    if (mode == 0) {
-      lm_update(st, sums, noPara, lv.iterationType, firstIterOfLevel != 0, a.terminationThreshold);
+}
+
+// The LM bookkeeping of one iteration, ITMDepthTracker.cpp:167-197.  Run by one thread; noPara is a template
+// parameter so that every array index is static and the 6x6 system lives in registers.
+template <int noPara>
+__device__ void lm_update(FrameState *st, const float *sSums, int iterationType, bool firstIterOfLevel, float terminationThreshold) {
+  IcpState &s = st->icp;
+  float M_d[16], params[6], approxInvPose[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) M_d[i] = st->M_d[i];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) params[i] = st->poseParams[i];
+  float fOld = s.fOld, lambda = s.lambda;
+  if (firstIterOfLevel) {
+    // lastKnownGoodPose(*pose_d); f_old = 1e20f; lambda = 1.0  (:162-165)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s.lastGoodM[i] = M_d[i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) s.lastGoodParams[i] = params[i];
+    fOld = 1e20f;
+    lambda = 1.0f;
+  }
+  const int noValid = (int)sSums[0];
+  const float fNew = (noValid > 100) ? sqrtf(sSums[1]) / (float)noValid : 1e5f;
+  s.lastNoValid = noValid;
+  s.lastF = fNew;
+  s.evalCount++;
+
+  float Hgood[36], ngood[6];
+  if ((noValid <= 0) || (fNew > fOld)) {
+    // revert to the last known good pose (:173-177)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) M_d[i] = s.lastGoodM[i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) params[i] = s.lastGoodParams[i];
+    mat4_inv(M_d, approxInvPose);
+    lambda *= 10.0f;
+#pragma unroll
+    for (int i = 0; i < 36; ++i) Hgood[i] = s.hessianGood[i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) ngood[i] = s.nablaGood[i];
+  } else {
+    if (firstIterOfLevel) {
+      mat4_inv(M_d, approxInvPose);  // approxInvPose = pose_d->GetInvM()  (:161)
     } else {
-      // ComputeGandH's return values (ITMDepthTracker_CPU.cpp:72-78)
-      const int noValid = (int)sums[0];
-      out44[0] = sums[0];
-      out44[1] = (noValid > 100) ? sqrtf(sums[1]) / (float)noValid : 1e5f;
-      for (int r = 0; r < 6; ++r) out44[2 + r] = r < noPara ? sums[2 + r] : 0.0f;
-      for (int i = 0; i < 36; ++i) out44[8 + i] = 0.0f;
-      for (int r = 0, counter = 0; r < noPara; r++)
-        for (int cc = 0; cc <= r; cc++, counter++) out44[8 + r + cc * 6] = sums[8 + counter];
-      for (int r = 0; r < noPara; ++r)
-        for (int cc = r + 1; cc < noPara; cc++) out44[8 + r + cc * 6] = out44[8 + cc + r * 6];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) approxInvPose[i] = s.approxInvPose[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s.lastGoodM[i] = M_d[i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) s.lastGoodParams[i] = params[i];
+    fOld = fNew;
+    // hessian_good / nabla_good = new / noValidPoints.  Entries outside the noPara block are garbage in
+    // the reference (never read); zero here.
+#pragma unroll
+    for (int i = 0; i < 36; ++i) Hgood[i] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) ngood[i] = 0.0f;
+#pragma unroll
+    for (int r = 0, counter = 0; r < noPara; r++) {
+#pragma unroll
+      for (int c = 0; c <= r; c++, counter++) {
+        const float h = sSums[2 + noPara + counter] / (float)noValid;
+        Hgood[r + c * 6] = h;
+        Hgood[c + r * 6] = h;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < noPara; ++r) ngood[r] = sSums[2 + r] / (float)noValid;
+#pragma unroll
+    for (int i = 0; i < 36; ++i) s.hessianGood[i] = Hgood[i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) s.nablaGood[i] = ngood[i];
+    lambda /= 10.0f;
+  }
+  float A[36];
+#pragma unroll
+  for (int i = 0; i < 36; ++i) A[i] = Hgood[i];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) A[i + i * 6] *= 1.0f + lambda;
+  float step[6];
+  icp_compute_delta(step, ngood, A, noPara == 3);
+  icp_apply_delta(approxInvPose, step, iterationType, approxInvPose);
+  pose_set_invM_coerce(approxInvPose, M_d, params);
+  mat4_inv(M_d, approxInvPose);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    st->M_d[i] = M_d[i];
+    st->invM_d[i] = approxInvPose[i];
+    s.approxInvPose[i] = approxInvPose[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) st->poseParams[i] = params[i];
+  s.fOld = fOld;
+  s.lambda = lambda;
+  s.levelDone = icp_has_converged(step, terminationThreshold) ? 1 : 0;
+}
+
+struct TrackArgs {
+  IcpArgs a;
+  IcpLevelArgs lv[ITM_MAX_LEVELS];
+  int iters[ITM_MAX_LEVELS];
+  int nLevels, noIcpLevel;
+  unsigned *barrier;  // [0] arrival count, [1] generation
+};
+
+// One launch = one TrackCamera.  Must be launched cooperatively (all CTAs co-resident).
+__global__ void __launch_bounds__(ICP_THREADS, 2) k_icp_track(TrackArgs t) {
+  __shared__ IcpConsts c;
+  __shared__ double sPart[ICP_THREADS / 32][ICP_NVALS];
+  __shared__ float sSums[ICP_NVALS];
+  __shared__ int sFlag;  // bit0: this CTA arrived last, bit1: level finished
+  FrameState *st = t.a.st;
+  const float4 *pointsMap = reinterpret_cast<const float4 *>(t.a.pointsMap);
+  const float4 *normalsMap = reinterpret_cast<const float4 *>(t.a.normalsMap);
+  unsigned *bCount = t.barrier, *bGen = t.barrier + 1;
+  const int nCtas = gridDim.x;
+
+  if (threadIdx.x < 16) c.scenePose[threadIdx.x] = st->scenePose[threadIdx.x];
+  if (blockIdx.x == 0 && threadIdx.x == 32) {
+    // hessian_good / nabla_good are uninitialised stack variables in the reference (:151-153); start from zero
+    for (int i = 0; i < 36; ++i) st->icp.hessianGood[i] = 0.0f;
+    for (int i = 0; i < 6; ++i) st->icp.nablaGood[i] = 0.0f;
+    st->icp.evalCount = 0;
+  }
+
+  for (int level = t.nLevels - 1; level >= t.noIcpLevel; --level) {
+    const IcpLevelArgs lv = t.lv[level];
+    const int type = lv.iterationType;
+    if (type == ITM_ITER_NONE) continue;
+    for (int it = 0; it < t.iters[level]; ++it) {
+      // pose to evaluate at: pose_d->GetInvM() on entering a level, the LM loop's approxInvPose afterwards.
+      // Both were written by the previous leader before it released the barrier; read them from L2.
+      if (threadIdx.x < 16) c.approxInvPose[threadIdx.x] = __ldcg((it == 0 ? st->invM_d : st->icp.approxInvPose) + threadIdx.x);
+      __syncthreads();
+      double *myPartial = t.a.partials + (size_t)blockIdx.x * ICP_NVALS;
+      // coarse levels have fewer pixels than the grid has threads: only the first nActive CTAs evaluate
+      const int nActive = min(nCtas, (lv.w * lv.h + ICP_THREADS - 1) / ICP_THREADS);
+      const int NV = (type == ITM_ITER_BOTH) ? 29 : 11;
+      if (blockIdx.x < nActive) {
+        if (type == ITM_ITER_ROTATION) eval_to_partial<true, true>(lv, t.a.sceneVp, c, pointsMap, normalsMap, sPart, myPartial, nActive);
+        else if (type == ITM_ITER_TRANSLATION) eval_to_partial<true, false>(lv, t.a.sceneVp, c, pointsMap, normalsMap, sPart, myPartial, nActive);
+        else eval_to_partial<false, false>(lv, t.a.sceneVp, c, pointsMap, normalsMap, sPart, myPartial, nActive);
+      }
+      // ---- grid barrier; the last CTA to arrive is this iteration's leader
+      __threadfence();
+      __syncthreads();
+      unsigned gen = 0;
+      if (threadIdx.x == 0) {
+        gen = *((volatile unsigned *)bGen);
+        const unsigned prev = atomicAdd(bCount, 1u);
+        sFlag = (prev == (unsigned)nCtas - 1u) ? 1 : 0;
+      }
+      __syncthreads();
+      if (sFlag & 1) {
+        __threadfence();
+        reduce_partials(t.a.partials, nActive, sPart, sSums);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          if (NV == 11) lm_update<3>(st, sSums, type, it == 0, t.a.terminationThreshold);
+          else lm_update<6>(st, sSums, type, it == 0, t.a.terminationThreshold);
+          *bCount = 0;
+          __threadfence();
+          atomicAdd(bGen, 1u);  // release
+        }
+      } else if (threadIdx.x == 0) {
+        while (*((volatile unsigned *)bGen) == gen) { /* spin */ }
+        __threadfence();
+      }
+      __syncthreads();
+      // HasConverged() -> break (:196); every CTA reads the same flag after the barrier
+      if (threadIdx.x == 0) sFlag = __ldcg(&st->icp.levelDone) ? 2 : 0;
+      __syncthreads();
+      const bool done = (sFlag & 2) != 0;
+      __syncthreads();
+      if (done) break;
     }
   }
 }
 
-__global__ void k_icp_begin_frame(FrameState *st) {
-  IcpState &s = st->icp;
-  for (int i = 0; i < 36; ++i) s.hessianGood[i] = 0.0f;
-  for (int i = 0; i < 6; ++i) s.nablaGood[i] = 0.0f;
-  s.levelDone = 0;
-  s.evalCount = 0;
-  s.fOld = 1e10f;
-  s.lambda = 1.0f;
+// Stand-alone evaluation at poseIn (16 floats, device): leaves ComputeGandH's results in out44.
+template <bool shortIteration, bool rotationOnly>
+__global__ void __launch_bounds__(ICP_THREADS) k_icp_eval_single(IcpArgs a, IcpLevelArgs lv, float *__restrict__ out44,
+                                                                 const float *__restrict__ poseIn) {
+  constexpr int noPara = shortIteration ? 3 : 6;
+  __shared__ IcpConsts c;
+  __shared__ double sPart[ICP_THREADS / 32][ICP_NVALS];
+  __shared__ float sSums[ICP_NVALS];
+  __shared__ bool sIsLast;
+  if (threadIdx.x < 16) c.approxInvPose[threadIdx.x] = poseIn[threadIdx.x];
+  if (threadIdx.x >= 32 && threadIdx.x < 48) c.scenePose[threadIdx.x - 32] = a.st->scenePose[threadIdx.x - 32];
+  __syncthreads();
+  eval_to_partial<shortIteration, rotationOnly>(lv, a.sceneVp, c, reinterpret_cast<const float4 *>(a.pointsMap),
+                                                reinterpret_cast<const float4 *>(a.normalsMap), sPart,
+                                                a.partials + (size_t)blockIdx.x * ICP_NVALS, gridDim.x);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) sIsLast = (atomicAdd(a.ctaCounter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!sIsLast) return;
+  __threadfence();
+  reduce_partials(a.partials, gridDim.x, sPart, sSums);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *a.ctaCounter = 0;
+    // ComputeGandH's return values (ITMDepthTracker_CPU.cpp:72-78)
+    const int noValid = (int)sSums[0];
+    out44[0] = sSums[0];
+    out44[1] = (noValid > 100) ? sqrtf(sSums[1]) / (float)noValid : 1e5f;
+    for (int r = 0; r < 6; ++r) out44[2 + r] = r < noPara ? sSums[2 + r] : 0.0f;
+    for (int i = 0; i < 36; ++i) out44[8 + i] = 0.0f;
+    for (int r = 0, counter = 0; r < noPara; r++)
+      for (int cc = 0; cc <= r; cc++, counter++) {
+        out44[8 + r + cc * 6] = sSums[2 + noPara + counter];
+        out44[8 + cc + r * 6] = sSums[2 + noPara + counter];
+      }
+  }
 }
 
 __global__ void k_set_pose(FrameState *st) {
@@ -278,25 +406,58 @@ namespace itm {
 
 int icp_max_ctas() { return 148 * 2; }
 
-void launch_icp_begin_frame(FrameState *st, cudaStream_t s) { k_icp_begin_frame<<<1, 1, 0, s>>>(st); }
-
 void launch_set_pose(FrameState *st, cudaStream_t s) { k_set_pose<<<1, 1, 0, s>>>(st); }
 
-void launch_icp_eval(const IcpArgs &a, const IcpLevelArgs &lv, int firstIterOfLevel, int mode, float *out44, const float *poseIn,
-                     cudaStream_t s) {
+// grid for the persistent tracker: as many CTAs as can be co-resident, capped at 2 per SM
+int icp_track_grid() {
+  static int grid = 0;
+  if (grid) return grid;
+  int dev = 0, sms = 0, perSm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_icp_track, ICP_THREADS, 0);
+  if (perSm > 2) perSm = 2;
+  if (perSm < 1) perSm = 1;
+  grid = sms * perSm;
+  if (grid > icp_max_ctas()) grid = icp_max_ctas();
+  return grid;
+}
+
+cudaError_t launch_icp_track(const IcpArgs &a, const IcpLevelArgs *levels, const int *iters, int nLevels, int noIcpLevel,
+                             unsigned *barrier, cudaStream_t s) {
+  TrackArgs t;
+  t.a = a;
+  for (int l = 0; l < ITM_MAX_LEVELS; ++l) {
+    if (l < nLevels) {
+      t.lv[l] = levels[l];
+      t.iters[l] = iters[l];
+    } else {
+      t.lv[l] = IcpLevelArgs();
+      t.lv[l].iterationType = ITM_ITER_NONE;
+      t.iters[l] = 0;
+    }
+  }
+  t.nLevels = nLevels;
+  t.noIcpLevel = noIcpLevel;
+  t.barrier = barrier;
+  void *args[] = {&t};
+  return cudaLaunchCooperativeKernel((const void *)k_icp_track, dim3(icp_track_grid()), dim3(ICP_THREADS), args, 0, s);
+}
+
+void launch_icp_eval_single(const IcpArgs &a, const IcpLevelArgs &lv, float *out44, const float *poseIn, cudaStream_t s) {
   const int n = lv.w * lv.h;
   int ctas = (n + ICP_THREADS - 1) / ICP_THREADS;
   if (ctas > icp_max_ctas()) ctas = icp_max_ctas();
   if (ctas < 1) ctas = 1;
   switch (lv.iterationType) {
     case ITM_ITER_ROTATION:
-      k_icp_eval<true, true><<<ctas, ICP_THREADS, 0, s>>>(a, lv, firstIterOfLevel, mode, out44, poseIn);
+      k_icp_eval_single<true, true><<<ctas, ICP_THREADS, 0, s>>>(a, lv, out44, poseIn);
       break;
     case ITM_ITER_TRANSLATION:
-      k_icp_eval<true, false><<<ctas, ICP_THREADS, 0, s>>>(a, lv, firstIterOfLevel, mode, out44, poseIn);
+      k_icp_eval_single<true, false><<<ctas, ICP_THREADS, 0, s>>>(a, lv, out44, poseIn);
       break;
     case ITM_ITER_BOTH:
-      k_icp_eval<false, false><<<ctas, ICP_THREADS, 0, s>>>(a, lv, firstIterOfLevel, mode, out44, poseIn);
+      k_icp_eval_single<false, false><<<ctas, ICP_THREADS, 0, s>>>(a, lv, out44, poseIn);
       break;
     default:
       break;

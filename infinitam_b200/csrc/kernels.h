@@ -77,13 +77,14 @@ void launch_convert_depth(const short *raw, float *out, int n, float a, float b,
 void launch_subsample_holes(float *out, const float *in, int wIn, int hIn, cudaStream_t s);
 void launch_view_pyramid(const short *raw, float a, float b, float *const *levels, int W, int H, int nLevels, cudaStream_t s);
 
-// one ICP evaluation.  mode 0: evaluate at the pose kept in FrameState and run the LM update on
-// the device (TrackCamera fast path).  mode 1: evaluate at poseIn (16 floats, device) only and
-// leave [n, f, nabla6, hessian36] in out44 (device) for the stage-level ComputeGandH entry.
-void launch_icp_begin_frame(FrameState *st, cudaStream_t s);
-void launch_icp_eval(const IcpArgs &a, const IcpLevelArgs &lv, int firstIterOfLevel, int mode, float *out44, const float *poseIn,
-                     cudaStream_t s);
+// The whole ITMDepthTracker::TrackCamera LM loop as ONE persistent cooperative kernel (levels[l], iters[l] for
+// l < nLevels; barrier = 2 zero-initialised words of scratch).
+cudaError_t launch_icp_track(const IcpArgs &a, const IcpLevelArgs *levels, const int *iters, int nLevels, int noIcpLevel,
+                             unsigned *barrier, cudaStream_t s);
+// One stand-alone evaluation at poseIn (16 floats, device); [n, f, nabla6, hessian36] left in out44 (device).
+void launch_icp_eval_single(const IcpArgs &a, const IcpLevelArgs &lv, float *out44, const float *poseIn, cudaStream_t s);
 int icp_max_ctas();
+int icp_track_grid();
 
 void launch_set_pose(FrameState *st, cudaStream_t s);  // recompute invM_d from M_d on device
 

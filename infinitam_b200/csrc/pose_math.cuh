@@ -17,6 +17,7 @@
 
 PM_HD bool mat4_inv(const float *m, float *dst) {
   float tmp[12], src[16], det;
+#pragma unroll
   for (int i = 0; i < 4; i++) {
     src[i] = m[i * 4];
     src[i + 4] = m[i * 4 + 1];
@@ -72,15 +73,19 @@ PM_HD bool mat4_inv(const float *m, float *dst) {
   dst[15] = (tmp[10] * src[10] + tmp[4] * src[8] + tmp[9] * src[9]) - (tmp[8] * src[9] + tmp[11] * src[10] + tmp[5] * src[8]);
 
   const float s = 1 / det;
+#pragma unroll
   for (int i = 0; i < 16; ++i) dst[i] *= s;
   return true;
 }
 
 // r = lhs * rhs, column-major; each element accumulated from 0 in k order like the reference
 PM_HD void mat4_mul(const float *lhs, const float *rhs, float *r) {
+#pragma unroll
   for (int x = 0; x < 4; x++)
+#pragma unroll
     for (int y = 0; y < 4; y++) {
       float acc = 0.0f;
+#pragma unroll
       for (int k = 0; k < 4; k++) acc += lhs[y + 4 * k] * rhs[k + 4 * x];
       r[y + 4 * x] = acc;
     }
@@ -149,7 +154,9 @@ PM_HD void pose_params_to_M(const float *p, float *M) {
   a = A * w[0], b = B * (w[1] * w[2]);
   R[1 + 3 * 2] = b - a;
   R[2 + 3 * 1] = b + a;
+#pragma unroll
   for (int c = 0; c < 3; ++c)
+#pragma unroll
     for (int r = 0; r < 3; ++r) M[r + 4 * c] = R[r + 3 * c];
   M[0 + 4 * 3] = T[0];
   M[1 + 4 * 3] = T[1];
@@ -162,7 +169,9 @@ PM_HD void pose_params_to_M(const float *p, float *M) {
 
 PM_HD void pose_M_to_params(const float *M, float *p) {
   float R[9], T[3];
+#pragma unroll
   for (int c = 0; c < 3; ++c)
+#pragma unroll
     for (int r = 0; r < 3; ++r) R[r + 3 * c] = M[r + 4 * c];
   T[0] = M[12];
   T[1] = M[13];
@@ -238,52 +247,68 @@ PM_HD void pose_M_to_params(const float *M, float *p) {
 PM_HD void pose_set_invM_coerce(const float *invM, float *M, float *params) {
   float Mtmp[16];
   mat4_inv(invM, Mtmp);
-  pose_M_to_params(Mtmp, params);  // SetInvM -> SetParamsFromModelView
-  pose_M_to_params(Mtmp, params);  // Coerce: SetParamsFromModelView (same input, same result)
-  pose_params_to_M(params, M);     // Coerce: SetModelViewFromParams
+  // SetInvM -> SetParamsFromModelView, then Coerce: SetParamsFromModelView once more on the same M (a pure
+  // function of M, so one evaluation gives the identical params), then SetModelViewFromParams
+  pose_M_to_params(Mtmp, params);
+  pose_params_to_M(params, M);
 }
 
-// ORUtils::Cholesky constructor + Backsub for size n (3 or 6), row/col conventions as in the reference
-PM_HD void cholesky_solve(const float *mat, int size, const float *v, float *result) {
-  float ch[36];
-  for (int i = 0; i < size * size; i++) ch[i] = mat[i];
-  for (int c = 0; c < size; c++) {
+// ORUtils::Cholesky constructor + Backsub for size N (3 or 6), row/col conventions as in the reference.
+// Templated on the size so that every index is a compile-time constant after unrolling (the arrays then
+// live in registers when this runs on the device).
+template <int N>
+PM_HD void cholesky_solve(const float *mat, const float *v, float *result) {
+  float ch[N * N];
+#pragma unroll
+  for (int i = 0; i < N * N; i++) ch[i] = mat[i];
+#pragma unroll
+  for (int c = 0; c < N; c++) {
     float inv_diag = 1;
-    for (int r = c; r < size; r++) {
-      float val = ch[c + r * size];
-      for (int c2 = 0; c2 < c; c2++) val -= ch[c + c2 * size] * ch[c2 + r * size];
+#pragma unroll
+    for (int r = c; r < N; r++) {
+      float val = ch[c + r * N];
+#pragma unroll
+      for (int c2 = 0; c2 < c; c2++) val -= ch[c + c2 * N] * ch[c2 + r * N];
       if (r == c) {
-        ch[c + r * size] = val;
+        ch[c + r * N] = val;
         inv_diag = 1.0f / val;
       } else {
-        ch[r + c * size] = val;
-        ch[c + r * size] = val * inv_diag;
+        ch[r + c * N] = val;
+        ch[c + r * N] = val * inv_diag;
       }
     }
   }
-  float y[6];
-  for (int i = 0; i < size; i++) {
+  float y[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) {
     float val = v[i];
-    for (int j = 0; j < i; j++) val -= ch[j + i * size] * y[j];
+#pragma unroll
+    for (int j = 0; j < i; j++) val -= ch[j + i * N] * y[j];
     y[i] = val;
   }
-  for (int i = 0; i < size; i++) y[i] /= ch[i + i * size];
-  for (int i = size - 1; i >= 0; i--) {
+#pragma unroll
+  for (int i = 0; i < N; i++) y[i] /= ch[i + i * N];
+#pragma unroll
+  for (int i = N - 1; i >= 0; i--) {
     float val = y[i];
-    for (int j = i + 1; j < size; j++) val -= ch[i + j * size] * result[j];
+#pragma unroll
+    for (int j = i + 1; j < N; j++) val -= ch[i + j * N] * result[j];
     result[i] = val;
   }
 }
 
 PM_HD void icp_compute_delta(float *step, const float *nabla, const float *hessian, bool shortIteration) {
+#pragma unroll
   for (int i = 0; i < 6; i++) step[i] = 0;
   if (shortIteration) {
     float small[9];
+#pragma unroll
     for (int r = 0; r < 3; r++)
+#pragma unroll
       for (int c = 0; c < 3; c++) small[r + c * 3] = hessian[r + c * 6];
-    cholesky_solve(small, 3, nabla, step);
+    cholesky_solve<3>(small, nabla, step);
   } else {
-    cholesky_solve(hessian, 6, nabla, step);
+    cholesky_solve<6>(hessian, nabla, step);
   }
 }
 
@@ -296,6 +321,7 @@ PM_HD void icp_apply_delta(const float *para_old, const float *delta, int iterat
     step[0] = 0.0f; step[1] = 0.0f; step[2] = 0.0f;
     step[3] = delta[0]; step[4] = delta[1]; step[5] = delta[2];
   } else {
+#pragma unroll
     for (int i = 0; i < 6; ++i) step[i] = delta[i];
   }
   float Tinc[16];
@@ -306,11 +332,13 @@ PM_HD void icp_apply_delta(const float *para_old, const float *delta, int iterat
   Tinc[3] = 0.0f;      Tinc[7] = 0.0f;      Tinc[11] = 0.0f;     Tinc[15] = 1.0f;
   float r[16];
   mat4_mul(Tinc, para_old, r);
+#pragma unroll
   for (int i = 0; i < 16; ++i) para_new[i] = r[i];
 }
 
 PM_HD bool icp_has_converged(const float *step, float terminationThreshold) {
   float stepLength = 0.0f;
+#pragma unroll
   for (int i = 0; i < 6; i++) stepLength += step[i] * step[i];
   return sqrtf(stepLength) / 6 < terminationThreshold;
 }
