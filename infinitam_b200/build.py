@@ -16,6 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libitm_b200.so")
 SOURCES = ["engine.cu", "k_view.cu", "k_alloc.cu", "k_integrate.cu", "k_render.cu", "k_icp.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+EXTRA = os.environ.get("ITM_B200_DEFINES", "").split()  # e.g. -DITM_ICP_TRACE for tools/icp_trace.py
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
     "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "-Xptxas", "-v",
@@ -40,7 +41,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         path = os.path.join(CSRC, src)
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
         if force or _stale(obj, [path] + headers):
-            jobs.append(([NVCC] + FLAGS + ["-c", path, "-o", obj], src))
+            jobs.append(([NVCC] + FLAGS + EXTRA + ["-c", path, "-o", obj], src))
 
     def run(job):
         cmd, src = job

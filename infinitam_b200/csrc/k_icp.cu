@@ -176,56 +176,59 @@ __device__ __forceinline__ void reduce_partials(const double *__restrict__ parti
   }
 }
 
+// Levenberg-Marquardt state of one TrackCamera call; lives in the master CTA's shared memory.
+struct LmShared {
+  float M_d[16], params[6];           // trackingState->pose_d
+  float approxInvPose[16];
+  float lastGoodM[16], lastGoodParams[6];
+  float Hgood[36], ngood[6];
+  float fOld, lambda;
+  int evalCount;
+};
+
 // The LM bookkeeping of one iteration, ITMDepthTracker.cpp:167-197.  Run by one thread; noPara is a template
-// parameter so that every array index is static and the 6x6 system lives in registers.
+// parameter so that every array index is static and the 6x6 system lives in registers.  Returns HasConverged().
 template <int noPara>
-__device__ void lm_update(FrameState *st, const float *sSums, int iterationType, bool firstIterOfLevel, float terminationThreshold) {
-  IcpState &s = st->icp;
+__device__ bool lm_update(LmShared &L, const float *sSums, int iterationType, bool firstIterOfLevel, float terminationThreshold) {
   float M_d[16], params[6], approxInvPose[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) M_d[i] = st->M_d[i];
+  for (int i = 0; i < 16; ++i) M_d[i] = L.M_d[i];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) params[i] = st->poseParams[i];
-  float fOld = s.fOld, lambda = s.lambda;
+  for (int i = 0; i < 6; ++i) params[i] = L.params[i];
+  float fOld = L.fOld, lambda = L.lambda;
   if (firstIterOfLevel) {
-    // lastKnownGoodPose(*pose_d); f_old = 1e20f; lambda = 1.0  (:162-165)
+    // approxInvPose = pose_d->GetInvM(); lastKnownGoodPose(*pose_d); f_old = 1e20f; lambda = 1.0  (:161-165)
 #pragma unroll
-    for (int i = 0; i < 16; ++i) s.lastGoodM[i] = M_d[i];
+    for (int i = 0; i < 16; ++i) L.lastGoodM[i] = M_d[i];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) s.lastGoodParams[i] = params[i];
+    for (int i = 0; i < 6; ++i) L.lastGoodParams[i] = params[i];
     fOld = 1e20f;
     lambda = 1.0f;
   }
   const int noValid = (int)sSums[0];
   const float fNew = (noValid > 100) ? sqrtf(sSums[1]) / (float)noValid : 1e5f;
-  s.lastNoValid = noValid;
-  s.lastF = fNew;
-  s.evalCount++;
+  L.evalCount++;
 
   float Hgood[36], ngood[6];
   if ((noValid <= 0) || (fNew > fOld)) {
     // revert to the last known good pose (:173-177)
 #pragma unroll
-    for (int i = 0; i < 16; ++i) M_d[i] = s.lastGoodM[i];
+    for (int i = 0; i < 16; ++i) M_d[i] = L.lastGoodM[i];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) params[i] = s.lastGoodParams[i];
+    for (int i = 0; i < 6; ++i) params[i] = L.lastGoodParams[i];
     mat4_inv(M_d, approxInvPose);
     lambda *= 10.0f;
 #pragma unroll
-    for (int i = 0; i < 36; ++i) Hgood[i] = s.hessianGood[i];
+    for (int i = 0; i < 36; ++i) Hgood[i] = L.Hgood[i];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) ngood[i] = s.nablaGood[i];
+    for (int i = 0; i < 6; ++i) ngood[i] = L.ngood[i];
   } else {
-    if (firstIterOfLevel) {
-      mat4_inv(M_d, approxInvPose);  // approxInvPose = pose_d->GetInvM()  (:161)
-    } else {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) approxInvPose[i] = s.approxInvPose[i];
-    }
+    for (int i = 0; i < 16; ++i) approxInvPose[i] = L.approxInvPose[i];  // == pose_d->GetInvM() on entering a level
 #pragma unroll
-    for (int i = 0; i < 16; ++i) s.lastGoodM[i] = M_d[i];
+    for (int i = 0; i < 16; ++i) L.lastGoodM[i] = M_d[i];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) s.lastGoodParams[i] = params[i];
+    for (int i = 0; i < 6; ++i) L.lastGoodParams[i] = params[i];
     fOld = fNew;
     // hessian_good / nabla_good = new / noValidPoints.  Entries outside the noPara block are garbage in
     // the reference (never read); zero here.
@@ -245,9 +248,9 @@ __device__ void lm_update(FrameState *st, const float *sSums, int iterationType,
 #pragma unroll
     for (int r = 0; r < noPara; ++r) ngood[r] = sSums[2 + r] / (float)noValid;
 #pragma unroll
-    for (int i = 0; i < 36; ++i) s.hessianGood[i] = Hgood[i];
+    for (int i = 0; i < 36; ++i) L.Hgood[i] = Hgood[i];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) s.nablaGood[i] = ngood[i];
+    for (int i = 0; i < 6; ++i) L.ngood[i] = ngood[i];
     lambda /= 10.0f;
   }
   float A[36];
@@ -262,96 +265,150 @@ __device__ void lm_update(FrameState *st, const float *sSums, int iterationType,
   mat4_inv(M_d, approxInvPose);
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    st->M_d[i] = M_d[i];
-    st->invM_d[i] = approxInvPose[i];
-    s.approxInvPose[i] = approxInvPose[i];
+    L.M_d[i] = M_d[i];
+    L.approxInvPose[i] = approxInvPose[i];
   }
 #pragma unroll
-  for (int i = 0; i < 6; ++i) st->poseParams[i] = params[i];
-  s.fOld = fOld;
-  s.lambda = lambda;
-  s.levelDone = icp_has_converged(step, terminationThreshold) ? 1 : 0;
+  for (int i = 0; i < 6; ++i) L.params[i] = params[i];
+  L.fOld = fOld;
+  L.lambda = lambda;
+  return icp_has_converged(step, terminationThreshold);
 }
+
+#ifdef ITM_ICP_TRACE
+__device__ unsigned long long g_icpTrace[64 * 8];
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define TRACE(slot, idx) if ((slot) < 64) g_icpTrace[(slot) * 8 + (idx)] = gtimer()
+#define TRACE_VAL(slot, idx, v) if ((slot) < 64) g_icpTrace[(slot) * 8 + (idx)] = (unsigned long long)(v)
+#else
+#define TRACE(slot, idx)
+#define TRACE_VAL(slot, idx, v)
+#endif
 
 struct TrackArgs {
   IcpArgs a;
   IcpLevelArgs lv[ITM_MAX_LEVELS];
   int iters[ITM_MAX_LEVELS];
   int nLevels, noIcpLevel;
-  unsigned *barrier;  // [0] arrival count, [1] generation
+  unsigned *barrier;  // [0] arrival count, [1] release word: (sequence << 1) | levelDone
 };
 
 // One launch = one TrackCamera.  Must be launched cooperatively (all CTAs co-resident).
+// CTA 0 is the master: it keeps the LM state in shared memory, waits for every CTA's partial sums, runs the LM
+// update and publishes the next pose + the "level finished" bit through the release word the others spin on.
+// (A fixed master keeps the long straight-line LM code warm in one SM's instruction cache.)
 __global__ void __launch_bounds__(ICP_THREADS, 2) k_icp_track(TrackArgs t) {
   __shared__ IcpConsts c;
   __shared__ double sPart[ICP_THREADS / 32][ICP_NVALS];
   __shared__ float sSums[ICP_NVALS];
-  __shared__ int sFlag;  // bit0: this CTA arrived last, bit1: level finished
+  __shared__ LmShared L;
+  __shared__ unsigned sRelease;
   FrameState *st = t.a.st;
   const float4 *pointsMap = reinterpret_cast<const float4 *>(t.a.pointsMap);
   const float4 *normalsMap = reinterpret_cast<const float4 *>(t.a.normalsMap);
-  unsigned *bCount = t.barrier, *bGen = t.barrier + 1;
+  unsigned *bCount = t.barrier;
+  volatile unsigned *bRelease = t.barrier + 1;
   const int nCtas = gridDim.x;
+  const bool master = blockIdx.x == 0;
 
+  if (master && threadIdx.x == 0) { TRACE(63, 0); }
   if (threadIdx.x < 16) c.scenePose[threadIdx.x] = st->scenePose[threadIdx.x];
-  if (blockIdx.x == 0 && threadIdx.x == 32) {
+  if (threadIdx.x == 0) sRelease = *bRelease;  // nobody can release before this CTA has arrived
+  if (master) {
+    if (threadIdx.x < 16) {
+      L.M_d[threadIdx.x] = st->M_d[threadIdx.x];
+      L.approxInvPose[threadIdx.x] = st->invM_d[threadIdx.x];
+    }
+    if (threadIdx.x < 6) {
+      L.params[threadIdx.x] = st->poseParams[threadIdx.x];
+      L.ngood[threadIdx.x] = 0.0f;
+    }
     // hessian_good / nabla_good are uninitialised stack variables in the reference (:151-153); start from zero
-    for (int i = 0; i < 36; ++i) st->icp.hessianGood[i] = 0.0f;
-    for (int i = 0; i < 6; ++i) st->icp.nablaGood[i] = 0.0f;
-    st->icp.evalCount = 0;
+    if (threadIdx.x >= 32 && threadIdx.x < 68) L.Hgood[threadIdx.x - 32] = 0.0f;
+    if (threadIdx.x == 0) { L.fOld = 1e10f; L.lambda = 1.0f; L.evalCount = 0; }
   }
+  __syncthreads();
+  unsigned seq = sRelease >> 1;
 
+  int evalNo = 0;
   for (int level = t.nLevels - 1; level >= t.noIcpLevel; --level) {
     const IcpLevelArgs lv = t.lv[level];
     const int type = lv.iterationType;
     if (type == ITM_ITER_NONE) continue;
-    for (int it = 0; it < t.iters[level]; ++it) {
-      // pose to evaluate at: pose_d->GetInvM() on entering a level, the LM loop's approxInvPose afterwards.
-      // Both were written by the previous leader before it released the barrier; read them from L2.
-      if (threadIdx.x < 16) c.approxInvPose[threadIdx.x] = __ldcg((it == 0 ? st->invM_d : st->icp.approxInvPose) + threadIdx.x);
-      __syncthreads();
-      double *myPartial = t.a.partials + (size_t)blockIdx.x * ICP_NVALS;
-      // coarse levels have fewer pixels than the grid has threads: only the first nActive CTAs evaluate
-      const int nActive = min(nCtas, (lv.w * lv.h + ICP_THREADS - 1) / ICP_THREADS);
-      const int NV = (type == ITM_ITER_BOTH) ? 29 : 11;
+    // coarse levels have fewer pixels than the grid has threads: only the first nActive CTAs evaluate
+    const int nActive = min(nCtas, (lv.w * lv.h + ICP_THREADS - 1) / ICP_THREADS);
+    const int NV = (type == ITM_ITER_BOTH) ? 29 : 11;
+    for (int it = 0; it < t.iters[level]; ++it, ++evalNo) {
+      // pose to evaluate at: pose_d->GetInvM() on entering a level, the LM loop's approxInvPose afterwards - the
+      // master published either one in st->icp.approxInvPose before the last release (st->invM_d before the first)
       if (blockIdx.x < nActive) {
+        if (threadIdx.x < 16) {
+          c.approxInvPose[threadIdx.x] = master ? L.approxInvPose[threadIdx.x]
+                                                : __ldcg((evalNo == 0 ? st->invM_d : st->icp.approxInvPose) + threadIdx.x);
+        }
+        __syncthreads();
+        if (master && threadIdx.x == 0) { TRACE(evalNo, 0); }
+        double *myPartial = t.a.partials + (size_t)blockIdx.x * ICP_NVALS;
         if (type == ITM_ITER_ROTATION) eval_to_partial<true, true>(lv, t.a.sceneVp, c, pointsMap, normalsMap, sPart, myPartial, nActive);
         else if (type == ITM_ITER_TRANSLATION) eval_to_partial<true, false>(lv, t.a.sceneVp, c, pointsMap, normalsMap, sPart, myPartial, nActive);
         else eval_to_partial<false, false>(lv, t.a.sceneVp, c, pointsMap, normalsMap, sPart, myPartial, nActive);
-      }
-      // ---- grid barrier; the last CTA to arrive is this iteration's leader
-      __threadfence();
-      __syncthreads();
-      unsigned gen = 0;
-      if (threadIdx.x == 0) {
-        gen = *((volatile unsigned *)bGen);
-        const unsigned prev = atomicAdd(bCount, 1u);
-        sFlag = (prev == (unsigned)nCtas - 1u) ? 1 : 0;
-      }
-      __syncthreads();
-      if (sFlag & 1) {
         __threadfence();
+      }
+      // every CTA arrives (idle ones at once): the master can then never run a whole iteration ahead of a CTA
+      // that has not started yet, which keeps the sequence number read at kernel start consistent grid-wide
+      __syncthreads();
+      if (threadIdx.x == 0) atomicAdd(bCount, 1u);
+      ++seq;
+      if (master) {
+        if (threadIdx.x == 0) {
+          TRACE(evalNo, 1);
+          while (*((volatile unsigned *)bCount) != (unsigned)nCtas) { /* wait for every partial */ }
+          __threadfence();
+          TRACE(evalNo, 2);
+        }
+        __syncthreads();
         reduce_partials(t.a.partials, nActive, sPart, sSums);
         __syncthreads();
         if (threadIdx.x == 0) {
-          if (NV == 11) lm_update<3>(st, sSums, type, it == 0, t.a.terminationThreshold);
-          else lm_update<6>(st, sSums, type, it == 0, t.a.terminationThreshold);
+          TRACE(evalNo, 3);
+          const bool conv = (NV == 11) ? lm_update<3>(L, sSums, type, it == 0, t.a.terminationThreshold)
+                                       : lm_update<6>(L, sSums, type, it == 0, t.a.terminationThreshold);
+          TRACE(evalNo, 4);
+          TRACE_VAL(evalNo, 6, level);
+          const bool lastOfLevel = conv || it == t.iters[level] - 1;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) st->icp.approxInvPose[i] = L.approxInvPose[i];
           *bCount = 0;
           __threadfence();
-          atomicAdd(bGen, 1u);  // release
+          sRelease = (seq << 1) | (lastOfLevel ? 1u : 0u);
+          *bRelease = sRelease;  // release
         }
       } else if (threadIdx.x == 0) {
-        while (*((volatile unsigned *)bGen) == gen) { /* spin */ }
+        unsigned v;
+        while (((v = *bRelease) >> 1) != seq) { /* spin */ }
         __threadfence();
+        sRelease = v;
       }
       __syncthreads();
-      // HasConverged() -> break (:196); every CTA reads the same flag after the barrier
-      if (threadIdx.x == 0) sFlag = __ldcg(&st->icp.levelDone) ? 2 : 0;
-      __syncthreads();
-      const bool done = (sFlag & 2) != 0;
-      __syncthreads();
-      if (done) break;
+      if (master && threadIdx.x == 0) { TRACE(evalNo, 5); }
+      const bool done = (sRelease & 1u) != 0;
+      if (done) { ++evalNo; break; }
     }
+  }
+  if (master && threadIdx.x == 0) {
+    float inv[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { st->M_d[i] = L.M_d[i]; inv[i] = L.approxInvPose[i]; }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) st->invM_d[i] = inv[i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) st->poseParams[i] = L.params[i];
+    st->icp.evalCount = L.evalCount;
+    TRACE(63, 1);
   }
 }
 
@@ -443,6 +500,12 @@ cudaError_t launch_icp_track(const IcpArgs &a, const IcpLevelArgs *levels, const
   void *args[] = {&t};
   return cudaLaunchCooperativeKernel((const void *)k_icp_track, dim3(icp_track_grid()), dim3(ICP_THREADS), args, 0, s);
 }
+
+#ifdef ITM_ICP_TRACE
+extern "C" int itm_b200_debug_icp_trace(unsigned long long *out512) {
+  return (int)cudaMemcpyFromSymbol(out512, g_icpTrace, sizeof(unsigned long long) * 512);
+}
+#endif
 
 void launch_icp_eval_single(const IcpArgs &a, const IcpLevelArgs &lv, float *out44, const float *poseIn, cudaStream_t s) {
   const int n = lv.w * lv.h;

@@ -1,0 +1,29 @@
+#!/usr/bin/env python
+"""Per-iteration timeline of the persistent ICP kernel (needs a build with ITM_B200_DEFINES=-DITM_ICP_TRACE)."""
+import ctypes as C, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+from infinitam_b200 import capi, synth
+from infinitam_b200.engines import ITMMainEngine
+
+lib = capi.load()
+eng = ITMMainEngine(width=640, height=480)
+eng.set_profiling(True)
+seq = synth.sequence(12, 640, 480)
+for k in range(12):
+    eng.ProcessFrame(None, seq[k])
+    if k >= 10:
+        buf = (C.c_ulonglong * 512)()
+        lib.itm_b200_debug_icp_trace(buf)
+        t = np.array(buf[:], dtype=np.uint64).reshape(64, 8).astype(np.int64)
+        _, cnt = eng.Sync()
+        n = int(cnt[5])
+        print("frame", k, "evals", n)
+        base = t[0, 0]
+        print("  kernel begin %+.1f us before eval 0, kernel end %+.1f us after it; stage_ms(track) = %.1f us" % (
+            (base - t[63, 0]) / 1e3, (t[63, 1] - base) / 1e3, 1e3 * eng.stage_times()[1]))
+        for i in range(n):
+            r = t[i]
+            print("  eval %d level %d: start %+6.1f us | cta0 arrives +%5.1f | last arrives +%5.1f | reduce %4.1f | lm %4.1f | cta0 released +%5.1f (total %5.1f)" % (
+                i, r[6], (r[0] - base) / 1e3, (r[1] - r[0]) / 1e3, (r[2] - r[0]) / 1e3, (r[3] - r[2]) / 1e3, (r[4] - r[3]) / 1e3, (r[5] - r[0]) / 1e3, (r[5] - r[0]) / 1e3))
