@@ -131,11 +131,11 @@ int ctx_alloc(itm_b200_ctx *c, void *stream) {
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->ownStream = true;
   }
-  const int numTiles = (c->sp.nEntries + 1023) / 1024;
+  const int numTiles = (c->sp.nEntries + 8191) / 8192;
   const long long maxKey = (long long)c->p.width * c->p.height * alloc_step_bound(c->sp);
   if (maxKey >= 0xFFFFFFFFLL) return fail(ITM_B200_EUNSUPPORTED, "image size x ray-segment steps exceeds the 32-bit allocation key");
-  CU(cudaMalloc(&c->allocKey, (size_t)numTiles * 1024 * sizeof(unsigned)));
-  CU(cudaMemsetAsync(c->allocKey, 0, (size_t)numTiles * 1024 * sizeof(unsigned), c->stream));
+  CU(cudaMalloc(&c->allocKey, (size_t)numTiles * 8192 * sizeof(unsigned)));
+  CU(cudaMemsetAsync(c->allocKey, 0, (size_t)numTiles * 8192 * sizeof(unsigned), c->stream));
   CU(cudaMalloc(&c->scanTickets, 2 * sizeof(unsigned long long)));
   CU(cudaMemsetAsync(c->scanTickets, 0, 2 * sizeof(unsigned long long), c->stream));
   CU(cudaMalloc(&c->allocTileState, numTiles * sizeof(unsigned long long)));
@@ -578,7 +578,7 @@ int engine_alloc(itm_b200_engine *e) {
   CU(cudaMalloc(&e->vbaAllocList, (size_t)c->sp.nLocal * 4));
   CU(cudaMalloc(&e->excessAllocList, (size_t)c->sp.nExcess * 4));
   CU(cudaMalloc(&e->visibleIds, (size_t)c->sp.nLocal * 4));
-  CU(cudaMalloc(&e->visType, (size_t)((c->sp.nEntries + 1023) / 1024) * 1024));
+  CU(cudaMalloc(&e->visType, (size_t)((c->sp.nEntries + 8191) / 8192) * 8192));
   CU(cudaMalloc(&e->minmax, P * 8));
   CU(cudaMalloc(&e->raycastResult, P * 16));
   CU(cudaMalloc(&e->raycastImage, P * 4));
@@ -625,7 +625,7 @@ int engine_reset(itm_b200_engine *e) {
   launch_reset_scene(e->voxels, e->vbaAllocList, e->hash, e->excessAllocList, c->sp, c->stream);
   g_launches += 1;
   // MemoryBlock constructors clear their memory (ORUtils/MemoryBlock.h:88-110)
-  CU(cudaMemsetAsync(e->visType, 0, (size_t)((c->sp.nEntries + 1023) / 1024) * 1024, c->stream));
+  CU(cudaMemsetAsync(e->visType, 0, (size_t)((c->sp.nEntries + 8191) / 8192) * 8192, c->stream));
   CU(cudaMemsetAsync(e->visibleIds, 0, (size_t)c->sp.nLocal * 4, c->stream));
   CU(cudaMemsetAsync(e->raycastResult, 0, P * 16, c->stream));
   CU(cudaMemsetAsync(e->raycastImage, 0, P * 4, c->stream));
@@ -633,7 +633,7 @@ int engine_reset(itm_b200_engine *e) {
   CU(cudaMemsetAsync(e->normals, 0, P * 16, c->stream));
   CU(cudaMemsetAsync(e->minmax, 0, P * 8, c->stream));
   CU(cudaMemsetAsync(e->depth, 0, P * 4, c->stream));
-  CU(cudaMemsetAsync(c->allocKey, 0, (size_t)((c->sp.nEntries + 1023) / 1024) * 1024 * sizeof(unsigned), c->stream));
+  CU(cudaMemsetAsync(c->allocKey, 0, (size_t)((c->sp.nEntries + 8191) / 8192) * 8192 * sizeof(unsigned), c->stream));
   host_state_init(c->hst, c->sp);
   int rc = push_state(c);
   if (rc) return rc;

@@ -12,11 +12,12 @@
 //      atomicMax(allocKey[slot], pixel * stepBound + step + 1) - the largest key IS the last
 //      writer of the serial loop.  The block coordinate is not stored; the winner's
 //      coordinate is recomputed from its key in step 2 by the same device function.
-//   2. k_alloc_scan: single-pass ordered scan over all slots (scan_util.cuh) gives every
+//   2. k_alloc_scan: single-pass ordered scan over all slots (8192-slot tiles, one CTA per SM) (scan_util.cuh) gives every
 //      request its rank, hence exactly the VBA / excess-list entries the serial loop would
 //      pop.  The hash table (pos, offset, ptr) comes out bit-identical to the reference.
 //   3. k_visible_scan: same scan machinery over entriesVisibleType; visibleEntryIDs come out
-//      in ascending slot order like the reference's.
+//      in ascending slot order like the reference's.  (The frustum re-check of last frame's entries
+//      runs one thread per entry at the start of k_alloc_scan.)
 // No counter is read back by the host; the free-list heads and the visible count live in
 // FrameState.
 #include "itm_common.cuh"
@@ -130,107 +131,6 @@ __global__ void __launch_bounds__(256) k_alloc_pixels(const float *__restrict__ 
   }
 }
 
-// 256 threads x 4 slots = 1024-slot tiles
-__global__ void __launch_bounds__(256) k_alloc_scan(unsigned *__restrict__ allocKey, HashEntry *__restrict__ table,
-                                                    unsigned char *__restrict__ visType, const int *__restrict__ vbaAllocList,
-                                                    const int *__restrict__ excessAllocList, const float *__restrict__ depth,
-                                                    FrameState *st, ViewParams vp, SceneParams sp, float oneOverVoxelSize,
-                                                    int stepBound, int doAllocate, unsigned long long *ticket,
-                                                    unsigned long long *tileState, int numTiles) {
-  __shared__ unsigned sWarp[8];
-  __shared__ unsigned sTotal;
-  __shared__ unsigned sExA, sExB;
-  __shared__ int sTile;
-  __shared__ unsigned sEpoch;
-  __shared__ float sInvM[16];
-  if (threadIdx.x == 0) {
-    const unsigned long long t = atomicAdd(ticket, 1ull);
-    sTile = (int)(t % (unsigned long long)numTiles);
-    sEpoch = (unsigned)((t / (unsigned long long)numTiles + 1ull) & 0xFFFFFull);
-  }
-  if (threadIdx.x < 16) sInvM[threadIdx.x] = st->invM_d[threadIdx.x];
-  __syncthreads();
-  const int tile = sTile;
-  const int slot0 = tile * 1024 + threadIdx.x * 4;
-  uint4 k4 = make_uint4(0, 0, 0, 0);
-  if (slot0 + 3 < sp.nEntries) {
-    k4 = *reinterpret_cast<const uint4 *>(allocKey + slot0);
-  } else {
-    if (slot0 + 0 < sp.nEntries) k4.x = allocKey[slot0 + 0];
-    if (slot0 + 1 < sp.nEntries) k4.y = allocKey[slot0 + 1];
-    if (slot0 + 2 < sp.nEntries) k4.z = allocKey[slot0 + 2];
-  }
-  const unsigned keys[4] = {k4.x, k4.y, k4.z, k4.w};
-  int type[4];
-  unsigned packed = 0;  // low 16: all requests, high 16: excess-list requests
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    type[j] = 0;
-    if (keys[j] != 0 && doAllocate) {
-      const int slot = slot0 + j;
-      int t = 2;
-      if (slot < sp.nBuckets && table[slot].ptr < -1) t = 1;
-      type[j] = t;
-      packed += 1u + (t == 2 ? 0x10000u : 0u);
-    }
-  }
-  const unsigned excl = block_exclusive_scan_256(packed, sWarp, &sTotal);
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    unsigned exA, exB;
-    scan_lookback(tileState, tile, sEpoch, sTotal & 0xFFFFu, sTotal >> 16, exA, exB);
-    if (threadIdx.x == 0) {
-      sExA = exA;
-      sExB = exB;
-      if (tile == numTiles - 1) {
-        // counters always count down by the number of requests, successful or not (:186, :204-205)
-        st->lastFreeBlockId = st->allocBaseBlockId - (int)(exA + (sTotal & 0xFFFFu));
-        st->lastFreeExcessId = st->allocBaseExcessId - (int)(exB + (sTotal >> 16));
-      }
-    }
-  }
-  __syncthreads();
-  if (packed == 0 && (k4.x | k4.y | k4.z | k4.w) == 0) return;
-  int rankA = (int)(sExA + (excl & 0xFFFFu));
-  int rankB = (int)(sExB + (excl >> 16));
-  const int baseVba = st->allocBaseBlockId, baseExl = st->allocBaseExcessId;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    if (keys[j] == 0) continue;
-    const int slot = slot0 + j;
-    allocKey[slot] = 0;  // leave the array clean for the next frame
-    if (type[j] == 0) continue;
-    // recompute the winning request's block coordinate from its (pixel, step) key
-    const unsigned key = keys[j] - 1u;
-    const int locId = (int)(key / (unsigned)stepBound), step = (int)(key % (unsigned)stepBound);
-    const int y = locId / vp.W, x = locId - y * vp.W;
-    RaySegment r;
-    make_ray_segment(r, __ldg(depth + locId), x, y, sInvM, 1.0f / vp.fx, 1.0f / vp.fy, vp.cx, vp.cy, sp.mu, oneOverVoxelSize, sp.vfMin,
-                     sp.vfMax);
-    float px = r.px, py = r.py, pz = r.pz;
-    for (int i = 0; i < step; ++i) { px += r.dx; py += r.dy; pz += r.dz; }
-    int bx, by, bz;
-    block_of(px, py, pz, bx, by, bz);
-    const int vbaIdx = baseVba - rankA;
-    rankA++;
-    if (type[j] == 1) {
-      if (vbaIdx >= 0) store_entry(table, slot, bx, by, bz, 0, vbaAllocList[vbaIdx]);
-      else atomicAdd(&st->allocFailures, 1);
-    } else {
-      const int exlIdx = baseExl - rankB;
-      rankB++;
-      if (vbaIdx >= 0 && exlIdx >= 0) {
-        const int exlOffset = excessAllocList[exlIdx];
-        table[slot].offset = exlOffset + 1;
-        store_entry(table, sp.nBuckets + exlOffset, bx, by, bz, 0, vbaAllocList[vbaIdx]);
-        visType[sp.nBuckets + exlOffset] = 1;
-      } else {
-        atomicAdd(&st->allocFailures, 1);
-      }
-    }
-  }
-}
-
 // checkPointVisibility<false>, ITMSceneReconstructionEngine.h:244-274
 __device__ __forceinline__ bool point_visible(const float *M, float x, float y, float z, const ViewParams &vp) {
   float bx, by, bz;
@@ -243,7 +143,7 @@ __device__ __forceinline__ bool point_visible(const float *M, float x, float y, 
 
 // checkBlockVisibility<false>, :277-342 - the corner coordinates are built by the same chain of
 // += / -= as the reference so that they round identically
-__device__ bool block_visible(const float *M, int hx, int hy, int hz, float voxelSize, const ViewParams &vp) {
+__device__ __noinline__ bool block_visible(const float *M, int hx, int hy, int hz, float voxelSize, const ViewParams &vp) {
   const float factor = (float)ITM_BLOCK_SIZE * voxelSize;
   float x = (float)hx * factor, y = (float)hy * factor, z = (float)hz * factor;
   if (point_visible(M, x, y, z, vp)) return true;  // 0 0 0
@@ -267,8 +167,138 @@ __device__ bool block_visible(const float *M, int hx, int hy, int hz, float voxe
   return false;
 }
 
-__global__ void __launch_bounds__(256) k_visible_scan(unsigned char *__restrict__ visType, const HashEntry *__restrict__ table,
-                                                      int *__restrict__ visibleIds, FrameState *st, ViewParams vp, SceneParams sp,
+#define SCAN_TILE 8192        // slots per CTA
+#define SCAN_PER_THREAD 32    // consecutive slots per thread (256 threads)
+
+// Every thread owns 32 consecutive slots; 1.18 M slots are 144 tiles, i.e. one CTA per SM and a look-back chain of
+// at most 5 warp-wide windows (with 1024-slot tiles the chain was 36 windows long and dominated the kernel).
+__global__ void __launch_bounds__(256) k_alloc_scan(unsigned *__restrict__ allocKey, HashEntry *__restrict__ table,
+                                                    unsigned char *__restrict__ visType, const int *__restrict__ vbaAllocList,
+                                                    const int *__restrict__ excessAllocList, const float *__restrict__ depth,
+                                                    FrameState *st, ViewParams vp, SceneParams sp, float oneOverVoxelSize,
+                                                    int stepBound, int doAllocate, unsigned long long *ticket,
+                                                    unsigned long long *tileState, int numTiles,
+                                                    const int *__restrict__ prevVisibleIds) {
+  __shared__ unsigned sWarp[8];
+  __shared__ unsigned sTotal;
+  __shared__ unsigned sExA, sExB;
+  __shared__ int sTile;
+  __shared__ unsigned sEpoch;
+  __shared__ float sInvM[16];
+  __shared__ float sM[16];
+  if (threadIdx.x == 0) {
+    const unsigned long long t = atomicAdd(ticket, 1ull);
+    sTile = (int)(t % (unsigned long long)numTiles);
+    sEpoch = (unsigned)((t / (unsigned long long)numTiles + 1ull) & 0xFFFFFull);
+  }
+  if (threadIdx.x < 16) sInvM[threadIdx.x] = st->invM_d[threadIdx.x];
+  if (threadIdx.x >= 32 && threadIdx.x < 48) sM[threadIdx.x - 32] = st->M_d[threadIdx.x - 32];
+  __syncthreads();
+  // Entries that were visible last frame and that no ray hit this frame still carry type 3: they stay in the list only
+  // while one of their corners projects into the image (:236-247).  One thread per previous entry, spread over the grid;
+  // independent of the allocation scan below (new entries are never in the previous list).
+  {
+    const int nPrev = st->noVisibleEntries;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nPrev; i += gridDim.x * blockDim.x) {
+      const int id = __ldg(prevVisibleIds + i);
+      if (visType[id] == 3) {
+        const HashEntry e = load_entry(table, id);
+        if (!block_visible(sM, e.px, e.py, e.pz, sp.voxelSize, vp)) visType[id] = 0;
+      }
+    }
+  }
+  const int tile = sTile;
+  const int slot0 = tile * SCAN_TILE + threadIdx.x * SCAN_PER_THREAD;
+  // the key array is padded to whole tiles, so the vector loads never run past it
+  const uint4 *k4 = reinterpret_cast<const uint4 *>(allocKey + slot0);
+  uint4 kv[SCAN_PER_THREAD / 4];
+  unsigned any = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_PER_THREAD / 4; ++i) {
+    kv[i] = k4[i];
+    any |= kv[i].x | kv[i].y | kv[i].z | kv[i].w;
+  }
+  unsigned typeMask1 = 0, typeMask2 = 0;  // bit j: slot0 + j requests a bucket entry / an excess-list entry
+  unsigned packed = 0;                    // low 16: all requests, high 16: excess-list requests
+  if (any && doAllocate) {
+#pragma unroll
+    for (int i = 0; i < SCAN_PER_THREAD / 4; ++i) {
+      const unsigned keys[4] = {kv[i].x, kv[i].y, kv[i].z, kv[i].w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (keys[q] == 0) continue;
+        const int j = i * 4 + q, slot = slot0 + j;
+        if (slot < sp.nBuckets && table[slot].ptr < -1) {
+          typeMask1 |= 1u << j;
+          packed += 1u;
+        } else {
+          typeMask2 |= 1u << j;
+          packed += 0x10001u;
+        }
+      }
+    }
+  }
+  const unsigned excl = block_exclusive_scan_256(packed, sWarp, &sTotal);
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    unsigned exA, exB;
+    scan_lookback(tileState, tile, sEpoch, sTotal & 0xFFFFu, sTotal >> 16, exA, exB);
+    if (threadIdx.x == 0) {
+      sExA = exA;
+      sExB = exB;
+      if (tile == numTiles - 1) {
+        // counters always count down by the number of requests, successful or not (:186, :204-205)
+        st->lastFreeBlockId = st->allocBaseBlockId - (int)(exA + (sTotal & 0xFFFFu));
+        st->lastFreeExcessId = st->allocBaseExcessId - (int)(exB + (sTotal >> 16));
+      }
+    }
+  }
+  __syncthreads();
+  if (!any) return;
+  int rankA = (int)(sExA + (excl & 0xFFFFu));
+  int rankB = (int)(sExB + (excl >> 16));
+  const int baseVba = st->allocBaseBlockId, baseExl = st->allocBaseExcessId;
+#pragma unroll 1
+  for (int j = 0; j < SCAN_PER_THREAD; ++j) {
+    const unsigned keyRaw = allocKey[slot0 + j];
+    if (keyRaw == 0) continue;
+    const int slot = slot0 + j;
+    allocKey[slot] = 0;  // leave the array clean for the next frame
+    const bool t1 = (typeMask1 >> j) & 1u, t2 = (typeMask2 >> j) & 1u;
+    if (!t1 && !t2) continue;
+    // recompute the winning request's block coordinate from its (pixel, step) key
+    const unsigned key = keyRaw - 1u;
+    const int locId = (int)(key / (unsigned)stepBound), step = (int)(key % (unsigned)stepBound);
+    const int y = locId / vp.W, x = locId - y * vp.W;
+    RaySegment r;
+    make_ray_segment(r, __ldg(depth + locId), x, y, sInvM, 1.0f / vp.fx, 1.0f / vp.fy, vp.cx, vp.cy, sp.mu, oneOverVoxelSize, sp.vfMin,
+                     sp.vfMax);
+    float px = r.px, py = r.py, pz = r.pz;
+    for (int i = 0; i < step; ++i) { px += r.dx; py += r.dy; pz += r.dz; }
+    int bx, by, bz;
+    block_of(px, py, pz, bx, by, bz);
+    const int vbaIdx = baseVba - rankA;
+    rankA++;
+    if (t1) {
+      if (vbaIdx >= 0) store_entry(table, slot, bx, by, bz, 0, vbaAllocList[vbaIdx]);
+      else atomicAdd(&st->allocFailures, 1);
+    } else {
+      const int exlIdx = baseExl - rankB;
+      rankB++;
+      if (vbaIdx >= 0 && exlIdx >= 0) {
+        const int exlOffset = excessAllocList[exlIdx];
+        table[slot].offset = exlOffset + 1;
+        store_entry(table, sp.nBuckets + exlOffset, bx, by, bz, 0, vbaAllocList[vbaIdx]);
+        visType[sp.nBuckets + exlOffset] = 1;
+      } else {
+        atomicAdd(&st->allocFailures, 1);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_visible_scan(const unsigned char *__restrict__ visType,
+                                                      int *__restrict__ visibleIds, FrameState *st, SceneParams sp,
                                                       int visibleCapacity, unsigned long long *ticket, unsigned long long *tileState,
                                                       int numTiles) {
   __shared__ unsigned sWarp[8];
@@ -276,43 +306,38 @@ __global__ void __launch_bounds__(256) k_visible_scan(unsigned char *__restrict_
   __shared__ unsigned sExA;
   __shared__ int sTile;
   __shared__ unsigned sEpoch;
-  __shared__ float sM[16];
   if (threadIdx.x == 0) {
     const unsigned long long t = atomicAdd(ticket, 1ull);
     sTile = (int)(t % (unsigned long long)numTiles);
     sEpoch = (unsigned)((t / (unsigned long long)numTiles + 1ull) & 0xFFFFFull);
   }
-  if (threadIdx.x < 16) sM[threadIdx.x] = st->M_d[threadIdx.x];
   __syncthreads();
   const int tile = sTile;
-  const int slot0 = tile * 1024 + threadIdx.x * 4;
-  unsigned v4 = 0;
-  if (slot0 + 3 < sp.nEntries) {
-    v4 = *reinterpret_cast<const unsigned *>(visType + slot0);
+  const int slot0 = tile * SCAN_TILE + threadIdx.x * SCAN_PER_THREAD;
+  // 32 type bytes per thread.  entriesVisibleType is caller-owned and exactly nEntries long: the last tile may be ragged.
+  unsigned w[SCAN_PER_THREAD / 4];
+  if (slot0 + SCAN_PER_THREAD <= sp.nEntries) {
+    const uint4 a = *reinterpret_cast<const uint4 *>(visType + slot0);
+    const uint4 b = *reinterpret_cast<const uint4 *>(visType + slot0 + 16);
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
   } else {
-    for (int j = 0; j < 4; ++j)
-      if (slot0 + j < sp.nEntries) v4 |= (unsigned)visType[slot0 + j] << (8 * j);
+#pragma unroll
+    for (int i = 0; i < SCAN_PER_THREAD / 4; ++i) {
+      w[i] = 0;
+      for (int q = 0; q < 4; ++q)
+        if (slot0 + i * 4 + q < sp.nEntries) w[i] |= (unsigned)visType[slot0 + i * 4 + q] << (8 * q);
+    }
   }
   unsigned cnt = 0;
-  unsigned out4 = v4;
-  if (v4 != 0) {
+  unsigned liveMask = 0;  // bit j: slot0 + j is in the visible list (type > 0; type 3 was re-checked by k_alloc_scan)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      unsigned t = (v4 >> (8 * j)) & 0xFFu;
-      if (t == 3) {
-        const HashEntry e = load_entry_cg(table, slot0 + j);
-        if (!block_visible(sM, e.px, e.py, e.pz, sp.voxelSize, vp)) {
-          t = 0;
-          out4 &= ~(0xFFu << (8 * j));
-        }
+  for (int i = 0; i < SCAN_PER_THREAD / 4; ++i) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if ((w[i] >> (8 * q)) & 0xFFu) {
+        cnt++;
+        liveMask |= 1u << (i * 4 + q);
       }
-      if (t > 0) cnt++;
-    }
-    if (out4 != v4) {
-      if (slot0 + 3 < sp.nEntries) *reinterpret_cast<unsigned *>(visType + slot0) = out4;
-      else
-        for (int j = 0; j < 4; ++j)
-          if (slot0 + j < sp.nEntries) visType[slot0 + j] = (unsigned char)(out4 >> (8 * j));
     }
   }
   const unsigned excl = block_exclusive_scan_256(cnt, sWarp, &sTotal);
@@ -335,12 +360,11 @@ __global__ void __launch_bounds__(256) k_visible_scan(unsigned char *__restrict_
   __syncthreads();
   if (cnt == 0) return;
   int pos = (int)(sExA + excl);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    if ((out4 >> (8 * j)) & 0xFFu) {
-      if (pos < visibleCapacity) visibleIds[pos] = slot0 + j;
-      pos++;
-    }
+  while (liveMask) {
+    const int j = __ffs(liveMask) - 1;
+    liveMask &= liveMask - 1;
+    if (pos < visibleCapacity) visibleIds[pos] = slot0 + j;
+    pos++;
   }
 }
 
@@ -382,10 +406,10 @@ void launch_allocate(const AllocArgs &a, cudaStream_t s) {
   k_mark_prev_visible<<<64, 256, 0, s>>>(a.visibleIds, a.visType, a.st);
   dim3 g((a.vp.W + 31) / 32, (a.vp.H + 7) / 8);
   k_alloc_pixels<<<g, 256, 0, s>>>(a.depth, table, a.visType, a.allocKey, a.st, a.vp, a.sp, oneOverVoxelSize, stepBound);
-  const int numTiles = (a.sp.nEntries + 1023) / 1024;
+  const int numTiles = (a.sp.nEntries + SCAN_TILE - 1) / SCAN_TILE;
   k_alloc_scan<<<numTiles, 256, 0, s>>>(a.allocKey, table, a.visType, a.vbaAllocList, a.excessAllocList, a.depth, a.st, a.vp, a.sp,
-                                        oneOverVoxelSize, stepBound, a.onlyUpdateVisibleList ? 0 : 1, a.scanTickets, a.allocTileState, numTiles);
-  k_visible_scan<<<numTiles, 256, 0, s>>>(a.visType, table, a.visibleIds, a.st, a.vp, a.sp, a.visibleCapacity, a.scanTickets + 1,
+                                        oneOverVoxelSize, stepBound, a.onlyUpdateVisibleList ? 0 : 1, a.scanTickets, a.allocTileState, numTiles, a.visibleIds);
+  k_visible_scan<<<numTiles, 256, 0, s>>>(a.visType, a.visibleIds, a.st, a.sp, a.visibleCapacity, a.scanTickets + 1,
                                           a.visTileState, numTiles);
 }
 

@@ -13,9 +13,9 @@ struct AllocArgs {
   int *visibleIds;               // ITMRenderState_VH::visibleEntryIDs
   unsigned char *visType;        // ITMRenderState_VH::entriesVisibleType
   int visibleCapacity;           // SDF_LOCAL_BLOCK_NUM
-  unsigned *allocKey;            // scratch: one key per slot, all zero between frames
+  unsigned *allocKey;            // scratch: one key per slot (padded to 8192), all zero between frames
   unsigned long long *scanTickets;     // scratch: [0] alloc scan, [1] visible scan
-  unsigned long long *allocTileState;  // scratch: one word per 1024-slot tile
+  unsigned long long *allocTileState;  // scratch: one word per 8192-slot tile
   unsigned long long *visTileState;
   FrameState *st;
   ViewParams vp;

@@ -4,7 +4,7 @@
 // free-list entries / visible-list positions in that order
 // (ITMSceneReconstructionEngine_CPU.cpp:179-226, 230-269).  To reproduce the very same
 // assignment on the GPU every slot needs its rank among the flagged slots: an exclusive
-// prefix sum over ~1.18 M flags.  One kernel does it: each CTA scans its 1024-slot tile in
+// prefix sum over ~1.18 M flags.  One kernel does it: each CTA scans its 8192-slot tile in
 // shared memory, publishes the tile aggregate in a 64-bit status word and resolves its
 // global offset by looking back at its predecessors.
 //
