@@ -560,6 +560,8 @@ struct itm_b200_engine {
   // view
   short *rawDepth = nullptr;
   unsigned char *rgb = nullptr;
+  cudaStream_t copyStream = nullptr;  // view->rgb upload: not consumed by the depth-only path, kept off its critical path
+  cudaEvent_t rgbDone = nullptr;
   float *depth = nullptr;
   int agePointCloud = -1;  // host copy; its evolution does not depend on device results
   bool profiling = false;
@@ -586,6 +588,8 @@ int engine_alloc(itm_b200_engine *e) {
   CU(cudaMalloc(&e->normals, P * 16));
   CU(cudaMalloc(&e->rawDepth, P * 2));
   CU(cudaMalloc(&e->rgb, P * 4));
+  CU(cudaStreamCreateWithFlags(&e->copyStream, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&e->rgbDone, cudaEventDisableTiming));
   CU(cudaMalloc(&e->depth, P * 4));
   for (int i = 0; i < 9; ++i) CU(cudaEventCreate(&e->ev[i]));
   e->bytes[ITM_B200_BUF_VOXELS] = (size_t)c->sp.nLocal * ITM_BLOCK_SIZE3 * 4;
@@ -611,6 +615,8 @@ void engine_free(itm_b200_engine *e) {
   cudaFree(e->visibleIds); cudaFree(e->visType); cudaFree(e->minmax); cudaFree(e->raycastResult);
   cudaFree(e->raycastImage); cudaFree(e->points); cudaFree(e->normals); cudaFree(e->rawDepth);
   cudaFree(e->rgb); cudaFree(e->depth);
+  if (e->copyStream) cudaStreamDestroy(e->copyStream);
+  if (e->rgbDone) cudaEventDestroy(e->rgbDone);
   for (int i = 0; i < 9; ++i)
     if (e->ev[i]) cudaEventDestroy(e->ev[i]);
   if (e->c) {
@@ -795,10 +801,16 @@ int itm_b200_engine_process_frame(itm_b200_engine *e, const unsigned char *rgb_h
   cudaStream_t s = e->c->stream;
   const size_t P = (size_t)e->c->vp.W * e->c->vp.H;
   if (e->profiling) cudaEventRecord(e->ev[0], s);
-  // ITMViewBuilder::UpdateView: rgb + raw depth to the device (ITMViewBuilder_CUDA.cu:52-53)
+  // ITMViewBuilder::UpdateView: rgb + raw depth to the device (ITMViewBuilder_CUDA.cu:52-53).  The colour image is
+  // not read by the ITMVoxel_s path, so it travels on a second stream while the frame is being fused; the call still
+  // returns only after view->rgb is complete.
   CU(cudaMemcpyAsync(e->rawDepth, raw_depth_host, P * 2, cudaMemcpyHostToDevice, s));
-  if (rgb_host) CU(cudaMemcpyAsync(e->rgb, rgb_host, P * 4, cudaMemcpyHostToDevice, s));
+  if (rgb_host) {
+    CU(cudaMemcpyAsync(e->rgb, rgb_host, P * 4, cudaMemcpyHostToDevice, e->copyStream));
+    CU(cudaEventRecord(e->rgbDone, e->copyStream));
+  }
   enqueue_frame(e);
+  if (rgb_host) CU(cudaStreamWaitEvent(s, e->rgbDone, 0));
   return itm_b200_engine_sync(e, pose_out, nullptr);
 }
 
