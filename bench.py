@@ -62,7 +62,7 @@ class ClockSampler(threading.Thread):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.rows.append([x.strip() for x in line.split(",")])
@@ -70,6 +70,15 @@ class ClockSampler(threading.Thread):
                     break
         except Exception:  # noqa: BLE001
             pass
+
+    def wait_first_sample(self, timeout_s=5.0):
+        t0 = time.perf_counter()
+        while not self.rows and time.perf_counter() - t0 < timeout_s:
+            time.sleep(0.01)
+
+    def mark(self):
+        """rows sampled from here on belong to the timed region"""
+        self.first_timed_row = len(self.rows)
 
     def stop(self):
         self._stop.set()
@@ -79,7 +88,7 @@ class ClockSampler(threading.Thread):
     def summary(self):
         sm, mx, reasons = [], 0.0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in self.rows[getattr(self, "first_timed_row", 0):]:
             try:
                 sm.append(float(r[0]))
                 mx = max(mx, float(r[1]))
@@ -89,6 +98,20 @@ class ClockSampler(threading.Thread):
             except Exception:  # noqa: BLE001
                 continue
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch and stage, from the newest committed `ncu --set full` summary
+    (profiles/rNN_ncu_summary.json, written by tools/ncu_summary.py); {} if there is none."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_summary.json")))
+    if not files:
+        return {}
+    try:
+        with open(files[-1]) as f:
+            return json.load(f).get("stage_traffic_bytes", {})
+    except Exception:  # noqa: BLE001
+        return {}
 
 
 def _dist_env():
@@ -207,17 +230,20 @@ def run_ours(args):
     # the engine runs on its own stream: time it there.  torch cannot record on a foreign stream, so the
     # engine's own per-stage CUDA events (recorded on that stream) provide the device time of each step.
     eng.set_profiling(True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    sampler.wait_first_sample()
     for k in range(args.warmup):
         flush.fill_(k)
         torch.cuda.synchronize()
         eng.EnqueueFrameDevice(frames_dev[k].data_ptr())
         eng.Sync()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark()
     launches0 = lib.itm_b200_launch_count()
     step_ms = []
     stage_ms = np.zeros(8)
+    n_vis_sum, level_evals = 0, np.zeros(capi.MAX_LEVELS, np.int64)
     for k in range(args.warmup, n):
         flush.fill_(k & 0xFF)
         torch.cuda.synchronize()
@@ -227,9 +253,10 @@ def run_ours(args):
         # ms[7] = frame start .. end of the last kernel, ms[0] includes the D2D placement of the input
         step_ms.append(float(ms[7]))
         stage_ms += ms
+        n_vis_sum += int(counters[0])
+        level_evals += eng.icp_stats()
     launches = lib.itm_b200_launch_count() - launches0
     barrier()
-    sampler.stop()
     total_ms = float(np.sum(step_ms))
     n_vis = int(counters[0])
     pose_dev_path, _ = eng.Sync()
@@ -250,6 +277,7 @@ def run_ours(args):
         pose = eng.ProcessFrame(rgb_pinned, frames_pinned[k])
         e2e_s += time.perf_counter() - t0
     barrier()
+    sampler.stop()
     eng.close()
 
     t = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
@@ -262,25 +290,40 @@ def run_ours(args):
         stage_names = ["view", "track", "allocate", "integrate", "expected_depths", "raycast", "icp_maps", "total"]
         stage_avg = {k: float(v / args.steps) for k, v in zip(stage_names, stage_ms)}
         P = W * H
-        # algorithmic bytes per launch
-        bytes_integrate = n_vis * (2 * 512 * 4 + 16 + 4) + 4 * P
-        bytes_raycast = 16 * P + n_vis * (512 * 4 + 16) + 8 * P // 64
+        E = params.sdf_bucket_num + params.sdf_excess_list_size
+        nv = n_vis_sum / args.steps  # mean visible blocks per timed frame
+        ev = level_evals / args.steps  # mean ComputeGandH evaluations per frame and pyramid level
+        # ALGORITHMIC bytes per frame of every stage (DESIGN.md "Kernels")
+        alg = {
+            "view": P * (2 + 4) + 4 * P * (1 / 4 + 1 / 16 + 1 / 64 + 1 / 256),
+            "track": float(sum(ev[l] * (4 * P / 4 ** l + min(128 * P / 4 ** l, 2 * 16 * P)) for l in range(5))),
+            "allocate": 4 * P + 3 * E + nv * (16 + 4 + 1),
+            "integrate": nv * (2 * 512 * 4 + 16 + 4) + 4 * P,
+            "expected_depths": 8 * P / 64 * 2 + nv * (4 + 16),
+            "raycast": 16 * P + nv * (512 * 4 + 16) + 8 * P / 64,
+            "icp_maps": P * (16 + 16 + 16 + 4),
+        }
+        kernels = {"view": "k_convert_pyramid", "track": "k_icp_track", "allocate": "k_mark_prev_visible+k_alloc_pixels+k_alloc_scan+k_visible_scan",
+                   "integrate": "k_integrate", "expected_depths": "k_minmax_init+k_expected_depths", "raycast": "k_raycast", "icp_maps": "k_icp_maps"}
+        traffic = _ncu_traffic()
         roof = {}
-        for name, b, ms in (("integrate", bytes_integrate, stage_avg["integrate"]), ("raycast", bytes_raycast, stage_avg["raycast"])):
+        for name, b in alg.items():
+            ms = stage_avg[name]
             ach = b / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
-            roof[name] = {"kernel": "k_" + name, "bound": "hbm", "achieved": ach, "peak": peak, "peak_kind": peak_kind + " (burst copy)", "unit": "GB/s",
-                          "frac": ach / peak, "traffic": None, "algorithmic_bytes": b, "avg_launch_ms": ms,
+            roof[name] = {"kernel": kernels[name], "bound": "hbm", "achieved": ach, "peak": peak, "peak_kind": peak_kind + " (burst copy)", "unit": "GB/s",
+                          "frac": ach / peak, "traffic": traffic.get(name), "algorithmic_bytes": int(b), "avg_launch_ms": ms,
                           "share_of_step": ms / stage_avg["total"] if stage_avg["total"] else None}
         dominant = max(roof, key=lambda k: roof[k]["avg_launch_ms"])
+        n_vis = int(round(nv))
         out = {
             "metric": "fused frames/s (allocate+integrate+raycast+ICP) 640x480", "value": world * args.steps / (total_ms_max * 1e-3),
             "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "configs[1]: synthetic 640x480 analytic-room sequence, 5 mm voxels, mu=0.02, ITMVoxel_s, depth ICP tracker",
-                       "frames": args.steps, "visible_blocks": n_vis, "l2": "flushed between frames (256 MiB write, outside the timed events)",
+                       "frames": args.steps, "visible_blocks": n_vis, "icp_evaluations_per_frame": float(ev.sum()), "l2": "flushed between frames (256 MiB write, outside the timed events)",
                        "parallelism": "replicas only: one independent scene per GPU, no collective on the data path",
                        "timing": "per-frame CUDA events on the engine stream, summed; max over ranks"},
-            "gvoxel_updates_per_s": world * n_vis * 512 / (stage_avg["integrate"] * 1e-3) / 1e9 if stage_avg["integrate"] else None,
+            "gvoxel_updates_per_s": world * nv * 512 / (stage_avg["integrate"] * 1e-3) / 1e9 if stage_avg["integrate"] else None,
             "stage_ms": stage_avg,
             "roofline": roof[dominant],
             "roofline_other": {k: v for k, v in roof.items() if k != dominant},

@@ -211,6 +211,10 @@ int itm_b200_engine_write_buffer(itm_b200_engine *e, int which, const void *host
 int itm_b200_engine_get_state(itm_b200_engine *e, float pose_d[16], float pose_point_cloud[16], int state6[6]);
 int itm_b200_engine_set_state(itm_b200_engine *e, const float pose_d[16], const float pose_point_cloud[16], const int state6[6]);
 
+/* ICP evaluations (ComputeGandH calls) per pyramid level during the last frame fetched by
+ * itm_b200_engine_sync / _process_frame (level 0 = full resolution). */
+int itm_b200_engine_icp_stats(itm_b200_engine *e, int evals_per_level[ITM_B200_MAX_LEVELS]);
+
 /* Per-stage device times (CUDA events) of the last processed frame in milliseconds:
  * {h2d+view, track, allocate, integrate, expected depths, raycast, icp maps, total}.
  * Enabled by itm_b200_engine_set_profiling(e, 1) (adds event records to the stream). */

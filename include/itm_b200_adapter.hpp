@@ -1,0 +1,325 @@
+// itm_b200_adapter.hpp - the B200 engines behind ITMLib's own engine interfaces.
+//
+// This header is compiled INSIDE the reference tree (it includes ITMLib headers); it is the code a
+// maintainer adds next to ITMLib/Engine/DeviceSpecific/{CPU,CUDA}/ to get a DEVICE_B200-style
+// engine set.  Every method forwards 1:1 to a function of the C ABI (include/itm_b200.h); nothing
+// of the path is computed here and there is no CPU fallback - a failing C call becomes
+// DIEWITHEXCEPTION (ORUtils/PlatformIndependence.h:34-38), like the reference's own error path.
+//
+//   reference interface (file:line)                                    -> adapter class below
+//   ITMSceneReconstructionEngine<TVoxel,TIndex>                        -> ITMSceneReconstructionEngine_B200
+//       (ITMLib/Engine/ITMSceneReconstructionEngine.h:29-52)
+//   ITMVisualisationEngine<TVoxel,TIndex> / IITMVisualisationEngine    -> ITMVisualisationEngine_B200
+//       (ITMLib/Engine/ITMVisualisationEngine.h:18-110)
+//   ITMDepthTracker (TrackCamera + ComputeGandH)                       -> ITMDepthTracker_B200
+//       (ITMLib/Engine/ITMDepthTracker.h:24-66)
+//   ITMLowLevelEngine::FilterSubsampleWithHoles(float)                 -> ITMLowLevelEngine_B200
+//       (ITMLib/Engine/ITMLowLevelEngine.h:16-34)
+//   ITMViewBuilder::UpdateView / ConvertDepthAffineToFloat             -> ITMViewBuilder_B200
+//       (ITMLib/Engine/ITMViewBuilder.h:19-60)
+//
+// All reference objects handed to these engines (ITMScene, ITMRenderState_VH, ITMTrackingState,
+// ITMView) must have been constructed with MEMORYDEVICE_CUDA / useGPU = true, exactly as the
+// reference's DEVICE_CUDA branch does (ITMMainEngine.cpp:17-18, ITMTrackingController.h:44): the
+// library borrows their device pointers for the duration of a call and never frees them.
+//
+// Only the voxel-block-hash index with ITMVoxel_s is supported (the north-star path); other
+// instantiations fail at compile time.
+#pragma once
+
+#include <string>
+
+#include "itm_b200.h"
+
+#include "ITMLib/Engine/ITMDepthTracker.h"
+#include "ITMLib/Engine/ITMLowLevelEngine.h"
+#include "ITMLib/Engine/ITMSceneReconstructionEngine.h"
+#include "ITMLib/Engine/ITMViewBuilder.h"
+#include "ITMLib/Engine/ITMVisualisationEngine.h"
+#include "ITMLib/Objects/ITMRenderState_VH.h"
+#include "ITMLib/Utils/ITMLibSettings.h"
+
+namespace ITMLib {
+namespace Engine {
+
+inline void itm_b200_check(int rc, const char *what) {
+  if (rc != ITM_B200_OK) {
+    static std::string msg;  // DIEWITHEXCEPTION keeps the pointer only until the throw
+    msg = std::string(what) + ": " + itm_b200_last_error();
+    DIEWITHEXCEPTION(msg.c_str());
+  }
+}
+
+/// One per engine set (= one scene): owns the library context, i.e. scratch memory and the stream.
+class ITMB200Context {
+ public:
+  itm_b200_ctx *ctx;
+  itm_b200_params params;
+
+  ITMB200Context(const ITMLibSettings *settings, const ITMRGBDCalib *calib, Vector2i imgSize_d, int device = 0) : ctx(NULL) {
+    itm_b200_default_params(&params, imgSize_d.x, imgSize_d.y);
+    const Vector4f &k = calib->intrinsics_d.projectionParamsSimple.all;
+    params.fx = k.x; params.fy = k.y; params.cx = k.z; params.cy = k.w;
+    const ITMSceneParams &sp = settings->sceneParams;
+    params.voxel_size = sp.voxelSize;
+    params.mu = sp.mu;
+    params.max_w = sp.maxW;
+    params.view_frustum_min = sp.viewFrustum_min;
+    params.view_frustum_max = sp.viewFrustum_max;
+    params.stop_integrating_at_max_w = sp.stopIntegratingAtMaxW ? 1 : 0;
+    params.depth_calib_a = calib->disparityCalib.params.x;
+    params.depth_calib_b = calib->disparityCalib.params.y;
+    params.sdf_local_block_num = SDF_LOCAL_BLOCK_NUM;
+    params.sdf_bucket_num = SDF_BUCKET_NUM;
+    params.sdf_excess_list_size = SDF_EXCESS_LIST_SIZE;
+    params.no_hierarchy_levels = settings->noHierarchyLevels;
+    for (int l = 0; l < settings->noHierarchyLevels && l < ITM_B200_MAX_LEVELS; ++l)
+      params.tracking_regime[l] = (int)settings->trackingRegime[l] + 1;  // enum order, ITMLibDefines.h:278-283
+    params.no_icp_run_till_level = settings->noICPRunTillLevel;
+    params.depth_tracker_icp_threshold = settings->depthTrackerICPThreshold;
+    params.depth_tracker_termination_threshold = settings->depthTrackerTerminationThreshold;
+    params.device = device;
+    itm_b200_check(itm_b200_ctx_create(&params, NULL, &ctx), "itm_b200_ctx_create");
+  }
+  ~ITMB200Context() { itm_b200_ctx_destroy(ctx); }
+
+ private:
+  ITMB200Context(const ITMB200Context &);
+  ITMB200Context &operator=(const ITMB200Context &);
+};
+
+namespace b200_detail {
+
+template <class TVoxel>
+inline itm_b200_scene scene_view(ITMScene<TVoxel, ITMVoxelBlockHash> *scene) {
+  itm_b200_scene s;
+  s.voxel_blocks_dev = scene->localVBA.GetVoxelBlocks();
+  s.hash_entries_dev = scene->index.GetEntries();
+  s.vba_allocation_list_dev = scene->localVBA.GetAllocationList();
+  s.excess_allocation_list_dev = scene->index.GetExcessAllocationList();
+  s.last_free_block_id = scene->localVBA.lastFreeBlockId;
+  s.last_free_excess_list_id = scene->index.GetLastFreeExcessListId();
+  return s;
+}
+
+inline itm_b200_render_state render_state_view(ITMRenderState_VH *rs) {
+  itm_b200_render_state r;
+  r.visible_entry_ids_dev = rs->GetVisibleEntryIDs();
+  r.entries_visible_type_dev = rs->GetEntriesVisibleType();
+  r.no_visible_entries = rs->noVisibleEntries;
+  r.rendering_range_image_dev = (float *)rs->renderingRangeImage->GetData(MEMORYDEVICE_CUDA);
+  r.raycast_result_dev = (float *)rs->raycastResult->GetData(MEMORYDEVICE_CUDA);
+  r.raycast_image_dev = (unsigned char *)rs->raycastImage->GetData(MEMORYDEVICE_CUDA);
+  return r;
+}
+
+inline itm_b200_tracking_state tracking_state_view(ITMTrackingState *ts) {
+  itm_b200_tracking_state t;
+  t.points_map_dev = (float *)ts->pointCloud->locations->GetData(MEMORYDEVICE_CUDA);
+  t.normals_map_dev = (float *)ts->pointCloud->colours->GetData(MEMORYDEVICE_CUDA);
+  for (int i = 0; i < 16; ++i) {
+    t.pose_d[i] = ts->pose_d->GetM().m[i];
+    t.pose_point_cloud[i] = ts->pose_pointCloud->GetM().m[i];
+  }
+  t.age_point_cloud = ts->age_pointCloud;
+  return t;
+}
+
+}  // namespace b200_detail
+
+// ---------------------------------------------------------------------------------------------
+template <class TVoxel, class TIndex>
+class ITMSceneReconstructionEngine_B200;  // only the voxel-block-hash specialisation exists
+
+template <class TVoxel>
+class ITMSceneReconstructionEngine_B200<TVoxel, ITMVoxelBlockHash> : public ITMSceneReconstructionEngine<TVoxel, ITMVoxelBlockHash> {
+  ITMB200Context *c;
+
+ public:
+  explicit ITMSceneReconstructionEngine_B200(ITMB200Context *context) : c(context) {
+    // the library reads and writes the reference's packed voxel directly
+    static_assert(sizeof(TVoxel) == 4 && !TVoxel::hasColorInformation, "libitm_b200: ITMVoxel_s only");
+  }
+
+  void ResetScene(ITMScene<TVoxel, ITMVoxelBlockHash> *scene) {
+    itm_b200_scene s = b200_detail::scene_view(scene);
+    itm_b200_check(itm_b200_reset_scene(c->ctx, &s), "ResetScene");
+    scene->localVBA.lastFreeBlockId = s.last_free_block_id;
+    scene->index.SetLastFreeExcessListId(s.last_free_excess_list_id);
+  }
+
+  void AllocateSceneFromDepth(ITMScene<TVoxel, ITMVoxelBlockHash> *scene, const ITMView *view, const ITMTrackingState *trackingState,
+                              const ITMRenderState *renderState, bool onlyUpdateVisibleList = false) {
+    if (scene->useSwapping) DIEWITHEXCEPTION("libitm_b200: swapping is not part of the fusion hot path");
+    ITMRenderState_VH *rsVH = (ITMRenderState_VH *)renderState;
+    itm_b200_scene s = b200_detail::scene_view(scene);
+    itm_b200_render_state r = b200_detail::render_state_view(rsVH);
+    itm_b200_check(itm_b200_allocate_scene_from_depth(c->ctx, &s, &r, view->depth->GetData(MEMORYDEVICE_CUDA),
+                                                      trackingState->pose_d->GetM().m, onlyUpdateVisibleList ? 1 : 0),
+                   "AllocateSceneFromDepth");
+    // host-visible counters other ITMLib code reads (ITMRenderState_VH.h:36, ITMLocalVBA.h:36, ITMVoxelBlockHash.h:83-84)
+    rsVH->noVisibleEntries = r.no_visible_entries;
+    scene->localVBA.lastFreeBlockId = s.last_free_block_id;
+    scene->index.SetLastFreeExcessListId(s.last_free_excess_list_id);
+  }
+
+  void IntegrateIntoScene(ITMScene<TVoxel, ITMVoxelBlockHash> *scene, const ITMView *view, const ITMTrackingState *trackingState,
+                          const ITMRenderState *renderState) {
+    itm_b200_scene s = b200_detail::scene_view(scene);
+    const itm_b200_render_state r = b200_detail::render_state_view((ITMRenderState_VH *)renderState);
+    itm_b200_check(itm_b200_integrate_into_scene(c->ctx, &s, &r, view->depth->GetData(MEMORYDEVICE_CUDA), trackingState->pose_d->GetM().m),
+                   "IntegrateIntoScene");
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+template <class TVoxel, class TIndex>
+class ITMVisualisationEngine_B200;
+
+template <class TVoxel>
+class ITMVisualisationEngine_B200<TVoxel, ITMVoxelBlockHash> : public ITMVisualisationEngine<TVoxel, ITMVoxelBlockHash> {
+  ITMB200Context *c;
+  typedef ITMScene<TVoxel, ITMVoxelBlockHash> Scene;
+
+ public:
+  ITMVisualisationEngine_B200(const Scene *scene, ITMB200Context *context) : ITMVisualisationEngine<TVoxel, ITMVoxelBlockHash>(scene), c(context) {}
+
+  ITMRenderState_VH *CreateRenderState(const Vector2i &imgSize) const {
+    return new ITMRenderState_VH(ITMVoxelBlockHash::noTotalEntries, imgSize, this->scene->sceneParams->viewFrustum_min,
+                                 this->scene->sceneParams->viewFrustum_max, MEMORYDEVICE_CUDA);
+  }
+
+  void CreateExpectedDepths(const ITMPose *pose, const ITMIntrinsics *intrinsics, ITMRenderState *renderState) const {
+    itm_b200_scene s = b200_detail::scene_view(const_cast<Scene *>(this->scene));
+    itm_b200_render_state r = b200_detail::render_state_view((ITMRenderState_VH *)renderState);
+    const Vector4f &k = intrinsics->projectionParamsSimple.all;
+    const float intr[4] = {k.x, k.y, k.z, k.w};
+    itm_b200_check(itm_b200_create_expected_depths(c->ctx, &s, &r, pose->GetM().m, intr), "CreateExpectedDepths");
+  }
+
+  void CreateICPMaps(const ITMView *view, ITMTrackingState *trackingState, ITMRenderState *renderState) const {
+    (void)view;
+    itm_b200_scene s = b200_detail::scene_view(const_cast<Scene *>(this->scene));
+    itm_b200_render_state r = b200_detail::render_state_view((ITMRenderState_VH *)renderState);
+    itm_b200_tracking_state t = b200_detail::tracking_state_view(trackingState);
+    itm_b200_check(itm_b200_create_icp_maps(c->ctx, &s, &r, &t), "CreateICPMaps");
+    trackingState->pose_pointCloud->SetFrom(trackingState->pose_d);  // ITMVisualisationEngine_CPU.cpp:273
+  }
+
+  // SURVEY.md 8f "next" rows: not on the fusion hot path, and there is no CPU fallback to hide behind.
+  void FindVisibleBlocks(const ITMPose *, const ITMIntrinsics *, ITMRenderState *) const { DIEWITHEXCEPTION("libitm_b200: FindVisibleBlocks not provided"); }
+  void RenderImage(const ITMPose *, const ITMIntrinsics *, const ITMRenderState *, ITMUChar4Image *, IITMVisualisationEngine::RenderImageType) const {
+    DIEWITHEXCEPTION("libitm_b200: RenderImage not provided");
+  }
+  void FindSurface(const ITMPose *, const ITMIntrinsics *, const ITMRenderState *) const { DIEWITHEXCEPTION("libitm_b200: FindSurface not provided"); }
+  void CreatePointCloud(const ITMView *, ITMTrackingState *, ITMRenderState *, bool) const { DIEWITHEXCEPTION("libitm_b200: CreatePointCloud not provided"); }
+  void ForwardRender(const ITMView *, ITMTrackingState *, ITMRenderState *) const { DIEWITHEXCEPTION("libitm_b200: ForwardRender not provided"); }
+};
+
+// ---------------------------------------------------------------------------------------------
+class ITMLowLevelEngine_B200 : public ITMLowLevelEngine {
+  ITMB200Context *c;
+
+ public:
+  explicit ITMLowLevelEngine_B200(ITMB200Context *context) : c(context) {}
+
+  void FilterSubsampleWithHoles(ITMFloatImage *image_out, const ITMFloatImage *image_in) const {
+    const Vector2i in = image_in->noDims;
+    image_out->ChangeDims(Vector2i(in.x / 2, in.y / 2));  // ITMLowLevelEngine_CPU.cpp:52-54
+    itm_b200_check(itm_b200_filter_subsample_with_holes(c->ctx, image_out->GetData(MEMORYDEVICE_CUDA), image_in->GetData(MEMORYDEVICE_CUDA), in.x, in.y),
+                   "FilterSubsampleWithHoles");
+  }
+
+  // colour-tracker helpers: not on the depth-ICP path
+  void CopyImage(ITMUChar4Image *, const ITMUChar4Image *) const { DIEWITHEXCEPTION("libitm_b200: CopyImage not provided"); }
+  void CopyImage(ITMFloatImage *, const ITMFloatImage *) const { DIEWITHEXCEPTION("libitm_b200: CopyImage not provided"); }
+  void CopyImage(ITMFloat4Image *, const ITMFloat4Image *) const { DIEWITHEXCEPTION("libitm_b200: CopyImage not provided"); }
+  void FilterSubsample(ITMUChar4Image *, const ITMUChar4Image *) const { DIEWITHEXCEPTION("libitm_b200: FilterSubsample not provided"); }
+  void FilterSubsampleWithHoles(ITMFloat4Image *, const ITMFloat4Image *) const { DIEWITHEXCEPTION("libitm_b200: FilterSubsampleWithHoles(float4) not provided"); }
+  void GradientX(ITMShort4Image *, const ITMUChar4Image *) const { DIEWITHEXCEPTION("libitm_b200: GradientX not provided"); }
+  void GradientY(ITMShort4Image *, const ITMUChar4Image *) const { DIEWITHEXCEPTION("libitm_b200: GradientY not provided"); }
+};
+
+// ---------------------------------------------------------------------------------------------
+class ITMViewBuilder_B200 : public ITMViewBuilder {
+  ITMB200Context *c;
+
+ public:
+  ITMViewBuilder_B200(const ITMRGBDCalib *calib, ITMB200Context *context) : ITMViewBuilder(calib), c(context) {}
+
+  void ConvertDepthAffineToFloat(ITMFloatImage *depth_out, const ITMShortImage *depth_in, Vector2f depthCalibParams) {
+    itm_b200_check(itm_b200_convert_depth_affine_to_float(c->ctx, depth_out->GetData(MEMORYDEVICE_CUDA), depth_in->GetData(MEMORYDEVICE_CUDA),
+                                                          depth_in->noDims.x, depth_in->noDims.y, depthCalibParams.x, depthCalibParams.y),
+                   "ConvertDepthAffineToFloat");
+  }
+
+  // same sequence as ITMViewBuilder_CPU::UpdateView (ITMViewBuilder_CPU.cpp:14-64) with the images in HBM
+  void UpdateView(ITMView **view_ptr, ITMUChar4Image *rgbImage, ITMShortImage *rawDepthImage, bool useBilateralFilter, bool modelSensorNoise = false) {
+    if (useBilateralFilter || modelSensorNoise) DIEWITHEXCEPTION("libitm_b200: bilateral filter / sensor-noise model not provided");
+    if (*view_ptr == NULL) {
+      *view_ptr = new ITMView(calib, rgbImage->noDims, rawDepthImage->noDims, true);
+      if (this->shortImage != NULL) delete this->shortImage;
+      this->shortImage = new ITMShortImage(rawDepthImage->noDims, true, true);
+    }
+    ITMView *view = *view_ptr;
+    view->rgb->SetFrom(rgbImage, ORUtils::MemoryBlock<Vector4u>::CPU_TO_CUDA);
+    this->shortImage->SetFrom(rawDepthImage, ORUtils::MemoryBlock<short>::CPU_TO_CUDA);
+    if (view->calib->disparityCalib.type != ITMDisparityCalib::TRAFO_AFFINE) DIEWITHEXCEPTION("libitm_b200: only TRAFO_AFFINE depth is provided");
+    this->ConvertDepthAffineToFloat(view->depth, this->shortImage, view->calib->disparityCalib.params);
+  }
+
+  void ConvertDisparityToDepth(ITMFloatImage *, const ITMShortImage *, const ITMIntrinsics *, Vector2f) { DIEWITHEXCEPTION("libitm_b200: ConvertDisparityToDepth not provided"); }
+  void DepthFiltering(ITMFloatImage *, const ITMFloatImage *) { DIEWITHEXCEPTION("libitm_b200: DepthFiltering not provided"); }
+  void ComputeNormalAndWeights(ITMFloat4Image *, ITMFloatImage *, const ITMFloatImage *, Vector4f) { DIEWITHEXCEPTION("libitm_b200: ComputeNormalAndWeights not provided"); }
+  void UpdateView(ITMView **, ITMUChar4Image *, ITMFloatImage *) { DIEWITHEXCEPTION("libitm_b200: UpdateView(float depth) not provided"); }
+  void UpdateView(ITMView **, ITMUChar4Image *, ITMShortImage *, bool, ITMIMUMeasurement *) { DIEWITHEXCEPTION("libitm_b200: UpdateView(imu) not provided"); }
+};
+
+// ---------------------------------------------------------------------------------------------
+/// ITMDepthTracker with (a) the whole Levenberg-Marquardt loop of TrackCamera on the device and
+/// (b) ComputeGandH as a single-evaluation entry point, so the base class' own host loop
+/// (ITMDepthTracker.cpp:145-199) also works on top of it (set useDeviceLoop = false).
+class ITMDepthTracker_B200 : public ITMDepthTracker {
+  ITMB200Context *c;
+
+ public:
+  bool useDeviceLoop;
+
+  ITMDepthTracker_B200(Vector2i imgSize, TrackerIterationType *trackingRegime, int noHierarchyLevels, int noICPRunTillLevel, float distThresh,
+                       float terminationThreshold, const ITMLowLevelEngine *lowLevelEngine, ITMB200Context *context)
+      : ITMDepthTracker(imgSize, trackingRegime, noHierarchyLevels, noICPRunTillLevel, distThresh, terminationThreshold, lowLevelEngine, MEMORYDEVICE_CUDA),
+        c(context), useDeviceLoop(true) {}
+
+  void TrackCamera(ITMTrackingState *trackingState, const ITMView *view) {
+    if (!useDeviceLoop) {
+      ITMDepthTracker::TrackCamera(trackingState, view);
+      return;
+    }
+    itm_b200_tracking_state t = b200_detail::tracking_state_view(trackingState);
+    itm_b200_check(itm_b200_track_camera(c->ctx, view->depth->GetData(MEMORYDEVICE_CUDA), &t), "TrackCamera");
+    Matrix4f M;
+    for (int i = 0; i < 16; ++i) M.m[i] = t.pose_d[i];
+    trackingState->pose_d->SetM(M);  // already coerced on the device (ITMDepthTracker.cpp:194-196)
+  }
+
+ protected:
+  int ComputeGandH(float &f, float *nabla, float *hessian, Matrix4f approxInvPose) {
+    const Vector4f &vk = viewHierarchyLevel->intrinsics, &sk = sceneHierarchyLevel->intrinsics;
+    const float viewIntr[4] = {vk.x, vk.y, vk.z, vk.w}, sceneIntr[4] = {sk.x, sk.y, sk.z, sk.w};
+    const Vector2i viewSize = viewHierarchyLevel->depth->noDims, sceneSize = sceneHierarchyLevel->pointsMap->noDims;
+    int noValid = 0;
+    float h36[36];
+    itm_b200_check(itm_b200_compute_g_and_h(c->ctx, viewHierarchyLevel->depth->GetData(MEMORYDEVICE_CUDA), viewSize.x, viewSize.y, viewIntr,
+                                            (const float *)sceneHierarchyLevel->pointsMap->GetData(MEMORYDEVICE_CUDA),
+                                            (const float *)sceneHierarchyLevel->normalsMap->GetData(MEMORYDEVICE_CUDA), sceneSize.x, sceneSize.y,
+                                            sceneIntr, approxInvPose.m, scenePose.m, distThresh[levelId], (int)iterationType + 1, &f, nabla, h36,
+                                            &noValid),
+                   "ComputeGandH");
+    // stride 6 for 3- and 6-parameter iterations alike (ITMDepthTracker_CPU.cpp:72-73)
+    for (int i = 0; i < 36; ++i) hessian[i] = h36[i];
+    return noValid;
+  }
+};
+
+}  // namespace Engine
+}  // namespace ITMLib

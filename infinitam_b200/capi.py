@@ -74,7 +74,7 @@ SYMBOLS = [
     "itm_b200_engine_process_frame", "itm_b200_engine_enqueue_frame_dev", "itm_b200_engine_sync",
     "itm_b200_engine_upload_depth", "itm_b200_engine_run_stage", "itm_b200_engine_get_buffer",
     "itm_b200_engine_read_buffer", "itm_b200_engine_write_buffer", "itm_b200_engine_get_state",
-    "itm_b200_engine_set_state", "itm_b200_engine_set_profiling", "itm_b200_engine_stage_times",
+    "itm_b200_engine_set_state", "itm_b200_engine_icp_stats", "itm_b200_engine_set_profiling", "itm_b200_engine_stage_times",
     "itm_b200_mat4_inv", "itm_b200_pose_from_inv_m_coerced", "itm_b200_compute_delta",
 ]
 
@@ -128,6 +128,7 @@ def load():
     lib.itm_b200_engine_write_buffer.argtypes = [vp, C.c_int, vp, C.c_size_t, C.c_size_t]
     lib.itm_b200_engine_get_state.argtypes = [vp, f32p, f32p, i32p]
     lib.itm_b200_engine_set_state.argtypes = [vp, f32p, f32p, i32p]
+    lib.itm_b200_engine_icp_stats.argtypes = [vp, i32p]
     lib.itm_b200_engine_set_profiling.argtypes = [vp, C.c_int]
     lib.itm_b200_engine_stage_times.argtypes = [vp, f32p]
     lib.itm_b200_mat4_inv.argtypes = [f32p, f32p]

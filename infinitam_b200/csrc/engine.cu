@@ -924,6 +924,12 @@ int itm_b200_engine_set_state(itm_b200_engine *e, const float pose_d[16], const 
   return ITM_B200_OK;
 }
 
+int itm_b200_engine_icp_stats(itm_b200_engine *e, int evals_per_level[ITM_B200_MAX_LEVELS]) {
+  if (!e || !evals_per_level) return fail(ITM_B200_EINVAL, "NULL argument");
+  for (int l = 0; l < ITM_B200_MAX_LEVELS; ++l) evals_per_level[l] = e->c->hst->icp.levelEvals[l];
+  return ITM_B200_OK;
+}
+
 int itm_b200_engine_set_profiling(itm_b200_engine *e, int on) {
   if (!e) return fail(ITM_B200_EINVAL, "NULL engine");
   e->profiling = on != 0;

@@ -184,12 +184,13 @@ struct LmShared {
   float Hgood[36], ngood[6];
   float fOld, lambda;
   int evalCount;
+  int levelEvals[ITM_MAX_LEVELS];
 };
 
 // The LM bookkeeping of one iteration, ITMDepthTracker.cpp:167-197.  Run by one thread; noPara is a template
 // parameter so that every array index is static and the 6x6 system lives in registers.  Returns HasConverged().
 template <int noPara>
-__device__ bool lm_update(LmShared &L, const float *sSums, int iterationType, bool firstIterOfLevel, float terminationThreshold) {
+__device__ bool lm_update(LmShared &L, const float *sSums, int iterationType, int level, bool firstIterOfLevel, float terminationThreshold) {
   float M_d[16], params[6], approxInvPose[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) M_d[i] = L.M_d[i];
@@ -208,6 +209,7 @@ __device__ bool lm_update(LmShared &L, const float *sSums, int iterationType, bo
   const int noValid = (int)sSums[0];
   const float fNew = (noValid > 100) ? sqrtf(sSums[1]) / (float)noValid : 1e5f;
   L.evalCount++;
+  L.levelEvals[level]++;
 
   float Hgood[36], ngood[6];
   if ((noValid <= 0) || (fNew > fOld)) {
@@ -330,6 +332,7 @@ __global__ void __launch_bounds__(ICP_THREADS, 2) k_icp_track(TrackArgs t) {
     // hessian_good / nabla_good are uninitialised stack variables in the reference (:151-153); start from zero
     if (threadIdx.x >= 32 && threadIdx.x < 68) L.Hgood[threadIdx.x - 32] = 0.0f;
     if (threadIdx.x == 0) { L.fOld = 1e10f; L.lambda = 1.0f; L.evalCount = 0; }
+    if (threadIdx.x >= 96 && threadIdx.x < 96 + ITM_MAX_LEVELS) L.levelEvals[threadIdx.x - 96] = 0;
   }
   __syncthreads();
   unsigned seq = sRelease >> 1;
@@ -375,8 +378,8 @@ __global__ void __launch_bounds__(ICP_THREADS, 2) k_icp_track(TrackArgs t) {
         __syncthreads();
         if (threadIdx.x == 0) {
           TRACE(evalNo, 3);
-          const bool conv = (NV == 11) ? lm_update<3>(L, sSums, type, it == 0, t.a.terminationThreshold)
-                                       : lm_update<6>(L, sSums, type, it == 0, t.a.terminationThreshold);
+          const bool conv = (NV == 11) ? lm_update<3>(L, sSums, type, level, it == 0, t.a.terminationThreshold)
+                                       : lm_update<6>(L, sSums, type, level, it == 0, t.a.terminationThreshold);
           TRACE(evalNo, 4);
           TRACE_VAL(evalNo, 6, level);
           const bool lastOfLevel = conv || it == t.iters[level] - 1;
@@ -408,6 +411,8 @@ __global__ void __launch_bounds__(ICP_THREADS, 2) k_icp_track(TrackArgs t) {
 #pragma unroll
     for (int i = 0; i < 6; ++i) st->poseParams[i] = L.params[i];
     st->icp.evalCount = L.evalCount;
+#pragma unroll
+    for (int i = 0; i < ITM_MAX_LEVELS; ++i) st->icp.levelEvals[i] = L.levelEvals[i];
     TRACE(63, 1);
   }
 }

@@ -121,6 +121,12 @@ class ITMMainEngine:
         capi.check(self.lib.itm_b200_engine_set_state(
             self.h, None if p is None else _f32p(p), None if q is None else _f32p(q), None if s is None else _i32p(s)))
 
+    def icp_stats(self):
+        """ComputeGandH evaluations per pyramid level in the last synced frame (level 0 = full resolution)"""
+        n = np.zeros(capi.MAX_LEVELS, np.int32)
+        capi.check(self.lib.itm_b200_engine_icp_stats(self.h, _i32p(n)))
+        return n
+
     def set_profiling(self, on=True):
         capi.check(self.lib.itm_b200_engine_set_profiling(self.h, int(on)))
 

@@ -1,0 +1,76 @@
+"""ctypes view of oracle/_ref/libitm_adapter.so: the reference's own host objects (CUDA memory) driven through
+include/itm_b200_adapter.hpp and the C ABI of libitm_b200.so (oracle/adapter_harness.cpp).
+
+TEST INFRASTRUCTURE.  Only tests/ may import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .ref import HASH_ENTRY_DTYPE
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "_ref", "libitm_adapter.so")
+
+(READ_HASH, READ_VOXELS, READ_VISIBLE_IDS, READ_RAYCAST, READ_POINTS, READ_NORMALS, READ_VISIBLE_TYPES) = range(7)
+_DTYPES = {READ_HASH: HASH_ENTRY_DTYPE, READ_VOXELS: np.uint32, READ_VISIBLE_IDS: np.int32, READ_RAYCAST: np.float32,
+           READ_POINTS: np.float32, READ_NORMALS: np.float32, READ_VISIBLE_TYPES: np.uint8}
+
+
+def available() -> bool:
+    return os.path.exists(LIB)
+
+
+class AdapterEngine:
+    """ITMMainEngine::ProcessFrame composed from reference host objects + the B200 adapter engines."""
+
+    def __init__(self, w, h, intr=None, voxel_size=0.005, mu=0.02, max_w=100, vf_min=0.35, vf_max=3.0, device_loop=True):
+        lib = C.CDLL(LIB)
+        lib.adp_create.restype = C.c_void_p
+        lib.adp_create.argtypes = [C.c_int, C.c_int] + [C.c_float] * 6 + [C.c_int, C.c_float, C.c_float, C.c_int]
+        lib.adp_destroy.argtypes = [C.c_void_p]
+        lib.adp_process_frame.argtypes = [C.c_void_p, C.c_void_p]
+        lib.adp_get_pose.argtypes = [C.c_void_p, C.c_void_p]
+        lib.adp_counters.argtypes = [C.c_void_p, C.c_void_p]
+        lib.adp_read.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong]
+        lib.adp_read.restype = C.c_longlong
+        lib.adp_last_error.restype = C.c_char_p
+        self.lib, self.W, self.H = lib, w, h
+        s = w / 640.0
+        fx, fy, cx, cy = intr if intr is not None else (580.0 * s, 580.0 * s, w / 2.0, h / 2.0)
+        self.h = lib.adp_create(w, h, fx, fy, cx, cy, voxel_size, mu, max_w, vf_min, vf_max, int(device_loop))
+        if not self.h:
+            raise RuntimeError("adp_create failed: %s" % lib.adp_last_error().decode())
+
+    def close(self):
+        if self.h:
+            self.lib.adp_destroy(self.h)
+            self.h = None
+
+    def process_frame(self, depth_i16):
+        d = np.ascontiguousarray(depth_i16, np.int16)
+        if self.lib.adp_process_frame(self.h, d.ctypes.data) != 0:
+            raise RuntimeError("adp_process_frame: %s" % self.lib.adp_last_error().decode())
+
+    @property
+    def pose_M(self):
+        m = np.zeros(16, np.float32)
+        self.lib.adp_get_pose(self.h, m.ctypes.data)
+        return m
+
+    @property
+    def counters(self):
+        c = np.zeros(4, np.int32)
+        self.lib.adp_counters(self.h, c.ctypes.data)
+        return c
+
+    def read(self, which):
+        need = -self.lib.adp_read(self.h, which, None, 0)
+        out = np.empty(need // np.dtype(_DTYPES[which]).itemsize, dtype=_DTYPES[which])
+        got = self.lib.adp_read(self.h, which, out.ctypes.data, need)
+        if got != need:
+            raise RuntimeError("adp_read(%d) failed" % which)
+        return out

@@ -1,0 +1,168 @@
+// oracle/adapter_harness.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// Drop-in proof: the reference's OWN host objects (ITMScene, ITMRenderState_VH, ITMTrackingState,
+// ITMView, ITMTrackingController, ITMDepthTracker's host LM loop, ITMPose - compiled from
+// /root/reference/InfiniTAM where they lie, with CUDA memory exactly as the reference's
+// DEVICE_CUDA branch allocates it) driven through the adapter classes of
+// include/itm_b200_adapter.hpp, i.e. through the C ABI of libitm_b200.so.  The composition mirrors
+// ITMMainEngine's constructor and ProcessFrame (ITMLib/Engine/ITMMainEngine.cpp:17-68, 111-127)
+// and ITMDenseMapper::ProcessFrame (ITMLib/Engine/ITMDenseMapper.cpp:51-65); the only change a
+// maintainer makes is which engine classes are constructed.
+//
+// Built by oracle/build_ref.py into oracle/_ref/libitm_adapter.so; loaded only by tests/.
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+#include <cuda_runtime.h>
+
+#include "ITMLib/Engine/ITMTrackingController.h"
+#include "itm_b200_adapter.hpp"
+
+using namespace ITMLib::Engine;
+using namespace ITMLib::Objects;
+
+typedef ITMVoxel TV;
+typedef ITMVoxelIndex TI;
+
+struct adp_engine {
+  ITMLibSettings *settings;
+  ITMRGBDCalib calib;
+  ITMB200Context *ctx;
+  ITMScene<TV, TI> *scene;
+  ITMLowLevelEngine_B200 *lowLevel;
+  ITMViewBuilder_B200 *viewBuilder;
+  ITMVisualisationEngine_B200<TV, TI> *vis;
+  ITMSceneReconstructionEngine_B200<TV, TI> *reco;
+  ITMDepthTracker_B200 *tracker;
+  ITMTrackingController *controller;
+  ITMTrackingState *trackingState;
+  ITMRenderState *renderState;
+  ITMView *view;
+  ITMUChar4Image *rgb;
+  ITMShortImage *rawDepth;
+  Vector2i imgSize;
+};
+
+static std::string g_err;
+
+extern "C" {
+
+const char *adp_last_error() { return g_err.c_str(); }
+
+adp_engine *adp_create(int W, int H, float fx, float fy, float cx, float cy, float voxelSize, float mu, int maxW, float vfMin, float vfMax,
+                       int deviceLoop) {
+  try {
+    adp_engine *e = new adp_engine();
+    e->settings = new ITMLibSettings();
+    e->settings->deviceType = ITMLibSettings::DEVICE_CUDA;  // memory placement of every reference object below
+    e->settings->trackerType = ITMLibSettings::TRACKER_ICP;
+    e->settings->useSwapping = false;
+    e->settings->useApproximateRaycast = false;
+    e->settings->useBilateralFilter = false;
+    e->settings->modelSensorNoise = false;
+    e->settings->sceneParams.voxelSize = voxelSize;
+    e->settings->sceneParams.mu = mu;
+    e->settings->sceneParams.maxW = maxW;
+    e->settings->sceneParams.viewFrustum_min = vfMin;
+    e->settings->sceneParams.viewFrustum_max = vfMax;
+    e->imgSize = Vector2i(W, H);
+    e->calib.intrinsics_d.SetFrom(fx, fy, cx, cy, (float)W, (float)H);
+    e->calib.intrinsics_rgb.SetFrom(fx, fy, cx, cy, (float)W, (float)H);
+    e->calib.disparityCalib.SetFrom(1.0f / 1000.0f, 0.0f, ITMDisparityCalib::TRAFO_AFFINE);
+
+    // ITMMainEngine::ITMMainEngine (ITMMainEngine.cpp:17-68) with the B200 engine set
+    e->ctx = new ITMB200Context(e->settings, &e->calib, e->imgSize);
+    e->scene = new ITMScene<TV, TI>(&e->settings->sceneParams, false, MEMORYDEVICE_CUDA);
+    e->lowLevel = new ITMLowLevelEngine_B200(e->ctx);
+    e->viewBuilder = new ITMViewBuilder_B200(&e->calib, e->ctx);
+    e->vis = new ITMVisualisationEngine_B200<TV, TI>(e->scene, e->ctx);
+    e->reco = new ITMSceneReconstructionEngine_B200<TV, TI>(e->ctx);
+    e->renderState = e->vis->CreateRenderState(e->imgSize);
+    e->reco->ResetScene(e->scene);
+    e->tracker = new ITMDepthTracker_B200(e->imgSize, e->settings->trackingRegime, e->settings->noHierarchyLevels, e->settings->noICPRunTillLevel,
+                                          e->settings->depthTrackerICPThreshold, e->settings->depthTrackerTerminationThreshold, e->lowLevel, e->ctx);
+    e->tracker->useDeviceLoop = deviceLoop != 0;
+    e->controller = new ITMTrackingController(e->tracker, e->vis, e->lowLevel, e->settings);
+    e->trackingState = e->controller->BuildTrackingState(e->imgSize);
+    e->tracker->UpdateInitialPose(e->trackingState);
+    e->view = NULL;
+    e->rgb = new ITMUChar4Image(e->imgSize, true, false);
+    e->rawDepth = new ITMShortImage(e->imgSize, true, false);
+    memset(e->rgb->GetData(MEMORYDEVICE_CPU), 128, (size_t)W * H * 4);
+    return e;
+  } catch (std::exception &ex) {
+    g_err = ex.what();
+    return NULL;
+  }
+}
+
+void adp_destroy(adp_engine *e) {
+  if (!e) return;
+  delete e->renderState;
+  delete e->scene;
+  delete e->controller;
+  delete e->tracker;
+  delete e->lowLevel;
+  delete e->viewBuilder;
+  delete e->trackingState;
+  if (e->view) delete e->view;
+  delete e->vis;
+  delete e->reco;
+  delete e->rgb;
+  delete e->rawDepth;
+  delete e->ctx;
+  delete e->settings;
+  delete e;
+}
+
+// ITMMainEngine::ProcessFrame (ITMMainEngine.cpp:111-127)
+int adp_process_frame(adp_engine *e, const short *depth) {
+  try {
+    memcpy(e->rawDepth->GetData(MEMORYDEVICE_CPU), depth, (size_t)e->imgSize.x * e->imgSize.y * sizeof(short));
+    e->viewBuilder->UpdateView(&e->view, e->rgb, e->rawDepth, e->settings->useBilateralFilter, e->settings->modelSensorNoise);
+    e->controller->Track(e->trackingState, e->view);
+    // ITMDenseMapper::ProcessFrame (ITMDenseMapper.cpp:51-65)
+    e->reco->AllocateSceneFromDepth(e->scene, e->view, e->trackingState, e->renderState);
+    e->reco->IntegrateIntoScene(e->scene, e->view, e->trackingState, e->renderState);
+    e->controller->Prepare(e->trackingState, e->view, e->renderState);
+    return 0;
+  } catch (std::exception &ex) {
+    g_err = ex.what();
+    return -1;
+  }
+}
+
+void adp_get_pose(adp_engine *e, float *M16) { memcpy(M16, e->trackingState->pose_d->GetM().m, 64); }
+
+// counters = {noVisibleEntries, lastFreeBlockId, lastFreeExcessListId, age_pointCloud}
+void adp_counters(adp_engine *e, int *c4) {
+  c4[0] = ((ITMRenderState_VH *)e->renderState)->noVisibleEntries;
+  c4[1] = e->scene->localVBA.lastFreeBlockId;
+  c4[2] = e->scene->index.GetLastFreeExcessListId();
+  c4[3] = e->trackingState->age_pointCloud;
+}
+
+// which: 0 hash entries, 1 voxel blocks, 2 visible ids, 3 raycast result, 4 points map, 5 normals map, 6 entriesVisibleType
+long long adp_read(adp_engine *e, int which, void *dst, long long capacity) {
+  const size_t P = (size_t)e->imgSize.x * e->imgSize.y;
+  const void *src = NULL;
+  size_t bytes = 0;
+  ITMRenderState_VH *rs = (ITMRenderState_VH *)e->renderState;
+  switch (which) {
+    case 0: src = e->scene->index.GetEntries(); bytes = (size_t)ITMVoxelBlockHash::noTotalEntries * sizeof(ITMHashEntry); break;
+    case 1: src = e->scene->localVBA.GetVoxelBlocks(); bytes = (size_t)e->scene->localVBA.allocatedSize * sizeof(TV); break;
+    case 2: src = rs->GetVisibleEntryIDs(); bytes = (size_t)SDF_LOCAL_BLOCK_NUM * sizeof(int); break;
+    case 3: src = rs->raycastResult->GetData(MEMORYDEVICE_CUDA); bytes = P * 16; break;
+    case 4: src = e->trackingState->pointCloud->locations->GetData(MEMORYDEVICE_CUDA); bytes = P * 16; break;
+    case 5: src = e->trackingState->pointCloud->colours->GetData(MEMORYDEVICE_CUDA); bytes = P * 16; break;
+    case 6: src = rs->GetEntriesVisibleType(); bytes = (size_t)ITMVoxelBlockHash::noTotalEntries; break;
+    default: return -1;
+  }
+  if ((long long)bytes > capacity) return -(long long)bytes;
+  if (cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return (long long)bytes;
+}
+
+}  // extern "C"

@@ -16,6 +16,11 @@ oracle/_ref/:
                       binary is built here and executed on the GPU box's host)
   libitm_ref_fast1.so timing flavour, serial (-O3 -mavx2 -mfma, no OpenMP)
 
+  libitm_adapter.so   drop-in proof: the reference's own host objects (scene, render state,
+                      tracking state, view, tracking controller, ITMDepthTracker's host loop,
+                      ITMPose) compiled WITH CUDA memory placement, driven through
+                      include/itm_b200_adapter.hpp -> libitm_b200.so (oracle/adapter_harness.cpp)
+
 oracle/_ref/ is git-ignored but travels to the GPU box with gpurun.
 """
 import os
@@ -83,6 +88,46 @@ def build(flavours=None, force=False):
     return True
 
 
+ADAPTER_SOURCES = [
+    "ITMLib/Objects/ITMPose.cpp",
+    "ITMLib/Utils/ITMLibSettings.cpp",
+    "ITMLib/Engine/ITMDepthTracker.cpp",
+    "ITMLib/Engine/ITMTrackingController.cpp",
+]
+
+
+def build_adapter(force=False):
+    """reference host objects + include/itm_b200_adapter.hpp, linked against infinitam_b200/libitm_b200.so"""
+    repo = os.path.dirname(HERE)
+    product = os.path.join(repo, "infinitam_b200", "libitm_b200.so")
+    if not available() or not os.path.exists(product):
+        return False
+    os.makedirs(OUT, exist_ok=True)
+    harness = os.path.join(HERE, "adapter_harness.cpp")
+    header = os.path.join(repo, "include", "itm_b200_adapter.hpp")
+    target = os.path.join(OUT, "libitm_adapter.so")
+    deps = [harness, header, os.path.join(repo, "include", "itm_b200.h"), __file__]
+    if not force and os.path.exists(target) and all(os.path.getmtime(target) > os.path.getmtime(d) for d in deps):
+        return True
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    objdir = os.path.join(OUT, "obj_adapter")
+    os.makedirs(objdir, exist_ok=True)
+    common = ["-std=c++11", "-fPIC", "-w", "-O2", "-ffp-contract=off", "-include", "iostream", "-I" + os.path.join(HERE, "shim"),
+              "-I" + REF, "-I" + os.path.join(repo, "include"), "-I" + os.path.join(cuda, "include")]
+    jobs = []
+    for src in ADAPTER_SOURCES + [harness]:
+        path = src if os.path.isabs(src) else os.path.join(REF, src)
+        obj = os.path.join(objdir, os.path.basename(src).replace(".cpp", ".o"))
+        jobs.append((["g++"] + common + ["-c", path, "-o", obj], obj))
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
+        list(ex.map(lambda j: subprocess.check_call(j[0]), jobs))
+    subprocess.check_call(["g++", "-shared", "-o", target] + [j[1] for j in jobs] + [
+        "-L" + os.path.dirname(product), "-litm_b200", "-L" + os.path.join(cuda, "lib64"), "-lcudart",
+        "-Wl,-rpath,$ORIGIN/../../infinitam_b200", "-Wl,-rpath," + os.path.join(cuda, "lib64")])
+    return True
+
+
 if __name__ == "__main__":
     ok = build(force="--force" in sys.argv)
+    build_adapter(force="--force" in sys.argv)
     print("built" if ok else "reference not present; nothing built")

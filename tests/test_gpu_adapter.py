@@ -1,0 +1,56 @@
+"""-m gpu: the drop-in boundary end to end.  The reference's own host objects (ITMScene, ITMRenderState_VH,
+ITMTrackingState, ITMView, ITMTrackingController, ITMPose - compiled from the reference sources with CUDA memory
+placement) run ITMMainEngine::ProcessFrame through include/itm_b200_adapter.hpp -> libitm_b200.so, and are compared
+with the reference's CPU engines on the same frames (oracle/adapter_harness.cpp vs oracle/ref_harness.cpp)."""
+import numpy as np
+import pytest
+
+import parity
+from infinitam_b200 import synth
+from oracle import adapter, ref
+
+pytestmark = pytest.mark.gpu
+
+needs_libs = pytest.mark.skipif(not (adapter.available() and ref.available("parity")),
+                                reason="oracle/_ref not built (needs /root/reference at build time)")
+
+
+def _exact_scene_checks(o, a):
+    """hash table and visible list bit exact, voxels within 1 LSB, raycast / ICP maps within 1e-4 m"""
+    assert [int(x) for x in a.counters] == [int(x) for x in o.counters] + [int(o.age)]
+    assert parity.hash_equal(a.read(adapter.READ_HASH), o.hash_entries)
+    n_vis = int(o.counters[0])
+    assert np.array_equal(np.sort(a.read(adapter.READ_VISIBLE_IDS)[:n_vis]), np.sort(o.visible_ids[:n_vis]))
+    assert np.array_equal(a.read(adapter.READ_VISIBLE_TYPES), o.visible_types)
+    ds, dw, _, _ = parity.voxel_diff(a.read(adapter.READ_VOXELS), o.voxels)
+    assert ds <= 1 and dw <= 1
+    ray_a, ray_o = a.read(adapter.READ_RAYCAST).reshape(o.H, o.W, 4), o.raycast_result
+    assert np.array_equal(ray_a[..., 3] > 0, ray_o[..., 3] > 0)
+    assert np.abs(ray_a[..., :3] - ray_o[..., :3]).max() * o.voxel_size <= 1e-4
+    pts_a, nrm_a = a.read(adapter.READ_POINTS).reshape(o.H, o.W, 4), a.read(adapter.READ_NORMALS).reshape(o.H, o.W, 4)
+    assert np.array_equal(pts_a[..., 3], o.points[..., 3])
+    assert np.abs(pts_a - o.points).max() <= 1e-4 and np.abs(nrm_a - o.normals).max() <= 1e-3
+
+
+@needs_libs
+@pytest.mark.parametrize("device_loop", [True, False], ids=["device-LM-loop", "reference-host-LM-loop+ComputeGandH"])
+def test_reference_host_objects_with_b200_engines(device_loop):
+    w, h, n = 320, 240, 6
+    seq = synth.sequence(n, w, h)
+    o = ref.RefEngine(w, h)
+    a = adapter.AdapterEngine(w, h, intr=o.intr, device_loop=device_loop)
+    # frame 0 runs at the identity pose on both sides: everything downstream of it must agree exactly
+    o.process_frame(seq[0])
+    a.process_frame(seq[0])
+    assert np.array_equal(a.pose_M, o.pose_M)
+    _exact_scene_checks(o, a)
+    # free running from here on: each side tracks against its own maps
+    for k in range(1, n):
+        o.process_frame(seq[k])
+        a.process_frame(seq[k])
+        rot, trans = parity.pose_diff(a.pose_M, o.pose_M)
+        assert rot <= 1e-4 and trans <= 1e-4, "frame %d pose differs: %g rad %g m" % (k, rot, trans)
+        ca, co = a.counters, o.counters
+        assert abs(int(ca[0]) - int(co[0])) <= 0.01 * co[0] and abs(int(ca[1]) - int(co[1])) <= 0.01 * (o.n_local - co[1])
+        assert int(ca[3]) == int(o.age)
+    a.close(); o.close()
