@@ -74,7 +74,7 @@ class ITMB200Context {
     params.sdf_excess_list_size = SDF_EXCESS_LIST_SIZE;
     params.no_hierarchy_levels = settings->noHierarchyLevels;
     for (int l = 0; l < settings->noHierarchyLevels && l < ITM_B200_MAX_LEVELS; ++l)
-      params.tracking_regime[l] = (int)settings->trackingRegime[l] + 1;  // enum order, ITMLibDefines.h:278-283
+      params.tracking_regime[l] = (int)settings->trackingRegime[l];  // same numeric values, ITMLibDefines.h:278-283
     params.no_icp_run_till_level = settings->noICPRunTillLevel;
     params.depth_tracker_icp_threshold = settings->depthTrackerICPThreshold;
     params.depth_tracker_termination_threshold = settings->depthTrackerTerminationThreshold;
@@ -312,7 +312,7 @@ class ITMDepthTracker_B200 : public ITMDepthTracker {
     itm_b200_check(itm_b200_compute_g_and_h(c->ctx, viewHierarchyLevel->depth->GetData(MEMORYDEVICE_CUDA), viewSize.x, viewSize.y, viewIntr,
                                             (const float *)sceneHierarchyLevel->pointsMap->GetData(MEMORYDEVICE_CUDA),
                                             (const float *)sceneHierarchyLevel->normalsMap->GetData(MEMORYDEVICE_CUDA), sceneSize.x, sceneSize.y,
-                                            sceneIntr, approxInvPose.m, scenePose.m, distThresh[levelId], (int)iterationType + 1, &f, nabla, h36,
+                                            sceneIntr, approxInvPose.m, scenePose.m, distThresh[levelId], (int)iterationType, &f, nabla, h36,
                                             &noValid),
                    "ComputeGandH");
     // stride 6 for 3- and 6-parameter iterations alike (ITMDepthTracker_CPU.cpp:72-73)
