@@ -59,7 +59,9 @@ struct itm_b200_ctx {
   unsigned long long *visTileState = nullptr;
   double *icpPartials = nullptr;
   unsigned *icpCounter = nullptr;
-  unsigned *icpBarrier = nullptr;  // [0] arrivals, [1] generation
+  unsigned long long *icpRows = nullptr;   // tagged CTA partial sums of k_icp_track
+  unsigned long long *icpBcast = nullptr;  // tagged pose broadcast ring
+  unsigned icpEpoch = 0;
   float *icpOut = nullptr;     // 44 floats
   float *icpPoseIn = nullptr;  // 16 floats
   FrameState *st = nullptr;    // device
@@ -145,8 +147,10 @@ int ctx_alloc(itm_b200_ctx *c, void *stream) {
   CU(cudaMalloc(&c->icpPartials, (size_t)icp_max_ctas() * 32 * sizeof(double)));
   CU(cudaMalloc(&c->icpCounter, sizeof(unsigned)));
   CU(cudaMemsetAsync(c->icpCounter, 0, sizeof(unsigned), c->stream));
-  CU(cudaMalloc(&c->icpBarrier, 2 * sizeof(unsigned)));
-  CU(cudaMemsetAsync(c->icpBarrier, 0, 2 * sizeof(unsigned), c->stream));
+  CU(cudaMalloc(&c->icpRows, icp_rows_bytes()));
+  CU(cudaMemsetAsync(c->icpRows, 0, icp_rows_bytes(), c->stream));
+  CU(cudaMalloc(&c->icpBcast, icp_bcast_bytes()));
+  CU(cudaMemsetAsync(c->icpBcast, 0, icp_bcast_bytes(), c->stream));
   CU(cudaMalloc(&c->icpOut, 44 * sizeof(float)));
   CU(cudaMalloc(&c->icpPoseIn, 16 * sizeof(float)));
   CU(cudaMalloc(&c->st, sizeof(FrameState)));
@@ -169,7 +173,8 @@ void ctx_free(itm_b200_ctx *c) {
   cudaFree(c->visTileState);
   cudaFree(c->icpPartials);
   cudaFree(c->icpCounter);
-  cudaFree(c->icpBarrier);
+  cudaFree(c->icpRows);
+  cudaFree(c->icpBcast);
   cudaFree(c->icpOut);
   cudaFree(c->icpPoseIn);
   cudaFree(c->st);
@@ -226,6 +231,7 @@ AllocArgs make_alloc_args(itm_b200_ctx *c, const float *depth, void *hash, const
   a.vp = c->vp;
   a.sp = c->sp;
   a.onlyUpdateVisibleList = onlyVisible;
+  a.prologueDone = 0;
   return a;
 }
 
@@ -264,7 +270,7 @@ void enqueue_track(itm_b200_ctx *c, const float *depth0, const float *points, co
     lv[l] = make_level_args(c, l, l == 0 ? depth0 : c->pyramid[l]);
     iters[l] = c->levels[l].noIterations;
   }
-  const cudaError_t e = launch_icp_track(a, lv, iters, c->nLevels, c->p.no_icp_run_till_level, c->icpBarrier, s);
+  const cudaError_t e = launch_icp_track(a, lv, iters, c->nLevels, c->p.no_icp_run_till_level, c->icpRows, c->icpBcast, ++c->icpEpoch, s);
   if (e != cudaSuccess) g_lastError = std::string("cooperative launch of the ICP tracker failed: ") + cudaGetErrorString(e);
   g_launches += 1;
 }
@@ -564,6 +570,7 @@ struct itm_b200_engine {
   cudaEvent_t rgbDone = nullptr;
   float *depth = nullptr;
   int agePointCloud = -1;  // host copy; its evolution does not depend on device results
+  bool prologueDone = false;  // this frame's view kernel already did the FramePrologue chores
   bool profiling = false;
   cudaEvent_t ev[9] = {nullptr};
   float stageMs[8] = {0};
@@ -649,12 +656,17 @@ int engine_reset(itm_b200_engine *e) {
   return ITM_B200_OK;
 }
 
-void stage_view(itm_b200_engine *e) {
+// withPrologue: the whole frame follows in this stream (ProcessFrame path), so the view kernel also does the
+// pose-independent first steps of the allocate and expected-depth stages
+void stage_view(itm_b200_engine *e, bool withPrologue) {
   itm_b200_ctx *c = e->c;
   float *lv[ITM_MAX_LEVELS];
   lv[0] = e->depth;
   for (int l = 1; l < c->nLevels; ++l) lv[l] = c->pyramid[l];
-  launch_view_pyramid(e->rawDepth, c->p.depth_calib_a, c->p.depth_calib_b, lv, c->vp.W, c->vp.H, c->nLevels, c->stream);
+  FramePrologue pro{c->st, e->visibleIds, e->visType, reinterpret_cast<float2 *>(e->minmax), c->vp.W * c->vp.H};
+  launch_view_pyramid(e->rawDepth, c->p.depth_calib_a, c->p.depth_calib_b, lv, c->vp.W, c->vp.H, c->nLevels, c->stream,
+                      withPrologue ? &pro : nullptr);
+  e->prologueDone = withPrologue;
   g_launches += 1 + (c->nLevels > 5 ? c->nLevels - 5 : 0);
 }
 
@@ -665,8 +677,10 @@ void stage_track(itm_b200_engine *e) {
 
 void stage_allocate(itm_b200_engine *e) {
   itm_b200_ctx *c = e->c;
-  launch_allocate(make_alloc_args(c, e->depth, e->hash, e->vbaAllocList, e->excessAllocList, e->visibleIds, e->visType, 0), c->stream);
-  g_launches += 4;
+  AllocArgs a = make_alloc_args(c, e->depth, e->hash, e->vbaAllocList, e->excessAllocList, e->visibleIds, e->visType, 0);
+  a.prologueDone = e->prologueDone ? 1 : 0;
+  launch_allocate(a, c->stream);
+  g_launches += e->prologueDone ? 3 : 4;
 }
 
 void stage_integrate(itm_b200_engine *e) {
@@ -694,6 +708,7 @@ RenderArgs engine_render_args(itm_b200_engine *e) {
   a.pointsMap = e->points;
   a.normalsMap = e->normals;
   a.raycastImage = e->raycastImage;
+  a.minmaxReady = 0;
   a.st = c->st;
   a.vp = c->vp;
   a.sp = c->sp;
@@ -701,8 +716,11 @@ RenderArgs engine_render_args(itm_b200_engine *e) {
 }
 
 void stage_expected_depths(itm_b200_engine *e) {
-  launch_expected_depths(engine_render_args(e), e->c->stream);
-  g_launches += 2;
+  RenderArgs a = engine_render_args(e);
+  a.minmaxReady = e->prologueDone ? 1 : 0;
+  launch_expected_depths(a, e->c->stream);
+  g_launches += e->prologueDone ? 1 : 2;
+  e->prologueDone = false;  // both consumers have run
 }
 void stage_raycast(itm_b200_engine *e) {
   launch_raycast(engine_render_args(e), e->c->stream);
@@ -721,7 +739,7 @@ void enqueue_frame(itm_b200_engine *e) {
   cudaStream_t s = e->c->stream;
   const bool prof = e->profiling;
   if (prof) cudaEventRecord(e->ev[1], s);
-  stage_view(e);
+  stage_view(e, true);
   if (prof) cudaEventRecord(e->ev[2], s);
   stage_track(e);
   if (prof) cudaEventRecord(e->ev[3], s);
@@ -828,7 +846,7 @@ int itm_b200_engine_enqueue_frame_dev(itm_b200_engine *e, const short *raw_depth
 int itm_b200_engine_run_stage(itm_b200_engine *e, int stage) {
   if (!e) return fail(ITM_B200_EINVAL, "NULL engine");
   switch (stage) {
-    case 0: stage_view(e); break;
+    case 0: stage_view(e, false); break;
     case 1: stage_track(e); break;
     case 2: stage_allocate(e); break;
     case 3: stage_integrate(e); break;

@@ -403,7 +403,7 @@ void launch_allocate(const AllocArgs &a, cudaStream_t s) {
   const float oneOverVoxelSize = 1.0f / (a.sp.voxelSize * ITM_BLOCK_SIZE);
   const int stepBound = alloc_step_bound(a.sp);
   HashEntry *table = reinterpret_cast<HashEntry *>(a.hashTable);
-  k_mark_prev_visible<<<64, 256, 0, s>>>(a.visibleIds, a.visType, a.st);
+  if (!a.prologueDone) k_mark_prev_visible<<<64, 256, 0, s>>>(a.visibleIds, a.visType, a.st);
   dim3 g((a.vp.W + 31) / 32, (a.vp.H + 7) / 8);
   k_alloc_pixels<<<g, 256, 0, s>>>(a.depth, table, a.visType, a.allocKey, a.st, a.vp, a.sp, oneOverVoxelSize, stepBound);
   const int numTiles = (a.sp.nEntries + SCAN_TILE - 1) / SCAN_TILE;

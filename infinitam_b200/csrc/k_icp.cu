@@ -26,8 +26,20 @@ namespace {
 
 using namespace itm;
 
-#define ICP_THREADS 256
+#ifndef ICP_THREADS
+#define ICP_THREADS 512
+#endif
+#ifndef ICP_CTAS_PER_SM
+#define ICP_CTAS_PER_SM 1
+#endif
+#define ICP_MAX_CTAS (148 * ICP_CTAS_PER_SM)
 #define ICP_NVALS 32  // 1 count + 1 f + 6 nabla + 21 hessian, padded
+#ifndef ICP_EARLY_NORMALS
+#define ICP_EARLY_NORMALS 0  // 1: issue the normal-map taps together with the point-map taps (more registers)
+#endif
+#ifndef ICP_BATCH
+#define ICP_BATCH 1   // pixels whose gathers a thread keeps in flight together (2 spills registers: slower)
+#endif
 
 __device__ __forceinline__ bool bilinear_holes(const float4 *__restrict__ src, float px, float py, int W, float &rx, float &ry,
                                                float &rz, float &rw) {
@@ -148,13 +160,13 @@ __device__ __forceinline__ void eval_to_partial(const IcpLevelArgs &lv, const Vi
   __syncthreads();  // sPart is reused by the caller
 }
 
-// Sum of the first nRows CTA partials (fp64) by the 8 warps of one CTA; result (float) in sSums[0..32).
+// Sum of the first nRows CTA partials (fp64) by the warps of one CTA; result (float) in sSums[0..32).
 // Lane = value index, warp w owns a contiguous chunk of rows; loads are issued 8 deep so the chain of L2
 // round trips stays short.  The summation order is fixed (rows ascending inside a chunk, chunks ascending),
 // hence bit-reproducible run to run.
 __device__ __forceinline__ void reduce_partials(const double *__restrict__ partials, int nRows, double (*sPart)[ICP_NVALS], float *sSums) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int chunk = (nRows + 7) >> 3;
+  const int chunk = (nRows + ICP_THREADS / 32 - 1) / (ICP_THREADS / 32);
   const int r0 = warp * chunk, r1 = min(nRows, r0 + chunk);
   double s = 0.0;
   int r = r0;
@@ -190,7 +202,7 @@ struct LmShared {
 // The LM bookkeeping of one iteration, ITMDepthTracker.cpp:167-197.  Run by one thread; noPara is a template
 // parameter so that every array index is static and the 6x6 system lives in registers.  Returns HasConverged().
 template <int noPara>
-__device__ bool lm_update(LmShared &L, const float *sSums, int iterationType, int level, bool firstIterOfLevel, float terminationThreshold) {
+__device__ __noinline__ bool lm_update(LmShared &L, const float *sSums, int iterationType, int level, bool firstIterOfLevel, float terminationThreshold) {
   float M_d[16], params[6], approxInvPose[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) M_d[i] = L.M_d[i];
@@ -291,35 +303,277 @@ __device__ __forceinline__ unsigned long long gtimer() {
 #define TRACE_VAL(slot, idx, v)
 #endif
 
+// ---- self-validating 64-bit words: [63:32] tag, [31:0] payload ------------------------------------------------
+// Everything that crosses CTAs inside the tracker travels as 8-byte words carrying their own tag (launch epoch and
+// evaluation number), written and polled with relaxed gpu-scope accesses: a reader that sees the tag has the payload,
+// so no fence, no arrival counter and no second round trip for the data are needed.
+#define ICP_RING 128  // broadcast slots per launch (>= the largest possible number of evaluations, 72 for 8 levels)
+#define ICP_BCAST_WORDS 20  // 16 pose words + 1 flag word, padded
+__device__ __forceinline__ unsigned icp_tag(unsigned epoch, int evalNo) { return (epoch << 7) | (unsigned)(evalNo + 1); }
+__device__ __forceinline__ void word_st(unsigned long long *p, unsigned payload, unsigned tag) {
+  const unsigned long long v = ((unsigned long long)tag << 32) | payload;
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long word_ld(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
 struct TrackArgs {
   IcpArgs a;
   IcpLevelArgs lv[ITM_MAX_LEVELS];
   int iters[ITM_MAX_LEVELS];
   int nLevels, noIcpLevel;
-  unsigned *barrier;  // [0] arrival count, [1] release word: (sequence << 1) | levelDone
+  unsigned long long *rows;   // [maxCtas][32] CTA partial sums (float payload)
+  unsigned long long *bcast;  // [ICP_RING][ICP_BCAST_WORDS] pose for the next evaluation + flags
+  unsigned epoch;             // launch number (never 0)
 };
 
-// One launch = one TrackCamera.  Must be launched cooperatively (all CTAs co-resident).
-// CTA 0 is the master: it keeps the LM state in shared memory, waits for every CTA's partial sums, runs the LM
-// update and publishes the next pose + the "level finished" bit through the release word the others spin on.
+// What a thread needs to finish one pixel once the gathers have landed
+struct IcpPixel {
+  float wx, wy, wz;   // point in world coordinates
+  float u, v;         // its projection into the raycast maps
+  bool inside;
+};
+
+__device__ __forceinline__ void icp_project(IcpPixel &q, int x, int y, float depth, const IcpLevelArgs &lv, const ViewParams &sv,
+                                            const IcpConsts &c) {
+  q.inside = false;
+  q.u = 0.0f; q.v = 0.0f;
+  if (depth <= 1e-8f) return;
+  const float tx = depth * (((float)x - lv.cx) / lv.fx);
+  const float ty = depth * (((float)y - lv.cy) / lv.fy);
+  mat4_mul_vec4(c.approxInvPose, tx, ty, depth, 1.0f, q.wx, q.wy, q.wz);
+  float rx, ry, rz;
+  mat4_mul_vec4(c.scenePose, q.wx, q.wy, q.wz, 1.0f, rx, ry, rz);
+  if (rz <= 0.0f) return;
+  q.u = sv.fx * rx / rz + sv.cx;
+  q.v = sv.fy * ry / rz + sv.cy;
+  q.inside = (q.u >= 0.0f) && (q.u <= (float)(sv.W - 2)) && (q.v >= 0.0f) && (q.v <= (float)(sv.H - 2));
+}
+
+struct IcpTaps {
+  float4 p[4], n[4];
+};
+
+// the 4 + 4 taps of interpolateBilinear_withHoles for points and normals, issued together
+__device__ __forceinline__ void icp_gather(IcpTaps &t, const IcpPixel &q, const float4 *__restrict__ pointsMap,
+                                           const float4 *__restrict__ normalsMap, int W) {
+  if (!q.inside) return;
+  const int ix = (short)(int)floorf(q.u), iy = (short)(int)floorf(q.v);
+  const int o = ix + iy * W;
+  t.p[0] = __ldg(pointsMap + o); t.p[1] = __ldg(pointsMap + o + 1); t.p[2] = __ldg(pointsMap + o + W); t.p[3] = __ldg(pointsMap + o + W + 1);
+#if ICP_EARLY_NORMALS
+  t.n[0] = __ldg(normalsMap + o); t.n[1] = __ldg(normalsMap + o + 1); t.n[2] = __ldg(normalsMap + o + W); t.n[3] = __ldg(normalsMap + o + W + 1);
+#endif
+}
+
+__device__ __forceinline__ float bilerp(float a, float b, float c, float d, float dx, float dy) {
+  return (a * (1.0f - dx) * (1.0f - dy) + b * dx * (1.0f - dy) + c * (1.0f - dx) * dy + d * dx * dy);
+}
+
+// rest of computePerPointGH_Depth_Ab (ITMDepthTracker.h:40-77) and the accumulation of ComputeGandH (..._CPU.cpp:60-66)
+template <bool shortIteration, bool rotationOnly, int NV>
+__device__ __forceinline__ void icp_accumulate(float *acc, const IcpPixel &q, IcpTaps &t, float distThresh, const float4 *__restrict__ normalsMap, int W) {
+  constexpr int noPara = shortIteration ? 3 : 6;
+  if (!q.inside) return;
+  if (t.p[0].w < 0 || t.p[1].w < 0 || t.p[2].w < 0 || t.p[3].w < 0) return;
+  const int ix = (short)(int)floorf(q.u), iy = (short)(int)floorf(q.v);
+  const float fx = q.u - (float)ix, fy = q.v - (float)iy;
+  const float cx = bilerp(t.p[0].x, t.p[1].x, t.p[2].x, t.p[3].x, fx, fy);
+  const float cy = bilerp(t.p[0].y, t.p[1].y, t.p[2].y, t.p[3].y, fx, fy);
+  const float cz = bilerp(t.p[0].z, t.p[1].z, t.p[2].z, t.p[3].z, fx, fy);
+  const float cw = bilerp(t.p[0].w, t.p[1].w, t.p[2].w, t.p[3].w, fx, fy);
+  if (cw < 0.0f) return;
+  const float dx = cx - q.wx, dy = cy - q.wy, dz = cz - q.wz;
+  const float dist = dx * dx + dy * dy + dz * dz;
+  if (dist > distThresh) return;
+#if !ICP_EARLY_NORMALS
+  {
+    const int o = ix + iy * W;
+    t.n[0] = __ldg(normalsMap + o); t.n[1] = __ldg(normalsMap + o + 1); t.n[2] = __ldg(normalsMap + o + W); t.n[3] = __ldg(normalsMap + o + W + 1);
+  }
+#endif
+  float nx, ny, nz;
+  if (t.n[0].w < 0 || t.n[1].w < 0 || t.n[2].w < 0 || t.n[3].w < 0) {
+    nx = 0; ny = 0; nz = 0;  // interpolateBilinear_withHoles returns (0,0,0,-1); the reference does not test it here
+  } else {
+    nx = bilerp(t.n[0].x, t.n[1].x, t.n[2].x, t.n[3].x, fx, fy);
+    ny = bilerp(t.n[0].y, t.n[1].y, t.n[2].y, t.n[3].y, fx, fy);
+    nz = bilerp(t.n[0].z, t.n[1].z, t.n[2].z, t.n[3].z, fx, fy);
+  }
+  const float b = nx * dx + ny * dy + nz * dz;
+  float A[noPara];
+  if (shortIteration) {
+    if (rotationOnly) {
+      A[0] = +q.wz * ny - q.wy * nz;
+      A[1] = -q.wz * nx + q.wx * nz;
+      A[2] = +q.wy * nx - q.wx * ny;
+    } else {
+      A[0] = nx; A[1] = ny; A[2] = nz;
+    }
+  } else {
+    A[0] = +q.wz * ny - q.wy * nz;
+    A[1] = -q.wz * nx + q.wx * nz;
+    A[2] = +q.wy * nx - q.wx * ny;
+    A[3] = nx; A[4] = ny; A[5] = nz;
+  }
+  acc[0] += 1.0f;
+  acc[1] += b * b;
+#pragma unroll
+  for (int r = 0, counter = 0; r < noPara; r++) {
+    acc[2 + r] += b * A[r];
+#pragma unroll
+    for (int cc = 0; cc <= r; cc++, counter++) acc[2 + noPara + counter] += A[r] * A[cc];
+  }
+}
+
+// Warp reduction of NV (<= 32) per-thread values: instead of 5 butterfly steps per value (5*NV shuffles) the values are
+// transposed while they are summed - each step halves the number of values a lane holds - so that 31 (NV > 16) or
+// NV + 15 (NV <= 16) shuffles suffice and lane l ends up with the warp total of value l (l and l+16 both, if NV <= 16).
+template <int NV>
+__device__ __forceinline__ float warp_transpose_reduce(const float *acc) {
+  const int lane = threadIdx.x & 31;
+  float v[16];
+  if (NV > 16) {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float lo = acc[i], hi = (i + 16 < NV) ? acc[i + 16] : 0.0f;
+      const float send = up ? lo : hi, keep = up ? hi : lo;
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = (i < NV) ? acc[i] + __shfl_xor_sync(0xffffffffu, acc[i], 16) : 0.0f;
+  }
+#pragma unroll
+  for (int h = 8; h >= 1; h >>= 1) {
+    const bool up = lane & h;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const float send = up ? v[i] : v[i + h], keep = up ? v[i + h] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+    }
+  }
+  return v[0];
+}
+
+// This CTA's share of one evaluation, pixels two at a time so that 16 gathers are in flight per thread; the CTA sum
+// (fp32 per thread and warp, fp64 across the 8 warps) is published as tagged words in rowOut[0..32).
+template <bool shortIteration, bool rotationOnly>
+__device__ __forceinline__ void eval_to_row(const IcpLevelArgs &lv, const ViewParams &sv, const IcpConsts &c,
+                                            const float4 *__restrict__ pointsMap, const float4 *__restrict__ normalsMap,
+                                            double (*sPart)[ICP_NVALS], unsigned long long *rowOut, unsigned tag, int nCtas) {
+  constexpr int noPara = shortIteration ? 3 : 6;
+  constexpr int noParaSQ = shortIteration ? 6 : 21;
+  constexpr int NV = 2 + noPara + noParaSQ;
+  float acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = 0.0f;
+  const int n = lv.w * lv.h;
+  const int stride = nCtas * ICP_THREADS;
+#if ICP_BATCH == 2
+  for (int i = blockIdx.x * ICP_THREADS + threadIdx.x; i < n; i += 2 * stride) {
+    const int i2 = i + stride;
+    const bool has2 = i2 < n;
+    const float d1 = __ldg(lv.depth + i), d2 = has2 ? __ldg(lv.depth + i2) : 0.0f;
+    IcpPixel q1, q2;
+    const int y1 = i / lv.w, y2 = i2 / lv.w;
+    icp_project(q1, i - y1 * lv.w, y1, d1, lv, sv, c);
+    icp_project(q2, i2 - y2 * lv.w, y2, d2, lv, sv, c);
+    IcpTaps t1, t2;
+    icp_gather(t1, q1, pointsMap, normalsMap, sv.W);
+    icp_gather(t2, q2, pointsMap, normalsMap, sv.W);
+    icp_accumulate<shortIteration, rotationOnly, NV>(acc, q1, t1, lv.distThresh, normalsMap, sv.W);
+    icp_accumulate<shortIteration, rotationOnly, NV>(acc, q2, t2, lv.distThresh, normalsMap, sv.W);
+  }
+#else
+  for (int i = blockIdx.x * ICP_THREADS + threadIdx.x; i < n; i += stride) {
+    IcpPixel q1;
+    const int y1 = i / lv.w;
+    icp_project(q1, i - y1 * lv.w, y1, __ldg(lv.depth + i), lv, sv, c);
+    IcpTaps t1;
+    icp_gather(t1, q1, pointsMap, normalsMap, sv.W);
+    icp_accumulate<shortIteration, rotationOnly, NV>(acc, q1, t1, lv.distThresh, normalsMap, sv.W);
+  }
+#endif
+  const float tot = warp_transpose_reduce<NV>(acc);  // lane l: warp total of value l
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane < NV) sPart[warp][lane] = (double)tot;
+  __syncthreads();
+  if (threadIdx.x < ICP_NVALS) {
+    double s = 0.0;
+    if (threadIdx.x < NV) {
+#pragma unroll
+      for (int w = 0; w < ICP_THREADS / 32; ++w) s += sPart[w][threadIdx.x];
+    }
+    word_st(rowOut + threadIdx.x, __float_as_uint((float)s), tag);
+  }
+  __syncthreads();  // sPart is reused by the caller
+}
+
+// Master only: waits for the first nRows tagged rows and sums them (fp64, fixed order: rows ascending inside each of
+// the interleaved per-warp groups, groups ascending) -> sSums[0..32).  Each thread has all of its rows' loads in flight at once.
+#define ICP_GROUPS (ICP_THREADS / 32)
+#define ICP_ROWS_PER_THREAD ((ICP_MAX_CTAS + ICP_GROUPS - 1) / ICP_GROUPS)
+__device__ __forceinline__ void gather_rows(const unsigned long long *rows, int nRows, unsigned tag, double (*sPart)[ICP_NVALS], float *sSums) {
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  double s = 0.0;
+  constexpr int CH = 10;  // rows in flight per thread
+#pragma unroll 1
+  for (int k0 = 0; k0 < ICP_ROWS_PER_THREAD; k0 += CH) {
+    unsigned long long w[CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+      const int r = g + ICP_GROUPS * (k0 + k);
+      w[k] = r < nRows ? word_ld(rows + (size_t)r * ICP_NVALS + lane) : 0ull;
+    }
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+      const int r = g + ICP_GROUPS * (k0 + k);
+      if (r < nRows) {
+        while ((unsigned)(w[k] >> 32) != tag) w[k] = word_ld(rows + (size_t)r * ICP_NVALS + lane);
+        s += (double)__uint_as_float((unsigned)w[k]);
+      }
+    }
+  }
+  sPart[g][lane] = s;
+  __syncthreads();
+  if (threadIdx.x < ICP_NVALS) {
+    double t = 0.0;
+#pragma unroll
+    for (int q = 0; q < ICP_THREADS / 32; ++q) t += sPart[q][threadIdx.x];
+    sSums[threadIdx.x] = (float)t;
+  }
+  __syncthreads();
+}
+
+// One launch = one TrackCamera.  Must be launched cooperatively (all CTAs co-resident: they wait for each other).
+// CTA 0 is the master: it keeps the LM state in shared memory, collects every active CTA's row, runs the LM update and
+// broadcasts the next pose together with the "level finished" flag in slot evalNo of the ring; everybody (active or
+// not) follows the ring, so all CTAs walk the same sequence of levels and iterations.
 // (A fixed master keeps the long straight-line LM code warm in one SM's instruction cache.)
-__global__ void __launch_bounds__(ICP_THREADS, 2) k_icp_track(TrackArgs t) {
+__global__ void __launch_bounds__(ICP_THREADS, ICP_CTAS_PER_SM) k_icp_track(TrackArgs t) {
   __shared__ IcpConsts c;
   __shared__ double sPart[ICP_THREADS / 32][ICP_NVALS];
   __shared__ float sSums[ICP_NVALS];
   __shared__ LmShared L;
-  __shared__ unsigned sRelease;
+  __shared__ unsigned sFlags;
+  __shared__ IcpLevelArgs sLv;
+  __shared__ ViewParams sSv;
   FrameState *st = t.a.st;
   const float4 *pointsMap = reinterpret_cast<const float4 *>(t.a.pointsMap);
   const float4 *normalsMap = reinterpret_cast<const float4 *>(t.a.normalsMap);
-  unsigned *bCount = t.barrier;
-  volatile unsigned *bRelease = t.barrier + 1;
   const int nCtas = gridDim.x;
   const bool master = blockIdx.x == 0;
 
   if (master && threadIdx.x == 0) { TRACE(63, 0); }
-  if (threadIdx.x < 16) c.scenePose[threadIdx.x] = st->scenePose[threadIdx.x];
-  if (threadIdx.x == 0) sRelease = *bRelease;  // nobody can release before this CTA has arrived
+  if (threadIdx.x < 16) {
+    c.scenePose[threadIdx.x] = st->scenePose[threadIdx.x];
+    c.approxInvPose[threadIdx.x] = st->invM_d[threadIdx.x];  // pose_d->GetInvM() on entering the first level
+  }
   if (master) {
     if (threadIdx.x < 16) {
       L.M_d[threadIdx.x] = st->M_d[threadIdx.x];
@@ -335,71 +589,57 @@ __global__ void __launch_bounds__(ICP_THREADS, 2) k_icp_track(TrackArgs t) {
     if (threadIdx.x >= 96 && threadIdx.x < 96 + ITM_MAX_LEVELS) L.levelEvals[threadIdx.x - 96] = 0;
   }
   __syncthreads();
-  unsigned seq = sRelease >> 1;
 
   int evalNo = 0;
   for (int level = t.nLevels - 1; level >= t.noIcpLevel; --level) {
-    const IcpLevelArgs lv = t.lv[level];
-    const int type = lv.iterationType;
+    const int type = t.lv[level].iterationType;
     if (type == ITM_ITER_NONE) continue;
+    __syncthreads();
+    if (threadIdx.x == 0) { sLv = t.lv[level]; sSv = t.a.sceneVp; }
+    __syncthreads();
+    const IcpLevelArgs &lv = sLv;
     // coarse levels have fewer pixels than the grid has threads: only the first nActive CTAs evaluate
     const int nActive = min(nCtas, (lv.w * lv.h + ICP_THREADS - 1) / ICP_THREADS);
     const int NV = (type == ITM_ITER_BOTH) ? 29 : 11;
-    for (int it = 0; it < t.iters[level]; ++it, ++evalNo) {
-      // pose to evaluate at: pose_d->GetInvM() on entering a level, the LM loop's approxInvPose afterwards - the
-      // master published either one in st->icp.approxInvPose before the last release (st->invM_d before the first)
+    const int nIters = t.iters[level];
+    for (int it = 0; it < nIters; ++it, ++evalNo) {
+      const unsigned tag = icp_tag(t.epoch, evalNo);
       if (blockIdx.x < nActive) {
-        if (threadIdx.x < 16) {
-          c.approxInvPose[threadIdx.x] = master ? L.approxInvPose[threadIdx.x]
-                                                : __ldcg((evalNo == 0 ? st->invM_d : st->icp.approxInvPose) + threadIdx.x);
-        }
-        __syncthreads();
         if (master && threadIdx.x == 0) { TRACE(evalNo, 0); }
-        double *myPartial = t.a.partials + (size_t)blockIdx.x * ICP_NVALS;
-        if (type == ITM_ITER_ROTATION) eval_to_partial<true, true>(lv, t.a.sceneVp, c, pointsMap, normalsMap, sPart, myPartial, nActive);
-        else if (type == ITM_ITER_TRANSLATION) eval_to_partial<true, false>(lv, t.a.sceneVp, c, pointsMap, normalsMap, sPart, myPartial, nActive);
-        else eval_to_partial<false, false>(lv, t.a.sceneVp, c, pointsMap, normalsMap, sPart, myPartial, nActive);
-        __threadfence();
+        unsigned long long *myRow = t.rows + (size_t)blockIdx.x * ICP_NVALS;
+        if (type == ITM_ITER_ROTATION) eval_to_row<true, true>(lv, sSv, c, pointsMap, normalsMap, sPart, myRow, tag, nActive);
+        else if (type == ITM_ITER_TRANSLATION) eval_to_row<true, false>(lv, sSv, c, pointsMap, normalsMap, sPart, myRow, tag, nActive);
+        else eval_to_row<false, false>(lv, sSv, c, pointsMap, normalsMap, sPart, myRow, tag, nActive);
       }
-      // every CTA arrives (idle ones at once): the master can then never run a whole iteration ahead of a CTA
-      // that has not started yet, which keeps the sequence number read at kernel start consistent grid-wide
-      __syncthreads();
-      if (threadIdx.x == 0) atomicAdd(bCount, 1u);
-      ++seq;
+      unsigned long long *slot = t.bcast + (size_t)(evalNo & (ICP_RING - 1)) * ICP_BCAST_WORDS;
       if (master) {
-        if (threadIdx.x == 0) {
-          TRACE(evalNo, 1);
-          while (*((volatile unsigned *)bCount) != (unsigned)nCtas) { /* wait for every partial */ }
-          __threadfence();
-          TRACE(evalNo, 2);
-        }
-        __syncthreads();
-        reduce_partials(t.a.partials, nActive, sPart, sSums);
-        __syncthreads();
+        if (threadIdx.x == 0) { TRACE(evalNo, 1); }
+        gather_rows(t.rows, nActive, tag, sPart, sSums);
         if (threadIdx.x == 0) {
           TRACE(evalNo, 3);
           const bool conv = (NV == 11) ? lm_update<3>(L, sSums, type, level, it == 0, t.a.terminationThreshold)
                                        : lm_update<6>(L, sSums, type, level, it == 0, t.a.terminationThreshold);
           TRACE(evalNo, 4);
           TRACE_VAL(evalNo, 6, level);
-          const bool lastOfLevel = conv || it == t.iters[level] - 1;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) st->icp.approxInvPose[i] = L.approxInvPose[i];
-          *bCount = 0;
-          __threadfence();
-          sRelease = (seq << 1) | (lastOfLevel ? 1u : 0u);
-          *bRelease = sRelease;  // release
+          sFlags = (conv || it == nIters - 1) ? 1u : 0u;
         }
-      } else if (threadIdx.x == 0) {
-        unsigned v;
-        while (((v = *bRelease) >> 1) != seq) { /* spin */ }
-        __threadfence();
-        sRelease = v;
+        __syncthreads();
+        if (threadIdx.x < 16) {
+          const float v = L.approxInvPose[threadIdx.x];
+          c.approxInvPose[threadIdx.x] = v;
+          word_st(slot + threadIdx.x, __float_as_uint(v), tag);
+        } else if (threadIdx.x == 16) {
+          word_st(slot + 16, sFlags, tag);
+        }
+      } else if (threadIdx.x < 17) {
+        unsigned long long w;
+        while ((unsigned)((w = word_ld(slot + threadIdx.x)) >> 32) != tag) { /* spin */ }
+        if (threadIdx.x < 16) c.approxInvPose[threadIdx.x] = __uint_as_float((unsigned)w);
+        else sFlags = (unsigned)w;
       }
       __syncthreads();
       if (master && threadIdx.x == 0) { TRACE(evalNo, 5); }
-      const bool done = (sRelease & 1u) != 0;
-      if (done) { ++evalNo; break; }
+      if (sFlags & 1u) { ++evalNo; break; }
     }
   }
   if (master && threadIdx.x == 0) {
@@ -466,7 +706,7 @@ __global__ void k_set_pose(FrameState *st) {
 
 namespace itm {
 
-int icp_max_ctas() { return 148 * 2; }
+int icp_max_ctas() { return ICP_MAX_CTAS; }
 
 void launch_set_pose(FrameState *st, cudaStream_t s) { k_set_pose<<<1, 1, 0, s>>>(st); }
 
@@ -478,7 +718,7 @@ int icp_track_grid() {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_icp_track, ICP_THREADS, 0);
-  if (perSm > 2) perSm = 2;
+  if (perSm > ICP_CTAS_PER_SM) perSm = ICP_CTAS_PER_SM;
   if (perSm < 1) perSm = 1;
   grid = sms * perSm;
   if (grid > icp_max_ctas()) grid = icp_max_ctas();
@@ -486,7 +726,7 @@ int icp_track_grid() {
 }
 
 cudaError_t launch_icp_track(const IcpArgs &a, const IcpLevelArgs *levels, const int *iters, int nLevels, int noIcpLevel,
-                             unsigned *barrier, cudaStream_t s) {
+                             unsigned long long *rows, unsigned long long *bcast, unsigned epoch, cudaStream_t s) {
   TrackArgs t;
   t.a = a;
   for (int l = 0; l < ITM_MAX_LEVELS; ++l) {
@@ -501,10 +741,16 @@ cudaError_t launch_icp_track(const IcpArgs &a, const IcpLevelArgs *levels, const
   }
   t.nLevels = nLevels;
   t.noIcpLevel = noIcpLevel;
-  t.barrier = barrier;
+  t.rows = rows;
+  t.bcast = bcast;
+  t.epoch = epoch & 0x1FFFFFFu;
+  if (t.epoch == 0) t.epoch = 1;
   void *args[] = {&t};
   return cudaLaunchCooperativeKernel((const void *)k_icp_track, dim3(icp_track_grid()), dim3(ICP_THREADS), args, 0, s);
 }
+
+size_t icp_rows_bytes() { return (size_t)icp_max_ctas() * ICP_NVALS * sizeof(unsigned long long); }
+size_t icp_bcast_bytes() { return (size_t)ICP_RING * ICP_BCAST_WORDS * sizeof(unsigned long long); }
 
 #ifdef ITM_ICP_TRACE
 extern "C" int itm_b200_debug_icp_trace(unsigned long long *out512) {

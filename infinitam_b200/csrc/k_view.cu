@@ -34,6 +34,7 @@ struct PyramidArgs {
   float *level[ITM_MAX_LEVELS];  // level[0] = full resolution
   int w[ITM_MAX_LEVELS], h[ITM_MAX_LEVELS];
   int nLevels;                   // <= 5 handled by the fused kernel
+  itm::FramePrologue pro;        // pose-independent chores of later stages, folded into this launch (all NULL: none)
 };
 
 // One CTA (256 threads) per 32x32 full-res tile.  raw may be NULL (then level 0 is
@@ -47,6 +48,30 @@ __global__ void __launch_bounds__(256) k_convert_pyramid(const short *__restrict
   const int tx0 = blockIdx.x * 32, ty0 = blockIdx.y * 32;
   const int tid = threadIdx.x;
   float *__restrict__ out0 = args.level[0];
+
+  // Frame prologue (ProcessFrame path only).  Two small launches of later stages do not depend on the camera pose that
+  // the tracker is about to compute, so they ride along here instead of sitting on the frame's critical path:
+  //  * AllocateSceneFromDepth's first loop: last frame's visible entries become type 3 (..._CPU.cpp:159-160), and the
+  //    free-list heads the allocation scan counts down from are snapshot;
+  //  * CreateExpectedDepths' initialisation of the whole min/max image (ITMVisualisationEngine_CPU.cpp:104-108).
+  {
+    const int nThreads = gridDim.x * gridDim.y * 256, gtid = (blockIdx.y * gridDim.x + blockIdx.x) * 256 + tid;
+    if (args.pro.visType) {
+      FrameState *st = args.pro.st;
+      if (gtid == 0) {
+        st->allocBaseBlockId = st->lastFreeBlockId;
+        st->allocBaseExcessId = st->lastFreeExcessId;
+      }
+      const int n = st->noVisibleEntries;
+      for (int i = gtid; i < n; i += nThreads) args.pro.visType[__ldg(args.pro.visibleIds + i)] = 3;
+    }
+    if (args.pro.minmax) {
+      float4 *mm4 = reinterpret_cast<float4 *>(args.pro.minmax);
+      const float4 init = make_float4(ITM_FAR_AWAY, ITM_VERY_CLOSE, ITM_FAR_AWAY, ITM_VERY_CLOSE);
+      for (int i = gtid; i < args.pro.minmaxPixels / 2; i += nThreads) mm4[i] = init;
+      if (gtid == 0 && (args.pro.minmaxPixels & 1)) args.pro.minmax[args.pro.minmaxPixels - 1] = make_float2(ITM_FAR_AWAY, ITM_VERY_CLOSE);
+    }
+  }
 
   // level 0: 4 pixels per thread, rows coalesced
 #pragma unroll
@@ -127,8 +152,11 @@ void launch_subsample_holes(float *out, const float *in, int wIn, int hIn, cudaS
 // Fused conversion + pyramid.  levels[0] is the full-resolution float depth; levels 1.. are
 // the tracker's view hierarchy.  Falls back to per-level launches above 5 levels or when a
 // level's children would straddle tiles (never for even dims >= level count).
-void launch_view_pyramid(const short *raw, float a, float b, float *const *levels, int W, int H, int nLevels, cudaStream_t s) {
+void launch_view_pyramid(const short *raw, float a, float b, float *const *levels, int W, int H, int nLevels, cudaStream_t s,
+                         const FramePrologue *prologue) {
   PyramidArgs args;
+  if (prologue) args.pro = *prologue;
+  else args.pro = FramePrologue{nullptr, nullptr, nullptr, nullptr, 0};
   int w = W, h = H;
   for (int l = 0; l < ITM_MAX_LEVELS; ++l) {
     args.level[l] = l < nLevels ? levels[l] : nullptr;

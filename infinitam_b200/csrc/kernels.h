@@ -21,6 +21,7 @@ struct AllocArgs {
   ViewParams vp;
   SceneParams sp;
   int onlyUpdateVisibleList;
+  int prologueDone;              // the marking pass already ran (FramePrologue)
 };
 
 struct IntegrateArgs {
@@ -42,6 +43,7 @@ struct RenderArgs {
   float *pointsMap;     // Vector4f[W*H]
   float *normalsMap;    // Vector4f[W*H]
   unsigned char *raycastImage;  // Vector4u[W*H]
+  int minmaxReady;      // the min/max image is already initialised (FramePrologue)
   FrameState *st;
   ViewParams vp;
   SceneParams sp;
@@ -75,12 +77,25 @@ void launch_icp_maps(const RenderArgs &a, cudaStream_t s);
 
 void launch_convert_depth(const short *raw, float *out, int n, float a, float b, cudaStream_t s);
 void launch_subsample_holes(float *out, const float *in, int wIn, int hIn, cudaStream_t s);
-void launch_view_pyramid(const short *raw, float a, float b, float *const *levels, int W, int H, int nLevels, cudaStream_t s);
+// Pose-independent first steps of AllocateSceneFromDepth (mark last frame's visible entries, snapshot the free-list
+// heads) and of CreateExpectedDepths (min/max image initialisation); when given to launch_view_pyramid they are done
+// by the view kernel and the allocate / expected-depth launches skip them (AllocArgs::prologueDone, RenderArgs::minmaxReady).
+struct FramePrologue {
+  FrameState *st;
+  const int *visibleIds;
+  unsigned char *visType;   // NULL: no marking
+  float2 *minmax;           // NULL: no min/max initialisation
+  int minmaxPixels;
+};
+void launch_view_pyramid(const short *raw, float a, float b, float *const *levels, int W, int H, int nLevels, cudaStream_t s,
+                         const FramePrologue *prologue = nullptr);
 
 // The whole ITMDepthTracker::TrackCamera LM loop as ONE persistent cooperative kernel (levels[l], iters[l] for
-// l < nLevels; barrier = 2 zero-initialised words of scratch).
+// l < nLevels).  rows / bcast: zero-initialised scratch of icp_rows_bytes() / icp_bcast_bytes(); epoch: launch number.
 cudaError_t launch_icp_track(const IcpArgs &a, const IcpLevelArgs *levels, const int *iters, int nLevels, int noIcpLevel,
-                             unsigned *barrier, cudaStream_t s);
+                             unsigned long long *rows, unsigned long long *bcast, unsigned epoch, cudaStream_t s);
+size_t icp_rows_bytes();
+size_t icp_bcast_bytes();
 // One stand-alone evaluation at poseIn (16 floats, device); [n, f, nabla6, hessian36] left in out44 (device).
 void launch_icp_eval_single(const IcpArgs &a, const IcpLevelArgs &lv, float *out44, const float *poseIn, cudaStream_t s);
 int icp_max_ctas();

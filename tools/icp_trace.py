@@ -25,5 +25,5 @@ for k in range(12):
             (base - t[63, 0]) / 1e3, (t[63, 1] - base) / 1e3, 1e3 * eng.stage_times()[1]))
         for i in range(n):
             r = t[i]
-            print("  eval %d level %d: start %+6.1f us | cta0 arrives +%5.1f | last arrives +%5.1f | reduce %4.1f | lm %4.1f | cta0 released +%5.1f (total %5.1f)" % (
-                i, r[6], (r[0] - base) / 1e3, (r[1] - r[0]) / 1e3, (r[2] - r[0]) / 1e3, (r[3] - r[2]) / 1e3, (r[4] - r[3]) / 1e3, (r[5] - r[0]) / 1e3, (r[5] - r[0]) / 1e3))
+            print("  eval %d level %d: start %+6.1f us | cta0 row written +%5.1f | all rows gathered +%5.1f | lm %4.1f | next pose at cta0 +%5.1f" % (
+                i, r[6], (r[0] - base) / 1e3, (r[1] - r[0]) / 1e3, (r[3] - r[0]) / 1e3, (r[4] - r[3]) / 1e3, (r[5] - r[0]) / 1e3))
