@@ -181,6 +181,32 @@ int itm_b200_engine_reset(itm_b200_engine *e);
 int itm_b200_engine_process_frame(itm_b200_engine *e, const unsigned char *rgb_host, const short *raw_depth_host,
                                   float pose_out[16]);
 
+/* ---- work sharding across the GPUs of one NVLink domain (BASELINE configs[2]) --------------------------------
+ * One process per GPU.  The index (hash table, free lists, visible list), the pose and all images evolve identically
+ * on every rank (same deterministic kernels on the same broadcast depth frame); the voxel payload and the raycast
+ * image are replicated as well, but every rank integrates only the voxel blocks it owns (by block coordinate,
+ * itm_b200_shard_owner_of_block) and casts only its share of the image tiles, storing the results into EVERY rank's copy
+ * through NVLink peer pointers, with a cross-GPU barrier after each of the two stages.  The results are bit-identical to
+ * a single-GPU engine.  The three shared buffers per rank are allocated with itm_b200_ipc_alloc, their handles exchanged
+ * by the host (torch.distributed all_gather in infinitam_b200/multi.py) and opened with itm_b200_ipc_open. */
+#define ITM_B200_MAX_SHARDS 8
+#define ITM_B200_IPC_HANDLE_BYTES 64
+typedef struct itm_b200_shard {
+  int rank, world;
+  void *voxel_blocks_dev[ITM_B200_MAX_SHARDS];   /* ITMVoxel_s[local*512] of every rank ([rank] = the local one) */
+  void *raycast_result_dev[ITM_B200_MAX_SHARDS]; /* Vector4f[w*h] of every rank */
+  void *barrier_flags_dev[ITM_B200_MAX_SHARDS];  /* unsigned[ITM_B200_MAX_SHARDS] of every rank, zero-initialised */
+  void *stream;                                  /* cudaStream_t the frames are enqueued on (NULL: a private one) */
+} itm_b200_shard;
+int itm_b200_engine_create_sharded(const itm_b200_params *params, const itm_b200_shard *shard, itm_b200_engine **out);
+/* cudaMalloc + zero fill + cudaIpcGetMemHandle / cudaIpcOpenMemHandle (peer access enabled lazily) / close / free */
+int itm_b200_ipc_alloc(size_t bytes, void **dev_ptr, unsigned char handle[ITM_B200_IPC_HANDLE_BYTES]);
+int itm_b200_ipc_open(const unsigned char handle[ITM_B200_IPC_HANDLE_BYTES], void **dev_ptr);
+int itm_b200_ipc_close(void *dev_ptr);
+int itm_b200_ipc_free(void *dev_ptr);
+/* rank that integrates the voxel block at block coordinate (x, y, z) */
+int itm_b200_shard_owner_of_block(int x, int y, int z, int world);
+
 /* Same frame, input already resident in HBM, enqueued asynchronously on the engine's stream. */
 int itm_b200_engine_enqueue_frame_dev(itm_b200_engine *e, const short *raw_depth_dev);
 /* Wait for everything enqueued; counters = {noVisibleEntries, lastFreeBlockId,

@@ -64,6 +64,18 @@ class TrackingState(C.Structure):
     ]
 
 
+MAX_SHARDS = 8
+IPC_HANDLE_BYTES = 64
+
+
+class Shard(C.Structure):
+    _fields_ = [
+        ("rank", C.c_int), ("world", C.c_int),
+        ("voxel_blocks_dev", C.c_void_p * MAX_SHARDS), ("raycast_result_dev", C.c_void_p * MAX_SHARDS),
+        ("barrier_flags_dev", C.c_void_p * MAX_SHARDS), ("stream", C.c_void_p),
+    ]
+
+
 # every symbol include/itm_b200.h declares
 SYMBOLS = [
     "itm_b200_default_params", "itm_b200_last_error", "itm_b200_device_count", "itm_b200_launch_count",
@@ -71,7 +83,8 @@ SYMBOLS = [
     "itm_b200_integrate_into_scene", "itm_b200_create_expected_depths", "itm_b200_create_icp_maps",
     "itm_b200_convert_depth_affine_to_float", "itm_b200_filter_subsample_with_holes", "itm_b200_compute_g_and_h",
     "itm_b200_track_camera", "itm_b200_engine_create", "itm_b200_engine_destroy", "itm_b200_engine_reset",
-    "itm_b200_engine_process_frame", "itm_b200_engine_enqueue_frame_dev", "itm_b200_engine_sync",
+    "itm_b200_engine_create_sharded", "itm_b200_ipc_alloc", "itm_b200_ipc_open", "itm_b200_ipc_close", "itm_b200_ipc_free",
+    "itm_b200_shard_owner_of_block", "itm_b200_engine_process_frame", "itm_b200_engine_enqueue_frame_dev", "itm_b200_engine_sync",
     "itm_b200_engine_upload_depth", "itm_b200_engine_run_stage", "itm_b200_engine_get_buffer",
     "itm_b200_engine_read_buffer", "itm_b200_engine_write_buffer", "itm_b200_engine_get_state",
     "itm_b200_engine_set_state", "itm_b200_engine_icp_stats", "itm_b200_engine_set_profiling", "itm_b200_engine_stage_times",
@@ -115,6 +128,12 @@ def load():
                                              C.c_float, C.c_int, f32p, f32p, f32p, i32p]
     lib.itm_b200_track_camera.argtypes = [vp, vp, C.POINTER(TrackingState)]
     lib.itm_b200_engine_create.argtypes = [C.POINTER(Params), C.POINTER(vp)]
+    lib.itm_b200_engine_create_sharded.argtypes = [C.POINTER(Params), C.POINTER(Shard), C.POINTER(vp)]
+    lib.itm_b200_ipc_alloc.argtypes = [C.c_size_t, C.POINTER(vp), C.c_char_p]
+    lib.itm_b200_ipc_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+    lib.itm_b200_ipc_close.argtypes = [vp]
+    lib.itm_b200_ipc_free.argtypes = [vp]
+    lib.itm_b200_shard_owner_of_block.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
     lib.itm_b200_engine_destroy.argtypes = [vp]
     lib.itm_b200_engine_destroy.restype = None
     lib.itm_b200_engine_reset.argtypes = [vp]

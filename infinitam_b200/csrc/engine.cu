@@ -391,6 +391,8 @@ int itm_b200_integrate_into_scene(itm_b200_ctx *c, itm_b200_scene *scene, const 
   int rc = push_state(c);
   if (rc) return rc;
   IntegrateArgs a;
+  memset(&a.shard, 0, sizeof(a.shard));
+  a.shard.world = 1;
   a.depth = depth_dev;
   a.voxels = scene->voxel_blocks_dev;
   a.hashTable = scene->hash_entries_dev;
@@ -414,6 +416,7 @@ int itm_b200_create_expected_depths(itm_b200_ctx *c, const itm_b200_scene *scene
   if (rc) return rc;
   RenderArgs a;
   memset(&a, 0, sizeof(a));
+  a.shard.world = 1;
   a.hashTable = scene->hash_entries_dev;
   a.visibleIds = rs->visible_entry_ids_dev;
   a.minmax = rs->rendering_range_image_dev;
@@ -435,6 +438,7 @@ int itm_b200_create_icp_maps(itm_b200_ctx *c, const itm_b200_scene *scene, itm_b
   if (rc) return rc;
   RenderArgs a;
   memset(&a, 0, sizeof(a));
+  a.shard.world = 1;
   a.voxels = scene->voxel_blocks_dev;
   a.hashTable = scene->hash_entries_dev;
   a.minmax = rs->rendering_range_image_dev;
@@ -571,6 +575,9 @@ struct itm_b200_engine {
   float *depth = nullptr;
   int agePointCloud = -1;  // host copy; its evolution does not depend on device results
   bool prologueDone = false;  // this frame's view kernel already did the FramePrologue chores
+  ShardInfo shard;            // world == 1 unless created with itm_b200_engine_create_sharded
+  bool externalBuffers = false;  // voxels / raycastResult belong to the caller (sharded engines)
+  unsigned barrierSeq = 0;
   bool profiling = false;
   cudaEvent_t ev[9] = {nullptr};
   float stageMs[8] = {0};
@@ -582,14 +589,14 @@ namespace {
 int engine_alloc(itm_b200_engine *e) {
   itm_b200_ctx *c = e->c;
   const size_t P = (size_t)c->vp.W * c->vp.H;
-  CU(cudaMalloc(&e->voxels, (size_t)c->sp.nLocal * ITM_BLOCK_SIZE3 * 4));
+  if (!e->externalBuffers) CU(cudaMalloc(&e->voxels, (size_t)c->sp.nLocal * ITM_BLOCK_SIZE3 * 4));
   CU(cudaMalloc(&e->hash, (size_t)c->sp.nEntries * 16));
   CU(cudaMalloc(&e->vbaAllocList, (size_t)c->sp.nLocal * 4));
   CU(cudaMalloc(&e->excessAllocList, (size_t)c->sp.nExcess * 4));
   CU(cudaMalloc(&e->visibleIds, (size_t)c->sp.nLocal * 4));
   CU(cudaMalloc(&e->visType, (size_t)((c->sp.nEntries + 8191) / 8192) * 8192));
   CU(cudaMalloc(&e->minmax, P * 8));
-  CU(cudaMalloc(&e->raycastResult, P * 16));
+  if (!e->externalBuffers) CU(cudaMalloc(&e->raycastResult, P * 16));
   CU(cudaMalloc(&e->raycastImage, P * 4));
   CU(cudaMalloc(&e->points, P * 16));
   CU(cudaMalloc(&e->normals, P * 16));
@@ -618,8 +625,9 @@ int engine_alloc(itm_b200_engine *e) {
 }
 
 void engine_free(itm_b200_engine *e) {
-  cudaFree(e->voxels); cudaFree(e->hash); cudaFree(e->vbaAllocList); cudaFree(e->excessAllocList);
-  cudaFree(e->visibleIds); cudaFree(e->visType); cudaFree(e->minmax); cudaFree(e->raycastResult);
+  if (!e->externalBuffers) { cudaFree(e->voxels); cudaFree(e->raycastResult); }
+  cudaFree(e->hash); cudaFree(e->vbaAllocList); cudaFree(e->excessAllocList);
+  cudaFree(e->visibleIds); cudaFree(e->visType); cudaFree(e->minmax);
   cudaFree(e->raycastImage); cudaFree(e->points); cudaFree(e->normals); cudaFree(e->rawDepth);
   cudaFree(e->rgb); cudaFree(e->depth);
   if (e->copyStream) cudaStreamDestroy(e->copyStream);
@@ -686,6 +694,7 @@ void stage_allocate(itm_b200_engine *e) {
 void stage_integrate(itm_b200_engine *e) {
   itm_b200_ctx *c = e->c;
   IntegrateArgs a;
+  a.shard = e->shard;
   a.depth = e->depth;
   a.voxels = e->voxels;
   a.hashTable = e->hash;
@@ -700,6 +709,7 @@ void stage_integrate(itm_b200_engine *e) {
 RenderArgs engine_render_args(itm_b200_engine *e) {
   itm_b200_ctx *c = e->c;
   RenderArgs a;
+  a.shard = e->shard;
   a.voxels = e->voxels;
   a.hashTable = e->hash;
   a.visibleIds = e->visibleIds;
@@ -735,6 +745,13 @@ void stage_icp_maps(itm_b200_engine *e) {
   else e->agePointCloud = 0;
 }
 
+void stage_shard_barrier(itm_b200_engine *e) {
+  if (e->shard.world > 1) {
+    launch_shard_barrier(e->shard, ++e->barrierSeq, e->c->stream);
+    g_launches += 1;
+  }
+}
+
 void enqueue_frame(itm_b200_engine *e) {
   cudaStream_t s = e->c->stream;
   const bool prof = e->profiling;
@@ -746,10 +763,12 @@ void enqueue_frame(itm_b200_engine *e) {
   stage_allocate(e);
   if (prof) cudaEventRecord(e->ev[4], s);
   stage_integrate(e);
+  stage_shard_barrier(e);  // every rank's share of the voxel updates has landed in every copy
   if (prof) cudaEventRecord(e->ev[5], s);
   stage_expected_depths(e);
   if (prof) cudaEventRecord(e->ev[6], s);
   stage_raycast(e);
+  stage_shard_barrier(e);  // ... and every rank's tiles of the raycast image
   if (prof) cudaEventRecord(e->ev[7], s);
   stage_icp_maps(e);
   if (prof) cudaEventRecord(e->ev[8], s);
@@ -767,6 +786,8 @@ int itm_b200_engine_create(const itm_b200_params *params, itm_b200_engine **out)
   if (rc) return rc;
   itm_b200_engine *e = new itm_b200_engine();
   e->c = c;
+  memset(&e->shard, 0, sizeof(e->shard));
+  e->shard.world = 1;
   rc = engine_alloc(e);
   if (!rc) rc = engine_reset(e);
   if (rc) {
@@ -776,6 +797,76 @@ int itm_b200_engine_create(const itm_b200_params *params, itm_b200_engine **out)
   }
   *out = e;
   return ITM_B200_OK;
+}
+
+int itm_b200_engine_create_sharded(const itm_b200_params *params, const itm_b200_shard *shard, itm_b200_engine **out) {
+  if (!out || !shard) return fail(ITM_B200_EINVAL, "NULL argument");
+  *out = nullptr;
+  if (shard->world < 1 || shard->world > ITM_MAX_SHARDS || shard->rank < 0 || shard->rank >= shard->world)
+    return fail(ITM_B200_EINVAL, "rank / world out of range (at most 8 ranks)");
+  for (int r = 0; r < shard->world; ++r)
+    if (!shard->voxel_blocks_dev[r] || !shard->raycast_result_dev[r] || !shard->barrier_flags_dev[r])
+      return fail(ITM_B200_EINVAL, "every rank's voxel, raycast and flag buffer must be given");
+  itm_b200_ctx *c = nullptr;
+  int rc = itm_b200_ctx_create(params, shard->stream, &c);
+  if (rc) return rc;
+  itm_b200_engine *e = new itm_b200_engine();
+  e->c = c;
+  e->externalBuffers = true;
+  memset(&e->shard, 0, sizeof(e->shard));
+  e->shard.rank = shard->rank;
+  e->shard.world = shard->world;
+  for (int r = 0; r < shard->world; ++r) {
+    e->shard.voxels[r] = shard->voxel_blocks_dev[r];
+    e->shard.raycast[r] = shard->raycast_result_dev[r];
+    e->shard.flags[r] = (unsigned *)shard->barrier_flags_dev[r];
+  }
+  e->voxels = shard->voxel_blocks_dev[shard->rank];
+  e->raycastResult = (float *)shard->raycast_result_dev[shard->rank];
+  rc = engine_alloc(e);
+  if (!rc) rc = engine_reset(e);  // every rank resets its own copy of the replicated state
+  if (rc) {
+    engine_free(e);
+    delete e;
+    return rc;
+  }
+  *out = e;
+  return ITM_B200_OK;
+}
+
+int itm_b200_ipc_alloc(size_t bytes, void **dev_ptr, unsigned char handle[ITM_B200_IPC_HANDLE_BYTES]) {
+  if (!dev_ptr || !handle || !bytes) return fail(ITM_B200_EINVAL, "NULL argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) <= ITM_B200_IPC_HANDLE_BYTES, "handle size");
+  CU(cudaMalloc(dev_ptr, bytes));
+  CU(cudaMemset(*dev_ptr, 0, bytes));
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, *dev_ptr));
+  memset(handle, 0, ITM_B200_IPC_HANDLE_BYTES);
+  memcpy(handle, &h, sizeof(h));
+  return ITM_B200_OK;
+}
+
+int itm_b200_ipc_open(const unsigned char handle[ITM_B200_IPC_HANDLE_BYTES], void **dev_ptr) {
+  if (!dev_ptr || !handle) return fail(ITM_B200_EINVAL, "NULL argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  CU(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return ITM_B200_OK;
+}
+
+int itm_b200_ipc_close(void *dev_ptr) {
+  CU(cudaIpcCloseMemHandle(dev_ptr));
+  return ITM_B200_OK;
+}
+
+int itm_b200_ipc_free(void *dev_ptr) {
+  CU(cudaFree(dev_ptr));
+  return ITM_B200_OK;
+}
+
+int itm_b200_shard_owner_of_block(int x, int y, int z, int world) {
+  if (world < 1) return fail(ITM_B200_EINVAL, "world must be >= 1");
+  return shard_owner_of_block(x, y, z, world);
 }
 
 void itm_b200_engine_destroy(itm_b200_engine *e) {
@@ -849,9 +940,9 @@ int itm_b200_engine_run_stage(itm_b200_engine *e, int stage) {
     case 0: stage_view(e, false); break;
     case 1: stage_track(e); break;
     case 2: stage_allocate(e); break;
-    case 3: stage_integrate(e); break;
+    case 3: stage_integrate(e); stage_shard_barrier(e); break;
     case 4: stage_expected_depths(e); break;
-    case 5: stage_raycast(e); stage_icp_maps(e); break;
+    case 5: stage_raycast(e); stage_shard_barrier(e); stage_icp_maps(e); break;
     default: return fail(ITM_B200_EINVAL, "unknown stage");
   }
   return itm_b200_engine_sync(e, nullptr, nullptr);

@@ -5,6 +5,24 @@
 
 namespace itm {
 
+#define ITM_MAX_SHARDS 8
+
+// Work sharding across GPUs of one NVLink domain (DESIGN.md "Multi-GPU").  The index (hash table, free lists, visible
+// list) is replicated and evolves identically on every rank; the voxel payload and the raycast image are replicated too,
+// but each rank computes only its share and stores the results into every rank's copy through peer pointers.
+struct ShardInfo {
+  int rank, world;                    // world == 1: single GPU, peer arrays unused
+  void *voxels[ITM_MAX_SHARDS];       // every rank's voxel block array (entry [rank] is the local one)
+  void *raycast[ITM_MAX_SHARDS];      // every rank's raycastResult image
+  unsigned *flags[ITM_MAX_SHARDS];    // every rank's barrier words: flags[r][src] = last barrier number src has reached
+};
+
+// block coordinate -> owning rank (any deterministic function of the coordinate works; this one mixes all three axes)
+__host__ __device__ __forceinline__ int shard_owner_of_block(int x, int y, int z, int world) {
+  const unsigned h = ((unsigned)x * 73856093u) ^ ((unsigned)y * 19349669u) ^ ((unsigned)z * 83492791u);
+  return (int)((h >> 7) % (unsigned)world);
+}
+
 struct AllocArgs {
   const float *depth;            // view->depth, float metres
   void *hashTable;               // ITMHashEntry[nEntries]
@@ -25,6 +43,7 @@ struct AllocArgs {
 };
 
 struct IntegrateArgs {
+  ShardInfo shard;
   const float *depth;
   void *voxels;
   const void *hashTable;
@@ -35,6 +54,7 @@ struct IntegrateArgs {
 };
 
 struct RenderArgs {
+  ShardInfo shard;
   const void *voxels;
   const void *hashTable;
   const int *visibleIds;
@@ -98,6 +118,8 @@ size_t icp_rows_bytes();
 size_t icp_bcast_bytes();
 // One stand-alone evaluation at poseIn (16 floats, device); [n, f, nabla6, hessian36] left in out44 (device).
 void launch_icp_eval_single(const IcpArgs &a, const IcpLevelArgs &lv, float *out44, const float *poseIn, cudaStream_t s);
+// all ranks meet: returns (on the stream) once every rank has enqueued barrier number seq after its own prior work
+void launch_shard_barrier(const ShardInfo &sh, unsigned seq, cudaStream_t s);
 int icp_max_ctas();
 int icp_track_grid();
 
