@@ -68,7 +68,15 @@ typedef struct itm_b200_params {
   float depth_tracker_icp_threshold; /* settings.depthTrackerICPThreshold (0.1*0.1) */
   float depth_tracker_termination_threshold; /* (1e-3) */
   int device;                        /* CUDA device ordinal */
+  /* voxel type (ITMLib/Utils/ITMLibDefines.h:205 picks it at compile time; here it is a run-time choice):
+   * ITM_B200_VOXEL_S = ITMVoxel_s (4 B: short sdf, uchar w_depth), ITM_B200_VOXEL_S_RGB = ITMVoxel_s_rgb (8 B: + uchar
+   * clr[3], uchar w_color; ITMLibDefines.h:127-155) with colour integration from view->rgb */
+  int voxel_type;
+  float rgb_fx, rgb_fy, rgb_cx, rgb_cy;      /* calib.intrinsics_rgb.projectionParamsSimple.all (rgb image = depth image size) */
+  float trafo_rgb_to_depth_inv[16];  /* calib.trafo_rgb_to_depth.calib_inv, column-major (identity by default) */
 } itm_b200_params;
+#define ITM_B200_VOXEL_S 0
+#define ITM_B200_VOXEL_S_RGB 1
 
 /* Fills *p with the reference's defaults (ICP tracker regime) for a width x height sensor;
  * intrinsics default to ITMIntrinsics() = (580, 580, 320, 240) scaled by width/640. */
@@ -94,7 +102,7 @@ void itm_b200_ctx_destroy(itm_b200_ctx *ctx);
 
 /* ITMScene<ITMVoxel_s, ITMVoxelBlockHash>: index + localVBA (ITMLib/Objects/ITMScene.h:20-51) */
 typedef struct itm_b200_scene {
-  void *voxel_blocks_dev;            /* localVBA.GetVoxelBlocks():  ITMVoxel_s[local*512]      */
+  void *voxel_blocks_dev;            /* localVBA.GetVoxelBlocks():  ITMVoxel_s / _s_rgb [local*512] */
   void *hash_entries_dev;            /* index.GetEntries():         ITMHashEntry[bucket+excess] */
   int *vba_allocation_list_dev;      /* localVBA.GetAllocationList(): int[local]               */
   int *excess_allocation_list_dev;   /* index.GetExcessAllocationList(): int[excess]           */
@@ -129,9 +137,12 @@ int itm_b200_reset_scene(itm_b200_ctx *ctx, itm_b200_scene *scene);
 int itm_b200_allocate_scene_from_depth(itm_b200_ctx *ctx, itm_b200_scene *scene, itm_b200_render_state *rs,
                                        const float *depth_dev, const float pose_M[16], int only_update_visible_list);
 
-/* ITMSceneReconstructionEngine::IntegrateIntoScene (Engine/ITMSceneReconstructionEngine.h:47-48) */
+/* ITMSceneReconstructionEngine::IntegrateIntoScene (Engine/ITMSceneReconstructionEngine.h:47-48).  The _rgb variant is
+ * the one for ITM_B200_VOXEL_S_RGB contexts: rgb_dev = view->rgb (Vector4u[w*h]). */
 int itm_b200_integrate_into_scene(itm_b200_ctx *ctx, itm_b200_scene *scene, const itm_b200_render_state *rs,
                                   const float *depth_dev, const float pose_M[16]);
+int itm_b200_integrate_into_scene_rgb(itm_b200_ctx *ctx, itm_b200_scene *scene, const itm_b200_render_state *rs,
+                                      const float *depth_dev, const unsigned char *rgb_dev, const float pose_M[16]);
 
 /* IITMVisualisationEngine::CreateExpectedDepths (Engine/ITMVisualisationEngine.h:46-47) */
 int itm_b200_create_expected_depths(itm_b200_ctx *ctx, const itm_b200_scene *scene, itm_b200_render_state *rs,
@@ -224,7 +235,7 @@ enum {
   ITM_B200_BUF_VOXELS = 0, ITM_B200_BUF_HASH, ITM_B200_BUF_VBA_ALLOC_LIST, ITM_B200_BUF_EXCESS_ALLOC_LIST,
   ITM_B200_BUF_VISIBLE_IDS, ITM_B200_BUF_VISIBLE_TYPES, ITM_B200_BUF_DEPTH, ITM_B200_BUF_MINMAX, ITM_B200_BUF_RAYCAST_RESULT,
   ITM_B200_BUF_RAYCAST_IMAGE, ITM_B200_BUF_POINTS, ITM_B200_BUF_NORMALS, ITM_B200_BUF_RAW_DEPTH, ITM_B200_BUF_PYRAMID_1,
-  ITM_B200_BUF_PYRAMID_2, ITM_B200_BUF_PYRAMID_3, ITM_B200_BUF_PYRAMID_4, ITM_B200_BUF_COUNT
+  ITM_B200_BUF_PYRAMID_2, ITM_B200_BUF_PYRAMID_3, ITM_B200_BUF_PYRAMID_4, ITM_B200_BUF_RGB, ITM_B200_BUF_COUNT
 };
 int itm_b200_engine_get_buffer(itm_b200_engine *e, int which, void **dev_ptr, size_t *bytes);
 /* Blocking copies between one of those buffers and host memory (the reference's

@@ -18,7 +18,8 @@ ITER_ROTATION, ITER_TRANSLATION, ITER_BOTH, ITER_NONE = 1, 2, 3, 4
 
 (BUF_VOXELS, BUF_HASH, BUF_VBA_ALLOC_LIST, BUF_EXCESS_ALLOC_LIST, BUF_VISIBLE_IDS, BUF_VISIBLE_TYPES, BUF_DEPTH,
  BUF_MINMAX, BUF_RAYCAST_RESULT, BUF_RAYCAST_IMAGE, BUF_POINTS, BUF_NORMALS, BUF_RAW_DEPTH, BUF_PYRAMID_1,
- BUF_PYRAMID_2, BUF_PYRAMID_3, BUF_PYRAMID_4, BUF_COUNT) = range(18)
+ BUF_PYRAMID_2, BUF_PYRAMID_3, BUF_PYRAMID_4, BUF_RGB, BUF_COUNT) = range(19)
+VOXEL_S, VOXEL_S_RGB = 0, 1
 
 STAGE_VIEW, STAGE_TRACK, STAGE_ALLOCATE, STAGE_INTEGRATE, STAGE_EXPECTED_DEPTHS, STAGE_ICP_MAPS = range(6)
 
@@ -36,6 +37,9 @@ class Params(C.Structure):
         ("no_icp_run_till_level", C.c_int),
         ("depth_tracker_icp_threshold", C.c_float), ("depth_tracker_termination_threshold", C.c_float),
         ("device", C.c_int),
+        ("voxel_type", C.c_int),
+        ("rgb_fx", C.c_float), ("rgb_fy", C.c_float), ("rgb_cx", C.c_float), ("rgb_cy", C.c_float),
+        ("trafo_rgb_to_depth_inv", C.c_float * 16),
     ]
 
 
@@ -80,7 +84,7 @@ class Shard(C.Structure):
 SYMBOLS = [
     "itm_b200_default_params", "itm_b200_last_error", "itm_b200_device_count", "itm_b200_launch_count",
     "itm_b200_ctx_create", "itm_b200_ctx_destroy", "itm_b200_reset_scene", "itm_b200_allocate_scene_from_depth",
-    "itm_b200_integrate_into_scene", "itm_b200_create_expected_depths", "itm_b200_create_icp_maps",
+    "itm_b200_integrate_into_scene", "itm_b200_integrate_into_scene_rgb", "itm_b200_create_expected_depths", "itm_b200_create_icp_maps",
     "itm_b200_convert_depth_affine_to_float", "itm_b200_filter_subsample_with_holes", "itm_b200_compute_g_and_h",
     "itm_b200_track_camera", "itm_b200_engine_create", "itm_b200_engine_destroy", "itm_b200_engine_reset",
     "itm_b200_engine_create_sharded", "itm_b200_ipc_alloc", "itm_b200_ipc_open", "itm_b200_ipc_close", "itm_b200_ipc_free",
@@ -120,6 +124,7 @@ def load():
     lib.itm_b200_reset_scene.argtypes = [vp, C.POINTER(Scene)]
     lib.itm_b200_allocate_scene_from_depth.argtypes = [vp, C.POINTER(Scene), C.POINTER(RenderState), vp, f32p, C.c_int]
     lib.itm_b200_integrate_into_scene.argtypes = [vp, C.POINTER(Scene), C.POINTER(RenderState), vp, f32p]
+    lib.itm_b200_integrate_into_scene_rgb.argtypes = [vp, C.POINTER(Scene), C.POINTER(RenderState), vp, vp, f32p]
     lib.itm_b200_create_expected_depths.argtypes = [vp, C.POINTER(Scene), C.POINTER(RenderState), f32p, f32p]
     lib.itm_b200_create_icp_maps.argtypes = [vp, C.POINTER(Scene), C.POINTER(RenderState), C.POINTER(TrackingState)]
     lib.itm_b200_convert_depth_affine_to_float.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_float, C.c_float]

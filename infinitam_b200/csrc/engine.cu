@@ -81,6 +81,7 @@ int validate_params(const itm_b200_params *p) {
   if ((long long)p->sdf_bucket_num + p->sdf_excess_list_size >= (1 << 21) * 1024LL) return fail(ITM_B200_EUNSUPPORTED, "hash table too large");
   if (p->no_hierarchy_levels < 1 || p->no_hierarchy_levels > ITM_MAX_LEVELS) return fail(ITM_B200_EINVAL, "no_hierarchy_levels out of range");
   if (!(p->voxel_size > 0) || !(p->mu > 0)) return fail(ITM_B200_EINVAL, "voxel_size and mu must be positive");
+  if (p->voxel_type != ITM_B200_VOXEL_S && p->voxel_type != ITM_B200_VOXEL_S_RGB) return fail(ITM_B200_EINVAL, "unknown voxel_type");
   return ITM_B200_OK;
 }
 
@@ -97,6 +98,7 @@ void derive(itm_b200_ctx *c) {
   c->sp.nExcess = p.sdf_excess_list_size;
   c->sp.nEntries = p.sdf_bucket_num + p.sdf_excess_list_size;
   c->sp.hashMask = (unsigned)p.sdf_bucket_num - 1u;
+  c->sp.voxelWords = p.voxel_type == ITM_B200_VOXEL_S_RGB ? 2 : 1;
   c->vp.W = p.width;
   c->vp.H = p.height;
   c->vp.fx = p.fx;
@@ -235,6 +237,12 @@ AllocArgs make_alloc_args(itm_b200_ctx *c, const float *depth, void *hash, const
   return a;
 }
 
+void fill_integrate_calib(const itm_b200_ctx *c, IntegrateArgs &a, const unsigned char *rgb) {
+  a.rgb = rgb;
+  a.rgbIntr[0] = c->p.rgb_fx; a.rgbIntr[1] = c->p.rgb_fy; a.rgbIntr[2] = c->p.rgb_cx; a.rgbIntr[3] = c->p.rgb_cy;
+  memcpy(a.calibInv, c->p.trafo_rgb_to_depth_inv, sizeof(a.calibInv));
+}
+
 IcpLevelArgs make_level_args(const itm_b200_ctx *c, int l, const float *depth) {
   const LevelCfg &L = c->levels[l];
   IcpLevelArgs lv;
@@ -310,6 +318,9 @@ void itm_b200_default_params(itm_b200_params *p, int width, int height) {
   p->depth_tracker_icp_threshold = 0.1f * 0.1f;
   p->depth_tracker_termination_threshold = 1e-3f;
   p->device = 0;
+  p->voxel_type = ITM_B200_VOXEL_S;
+  p->rgb_fx = p->fx; p->rgb_fy = p->fy; p->rgb_cx = p->cx; p->rgb_cy = p->cy;
+  for (int i = 0; i < 16; ++i) p->trafo_rgb_to_depth_inv[i] = (i % 5 == 0) ? 1.0f : 0.0f;
 }
 
 const char *itm_b200_last_error(void) { return g_lastError.c_str(); }
@@ -383,9 +394,11 @@ int itm_b200_allocate_scene_from_depth(itm_b200_ctx *c, itm_b200_scene *scene, i
   return ITM_B200_OK;
 }
 
-int itm_b200_integrate_into_scene(itm_b200_ctx *c, itm_b200_scene *scene, const itm_b200_render_state *rs, const float *depth_dev,
-                                  const float pose_M[16]) {
+static int integrate_layer_a(itm_b200_ctx *c, itm_b200_scene *scene, const itm_b200_render_state *rs, const float *depth_dev,
+                             const unsigned char *rgb_dev, const float pose_M[16]) {
   if (!c || !scene || !rs || !depth_dev || !pose_M) return fail(ITM_B200_EINVAL, "NULL argument");
+  if (c->sp.voxelWords == 2 && !rgb_dev)
+    return fail(ITM_B200_EINVAL, "ITMVoxel_s_rgb context: use itm_b200_integrate_into_scene_rgb (needs view->rgb)");
   set_pose_host(c->hst, pose_M);
   c->hst->noVisibleEntries = rs->no_visible_entries;
   int rc = push_state(c);
@@ -393,6 +406,7 @@ int itm_b200_integrate_into_scene(itm_b200_ctx *c, itm_b200_scene *scene, const 
   IntegrateArgs a;
   memset(&a.shard, 0, sizeof(a.shard));
   a.shard.world = 1;
+  fill_integrate_calib(c, a, rgb_dev);
   a.depth = depth_dev;
   a.voxels = scene->voxel_blocks_dev;
   a.hashTable = scene->hash_entries_dev;
@@ -405,6 +419,17 @@ int itm_b200_integrate_into_scene(itm_b200_ctx *c, itm_b200_scene *scene, const 
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaGetLastError());
   return ITM_B200_OK;
+}
+
+int itm_b200_integrate_into_scene(itm_b200_ctx *c, itm_b200_scene *scene, const itm_b200_render_state *rs, const float *depth_dev,
+                                  const float pose_M[16]) {
+  return integrate_layer_a(c, scene, rs, depth_dev, nullptr, pose_M);
+}
+
+int itm_b200_integrate_into_scene_rgb(itm_b200_ctx *c, itm_b200_scene *scene, const itm_b200_render_state *rs, const float *depth_dev,
+                                      const unsigned char *rgb_dev, const float pose_M[16]) {
+  if (!rgb_dev) return fail(ITM_B200_EINVAL, "NULL argument");
+  return integrate_layer_a(c, scene, rs, depth_dev, rgb_dev, pose_M);
 }
 
 int itm_b200_create_expected_depths(itm_b200_ctx *c, const itm_b200_scene *scene, itm_b200_render_state *rs, const float pose_M[16],
@@ -589,7 +614,7 @@ namespace {
 int engine_alloc(itm_b200_engine *e) {
   itm_b200_ctx *c = e->c;
   const size_t P = (size_t)c->vp.W * c->vp.H;
-  if (!e->externalBuffers) CU(cudaMalloc(&e->voxels, (size_t)c->sp.nLocal * ITM_BLOCK_SIZE3 * 4));
+  if (!e->externalBuffers) CU(cudaMalloc(&e->voxels, (size_t)c->sp.nLocal * ITM_BLOCK_SIZE3 * 4 * c->sp.voxelWords));
   CU(cudaMalloc(&e->hash, (size_t)c->sp.nEntries * 16));
   CU(cudaMalloc(&e->vbaAllocList, (size_t)c->sp.nLocal * 4));
   CU(cudaMalloc(&e->excessAllocList, (size_t)c->sp.nExcess * 4));
@@ -606,7 +631,8 @@ int engine_alloc(itm_b200_engine *e) {
   CU(cudaEventCreateWithFlags(&e->rgbDone, cudaEventDisableTiming));
   CU(cudaMalloc(&e->depth, P * 4));
   for (int i = 0; i < 9; ++i) CU(cudaEventCreate(&e->ev[i]));
-  e->bytes[ITM_B200_BUF_VOXELS] = (size_t)c->sp.nLocal * ITM_BLOCK_SIZE3 * 4;
+  e->bytes[ITM_B200_BUF_VOXELS] = (size_t)c->sp.nLocal * ITM_BLOCK_SIZE3 * 4 * c->sp.voxelWords;
+  e->bytes[ITM_B200_BUF_RGB] = P * 4;
   e->bytes[ITM_B200_BUF_HASH] = (size_t)c->sp.nEntries * 16;
   e->bytes[ITM_B200_BUF_VBA_ALLOC_LIST] = (size_t)c->sp.nLocal * 4;
   e->bytes[ITM_B200_BUF_EXCESS_ALLOC_LIST] = (size_t)c->sp.nExcess * 4;
@@ -695,6 +721,7 @@ void stage_integrate(itm_b200_engine *e) {
   itm_b200_ctx *c = e->c;
   IntegrateArgs a;
   a.shard = e->shard;
+  fill_integrate_calib(c, a, e->rgb);
   a.depth = e->depth;
   a.voxels = e->voxels;
   a.hashTable = e->hash;
@@ -804,6 +831,7 @@ int itm_b200_engine_create_sharded(const itm_b200_params *params, const itm_b200
   *out = nullptr;
   if (shard->world < 1 || shard->world > ITM_MAX_SHARDS || shard->rank < 0 || shard->rank >= shard->world)
     return fail(ITM_B200_EINVAL, "rank / world out of range (at most 8 ranks)");
+  if (params && params->voxel_type != ITM_B200_VOXEL_S) return fail(ITM_B200_EUNSUPPORTED, "sharded engines support ITMVoxel_s only");
   for (int r = 0; r < shard->world; ++r)
     if (!shard->voxel_blocks_dev[r] || !shard->raycast_result_dev[r] || !shard->barrier_flags_dev[r])
       return fail(ITM_B200_EINVAL, "every rank's voxel, raycast and flag buffer must be given");
@@ -918,8 +946,10 @@ int itm_b200_engine_process_frame(itm_b200_engine *e, const unsigned char *rgb_h
     CU(cudaMemcpyAsync(e->rgb, rgb_host, P * 4, cudaMemcpyHostToDevice, e->copyStream));
     CU(cudaEventRecord(e->rgbDone, e->copyStream));
   }
+  // colour voxels read view->rgb during integration: then the frame waits for it up front
+  if (rgb_host && e->c->sp.voxelWords == 2) CU(cudaStreamWaitEvent(s, e->rgbDone, 0));
   enqueue_frame(e);
-  if (rgb_host) CU(cudaStreamWaitEvent(s, e->rgbDone, 0));
+  if (rgb_host && e->c->sp.voxelWords != 2) CU(cudaStreamWaitEvent(s, e->rgbDone, 0));
   return itm_b200_engine_sync(e, pose_out, nullptr);
 }
 
@@ -965,6 +995,7 @@ int itm_b200_engine_get_buffer(itm_b200_engine *e, int which, void **dev_ptr, si
     case ITM_B200_BUF_POINTS: p = e->points; break;
     case ITM_B200_BUF_NORMALS: p = e->normals; break;
     case ITM_B200_BUF_RAW_DEPTH: p = e->rawDepth; break;
+    case ITM_B200_BUF_RGB: p = e->rgb; break;
     case ITM_B200_BUF_PYRAMID_1: case ITM_B200_BUF_PYRAMID_2: case ITM_B200_BUF_PYRAMID_3: case ITM_B200_BUF_PYRAMID_4:
       p = e->c->pyramid[which - ITM_B200_BUF_PYRAMID_1 + 1]; break;
     default: return fail(ITM_B200_EINVAL, "unknown buffer id");

@@ -369,14 +369,13 @@ __global__ void __launch_bounds__(256) k_visible_scan(const unsigned char *__res
 }
 
 // ResetScene, ITMSceneReconstructionEngine_CPU.cpp:25-45
-__global__ void k_reset_scene(uint32_t *__restrict__ voxels, size_t nVoxels, int *__restrict__ vbaAllocList, int nLocal,
+__global__ void k_reset_scene(uint32_t *__restrict__ voxels, size_t nVectors, int *__restrict__ vbaAllocList, int nLocal,
                               HashEntry *__restrict__ table, int nEntries, int *__restrict__ excessAllocList, int nExcess,
-                              uint32_t emptyVoxel) {
+                              uint4 ev) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint4 *v4 = reinterpret_cast<uint4 *>(voxels);
-  const uint4 ev = make_uint4(emptyVoxel, emptyVoxel, emptyVoxel, emptyVoxel);
-  for (size_t i = tid; i < nVoxels / 4; i += stride) v4[i] = ev;
+  for (size_t i = tid; i < nVectors; i += stride) v4[i] = ev;
   for (size_t i = tid; i < (size_t)nLocal; i += stride) vbaAllocList[i] = (int)i;
   for (size_t i = tid; i < (size_t)nEntries; i += stride) store_entry(table, (int)i, 0, 0, 0, 0, -2);
   for (size_t i = tid; i < (size_t)nExcess; i += stride) excessAllocList[i] = (int)i;
@@ -393,10 +392,11 @@ int alloc_step_bound(const SceneParams &sp) {
 }
 
 void launch_reset_scene(void *voxels, int *vbaAllocList, void *table, int *excessAllocList, const SceneParams &sp, cudaStream_t s) {
-  // ITMVoxel_s(): sdf = 32767, w_depth = 0 (ITMLibDefines.h:175-178)
+  // ITMVoxel_s(): sdf = 32767, w_depth = 0 (ITMLibDefines.h:175-178); ITMVoxel_s_rgb(): + clr = 0, w_color = 0 (:149-154)
   const uint32_t emptyVoxel = 0x00007FFFu;
-  k_reset_scene<<<148 * 8, 256, 0, s>>>(reinterpret_cast<uint32_t *>(voxels), (size_t)sp.nLocal * ITM_BLOCK_SIZE3, vbaAllocList, sp.nLocal,
-                                       reinterpret_cast<HashEntry *>(table), sp.nEntries, excessAllocList, sp.nExcess, emptyVoxel);
+  const uint4 ev = sp.voxelWords == 2 ? make_uint4(emptyVoxel, 0u, emptyVoxel, 0u) : make_uint4(emptyVoxel, emptyVoxel, emptyVoxel, emptyVoxel);
+  k_reset_scene<<<148 * 8, 256, 0, s>>>(reinterpret_cast<uint32_t *>(voxels), (size_t)sp.nLocal * ITM_BLOCK_SIZE3 * sp.voxelWords / 4, vbaAllocList,
+                                       sp.nLocal, reinterpret_cast<HashEntry *>(table), sp.nEntries, excessAllocList, sp.nExcess, ev);
 }
 
 void launch_allocate(const AllocArgs &a, cudaStream_t s) {

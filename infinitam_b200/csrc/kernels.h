@@ -44,6 +44,9 @@ struct AllocArgs {
 
 struct IntegrateArgs {
   ShardInfo shard;
+  const unsigned char *rgb;   // view->rgb, Vector4u[W*H] (ITMVoxel_s_rgb only)
+  float rgbIntr[4];           // intrinsics_rgb (fx, fy, cx, cy)
+  float calibInv[16];         // trafo_rgb_to_depth.calib_inv
   const float *depth;
   void *voxels;
   const void *hashTable;

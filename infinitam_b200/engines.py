@@ -27,7 +27,7 @@ _BUF_DTYPES = {
     capi.BUF_DEPTH: np.float32, capi.BUF_MINMAX: np.float32, capi.BUF_RAYCAST_RESULT: np.float32,
     capi.BUF_RAYCAST_IMAGE: np.uint8, capi.BUF_POINTS: np.float32, capi.BUF_NORMALS: np.float32,
     capi.BUF_RAW_DEPTH: np.int16, capi.BUF_PYRAMID_1: np.float32, capi.BUF_PYRAMID_2: np.float32,
-    capi.BUF_PYRAMID_3: np.float32, capi.BUF_PYRAMID_4: np.float32,
+    capi.BUF_PYRAMID_3: np.float32, capi.BUF_PYRAMID_4: np.float32, capi.BUF_RGB: np.uint8,
 }
 
 
@@ -96,6 +96,8 @@ class ITMMainEngine:
     def read(self, which, count=None):
         _, nbytes = self.buffer_info(which)
         dt = np.dtype(_BUF_DTYPES[which])
+        if which == capi.BUF_VOXELS and self.params.voxel_type == capi.VOXEL_S_RGB:
+            dt = np.dtype(np.uint64)  # one word per ITMVoxel_s_rgb
         n = nbytes // dt.itemsize if count is None else count
         out = np.empty(n, dtype=dt)
         capi.check(self.lib.itm_b200_engine_read_buffer(self.h, which, out.ctypes.data, n * dt.itemsize, 0))

@@ -45,8 +45,13 @@ SOURCES = [
     "ITMLib/Engine/DeviceSpecific/CPU/ITMVisualisationEngine_CPU.cpp",
 ]
 
+# sources that ref_harness.cpp compiles itself (by #include) when it instantiates them for another voxel type
+VOXEL_DEPENDENT = ["ITMLib/Engine/DeviceSpecific/CPU/ITMSceneReconstructionEngine_CPU.cpp",
+                   "ITMLib/Engine/DeviceSpecific/CPU/ITMVisualisationEngine_CPU.cpp"]
+
 FLAVOURS = {
     "libitm_ref.so": ["-O2", "-ffp-contract=off"],
+    "libitm_ref_rgb.so": ["-O2", "-ffp-contract=off", "-DREF_VOXEL_RGB"],  # ITMVoxel_s_rgb, parity flags
     "libitm_ref_fast.so": ["-O3", "-mavx2", "-mfma", "-fopenmp", "-DWITH_OPENMP"],
     "libitm_ref_fast1.so": ["-O3", "-mavx2", "-mfma"],
 }
@@ -76,6 +81,8 @@ def build(flavours=None, force=False):
         os.makedirs(objdir, exist_ok=True)
         jobs = []
         for src in SOURCES + [harness]:
+            if "-DREF_VOXEL_RGB" in flags and src in VOXEL_DEPENDENT:
+                continue
             path = src if os.path.isabs(src) else os.path.join(REF, src)
             obj = os.path.join(objdir, os.path.basename(src).replace(".cpp", ".o"))
             jobs.append((["g++"] + COMMON + flags + ["-c", path, "-o", obj], obj))

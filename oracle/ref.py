@@ -23,7 +23,7 @@ VOXEL_S_DTYPE = np.dtype({"names": ["sdf", "w_depth"], "formats": ["<i2", "u1"],
 
 
 def lib_path(flavour: str = "parity") -> str:
-    name = {"parity": "libitm_ref.so", "fast": "libitm_ref_fast.so", "fast1": "libitm_ref_fast1.so"}[flavour]
+    name = {"parity": "libitm_ref.so", "fast": "libitm_ref_fast.so", "fast1": "libitm_ref_fast1.so", "rgb": "libitm_ref_rgb.so"}[flavour]
     return os.path.join(REF_DIR, name)
 
 
@@ -64,6 +64,9 @@ def declare_common(lib):
                  "ref_icp_prepare"):
         getattr(lib, name).restype = None
         getattr(lib, name).argtypes = [C.c_void_p]
+    if hasattr(lib._lib if isinstance(lib, _Prefixed) else lib, (lib._prefix if isinstance(lib, _Prefixed) else "ref") + "_set_rgb"):
+        lib.ref_set_rgb.argtypes = [C.c_void_p, C.c_void_p]
+        lib.ref_set_rgb.restype = None
     lib.ref_update_view.argtypes = [C.c_void_p, C.c_void_p]
     lib.ref_update_view.restype = None
     lib.ref_process_frame.argtypes = [C.c_void_p, C.c_void_p]
@@ -143,6 +146,12 @@ class RefEngine:
             pass
 
     # ---- stages -------------------------------------------------------------
+    def set_rgb(self, rgba_u8):
+        """view->rgb of the following frames, (H, W, 4) uint8"""
+        a = np.ascontiguousarray(rgba_u8, dtype=np.uint8)
+        assert a.size == self.W * self.H * 4
+        self.lib.ref_set_rgb(self.h, a.ctypes.data)
+
     def update_view(self, depth_i16):
         d = np.ascontiguousarray(depth_i16, dtype=np.int16)
         self.lib.ref_update_view(self.h, d.ctypes.data)
@@ -264,8 +273,10 @@ class RefEngine:
 
     @property
     def voxels(self):
-        """raw uint32 view, one word per ITMVoxel_s (sdf | w_depth<<16 | pad<<24)"""
-        return _view(self.lib.ref_voxels(self.h), np.uint32, self.n_local * 512)
+        """raw view, one word per voxel: uint32 for ITMVoxel_s (sdf | w_depth<<16 | pad<<24), uint64 for ITMVoxel_s_rgb
+        (sdf | w_depth<<16 | clr.r<<24 | clr.g<<32 | clr.b<<40 | w_color<<48 | pad<<56)"""
+        dt = np.uint64 if self.const("sizeof_voxel") == 8 else np.uint32
+        return _view(self.lib.ref_voxels(self.h), dt, self.n_local * 512)
 
     @property
     def vba_alloc_list(self):

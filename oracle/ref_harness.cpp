@@ -32,8 +32,19 @@
 using namespace ITMLib::Engine;
 using namespace ITMLib::Objects;
 
-typedef ITMVoxel TV;
 typedef ITMVoxelIndex TI;
+#ifdef REF_VOXEL_RGB
+// Colour flavour (BASELINE configs[4]).  The reference fixes its voxel type with a typedef (ITMLib/Utils/ITMLibDefines.h:205)
+// and instantiates its engine templates for that type only, at the end of each .cpp.  Instead of patching a copy of the
+// header, the two voxel-dependent engine sources are compiled HERE, where they lie, and instantiated for ITMVoxel_s_rgb.
+typedef ITMVoxel_s_rgb TV;
+#include "ITMLib/Engine/DeviceSpecific/CPU/ITMSceneReconstructionEngine_CPU.cpp"
+#include "ITMLib/Engine/DeviceSpecific/CPU/ITMVisualisationEngine_CPU.cpp"
+template class ITMLib::Engine::ITMSceneReconstructionEngine_CPU<ITMVoxel_s_rgb, ITMVoxelBlockHash>;
+template class ITMLib::Engine::ITMVisualisationEngine_CPU<ITMVoxel_s_rgb, ITMVoxelBlockHash>;
+#else
+typedef ITMVoxel TV;
+#endif
 
 struct ref_engine {
   ITMLibSettings *settings;
@@ -139,6 +150,11 @@ void ref_destroy(ref_engine *e) {
 }
 
 // ---- stages, in ProcessFrame order (ITMMainEngine.cpp:111-127) -------------
+// colour image of the next frames (Vector4u[w*h]); the default is constant grey
+void ref_set_rgb(ref_engine *e, const unsigned char *rgba) {
+  memcpy(e->rgb->GetData(MEMORYDEVICE_CPU), rgba, (size_t)e->imgSize.x * e->imgSize.y * 4);
+}
+
 void ref_update_view(ref_engine *e, const short *depth) {
   memcpy(e->rawDepth->GetData(MEMORYDEVICE_CPU), depth, (size_t)e->imgSize.x * e->imgSize.y * sizeof(short));
   e->viewBuilder->UpdateView(&e->view, e->rgb, e->rawDepth, false, false);

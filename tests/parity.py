@@ -25,6 +25,9 @@ def make_cuda_engine(oracle) -> ITMMainEngine:
     p.voxel_size, p.mu, p.max_w = oracle.voxel_size, oracle.mu, oracle.max_w
     p.view_frustum_min, p.view_frustum_max = oracle.vf_min, oracle.vf_max
     p.sdf_local_block_num, p.sdf_bucket_num, p.sdf_excess_list_size = oracle.n_local, oracle.n_bucket, oracle.n_excess
+    p.rgb_fx, p.rgb_fy, p.rgb_cx, p.rgb_cy = oracle.intr
+    if oracle.const("sizeof_voxel") == 8:
+        p.voxel_type = capi.VOXEL_S_RGB
     return ITMMainEngine(p)
 
 
@@ -56,12 +59,25 @@ def hash_equal(a, b):
 
 def voxel_diff(a_u32, b_u32):
     """max |sdf| and |w| difference between two ITMVoxel_s arrays given as uint32 words"""
+    a_u32, b_u32 = a_u32.astype(np.uint32), b_u32.astype(np.uint32)  # uint64 words of ITMVoxel_s_rgb: the low half
     sa = (a_u32 & 0xFFFF).astype(np.uint16).view(np.int16).astype(np.int32)
     sb = (b_u32 & 0xFFFF).astype(np.uint16).view(np.int16).astype(np.int32)
     wa = ((a_u32 >> 16) & 0xFF).astype(np.int32)
     wb = ((b_u32 >> 16) & 0xFF).astype(np.int32)
     ds, dw = np.abs(sa - sb), np.abs(wa - wb)
     return int(ds.max()), int(dw.max()), int(np.count_nonzero(ds)), int(np.count_nonzero(dw))
+
+
+def voxel_colour_diff(a_u64, b_u64):
+    """max difference of clr.r/g/b and of w_color between two ITMVoxel_s_rgb arrays given as uint64 words"""
+    d = 0
+    for shift in (24, 32, 40):
+        ca = ((a_u64 >> np.uint64(shift)) & np.uint64(0xFF)).astype(np.int32)
+        cb = ((b_u64 >> np.uint64(shift)) & np.uint64(0xFF)).astype(np.int32)
+        d = max(d, int(np.abs(ca - cb).max()))
+    wa = ((a_u64 >> np.uint64(48)) & np.uint64(0xFF)).astype(np.int32)
+    wb = ((b_u64 >> np.uint64(48)) & np.uint64(0xFF)).astype(np.int32)
+    return d, int(np.abs(wa - wb).max())
 
 
 def pose_diff(Ma, Mb):
@@ -146,6 +162,11 @@ def compare_frame(oracle, eng: ITMMainEngine, depth_i16, frame_no, report=None, 
     ds, dw, ns, nw = voxel_diff(v_gpu, oracle.voxels)
     r["voxel_max_dsdf"], r["voxel_max_dw"], r["voxel_n_dsdf"], r["voxel_n_dw"] = ds, dw, ns, nw
     check(ds <= 1 and dw <= 1, "voxels differ by more than 1 LSB: sdf %d w %d" % (ds, dw))
+    if v_gpu.dtype == np.uint64:
+        dc, dwc = voxel_colour_diff(v_gpu, oracle.voxels)
+        r["voxel_max_dclr"], r["voxel_max_dwcolor"] = dc, dwc
+        ns += int(np.count_nonzero((v_gpu ^ oracle.voxels) & np.uint64(0x00FFFFFFFFFFFFFF)))
+        check(dc <= 1 and dwc <= 1, "voxel colours differ by more than 1 LSB: clr %d w_color %d" % (dc, dwc))
     if ns or nw:
         eng.write(capi.BUF_VOXELS, oracle.voxels)  # keep teacher forcing exact
 
