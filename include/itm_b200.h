@@ -74,6 +74,9 @@ typedef struct itm_b200_params {
   int voxel_type;
   float rgb_fx, rgb_fy, rgb_cx, rgb_cy;      /* calib.intrinsics_rgb.projectionParamsSimple.all (rgb image = depth image size) */
   float trafo_rgb_to_depth_inv[16];  /* calib.trafo_rgb_to_depth.calib_inv, column-major (identity by default) */
+  /* settings.useSwapping (ITMLibSettings.cpp:35, off by default): Layer B keeps an ITMGlobalCache in host memory and runs
+   * ITMSwappingEngine::IntegrateGlobalIntoLocal / SaveToGlobalMemory after every integration (ITMDenseMapper.cpp:59-64) */
+  int use_swapping;
 } itm_b200_params;
 #define ITM_B200_VOXEL_S 0
 #define ITM_B200_VOXEL_S_RGB 1
@@ -226,7 +229,8 @@ int itm_b200_engine_sync(itm_b200_engine *e, float pose_out[16], int counters[6]
 
 /* Single stages on the engine's own state, for stage-by-stage parity tests ("teacher forcing"):
  * 0 view (needs a frame uploaded with itm_b200_engine_upload_depth), 1 track, 2 allocate,
- * 3 integrate, 4 expected depths, 5 raycast + ICP maps. */
+ * 3 integrate, 4 expected depths, 5 raycast + ICP maps, 6 swap in / out (use_swapping engines; part of stage 3's slot in
+ * a whole frame, ITMDenseMapper.cpp:59-64). */
 int itm_b200_engine_upload_depth(itm_b200_engine *e, const short *raw_depth_host);
 int itm_b200_engine_run_stage(itm_b200_engine *e, int stage);
 
@@ -235,13 +239,19 @@ enum {
   ITM_B200_BUF_VOXELS = 0, ITM_B200_BUF_HASH, ITM_B200_BUF_VBA_ALLOC_LIST, ITM_B200_BUF_EXCESS_ALLOC_LIST,
   ITM_B200_BUF_VISIBLE_IDS, ITM_B200_BUF_VISIBLE_TYPES, ITM_B200_BUF_DEPTH, ITM_B200_BUF_MINMAX, ITM_B200_BUF_RAYCAST_RESULT,
   ITM_B200_BUF_RAYCAST_IMAGE, ITM_B200_BUF_POINTS, ITM_B200_BUF_NORMALS, ITM_B200_BUF_RAW_DEPTH, ITM_B200_BUF_PYRAMID_1,
-  ITM_B200_BUF_PYRAMID_2, ITM_B200_BUF_PYRAMID_3, ITM_B200_BUF_PYRAMID_4, ITM_B200_BUF_RGB, ITM_B200_BUF_COUNT
+  ITM_B200_BUF_PYRAMID_2, ITM_B200_BUF_PYRAMID_3, ITM_B200_BUF_PYRAMID_4, ITM_B200_BUF_RGB, ITM_B200_BUF_SWAP_STATES,
+  ITM_B200_BUF_COUNT
 };
 int itm_b200_engine_get_buffer(itm_b200_engine *e, int which, void **dev_ptr, size_t *bytes);
 /* Blocking copies between one of those buffers and host memory (the reference's
  * MemoryBlock::UpdateHostFromDevice / UpdateDeviceFromHost, ORUtils/MemoryBlock.h:112-121). */
 int itm_b200_engine_read_buffer(itm_b200_engine *e, int which, void *host_dst, size_t bytes, size_t offset);
 int itm_b200_engine_write_buffer(itm_b200_engine *e, int which, const void *host_src, size_t bytes, size_t offset);
+
+/* ITMGlobalCache of a swapping engine (host memory, borrowed): hasStoredData[bucket+excess] and the stored voxel
+ * blocks (ITMLib/Objects/ITMGlobalCache.h:21-36).  *swapped_in / *swapped_out: entries moved by the last frame. */
+int itm_b200_engine_global_cache(itm_b200_engine *e, const unsigned char **has_stored_data, const void **stored_voxel_blocks,
+                                 int *swapped_in, int *swapped_out);
 
 /* Host-visible tracking / scene state: pose_d, pose_pointCloud (column-major), and
  * state6 = {noVisibleEntries, lastFreeBlockId, lastFreeExcessListId, age_pointCloud, 0, 0}. */

@@ -18,10 +18,10 @@ ITER_ROTATION, ITER_TRANSLATION, ITER_BOTH, ITER_NONE = 1, 2, 3, 4
 
 (BUF_VOXELS, BUF_HASH, BUF_VBA_ALLOC_LIST, BUF_EXCESS_ALLOC_LIST, BUF_VISIBLE_IDS, BUF_VISIBLE_TYPES, BUF_DEPTH,
  BUF_MINMAX, BUF_RAYCAST_RESULT, BUF_RAYCAST_IMAGE, BUF_POINTS, BUF_NORMALS, BUF_RAW_DEPTH, BUF_PYRAMID_1,
- BUF_PYRAMID_2, BUF_PYRAMID_3, BUF_PYRAMID_4, BUF_RGB, BUF_COUNT) = range(19)
+ BUF_PYRAMID_2, BUF_PYRAMID_3, BUF_PYRAMID_4, BUF_RGB, BUF_SWAP_STATES, BUF_COUNT) = range(20)
 VOXEL_S, VOXEL_S_RGB = 0, 1
 
-STAGE_VIEW, STAGE_TRACK, STAGE_ALLOCATE, STAGE_INTEGRATE, STAGE_EXPECTED_DEPTHS, STAGE_ICP_MAPS = range(6)
+STAGE_VIEW, STAGE_TRACK, STAGE_ALLOCATE, STAGE_INTEGRATE, STAGE_EXPECTED_DEPTHS, STAGE_ICP_MAPS, STAGE_SWAP = range(7)
 
 
 class Params(C.Structure):
@@ -40,6 +40,7 @@ class Params(C.Structure):
         ("voxel_type", C.c_int),
         ("rgb_fx", C.c_float), ("rgb_fy", C.c_float), ("rgb_cx", C.c_float), ("rgb_cy", C.c_float),
         ("trafo_rgb_to_depth_inv", C.c_float * 16),
+        ("use_swapping", C.c_int),
     ]
 
 
@@ -90,7 +91,7 @@ SYMBOLS = [
     "itm_b200_engine_create_sharded", "itm_b200_ipc_alloc", "itm_b200_ipc_open", "itm_b200_ipc_close", "itm_b200_ipc_free",
     "itm_b200_shard_owner_of_block", "itm_b200_engine_process_frame", "itm_b200_engine_enqueue_frame_dev", "itm_b200_engine_sync",
     "itm_b200_engine_upload_depth", "itm_b200_engine_run_stage", "itm_b200_engine_get_buffer",
-    "itm_b200_engine_read_buffer", "itm_b200_engine_write_buffer", "itm_b200_engine_get_state",
+    "itm_b200_engine_read_buffer", "itm_b200_engine_write_buffer", "itm_b200_engine_global_cache", "itm_b200_engine_get_state",
     "itm_b200_engine_set_state", "itm_b200_engine_icp_stats", "itm_b200_engine_set_profiling", "itm_b200_engine_stage_times",
     "itm_b200_mat4_inv", "itm_b200_pose_from_inv_m_coerced", "itm_b200_compute_delta",
 ]
@@ -150,6 +151,7 @@ def load():
     lib.itm_b200_engine_get_buffer.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)]
     lib.itm_b200_engine_read_buffer.argtypes = [vp, C.c_int, vp, C.c_size_t, C.c_size_t]
     lib.itm_b200_engine_write_buffer.argtypes = [vp, C.c_int, vp, C.c_size_t, C.c_size_t]
+    lib.itm_b200_engine_global_cache.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), i32p, i32p]
     lib.itm_b200_engine_get_state.argtypes = [vp, f32p, f32p, i32p]
     lib.itm_b200_engine_set_state.argtypes = [vp, f32p, f32p, i32p]
     lib.itm_b200_engine_icp_stats.argtypes = [vp, i32p]

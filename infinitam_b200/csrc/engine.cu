@@ -233,6 +233,7 @@ AllocArgs make_alloc_args(itm_b200_ctx *c, const float *depth, void *hash, const
   a.vp = c->vp;
   a.sp = c->sp;
   a.onlyUpdateVisibleList = onlyVisible;
+  a.swapStates = nullptr;
   a.prologueDone = 0;
   return a;
 }
@@ -601,6 +602,19 @@ struct itm_b200_engine {
   int agePointCloud = -1;  // host copy; its evolution does not depend on device results
   bool prologueDone = false;  // this frame's view kernel already did the FramePrologue chores
   ShardInfo shard;            // world == 1 unless created with itm_b200_engine_create_sharded
+  // swapping (settings.useSwapping): ITMGlobalCache
+  unsigned char *swapStates = nullptr;      // device, ITMHashSwapState[nEntries]
+  int *neededIds = nullptr;                 // device
+  void *transfer = nullptr;                 // device, syncedVoxelBlocks
+  unsigned char *hasSynced = nullptr;       // device
+  int *neededIdsHost = nullptr;             // pinned
+  void *transferHost = nullptr;             // pinned
+  unsigned char *hasSyncedHost = nullptr;   // pinned
+  unsigned char *hasStoredData = nullptr;   // host, [nEntries]
+  char *storedVoxelBlocks = nullptr;        // host, [nEntries] blocks (allocated lazily by the OS)
+  unsigned long long *swapTileState = nullptr;
+  unsigned long long *swapTicket = nullptr;
+  int lastSwappedIn = 0, lastSwappedOut = 0;
   bool externalBuffers = false;  // voxels / raycastResult belong to the caller (sharded engines)
   unsigned barrierSeq = 0;
   bool profiling = false;
@@ -631,6 +645,25 @@ int engine_alloc(itm_b200_engine *e) {
   CU(cudaEventCreateWithFlags(&e->rgbDone, cudaEventDisableTiming));
   CU(cudaMalloc(&e->depth, P * 4));
   for (int i = 0; i < 9; ++i) CU(cudaEventCreate(&e->ev[i]));
+  if (c->p.use_swapping) {
+    const size_t blockBytes = (size_t)ITM_BLOCK_SIZE3 * 4 * c->sp.voxelWords;
+    const int numTiles = (c->sp.nEntries + 8191) / 8192;
+    CU(cudaMalloc(&e->swapStates, (size_t)numTiles * 8192));
+    CU(cudaMalloc(&e->neededIds, ITM_TRANSFER_BLOCK_NUM * sizeof(int)));
+    CU(cudaMalloc(&e->transfer, ITM_TRANSFER_BLOCK_NUM * blockBytes));
+    CU(cudaMalloc(&e->hasSynced, ITM_TRANSFER_BLOCK_NUM));
+    CU(cudaMallocHost(&e->neededIdsHost, ITM_TRANSFER_BLOCK_NUM * sizeof(int)));
+    CU(cudaMallocHost(&e->transferHost, ITM_TRANSFER_BLOCK_NUM * blockBytes));
+    CU(cudaMallocHost(&e->hasSyncedHost, ITM_TRANSFER_BLOCK_NUM));
+    CU(cudaMalloc(&e->swapTileState, numTiles * sizeof(unsigned long long)));
+    CU(cudaMemset(e->swapTileState, 0, numTiles * sizeof(unsigned long long)));
+    CU(cudaMalloc(&e->swapTicket, sizeof(unsigned long long)));
+    CU(cudaMemset(e->swapTicket, 0, sizeof(unsigned long long)));
+    e->hasStoredData = (unsigned char *)calloc(c->sp.nEntries, 1);
+    e->storedVoxelBlocks = (char *)malloc((size_t)c->sp.nEntries * blockBytes);
+    if (!e->hasStoredData || !e->storedVoxelBlocks) return fail(ITM_B200_ECUDA, "host memory for the global cache");
+    e->bytes[ITM_B200_BUF_SWAP_STATES] = (size_t)c->sp.nEntries;
+  }
   e->bytes[ITM_B200_BUF_VOXELS] = (size_t)c->sp.nLocal * ITM_BLOCK_SIZE3 * 4 * c->sp.voxelWords;
   e->bytes[ITM_B200_BUF_RGB] = P * 4;
   e->bytes[ITM_B200_BUF_HASH] = (size_t)c->sp.nEntries * 16;
@@ -656,6 +689,12 @@ void engine_free(itm_b200_engine *e) {
   cudaFree(e->visibleIds); cudaFree(e->visType); cudaFree(e->minmax);
   cudaFree(e->raycastImage); cudaFree(e->points); cudaFree(e->normals); cudaFree(e->rawDepth);
   cudaFree(e->rgb); cudaFree(e->depth);
+  cudaFree(e->swapStates); cudaFree(e->neededIds); cudaFree(e->transfer); cudaFree(e->hasSynced);
+  cudaFree(e->swapTileState); cudaFree(e->swapTicket);
+  if (e->neededIdsHost) cudaFreeHost(e->neededIdsHost);
+  if (e->transferHost) cudaFreeHost(e->transferHost);
+  if (e->hasSyncedHost) cudaFreeHost(e->hasSyncedHost);
+  free(e->hasStoredData); free(e->storedVoxelBlocks);
   if (e->copyStream) cudaStreamDestroy(e->copyStream);
   if (e->rgbDone) cudaEventDestroy(e->rgbDone);
   for (int i = 0; i < 9; ++i)
@@ -681,6 +720,10 @@ int engine_reset(itm_b200_engine *e) {
   CU(cudaMemsetAsync(e->minmax, 0, P * 8, c->stream));
   CU(cudaMemsetAsync(e->depth, 0, P * 4, c->stream));
   CU(cudaMemsetAsync(c->allocKey, 0, (size_t)((c->sp.nEntries + 8191) / 8192) * 8192 * sizeof(unsigned), c->stream));
+  if (e->swapStates) {
+    CU(cudaMemsetAsync(e->swapStates, 0, (size_t)((c->sp.nEntries + 8191) / 8192) * 8192, c->stream));
+    memset(e->hasStoredData, 0, c->sp.nEntries);
+  }
   host_state_init(c->hst, c->sp);
   int rc = push_state(c);
   if (rc) return rc;
@@ -713,6 +756,7 @@ void stage_allocate(itm_b200_engine *e) {
   itm_b200_ctx *c = e->c;
   AllocArgs a = make_alloc_args(c, e->depth, e->hash, e->vbaAllocList, e->excessAllocList, e->visibleIds, e->visType, 0);
   a.prologueDone = e->prologueDone ? 1 : 0;
+  a.swapStates = e->swapStates;
   launch_allocate(a, c->stream);
   g_launches += e->prologueDone ? 3 : 4;
 }
@@ -772,6 +816,56 @@ void stage_icp_maps(itm_b200_engine *e) {
   else e->agePointCloud = 0;
 }
 
+// ITMSwappingEngine::IntegrateGlobalIntoLocal + SaveToGlobalMemory (ITMDenseMapper.cpp:59-64).  Unlike the rest of the
+// frame this needs the host in the loop (the global cache is host memory): two list read-backs and the block transfers.
+int stage_swap(itm_b200_engine *e) {
+  itm_b200_ctx *c = e->c;
+  cudaStream_t s = c->stream;
+  const size_t blockBytes = (size_t)ITM_BLOCK_SIZE3 * 4 * c->sp.voxelWords;
+  SwapArgs a;
+  a.voxels = e->voxels; a.hashTable = e->hash; a.vbaAllocList = e->vbaAllocList; a.visType = e->visType; a.swapStates = e->swapStates;
+  a.neededIds = e->neededIds; a.transfer = e->transfer; a.hasSynced = e->hasSynced; a.ticket = e->swapTicket; a.tileState = e->swapTileState;
+  a.st = c->st; a.sp = c->sp;
+  // ---- host -> active memory (ITMSwappingEngine_CPU.cpp:69-104)
+  launch_swap_select(a, 0, s);
+  g_launches += 1;
+  CU(cudaMemcpyAsync(e->neededIdsHost, e->neededIds, ITM_TRANSFER_BLOCK_NUM * sizeof(int), cudaMemcpyDeviceToHost, s));
+  int rc = pull_state(c);
+  if (rc) return rc;
+  const int nIn = c->hst->swapCount;
+  for (int i = 0; i < nIn; ++i) {  // LoadFromGlobalMemory (:47-60)
+    const int id = e->neededIdsHost[i];
+    e->hasSyncedHost[i] = e->hasStoredData[id];
+    if (e->hasStoredData[id]) memcpy((char *)e->transferHost + (size_t)i * blockBytes, e->storedVoxelBlocks + (size_t)id * blockBytes, blockBytes);
+  }
+  if (nIn > 0) {
+    CU(cudaMemcpyAsync(e->hasSynced, e->hasSyncedHost, nIn, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(e->transfer, e->transferHost, (size_t)nIn * blockBytes, cudaMemcpyHostToDevice, s));
+    launch_swap_in_apply(a, s);
+    g_launches += 1;
+  }
+  // ---- active memory -> host (:107-176)
+  launch_swap_select(a, 1, s);
+  launch_swap_out_apply(a, s);
+  g_launches += 2;
+  CU(cudaMemcpyAsync(e->neededIdsHost, e->neededIds, ITM_TRANSFER_BLOCK_NUM * sizeof(int), cudaMemcpyDeviceToHost, s));
+  rc = pull_state(c);
+  if (rc) return rc;
+  const int nOut = c->hst->swapCount;
+  if (nOut > 0) {
+    CU(cudaMemcpyAsync(e->transferHost, e->transfer, (size_t)nOut * blockBytes, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    for (int i = 0; i < nOut; ++i) {  // SetStoredData (:168-174)
+      const int id = e->neededIdsHost[i];
+      e->hasStoredData[id] = 1;
+      memcpy(e->storedVoxelBlocks + (size_t)id * blockBytes, (char *)e->transferHost + (size_t)i * blockBytes, blockBytes);
+    }
+  }
+  e->lastSwappedIn = nIn;
+  e->lastSwappedOut = nOut;
+  return ITM_B200_OK;
+}
+
 void stage_shard_barrier(itm_b200_engine *e) {
   if (e->shard.world > 1) {
     launch_shard_barrier(e->shard, ++e->barrierSeq, e->c->stream);
@@ -791,6 +885,7 @@ void enqueue_frame(itm_b200_engine *e) {
   if (prof) cudaEventRecord(e->ev[4], s);
   stage_integrate(e);
   stage_shard_barrier(e);  // every rank's share of the voxel updates has landed in every copy
+  if (e->swapStates) stage_swap(e);
   if (prof) cudaEventRecord(e->ev[5], s);
   stage_expected_depths(e);
   if (prof) cudaEventRecord(e->ev[6], s);
@@ -831,7 +926,8 @@ int itm_b200_engine_create_sharded(const itm_b200_params *params, const itm_b200
   *out = nullptr;
   if (shard->world < 1 || shard->world > ITM_MAX_SHARDS || shard->rank < 0 || shard->rank >= shard->world)
     return fail(ITM_B200_EINVAL, "rank / world out of range (at most 8 ranks)");
-  if (params && params->voxel_type != ITM_B200_VOXEL_S) return fail(ITM_B200_EUNSUPPORTED, "sharded engines support ITMVoxel_s only");
+  if (params && (params->voxel_type != ITM_B200_VOXEL_S || params->use_swapping))
+    return fail(ITM_B200_EUNSUPPORTED, "sharded engines support ITMVoxel_s without swapping only");
   for (int r = 0; r < shard->world; ++r)
     if (!shard->voxel_blocks_dev[r] || !shard->raycast_result_dev[r] || !shard->barrier_flags_dev[r])
       return fail(ITM_B200_EINVAL, "every rank's voxel, raycast and flag buffer must be given");
@@ -971,6 +1067,7 @@ int itm_b200_engine_run_stage(itm_b200_engine *e, int stage) {
     case 1: stage_track(e); break;
     case 2: stage_allocate(e); break;
     case 3: stage_integrate(e); stage_shard_barrier(e); break;
+    case 6: if (!e->swapStates) return fail(ITM_B200_EINVAL, "engine was created without use_swapping"); { int rc = stage_swap(e); if (rc) return rc; } break;
     case 4: stage_expected_depths(e); break;
     case 5: stage_raycast(e); stage_shard_barrier(e); stage_icp_maps(e); break;
     default: return fail(ITM_B200_EINVAL, "unknown stage");
@@ -996,6 +1093,7 @@ int itm_b200_engine_get_buffer(itm_b200_engine *e, int which, void **dev_ptr, si
     case ITM_B200_BUF_NORMALS: p = e->normals; break;
     case ITM_B200_BUF_RAW_DEPTH: p = e->rawDepth; break;
     case ITM_B200_BUF_RGB: p = e->rgb; break;
+    case ITM_B200_BUF_SWAP_STATES: p = e->swapStates; break;
     case ITM_B200_BUF_PYRAMID_1: case ITM_B200_BUF_PYRAMID_2: case ITM_B200_BUF_PYRAMID_3: case ITM_B200_BUF_PYRAMID_4:
       p = e->c->pyramid[which - ITM_B200_BUF_PYRAMID_1 + 1]; break;
     default: return fail(ITM_B200_EINVAL, "unknown buffer id");
@@ -1024,6 +1122,17 @@ int itm_b200_engine_write_buffer(itm_b200_engine *e, int which, const void *host
   if (!host_src || offset + bytes > total) return fail(ITM_B200_EINVAL, "write_buffer: range outside the buffer");
   CU(cudaMemcpyAsync((char *)p + offset, host_src, bytes, cudaMemcpyHostToDevice, e->c->stream));
   CU(cudaStreamSynchronize(e->c->stream));
+  return ITM_B200_OK;
+}
+
+int itm_b200_engine_global_cache(itm_b200_engine *e, const unsigned char **has_stored_data, const void **stored_voxel_blocks,
+                                 int *swapped_in, int *swapped_out) {
+  if (!e) return fail(ITM_B200_EINVAL, "NULL engine");
+  if (!e->swapStates) return fail(ITM_B200_EINVAL, "engine was created without use_swapping");
+  if (has_stored_data) *has_stored_data = e->hasStoredData;
+  if (stored_voxel_blocks) *stored_voxel_blocks = e->storedVoxelBlocks;
+  if (swapped_in) *swapped_in = e->lastSwappedIn;
+  if (swapped_out) *swapped_out = e->lastSwappedOut;
   return ITM_B200_OK;
 }
 

@@ -141,6 +141,43 @@ __device__ __forceinline__ bool point_visible(const float *M, float x, float y, 
   return bx >= 0 && bx < (float)vp.W && by >= 0 && by < (float)vp.H;
 }
 
+// checkPointVisibility<true>'s second answer (:262-273): inside the image enlarged by 1/8 on every side
+__device__ __forceinline__ bool point_visible_enlarged(const float *M, float x, float y, float z, const ViewParams &vp) {
+  float bx, by, bz;
+  mat4_mul_vec4(M, x, y, z, 1.0f, bx, by, bz);
+  if (bz < 1e-10f) return false;
+  bx = vp.fx * bx / bz + vp.cx;
+  by = vp.fy * by / bz + vp.cy;
+  const int lx = -vp.W / 8, ux = vp.W + vp.W / 8, ly = -vp.H / 8, uy = vp.H + vp.H / 8;
+  return bx >= (float)lx && bx < (float)ux && by >= (float)ly && by < (float)uy;
+}
+
+// checkBlockVisibility<true>'s isVisibleEnlarged: some corner lies in the enlarged image (a corner inside the image
+// proper ends the reference's walk early, but it is inside the enlarged one too)
+__device__ __noinline__ bool block_visible_enlarged(const float *M, int hx, int hy, int hz, float voxelSize, const ViewParams &vp) {
+  const float factor = (float)ITM_BLOCK_SIZE * voxelSize;
+  float x = (float)hx * factor, y = (float)hy * factor, z = (float)hz * factor;
+  if (point_visible_enlarged(M, x, y, z, vp)) return true;  // 0 0 0
+  z += factor;
+  if (point_visible_enlarged(M, x, y, z, vp)) return true;  // 0 0 1
+  y += factor;
+  if (point_visible_enlarged(M, x, y, z, vp)) return true;  // 0 1 1
+  x += factor;
+  if (point_visible_enlarged(M, x, y, z, vp)) return true;  // 1 1 1
+  z -= factor;
+  if (point_visible_enlarged(M, x, y, z, vp)) return true;  // 1 1 0
+  y -= factor;
+  if (point_visible_enlarged(M, x, y, z, vp)) return true;  // 1 0 0
+  x -= factor;
+  y += factor;
+  if (point_visible_enlarged(M, x, y, z, vp)) return true;  // 0 1 0
+  x += factor;
+  y -= factor;
+  z += factor;
+  if (point_visible_enlarged(M, x, y, z, vp)) return true;  // 1 0 1
+  return false;
+}
+
 // checkBlockVisibility<false>, :277-342 - the corner coordinates are built by the same chain of
 // += / -= as the reference so that they round identically
 __device__ __noinline__ bool block_visible(const float *M, int hx, int hy, int hz, float voxelSize, const ViewParams &vp) {
@@ -178,7 +215,7 @@ __global__ void __launch_bounds__(256) k_alloc_scan(unsigned *__restrict__ alloc
                                                     FrameState *st, ViewParams vp, SceneParams sp, float oneOverVoxelSize,
                                                     int stepBound, int doAllocate, unsigned long long *ticket,
                                                     unsigned long long *tileState, int numTiles,
-                                                    const int *__restrict__ prevVisibleIds) {
+                                                    const int *__restrict__ prevVisibleIds, int useSwapping) {
   __shared__ unsigned sWarp[8];
   __shared__ unsigned sTotal;
   __shared__ unsigned sExA, sExB;
@@ -203,7 +240,9 @@ __global__ void __launch_bounds__(256) k_alloc_scan(unsigned *__restrict__ alloc
       const int id = __ldg(prevVisibleIds + i);
       if (visType[id] == 3) {
         const HashEntry e = load_entry(table, id);
-        if (!block_visible(sM, e.px, e.py, e.pz, sp.voxelSize, vp)) visType[id] = 0;
+        const bool keep = useSwapping ? block_visible_enlarged(sM, e.px, e.py, e.pz, sp.voxelSize, vp)
+                                      : block_visible(sM, e.px, e.py, e.pz, sp.voxelSize, vp);
+        if (!keep) visType[id] = 0;
       }
     }
   }
@@ -250,6 +289,7 @@ __global__ void __launch_bounds__(256) k_alloc_scan(unsigned *__restrict__ alloc
         // counters always count down by the number of requests, successful or not (:186, :204-205)
         st->lastFreeBlockId = st->allocBaseBlockId - (int)(exA + (sTotal & 0xFFFFu));
         st->lastFreeExcessId = st->allocBaseExcessId - (int)(exB + (sTotal >> 16));
+        st->reallocBaseBlockId = st->lastFreeBlockId;
       }
     }
   }
@@ -297,13 +337,17 @@ __global__ void __launch_bounds__(256) k_alloc_scan(unsigned *__restrict__ alloc
   }
 }
 
+// swapStates != NULL (scene->useSwapping, not onlyUpdateVisibleList): visible entries whose data is not the most recent copy
+// are flagged for swap-in (..._CPU.cpp:250-253), and visible entries that were swapped out (ptr == -1) get a voxel block
+// again, in ascending slot order from the free list (:272-285) - the second count of the same scan.
 __global__ void __launch_bounds__(256) k_visible_scan(const unsigned char *__restrict__ visType,
                                                       int *__restrict__ visibleIds, FrameState *st, SceneParams sp,
                                                       int visibleCapacity, unsigned long long *ticket, unsigned long long *tileState,
-                                                      int numTiles) {
+                                                      int numTiles, unsigned char *__restrict__ swapStates, HashEntry *__restrict__ table,
+                                                      const int *__restrict__ vbaAllocList) {
   __shared__ unsigned sWarp[8];
   __shared__ unsigned sTotal;
-  __shared__ unsigned sExA;
+  __shared__ unsigned sExA, sExB;
   __shared__ int sTile;
   __shared__ unsigned sEpoch;
   if (threadIdx.x == 0) {
@@ -340,31 +384,52 @@ __global__ void __launch_bounds__(256) k_visible_scan(const unsigned char *__res
       }
     }
   }
-  const unsigned excl = block_exclusive_scan_256(cnt, sWarp, &sTotal);
+  unsigned reallocMask = 0;  // bit j: slot0 + j is visible but swapped out
+  if (swapStates) {
+    unsigned m = liveMask;
+    while (m) {
+      const int j = __ffs(m) - 1;
+      m &= m - 1;
+      if (swapStates[slot0 + j] != 2) swapStates[slot0 + j] = 1;
+      if (table[slot0 + j].ptr == -1) reallocMask |= 1u << j;
+    }
+  }
+  const unsigned excl = block_exclusive_scan_256(cnt | ((unsigned)__popc(reallocMask) << 16), sWarp, &sTotal);
   __syncthreads();
   if (threadIdx.x < 32) {
     unsigned exA, exB;
-    scan_lookback(tileState, tile, sEpoch, sTotal, 0, exA, exB);
+    scan_lookback(tileState, tile, sEpoch, sTotal & 0xFFFFu, sTotal >> 16, exA, exB);
     if (threadIdx.x == 0) {
       sExA = exA;
+      sExB = exB;
       if (tile == numTiles - 1) {
-        int total = (int)(exA + sTotal);
+        int total = (int)(exA + (sTotal & 0xFFFFu));
         if (total > visibleCapacity) {
           atomicOr(&st->errorFlags, 2);
           total = visibleCapacity;
         }
         st->noVisibleEntries = total;
+        if (swapStates) st->lastFreeBlockId = st->reallocBaseBlockId - (int)(exB + (sTotal >> 16));
       }
     }
   }
   __syncthreads();
   if (cnt == 0) return;
-  int pos = (int)(sExA + excl);
+  int pos = (int)(sExA + (excl & 0xFFFFu));
   while (liveMask) {
     const int j = __ffs(liveMask) - 1;
     liveMask &= liveMask - 1;
     if (pos < visibleCapacity) visibleIds[pos] = slot0 + j;
     pos++;
+  }
+  if (reallocMask) {
+    int vbaIdx = st->reallocBaseBlockId - (int)(sExB + (excl >> 16));
+    while (reallocMask) {
+      const int j = __ffs(reallocMask) - 1;
+      reallocMask &= reallocMask - 1;
+      if (vbaIdx >= 0) table[slot0 + j].ptr = vbaAllocList[vbaIdx];
+      vbaIdx--;
+    }
   }
 }
 
@@ -408,9 +473,10 @@ void launch_allocate(const AllocArgs &a, cudaStream_t s) {
   k_alloc_pixels<<<g, 256, 0, s>>>(a.depth, table, a.visType, a.allocKey, a.st, a.vp, a.sp, oneOverVoxelSize, stepBound);
   const int numTiles = (a.sp.nEntries + SCAN_TILE - 1) / SCAN_TILE;
   k_alloc_scan<<<numTiles, 256, 0, s>>>(a.allocKey, table, a.visType, a.vbaAllocList, a.excessAllocList, a.depth, a.st, a.vp, a.sp,
-                                        oneOverVoxelSize, stepBound, a.onlyUpdateVisibleList ? 0 : 1, a.scanTickets, a.allocTileState, numTiles, a.visibleIds);
+                                        oneOverVoxelSize, stepBound, a.onlyUpdateVisibleList ? 0 : 1, a.scanTickets, a.allocTileState, numTiles, a.visibleIds,
+                                        (a.swapStates && !a.onlyUpdateVisibleList) ? 1 : 0);
   k_visible_scan<<<numTiles, 256, 0, s>>>(a.visType, a.visibleIds, a.st, a.sp, a.visibleCapacity, a.scanTickets + 1,
-                                          a.visTileState, numTiles);
+                                          a.visTileState, numTiles, a.onlyUpdateVisibleList ? nullptr : a.swapStates, table, a.vbaAllocList);
 }
 
 }  // namespace itm

@@ -39,6 +39,7 @@ struct AllocArgs {
   ViewParams vp;
   SceneParams sp;
   int onlyUpdateVisibleList;
+  unsigned char *swapStates;     // ITMHashSwapState[nEntries] when the scene swaps (scene->useSwapping), else NULL
   int prologueDone;              // the marking pass already ran (FramePrologue)
 };
 
@@ -121,6 +122,28 @@ size_t icp_rows_bytes();
 size_t icp_bcast_bytes();
 // One stand-alone evaluation at poseIn (16 floats, device); [n, f, nabla6, hessian36] left in out44 (device).
 void launch_icp_eval_single(const IcpArgs &a, const IcpLevelArgs &lv, float *out44, const float *poseIn, cudaStream_t s);
+// ITMSwappingEngine (ITMLib/Engine/DeviceSpecific/CPU/ITMSwappingEngine_CPU.cpp); SDF_TRANSFER_BLOCK_NUM = 0x1000
+#define ITM_TRANSFER_BLOCK_NUM 0x1000
+struct SwapArgs {
+  void *voxels;
+  void *hashTable;
+  int *vbaAllocList;
+  const unsigned char *visType;
+  unsigned char *swapStates;
+  int *neededIds;                   // device: selected entry ids (ITM_TRANSFER_BLOCK_NUM)
+  void *transfer;                   // device: syncedVoxelBlocks (ITM_TRANSFER_BLOCK_NUM blocks)
+  const unsigned char *hasSynced;   // device: hasSyncedData for the swap-in direction
+  unsigned long long *ticket;       // scan scratch
+  unsigned long long *tileState;
+  FrameState *st;
+  SceneParams sp;
+};
+// ordered selection of the first ITM_TRANSFER_BLOCK_NUM entries (ascending slot order) that need swapping in (mode 0:
+// state 1) or can be swapped out (mode 1: state 2, resident, not visible); st->swapCount = how many
+void launch_swap_select(const SwapArgs &a, int mode, cudaStream_t s);
+void launch_swap_in_apply(const SwapArgs &a, cudaStream_t s);   // IntegrateGlobalIntoLocal's combine loop
+void launch_swap_out_apply(const SwapArgs &a, cudaStream_t s);  // SaveToGlobalMemory's device part
+
 // all ranks meet: returns (on the stream) once every rank has enqueued barrier number seq after its own prior work
 void launch_shard_barrier(const ShardInfo &sh, unsigned seq, cudaStream_t s);
 int icp_max_ctas();

@@ -27,7 +27,7 @@ _BUF_DTYPES = {
     capi.BUF_DEPTH: np.float32, capi.BUF_MINMAX: np.float32, capi.BUF_RAYCAST_RESULT: np.float32,
     capi.BUF_RAYCAST_IMAGE: np.uint8, capi.BUF_POINTS: np.float32, capi.BUF_NORMALS: np.float32,
     capi.BUF_RAW_DEPTH: np.int16, capi.BUF_PYRAMID_1: np.float32, capi.BUF_PYRAMID_2: np.float32,
-    capi.BUF_PYRAMID_3: np.float32, capi.BUF_PYRAMID_4: np.float32, capi.BUF_RGB: np.uint8,
+    capi.BUF_PYRAMID_3: np.float32, capi.BUF_PYRAMID_4: np.float32, capi.BUF_RGB: np.uint8, capi.BUF_SWAP_STATES: np.uint8,
 }
 
 
@@ -122,6 +122,18 @@ class ITMMainEngine:
         s = None if state6 is None else np.ascontiguousarray(state6, np.int32).reshape(6)
         capi.check(self.lib.itm_b200_engine_set_state(
             self.h, None if p is None else _f32p(p), None if q is None else _f32p(q), None if s is None else _i32p(s)))
+
+    def global_cache(self):
+        """(hasStoredData uint8[entries], storedVoxelBlocks words[entries, 512], swapped_in, swapped_out) of a swapping engine -
+        numpy views onto the engine's host memory"""
+        has, blocks = C.c_void_p(), C.c_void_p()
+        n_in, n_out = C.c_int(), C.c_int()
+        capi.check(self.lib.itm_b200_engine_global_cache(self.h, C.byref(has), C.byref(blocks), C.byref(n_in), C.byref(n_out)))
+        n = self.params.sdf_bucket_num + self.params.sdf_excess_list_size
+        wdt = np.uint64 if self.params.voxel_type == capi.VOXEL_S_RGB else np.uint32
+        h = np.frombuffer((C.c_char * n).from_address(has.value), dtype=np.uint8)
+        b = np.frombuffer((C.c_char * (n * 512 * np.dtype(wdt).itemsize)).from_address(blocks.value), dtype=wdt).reshape(n, 512)
+        return h, b, n_in.value, n_out.value
 
     def icp_stats(self):
         """ComputeGandH evaluations per pyramid level in the last synced frame (level 0 = full resolution)"""

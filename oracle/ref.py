@@ -67,6 +67,13 @@ def declare_common(lib):
     if hasattr(lib._lib if isinstance(lib, _Prefixed) else lib, (lib._prefix if isinstance(lib, _Prefixed) else "ref") + "_set_rgb"):
         lib.ref_set_rgb.argtypes = [C.c_void_p, C.c_void_p]
         lib.ref_set_rgb.restype = None
+        lib.ref_set_use_swapping.argtypes = [C.c_int]
+        lib.ref_set_use_swapping.restype = None
+        lib.ref_swap.argtypes = [C.c_void_p]
+        lib.ref_swap.restype = None
+        for name in ("ref_swap_states", "ref_has_stored_data", "ref_stored_voxel_blocks"):
+            getattr(lib, name).argtypes = [C.c_void_p]
+            getattr(lib, name).restype = C.c_void_p
     lib.ref_update_view.argtypes = [C.c_void_p, C.c_void_p]
     lib.ref_update_view.restype = None
     lib.ref_process_frame.argtypes = [C.c_void_p, C.c_void_p]
@@ -114,9 +121,10 @@ class RefEngine:
     """The reference CPU engines composed like ITMMainEngine (ITMLib/Engine/ITMMainEngine.cpp:17-127)."""
 
     def __init__(self, width=640, height=480, intr=None, voxel_size=0.005, mu=0.02, max_w=100, vf_min=0.35,
-                 vf_max=3.0, flavour="parity"):
+                 vf_max=3.0, flavour="parity", use_swapping=False):
         from infinitam_b200 import synth  # numpy-only helper
 
+        self.use_swapping = use_swapping
         self.W, self.H = width, height
         self.intr = tuple(float(x) for x in (intr or synth.intrinsics_for(width, height)))
         self.voxel_size, self.mu, self.max_w, self.vf_min, self.vf_max = voxel_size, mu, max_w, vf_min, vf_max
@@ -125,7 +133,11 @@ class RefEngine:
 
     def _create(self, flavour):
         self.lib = load(flavour)
+        if self.use_swapping:
+            self.lib.ref_set_use_swapping(1)
         self.h = self.lib.ref_create(self.W, self.H, *self.intr, self.voxel_size, self.mu, self.max_w, self.vf_min, self.vf_max)
+        if self.use_swapping:
+            self.lib.ref_set_use_swapping(0)
         c = self.const
         self.n_local = c("SDF_LOCAL_BLOCK_NUM")
         self.n_bucket = c("SDF_BUCKET_NUM")
@@ -164,6 +176,23 @@ class RefEngine:
 
     def integrate(self):
         self.lib.ref_integrate(self.h)
+
+    def swap(self):
+        """ITMSwappingEngine::IntegrateGlobalIntoLocal + SaveToGlobalMemory"""
+        self.lib.ref_swap(self.h)
+
+    @property
+    def swap_states(self):
+        return _view(self.lib.ref_swap_states(self.h), np.uint8, self.n_entries)
+
+    @property
+    def has_stored_data(self):
+        return _view(self.lib.ref_has_stored_data(self.h), np.uint8, self.n_entries)
+
+    def stored_voxel_block(self, entry):
+        """one block of the global cache (512 voxel words)"""
+        dt = np.dtype(np.uint64 if self.const("sizeof_voxel") == 8 else np.uint32)
+        return _view(self.lib.ref_stored_voxel_blocks(self.h) + int(entry) * 512 * dt.itemsize, dt, 512)
 
     def expected_depths(self):
         self.lib.ref_expected_depths(self.h)

@@ -40,8 +40,10 @@ typedef ITMVoxelIndex TI;
 typedef ITMVoxel_s_rgb TV;
 #include "ITMLib/Engine/DeviceSpecific/CPU/ITMSceneReconstructionEngine_CPU.cpp"
 #include "ITMLib/Engine/DeviceSpecific/CPU/ITMVisualisationEngine_CPU.cpp"
+#include "ITMLib/Engine/DeviceSpecific/CPU/ITMSwappingEngine_CPU.cpp"
 template class ITMLib::Engine::ITMSceneReconstructionEngine_CPU<ITMVoxel_s_rgb, ITMVoxelBlockHash>;
 template class ITMLib::Engine::ITMVisualisationEngine_CPU<ITMVoxel_s_rgb, ITMVoxelBlockHash>;
+template class ITMLib::Engine::ITMSwappingEngine_CPU<ITMVoxel_s_rgb, ITMVoxelBlockHash>;
 #else
 typedef ITMVoxel TV;
 #endif
@@ -54,6 +56,7 @@ struct ref_engine {
   ITMViewBuilder_CPU *viewBuilder;
   ITMVisualisationEngine_CPU<TV, TI> *vis;
   ITMSceneReconstructionEngine_CPU<TV, TI> *reco;
+  ITMSwappingEngine_CPU<TV, TI> *swapper;  // NULL unless created after ref_set_use_swapping(1)
   ITMDepthTracker_CPU *tracker;
   ITMTrackingController *controller;
   ITMTrackingState *trackingState;
@@ -69,7 +72,12 @@ static double now_ms() {
              std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+static int g_nextUseSwapping = 0;
+
 extern "C" {
+
+// settings.useSwapping of the engines created from now on (ITMLibSettings.cpp:35; ITMDenseMapper.cpp:20,59-64)
+void ref_set_use_swapping(int on) { g_nextUseSwapping = on; }
 
 int ref_const(const char *name) {
   std::string n(name);
@@ -96,7 +104,7 @@ ref_engine *ref_create(int W, int H, float fx, float fy, float cx, float cy,
   // fork defaults differ from upstream (ITMLib/Utils/ITMLibSettings.cpp:44)
   e->settings->deviceType = ITMLibSettings::DEVICE_CPU;
   e->settings->trackerType = ITMLibSettings::TRACKER_ICP;
-  e->settings->useSwapping = false;
+  e->settings->useSwapping = g_nextUseSwapping != 0;
   e->settings->useApproximateRaycast = false;
   e->settings->useBilateralFilter = false;
   e->settings->modelSensorNoise = false;
@@ -111,7 +119,8 @@ ref_engine *ref_create(int W, int H, float fx, float fy, float cx, float cy,
   e->calib.intrinsics_rgb.SetFrom(fx, fy, cx, cy, (float)W, (float)H);
   e->calib.disparityCalib.SetFrom(1.0f / 1000.0f, 0.0f, ITMDisparityCalib::TRAFO_AFFINE);
 
-  e->scene = new ITMScene<TV, TI>(&e->settings->sceneParams, false, MEMORYDEVICE_CPU);
+  e->scene = new ITMScene<TV, TI>(&e->settings->sceneParams, e->settings->useSwapping, MEMORYDEVICE_CPU);
+  e->swapper = e->settings->useSwapping ? new ITMSwappingEngine_CPU<TV, TI>() : NULL;
   e->lowLevel = new ITMLowLevelEngine_CPU();
   e->viewBuilder = new ITMViewBuilder_CPU(&e->calib);
   e->vis = new ITMVisualisationEngine_CPU<TV, TI>(e->scene);
@@ -133,6 +142,7 @@ ref_engine *ref_create(int W, int H, float fx, float fy, float cx, float cy,
 }
 
 void ref_destroy(ref_engine *e) {
+  if (e->swapper) delete e->swapper;
   delete e->renderState;
   delete e->scene;
   delete e->controller;
@@ -166,6 +176,18 @@ void ref_allocate(ref_engine *e, int onlyVisible) {
 void ref_integrate(ref_engine *e) {
   e->reco->IntegrateIntoScene(e->scene, e->view, e->trackingState, e->renderState);
 }
+// ITMDenseMapper::ProcessFrame's swapping part (ITMDenseMapper.cpp:59-64)
+void ref_swap(ref_engine *e) {
+  if (!e->swapper) return;
+  e->swapper->IntegrateGlobalIntoLocal(e->scene, e->renderState);
+  e->swapper->SaveToGlobalMemory(e->scene, e->renderState);
+}
+unsigned char *ref_swap_states(ref_engine *e) { return e->swapper ? (unsigned char *)e->scene->globalCache->GetSwapStates(false) : NULL; }
+unsigned char *ref_has_stored_data(ref_engine *e) {
+  static_assert(sizeof(bool) == 1, "bool");
+  return e->swapper ? (unsigned char *)e->scene->globalCache->hasStoredData : NULL;  // private member, opened up above
+}
+void *ref_stored_voxel_blocks(ref_engine *e) { return e->swapper ? (void *)e->scene->globalCache->GetStoredVoxelBlock(0) : NULL; }
 void ref_expected_depths(ref_engine *e) {
   e->vis->CreateExpectedDepths(e->trackingState->pose_d, &(e->view->calib->intrinsics_d), e->renderState);
 }
@@ -184,6 +206,7 @@ void ref_process_frame(ref_engine *e, const short *depth) {
   e->controller->Track(e->trackingState, e->view);
   e->reco->AllocateSceneFromDepth(e->scene, e->view, e->trackingState, e->renderState);
   e->reco->IntegrateIntoScene(e->scene, e->view, e->trackingState, e->renderState);
+  ref_swap(e);
   e->controller->Prepare(e->trackingState, e->view, e->renderState);
 }
 
@@ -197,6 +220,7 @@ void ref_process_frame_timed(ref_engine *e, const short *depth, double *ms6) {
   e->reco->AllocateSceneFromDepth(e->scene, e->view, e->trackingState, e->renderState);
   double t3 = now_ms();
   e->reco->IntegrateIntoScene(e->scene, e->view, e->trackingState, e->renderState);
+  ref_swap(e);
   double t4 = now_ms();
   ref_expected_depths(e);
   double t5 = now_ms();
