@@ -77,6 +77,10 @@ typedef struct itm_b200_params {
   /* settings.useSwapping (ITMLibSettings.cpp:35, off by default): Layer B keeps an ITMGlobalCache in host memory and runs
    * ITMSwappingEngine::IntegrateGlobalIntoLocal / SaveToGlobalMemory after every integration (ITMDenseMapper.cpp:59-64) */
   int use_swapping;
+  /* settings.useApproximateRaycast (ITMLibSettings.cpp:32, off by default): ITMTrackingController::Track/Prepare
+   * (ITMTrackingController.cpp:11-46) skip the full raycast while the camera stays close to the pose of the last one
+   * (ITMTrackingState::TrackerFarFromPointCloud, Objects/ITMTrackingState.h:41-59) and forward-project it instead */
+  int use_approximate_raycast;
 } itm_b200_params;
 #define ITM_B200_VOXEL_S 0
 #define ITM_B200_VOXEL_S_RGB 1
@@ -121,6 +125,11 @@ typedef struct itm_b200_render_state {
   float *rendering_range_image_dev;      /* Vector2f[w*h] */
   float *raycast_result_dev;             /* Vector4f[w*h] */
   unsigned char *raycast_image_dev;      /* Vector4u[w*h] */
+  float *forward_projection_dev;         /* Vector4f[w*h]; only ForwardRender needs it (may be NULL otherwise) */
+  int *fwd_proj_missing_points_dev;      /* int[w*h];      only ForwardRender needs it */
+  int no_fwd_proj_missing_points;        /* host, out */
+  int img_width, img_height;             /* renderingRangeImage->noDims; 0 = the context's depth image size.  Free-view
+                                          * render states (ITMMainEngine::GetImage) may have another size */
 } itm_b200_render_state;
 
 /* ITMTrackingState (ITMLib/Objects/ITMTrackingState.h:19-85) */
@@ -155,6 +164,32 @@ int itm_b200_create_expected_depths(itm_b200_ctx *ctx, const itm_b200_scene *sce
  * ts->pose_d, fill points/normals/grey maps, set ts->pose_point_cloud = ts->pose_d. */
 int itm_b200_create_icp_maps(itm_b200_ctx *ctx, const itm_b200_scene *scene, itm_b200_render_state *rs,
                              itm_b200_tracking_state *ts);
+
+/* IITMVisualisationEngine::ForwardRender (Engine/ITMVisualisationEngine.h:73-74; CPU reference
+ * ITMVisualisationEngine_CPU.cpp:289-354): rs->raycast_result (the last full raycast) is projected to ts->pose_d into
+ * rs->forward_projection, pixels left without a point are ray cast, rs->raycast_image is shaded from the result.
+ * depth_dev = view->depth.  rs->no_fwd_proj_missing_points is set; the list itself comes out in no particular order
+ * (the reference's is raster order; nothing reads it). */
+int itm_b200_forward_render(itm_b200_ctx *ctx, const itm_b200_scene *scene, itm_b200_render_state *rs, const float *depth_dev,
+                            const itm_b200_tracking_state *ts);
+
+/* IITMVisualisationEngine::FindVisibleBlocks (Engine/ITMVisualisationEngine.h:42-43): every allocated block with a corner
+ * inside the image of (pose_M, intrinsics); rs->visible_entry_ids in ascending slot order, rs->no_visible_entries set. */
+int itm_b200_find_visible_blocks(itm_b200_ctx *ctx, const itm_b200_scene *scene, itm_b200_render_state *rs, const float pose_M[16],
+                                 const float intrinsics[4]);
+
+/* IITMVisualisationEngine::FindSurface (Engine/ITMVisualisationEngine.h:57-58): raycast from (pose_M, intrinsics) into
+ * rs->raycast_result using rs->rendering_range_image. */
+int itm_b200_find_surface(itm_b200_ctx *ctx, const itm_b200_scene *scene, itm_b200_render_state *rs, const float pose_M[16],
+                          const float intrinsics[4]);
+
+/* IITMVisualisationEngine::RenderImage (Engine/ITMVisualisationEngine.h:51-53): raycast into rs->raycast_result and shade
+ * into out_image_dev (Vector4u, rs image size).  type: IITMVisualisationEngine::RenderImageType. */
+#define ITM_B200_RENDER_SHADED_GREYSCALE 0
+#define ITM_B200_RENDER_COLOUR_FROM_VOLUME 1
+#define ITM_B200_RENDER_COLOUR_FROM_NORMAL 2
+int itm_b200_render_image(itm_b200_ctx *ctx, const itm_b200_scene *scene, itm_b200_render_state *rs, const float pose_M[16],
+                          const float intrinsics[4], unsigned char *out_image_dev, int type);
 
 /* ITMViewBuilder::ConvertDepthAffineToFloat (Engine/ITMViewBuilder.h) */
 int itm_b200_convert_depth_affine_to_float(itm_b200_ctx *ctx, float *depth_out_dev, const short *depth_in_dev, int w, int h,
@@ -230,7 +265,8 @@ int itm_b200_engine_sync(itm_b200_engine *e, float pose_out[16], int counters[6]
 /* Single stages on the engine's own state, for stage-by-stage parity tests ("teacher forcing"):
  * 0 view (needs a frame uploaded with itm_b200_engine_upload_depth), 1 track, 2 allocate,
  * 3 integrate, 4 expected depths, 5 raycast + ICP maps, 6 swap in / out (use_swapping engines; part of stage 3's slot in
- * a whole frame, ITMDenseMapper.cpp:59-64). */
+ * a whole frame, ITMDenseMapper.cpp:59-64), 7 ForwardRender (what Prepare runs instead of stage 5 when
+ * !requiresFullRendering), 8 the requiresFullRendering decision of ITMTrackingController::Track. */
 int itm_b200_engine_upload_depth(itm_b200_engine *e, const short *raw_depth_host);
 int itm_b200_engine_run_stage(itm_b200_engine *e, int stage);
 
@@ -240,6 +276,9 @@ enum {
   ITM_B200_BUF_VISIBLE_IDS, ITM_B200_BUF_VISIBLE_TYPES, ITM_B200_BUF_DEPTH, ITM_B200_BUF_MINMAX, ITM_B200_BUF_RAYCAST_RESULT,
   ITM_B200_BUF_RAYCAST_IMAGE, ITM_B200_BUF_POINTS, ITM_B200_BUF_NORMALS, ITM_B200_BUF_RAW_DEPTH, ITM_B200_BUF_PYRAMID_1,
   ITM_B200_BUF_PYRAMID_2, ITM_B200_BUF_PYRAMID_3, ITM_B200_BUF_PYRAMID_4, ITM_B200_BUF_RGB, ITM_B200_BUF_SWAP_STATES,
+  ITM_B200_BUF_FORWARD_PROJECTION, ITM_B200_BUF_FWD_MISSING_POINTS,
+  /* renderState_freeview of the last GetImage call (ITMMainEngine.cpp:176-180) */
+  ITM_B200_BUF_FREEVIEW_VISIBLE_IDS, ITM_B200_BUF_FREEVIEW_MINMAX, ITM_B200_BUF_FREEVIEW_RAYCAST_RESULT, ITM_B200_BUF_FREEVIEW_IMAGE,
   ITM_B200_BUF_COUNT
 };
 int itm_b200_engine_get_buffer(itm_b200_engine *e, int which, void **dev_ptr, size_t *bytes);
@@ -254,9 +293,23 @@ int itm_b200_engine_global_cache(itm_b200_engine *e, const unsigned char **has_s
                                  int *swapped_in, int *swapped_out);
 
 /* Host-visible tracking / scene state: pose_d, pose_pointCloud (column-major), and
- * state6 = {noVisibleEntries, lastFreeBlockId, lastFreeExcessListId, age_pointCloud, 0, 0}. */
+ * state6 = {noVisibleEntries, lastFreeBlockId, lastFreeExcessListId, age_pointCloud, requiresFullRendering,
+ * noFwdProjMissingPoints} (set_state ignores the last two). */
 int itm_b200_engine_get_state(itm_b200_engine *e, float pose_d[16], float pose_point_cloud[16], int state6[6]);
 int itm_b200_engine_set_state(itm_b200_engine *e, const float pose_d[16], const float pose_point_cloud[16], const int state6[6]);
+
+/* ITMMainEngine::GetImage (ITMLib/Engine/ITMMainEngine.cpp:134-192).  image_type is ITMMainEngine::GetImageType
+ * (Engine/ITMMainEngine.h:78-87).  out_host receives Vector4u[out_w * out_h]; for the ORIGINAL_* / SCENERAYCAST types
+ * out_w x out_h must be the sensor size; the FREECAMERA types render a view of any size from (pose_M, intrinsics) through
+ * FindVisibleBlocks + CreateExpectedDepths + RenderImage on the engine's renderState_freeview. */
+#define ITM_B200_IMAGE_ORIGINAL_RGB 0
+#define ITM_B200_IMAGE_ORIGINAL_DEPTH 1
+#define ITM_B200_IMAGE_SCENERAYCAST 2
+#define ITM_B200_IMAGE_FREECAMERA_SHADED 3
+#define ITM_B200_IMAGE_FREECAMERA_COLOUR_FROM_VOLUME 4
+#define ITM_B200_IMAGE_FREECAMERA_COLOUR_FROM_NORMAL 5
+int itm_b200_engine_get_image(itm_b200_engine *e, int image_type, const float pose_M[16], const float intrinsics[4],
+                              unsigned char *out_host, int out_w, int out_h);
 
 /* ICP evaluations (ComputeGandH calls) per pyramid level during the last frame fetched by
  * itm_b200_engine_sync / _process_frame (level 0 = full resolution). */

@@ -110,6 +110,11 @@ inline itm_b200_render_state render_state_view(ITMRenderState_VH *rs) {
   r.rendering_range_image_dev = (float *)rs->renderingRangeImage->GetData(MEMORYDEVICE_CUDA);
   r.raycast_result_dev = (float *)rs->raycastResult->GetData(MEMORYDEVICE_CUDA);
   r.raycast_image_dev = (unsigned char *)rs->raycastImage->GetData(MEMORYDEVICE_CUDA);
+  r.forward_projection_dev = (float *)rs->forwardProjection->GetData(MEMORYDEVICE_CUDA);
+  r.fwd_proj_missing_points_dev = rs->fwdProjMissingPoints->GetData(MEMORYDEVICE_CUDA);
+  r.no_fwd_proj_missing_points = rs->noFwdProjMissingPoints;
+  r.img_width = rs->renderingRangeImage->noDims.x;   // free-view render states have their own size (ITMMainEngine.cpp:176)
+  r.img_height = rs->renderingRangeImage->noDims.y;
   return r;
 }
 
@@ -206,14 +211,48 @@ class ITMVisualisationEngine_B200<TVoxel, ITMVoxelBlockHash> : public ITMVisuali
     trackingState->pose_pointCloud->SetFrom(trackingState->pose_d);  // ITMVisualisationEngine_CPU.cpp:273
   }
 
-  // SURVEY.md 8f "next" rows: not on the fusion hot path, and there is no CPU fallback to hide behind.
-  void FindVisibleBlocks(const ITMPose *, const ITMIntrinsics *, ITMRenderState *) const { DIEWITHEXCEPTION("libitm_b200: FindVisibleBlocks not provided"); }
-  void RenderImage(const ITMPose *, const ITMIntrinsics *, const ITMRenderState *, ITMUChar4Image *, IITMVisualisationEngine::RenderImageType) const {
-    DIEWITHEXCEPTION("libitm_b200: RenderImage not provided");
+  void ForwardRender(const ITMView *view, ITMTrackingState *trackingState, ITMRenderState *renderState) const {
+    itm_b200_scene s = b200_detail::scene_view(const_cast<Scene *>(this->scene));
+    itm_b200_render_state r = b200_detail::render_state_view((ITMRenderState_VH *)renderState);
+    const itm_b200_tracking_state t = b200_detail::tracking_state_view(trackingState);
+    itm_b200_check(itm_b200_forward_render(c->ctx, &s, &r, view->depth->GetData(MEMORYDEVICE_CUDA), &t), "ForwardRender");
+    renderState->noFwdProjMissingPoints = r.no_fwd_proj_missing_points;
   }
-  void FindSurface(const ITMPose *, const ITMIntrinsics *, const ITMRenderState *) const { DIEWITHEXCEPTION("libitm_b200: FindSurface not provided"); }
+
+  void FindVisibleBlocks(const ITMPose *pose, const ITMIntrinsics *intrinsics, ITMRenderState *renderState) const {
+    itm_b200_scene s = b200_detail::scene_view(const_cast<Scene *>(this->scene));
+    ITMRenderState_VH *rsVH = (ITMRenderState_VH *)renderState;
+    itm_b200_render_state r = b200_detail::render_state_view(rsVH);
+    const Vector4f &k = intrinsics->projectionParamsSimple.all;
+    const float intr[4] = {k.x, k.y, k.z, k.w};
+    itm_b200_check(itm_b200_find_visible_blocks(c->ctx, &s, &r, pose->GetM().m, intr), "FindVisibleBlocks");
+    rsVH->noVisibleEntries = r.no_visible_entries;
+  }
+
+  void RenderImage(const ITMPose *pose, const ITMIntrinsics *intrinsics, const ITMRenderState *renderState, ITMUChar4Image *outputImage,
+                   IITMVisualisationEngine::RenderImageType type) const {
+    itm_b200_scene s = b200_detail::scene_view(const_cast<Scene *>(this->scene));
+    itm_b200_render_state r = b200_detail::render_state_view((ITMRenderState_VH *)const_cast<ITMRenderState *>(renderState));
+    r.img_width = outputImage->noDims.x;  // RenderImage_common: imgSize = outputImage->noDims
+    r.img_height = outputImage->noDims.y;
+    const Vector4f &k = intrinsics->projectionParamsSimple.all;
+    const float intr[4] = {k.x, k.y, k.z, k.w};
+    itm_b200_check(itm_b200_render_image(c->ctx, &s, &r, pose->GetM().m, intr, (unsigned char *)outputImage->GetData(MEMORYDEVICE_CUDA), (int)type),
+                   "RenderImage");
+  }
+
+  void FindSurface(const ITMPose *pose, const ITMIntrinsics *intrinsics, const ITMRenderState *renderState) const {
+    itm_b200_scene s = b200_detail::scene_view(const_cast<Scene *>(this->scene));
+    itm_b200_render_state r = b200_detail::render_state_view((ITMRenderState_VH *)const_cast<ITMRenderState *>(renderState));
+    r.img_width = renderState->raycastResult->noDims.x;
+    r.img_height = renderState->raycastResult->noDims.y;
+    const Vector4f &k = intrinsics->projectionParamsSimple.all;
+    const float intr[4] = {k.x, k.y, k.z, k.w};
+    itm_b200_check(itm_b200_find_surface(c->ctx, &s, &r, pose->GetM().m, intr), "FindSurface");
+  }
+
+  // the colour tracker's point cloud (TRACKER_COLOR) is outside the depth-ICP fusion path (out of scope)
   void CreatePointCloud(const ITMView *, ITMTrackingState *, ITMRenderState *, bool) const { DIEWITHEXCEPTION("libitm_b200: CreatePointCloud not provided"); }
-  void ForwardRender(const ITMView *, ITMTrackingState *, ITMRenderState *) const { DIEWITHEXCEPTION("libitm_b200: ForwardRender not provided"); }
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -18,10 +18,16 @@ ITER_ROTATION, ITER_TRANSLATION, ITER_BOTH, ITER_NONE = 1, 2, 3, 4
 
 (BUF_VOXELS, BUF_HASH, BUF_VBA_ALLOC_LIST, BUF_EXCESS_ALLOC_LIST, BUF_VISIBLE_IDS, BUF_VISIBLE_TYPES, BUF_DEPTH,
  BUF_MINMAX, BUF_RAYCAST_RESULT, BUF_RAYCAST_IMAGE, BUF_POINTS, BUF_NORMALS, BUF_RAW_DEPTH, BUF_PYRAMID_1,
- BUF_PYRAMID_2, BUF_PYRAMID_3, BUF_PYRAMID_4, BUF_RGB, BUF_SWAP_STATES, BUF_COUNT) = range(20)
+ BUF_PYRAMID_2, BUF_PYRAMID_3, BUF_PYRAMID_4, BUF_RGB, BUF_SWAP_STATES, BUF_FORWARD_PROJECTION, BUF_FWD_MISSING_POINTS,
+ BUF_FREEVIEW_VISIBLE_IDS, BUF_FREEVIEW_MINMAX, BUF_FREEVIEW_RAYCAST_RESULT, BUF_FREEVIEW_IMAGE, BUF_COUNT) = range(26)
 VOXEL_S, VOXEL_S_RGB = 0, 1
 
-STAGE_VIEW, STAGE_TRACK, STAGE_ALLOCATE, STAGE_INTEGRATE, STAGE_EXPECTED_DEPTHS, STAGE_ICP_MAPS, STAGE_SWAP = range(7)
+(STAGE_VIEW, STAGE_TRACK, STAGE_ALLOCATE, STAGE_INTEGRATE, STAGE_EXPECTED_DEPTHS, STAGE_ICP_MAPS, STAGE_SWAP,
+ STAGE_FORWARD_RENDER, STAGE_TRACK_DECIDE) = range(9)
+# ITMMainEngine::GetImageType (Engine/ITMMainEngine.h:78-87), IITMVisualisationEngine::RenderImageType
+(IMAGE_ORIGINAL_RGB, IMAGE_ORIGINAL_DEPTH, IMAGE_SCENERAYCAST, IMAGE_FREECAMERA_SHADED, IMAGE_FREECAMERA_COLOUR_FROM_VOLUME,
+ IMAGE_FREECAMERA_COLOUR_FROM_NORMAL, IMAGE_UNKNOWN) = range(7)
+RENDER_SHADED_GREYSCALE, RENDER_COLOUR_FROM_VOLUME, RENDER_COLOUR_FROM_NORMAL = range(3)
 
 
 class Params(C.Structure):
@@ -41,6 +47,7 @@ class Params(C.Structure):
         ("rgb_fx", C.c_float), ("rgb_fy", C.c_float), ("rgb_cx", C.c_float), ("rgb_cy", C.c_float),
         ("trafo_rgb_to_depth_inv", C.c_float * 16),
         ("use_swapping", C.c_int),
+        ("use_approximate_raycast", C.c_int),
     ]
 
 
@@ -58,6 +65,8 @@ class RenderState(C.Structure):
         ("no_visible_entries", C.c_int),
         ("rendering_range_image_dev", C.c_void_p), ("raycast_result_dev", C.c_void_p),
         ("raycast_image_dev", C.c_void_p),
+        ("forward_projection_dev", C.c_void_p), ("fwd_proj_missing_points_dev", C.c_void_p),
+        ("no_fwd_proj_missing_points", C.c_int), ("img_width", C.c_int), ("img_height", C.c_int),
     ]
 
 
@@ -94,6 +103,8 @@ SYMBOLS = [
     "itm_b200_engine_read_buffer", "itm_b200_engine_write_buffer", "itm_b200_engine_global_cache", "itm_b200_engine_get_state",
     "itm_b200_engine_set_state", "itm_b200_engine_icp_stats", "itm_b200_engine_set_profiling", "itm_b200_engine_stage_times",
     "itm_b200_mat4_inv", "itm_b200_pose_from_inv_m_coerced", "itm_b200_compute_delta",
+    "itm_b200_forward_render", "itm_b200_find_visible_blocks", "itm_b200_find_surface", "itm_b200_render_image",
+    "itm_b200_engine_get_image",
 ]
 
 _lib = None
@@ -128,6 +139,11 @@ def load():
     lib.itm_b200_integrate_into_scene_rgb.argtypes = [vp, C.POINTER(Scene), C.POINTER(RenderState), vp, vp, f32p]
     lib.itm_b200_create_expected_depths.argtypes = [vp, C.POINTER(Scene), C.POINTER(RenderState), f32p, f32p]
     lib.itm_b200_create_icp_maps.argtypes = [vp, C.POINTER(Scene), C.POINTER(RenderState), C.POINTER(TrackingState)]
+    lib.itm_b200_forward_render.argtypes = [vp, C.POINTER(Scene), C.POINTER(RenderState), vp, C.POINTER(TrackingState)]
+    lib.itm_b200_find_visible_blocks.argtypes = [vp, C.POINTER(Scene), C.POINTER(RenderState), f32p, f32p]
+    lib.itm_b200_find_surface.argtypes = [vp, C.POINTER(Scene), C.POINTER(RenderState), f32p, f32p]
+    lib.itm_b200_render_image.argtypes = [vp, C.POINTER(Scene), C.POINTER(RenderState), f32p, f32p, vp, C.c_int]
+    lib.itm_b200_engine_get_image.argtypes = [vp, C.c_int, f32p, f32p, vp, C.c_int, C.c_int]
     lib.itm_b200_convert_depth_affine_to_float.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_float, C.c_float]
     lib.itm_b200_filter_subsample_with_holes.argtypes = [vp, vp, vp, C.c_int, C.c_int]
     lib.itm_b200_compute_g_and_h.argtypes = [vp, vp, C.c_int, C.c_int, f32p, vp, vp, C.c_int, C.c_int, f32p, f32p, f32p,

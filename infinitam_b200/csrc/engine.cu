@@ -62,6 +62,7 @@ struct itm_b200_ctx {
   unsigned long long *icpRows = nullptr;   // tagged CTA partial sums of k_icp_track
   unsigned long long *icpBcast = nullptr;  // tagged pose broadcast ring
   unsigned icpEpoch = 0;
+  int *fwdKey = nullptr;       // ForwardRender: winning source pixel + 1 per destination pixel, all zero between calls
   float *icpOut = nullptr;     // 44 floats
   float *icpPoseIn = nullptr;  // 16 floats
   FrameState *st = nullptr;    // device
@@ -153,6 +154,8 @@ int ctx_alloc(itm_b200_ctx *c, void *stream) {
   CU(cudaMemsetAsync(c->icpRows, 0, icp_rows_bytes(), c->stream));
   CU(cudaMalloc(&c->icpBcast, icp_bcast_bytes()));
   CU(cudaMemsetAsync(c->icpBcast, 0, icp_bcast_bytes(), c->stream));
+  CU(cudaMalloc(&c->fwdKey, (size_t)c->p.width * c->p.height * sizeof(int)));
+  CU(cudaMemsetAsync(c->fwdKey, 0, (size_t)c->p.width * c->p.height * sizeof(int), c->stream));
   CU(cudaMalloc(&c->icpOut, 44 * sizeof(float)));
   CU(cudaMalloc(&c->icpPoseIn, 16 * sizeof(float)));
   CU(cudaMalloc(&c->st, sizeof(FrameState)));
@@ -178,6 +181,7 @@ void ctx_free(itm_b200_ctx *c) {
   cudaFree(c->icpRows);
   cudaFree(c->icpBcast);
   cudaFree(c->icpOut);
+  cudaFree(c->fwdKey);
   cudaFree(c->icpPoseIn);
   cudaFree(c->st);
   if (c->hst) cudaFreeHost(c->hst);
@@ -196,6 +200,7 @@ void host_state_init(FrameState *h, const SceneParams &sp) {
   h->lastFreeBlockId = sp.nLocal - 1;
   h->lastFreeExcessId = sp.nExcess - 1;
   h->agePointCloud = -1;
+  h->requiresFullRendering = 1;
 }
 
 void set_pose_host(FrameState *h, const float *M) {
@@ -242,6 +247,17 @@ void fill_integrate_calib(const itm_b200_ctx *c, IntegrateArgs &a, const unsigne
   a.rgb = rgb;
   a.rgbIntr[0] = c->p.rgb_fx; a.rgbIntr[1] = c->p.rgb_fy; a.rgbIntr[2] = c->p.rgb_cx; a.rgbIntr[3] = c->p.rgb_cy;
   memcpy(a.calibInv, c->p.trafo_rgb_to_depth_inv, sizeof(a.calibInv));
+}
+
+// image size of a render state (free-view render states may differ from the sensor) + the intrinsics of this call
+ViewParams rs_view(const itm_b200_ctx *c, const itm_b200_render_state *rs, const float intrinsics[4]) {
+  ViewParams vp = c->vp;
+  if (rs->img_width > 0 && rs->img_height > 0) {
+    vp.W = rs->img_width;
+    vp.H = rs->img_height;
+  }
+  vp.fx = intrinsics[0]; vp.fy = intrinsics[1]; vp.cx = intrinsics[2]; vp.cy = intrinsics[3];
+  return vp;
 }
 
 IcpLevelArgs make_level_args(const itm_b200_ctx *c, int l, const float *depth) {
@@ -447,8 +463,7 @@ int itm_b200_create_expected_depths(itm_b200_ctx *c, const itm_b200_scene *scene
   a.visibleIds = rs->visible_entry_ids_dev;
   a.minmax = rs->rendering_range_image_dev;
   a.st = c->st;
-  a.vp = c->vp;
-  a.vp.fx = intrinsics[0]; a.vp.fy = intrinsics[1]; a.vp.cx = intrinsics[2]; a.vp.cy = intrinsics[3];
+  a.vp = rs_view(c, rs, intrinsics);
   a.sp = c->sp;
   launch_expected_depths(a, c->stream);
   g_launches += 2;
@@ -483,6 +498,91 @@ int itm_b200_create_icp_maps(itm_b200_ctx *c, const itm_b200_scene *scene, itm_b
   // trackingState->pose_pointCloud->SetFrom(trackingState->pose_d)  (ITMVisualisationEngine_CPU.cpp:273)
   memcpy(ts->pose_point_cloud, ts->pose_d, 64);
   return ITM_B200_OK;
+}
+
+int itm_b200_forward_render(itm_b200_ctx *c, const itm_b200_scene *scene, itm_b200_render_state *rs, const float *depth_dev,
+                            const itm_b200_tracking_state *ts) {
+  if (!c || !scene || !rs || !depth_dev || !ts) return fail(ITM_B200_EINVAL, "NULL argument");
+  if (!rs->forward_projection_dev || !rs->fwd_proj_missing_points_dev) return fail(ITM_B200_EINVAL, "render state without forward-projection buffers");
+  if ((rs->img_width > 0 && rs->img_width != c->vp.W) || (rs->img_height > 0 && rs->img_height != c->vp.H))
+    return fail(ITM_B200_EINVAL, "ForwardRender needs a render state of the sensor's size");
+  set_pose_host(c->hst, ts->pose_d);
+  int rc = push_state(c);
+  if (rc) return rc;
+  ForwardArgs f;
+  memset(&f, 0, sizeof(f));
+  f.render.shard.world = 1;
+  f.render.voxels = scene->voxel_blocks_dev;
+  f.render.hashTable = scene->hash_entries_dev;
+  f.render.minmax = rs->rendering_range_image_dev;
+  f.render.raycastResult = rs->raycast_result_dev;
+  f.render.raycastImage = rs->raycast_image_dev;
+  f.render.st = c->st;
+  f.render.vp = c->vp;
+  f.render.sp = c->sp;
+  f.forwardProjection = rs->forward_projection_dev;
+  f.missingPoints = rs->fwd_proj_missing_points_dev;
+  f.key = c->fwdKey;
+  f.depth = depth_dev;
+  f.gated = 0;
+  launch_forward_render(f, c->stream);
+  g_launches += 4;
+  rc = pull_state(c);
+  if (rc) return rc;
+  rs->no_fwd_proj_missing_points = c->hst->noFwdProjMissingPoints;
+  return ITM_B200_OK;
+}
+
+int itm_b200_find_visible_blocks(itm_b200_ctx *c, const itm_b200_scene *scene, itm_b200_render_state *rs, const float pose_M[16],
+                                 const float intrinsics[4]) {
+  if (!c || !scene || !rs || !pose_M || !intrinsics) return fail(ITM_B200_EINVAL, "NULL argument");
+  set_pose_host(c->hst, pose_M);
+  c->hst->errorFlags = 0;
+  int rc = push_state(c);
+  if (rc) return rc;
+  launch_find_visible_blocks(scene->hash_entries_dev, rs->visible_entry_ids_dev, c->st, rs_view(c, rs, intrinsics), c->sp, c->sp.nLocal,
+                             c->scanTickets + 1, c->visTileState, c->stream);
+  g_launches += 1;
+  rc = pull_state(c);
+  if (rc) return rc;
+  rs->no_visible_entries = c->hst->noVisibleEntries;
+  return ITM_B200_OK;
+}
+
+static int raycast_layer_a(itm_b200_ctx *c, const itm_b200_scene *scene, itm_b200_render_state *rs, const float pose_M[16],
+                           const float intrinsics[4], unsigned char *out_image_dev, int type) {
+  if (!c || !scene || !rs || !pose_M || !intrinsics) return fail(ITM_B200_EINVAL, "NULL argument");
+  set_pose_host(c->hst, pose_M);
+  int rc = push_state(c);
+  if (rc) return rc;
+  RenderArgs a;
+  memset(&a, 0, sizeof(a));
+  a.shard.world = 1;
+  a.voxels = scene->voxel_blocks_dev;
+  a.hashTable = scene->hash_entries_dev;
+  a.minmax = rs->rendering_range_image_dev;
+  a.raycastResult = rs->raycast_result_dev;
+  a.st = c->st;
+  a.vp = rs_view(c, rs, intrinsics);
+  a.sp = c->sp;
+  if (out_image_dev) launch_render_image(a, out_image_dev, type, c->stream);
+  else launch_raycast(a, c->stream);
+  g_launches += 1;
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  return ITM_B200_OK;
+}
+
+int itm_b200_find_surface(itm_b200_ctx *c, const itm_b200_scene *scene, itm_b200_render_state *rs, const float pose_M[16],
+                          const float intrinsics[4]) {
+  return raycast_layer_a(c, scene, rs, pose_M, intrinsics, nullptr, 0);
+}
+
+int itm_b200_render_image(itm_b200_ctx *c, const itm_b200_scene *scene, itm_b200_render_state *rs, const float pose_M[16],
+                          const float intrinsics[4], unsigned char *out_image_dev, int type) {
+  if (!out_image_dev) return fail(ITM_B200_EINVAL, "NULL argument");
+  if (type < 0 || type > 2) return fail(ITM_B200_EINVAL, "unknown RenderImageType");
+  return raycast_layer_a(c, scene, rs, pose_M, intrinsics, out_image_dev, type);
 }
 
 int itm_b200_convert_depth_affine_to_float(itm_b200_ctx *c, float *out_dev, const short *in_dev, int w, int h, float a, float b) {
@@ -590,6 +690,18 @@ struct itm_b200_engine {
   float *minmax = nullptr;
   float *raycastResult = nullptr;
   unsigned char *raycastImage = nullptr;
+  float *forwardProjection = nullptr;
+  int *fwdMissing = nullptr;
+  // renderState_freeview (ITMMainEngine.cpp:176: created on the first free-view GetImage, with that image's size)
+  int freeW = 0, freeH = 0;
+  int *freeVisibleIds = nullptr;
+  float *freeMinmax = nullptr;
+  float *freeRaycastResult = nullptr;
+  unsigned char *freeImage = nullptr;
+  FrameState *stFree = nullptr;    // device: pose + visible count of the free-view camera
+  FrameState *hstFree = nullptr;   // pinned
+  unsigned char *imageHost = nullptr;  // pinned staging for GetImage
+  size_t imageHostBytes = 0;
   // tracking state
   float *points = nullptr;
   float *normals = nullptr;
@@ -600,6 +712,7 @@ struct itm_b200_engine {
   cudaEvent_t rgbDone = nullptr;
   float *depth = nullptr;
   int agePointCloud = -1;  // host copy; its evolution does not depend on device results
+  bool haveView = false;      // a frame has been given to the engine (ITMMainEngine::view != NULL)
   bool prologueDone = false;  // this frame's view kernel already did the FramePrologue chores
   ShardInfo shard;            // world == 1 unless created with itm_b200_engine_create_sharded
   // swapping (settings.useSwapping): ITMGlobalCache
@@ -637,6 +750,10 @@ int engine_alloc(itm_b200_engine *e) {
   CU(cudaMalloc(&e->minmax, P * 8));
   if (!e->externalBuffers) CU(cudaMalloc(&e->raycastResult, P * 16));
   CU(cudaMalloc(&e->raycastImage, P * 4));
+  CU(cudaMalloc(&e->forwardProjection, P * 16));
+  CU(cudaMalloc(&e->fwdMissing, P * 4));
+  CU(cudaMalloc(&e->stFree, sizeof(FrameState)));
+  CU(cudaMallocHost(&e->hstFree, sizeof(FrameState)));
   CU(cudaMalloc(&e->points, P * 16));
   CU(cudaMalloc(&e->normals, P * 16));
   CU(cudaMalloc(&e->rawDepth, P * 2));
@@ -678,6 +795,8 @@ int engine_alloc(itm_b200_engine *e) {
   e->bytes[ITM_B200_BUF_POINTS] = P * 16;
   e->bytes[ITM_B200_BUF_NORMALS] = P * 16;
   e->bytes[ITM_B200_BUF_RAW_DEPTH] = P * 2;
+  e->bytes[ITM_B200_BUF_FORWARD_PROJECTION] = P * 16;
+  e->bytes[ITM_B200_BUF_FWD_MISSING_POINTS] = P * 4;
   for (int l = 1; l <= 4; ++l)
     e->bytes[ITM_B200_BUF_PYRAMID_1 + l - 1] = l < c->nLevels ? (size_t)c->levels[l].w * c->levels[l].h * 4 : 0;
   return ITM_B200_OK;
@@ -689,6 +808,10 @@ void engine_free(itm_b200_engine *e) {
   cudaFree(e->visibleIds); cudaFree(e->visType); cudaFree(e->minmax);
   cudaFree(e->raycastImage); cudaFree(e->points); cudaFree(e->normals); cudaFree(e->rawDepth);
   cudaFree(e->rgb); cudaFree(e->depth);
+  cudaFree(e->forwardProjection); cudaFree(e->fwdMissing); cudaFree(e->stFree);
+  cudaFree(e->freeVisibleIds); cudaFree(e->freeMinmax); cudaFree(e->freeRaycastResult); cudaFree(e->freeImage);
+  if (e->hstFree) cudaFreeHost(e->hstFree);
+  if (e->imageHost) cudaFreeHost(e->imageHost);
   cudaFree(e->swapStates); cudaFree(e->neededIds); cudaFree(e->transfer); cudaFree(e->hasSynced);
   cudaFree(e->swapTileState); cudaFree(e->swapTicket);
   if (e->neededIdsHost) cudaFreeHost(e->neededIdsHost);
@@ -715,10 +838,14 @@ int engine_reset(itm_b200_engine *e) {
   CU(cudaMemsetAsync(e->visibleIds, 0, (size_t)c->sp.nLocal * 4, c->stream));
   CU(cudaMemsetAsync(e->raycastResult, 0, P * 16, c->stream));
   CU(cudaMemsetAsync(e->raycastImage, 0, P * 4, c->stream));
+  CU(cudaMemsetAsync(e->forwardProjection, 0, P * 16, c->stream));
+  CU(cudaMemsetAsync(e->fwdMissing, 0, P * 4, c->stream));
+  CU(cudaMemsetAsync(c->fwdKey, 0, P * 4, c->stream));
   CU(cudaMemsetAsync(e->points, 0, P * 16, c->stream));
   CU(cudaMemsetAsync(e->normals, 0, P * 16, c->stream));
   CU(cudaMemsetAsync(e->minmax, 0, P * 8, c->stream));
   CU(cudaMemsetAsync(e->depth, 0, P * 4, c->stream));
+  CU(cudaMemsetAsync(e->rgb, 0, P * 4, c->stream));
   CU(cudaMemsetAsync(c->allocKey, 0, (size_t)((c->sp.nEntries + 8191) / 8192) * 8192 * sizeof(unsigned), c->stream));
   if (e->swapStates) {
     CU(cudaMemsetAsync(e->swapStates, 0, (size_t)((c->sp.nEntries + 8191) / 8192) * 8192, c->stream));
@@ -747,9 +874,18 @@ void stage_view(itm_b200_engine *e, bool withPrologue) {
   g_launches += 1 + (c->nLevels > 5 ? c->nLevels - 5 : 0);
 }
 
+// trackingState->requiresFullRendering (ITMTrackingController.cpp:15).  Without useApproximateRaycast it is always true and
+// nothing is launched: the render kernels are not gated then.
+void stage_track_decide(itm_b200_engine *e) {
+  if (!e->c->p.use_approximate_raycast) return;
+  launch_track_decide(e->c->st, 1, e->c->stream);
+  g_launches += 1;
+}
+
 void stage_track(itm_b200_engine *e) {
   // ITMTrackingController::Track (ITMTrackingController.cpp:11-16)
   if (e->agePointCloud != -1) enqueue_track(e->c, e->depth, e->points, e->normals, false);
+  stage_track_decide(e);
 }
 
 void stage_allocate(itm_b200_engine *e) {
@@ -790,6 +926,7 @@ RenderArgs engine_render_args(itm_b200_engine *e) {
   a.normalsMap = e->normals;
   a.raycastImage = e->raycastImage;
   a.minmaxReady = 0;
+  a.gated = c->p.use_approximate_raycast ? 1 : 0;
   a.st = c->st;
   a.vp = c->vp;
   a.sp = c->sp;
@@ -812,8 +949,23 @@ void stage_icp_maps(itm_b200_engine *e) {
   // pose_pointCloud <- pose_d happens inside the kernel (FrameState::scenePose)
   launch_icp_maps(engine_render_args(e), e->c->stream);
   g_launches += 1;
+  // the device copy (FrameState::agePointCloud, updated by the kernels) is the authoritative one; the host only needs to
+  // know whether a point cloud exists at all (Track's "age != -1" test)
   if (e->agePointCloud == -1) e->agePointCloud = -2;
   else e->agePointCloud = 0;
+}
+
+// ITMTrackingController::Prepare's else-branch (:40-44).  gated: only when the device decided !requiresFullRendering
+void stage_forward_render(itm_b200_engine *e, bool gated) {
+  ForwardArgs f;
+  f.render = engine_render_args(e);
+  f.forwardProjection = e->forwardProjection;
+  f.missingPoints = e->fwdMissing;
+  f.key = e->c->fwdKey;
+  f.depth = e->depth;
+  f.gated = gated ? 1 : 0;
+  launch_forward_render(f, e->c->stream);
+  g_launches += 4;
 }
 
 // ITMSwappingEngine::IntegrateGlobalIntoLocal + SaveToGlobalMemory (ITMDenseMapper.cpp:59-64).  Unlike the rest of the
@@ -891,6 +1043,7 @@ void enqueue_frame(itm_b200_engine *e) {
   if (prof) cudaEventRecord(e->ev[6], s);
   stage_raycast(e);
   stage_shard_barrier(e);  // ... and every rank's tiles of the raycast image
+  if (e->c->p.use_approximate_raycast) stage_forward_render(e, true);
   if (prof) cudaEventRecord(e->ev[7], s);
   stage_icp_maps(e);
   if (prof) cudaEventRecord(e->ev[8], s);
@@ -926,8 +1079,8 @@ int itm_b200_engine_create_sharded(const itm_b200_params *params, const itm_b200
   *out = nullptr;
   if (shard->world < 1 || shard->world > ITM_MAX_SHARDS || shard->rank < 0 || shard->rank >= shard->world)
     return fail(ITM_B200_EINVAL, "rank / world out of range (at most 8 ranks)");
-  if (params && (params->voxel_type != ITM_B200_VOXEL_S || params->use_swapping))
-    return fail(ITM_B200_EUNSUPPORTED, "sharded engines support ITMVoxel_s without swapping only");
+  if (params && (params->voxel_type != ITM_B200_VOXEL_S || params->use_swapping || params->use_approximate_raycast))
+    return fail(ITM_B200_EUNSUPPORTED, "sharded engines support ITMVoxel_s without swapping and approximate raycast only");
   for (int r = 0; r < shard->world; ++r)
     if (!shard->voxel_blocks_dev[r] || !shard->raycast_result_dev[r] || !shard->barrier_flags_dev[r])
       return fail(ITM_B200_EINVAL, "every rank's voxel, raycast and flag buffer must be given");
@@ -1008,6 +1161,7 @@ int itm_b200_engine_upload_depth(itm_b200_engine *e, const short *raw_depth_host
   if (!e || !raw_depth_host) return fail(ITM_B200_EINVAL, "NULL argument");
   const size_t P = (size_t)e->c->vp.W * e->c->vp.H;
   CU(cudaMemcpyAsync(e->rawDepth, raw_depth_host, P * 2, cudaMemcpyHostToDevice, e->c->stream));
+  e->haveView = true;
   return ITM_B200_OK;
 }
 
@@ -1044,6 +1198,7 @@ int itm_b200_engine_process_frame(itm_b200_engine *e, const unsigned char *rgb_h
   }
   // colour voxels read view->rgb during integration: then the frame waits for it up front
   if (rgb_host && e->c->sp.voxelWords == 2) CU(cudaStreamWaitEvent(s, e->rgbDone, 0));
+  e->haveView = true;
   enqueue_frame(e);
   if (rgb_host && e->c->sp.voxelWords != 2) CU(cudaStreamWaitEvent(s, e->rgbDone, 0));
   return itm_b200_engine_sync(e, pose_out, nullptr);
@@ -1055,6 +1210,7 @@ int itm_b200_engine_enqueue_frame_dev(itm_b200_engine *e, const short *raw_depth
   const size_t P = (size_t)e->c->vp.W * e->c->vp.H;
   if (e->profiling) cudaEventRecord(e->ev[0], s);
   if (raw_depth_dev != e->rawDepth) CU(cudaMemcpyAsync(e->rawDepth, raw_depth_dev, P * 2, cudaMemcpyDeviceToDevice, s));
+  e->haveView = true;
   enqueue_frame(e);
   CU(cudaGetLastError());
   return ITM_B200_OK;
@@ -1069,7 +1225,16 @@ int itm_b200_engine_run_stage(itm_b200_engine *e, int stage) {
     case 3: stage_integrate(e); stage_shard_barrier(e); break;
     case 6: if (!e->swapStates) return fail(ITM_B200_EINVAL, "engine was created without use_swapping"); { int rc = stage_swap(e); if (rc) return rc; } break;
     case 4: stage_expected_depths(e); break;
-    case 5: stage_raycast(e); stage_shard_barrier(e); stage_icp_maps(e); break;
+    case 5: {
+      // teacher forced: the full rendering is wanted, whatever the last decision was
+      const int approx = e->c->p.use_approximate_raycast;
+      e->c->p.use_approximate_raycast = 0;
+      stage_raycast(e); stage_shard_barrier(e); stage_icp_maps(e);
+      e->c->p.use_approximate_raycast = approx;
+      break;
+    }
+    case 7: stage_forward_render(e, false); break;
+    case 8: launch_track_decide(e->c->st, e->c->p.use_approximate_raycast, e->c->stream); g_launches += 1; break;
     default: return fail(ITM_B200_EINVAL, "unknown stage");
   }
   return itm_b200_engine_sync(e, nullptr, nullptr);
@@ -1094,6 +1259,12 @@ int itm_b200_engine_get_buffer(itm_b200_engine *e, int which, void **dev_ptr, si
     case ITM_B200_BUF_RAW_DEPTH: p = e->rawDepth; break;
     case ITM_B200_BUF_RGB: p = e->rgb; break;
     case ITM_B200_BUF_SWAP_STATES: p = e->swapStates; break;
+    case ITM_B200_BUF_FORWARD_PROJECTION: p = e->forwardProjection; break;
+    case ITM_B200_BUF_FWD_MISSING_POINTS: p = e->fwdMissing; break;
+    case ITM_B200_BUF_FREEVIEW_VISIBLE_IDS: p = e->freeVisibleIds; break;
+    case ITM_B200_BUF_FREEVIEW_MINMAX: p = e->freeMinmax; break;
+    case ITM_B200_BUF_FREEVIEW_RAYCAST_RESULT: p = e->freeRaycastResult; break;
+    case ITM_B200_BUF_FREEVIEW_IMAGE: p = e->freeImage; break;
     case ITM_B200_BUF_PYRAMID_1: case ITM_B200_BUF_PYRAMID_2: case ITM_B200_BUF_PYRAMID_3: case ITM_B200_BUF_PYRAMID_4:
       p = e->c->pyramid[which - ITM_B200_BUF_PYRAMID_1 + 1]; break;
     default: return fail(ITM_B200_EINVAL, "unknown buffer id");
@@ -1147,9 +1318,9 @@ int itm_b200_engine_get_state(itm_b200_engine *e, float pose_d[16], float pose_p
     state6[0] = h->noVisibleEntries;
     state6[1] = h->lastFreeBlockId;
     state6[2] = h->lastFreeExcessId;
-    state6[3] = e->agePointCloud;
-    state6[4] = 0;
-    state6[5] = 0;
+    state6[3] = h->agePointCloud;
+    state6[4] = h->requiresFullRendering;
+    state6[5] = h->noFwdProjMissingPoints;
   }
   return ITM_B200_OK;
 }
@@ -1166,10 +1337,129 @@ int itm_b200_engine_set_state(itm_b200_engine *e, const float pose_d[16], const 
     h->lastFreeBlockId = state6[1];
     h->lastFreeExcessId = state6[2];
     e->agePointCloud = state6[3];
+    h->agePointCloud = state6[3];
   }
   rc = push_state(e->c);
   if (rc) return rc;
   CU(cudaStreamSynchronize(e->c->stream));
+  return ITM_B200_OK;
+}
+
+// IITMVisualisationEngine::DepthToUchar4 (ITMLib/Engine/ITMVisualisationEngine.cpp:7-57) is host code in the reference for
+// every device type (it runs after UpdateHostFromDevice); same here.  Colour ramp over the valid depth range.
+static float ramp_segment(float v, float y0, float x0, float y1, float x1) { return (v - x0) * (y1 - y0) / (x1 - x0) + y0; }
+static float ramp_base(float v) {
+  if (v <= -0.75f) return 0.0f;
+  if (v <= -0.25f) return ramp_segment(v, 0.0f, -0.75f, 1.0f, -0.25f);
+  if (v <= 0.25f) return 1.0f;
+  if (v <= 0.75f) return ramp_segment(v, 1.0f, 0.25f, 0.0f, 0.75f);
+  return 0.0f;
+}
+static void depth_to_uchar4(unsigned char *dst, const float *src, size_t n) {
+  memset(dst, 0, n * 4);
+  float lo = 100000.0f, hi = -100000.0f;
+  for (size_t i = 0; i < n; ++i) {
+    const float v = src[i];
+    if (v > 0.0f) {
+      if (v < lo) lo = v;
+      if (v > hi) hi = v;
+    }
+  }
+  const float scale = ((hi - lo) != 0) ? 1.0f / (hi - lo) : 1.0f / hi;
+  if (lo == hi) return;
+  for (size_t i = 0; i < n; ++i) {
+    float v = src[i];
+    if (v > 0.0f) {
+      v = (v - lo) * scale;
+      dst[i * 4 + 0] = (unsigned char)(ramp_base(v - 0.5f) * 255.0f);
+      dst[i * 4 + 1] = (unsigned char)(ramp_base(v) * 255.0f);
+      dst[i * 4 + 2] = (unsigned char)(ramp_base(v + 0.5f) * 255.0f);
+      dst[i * 4 + 3] = 255;
+    }
+  }
+}
+
+int itm_b200_engine_get_image(itm_b200_engine *e, int image_type, const float pose_M[16], const float intrinsics[4],
+                              unsigned char *out_host, int out_w, int out_h) {
+  if (!e || !out_host || out_w <= 0 || out_h <= 0) return fail(ITM_B200_EINVAL, "NULL argument");
+  if (!e->haveView) return ITM_B200_OK;  // "if (view == NULL) return;"
+  itm_b200_ctx *c = e->c;
+  cudaStream_t s = c->stream;
+  const size_t P = (size_t)c->vp.W * c->vp.H, N = (size_t)out_w * out_h;
+  const size_t need = (P > N ? P : N) * 4;
+  if (e->imageHostBytes < need) {
+    if (e->imageHost) cudaFreeHost(e->imageHost);
+    e->imageHost = nullptr;
+    e->imageHostBytes = 0;
+    CU(cudaMallocHost(&e->imageHost, need));
+    e->imageHostBytes = need;
+  }
+  const bool sensorSized = out_w == c->vp.W && out_h == c->vp.H;
+  switch (image_type) {
+    case ITM_B200_IMAGE_ORIGINAL_RGB:
+    case ITM_B200_IMAGE_SCENERAYCAST:
+      if (!sensorSized) return fail(ITM_B200_EINVAL, "GetImage: this image type has the sensor's size");
+      CU(cudaMemcpyAsync(out_host, image_type == ITM_B200_IMAGE_ORIGINAL_RGB ? e->rgb : e->raycastImage, P * 4, cudaMemcpyDeviceToHost, s));
+      CU(cudaStreamSynchronize(s));
+      return ITM_B200_OK;
+    case ITM_B200_IMAGE_ORIGINAL_DEPTH:
+      if (!sensorSized) return fail(ITM_B200_EINVAL, "GetImage: this image type has the sensor's size");
+      CU(cudaMemcpyAsync(e->imageHost, e->depth, P * 4, cudaMemcpyDeviceToHost, s));
+      CU(cudaStreamSynchronize(s));
+      depth_to_uchar4(out_host, reinterpret_cast<const float *>(e->imageHost), P);
+      return ITM_B200_OK;
+    case ITM_B200_IMAGE_FREECAMERA_SHADED:
+    case ITM_B200_IMAGE_FREECAMERA_COLOUR_FROM_VOLUME:
+    case ITM_B200_IMAGE_FREECAMERA_COLOUR_FROM_NORMAL:
+      break;
+    default:
+      memset(out_host, 0, N * 4);  // out->Clear() is all InfiniTAM_IMAGE_UNKNOWN does
+      return ITM_B200_OK;
+  }
+  if (!pose_M || !intrinsics) return fail(ITM_B200_EINVAL, "free-view images need a pose and intrinsics");
+  if (e->freeW != out_w || e->freeH != out_h) {  // visualisationEngine->CreateRenderState(out->noDims)
+    cudaFree(e->freeVisibleIds); cudaFree(e->freeMinmax); cudaFree(e->freeRaycastResult); cudaFree(e->freeImage);
+    e->freeVisibleIds = nullptr; e->freeMinmax = nullptr; e->freeRaycastResult = nullptr; e->freeImage = nullptr;
+    e->freeW = e->freeH = 0;
+    CU(cudaMalloc(&e->freeVisibleIds, (size_t)c->sp.nLocal * 4));
+    CU(cudaMalloc(&e->freeMinmax, N * 8));
+    CU(cudaMalloc(&e->freeRaycastResult, N * 16));
+    CU(cudaMalloc(&e->freeImage, N * 4));
+    CU(cudaMemsetAsync(e->freeVisibleIds, 0, (size_t)c->sp.nLocal * 4, s));
+    CU(cudaMemsetAsync(e->freeRaycastResult, 0, N * 16, s));
+    CU(cudaMemsetAsync(e->freeImage, 0, N * 4, s));
+    e->freeW = out_w;
+    e->freeH = out_h;
+    e->bytes[ITM_B200_BUF_FREEVIEW_VISIBLE_IDS] = (size_t)c->sp.nLocal * 4;
+    e->bytes[ITM_B200_BUF_FREEVIEW_MINMAX] = N * 8;
+    e->bytes[ITM_B200_BUF_FREEVIEW_RAYCAST_RESULT] = N * 16;
+    e->bytes[ITM_B200_BUF_FREEVIEW_IMAGE] = N * 4;
+  }
+  memset(e->hstFree, 0, sizeof(FrameState));
+  set_pose_host(e->hstFree, pose_M);
+  CU(cudaMemcpyAsync(e->stFree, e->hstFree, sizeof(FrameState), cudaMemcpyHostToDevice, s));
+  RenderArgs a;
+  memset(&a, 0, sizeof(a));
+  a.shard.world = 1;
+  a.voxels = e->voxels;
+  a.hashTable = e->hash;
+  a.visibleIds = e->freeVisibleIds;
+  a.minmax = e->freeMinmax;
+  a.raycastResult = e->freeRaycastResult;
+  a.st = e->stFree;
+  a.vp.W = out_w; a.vp.H = out_h;
+  a.vp.fx = intrinsics[0]; a.vp.fy = intrinsics[1]; a.vp.cx = intrinsics[2]; a.vp.cy = intrinsics[3];
+  a.sp = c->sp;
+  launch_find_visible_blocks(e->hash, e->freeVisibleIds, e->stFree, a.vp, c->sp, c->sp.nLocal, c->scanTickets + 1, c->visTileState, s);
+  launch_expected_depths(a, s);
+  const int type = image_type == ITM_B200_IMAGE_FREECAMERA_COLOUR_FROM_VOLUME ? ITM_B200_RENDER_COLOUR_FROM_VOLUME
+                 : image_type == ITM_B200_IMAGE_FREECAMERA_COLOUR_FROM_NORMAL ? ITM_B200_RENDER_COLOUR_FROM_NORMAL
+                                                                              : ITM_B200_RENDER_SHADED_GREYSCALE;
+  launch_render_image(a, e->freeImage, type, s);
+  g_launches += 4;
+  CU(cudaMemcpyAsync(out_host, e->freeImage, N * 4, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  CU(cudaGetLastError());
   return ITM_B200_OK;
 }
 

@@ -68,6 +68,7 @@ struct RenderArgs {
   float *normalsMap;    // Vector4f[W*H]
   unsigned char *raycastImage;  // Vector4u[W*H]
   int minmaxReady;      // the min/max image is already initialised (FramePrologue)
+  int gated;            // useApproximateRaycast engines: raycast / ICP maps run only when st->requiresFullRendering
   FrameState *st;
   ViewParams vp;
   SceneParams sp;
@@ -98,6 +99,26 @@ void launch_integrate(const IntegrateArgs &a, cudaStream_t s);
 void launch_expected_depths(const RenderArgs &a, cudaStream_t s);
 void launch_raycast(const RenderArgs &a, cudaStream_t s);
 void launch_icp_maps(const RenderArgs &a, cudaStream_t s);
+
+// ForwardRender (useApproximateRaycast): render.raycastResult is projected into forwardProjection at render.st's pose,
+// holes are ray cast, render.raycastImage is shaded from the result.  gated: skip unless !st->requiresFullRendering.
+struct ForwardArgs {
+  RenderArgs render;
+  float *forwardProjection;   // Vector4f[W*H]
+  int *missingPoints;         // int[W*H] fwdProjMissingPoints
+  int *key;                   // scratch int[W*H], all zero between calls
+  const float *depth;         // view->depth
+  int gated;
+};
+void launch_forward_render(const ForwardArgs &a, cudaStream_t s);
+// st->requiresFullRendering = TrackerFarFromPointCloud() || !useApproximateRaycast
+void launch_track_decide(FrameState *st, int useApproximateRaycast, cudaStream_t s);
+// FindVisibleBlocks at st's pose with the intrinsics in vp: visibleIds in ascending slot order, st->noVisibleEntries
+void launch_find_visible_blocks(const void *hashTable, int *visibleIds, FrameState *st, const ViewParams &vp, const SceneParams &sp,
+                                int visibleCapacity, unsigned long long *ticket, unsigned long long *tileState, cudaStream_t s);
+// RenderImage: raycast at st's pose into a.raycastResult and shade into outImage (Vector4u[W*H]); type 0 grey, 1 colour
+// from volume, 2 colour from normal
+void launch_render_image(const RenderArgs &a, unsigned char *outImage, int type, cudaStream_t s);
 
 void launch_convert_depth(const short *raw, float *out, int n, float a, float b, cudaStream_t s);
 void launch_subsample_holes(float *out, const float *in, int wIn, int hIn, cudaStream_t s);

@@ -28,6 +28,8 @@ _BUF_DTYPES = {
     capi.BUF_RAYCAST_IMAGE: np.uint8, capi.BUF_POINTS: np.float32, capi.BUF_NORMALS: np.float32,
     capi.BUF_RAW_DEPTH: np.int16, capi.BUF_PYRAMID_1: np.float32, capi.BUF_PYRAMID_2: np.float32,
     capi.BUF_PYRAMID_3: np.float32, capi.BUF_PYRAMID_4: np.float32, capi.BUF_RGB: np.uint8, capi.BUF_SWAP_STATES: np.uint8,
+    capi.BUF_FORWARD_PROJECTION: np.float32, capi.BUF_FWD_MISSING_POINTS: np.int32, capi.BUF_FREEVIEW_VISIBLE_IDS: np.int32,
+    capi.BUF_FREEVIEW_MINMAX: np.float32, capi.BUF_FREEVIEW_RAYCAST_RESULT: np.float32, capi.BUF_FREEVIEW_IMAGE: np.uint8,
 }
 
 
@@ -68,6 +70,17 @@ class ITMMainEngine:
         pose = np.zeros(16, dtype=np.float32)
         capi.check(self.lib.itm_b200_engine_process_frame(self.h, _addr(rgbImage), _addr(rawDepthImage), _f32p(pose)))
         return pose
+
+    def GetImage(self, getImageType: int, pose=None, intrinsics=None, width: int | None = None, height: int | None = None):
+        """ITMMainEngine::GetImage (ITMMainEngine.cpp:134-192): returns the (h, w, 4) uint8 image.  pose (column-major
+        16 floats, pose->GetM()) and intrinsics (fx, fy, cx, cy) are needed by the FREECAMERA types only."""
+        w, h = width or self.W, height or self.H
+        out = np.zeros((h, w, 4), dtype=np.uint8)
+        p = None if pose is None else np.ascontiguousarray(pose, np.float32).reshape(16)
+        k = None if intrinsics is None else np.ascontiguousarray(intrinsics, np.float32).reshape(4)
+        capi.check(self.lib.itm_b200_engine_get_image(self.h, int(getImageType), None if p is None else _f32p(p),
+                                                      None if k is None else _f32p(k), out.ctypes.data, w, h))
+        return out
 
     def EnqueueFrameDevice(self, raw_depth_dev_ptr: int):
         capi.check(self.lib.itm_b200_engine_enqueue_frame_dev(self.h, C.c_void_p(raw_depth_dev_ptr)))

@@ -15,9 +15,9 @@ from .ref import HASH_ENTRY_DTYPE
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "_ref", "libitm_adapter.so")
 
-(READ_HASH, READ_VOXELS, READ_VISIBLE_IDS, READ_RAYCAST, READ_POINTS, READ_NORMALS, READ_VISIBLE_TYPES) = range(7)
+(READ_HASH, READ_VOXELS, READ_VISIBLE_IDS, READ_RAYCAST, READ_POINTS, READ_NORMALS, READ_VISIBLE_TYPES, READ_RAYCAST_IMAGE) = range(8)
 _DTYPES = {READ_HASH: HASH_ENTRY_DTYPE, READ_VOXELS: np.uint32, READ_VISIBLE_IDS: np.int32, READ_RAYCAST: np.float32,
-           READ_POINTS: np.float32, READ_NORMALS: np.float32, READ_VISIBLE_TYPES: np.uint8}
+           READ_POINTS: np.float32, READ_NORMALS: np.float32, READ_VISIBLE_TYPES: np.uint8, READ_RAYCAST_IMAGE: np.uint8}
 
 
 def available() -> bool:
@@ -38,6 +38,9 @@ class AdapterEngine:
         lib.adp_read.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong]
         lib.adp_read.restype = C.c_longlong
         lib.adp_last_error.restype = C.c_char_p
+        lib.adp_set_use_approximate_raycast.argtypes = [C.c_void_p, C.c_int]
+        lib.adp_requires_full_rendering.argtypes = [C.c_void_p]
+        lib.adp_get_free_image.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         self.lib, self.W, self.H = lib, w, h
         s = w / 640.0
         fx, fy, cx, cy = intr if intr is not None else (580.0 * s, 580.0 * s, w / 2.0, h / 2.0)
@@ -54,6 +57,22 @@ class AdapterEngine:
         d = np.ascontiguousarray(depth_i16, np.int16)
         if self.lib.adp_process_frame(self.h, d.ctypes.data) != 0:
             raise RuntimeError("adp_process_frame: %s" % self.lib.adp_last_error().decode())
+
+    def set_use_approximate_raycast(self, on=True):
+        self.lib.adp_set_use_approximate_raycast(self.h, int(on))
+
+    @property
+    def requires_full_rendering(self):
+        return bool(self.lib.adp_requires_full_rendering(self.h))
+
+    def get_free_image(self, render_type, pose_M, intr, w, h):
+        """FindVisibleBlocks + CreateExpectedDepths + RenderImage on a free-view render state (ITMMainEngine.cpp:167-186)"""
+        M = np.ascontiguousarray(pose_M, np.float32).reshape(16)
+        k = np.ascontiguousarray(intr, np.float32).reshape(4)
+        out = np.zeros((h, w, 4), np.uint8)
+        if self.lib.adp_get_free_image(self.h, int(render_type), M.ctypes.data, k.ctypes.data, w, h, out.ctypes.data) != 0:
+            raise RuntimeError("adp_get_free_image: %s" % self.lib.adp_last_error().decode())
+        return out
 
     @property
     def pose_M(self):

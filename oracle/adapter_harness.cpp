@@ -39,6 +39,8 @@ struct adp_engine {
   ITMTrackingController *controller;
   ITMTrackingState *trackingState;
   ITMRenderState *renderState;
+  ITMRenderState *renderStateFree;
+  ITMUChar4Image *freeOut;
   ITMView *view;
   ITMUChar4Image *rgb;
   ITMShortImage *rawDepth;
@@ -88,6 +90,8 @@ adp_engine *adp_create(int W, int H, float fx, float fy, float cx, float cy, flo
     e->trackingState = e->controller->BuildTrackingState(e->imgSize);
     e->tracker->UpdateInitialPose(e->trackingState);
     e->view = NULL;
+    e->renderStateFree = NULL;
+    e->freeOut = NULL;
     e->rgb = new ITMUChar4Image(e->imgSize, true, false);
     e->rawDepth = new ITMShortImage(e->imgSize, true, false);
     memset(e->rgb->GetData(MEMORYDEVICE_CPU), 128, (size_t)W * H * 4);
@@ -101,6 +105,8 @@ adp_engine *adp_create(int W, int H, float fx, float fy, float cx, float cy, flo
 void adp_destroy(adp_engine *e) {
   if (!e) return;
   delete e->renderState;
+  if (e->renderStateFree) delete e->renderStateFree;
+  if (e->freeOut) delete e->freeOut;
   delete e->scene;
   delete e->controller;
   delete e->tracker;
@@ -134,6 +140,34 @@ int adp_process_frame(adp_engine *e, const short *depth) {
   }
 }
 
+// settings.useApproximateRaycast: ITMTrackingController::Track / Prepare then alternate CreateICPMaps and ForwardRender
+void adp_set_use_approximate_raycast(adp_engine *e, int on) { e->settings->useApproximateRaycast = on != 0; }
+int adp_requires_full_rendering(adp_engine *e) { return e->trackingState->requiresFullRendering ? 1 : 0; }
+
+// the free-view branch of ITMMainEngine::GetImage (ITMMainEngine.cpp:167-186) through the adapter's visualisation engine
+int adp_get_free_image(adp_engine *e, int renderType, const float *poseM16, const float *intr4, int w, int h, unsigned char *out) {
+  try {
+    if (e->freeOut == NULL || e->freeOut->noDims.x != w || e->freeOut->noDims.y != h) {
+      if (e->freeOut) delete e->freeOut;
+      if (e->renderStateFree) delete e->renderStateFree;
+      e->freeOut = new ITMUChar4Image(Vector2i(w, h), true, false);
+      e->renderStateFree = e->vis->CreateRenderState(e->freeOut->noDims);
+    }
+    Matrix4f M(poseM16);
+    ITMPose pose; pose.SetM(M);
+    ITMIntrinsics intr; intr.SetFrom(intr4[0], intr4[1], intr4[2], intr4[3], (float)w, (float)h);
+    e->vis->FindVisibleBlocks(&pose, &intr, e->renderStateFree);
+    e->vis->CreateExpectedDepths(&pose, &intr, e->renderStateFree);
+    e->vis->RenderImage(&pose, &intr, e->renderStateFree, e->renderStateFree->raycastImage, (IITMVisualisationEngine::RenderImageType)renderType);
+    e->freeOut->SetFrom(e->renderStateFree->raycastImage, ORUtils::MemoryBlock<Vector4u>::CUDA_TO_CPU);
+    memcpy(out, e->freeOut->GetData(MEMORYDEVICE_CPU), (size_t)w * h * 4);
+    return 0;
+  } catch (std::exception &ex) {
+    g_err = ex.what();
+    return -1;
+  }
+}
+
 void adp_get_pose(adp_engine *e, float *M16) { memcpy(M16, e->trackingState->pose_d->GetM().m, 64); }
 
 // counters = {noVisibleEntries, lastFreeBlockId, lastFreeExcessListId, age_pointCloud}
@@ -144,7 +178,8 @@ void adp_counters(adp_engine *e, int *c4) {
   c4[3] = e->trackingState->age_pointCloud;
 }
 
-// which: 0 hash entries, 1 voxel blocks, 2 visible ids, 3 raycast result, 4 points map, 5 normals map, 6 entriesVisibleType
+// which: 0 hash entries, 1 voxel blocks, 2 visible ids, 3 raycast result, 4 points map, 5 normals map, 6 entriesVisibleType,
+// 7 raycastImage
 long long adp_read(adp_engine *e, int which, void *dst, long long capacity) {
   const size_t P = (size_t)e->imgSize.x * e->imgSize.y;
   const void *src = NULL;
@@ -158,6 +193,7 @@ long long adp_read(adp_engine *e, int which, void *dst, long long capacity) {
     case 4: src = e->trackingState->pointCloud->locations->GetData(MEMORYDEVICE_CUDA); bytes = P * 16; break;
     case 5: src = e->trackingState->pointCloud->colours->GetData(MEMORYDEVICE_CUDA); bytes = P * 16; break;
     case 6: src = rs->GetEntriesVisibleType(); bytes = (size_t)ITMVoxelBlockHash::noTotalEntries; break;
+    case 7: src = rs->raycastImage->GetData(MEMORYDEVICE_CUDA); bytes = P * 4; break;
     default: return -1;
   }
   if ((long long)bytes > capacity) return -(long long)bytes;

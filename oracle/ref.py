@@ -5,8 +5,10 @@ legs may import this module; the product (infinitam_b200/) never does.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import os
+import sys
 
 import numpy as np
 
@@ -59,6 +61,12 @@ def load(flavour: str = "parity"):
     return lib
 
 
+def _has(lib, name):
+    if isinstance(lib, _Prefixed):
+        return hasattr(lib._lib, lib._prefix + name[3:])
+    return hasattr(lib, name)
+
+
 def declare_common(lib):
     for name in ("ref_destroy", "ref_track", "ref_integrate", "ref_expected_depths", "ref_icp_maps", "ref_prepare",
                  "ref_icp_prepare"):
@@ -74,6 +82,20 @@ def declare_common(lib):
         for name in ("ref_swap_states", "ref_has_stored_data", "ref_stored_voxel_blocks"):
             getattr(lib, name).argtypes = [C.c_void_p]
             getattr(lib, name).restype = C.c_void_p
+    if _has(lib, "ref_forward_render"):
+        lib.ref_set_use_approximate_raycast.argtypes = [C.c_void_p, C.c_int]
+        lib.ref_set_use_approximate_raycast.restype = None
+        lib.ref_forward_render.argtypes = [C.c_void_p]
+        lib.ref_forward_render.restype = None
+        for name in ("ref_requires_full_rendering", "ref_no_fwd_missing_points", "ref_free_no_visible"):
+            getattr(lib, name).argtypes = [C.c_void_p]
+            getattr(lib, name).restype = C.c_int
+        for name in ("ref_forward_projection", "ref_fwd_missing_points", "ref_free_visible_ids", "ref_free_minmax",
+                     "ref_free_raycast_result"):
+            getattr(lib, name).argtypes = [C.c_void_p]
+            getattr(lib, name).restype = C.c_void_p
+        lib.ref_get_image.argtypes = [C.c_void_p, C.c_int, _f32p, _f32p, C.c_int, C.c_int, C.c_void_p]
+        lib.ref_get_image.restype = C.c_int
     lib.ref_update_view.argtypes = [C.c_void_p, C.c_void_p]
     lib.ref_update_view.restype = None
     lib.ref_process_frame.argtypes = [C.c_void_p, C.c_void_p]
@@ -111,6 +133,23 @@ def _fp(a):
     return a.ctypes.data_as(_f32p)
 
 
+@contextlib.contextmanager
+def _stdout_to_stderr():
+    """C-level stdout of the reference goes to stderr while inside (bench.py must print exactly one JSON line on stdout)"""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    try:
+        os.dup2(2, 1)
+        yield
+    finally:
+        try:
+            C.CDLL(None).fflush(None)
+        except Exception:
+            pass
+        os.dup2(saved, 1)
+        os.close(saved)
+
+
 def _view(ptr, dtype, count):
     dtype = np.dtype(dtype)
     buf = (C.c_char * (count * dtype.itemsize)).from_address(ptr)
@@ -135,7 +174,8 @@ class RefEngine:
         self.lib = load(flavour)
         if self.use_swapping:
             self.lib.ref_set_use_swapping(1)
-        self.h = self.lib.ref_create(self.W, self.H, *self.intr, self.voxel_size, self.mu, self.max_w, self.vf_min, self.vf_max)
+        with _stdout_to_stderr():  # ITMLibSettings() prints its tracker type on std::cout (ITMLibSettings.cpp:85-86)
+            self.h = self.lib.ref_create(self.W, self.H, *self.intr, self.voxel_size, self.mu, self.max_w, self.vf_min, self.vf_max)
         if self.use_swapping:
             self.lib.ref_set_use_swapping(0)
         c = self.const
@@ -199,6 +239,56 @@ class RefEngine:
 
     def icp_maps(self):
         self.lib.ref_icp_maps(self.h)
+
+    # ---- useApproximateRaycast / ForwardRender / GetImage ---------------------------------
+    def set_use_approximate_raycast(self, on=True):
+        self.lib.ref_set_use_approximate_raycast(self.h, int(on))
+
+    @property
+    def requires_full_rendering(self):
+        return bool(self.lib.ref_requires_full_rendering(self.h))
+
+    def forward_render(self):
+        """IITMVisualisationEngine::ForwardRender + age_pointCloud++ (ITMTrackingController.cpp:40-44)"""
+        self.lib.ref_forward_render(self.h)
+
+    def prepare(self):
+        """ITMTrackingController::Prepare"""
+        self.lib.ref_prepare(self.h)
+
+    @property
+    def forward_projection(self):
+        return self._img(self.lib.ref_forward_projection, np.float32, 4)
+
+    @property
+    def fwd_missing_points(self):
+        n = self.lib.ref_no_fwd_missing_points(self.h)
+        return _view(self.lib.ref_fwd_missing_points(self.h), np.int32, self.W * self.H)[:n]
+
+    def get_image(self, image_type, pose_M=None, intr=None, width=None, height=None):
+        """ITMMainEngine::GetImage; returns (h, w, 4) uint8 or None when there is no view yet"""
+        w, h = width or self.W, height or self.H
+        out = np.zeros((h, w, 4), np.uint8)
+        M = np.ascontiguousarray(pose_M if pose_M is not None else np.eye(4).T.reshape(16), dtype=np.float32).reshape(16)
+        k = np.ascontiguousarray(intr if intr is not None else self.intr, dtype=np.float32).reshape(4)
+        rc = self.lib.ref_get_image(self.h, int(image_type), _fp(M), _fp(k), w, h, out.ctypes.data)
+        self._free_dims = (w, h)
+        return out if rc == 0 else None
+
+    @property
+    def free_visible_ids(self):
+        n = self.lib.ref_free_no_visible(self.h)
+        return _view(self.lib.ref_free_visible_ids(self.h), np.int32, self.n_local)[:n]
+
+    @property
+    def free_minmax(self):
+        w, h = self._free_dims
+        return _view(self.lib.ref_free_minmax(self.h), np.float32, w * h * 2).reshape(h, w, 2)
+
+    @property
+    def free_raycast_result(self):
+        w, h = self._free_dims
+        return _view(self.lib.ref_free_raycast_result(self.h), np.float32, w * h * 4).reshape(h, w, 4)
 
     def process_frame(self, depth_i16):
         d = np.ascontiguousarray(depth_i16, dtype=np.int16)

@@ -61,6 +61,8 @@ struct ref_engine {
   ITMTrackingController *controller;
   ITMTrackingState *trackingState;
   ITMRenderState *renderState;
+  ITMRenderState *renderStateFree;  // ITMMainEngine::renderState_freeview
+  ITMUChar4Image *freeOut;
   ITMView *view;
   ITMUChar4Image *rgb;
   ITMShortImage *rawDepth;
@@ -135,6 +137,8 @@ ref_engine *ref_create(int W, int H, float fx, float fy, float cx, float cy,
   e->trackingState = e->controller->BuildTrackingState(e->imgSize);
   e->tracker->UpdateInitialPose(e->trackingState);
   e->view = NULL;
+  e->renderStateFree = NULL;
+  e->freeOut = NULL;
   e->rgb = new ITMUChar4Image(e->imgSize, true, false);
   e->rawDepth = new ITMShortImage(e->imgSize, true, false);
   memset(e->rgb->GetData(MEMORYDEVICE_CPU), 128, (size_t)W * H * 4);
@@ -144,6 +148,8 @@ ref_engine *ref_create(int W, int H, float fx, float fy, float cx, float cy,
 void ref_destroy(ref_engine *e) {
   if (e->swapper) delete e->swapper;
   delete e->renderState;
+  if (e->renderStateFree) delete e->renderStateFree;
+  if (e->freeOut) delete e->freeOut;
   delete e->scene;
   delete e->controller;
   delete e->tracker;
@@ -199,6 +205,68 @@ void ref_icp_maps(ref_engine *e) {
   if (e->trackingState->age_pointCloud == -1) e->trackingState->age_pointCloud = -2;
   else e->trackingState->age_pointCloud = 0;
 }
+// settings.useApproximateRaycast (ITMLibSettings.cpp:32); read by ITMTrackingController::Track (:15)
+void ref_set_use_approximate_raycast(ref_engine *e, int on) { e->settings->useApproximateRaycast = on != 0; }
+int ref_requires_full_rendering(ref_engine *e) { return e->trackingState->requiresFullRendering ? 1 : 0; }
+// what ITMTrackingController::Prepare does when !requiresFullRendering (ITMTrackingController.cpp:40-44)
+void ref_forward_render(ref_engine *e) {
+  e->vis->ForwardRender(e->view, e->trackingState, e->renderState);
+  e->trackingState->age_pointCloud++;
+}
+float *ref_forward_projection(ref_engine *e) { return (float *)e->renderState->forwardProjection->GetData(MEMORYDEVICE_CPU); }
+int *ref_fwd_missing_points(ref_engine *e) { return e->renderState->fwdProjMissingPoints->GetData(MEMORYDEVICE_CPU); }
+int ref_no_fwd_missing_points(ref_engine *e) { return e->renderState->noFwdProjMissingPoints; }
+
+// ITMMainEngine::GetImage (ITMMainEngine.cpp:134-192) composed from the same public calls.  type = GetImageType.
+// out: Vector4u[w*h].  Returns 0, or -1 when there is no view yet.
+int ref_get_image(ref_engine *e, int type, const float *poseM16, const float *intr4, int w, int h, unsigned char *out) {
+  if (e->view == NULL) return -1;
+  if (e->freeOut == NULL || e->freeOut->noDims.x != w || e->freeOut->noDims.y != h) {
+    if (e->freeOut) delete e->freeOut;
+    e->freeOut = new ITMUChar4Image(Vector2i(w, h), true, false);
+  }
+  ITMUChar4Image *o = e->freeOut;
+  o->Clear();
+  switch (type) {
+    case ITMMainEngine::InfiniTAM_IMAGE_ORIGINAL_RGB:
+      o->SetFrom(e->view->rgb, ORUtils::MemoryBlock<Vector4u>::CPU_TO_CPU);
+      break;
+    case ITMMainEngine::InfiniTAM_IMAGE_ORIGINAL_DEPTH:
+      IITMVisualisationEngine::DepthToUchar4(o, e->view->depth);
+      break;
+    case ITMMainEngine::InfiniTAM_IMAGE_SCENERAYCAST:
+      o->SetFrom(e->renderState->raycastImage, ORUtils::MemoryBlock<Vector4u>::CPU_TO_CPU);
+      break;
+    case ITMMainEngine::InfiniTAM_IMAGE_FREECAMERA_SHADED:
+    case ITMMainEngine::InfiniTAM_IMAGE_FREECAMERA_COLOUR_FROM_VOLUME:
+    case ITMMainEngine::InfiniTAM_IMAGE_FREECAMERA_COLOUR_FROM_NORMAL: {
+      IITMVisualisationEngine::RenderImageType rt = IITMVisualisationEngine::RENDER_SHADED_GREYSCALE;
+      if (type == ITMMainEngine::InfiniTAM_IMAGE_FREECAMERA_COLOUR_FROM_VOLUME) rt = IITMVisualisationEngine::RENDER_COLOUR_FROM_VOLUME;
+      else if (type == ITMMainEngine::InfiniTAM_IMAGE_FREECAMERA_COLOUR_FROM_NORMAL) rt = IITMVisualisationEngine::RENDER_COLOUR_FROM_NORMAL;
+      if (e->renderStateFree == NULL || e->renderStateFree->raycastImage->noDims.x != w || e->renderStateFree->raycastImage->noDims.y != h) {
+        if (e->renderStateFree) delete e->renderStateFree;
+        e->renderStateFree = e->vis->CreateRenderState(o->noDims);
+      }
+      Matrix4f M(poseM16);
+      ITMPose pose; pose.SetM(M);
+      ITMIntrinsics intr; intr.SetFrom(intr4[0], intr4[1], intr4[2], intr4[3], (float)w, (float)h);
+      e->vis->FindVisibleBlocks(&pose, &intr, e->renderStateFree);
+      e->vis->CreateExpectedDepths(&pose, &intr, e->renderStateFree);
+      e->vis->RenderImage(&pose, &intr, e->renderStateFree, e->renderStateFree->raycastImage, rt);
+      o->SetFrom(e->renderStateFree->raycastImage, ORUtils::MemoryBlock<Vector4u>::CPU_TO_CPU);
+      break;
+    }
+    default: break;
+  }
+  memcpy(out, o->GetData(MEMORYDEVICE_CPU), (size_t)w * h * 4);
+  return 0;
+}
+// renderState_freeview after the last free-view ref_get_image
+int *ref_free_visible_ids(ref_engine *e) { return e->renderStateFree ? ((ITMRenderState_VH *)e->renderStateFree)->GetVisibleEntryIDs() : NULL; }
+int ref_free_no_visible(ref_engine *e) { return e->renderStateFree ? ((ITMRenderState_VH *)e->renderStateFree)->noVisibleEntries : -1; }
+float *ref_free_minmax(ref_engine *e) { return e->renderStateFree ? (float *)e->renderStateFree->renderingRangeImage->GetData(MEMORYDEVICE_CPU) : NULL; }
+float *ref_free_raycast_result(ref_engine *e) { return e->renderStateFree ? (float *)e->renderStateFree->raycastResult->GetData(MEMORYDEVICE_CPU) : NULL; }
+
 void ref_prepare(ref_engine *e) { e->controller->Prepare(e->trackingState, e->view, e->renderState); }
 
 void ref_process_frame(ref_engine *e, const short *depth) {

@@ -54,3 +54,38 @@ def test_reference_host_objects_with_b200_engines(device_loop):
         assert abs(int(ca[0]) - int(co[0])) <= 0.01 * co[0] and abs(int(ca[1]) - int(co[1])) <= 0.01 * (o.n_local - co[1])
         assert int(ca[3]) == int(o.age)
     a.close(); o.close()
+
+
+@needs_libs
+def test_adapter_approximate_raycast_and_free_view():
+    """settings.useApproximateRaycast through the reference's own ITMTrackingController (Track decides on the host, Prepare
+    calls the adapter's CreateICPMaps or ForwardRender), then a free-view rendering through FindVisibleBlocks +
+    CreateExpectedDepths + RenderImage of the adapter - against the reference CPU engines doing the same."""
+    w, h, n = 320, 240, 12
+    seq = synth.sequence(n, w, h)
+    o = ref.RefEngine(w, h)
+    o.set_use_approximate_raycast(True)
+    a = adapter.AdapterEngine(w, h, intr=o.intr)
+    a.set_use_approximate_raycast(True)
+    n_fwd = 0
+    for k in range(n):
+        o.process_frame(seq[k])
+        a.process_frame(seq[k])
+        rot, trans = parity.pose_diff(a.pose_M, o.pose_M)
+        assert rot <= 1e-4 and trans <= 1e-4, "frame %d pose differs: %g rad %g m" % (k, rot, trans)
+        assert a.requires_full_rendering == o.requires_full_rendering
+        assert int(a.counters[3]) == int(o.age)
+        n_fwd += 0 if o.requires_full_rendering else 1
+        img_a, img_o = a.read(adapter.READ_RAYCAST_IMAGE).reshape(h, w, 4), o.raycast_image
+        bad = np.count_nonzero(np.abs(img_a.astype(np.int32) - img_o.astype(np.int32)).max(axis=2) > 1)
+        assert bad <= 0.002 * w * h, "frame %d: %d raycast-image pixels differ" % (k, bad)
+    assert n_fwd > 0
+    M = np.eye(4, dtype=np.float32)
+    M[:3, 3] = [0.1, -0.04, 0.06]
+    M = M.T.reshape(16)
+    for rt in (0, 2):
+        img_a = a.get_free_image(rt, M, o.intr, w, h)
+        img_o = o.get_image(3 if rt == 0 else 5, M, o.intr, w, h)
+        bad = np.count_nonzero(np.abs(img_a.astype(np.int32) - img_o.astype(np.int32)).max(axis=2) > 1)
+        assert img_o.any() and bad <= 0.002 * w * h, "free-view type %d: %d pixels differ" % (rt, bad)
+    a.close(); o.close()
