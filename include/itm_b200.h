@@ -191,6 +191,18 @@ int itm_b200_find_surface(itm_b200_ctx *ctx, const itm_b200_scene *scene, itm_b2
 int itm_b200_render_image(itm_b200_ctx *ctx, const itm_b200_scene *scene, itm_b200_render_state *rs, const float pose_M[16],
                           const float intrinsics[4], unsigned char *out_image_dev, int type);
 
+/* ITMMeshingEngine::MeshScene (Engine/ITMMeshingEngine.h:22; CPU reference ITMMeshingEngine_CPU.cpp:19-58): marching
+ * cubes over every allocated voxel block.  triangles_dev = mesh->triangles (ITMMesh::Triangle = 9 floats, Objects/ITMMesh.h:17)
+ * with room for no_max_triangles (ITMMesh::noMaxTriangles = SDF_LOCAL_BLOCK_NUM * 32); it is cleared and filled in the
+ * reference's serial order (entry id, z, y, x, case-table order), *no_total_triangles = mesh->noTotalTriangles. */
+int itm_b200_mesh_scene(itm_b200_ctx *ctx, const itm_b200_scene *scene, float *triangles_dev, unsigned no_max_triangles,
+                        unsigned *no_total_triangles);
+
+/* ITMMesh::WriteSTL / WriteOBJ (Objects/ITMMesh.h:34-118) for a HOST triangle array (9 floats per triangle): same bytes as
+ * the reference writes.  No GPU needed. */
+int itm_b200_write_stl(const char *file_name, const float *triangles_host, unsigned no_triangles);
+int itm_b200_write_obj(const char *file_name, const float *triangles_host, unsigned no_triangles);
+
 /* ITMViewBuilder::ConvertDepthAffineToFloat (Engine/ITMViewBuilder.h) */
 int itm_b200_convert_depth_affine_to_float(itm_b200_ctx *ctx, float *depth_out_dev, const short *depth_in_dev, int w, int h,
                                            float a, float b);
@@ -310,6 +322,13 @@ int itm_b200_engine_set_state(itm_b200_engine *e, const float pose_d[16], const 
 #define ITM_B200_IMAGE_FREECAMERA_COLOUR_FROM_NORMAL 5
 int itm_b200_engine_get_image(itm_b200_engine *e, int image_type, const float pose_M[16], const float intrinsics[4],
                               unsigned char *out_host, int out_w, int out_h);
+
+/* ITMMainEngine::UpdateMesh / SaveSceneToMesh (ITMMainEngine.cpp:97-109): meshes the engine's scene into a device mesh of
+ * ITMMesh::noMaxTriangles and copies the first min(noTotalTriangles, capacity_triangles) triangles to triangles_host
+ * (9 floats each; may be NULL to only count).  *no_total_triangles = mesh->noTotalTriangles. */
+int itm_b200_engine_mesh_scene(itm_b200_engine *e, float *triangles_host, unsigned capacity_triangles, unsigned *no_total_triangles);
+/* SaveSceneToMesh: MeshScene + ITMMesh::WriteSTL */
+int itm_b200_engine_save_scene_to_mesh(itm_b200_engine *e, const char *file_name);
 
 /* ICP evaluations (ComputeGandH calls) per pyramid level during the last frame fetched by
  * itm_b200_engine_sync / _process_frame (level 0 = full resolution). */

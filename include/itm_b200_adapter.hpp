@@ -11,6 +11,8 @@
 //       (ITMLib/Engine/ITMSceneReconstructionEngine.h:29-52)
 //   ITMVisualisationEngine<TVoxel,TIndex> / IITMVisualisationEngine    -> ITMVisualisationEngine_B200
 //       (ITMLib/Engine/ITMVisualisationEngine.h:18-110)
+//   ITMMeshingEngine<TVoxel,TIndex>::MeshScene                         -> ITMMeshingEngine_B200
+//       (ITMLib/Engine/ITMMeshingEngine.h:15-30)
 //   ITMDepthTracker (TrackCamera + ComputeGandH)                       -> ITMDepthTracker_B200
 //       (ITMLib/Engine/ITMDepthTracker.h:24-66)
 //   ITMLowLevelEngine::FilterSubsampleWithHoles(float)                 -> ITMLowLevelEngine_B200
@@ -33,6 +35,7 @@
 
 #include "ITMLib/Engine/ITMDepthTracker.h"
 #include "ITMLib/Engine/ITMLowLevelEngine.h"
+#include "ITMLib/Engine/ITMMeshingEngine.h"
 #include "ITMLib/Engine/ITMSceneReconstructionEngine.h"
 #include "ITMLib/Engine/ITMViewBuilder.h"
 #include "ITMLib/Engine/ITMVisualisationEngine.h"
@@ -253,6 +256,26 @@ class ITMVisualisationEngine_B200<TVoxel, ITMVoxelBlockHash> : public ITMVisuali
 
   // the colour tracker's point cloud (TRACKER_COLOR) is outside the depth-ICP fusion path (out of scope)
   void CreatePointCloud(const ITMView *, ITMTrackingState *, ITMRenderState *, bool) const { DIEWITHEXCEPTION("libitm_b200: CreatePointCloud not provided"); }
+};
+
+// ---------------------------------------------------------------------------------------------
+template <class TVoxel, class TIndex>
+class ITMMeshingEngine_B200;
+
+template <class TVoxel>
+class ITMMeshingEngine_B200<TVoxel, ITMVoxelBlockHash> : public ITMMeshingEngine<TVoxel, ITMVoxelBlockHash> {
+  ITMB200Context *c;
+
+ public:
+  explicit ITMMeshingEngine_B200(ITMB200Context *context) : c(context) {}
+
+  /// mesh must have been created with MEMORYDEVICE_CUDA (ITMMainEngine.cpp:48 does so for DEVICE_CUDA)
+  void MeshScene(ITMMesh *mesh, const ITMScene<TVoxel, ITMVoxelBlockHash> *scene) {
+    itm_b200_scene s = b200_detail::scene_view(const_cast<ITMScene<TVoxel, ITMVoxelBlockHash> *>(scene));
+    unsigned n = 0;
+    itm_b200_check(itm_b200_mesh_scene(c->ctx, &s, (float *)mesh->triangles->GetData(MEMORYDEVICE_CUDA), ITMMesh::noMaxTriangles, &n), "MeshScene");
+    mesh->noTotalTriangles = n;
+  }
 };
 
 // ---------------------------------------------------------------------------------------------

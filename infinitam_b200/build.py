@@ -14,7 +14,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libitm_b200.so")
-SOURCES = ["engine.cu", "k_view.cu", "k_alloc.cu", "k_integrate.cu", "k_render.cu", "k_vis.cu", "k_icp.cu", "k_swap.cu"]
+SOURCES = ["engine.cu", "k_view.cu", "k_alloc.cu", "k_integrate.cu", "k_render.cu", "k_vis.cu", "k_mesh.cu", "k_icp.cu", "k_swap.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 EXTRA = os.environ.get("ITM_B200_DEFINES", "").split()  # e.g. -DITM_ICP_TRACE for tools/icp_trace.py
 FLAGS = [

@@ -104,7 +104,8 @@ SYMBOLS = [
     "itm_b200_engine_set_state", "itm_b200_engine_icp_stats", "itm_b200_engine_set_profiling", "itm_b200_engine_stage_times",
     "itm_b200_mat4_inv", "itm_b200_pose_from_inv_m_coerced", "itm_b200_compute_delta",
     "itm_b200_forward_render", "itm_b200_find_visible_blocks", "itm_b200_find_surface", "itm_b200_render_image",
-    "itm_b200_engine_get_image",
+    "itm_b200_engine_get_image", "itm_b200_mesh_scene", "itm_b200_write_stl", "itm_b200_write_obj",
+    "itm_b200_engine_mesh_scene", "itm_b200_engine_save_scene_to_mesh",
 ]
 
 _lib = None
@@ -144,6 +145,11 @@ def load():
     lib.itm_b200_find_surface.argtypes = [vp, C.POINTER(Scene), C.POINTER(RenderState), f32p, f32p]
     lib.itm_b200_render_image.argtypes = [vp, C.POINTER(Scene), C.POINTER(RenderState), f32p, f32p, vp, C.c_int]
     lib.itm_b200_engine_get_image.argtypes = [vp, C.c_int, f32p, f32p, vp, C.c_int, C.c_int]
+    lib.itm_b200_mesh_scene.argtypes = [vp, C.POINTER(Scene), vp, C.c_uint, C.POINTER(C.c_uint)]
+    lib.itm_b200_write_stl.argtypes = [C.c_char_p, vp, C.c_uint]
+    lib.itm_b200_write_obj.argtypes = [C.c_char_p, vp, C.c_uint]
+    lib.itm_b200_engine_mesh_scene.argtypes = [vp, vp, C.c_uint, C.POINTER(C.c_uint)]
+    lib.itm_b200_engine_save_scene_to_mesh.argtypes = [vp, C.c_char_p]
     lib.itm_b200_convert_depth_affine_to_float.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_float, C.c_float]
     lib.itm_b200_filter_subsample_with_holes.argtypes = [vp, vp, vp, C.c_int, C.c_int]
     lib.itm_b200_compute_g_and_h.argtypes = [vp, vp, C.c_int, C.c_int, f32p, vp, vp, C.c_int, C.c_int, f32p, f32p, f32p,

@@ -62,6 +62,12 @@ struct itm_b200_ctx {
   unsigned long long *icpRows = nullptr;   // tagged CTA partial sums of k_icp_track
   unsigned long long *icpBcast = nullptr;  // tagged pose broadcast ring
   unsigned icpEpoch = 0;
+  // MeshScene scratch (allocated on first use)
+  int *meshBlockList = nullptr;
+  unsigned *meshCounts = nullptr;
+  unsigned long long *meshOffsets = nullptr;
+  FrameState *meshSt = nullptr;       // device
+  FrameState *meshHst = nullptr;      // pinned
   int *fwdKey = nullptr;       // ForwardRender: winning source pixel + 1 per destination pixel, all zero between calls
   float *icpOut = nullptr;     // 44 floats
   float *icpPoseIn = nullptr;  // 16 floats
@@ -182,6 +188,8 @@ void ctx_free(itm_b200_ctx *c) {
   cudaFree(c->icpBcast);
   cudaFree(c->icpOut);
   cudaFree(c->fwdKey);
+  cudaFree(c->meshBlockList); cudaFree(c->meshCounts); cudaFree(c->meshOffsets); cudaFree(c->meshSt);
+  if (c->meshHst) cudaFreeHost(c->meshHst);
   cudaFree(c->icpPoseIn);
   cudaFree(c->st);
   if (c->hst) cudaFreeHost(c->hst);
@@ -585,6 +593,83 @@ int itm_b200_render_image(itm_b200_ctx *c, const itm_b200_scene *scene, itm_b200
   return raycast_layer_a(c, scene, rs, pose_M, intrinsics, out_image_dev, type);
 }
 
+// ---------------------------------------------------------------------------------------------
+// meshing
+static int mesh_scene_common(itm_b200_ctx *c, const void *voxels, const void *hash, float *triangles_dev, unsigned no_max_triangles,
+                             unsigned *no_total_triangles) {
+  if (no_max_triangles < 2) return fail(ITM_B200_EINVAL, "mesh capacity too small");
+  if (!c->meshBlockList) {
+    CU(cudaMalloc(&c->meshBlockList, (size_t)c->sp.nLocal * sizeof(int)));
+    CU(cudaMalloc(&c->meshCounts, (size_t)c->sp.nLocal * sizeof(unsigned)));
+    CU(cudaMalloc(&c->meshOffsets, ((size_t)c->sp.nLocal + 1) * sizeof(unsigned long long)));
+    CU(cudaMalloc(&c->meshSt, sizeof(FrameState)));
+    CU(cudaMallocHost(&c->meshHst, sizeof(FrameState)));
+  }
+  memset(c->meshHst, 0, sizeof(FrameState));
+  CU(cudaMemcpyAsync(c->meshSt, c->meshHst, sizeof(FrameState), cudaMemcpyHostToDevice, c->stream));
+  MeshArgs a;
+  a.voxels = voxels;
+  a.hashTable = hash;
+  a.blockList = c->meshBlockList;
+  a.counts = c->meshCounts;
+  a.offsets = c->meshOffsets;
+  a.triangles = triangles_dev;
+  a.noMaxTriangles = no_max_triangles;
+  a.st = c->meshSt;
+  a.sp = c->sp;
+  a.ticket = c->scanTickets + 1;
+  a.tileState = c->visTileState;
+  launch_mesh_scene(a, c->stream);
+  g_launches += 4;
+  CU(cudaMemcpyAsync(c->meshHst, c->meshSt, sizeof(FrameState), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  if (no_total_triangles) *no_total_triangles = (unsigned)c->meshHst->noMeshTriangles;
+  return ITM_B200_OK;
+}
+
+int itm_b200_mesh_scene(itm_b200_ctx *c, const itm_b200_scene *scene, float *triangles_dev, unsigned no_max_triangles,
+                        unsigned *no_total_triangles) {
+  if (!c || !scene || !triangles_dev) return fail(ITM_B200_EINVAL, "NULL argument");
+  return mesh_scene_common(c, scene->voxel_blocks_dev, scene->hash_entries_dev, triangles_dev, no_max_triangles, no_total_triangles);
+}
+
+// ITMMesh::WriteSTL (Objects/ITMMesh.h:66-118): 80 spaces, the triangle count, then per triangle a zero normal, the three
+// vertices in REVERSE order (p2, p1, p0) and a zero attribute word
+int itm_b200_write_stl(const char *file_name, const float *t, unsigned n) {
+  if (!file_name || (!t && n)) return fail(ITM_B200_EINVAL, "NULL argument");
+  FILE *f = fopen(file_name, "wb+");
+  if (!f) return fail(ITM_B200_EINVAL, std::string("cannot open ") + file_name);
+  char header[80];
+  memset(header, ' ', sizeof(header));
+  fwrite(header, 1, sizeof(header), f);
+  fwrite(&n, sizeof(int), 1, f);
+  std::vector<unsigned char> rec(50, 0);
+  for (unsigned i = 0; i < n; ++i) {
+    const float *p = t + (size_t)i * 9;
+    memcpy(&rec[12], p + 6, 12);
+    memcpy(&rec[24], p + 3, 12);
+    memcpy(&rec[36], p + 0, 12);
+    fwrite(rec.data(), 1, 50, f);
+  }
+  fclose(f);
+  return ITM_B200_OK;
+}
+
+// ITMMesh::WriteOBJ (Objects/ITMMesh.h:34-64)
+int itm_b200_write_obj(const char *file_name, const float *t, unsigned n) {
+  if (!file_name || (!t && n)) return fail(ITM_B200_EINVAL, "NULL argument");
+  FILE *f = fopen(file_name, "w+");
+  if (!f) return fail(ITM_B200_EINVAL, std::string("cannot open ") + file_name);
+  for (unsigned i = 0; i < n; ++i) {
+    const float *p = t + (size_t)i * 9;
+    for (int v = 0; v < 3; ++v) fprintf(f, "v %f %f %f\n", p[v * 3 + 0], p[v * 3 + 1], p[v * 3 + 2]);
+  }
+  for (unsigned i = 0; i < n; ++i) fprintf(f, "f %d %d %d\n", i * 3 + 2 + 1, i * 3 + 1 + 1, i * 3 + 0 + 1);
+  fclose(f);
+  return ITM_B200_OK;
+}
+
 int itm_b200_convert_depth_affine_to_float(itm_b200_ctx *c, float *out_dev, const short *in_dev, int w, int h, float a, float b) {
   if (!c || !out_dev || !in_dev) return fail(ITM_B200_EINVAL, "NULL argument");
   launch_convert_depth(in_dev, out_dev, w * h, a, b, c->stream);
@@ -700,6 +785,7 @@ struct itm_b200_engine {
   unsigned char *freeImage = nullptr;
   FrameState *stFree = nullptr;    // device: pose + visible count of the free-view camera
   FrameState *hstFree = nullptr;   // pinned
+  float *meshTriangles = nullptr;      // device ITMMesh::triangles (noMaxTriangles), allocated by the first UpdateMesh
   unsigned char *imageHost = nullptr;  // pinned staging for GetImage
   size_t imageHostBytes = 0;
   // tracking state
@@ -812,6 +898,7 @@ void engine_free(itm_b200_engine *e) {
   cudaFree(e->freeVisibleIds); cudaFree(e->freeMinmax); cudaFree(e->freeRaycastResult); cudaFree(e->freeImage);
   if (e->hstFree) cudaFreeHost(e->hstFree);
   if (e->imageHost) cudaFreeHost(e->imageHost);
+  cudaFree(e->meshTriangles);
   cudaFree(e->swapStates); cudaFree(e->neededIds); cudaFree(e->transfer); cudaFree(e->hasSynced);
   cudaFree(e->swapTileState); cudaFree(e->swapTicket);
   if (e->neededIdsHost) cudaFreeHost(e->neededIdsHost);
@@ -1389,6 +1476,7 @@ int itm_b200_engine_get_image(itm_b200_engine *e, int image_type, const float po
   const size_t need = (P > N ? P : N) * 4;
   if (e->imageHostBytes < need) {
     if (e->imageHost) cudaFreeHost(e->imageHost);
+  cudaFree(e->meshTriangles);
     e->imageHost = nullptr;
     e->imageHostBytes = 0;
     CU(cudaMallocHost(&e->imageHost, need));
@@ -1461,6 +1549,32 @@ int itm_b200_engine_get_image(itm_b200_engine *e, int image_type, const float po
   CU(cudaStreamSynchronize(s));
   CU(cudaGetLastError());
   return ITM_B200_OK;
+}
+
+int itm_b200_engine_mesh_scene(itm_b200_engine *e, float *triangles_host, unsigned capacity_triangles, unsigned *no_total_triangles) {
+  if (!e) return fail(ITM_B200_EINVAL, "NULL engine");
+  itm_b200_ctx *c = e->c;
+  const unsigned noMax = (unsigned)c->sp.nLocal * 32u;  // ITMMesh::noMaxTriangles (Objects/ITMMesh.h:22)
+  if (!e->meshTriangles) CU(cudaMalloc(&e->meshTriangles, (size_t)noMax * 36));
+  unsigned n = 0;
+  int rc = mesh_scene_common(c, e->voxels, e->hash, e->meshTriangles, noMax, &n);
+  if (rc) return rc;
+  if (no_total_triangles) *no_total_triangles = n;
+  if (triangles_host) {
+    const unsigned k = n < capacity_triangles ? n : capacity_triangles;
+    if (k) CU(cudaMemcpy(triangles_host, e->meshTriangles, (size_t)k * 36, cudaMemcpyDeviceToHost));
+  }
+  return ITM_B200_OK;
+}
+
+int itm_b200_engine_save_scene_to_mesh(itm_b200_engine *e, const char *file_name) {
+  if (!e || !file_name) return fail(ITM_B200_EINVAL, "NULL argument");
+  unsigned n = 0;
+  int rc = itm_b200_engine_mesh_scene(e, nullptr, 0, &n);
+  if (rc) return rc;
+  std::vector<float> host((size_t)n * 9);
+  if (n) CU(cudaMemcpy(host.data(), e->meshTriangles, (size_t)n * 36, cudaMemcpyDeviceToHost));
+  return itm_b200_write_stl(file_name, host.data(), n);
 }
 
 int itm_b200_engine_icp_stats(itm_b200_engine *e, int evals_per_level[ITM_B200_MAX_LEVELS]) {

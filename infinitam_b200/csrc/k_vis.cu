@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(256) k_fwd_shade(const float4 *__restrict__ fw
 
 __global__ void __launch_bounds__(256) k_find_visible(const HashEntry *__restrict__ table, int *__restrict__ visibleIds, FrameState *st,
                                                       ViewParams vp, SceneParams sp, int visibleCapacity, unsigned long long *ticket,
-                                                      unsigned long long *tileState, int numTiles) {
+                                                      unsigned long long *tileState, int numTiles, int allAllocated) {
   __shared__ unsigned sWarp[8];
   __shared__ unsigned sTotal;
   __shared__ unsigned sExA;
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(256) k_find_visible(const HashEntry *__restric
     bool vis = false;
     if (slot < sp.nEntries) {
       const HashEntry e = load_entry(table, slot);
-      if (e.ptr >= 0) vis = block_visible(sM, e.px, e.py, e.pz, sp.voxelSize, vp);
+      if (e.ptr >= 0) vis = allAllocated ? true : block_visible(sM, e.px, e.py, e.pz, sp.voxelSize, vp);
     }
     const unsigned b = __ballot_sync(0xffffffffu, vis);
     if (lane == 0) sBallot[warp][i] = b;
@@ -376,10 +376,11 @@ void launch_forward_render(const ForwardArgs &a, cudaStream_t s) {
 }
 
 void launch_find_visible_blocks(const void *hashTable, int *visibleIds, FrameState *st, const ViewParams &vp, const SceneParams &sp,
-                                int visibleCapacity, unsigned long long *ticket, unsigned long long *tileState, cudaStream_t s) {
+                                int visibleCapacity, unsigned long long *ticket, unsigned long long *tileState, cudaStream_t s,
+                                int allAllocated) {
   const int numTiles = (sp.nEntries + VIS_TILE - 1) / VIS_TILE;
   k_find_visible<<<numTiles, 256, 0, s>>>(reinterpret_cast<const HashEntry *>(hashTable), visibleIds, st, vp, sp, visibleCapacity, ticket,
-                                          tileState, numTiles);
+                                          tileState, numTiles, allAllocated);
 }
 
 void launch_render_image(const RenderArgs &a, unsigned char *outImage, int type, cudaStream_t s) {

@@ -115,7 +115,23 @@ void launch_forward_render(const ForwardArgs &a, cudaStream_t s);
 void launch_track_decide(FrameState *st, int useApproximateRaycast, cudaStream_t s);
 // FindVisibleBlocks at st's pose with the intrinsics in vp: visibleIds in ascending slot order, st->noVisibleEntries
 void launch_find_visible_blocks(const void *hashTable, int *visibleIds, FrameState *st, const ViewParams &vp, const SceneParams &sp,
-                                int visibleCapacity, unsigned long long *ticket, unsigned long long *tileState, cudaStream_t s);
+                                int visibleCapacity, unsigned long long *ticket, unsigned long long *tileState, cudaStream_t s,
+                                int allAllocated = 0);  // allAllocated: list every entry that owns a voxel block (meshing)
+// ITMMeshingEngine::MeshScene: marching cubes over every allocated block, triangles in the reference's serial order
+struct MeshArgs {
+  const void *voxels;
+  const void *hashTable;
+  int *blockList;                 // scratch int[nLocal]: allocated entries, ascending
+  unsigned *counts;               // scratch unsigned[nLocal]
+  unsigned long long *offsets;    // scratch u64[nLocal + 1]
+  void *triangles;                // ITMMesh::Triangle[noMaxTriangles] (36 B each)
+  unsigned noMaxTriangles;
+  FrameState *st;                 // a FrameState of its own: noVisibleEntries = list length, noMeshTriangles = result
+  SceneParams sp;
+  unsigned long long *ticket;     // scan scratch (see launch_find_visible_blocks)
+  unsigned long long *tileState;
+};
+void launch_mesh_scene(const MeshArgs &a, cudaStream_t s);
 // RenderImage: raycast at st's pose into a.raycastResult and shade into outImage (Vector4u[W*H]); type 0 grey, 1 colour
 // from volume, 2 colour from normal
 void launch_render_image(const RenderArgs &a, unsigned char *outImage, int type, cudaStream_t s);

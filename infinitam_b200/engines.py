@@ -82,6 +82,20 @@ class ITMMainEngine:
                                                       None if k is None else _f32p(k), out.ctypes.data, w, h))
         return out
 
+    def UpdateMesh(self):
+        """ITMMainEngine::UpdateMesh (ITMMainEngine.cpp:97-101): marching cubes over the scene; returns the (n, 9) float32
+        triangle array (p0, p1, p2 per row) in the reference's order"""
+        n = C.c_uint()
+        capi.check(self.lib.itm_b200_engine_mesh_scene(self.h, None, 0, C.byref(n)))
+        tri = np.zeros((n.value, 9), dtype=np.float32)
+        if n.value:
+            capi.check(self.lib.itm_b200_engine_mesh_scene(self.h, tri.ctypes.data, n.value, C.byref(n)))
+        return tri
+
+    def SaveSceneToMesh(self, objFileName: str):
+        """ITMMainEngine::SaveSceneToMesh (ITMMainEngine.cpp:103-109): MeshScene + ITMMesh::WriteSTL"""
+        capi.check(self.lib.itm_b200_engine_save_scene_to_mesh(self.h, str(objFileName).encode()))
+
     def EnqueueFrameDevice(self, raw_depth_dev_ptr: int):
         capi.check(self.lib.itm_b200_engine_enqueue_frame_dev(self.h, C.c_void_p(raw_depth_dev_ptr)))
 

@@ -61,6 +61,13 @@ class AdapterEngine:
     def set_use_approximate_raycast(self, on=True):
         self.lib.adp_set_use_approximate_raycast(self.h, int(on))
 
+    def save_scene_to_mesh(self, path):
+        self.lib.adp_save_scene_to_mesh.argtypes = [C.c_void_p, C.c_char_p]
+        n = self.lib.adp_save_scene_to_mesh(self.h, str(path).encode())
+        if n < 0:
+            raise RuntimeError("adp_save_scene_to_mesh: %s" % self.lib.adp_last_error().decode())
+        return n
+
     @property
     def requires_full_rendering(self):
         return bool(self.lib.adp_requires_full_rendering(self.h))

@@ -41,6 +41,8 @@ struct adp_engine {
   ITMRenderState *renderState;
   ITMRenderState *renderStateFree;
   ITMUChar4Image *freeOut;
+  ITMMesh *mesh;
+  ITMMeshingEngine_B200<TV, TI> *meshing;
   ITMView *view;
   ITMUChar4Image *rgb;
   ITMShortImage *rawDepth;
@@ -92,6 +94,8 @@ adp_engine *adp_create(int W, int H, float fx, float fy, float cx, float cy, flo
     e->view = NULL;
     e->renderStateFree = NULL;
     e->freeOut = NULL;
+    e->mesh = NULL;
+    e->meshing = new ITMMeshingEngine_B200<TV, TI>(e->ctx);
     e->rgb = new ITMUChar4Image(e->imgSize, true, false);
     e->rawDepth = new ITMShortImage(e->imgSize, true, false);
     memset(e->rgb->GetData(MEMORYDEVICE_CPU), 128, (size_t)W * H * 4);
@@ -107,6 +111,8 @@ void adp_destroy(adp_engine *e) {
   delete e->renderState;
   if (e->renderStateFree) delete e->renderStateFree;
   if (e->freeOut) delete e->freeOut;
+  if (e->mesh) delete e->mesh;
+  delete e->meshing;
   delete e->scene;
   delete e->controller;
   delete e->tracker;
@@ -162,6 +168,19 @@ int adp_get_free_image(adp_engine *e, int renderType, const float *poseM16, cons
     e->freeOut->SetFrom(e->renderStateFree->raycastImage, ORUtils::MemoryBlock<Vector4u>::CUDA_TO_CPU);
     memcpy(out, e->freeOut->GetData(MEMORYDEVICE_CPU), (size_t)w * h * 4);
     return 0;
+  } catch (std::exception &ex) {
+    g_err = ex.what();
+    return -1;
+  }
+}
+
+// ITMMainEngine::SaveSceneToMesh (ITMMainEngine.cpp:103-109): MeshScene into a CUDA ITMMesh, then the reference's own WriteSTL
+int adp_save_scene_to_mesh(adp_engine *e, const char *fileName) {
+  try {
+    if (!e->mesh) e->mesh = new ITMMesh(MEMORYDEVICE_CUDA);
+    e->meshing->MeshScene(e->mesh, e->scene);
+    e->mesh->WriteSTL(fileName);
+    return (int)e->mesh->noTotalTriangles;
   } catch (std::exception &ex) {
     g_err = ex.what();
     return -1;

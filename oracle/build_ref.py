@@ -44,12 +44,14 @@ SOURCES = [
     "ITMLib/Engine/DeviceSpecific/CPU/ITMSceneReconstructionEngine_CPU.cpp",
     "ITMLib/Engine/DeviceSpecific/CPU/ITMVisualisationEngine_CPU.cpp",
     "ITMLib/Engine/DeviceSpecific/CPU/ITMSwappingEngine_CPU.cpp",
+    "ITMLib/Engine/DeviceSpecific/CPU/ITMMeshingEngine_CPU.cpp",
 ]
 
 # sources that ref_harness.cpp compiles itself (by #include) when it instantiates them for another voxel type
 VOXEL_DEPENDENT = ["ITMLib/Engine/DeviceSpecific/CPU/ITMSceneReconstructionEngine_CPU.cpp",
                    "ITMLib/Engine/DeviceSpecific/CPU/ITMVisualisationEngine_CPU.cpp",
-                   "ITMLib/Engine/DeviceSpecific/CPU/ITMSwappingEngine_CPU.cpp"]
+                   "ITMLib/Engine/DeviceSpecific/CPU/ITMSwappingEngine_CPU.cpp",
+                   "ITMLib/Engine/DeviceSpecific/CPU/ITMMeshingEngine_CPU.cpp"]
 
 FLAVOURS = {
     "libitm_ref.so": ["-O2", "-ffp-contract=off"],

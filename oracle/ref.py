@@ -96,6 +96,13 @@ def declare_common(lib):
             getattr(lib, name).restype = C.c_void_p
         lib.ref_get_image.argtypes = [C.c_void_p, C.c_int, _f32p, _f32p, C.c_int, C.c_int, C.c_void_p]
         lib.ref_get_image.restype = C.c_int
+    if _has(lib, "ref_mesh_scene"):
+        lib.ref_mesh_scene.argtypes = [C.c_void_p, C.POINTER(_f32p), _i32p]
+        lib.ref_mesh_scene.restype = C.c_int
+        lib.ref_write_stl.argtypes = [C.c_void_p, C.c_char_p]
+        lib.ref_write_stl.restype = None
+        lib.ref_write_obj.argtypes = [C.c_void_p, C.c_char_p]
+        lib.ref_write_obj.restype = None
     lib.ref_update_view.argtypes = [C.c_void_p, C.c_void_p]
     lib.ref_update_view.restype = None
     lib.ref_process_frame.argtypes = [C.c_void_p, C.c_void_p]
@@ -289,6 +296,24 @@ class RefEngine:
     def free_raycast_result(self):
         w, h = self._free_dims
         return _view(self.lib.ref_free_raycast_result(self.h), np.float32, w * h * 4).reshape(h, w, 4)
+
+    # ---- meshing -----------------------------------------------------------------------
+    def mesh_scene(self, whole_buffer=False):
+        """ITMMeshingEngine::MeshScene; returns the (n, 9) float32 triangle array (a view onto the reference's mesh; the
+        whole noMaxTriangles buffer when whole_buffer)"""
+        p, nmax = _f32p(), C.c_int()
+        n = self.lib.ref_mesh_scene(self.h, C.byref(p), C.byref(nmax))
+        self.no_max_triangles = nmax.value
+        rows = nmax.value if whole_buffer else n
+        arr = np.ctypeslib.as_array(p, shape=(nmax.value, 9))
+        self.no_total_triangles = n
+        return arr[:rows]
+
+    def write_stl(self, path):
+        self.lib.ref_write_stl(self.h, str(path).encode())
+
+    def write_obj(self, path):
+        self.lib.ref_write_obj(self.h, str(path).encode())
 
     def process_frame(self, depth_i16):
         d = np.ascontiguousarray(depth_i16, dtype=np.int16)

@@ -44,6 +44,8 @@ typedef ITMVoxel_s_rgb TV;
 template class ITMLib::Engine::ITMSceneReconstructionEngine_CPU<ITMVoxel_s_rgb, ITMVoxelBlockHash>;
 template class ITMLib::Engine::ITMVisualisationEngine_CPU<ITMVoxel_s_rgb, ITMVoxelBlockHash>;
 template class ITMLib::Engine::ITMSwappingEngine_CPU<ITMVoxel_s_rgb, ITMVoxelBlockHash>;
+#include "ITMLib/Engine/DeviceSpecific/CPU/ITMMeshingEngine_CPU.cpp"
+template class ITMLib::Engine::ITMMeshingEngine_CPU<ITMVoxel_s_rgb, ITMVoxelBlockHash>;
 #else
 typedef ITMVoxel TV;
 #endif
@@ -63,6 +65,8 @@ struct ref_engine {
   ITMRenderState *renderState;
   ITMRenderState *renderStateFree;  // ITMMainEngine::renderState_freeview
   ITMUChar4Image *freeOut;
+  ITMMesh *mesh;
+  ITMMeshingEngine_CPU<TV, TI> *meshing;
   ITMView *view;
   ITMUChar4Image *rgb;
   ITMShortImage *rawDepth;
@@ -139,6 +143,8 @@ ref_engine *ref_create(int W, int H, float fx, float fy, float cx, float cy,
   e->view = NULL;
   e->renderStateFree = NULL;
   e->freeOut = NULL;
+  e->mesh = NULL;
+  e->meshing = NULL;
   e->rgb = new ITMUChar4Image(e->imgSize, true, false);
   e->rawDepth = new ITMShortImage(e->imgSize, true, false);
   memset(e->rgb->GetData(MEMORYDEVICE_CPU), 128, (size_t)W * H * 4);
@@ -150,6 +156,8 @@ void ref_destroy(ref_engine *e) {
   delete e->renderState;
   if (e->renderStateFree) delete e->renderStateFree;
   if (e->freeOut) delete e->freeOut;
+  if (e->mesh) delete e->mesh;
+  if (e->meshing) delete e->meshing;
   delete e->scene;
   delete e->controller;
   delete e->tracker;
@@ -266,6 +274,17 @@ int *ref_free_visible_ids(ref_engine *e) { return e->renderStateFree ? ((ITMRend
 int ref_free_no_visible(ref_engine *e) { return e->renderStateFree ? ((ITMRenderState_VH *)e->renderStateFree)->noVisibleEntries : -1; }
 float *ref_free_minmax(ref_engine *e) { return e->renderStateFree ? (float *)e->renderStateFree->renderingRangeImage->GetData(MEMORYDEVICE_CPU) : NULL; }
 float *ref_free_raycast_result(ref_engine *e) { return e->renderStateFree ? (float *)e->renderStateFree->raycastResult->GetData(MEMORYDEVICE_CPU) : NULL; }
+
+// ITMMainEngine::UpdateMesh (ITMMainEngine.cpp:97-101): returns noTotalTriangles; *triangles = ITMMesh::Triangle array
+int ref_mesh_scene(ref_engine *e, float **triangles, int *noMaxTriangles) {
+  if (!e->mesh) { e->mesh = new ITMMesh(MEMORYDEVICE_CPU); e->meshing = new ITMMeshingEngine_CPU<TV, TI>(); }
+  e->meshing->MeshScene(e->mesh, e->scene);
+  *triangles = (float *)e->mesh->triangles->GetData(MEMORYDEVICE_CPU);
+  *noMaxTriangles = (int)ITMMesh::noMaxTriangles;
+  return (int)e->mesh->noTotalTriangles;
+}
+void ref_write_stl(ref_engine *e, const char *fileName) { if (e->mesh) e->mesh->WriteSTL(fileName); }
+void ref_write_obj(ref_engine *e, const char *fileName) { if (e->mesh) e->mesh->WriteOBJ(fileName); }
 
 void ref_prepare(ref_engine *e) { e->controller->Prepare(e->trackingState, e->view, e->renderState); }
 
