@@ -194,6 +194,87 @@ def cpu_baseline_sample(seconds_budget=20.0):
             "sample": "frames %d..%d of the same sequence (%.1f s of CPU work), %s build" % (warm, n - 1, dt, flavour)}
 
 
+def next_rows_sample(params, frames_dev, frames_np, n_frames=40):
+    """SURVEY.md 8f rows measured beside the hot path (rank 0, N=1; outside the timed region of the headline numbers):
+    useApproximateRaycast frames/s, free-view GetImage and MeshScene on the fused scene, each next to the reference CPU
+    engines doing the same on a bounded sample."""
+    import copy
+
+    from infinitam_b200 import capi
+    from infinitam_b200.engines import ITMMainEngine
+
+    out = {}
+    n = min(n_frames, len(frames_np))
+    # --- ForwardRender / useApproximateRaycast
+    p2 = copy.copy(params)
+    p2.use_approximate_raycast = 1
+    eng = ITMMainEngine(p2)
+    eng.set_profiling(True)
+    ms, n_fwd = [], 0
+    for k in range(n):
+        eng.EnqueueFrameDevice(frames_dev[k].data_ptr())
+        eng.Sync()
+        if k >= 5:
+            ms.append(float(eng.stage_times()[7]))
+            n_fwd += 0 if eng.get_state()[2][4] else 1
+    out["approximate_raycast"] = {"frames_per_s": 1e3 * len(ms) / sum(ms), "forward_rendered_frames": n_fwd, "frames": len(ms),
+                                  "kernels": "k_track_decide+k_fwd_project+k_fwd_gather+k_fwd_cast+k_fwd_shade"}
+    # --- free-view rendering and meshing of the scene fused so far
+    K = synth.intrinsics_for(W, H)
+    M = np.eye(4, dtype=np.float32)
+    M[:3, 3] = [0.1, -0.04, 0.06]
+    M = M.T.reshape(16)
+    eng.GetImage(capi.IMAGE_FREECAMERA_SHADED, M, K)
+    t0 = time.perf_counter()
+    reps = 20
+    for _ in range(reps):
+        eng.GetImage(capi.IMAGE_FREECAMERA_SHADED, M, K)
+    out["get_image_freecamera"] = {"ms": 1e3 * (time.perf_counter() - t0) / reps, "what": "FindVisibleBlocks + CreateExpectedDepths + RenderImage + D2H of the 640x480 image, host clock",
+                                   "kernels": "k_find_visible+k_minmax_init+k_expected_depths+k_render_image"}
+    tri = eng.UpdateMesh()
+    t0 = time.perf_counter()
+    reps = 5
+    nt = C.c_uint()
+    for _ in range(reps):
+        capi.check(eng.lib.itm_b200_engine_mesh_scene(eng.h, None, 0, C.byref(nt)))
+    mesh_ms = 1e3 * (time.perf_counter() - t0) / reps
+    _, _, st = eng.get_state()
+    n_blocks = params.sdf_local_block_num - 1 - int(st[1])
+    mesh_bytes = 2 * n_blocks * 2048 + len(tri) * 36 + params.sdf_local_block_num * 32 * 36 + 2 * 16 * (params.sdf_bucket_num + params.sdf_excess_list_size)
+    out["mesh_scene"] = {"ms": mesh_ms, "triangles": int(len(tri)), "allocated_blocks": n_blocks, "mtriangles_per_s": len(tri) / mesh_ms / 1e3,
+                         "algorithmic_bytes": int(mesh_bytes), "achieved_gbs": mesh_bytes / (mesh_ms * 1e-3) / 1e9,
+                         "kernels": "memset+k_find_visible+k_mesh_blocks(count)+k_mesh_scan+k_mesh_blocks(emit)"}
+    eng.close()
+    # --- the reference CPU engines on the same scene
+    try:
+        from oracle import ref
+        flavour = "fast" if ref.available("fast") else ("parity" if ref.available("parity") else None)
+        if flavour:
+            o = ref.RefEngine(W, H, flavour=flavour)
+            o.set_use_approximate_raycast(True)
+            m = min(n, 12)
+            for k in range(3):
+                o.process_frame(frames_np[k])
+            t0 = time.perf_counter()
+            for k in range(3, m):
+                o.process_frame(frames_np[k])
+            cpu = {"approximate_raycast_frames_per_s": (m - 3) / (time.perf_counter() - t0)}
+            t0 = time.perf_counter()
+            o.get_image(capi.IMAGE_FREECAMERA_SHADED, M, K)
+            cpu["get_image_freecamera_ms"] = 1e3 * (time.perf_counter() - t0)
+            t0 = time.perf_counter()
+            tr = o.mesh_scene()
+            cpu["mesh_scene_ms"] = 1e3 * (time.perf_counter() - t0)
+            cpu["mesh_triangles"] = int(len(tr))
+            cpu["cores"] = (os.cpu_count() or 1) if flavour == "fast" else 1
+            cpu["sample"] = "%d frames, %s build; MeshScene is serial in the reference" % (m, flavour)
+            out["cpu_reference"] = cpu
+            o.close()
+    except Exception as ex:  # noqa: BLE001
+        out["cpu_reference"] = {"error": str(ex)}
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -334,6 +415,11 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline_sample()
+        if world == 1 and not args.no_next_rows:
+            try:
+                out["next_rows"] = next_rows_sample(params, frames_dev, frames_np)
+            except Exception as ex:  # noqa: BLE001
+                out["next_rows"] = {"error": str(ex)}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -346,6 +432,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-next-rows", action="store_true", help="skip the SURVEY 8f rows (approximate raycast, GetImage, MeshScene)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -7,6 +7,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -61,7 +62,7 @@ struct itm_b200_ctx {
   unsigned *icpCounter = nullptr;
   unsigned long long *icpRows = nullptr;   // tagged CTA partial sums of k_icp_track
   unsigned long long *icpBcast = nullptr;  // tagged pose broadcast ring
-  unsigned icpEpoch = 0;
+  unsigned *icpEpochDev = nullptr;         // launch number of k_icp_track, advanced on the device, never reset
   // MeshScene scratch (allocated on first use)
   int *meshBlockList = nullptr;
   unsigned *meshCounts = nullptr;
@@ -158,6 +159,8 @@ int ctx_alloc(itm_b200_ctx *c, void *stream) {
   CU(cudaMemsetAsync(c->icpCounter, 0, sizeof(unsigned), c->stream));
   CU(cudaMalloc(&c->icpRows, icp_rows_bytes()));
   CU(cudaMemsetAsync(c->icpRows, 0, icp_rows_bytes(), c->stream));
+  CU(cudaMalloc(&c->icpEpochDev, sizeof(unsigned)));
+  CU(cudaMemsetAsync(c->icpEpochDev, 0, sizeof(unsigned), c->stream));
   CU(cudaMalloc(&c->icpBcast, icp_bcast_bytes()));
   CU(cudaMemsetAsync(c->icpBcast, 0, icp_bcast_bytes(), c->stream));
   CU(cudaMalloc(&c->fwdKey, (size_t)c->p.width * c->p.height * sizeof(int)));
@@ -172,6 +175,9 @@ int ctx_alloc(itm_b200_ctx *c, void *stream) {
     const size_t n = (size_t)c->levels[l].w * c->levels[l].h;
     CU(cudaMalloc(&c->pyramid[l], (n ? n : 1) * sizeof(float)));
   }
+  // occupancy / attribute queries of the persistent kernels happen here, never inside a stream capture
+  (void)icp_track_grid();
+  (void)integrate_grid();
   CU(cudaStreamSynchronize(c->stream));
   return ITM_B200_OK;
 }
@@ -186,6 +192,7 @@ void ctx_free(itm_b200_ctx *c) {
   cudaFree(c->icpCounter);
   cudaFree(c->icpRows);
   cudaFree(c->icpBcast);
+  cudaFree(c->icpEpochDev);
   cudaFree(c->icpOut);
   cudaFree(c->fwdKey);
   cudaFree(c->meshBlockList); cudaFree(c->meshCounts); cudaFree(c->meshOffsets); cudaFree(c->meshSt);
@@ -280,7 +287,8 @@ IcpLevelArgs make_level_args(const itm_b200_ctx *c, int l, const float *depth) {
 }
 
 // ITMDepthTracker::TrackCamera: pyramid (unless already built) + LM loop, all enqueued
-void enqueue_track(itm_b200_ctx *c, const float *depth0, const float *points, const float *normals, bool buildPyramid) {
+void enqueue_track(itm_b200_ctx *c, const float *depth0, const float *points, const float *normals, bool buildPyramid,
+                   bool epochBumped = false) {
   cudaStream_t s = c->stream;
   if (buildPyramid && c->nLevels > 1) {
     float *lv[ITM_MAX_LEVELS];
@@ -303,9 +311,10 @@ void enqueue_track(itm_b200_ctx *c, const float *depth0, const float *points, co
     lv[l] = make_level_args(c, l, l == 0 ? depth0 : c->pyramid[l]);
     iters[l] = c->levels[l].noIterations;
   }
-  const cudaError_t e = launch_icp_track(a, lv, iters, c->nLevels, c->p.no_icp_run_till_level, c->icpRows, c->icpBcast, ++c->icpEpoch, s);
+  const cudaError_t e = launch_icp_track(a, lv, iters, c->nLevels, c->p.no_icp_run_till_level, c->icpRows, c->icpBcast, c->icpEpochDev,
+                                         !epochBumped, s);
   if (e != cudaSuccess) g_lastError = std::string("cooperative launch of the ICP tracker failed: ") + cudaGetErrorString(e);
-  g_launches += 1;
+  g_launches += epochBumped ? 1 : 2;
 }
 
 }  // namespace
@@ -816,6 +825,11 @@ struct itm_b200_engine {
   int lastSwappedIn = 0, lastSwappedOut = 0;
   bool externalBuffers = false;  // voxels / raycastResult belong to the caller (sharded engines)
   unsigned barrierSeq = 0;
+  // whole-frame CUDA graphs, one per (tracking on/off, profiling on/off); see enqueue_frame
+  cudaGraphExec_t frameGraph[4] = {nullptr, nullptr, nullptr, nullptr};
+  int frameGraphLaunches[4] = {0, 0, 0, 0};
+  bool graphsOff = false;   // swapping / sharded engines, ITM_B200_NO_GRAPH=1, or a failed capture
+  bool capturing = false;
   bool profiling = false;
   cudaEvent_t ev[9] = {nullptr};
   float stageMs[8] = {0};
@@ -909,6 +923,8 @@ void engine_free(itm_b200_engine *e) {
   if (e->rgbDone) cudaEventDestroy(e->rgbDone);
   for (int i = 0; i < 9; ++i)
     if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+  for (int i = 0; i < 4; ++i)
+    if (e->frameGraph[i]) cudaGraphExecDestroy(e->frameGraph[i]);
   if (e->c) {
     ctx_free(e->c);
     delete e->c;
@@ -954,7 +970,7 @@ void stage_view(itm_b200_engine *e, bool withPrologue) {
   float *lv[ITM_MAX_LEVELS];
   lv[0] = e->depth;
   for (int l = 1; l < c->nLevels; ++l) lv[l] = c->pyramid[l];
-  FramePrologue pro{c->st, e->visibleIds, e->visType, reinterpret_cast<float2 *>(e->minmax), c->vp.W * c->vp.H};
+  FramePrologue pro{c->st, e->visibleIds, e->visType, reinterpret_cast<float2 *>(e->minmax), c->vp.W * c->vp.H, c->icpEpochDev};
   launch_view_pyramid(e->rawDepth, c->p.depth_calib_a, c->p.depth_calib_b, lv, c->vp.W, c->vp.H, c->nLevels, c->stream,
                       withPrologue ? &pro : nullptr);
   e->prologueDone = withPrologue;
@@ -971,7 +987,8 @@ void stage_track_decide(itm_b200_engine *e) {
 
 void stage_track(itm_b200_engine *e) {
   // ITMTrackingController::Track (ITMTrackingController.cpp:11-16)
-  if (e->agePointCloud != -1) enqueue_track(e->c, e->depth, e->points, e->normals, false);
+  // in a whole frame the view kernel has already advanced the tracker's launch number (FramePrologue)
+  if (e->agePointCloud != -1) enqueue_track(e->c, e->depth, e->points, e->normals, false, e->prologueDone);
   stage_track_decide(e);
 }
 
@@ -1112,28 +1129,84 @@ void stage_shard_barrier(itm_b200_engine *e) {
   }
 }
 
-void enqueue_frame(itm_b200_engine *e) {
-  cudaStream_t s = e->c->stream;
-  const bool prof = e->profiling;
-  if (prof) cudaEventRecord(e->ev[1], s);
+// stage-boundary time stamps; inside a stream capture they must become event-record NODES of the graph
+void stamp(itm_b200_engine *e, int i) {
+  if (!e->profiling) return;
+  if (e->capturing) cudaEventRecordWithFlags(e->ev[i], e->c->stream, cudaEventRecordExternal);
+  else cudaEventRecord(e->ev[i], e->c->stream);
+}
+
+void enqueue_frame_direct(itm_b200_engine *e) {
+  stamp(e, 1);
   stage_view(e, true);
-  if (prof) cudaEventRecord(e->ev[2], s);
+  stamp(e, 2);
   stage_track(e);
-  if (prof) cudaEventRecord(e->ev[3], s);
+  stamp(e, 3);
   stage_allocate(e);
-  if (prof) cudaEventRecord(e->ev[4], s);
+  stamp(e, 4);
   stage_integrate(e);
   stage_shard_barrier(e);  // every rank's share of the voxel updates has landed in every copy
   if (e->swapStates) stage_swap(e);
-  if (prof) cudaEventRecord(e->ev[5], s);
+  stamp(e, 5);
   stage_expected_depths(e);
-  if (prof) cudaEventRecord(e->ev[6], s);
+  stamp(e, 6);
   stage_raycast(e);
   stage_shard_barrier(e);  // ... and every rank's tiles of the raycast image
   if (e->c->p.use_approximate_raycast) stage_forward_render(e, true);
-  if (prof) cudaEventRecord(e->ev[7], s);
+  stamp(e, 7);
   stage_icp_maps(e);
-  if (prof) cudaEventRecord(e->ev[8], s);
+  stamp(e, 8);
+}
+
+// One ProcessFrame = ~12 launches of 3..100 us each, all with launch parameters that never change (everything that varies
+// from frame to frame lives in device memory: FrameState, the tracker's launch number).  So the frame is captured ONCE
+// into a CUDA graph and replayed with a single cudaGraphLaunch: no per-kernel launch latency on the host and back-to-back
+// scheduling on the device.  Two things do differ between frames and select the graph: whether the tracker runs (not on
+// the very first frame) and whether stage time stamps are wanted.  Engines whose frame needs the host in the middle
+// (swapping) or peers (sharding) keep the direct path.
+void enqueue_frame(itm_b200_engine *e) {
+  cudaStream_t s = e->c->stream;
+  if (e->graphsOff) {
+    enqueue_frame_direct(e);
+    return;
+  }
+  const int key = (e->agePointCloud != -1 ? 1 : 0) | (e->profiling ? 2 : 0);
+  if (!e->frameGraph[key]) {
+    const int ageBefore = e->agePointCloud;
+    const unsigned long long launchesBefore = g_launches.load();
+    cudaGraph_t graph = nullptr;
+    bool ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+    if (ok) {
+      e->capturing = true;
+      enqueue_frame_direct(e);
+      e->capturing = false;
+      ok = cudaStreamEndCapture(s, &graph) == cudaSuccess && graph != nullptr;
+    }
+    // the capture recorded the frame but ran nothing: undo its host-side bookkeeping
+    e->frameGraphLaunches[key] = (int)(g_launches.load() - launchesBefore);
+    g_launches -= (unsigned long long)e->frameGraphLaunches[key];
+    e->agePointCloud = ageBefore;
+    e->prologueDone = false;
+    if (ok) ok = cudaGraphInstantiate(&e->frameGraph[key], graph, 0) == cudaSuccess;
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok) {
+      cudaGetLastError();
+      e->frameGraph[key] = nullptr;
+      e->graphsOff = true;
+      enqueue_frame_direct(e);
+      return;
+    }
+  }
+  if (cudaGraphLaunch(e->frameGraph[key], s) != cudaSuccess) {
+    cudaGetLastError();
+    e->graphsOff = true;
+    enqueue_frame_direct(e);
+    return;
+  }
+  g_launches += (unsigned long long)e->frameGraphLaunches[key];
+  // what stage_icp_maps does on the host (ITMTrackingController::Prepare :35-37)
+  if (e->agePointCloud == -1) e->agePointCloud = -2;
+  else e->agePointCloud = 0;
 }
 
 }  // namespace
@@ -1150,6 +1223,7 @@ int itm_b200_engine_create(const itm_b200_params *params, itm_b200_engine **out)
   e->c = c;
   memset(&e->shard, 0, sizeof(e->shard));
   e->shard.world = 1;
+  e->graphsOff = params->use_swapping != 0 || getenv("ITM_B200_NO_GRAPH") != nullptr;
   rc = engine_alloc(e);
   if (!rc) rc = engine_reset(e);
   if (rc) {
@@ -1176,6 +1250,7 @@ int itm_b200_engine_create_sharded(const itm_b200_params *params, const itm_b200
   if (rc) return rc;
   itm_b200_engine *e = new itm_b200_engine();
   e->c = c;
+  e->graphsOff = true;
   e->externalBuffers = true;
   memset(&e->shard, 0, sizeof(e->shard));
   e->shard.rank = shard->rank;
@@ -1274,7 +1349,7 @@ int itm_b200_engine_process_frame(itm_b200_engine *e, const unsigned char *rgb_h
   if (!e || !raw_depth_host) return fail(ITM_B200_EINVAL, "NULL argument");
   cudaStream_t s = e->c->stream;
   const size_t P = (size_t)e->c->vp.W * e->c->vp.H;
-  if (e->profiling) cudaEventRecord(e->ev[0], s);
+  stamp(e, 0);
   // ITMViewBuilder::UpdateView: rgb + raw depth to the device (ITMViewBuilder_CUDA.cu:52-53).  The colour image is
   // not read by the ITMVoxel_s path, so it travels on a second stream while the frame is being fused; the call still
   // returns only after view->rgb is complete.
@@ -1295,7 +1370,7 @@ int itm_b200_engine_enqueue_frame_dev(itm_b200_engine *e, const short *raw_depth
   if (!e || !raw_depth_dev) return fail(ITM_B200_EINVAL, "NULL argument");
   cudaStream_t s = e->c->stream;
   const size_t P = (size_t)e->c->vp.W * e->c->vp.H;
-  if (e->profiling) cudaEventRecord(e->ev[0], s);
+  stamp(e, 0);
   if (raw_depth_dev != e->rawDepth) CU(cudaMemcpyAsync(e->rawDepth, raw_depth_dev, P * 2, cudaMemcpyDeviceToDevice, s));
   e->haveView = true;
   enqueue_frame(e);

@@ -327,7 +327,7 @@ struct TrackArgs {
   int nLevels, noIcpLevel;
   unsigned long long *rows;   // [maxCtas][32] CTA partial sums (float payload)
   unsigned long long *bcast;  // [ICP_RING][ICP_BCAST_WORDS] pose for the next evaluation + flags
-  unsigned epoch;             // launch number (never 0)
+  const unsigned *epochDev;   // launch number (never 0), advanced on the device before this launch
 };
 
 // What a thread needs to finish one pixel once the gathers have landed
@@ -590,6 +590,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_CTAS_PER_SM) k_icp_track(Trac
   }
   __syncthreads();
 
+  const unsigned epoch = *t.epochDev;  // stable for the whole launch: only earlier launches write it
   int evalNo = 0;
   for (int level = t.nLevels - 1; level >= t.noIcpLevel; --level) {
     const int type = t.lv[level].iterationType;
@@ -603,7 +604,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_CTAS_PER_SM) k_icp_track(Trac
     const int NV = (type == ITM_ITER_BOTH) ? 29 : 11;
     const int nIters = t.iters[level];
     for (int it = 0; it < nIters; ++it, ++evalNo) {
-      const unsigned tag = icp_tag(t.epoch, evalNo);
+      const unsigned tag = icp_tag(epoch, evalNo);
       if (blockIdx.x < nActive) {
         if (master && threadIdx.x == 0) { TRACE(evalNo, 0); }
         unsigned long long *myRow = t.rows + (size_t)blockIdx.x * ICP_NVALS;
@@ -725,8 +726,10 @@ int icp_track_grid() {
   return grid;
 }
 
+__global__ void k_icp_bump(unsigned *epochDev) { icp_bump_epoch(epochDev); }
+
 cudaError_t launch_icp_track(const IcpArgs &a, const IcpLevelArgs *levels, const int *iters, int nLevels, int noIcpLevel,
-                             unsigned long long *rows, unsigned long long *bcast, unsigned epoch, cudaStream_t s) {
+                             unsigned long long *rows, unsigned long long *bcast, unsigned *epochDev, bool bumpEpoch, cudaStream_t s) {
   TrackArgs t;
   t.a = a;
   for (int l = 0; l < ITM_MAX_LEVELS; ++l) {
@@ -743,8 +746,8 @@ cudaError_t launch_icp_track(const IcpArgs &a, const IcpLevelArgs *levels, const
   t.noIcpLevel = noIcpLevel;
   t.rows = rows;
   t.bcast = bcast;
-  t.epoch = epoch & 0x1FFFFFFu;
-  if (t.epoch == 0) t.epoch = 1;
+  t.epochDev = epochDev;
+  if (bumpEpoch) k_icp_bump<<<1, 1, 0, s>>>(epochDev);
   void *args[] = {&t};
   return cudaLaunchCooperativeKernel((const void *)k_icp_track, dim3(icp_track_grid()), dim3(ICP_THREADS), args, 0, s);
 }

@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(256) k_convert_pyramid(const short *__restrict
       const int n = st->noVisibleEntries;
       for (int i = gtid; i < n; i += nThreads) args.pro.visType[__ldg(args.pro.visibleIds + i)] = 3;
     }
+    if (args.pro.icpEpoch && gtid == 0) itm::icp_bump_epoch(args.pro.icpEpoch);
     if (args.pro.minmax) {
       float4 *mm4 = reinterpret_cast<float4 *>(args.pro.minmax);
       const float4 init = make_float4(ITM_FAR_AWAY, ITM_VERY_CLOSE, ITM_FAR_AWAY, ITM_VERY_CLOSE);
@@ -156,7 +157,7 @@ void launch_view_pyramid(const short *raw, float a, float b, float *const *level
                          const FramePrologue *prologue) {
   PyramidArgs args;
   if (prologue) args.pro = *prologue;
-  else args.pro = FramePrologue{nullptr, nullptr, nullptr, nullptr, 0};
+  else args.pro = FramePrologue{nullptr, nullptr, nullptr, nullptr, 0, nullptr};
   int w = W, h = H;
   for (int l = 0; l < ITM_MAX_LEVELS; ++l) {
     args.level[l] = l < nLevels ? levels[l] : nullptr;

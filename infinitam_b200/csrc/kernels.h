@@ -147,14 +147,19 @@ struct FramePrologue {
   unsigned char *visType;   // NULL: no marking
   float2 *minmax;           // NULL: no min/max initialisation
   int minmaxPixels;
+  unsigned *icpEpoch;       // NULL: not bumped here (launch_icp_track then bumps it with a launch of its own)
 };
 void launch_view_pyramid(const short *raw, float a, float b, float *const *levels, int W, int H, int nLevels, cudaStream_t s,
                          const FramePrologue *prologue = nullptr);
 
 // The whole ITMDepthTracker::TrackCamera LM loop as ONE persistent cooperative kernel (levels[l], iters[l] for
-// l < nLevels).  rows / bcast: zero-initialised scratch of icp_rows_bytes() / icp_bcast_bytes(); epoch: launch number.
+// l < nLevels).  rows / bcast: zero-initialised scratch of icp_rows_bytes() / icp_bcast_bytes().  epochDev: the launch
+// number, a device word that is never reset (it tags every word CTAs exchange); bumpEpoch: advance it with a 1-thread
+// launch first (false when the frame's view kernel already did, FramePrologue::icpEpoch).  Keeping it on the device
+// makes the launch parameters identical from frame to frame, so a whole frame can be replayed as a CUDA graph.
 cudaError_t launch_icp_track(const IcpArgs &a, const IcpLevelArgs *levels, const int *iters, int nLevels, int noIcpLevel,
-                             unsigned long long *rows, unsigned long long *bcast, unsigned epoch, cudaStream_t s);
+                             unsigned long long *rows, unsigned long long *bcast, unsigned *epochDev, bool bumpEpoch, cudaStream_t s);
+__device__ __forceinline__ void icp_bump_epoch(unsigned *epochDev) { *epochDev = (*epochDev % 0x1FFFFFEu) + 1u; }  // 1 .. 2^25 - 2
 size_t icp_rows_bytes();
 size_t icp_bcast_bytes();
 // One stand-alone evaluation at poseIn (16 floats, device); [n, f, nabla6, hessian36] left in out44 (device).
@@ -185,6 +190,7 @@ void launch_swap_out_apply(const SwapArgs &a, cudaStream_t s);  // SaveToGlobalM
 void launch_shard_barrier(const ShardInfo &sh, unsigned seq, cudaStream_t s);
 int icp_max_ctas();
 int icp_track_grid();
+int integrate_grid();
 
 void launch_set_pose(FrameState *st, cudaStream_t s);  // recompute invM_d from M_d on device
 
