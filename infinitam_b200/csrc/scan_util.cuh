@@ -6,7 +6,7 @@
 // assignment on the GPU every slot needs its rank among the flagged slots: an exclusive
 // prefix sum over ~1.18 M flags.  One kernel does it: each CTA scans its 8192-slot tile in
 // shared memory, publishes the tile aggregate in a 64-bit status word and resolves its
-// global offset by looking back at its predecessors.
+// global offset from its predecessors' aggregates.
 //
 // Status word: [63:62] status  [61:42] epoch (20 bit)  [41:21] count A  [20:0] count B.
 // Tiles are handed out by a 64-bit ticket (never reset): tile = ticket % numTiles,
@@ -39,48 +39,43 @@ __device__ __forceinline__ void scan_st(unsigned long long *p, unsigned long lon
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// Called by warp 0 of the CTA (all 32 lanes).  Publishes this tile's aggregate (a, b) and returns
-// the exclusive prefix over all previous tiles in (exA, exB) (valid in every lane).
+// Called by warp 0 of the CTA (all 32 lanes).  Publishes this tile's aggregate (a, b) and returns the exclusive prefix
+// over all previous tiles in (exA, exB) (valid in every lane).
+// The table is 144 tiles at the shipped size - about one CTA per SM, all resident - so instead of the classic chained
+// look-back (a tile waits for its predecessor's inclusive prefix: up to 5 dependent global round trips here) every tile
+// simply adds up the AGGREGATES of all its predecessors: lane l reads tiles l, l + 32, ... with all loads in flight at
+// once and re-polls only the ones not yet published.  No tile ever waits for another tile's look-back, so the critical
+// path is one publish + one read, whatever the number of tiles.
 __device__ __forceinline__ void scan_lookback(unsigned long long *state, int tile, unsigned epoch, unsigned aggA, unsigned aggB,
                                               unsigned &exA, unsigned &exB) {
   const int lane = threadIdx.x & 31;
-  if (tile == 0) {
-    if (lane == 0) scan_st(state, scan_pack(SCAN_STATUS_PREFIX, epoch, aggA, aggB));
-    exA = 0;
-    exB = 0;
-    return;
-  }
   if (lane == 0) scan_st(state + tile, scan_pack(SCAN_STATUS_AGGREGATE, epoch, aggA, aggB));
   unsigned accA = 0, accB = 0;
-  int base = tile - 1;
-  while (true) {
-    const int j = base - lane;
-    unsigned long long v = 0;
-    bool ready = true;
-    if (j >= 0) {
-      v = scan_ld(state + j);
-      ready = (scan_epoch(v) == epoch) && (scan_status(v) != SCAN_STATUS_INVALID);
-    }
-    if (!__all_sync(0xffffffffu, ready)) continue;  // spin until the whole window is published
-    const bool isPrefix = (j >= 0) && scan_status(v) == SCAN_STATUS_PREFIX;
-    const unsigned pm = __ballot_sync(0xffffffffu, isPrefix);
-    // take lanes up to and including the first (closest) tile that holds an inclusive prefix
-    const int stop = pm ? (__ffs(pm) - 1) : 31;
-    unsigned a = (j >= 0 && lane <= stop) ? scan_a(v) : 0;
-    unsigned b = (j >= 0 && lane <= stop) ? scan_b(v) : 0;
+  constexpr int CH = 8;  // loads in flight per lane
+  for (int j0 = lane; j0 < tile; j0 += 32 * CH) {
+    unsigned long long v[CH];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      a += __shfl_xor_sync(0xffffffffu, a, o);
-      b += __shfl_xor_sync(0xffffffffu, b, o);
+    for (int k = 0; k < CH; ++k) {
+      const int j = j0 + 32 * k;
+      v[k] = j < tile ? scan_ld(state + j) : 0ull;
     }
-    accA += a;
-    accB += b;
-    if (pm || base - 32 < 0) break;
-    base -= 32;
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+      const int j = j0 + 32 * k;
+      if (j < tile) {
+        while (scan_epoch(v[k]) != epoch || scan_status(v[k]) == SCAN_STATUS_INVALID) v[k] = scan_ld(state + j);
+        accA += scan_a(v[k]);
+        accB += scan_b(v[k]);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    accA += __shfl_xor_sync(0xffffffffu, accA, o);
+    accB += __shfl_xor_sync(0xffffffffu, accB, o);
   }
   exA = accA;
   exB = accB;
-  if (lane == 0) scan_st(state + tile, scan_pack(SCAN_STATUS_PREFIX, epoch, accA + aggA, accB + aggB));
 }
 
 // Exclusive scan of a packed per-thread value over a 256-thread CTA.  Returns the exclusive
