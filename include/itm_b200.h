@@ -94,6 +94,9 @@ const char *itm_b200_last_error(void);
 int itm_b200_device_count(void);
 /* total kernels launched by this library in the calling process so far */
 unsigned long long itm_b200_launch_count(void);
+/* the CUDA runtime's pending (non-sticky) error code of the calling thread, cleared by this call; 0 = none.  No entry point
+ * of the library leaves one behind (hosts such as PyTorch that share the CUDA runtime would trip over it). */
+int itm_b200_take_cuda_error(void);
 
 /* ===================================================================================== *
  *  Layer A - one function per engine method, on caller-owned device buffers.            *
@@ -115,6 +118,10 @@ typedef struct itm_b200_scene {
   int *excess_allocation_list_dev;   /* index.GetExcessAllocationList(): int[excess]           */
   int last_free_block_id;            /* localVBA.lastFreeBlockId            (host, in/out)      */
   int last_free_excess_list_id;      /* index.Get/SetLastFreeExcessListId() (host, in/out)      */
+  /* scene->useSwapping: globalCache->GetSwapStates(true), ITMHashSwapState[bucket+excess] (1 byte each); NULL otherwise.
+   * AllocateSceneFromDepth then flags visible entries for swap-in and re-allocates swapped-out ones
+   * (ITMSceneReconstructionEngine_CPU.cpp:250-253, 272-285) */
+  unsigned char *swap_states_dev;
 } itm_b200_scene;
 
 /* ITMRenderState_VH (ITMLib/Objects/ITMRenderState_VH.h:18-70, ITMRenderState.h:20-85) */
@@ -190,6 +197,26 @@ int itm_b200_find_surface(itm_b200_ctx *ctx, const itm_b200_scene *scene, itm_b2
 #define ITM_B200_RENDER_COLOUR_FROM_NORMAL 2
 int itm_b200_render_image(itm_b200_ctx *ctx, const itm_b200_scene *scene, itm_b200_render_state *rs, const float pose_M[16],
                           const float intrinsics[4], unsigned char *out_image_dev, int type);
+
+/* ITMSwappingEngine (Engine/ITMSwappingEngine.h:22-31; CPU reference ITMSwappingEngine_CPU.cpp).  The global cache lives in
+ * HOST memory and stays with the caller (ITMGlobalCache, Objects/ITMGlobalCache.h); these are the device halves of the two
+ * methods, split where the reference's own CUDA engine crosses the bus:
+ *   IntegrateGlobalIntoLocal = swap_in_select -> [host: LoadFromGlobalMemory's copy loop + H2D] -> swap_in_apply
+ *   SaveToGlobalMemory       = swap_out      -> [host: D2H + SetStoredData loop]
+ * Entries are selected in ascending slot order, at most SDF_TRANSFER_BLOCK_NUM (0x1000) per call, like the serial loops. */
+typedef struct itm_b200_swap_buffers {
+  int *needed_entry_ids_dev;           /* globalCache->GetNeededEntryIDs(true):    int[0x1000]          */
+  void *synced_voxel_blocks_dev;       /* globalCache->GetSyncedVoxelBlocks(true): TVoxel[0x1000 * 512] */
+  unsigned char *has_synced_data_dev;  /* globalCache->GetHasSyncedData(true):     bool[0x1000]         */
+} itm_b200_swap_buffers;
+/* entries whose swap state is 1 -> needed_entry_ids_dev[0..*no_needed) */
+int itm_b200_swap_in_select(itm_b200_ctx *ctx, const itm_b200_scene *scene, const itm_b200_swap_buffers *sw, int *no_needed);
+/* combine synced_voxel_blocks_dev (where has_synced_data_dev) into the active blocks, swap state -> 2 */
+int itm_b200_swap_in_apply(itm_b200_ctx *ctx, itm_b200_scene *scene, const itm_b200_swap_buffers *sw, int no_needed);
+/* entries with swap state 2 that are allocated and not visible: ids -> needed_entry_ids_dev, blocks -> synced_voxel_blocks_dev,
+ * the blocks are reset and returned to the free list (scene->last_free_block_id is updated), entries get ptr = -1, state 0 */
+int itm_b200_swap_out(itm_b200_ctx *ctx, itm_b200_scene *scene, const itm_b200_render_state *rs, const itm_b200_swap_buffers *sw,
+                      int *no_needed);
 
 /* ITMMeshingEngine::MeshScene (Engine/ITMMeshingEngine.h:22; CPU reference ITMMeshingEngine_CPU.cpp:19-58): marching
  * cubes over every allocated voxel block.  triangles_dev = mesh->triangles (ITMMesh::Triangle = 9 floats, Objects/ITMMesh.h:17)

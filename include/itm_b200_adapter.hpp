@@ -11,6 +11,8 @@
 //       (ITMLib/Engine/ITMSceneReconstructionEngine.h:29-52)
 //   ITMVisualisationEngine<TVoxel,TIndex> / IITMVisualisationEngine    -> ITMVisualisationEngine_B200
 //       (ITMLib/Engine/ITMVisualisationEngine.h:18-110)
+//   ITMSwappingEngine<TVoxel,TIndex>                                   -> ITMSwappingEngine_B200
+//       (ITMLib/Engine/ITMSwappingEngine.h:22-31)
 //   ITMMeshingEngine<TVoxel,TIndex>::MeshScene                         -> ITMMeshingEngine_B200
 //       (ITMLib/Engine/ITMMeshingEngine.h:15-30)
 //   ITMDepthTracker (TrackCamera + ComputeGandH)                       -> ITMDepthTracker_B200
@@ -25,8 +27,8 @@
 // reference's DEVICE_CUDA branch does (ITMMainEngine.cpp:17-18, ITMTrackingController.h:44): the
 // library borrows their device pointers for the duration of a call and never frees them.
 //
-// Only the voxel-block-hash index with ITMVoxel_s is supported (the north-star path); other
-// instantiations fail at compile time.
+// The voxel-block-hash index with ITMVoxel_s or ITMVoxel_s_rgb is supported (pass the voxel type to ITMB200Context);
+// other instantiations fail at compile time.
 #pragma once
 
 #include <string>
@@ -37,6 +39,7 @@
 #include "ITMLib/Engine/ITMLowLevelEngine.h"
 #include "ITMLib/Engine/ITMMeshingEngine.h"
 #include "ITMLib/Engine/ITMSceneReconstructionEngine.h"
+#include "ITMLib/Engine/ITMSwappingEngine.h"
 #include "ITMLib/Engine/ITMViewBuilder.h"
 #include "ITMLib/Engine/ITMVisualisationEngine.h"
 #include "ITMLib/Objects/ITMRenderState_VH.h"
@@ -59,8 +62,16 @@ class ITMB200Context {
   itm_b200_ctx *ctx;
   itm_b200_params params;
 
-  ITMB200Context(const ITMLibSettings *settings, const ITMRGBDCalib *calib, Vector2i imgSize_d, int device = 0) : ctx(NULL) {
+  /// voxelType: ITM_B200_VOXEL_S for ITMVoxel_s, ITM_B200_VOXEL_S_RGB for ITMVoxel_s_rgb (ITMLibDefines.h:205 picks one)
+  ITMB200Context(const ITMLibSettings *settings, const ITMRGBDCalib *calib, Vector2i imgSize_d, int device = 0,
+                 int voxelType = ITM_B200_VOXEL_S) : ctx(NULL) {
     itm_b200_default_params(&params, imgSize_d.x, imgSize_d.y);
+    params.voxel_type = voxelType;
+    const Vector4f &kr = calib->intrinsics_rgb.projectionParamsSimple.all;
+    params.rgb_fx = kr.x; params.rgb_fy = kr.y; params.rgb_cx = kr.z; params.rgb_cy = kr.w;
+    for (int i = 0; i < 16; ++i) params.trafo_rgb_to_depth_inv[i] = calib->trafo_rgb_to_depth.calib_inv.m[i];
+    params.use_swapping = settings->useSwapping ? 1 : 0;
+    params.use_approximate_raycast = settings->useApproximateRaycast ? 1 : 0;
     const Vector4f &k = calib->intrinsics_d.projectionParamsSimple.all;
     params.fx = k.x; params.fy = k.y; params.cx = k.z; params.cy = k.w;
     const ITMSceneParams &sp = settings->sceneParams;
@@ -102,6 +113,7 @@ inline itm_b200_scene scene_view(ITMScene<TVoxel, ITMVoxelBlockHash> *scene) {
   s.excess_allocation_list_dev = scene->index.GetExcessAllocationList();
   s.last_free_block_id = scene->localVBA.lastFreeBlockId;
   s.last_free_excess_list_id = scene->index.GetLastFreeExcessListId();
+  s.swap_states_dev = scene->useSwapping ? (unsigned char *)scene->globalCache->GetSwapStates(true) : NULL;
   return s;
 }
 
@@ -145,8 +157,11 @@ class ITMSceneReconstructionEngine_B200<TVoxel, ITMVoxelBlockHash> : public ITMS
 
  public:
   explicit ITMSceneReconstructionEngine_B200(ITMB200Context *context) : c(context) {
-    // the library reads and writes the reference's packed voxel directly
-    static_assert(sizeof(TVoxel) == 4 && !TVoxel::hasColorInformation, "libitm_b200: ITMVoxel_s only");
+    // the library reads and writes the reference's packed voxels directly
+    static_assert((sizeof(TVoxel) == 4 && !TVoxel::hasColorInformation) || (sizeof(TVoxel) == 8 && TVoxel::hasColorInformation),
+                  "libitm_b200: ITMVoxel_s or ITMVoxel_s_rgb");
+    if ((c->params.voxel_type == ITM_B200_VOXEL_S_RGB) != (bool)TVoxel::hasColorInformation)
+      DIEWITHEXCEPTION("libitm_b200: the context was created for another voxel type");
   }
 
   void ResetScene(ITMScene<TVoxel, ITMVoxelBlockHash> *scene) {
@@ -158,7 +173,6 @@ class ITMSceneReconstructionEngine_B200<TVoxel, ITMVoxelBlockHash> : public ITMS
 
   void AllocateSceneFromDepth(ITMScene<TVoxel, ITMVoxelBlockHash> *scene, const ITMView *view, const ITMTrackingState *trackingState,
                               const ITMRenderState *renderState, bool onlyUpdateVisibleList = false) {
-    if (scene->useSwapping) DIEWITHEXCEPTION("libitm_b200: swapping is not part of the fusion hot path");
     ITMRenderState_VH *rsVH = (ITMRenderState_VH *)renderState;
     itm_b200_scene s = b200_detail::scene_view(scene);
     itm_b200_render_state r = b200_detail::render_state_view(rsVH);
@@ -175,8 +189,77 @@ class ITMSceneReconstructionEngine_B200<TVoxel, ITMVoxelBlockHash> : public ITMS
                           const ITMRenderState *renderState) {
     itm_b200_scene s = b200_detail::scene_view(scene);
     const itm_b200_render_state r = b200_detail::render_state_view((ITMRenderState_VH *)renderState);
-    itm_b200_check(itm_b200_integrate_into_scene(c->ctx, &s, &r, view->depth->GetData(MEMORYDEVICE_CUDA), trackingState->pose_d->GetM().m),
-                   "IntegrateIntoScene");
+    if (TVoxel::hasColorInformation)
+      itm_b200_check(itm_b200_integrate_into_scene_rgb(c->ctx, &s, &r, view->depth->GetData(MEMORYDEVICE_CUDA),
+                                                       (const unsigned char *)view->rgb->GetData(MEMORYDEVICE_CUDA), trackingState->pose_d->GetM().m),
+                     "IntegrateIntoScene");
+    else
+      itm_b200_check(itm_b200_integrate_into_scene(c->ctx, &s, &r, view->depth->GetData(MEMORYDEVICE_CUDA), trackingState->pose_d->GetM().m),
+                     "IntegrateIntoScene");
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+/// Host swapping.  The global cache (host memory) and its transfer buffers are the reference's own ITMGlobalCache; the
+/// host halves below are what ITMSwappingEngine_CUDA does between its kernels (ITMSwappingEngine_CUDA.cu:46-93, 121-178).
+template <class TVoxel, class TIndex>
+class ITMSwappingEngine_B200;
+
+template <class TVoxel>
+class ITMSwappingEngine_B200<TVoxel, ITMVoxelBlockHash> : public ITMSwappingEngine<TVoxel, ITMVoxelBlockHash> {
+  ITMB200Context *c;
+
+  static itm_b200_swap_buffers buffers(ITMGlobalCache<TVoxel> *gc) {
+    itm_b200_swap_buffers b;
+    b.needed_entry_ids_dev = gc->GetNeededEntryIDs(true);
+    b.synced_voxel_blocks_dev = gc->GetSyncedVoxelBlocks(true);
+    b.has_synced_data_dev = (unsigned char *)gc->GetHasSyncedData(true);
+    return b;
+  }
+
+ public:
+  explicit ITMSwappingEngine_B200(ITMB200Context *context) : c(context) {}
+
+  void IntegrateGlobalIntoLocal(ITMScene<TVoxel, ITMVoxelBlockHash> *scene, ITMRenderState *renderState) {
+    (void)renderState;
+    ITMGlobalCache<TVoxel> *gc = scene->globalCache;
+    itm_b200_scene s = b200_detail::scene_view(scene);
+    const itm_b200_swap_buffers b = buffers(gc);
+    int n = 0;
+    itm_b200_check(itm_b200_swap_in_select(c->ctx, &s, &b, &n), "IntegrateGlobalIntoLocal");
+    if (n <= 0) return;
+    TVoxel *blocksHost = gc->GetSyncedVoxelBlocks(false);
+    bool *hasHost = gc->GetHasSyncedData(false);
+    int *idsHost = gc->GetNeededEntryIDs(false);
+    ITMSafeCall(cudaMemcpy(idsHost, b.needed_entry_ids_dev, sizeof(int) * n, cudaMemcpyDeviceToHost));
+    memset(blocksHost, 0, (size_t)n * SDF_BLOCK_SIZE3 * sizeof(TVoxel));
+    memset(hasHost, 0, (size_t)n * sizeof(bool));
+    for (int i = 0; i < n; i++) {
+      const int entryId = idsHost[i];
+      if (gc->HasStoredData(entryId)) {
+        hasHost[i] = true;
+        memcpy(blocksHost + (size_t)i * SDF_BLOCK_SIZE3, gc->GetStoredVoxelBlock(entryId), SDF_BLOCK_SIZE3 * sizeof(TVoxel));
+      }
+    }
+    ITMSafeCall(cudaMemcpy(b.has_synced_data_dev, hasHost, sizeof(bool) * n, cudaMemcpyHostToDevice));
+    ITMSafeCall(cudaMemcpy(b.synced_voxel_blocks_dev, blocksHost, sizeof(TVoxel) * SDF_BLOCK_SIZE3 * n, cudaMemcpyHostToDevice));
+    itm_b200_check(itm_b200_swap_in_apply(c->ctx, &s, &b, n), "IntegrateGlobalIntoLocal");
+  }
+
+  void SaveToGlobalMemory(ITMScene<TVoxel, ITMVoxelBlockHash> *scene, ITMRenderState *renderState) {
+    ITMGlobalCache<TVoxel> *gc = scene->globalCache;
+    itm_b200_scene s = b200_detail::scene_view(scene);
+    const itm_b200_render_state r = b200_detail::render_state_view((ITMRenderState_VH *)renderState);
+    const itm_b200_swap_buffers b = buffers(gc);
+    int n = 0;
+    itm_b200_check(itm_b200_swap_out(c->ctx, &s, &r, &b, &n), "SaveToGlobalMemory");
+    scene->localVBA.lastFreeBlockId = s.last_free_block_id;
+    if (n <= 0) return;
+    TVoxel *blocksHost = gc->GetSyncedVoxelBlocks(false);
+    int *idsHost = gc->GetNeededEntryIDs(false);
+    ITMSafeCall(cudaMemcpy(idsHost, b.needed_entry_ids_dev, sizeof(int) * n, cudaMemcpyDeviceToHost));
+    ITMSafeCall(cudaMemcpy(blocksHost, b.synced_voxel_blocks_dev, sizeof(TVoxel) * SDF_BLOCK_SIZE3 * n, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; i++) gc->SetStoredData(idsHost[i], blocksHost + (size_t)i * SDF_BLOCK_SIZE3);
   }
 };
 

@@ -56,7 +56,12 @@ class Scene(C.Structure):
         ("voxel_blocks_dev", C.c_void_p), ("hash_entries_dev", C.c_void_p),
         ("vba_allocation_list_dev", C.c_void_p), ("excess_allocation_list_dev", C.c_void_p),
         ("last_free_block_id", C.c_int), ("last_free_excess_list_id", C.c_int),
+        ("swap_states_dev", C.c_void_p),
     ]
+
+
+class SwapBuffers(C.Structure):
+    _fields_ = [("needed_entry_ids_dev", C.c_void_p), ("synced_voxel_blocks_dev", C.c_void_p), ("has_synced_data_dev", C.c_void_p)]
 
 
 class RenderState(C.Structure):
@@ -106,6 +111,7 @@ SYMBOLS = [
     "itm_b200_forward_render", "itm_b200_find_visible_blocks", "itm_b200_find_surface", "itm_b200_render_image",
     "itm_b200_engine_get_image", "itm_b200_mesh_scene", "itm_b200_write_stl", "itm_b200_write_obj",
     "itm_b200_engine_mesh_scene", "itm_b200_engine_save_scene_to_mesh",
+    "itm_b200_take_cuda_error", "itm_b200_swap_in_select", "itm_b200_swap_in_apply", "itm_b200_swap_out",
 ]
 
 _lib = None
@@ -145,6 +151,9 @@ def load():
     lib.itm_b200_find_surface.argtypes = [vp, C.POINTER(Scene), C.POINTER(RenderState), f32p, f32p]
     lib.itm_b200_render_image.argtypes = [vp, C.POINTER(Scene), C.POINTER(RenderState), f32p, f32p, vp, C.c_int]
     lib.itm_b200_engine_get_image.argtypes = [vp, C.c_int, f32p, f32p, vp, C.c_int, C.c_int]
+    lib.itm_b200_swap_in_select.argtypes = [vp, C.POINTER(Scene), C.POINTER(SwapBuffers), i32p]
+    lib.itm_b200_swap_in_apply.argtypes = [vp, C.POINTER(Scene), C.POINTER(SwapBuffers), C.c_int]
+    lib.itm_b200_swap_out.argtypes = [vp, C.POINTER(Scene), C.POINTER(RenderState), C.POINTER(SwapBuffers), i32p]
     lib.itm_b200_mesh_scene.argtypes = [vp, C.POINTER(Scene), vp, C.c_uint, C.POINTER(C.c_uint)]
     lib.itm_b200_write_stl.argtypes = [C.c_char_p, vp, C.c_uint]
     lib.itm_b200_write_obj.argtypes = [C.c_char_p, vp, C.c_uint]

@@ -37,6 +37,16 @@ int fail(int code, const std::string &msg) {
                   std::string(#expr) + ": " + cudaGetErrorString(_e));                             \
   } while (0)
 
+// releases report failures instead of leaving a pending error behind for whoever shares the CUDA runtime
+#define RELEASE(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      fprintf(stderr, "libitm_b200: %s: %s\n", #expr, cudaGetErrorString(_e));                     \
+      cudaGetLastError();                                                                          \
+    }                                                                                              \
+  } while (0)
+
 struct LevelCfg {
   int w, h;
   float fx, fy, cx, cy;
@@ -184,24 +194,24 @@ int ctx_alloc(itm_b200_ctx *c, void *stream) {
 
 void ctx_free(itm_b200_ctx *c) {
   if (!c) return;
-  cudaFree(c->allocKey);
-  cudaFree(c->scanTickets);
-  cudaFree(c->allocTileState);
-  cudaFree(c->visTileState);
-  cudaFree(c->icpPartials);
-  cudaFree(c->icpCounter);
-  cudaFree(c->icpRows);
-  cudaFree(c->icpBcast);
-  cudaFree(c->icpEpochDev);
-  cudaFree(c->icpOut);
-  cudaFree(c->fwdKey);
-  cudaFree(c->meshBlockList); cudaFree(c->meshCounts); cudaFree(c->meshOffsets); cudaFree(c->meshSt);
-  if (c->meshHst) cudaFreeHost(c->meshHst);
-  cudaFree(c->icpPoseIn);
-  cudaFree(c->st);
-  if (c->hst) cudaFreeHost(c->hst);
-  for (int l = 1; l < ITM_MAX_LEVELS; ++l) cudaFree(c->pyramid[l]);
-  if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
+  RELEASE(cudaFree(c->allocKey));
+  RELEASE(cudaFree(c->scanTickets));
+  RELEASE(cudaFree(c->allocTileState));
+  RELEASE(cudaFree(c->visTileState));
+  RELEASE(cudaFree(c->icpPartials));
+  RELEASE(cudaFree(c->icpCounter));
+  RELEASE(cudaFree(c->icpRows));
+  RELEASE(cudaFree(c->icpBcast));
+  RELEASE(cudaFree(c->icpEpochDev));
+  RELEASE(cudaFree(c->icpOut));
+  RELEASE(cudaFree(c->fwdKey));
+  RELEASE(cudaFree(c->meshBlockList)); RELEASE(cudaFree(c->meshCounts)); RELEASE(cudaFree(c->meshOffsets)); RELEASE(cudaFree(c->meshSt));
+  if (c->meshHst) RELEASE(cudaFreeHost(c->meshHst));
+  RELEASE(cudaFree(c->icpPoseIn));
+  RELEASE(cudaFree(c->st));
+  if (c->hst) RELEASE(cudaFreeHost(c->hst));
+  for (int l = 1; l < ITM_MAX_LEVELS; ++l) RELEASE(cudaFree(c->pyramid[l]));
+  if (c->ownStream && c->stream) RELEASE(cudaStreamDestroy(c->stream));
 }
 
 // identity pose etc.
@@ -368,6 +378,10 @@ int itm_b200_device_count(void) {
 
 unsigned long long itm_b200_launch_count(void) { return g_launches.load(); }
 
+// the CUDA runtime's pending (non-sticky) error of the calling thread, cleared by the call; 0 = none.  Every entry point
+// of this library is meant to leave none behind - tests check that.
+int itm_b200_take_cuda_error(void) { return (int)cudaGetLastError(); }
+
 int itm_b200_ctx_create(const itm_b200_params *params, void *stream, itm_b200_ctx **out) {
   if (!out) return fail(ITM_B200_EINVAL, "out is NULL");
   *out = nullptr;
@@ -415,9 +429,10 @@ int itm_b200_allocate_scene_from_depth(itm_b200_ctx *c, itm_b200_scene *scene, i
   c->hst->errorFlags = 0;
   int rc = push_state(c);
   if (rc) return rc;
-  launch_allocate(make_alloc_args(c, depth_dev, scene->hash_entries_dev, scene->vba_allocation_list_dev, scene->excess_allocation_list_dev,
-                                  rs->visible_entry_ids_dev, rs->entries_visible_type_dev, only_update_visible_list),
-                  c->stream);
+  AllocArgs aa = make_alloc_args(c, depth_dev, scene->hash_entries_dev, scene->vba_allocation_list_dev, scene->excess_allocation_list_dev,
+                                 rs->visible_entry_ids_dev, rs->entries_visible_type_dev, only_update_visible_list);
+  aa.swapStates = scene->swap_states_dev;
+  launch_allocate(aa, c->stream);
   g_launches += 4;
   rc = pull_state(c);
   if (rc) return rc;
@@ -600,6 +615,70 @@ int itm_b200_render_image(itm_b200_ctx *c, const itm_b200_scene *scene, itm_b200
   if (!out_image_dev) return fail(ITM_B200_EINVAL, "NULL argument");
   if (type < 0 || type > 2) return fail(ITM_B200_EINVAL, "unknown RenderImageType");
   return raycast_layer_a(c, scene, rs, pose_M, intrinsics, out_image_dev, type);
+}
+
+// ---------------------------------------------------------------------------------------------
+// swapping, Layer A
+static SwapArgs swap_args_layer_a(itm_b200_ctx *c, const itm_b200_scene *scene, const itm_b200_render_state *rs, const itm_b200_swap_buffers *sw) {
+  SwapArgs a;
+  a.voxels = scene->voxel_blocks_dev;
+  a.hashTable = scene->hash_entries_dev;
+  a.vbaAllocList = scene->vba_allocation_list_dev;
+  a.visType = rs ? rs->entries_visible_type_dev : nullptr;
+  a.swapStates = scene->swap_states_dev;
+  a.neededIds = sw->needed_entry_ids_dev;
+  a.transfer = sw->synced_voxel_blocks_dev;
+  a.hasSynced = sw->has_synced_data_dev;
+  a.ticket = c->scanTickets + 1;
+  a.tileState = c->visTileState;
+  a.st = c->st;
+  a.sp = c->sp;
+  return a;
+}
+
+int itm_b200_swap_in_select(itm_b200_ctx *c, const itm_b200_scene *scene, const itm_b200_swap_buffers *sw, int *no_needed) {
+  if (!c || !scene || !sw || !no_needed) return fail(ITM_B200_EINVAL, "NULL argument");
+  if (!scene->swap_states_dev) return fail(ITM_B200_EINVAL, "scene without swap states (scene->useSwapping is off)");
+  c->hst->lastFreeBlockId = scene->last_free_block_id;
+  int rc = push_state(c);
+  if (rc) return rc;
+  launch_swap_select(swap_args_layer_a(c, scene, nullptr, sw), 0, c->stream);
+  g_launches += 1;
+  rc = pull_state(c);
+  if (rc) return rc;
+  *no_needed = c->hst->swapCount;
+  return ITM_B200_OK;
+}
+
+int itm_b200_swap_in_apply(itm_b200_ctx *c, itm_b200_scene *scene, const itm_b200_swap_buffers *sw, int no_needed) {
+  if (!c || !scene || !sw) return fail(ITM_B200_EINVAL, "NULL argument");
+  if (no_needed <= 0) return ITM_B200_OK;
+  c->hst->swapCount = no_needed;
+  c->hst->lastFreeBlockId = scene->last_free_block_id;
+  int rc = push_state(c);
+  if (rc) return rc;
+  launch_swap_in_apply(swap_args_layer_a(c, scene, nullptr, sw), c->stream);
+  g_launches += 1;
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  return ITM_B200_OK;
+}
+
+int itm_b200_swap_out(itm_b200_ctx *c, itm_b200_scene *scene, const itm_b200_render_state *rs, const itm_b200_swap_buffers *sw, int *no_needed) {
+  if (!c || !scene || !rs || !sw || !no_needed) return fail(ITM_B200_EINVAL, "NULL argument");
+  if (!scene->swap_states_dev) return fail(ITM_B200_EINVAL, "scene without swap states (scene->useSwapping is off)");
+  c->hst->lastFreeBlockId = scene->last_free_block_id;
+  int rc = push_state(c);
+  if (rc) return rc;
+  const SwapArgs a = swap_args_layer_a(c, scene, rs, sw);
+  launch_swap_select(a, 1, c->stream);
+  launch_swap_out_apply(a, c->stream);
+  g_launches += 2;
+  rc = pull_state(c);
+  if (rc) return rc;
+  *no_needed = c->hst->swapCount;
+  scene->last_free_block_id = c->hst->lastFreeBlockId;
+  return ITM_B200_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -903,28 +982,28 @@ int engine_alloc(itm_b200_engine *e) {
 }
 
 void engine_free(itm_b200_engine *e) {
-  if (!e->externalBuffers) { cudaFree(e->voxels); cudaFree(e->raycastResult); }
-  cudaFree(e->hash); cudaFree(e->vbaAllocList); cudaFree(e->excessAllocList);
-  cudaFree(e->visibleIds); cudaFree(e->visType); cudaFree(e->minmax);
-  cudaFree(e->raycastImage); cudaFree(e->points); cudaFree(e->normals); cudaFree(e->rawDepth);
-  cudaFree(e->rgb); cudaFree(e->depth);
-  cudaFree(e->forwardProjection); cudaFree(e->fwdMissing); cudaFree(e->stFree);
-  cudaFree(e->freeVisibleIds); cudaFree(e->freeMinmax); cudaFree(e->freeRaycastResult); cudaFree(e->freeImage);
-  if (e->hstFree) cudaFreeHost(e->hstFree);
-  if (e->imageHost) cudaFreeHost(e->imageHost);
-  cudaFree(e->meshTriangles);
-  cudaFree(e->swapStates); cudaFree(e->neededIds); cudaFree(e->transfer); cudaFree(e->hasSynced);
-  cudaFree(e->swapTileState); cudaFree(e->swapTicket);
-  if (e->neededIdsHost) cudaFreeHost(e->neededIdsHost);
-  if (e->transferHost) cudaFreeHost(e->transferHost);
-  if (e->hasSyncedHost) cudaFreeHost(e->hasSyncedHost);
+  if (!e->externalBuffers) { RELEASE(cudaFree(e->voxels)); RELEASE(cudaFree(e->raycastResult)); }
+  RELEASE(cudaFree(e->hash)); RELEASE(cudaFree(e->vbaAllocList)); RELEASE(cudaFree(e->excessAllocList));
+  RELEASE(cudaFree(e->visibleIds)); RELEASE(cudaFree(e->visType)); RELEASE(cudaFree(e->minmax));
+  RELEASE(cudaFree(e->raycastImage)); RELEASE(cudaFree(e->points)); RELEASE(cudaFree(e->normals)); RELEASE(cudaFree(e->rawDepth));
+  RELEASE(cudaFree(e->rgb)); RELEASE(cudaFree(e->depth));
+  RELEASE(cudaFree(e->forwardProjection)); RELEASE(cudaFree(e->fwdMissing)); RELEASE(cudaFree(e->stFree));
+  RELEASE(cudaFree(e->freeVisibleIds)); RELEASE(cudaFree(e->freeMinmax)); RELEASE(cudaFree(e->freeRaycastResult)); RELEASE(cudaFree(e->freeImage));
+  if (e->hstFree) RELEASE(cudaFreeHost(e->hstFree));
+  if (e->imageHost) RELEASE(cudaFreeHost(e->imageHost));
+  RELEASE(cudaFree(e->meshTriangles));
+  RELEASE(cudaFree(e->swapStates)); RELEASE(cudaFree(e->neededIds)); RELEASE(cudaFree(e->transfer)); RELEASE(cudaFree(e->hasSynced));
+  RELEASE(cudaFree(e->swapTileState)); RELEASE(cudaFree(e->swapTicket));
+  if (e->neededIdsHost) RELEASE(cudaFreeHost(e->neededIdsHost));
+  if (e->transferHost) RELEASE(cudaFreeHost(e->transferHost));
+  if (e->hasSyncedHost) RELEASE(cudaFreeHost(e->hasSyncedHost));
   free(e->hasStoredData); free(e->storedVoxelBlocks);
-  if (e->copyStream) cudaStreamDestroy(e->copyStream);
-  if (e->rgbDone) cudaEventDestroy(e->rgbDone);
+  if (e->copyStream) RELEASE(cudaStreamDestroy(e->copyStream));
+  if (e->rgbDone) RELEASE(cudaEventDestroy(e->rgbDone));
   for (int i = 0; i < 9; ++i)
-    if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+    if (e->ev[i]) RELEASE(cudaEventDestroy(e->ev[i]));
   for (int i = 0; i < 4; ++i)
-    if (e->frameGraph[i]) cudaGraphExecDestroy(e->frameGraph[i]);
+    if (e->frameGraph[i]) RELEASE(cudaGraphExecDestroy(e->frameGraph[i]));
   if (e->c) {
     ctx_free(e->c);
     delete e->c;
@@ -1551,7 +1630,6 @@ int itm_b200_engine_get_image(itm_b200_engine *e, int image_type, const float po
   const size_t need = (P > N ? P : N) * 4;
   if (e->imageHostBytes < need) {
     if (e->imageHost) cudaFreeHost(e->imageHost);
-  cudaFree(e->meshTriangles);
     e->imageHost = nullptr;
     e->imageHostBytes = 0;
     CU(cudaMallocHost(&e->imageHost, need));

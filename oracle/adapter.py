@@ -27,8 +27,11 @@ def available() -> bool:
 class AdapterEngine:
     """ITMMainEngine::ProcessFrame composed from reference host objects + the B200 adapter engines."""
 
-    def __init__(self, w, h, intr=None, voxel_size=0.005, mu=0.02, max_w=100, vf_min=0.35, vf_max=3.0, device_loop=True):
+    def __init__(self, w, h, intr=None, voxel_size=0.005, mu=0.02, max_w=100, vf_min=0.35, vf_max=3.0, device_loop=True,
+                 use_swapping=False):
         lib = C.CDLL(LIB)
+        lib.adp_set_use_swapping.argtypes = [C.c_int]
+        lib.adp_count_stored.argtypes = [C.c_void_p]
         lib.adp_create.restype = C.c_void_p
         lib.adp_create.argtypes = [C.c_int, C.c_int] + [C.c_float] * 6 + [C.c_int, C.c_float, C.c_float, C.c_int]
         lib.adp_destroy.argtypes = [C.c_void_p]
@@ -44,7 +47,9 @@ class AdapterEngine:
         self.lib, self.W, self.H = lib, w, h
         s = w / 640.0
         fx, fy, cx, cy = intr if intr is not None else (580.0 * s, 580.0 * s, w / 2.0, h / 2.0)
+        lib.adp_set_use_swapping(int(use_swapping))
         self.h = lib.adp_create(w, h, fx, fy, cx, cy, voxel_size, mu, max_w, vf_min, vf_max, int(device_loop))
+        lib.adp_set_use_swapping(0)
         if not self.h:
             raise RuntimeError("adp_create failed: %s" % lib.adp_last_error().decode())
 
@@ -60,6 +65,11 @@ class AdapterEngine:
 
     def set_use_approximate_raycast(self, on=True):
         self.lib.adp_set_use_approximate_raycast(self.h, int(on))
+
+    @property
+    def stored_blocks(self):
+        """number of voxel blocks parked in the reference's host-side ITMGlobalCache"""
+        return self.lib.adp_count_stored(self.h)
 
     def save_scene_to_mesh(self, path):
         self.lib.adp_save_scene_to_mesh.argtypes = [C.c_void_p, C.c_char_p]

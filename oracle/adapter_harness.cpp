@@ -35,6 +35,7 @@ struct adp_engine {
   ITMViewBuilder_B200 *viewBuilder;
   ITMVisualisationEngine_B200<TV, TI> *vis;
   ITMSceneReconstructionEngine_B200<TV, TI> *reco;
+  ITMSwappingEngine_B200<TV, TI> *swapper;  // NULL unless created after adp_set_use_swapping(1)
   ITMDepthTracker_B200 *tracker;
   ITMTrackingController *controller;
   ITMTrackingState *trackingState;
@@ -50,10 +51,13 @@ struct adp_engine {
 };
 
 static std::string g_err;
+static int g_nextUseSwapping = 0;
 
 extern "C" {
 
 const char *adp_last_error() { return g_err.c_str(); }
+// settings.useSwapping of the engines created from now on (ITMDenseMapper.cpp:16-34, 59-64)
+void adp_set_use_swapping(int on) { g_nextUseSwapping = on; }
 
 adp_engine *adp_create(int W, int H, float fx, float fy, float cx, float cy, float voxelSize, float mu, int maxW, float vfMin, float vfMax,
                        int deviceLoop) {
@@ -62,7 +66,7 @@ adp_engine *adp_create(int W, int H, float fx, float fy, float cx, float cy, flo
     e->settings = new ITMLibSettings();
     e->settings->deviceType = ITMLibSettings::DEVICE_CUDA;  // memory placement of every reference object below
     e->settings->trackerType = ITMLibSettings::TRACKER_ICP;
-    e->settings->useSwapping = false;
+    e->settings->useSwapping = g_nextUseSwapping != 0;
     e->settings->useApproximateRaycast = false;
     e->settings->useBilateralFilter = false;
     e->settings->modelSensorNoise = false;
@@ -78,7 +82,8 @@ adp_engine *adp_create(int W, int H, float fx, float fy, float cx, float cy, flo
 
     // ITMMainEngine::ITMMainEngine (ITMMainEngine.cpp:17-68) with the B200 engine set
     e->ctx = new ITMB200Context(e->settings, &e->calib, e->imgSize);
-    e->scene = new ITMScene<TV, TI>(&e->settings->sceneParams, false, MEMORYDEVICE_CUDA);
+    e->scene = new ITMScene<TV, TI>(&e->settings->sceneParams, e->settings->useSwapping, MEMORYDEVICE_CUDA);
+    e->swapper = e->settings->useSwapping ? new ITMSwappingEngine_B200<TV, TI>(e->ctx) : NULL;
     e->lowLevel = new ITMLowLevelEngine_B200(e->ctx);
     e->viewBuilder = new ITMViewBuilder_B200(&e->calib, e->ctx);
     e->vis = new ITMVisualisationEngine_B200<TV, TI>(e->scene, e->ctx);
@@ -108,6 +113,7 @@ adp_engine *adp_create(int W, int H, float fx, float fy, float cx, float cy, flo
 
 void adp_destroy(adp_engine *e) {
   if (!e) return;
+  if (e->swapper) delete e->swapper;
   delete e->renderState;
   if (e->renderStateFree) delete e->renderStateFree;
   if (e->freeOut) delete e->freeOut;
@@ -138,6 +144,10 @@ int adp_process_frame(adp_engine *e, const short *depth) {
     // ITMDenseMapper::ProcessFrame (ITMDenseMapper.cpp:51-65)
     e->reco->AllocateSceneFromDepth(e->scene, e->view, e->trackingState, e->renderState);
     e->reco->IntegrateIntoScene(e->scene, e->view, e->trackingState, e->renderState);
+    if (e->swapper) {
+      e->swapper->IntegrateGlobalIntoLocal(e->scene, e->renderState);
+      e->swapper->SaveToGlobalMemory(e->scene, e->renderState);
+    }
     e->controller->Prepare(e->trackingState, e->view, e->renderState);
     return 0;
   } catch (std::exception &ex) {
@@ -185,6 +195,14 @@ int adp_save_scene_to_mesh(adp_engine *e, const char *fileName) {
     g_err = ex.what();
     return -1;
   }
+}
+
+// blocks parked in the host-side global cache (ITMGlobalCache::HasStoredData)
+int adp_count_stored(adp_engine *e) {
+  if (!e->swapper) return -1;
+  int n = 0;
+  for (int i = 0; i < e->scene->globalCache->noTotalEntries; ++i) n += e->scene->globalCache->HasStoredData(i) ? 1 : 0;
+  return n;
 }
 
 void adp_get_pose(adp_engine *e, float *M16) { memcpy(M16, e->trackingState->pose_d->GetM().m, 64); }

@@ -17,3 +17,16 @@ def pytest_configure(config):
 def ref_lib_available():
     from oracle import ref
     return ref.available("parity")
+
+
+@pytest.fixture(autouse=True)
+def no_pending_cuda_error(request):
+    """every -m gpu test must leave the CUDA runtime without a pending error (hosts that share the runtime with the library,
+    PyTorch for one, would report it at their next call)"""
+    yield
+    if request.node.get_closest_marker("gpu") is None:
+        return
+    from infinitam_b200 import capi
+    if capi._lib is not None:
+        err = capi._lib.itm_b200_take_cuda_error()
+        assert err == 0, "the test left CUDA error %d pending" % err

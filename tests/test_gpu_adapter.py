@@ -89,3 +89,29 @@ def test_adapter_approximate_raycast_and_free_view():
         bad = np.count_nonzero(np.abs(img_a.astype(np.int32) - img_o.astype(np.int32)).max(axis=2) > 1)
         assert img_o.any() and bad <= 0.002 * w * h, "free-view type %d: %d pixels differ" % (rt, bad)
     a.close(); o.close()
+
+
+@needs_libs
+def test_adapter_swapping_engine():
+    """settings.useSwapping through the reference's own ITMScene / ITMGlobalCache (CUDA memory placement) and the adapter's
+    ITMSwappingEngine_B200 + swap-aware AllocateSceneFromDepth, against the reference CPU engines with swapping: a camera
+    that leaves and re-enters its first view, so blocks are parked on the host and merged back"""
+    w, h = 320, 240
+    o = ref.RefEngine(w, h, use_swapping=True)
+    a = adapter.AdapterEngine(w, h, intr=o.intr, use_swapping=True)
+    frames = list(range(0, 60, 2)) + list(range(58, -1, -2))   # the same inter-frame motion as the Layer B swapping test
+    for i, k in enumerate(frames):
+        depth = synth.render_depth(k, w, h)
+        o.process_frame(depth)
+        a.process_frame(depth)
+        rot, trans = parity.pose_diff(a.pose_M, o.pose_M)
+        assert rot <= 1e-4 and trans <= 1e-4, "frame %d (%d) pose differs: %g rad %g m" % (i, k, rot, trans)
+        if i == 0:   # identity pose on both sides: exact
+            assert [int(x) for x in a.counters[:3]] == [int(x) for x in o.counters]
+            assert parity.hash_equal(a.read(adapter.READ_HASH), o.hash_entries)
+    n_ref, n_adp = int(o.has_stored_data.sum()), a.stored_blocks
+    assert n_ref > 100, "the trajectory should swap blocks out (reference parked %d)" % n_ref
+    assert abs(n_adp - n_ref) <= 0.02 * n_ref + 2, "blocks parked on the host: adapter %d reference %d" % (n_adp, n_ref)
+    ca, co = a.counters, o.counters
+    assert abs(int(ca[1]) - int(co[1])) <= 0.02 * (o.n_local - co[1]) + 2
+    a.close(); o.close()

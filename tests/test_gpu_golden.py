@@ -68,3 +68,47 @@ def test_cuda_hd_2mm_teacher_forced_against_port():
     rows = [parity.compare_frame(o, eng, seq[k], k, strict=True) for k in range(2)]
     assert rows[0]["counters_ref"][0] > 30000
     eng.close(); o.close()
+
+
+def test_cuda_rows_8f_reproduce_golden_vectors():
+    """MeshScene, the free-view GetImage chain and ForwardRender against tests/golden/ref_rows8f_qqvga.npz (made from the real
+    reference by tests/golden/make_golden_8f.py).  Frame 0 is fused at the identity pose, so the scene is bit-identical to
+    the reference's and every vector is compared exactly."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_rows8f_qqvga.npz"))
+    W, H = int(g["W"]), int(g["H"])
+    seq = synth.sequence(1, W, H, noise=True)
+    assert golden_check.crc(seq[0]) == int(g["depth_crc"]), "synthetic generator no longer reproduces the golden input"
+    eng = ITMMainEngine(width=W, height=H)
+    eng.ProcessFrame(None, seq[0])
+    # ---- meshing
+    tri = eng.UpdateMesh()
+    assert len(tri) == int(g["mesh_n"])
+    assert np.array_equal(tri[:32], g["mesh_head"]) and np.array_equal(tri[-32:], g["mesh_tail"])
+    assert golden_check.crc(tri) == int(g["mesh_crc"]), "triangle array differs"
+    # ---- free-view rendering
+    for k in range(2):
+        img = eng.GetImage(int(g["free%d_type" % k]), g["free%d_pose" % k], g["free%d_intr" % k], W, H)
+        n = int(g["free%d_nvis" % k])
+        c = [int(x) for x in g["free%d_crc" % k]]
+        assert golden_check.crc(eng.read(capi.BUF_FREEVIEW_VISIBLE_IDS)[:n]) == c[0], "FindVisibleBlocks differs"
+        assert golden_check.crc(eng.read(capi.BUF_FREEVIEW_MINMAX)) == c[1], "free-view expected depths differ"
+        assert golden_check.crc(eng.read(capi.BUF_FREEVIEW_RAYCAST_RESULT)) == c[2], "free-view raycast differs"
+        d = np.abs(img[::5, ::7].astype(np.int32) - g["free%d_sample" % k].astype(np.int32)).max()
+        assert d <= 1, "free-view image differs by %d levels" % d
+        assert golden_check.crc(img) == c[3], "free-view image differs"
+    # ---- forward rendering at a pose a few millimetres away, without a new raycast
+    pose, pc, st = eng.get_state()
+    eng.set_state(g["fwd_pose"], pc, st)
+    eng.RunStage(capi.STAGE_EXPECTED_DEPTHS)
+    eng.RunStage(capi.STAGE_FORWARD_RENDER)
+    c = [int(x) for x in g["fwd_crc"]]
+    _, _, st = eng.get_state()
+    assert golden_check.crc(eng.read_image(capi.BUF_MINMAX, 2)) == c[3]
+    assert int(st[5]) == int(g["fwd_nmissing"])
+    assert golden_check.crc(np.sort(eng.read(capi.BUF_FWD_MISSING_POINTS)[:int(st[5])])) == c[1], "missing-point set differs"
+    fp = eng.read_image(capi.BUF_FORWARD_PROJECTION, 4)
+    assert int(np.count_nonzero(fp[..., 3] > 0)) == int(g["fwd_nvalid"])
+    assert golden_check.crc(fp) == c[0], "forward projection differs"
+    assert golden_check.crc(eng.read_image(capi.BUF_RAYCAST_IMAGE, 4)) == c[2], "forward-rendered image differs"
+    eng.close()
