@@ -118,6 +118,14 @@ def _dist_env():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
 
+def _omp_threads(n):
+    """OpenMP thread count of the already loaded runtime (the environment variable only counts when libgomp loads)"""
+    try:
+        C.CDLL("libgomp.so.1").omp_set_num_threads(int(n))
+    except OSError:
+        pass
+
+
 def run_reference(args):
     """CPU arm: the reference's own engines on the host cores (rank 0 only)."""
     rank, _, world = _dist_env()
@@ -132,11 +140,12 @@ def run_reference(args):
         kind, cores = "port", 1
     else:
         cores = os.cpu_count() or 1
-        os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+        os.environ["OMP_NUM_THREADS"] = str(cores)  # torchrun exports OMP_NUM_THREADS=1; libgomp reads it when the library loads
         eng = ref.RefEngine(W, H, flavour=flavour)
         kind = "reference"
         if flavour != "fast":
             cores = 1
+        _omp_threads(cores)
     n = args.warmup + args.steps
     frames = synth.sequence(n, W, H)
     for k in range(args.warmup):
@@ -177,8 +186,9 @@ def cpu_baseline_sample(seconds_budget=20.0):
             return None
     else:
         cores = (os.cpu_count() or 1) if flavour == "fast" else 1
-        os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+        os.environ["OMP_NUM_THREADS"] = str(cores)  # torchrun exports OMP_NUM_THREADS=1; libgomp reads it when the library loads
         eng, kind = ref.RefEngine(W, H, flavour=flavour), "reference"
+        _omp_threads(cores)
     warm, n = 3, 3
     frames = synth.sequence(64, W, H)
     for k in range(warm):
