@@ -246,6 +246,25 @@ int itm_b200_compute_g_and_h(itm_b200_ctx *ctx, const float *level_depth_dev, in
                              float dist_thresh, int iteration_type, float *f, float nabla[6], float hessian[36],
                              int *no_valid_points);
 
+/* ITMWeightedICPTracker::ComputeGandH (Engine/ITMWeightedICPTracker.h:58; CPU reference
+ * ITMWeightedICPTracker_CPU.cpp:14-85): the same evaluation with the per-pixel weight 0.0012 / sigma_z * 0.5 + 0.5 taken from
+ * level_weight_dev (the level of the weight hierarchy built from view->depthUncertainty).  ITMWeightedICPTracker's own host
+ * loop (Engine/ITMWeightedICPTracker.cpp:164-192, plain Gauss-Newton) runs on top of it unchanged. */
+int itm_b200_compute_g_and_h_weighted(itm_b200_ctx *ctx, const float *level_depth_dev, const float *level_weight_dev, int w, int h,
+                                      const float view_intrinsics[4], const float *points_map_dev, const float *normals_map_dev,
+                                      int scene_w, int scene_h, const float scene_intrinsics[4], const float approx_inv_pose[16],
+                                      const float scene_pose[16], float dist_thresh, int iteration_type, float *f, float nabla[6],
+                                      float hessian[36], int *no_valid_points);
+
+/* ITMViewBuilder::DepthFiltering (Engine/ITMViewBuilder.h:29; filterDepth, DeviceAgnostic/ITMViewBuilder.h:31-56): one pass of
+ * the 5x5 bilateral depth filter (settings.useBilateralFilter runs five, ITMViewBuilder_CPU.cpp:50-59).  Uses expf: results
+ * agree with the CPU reference to a few ulp, not bit for bit. */
+int itm_b200_depth_filtering(itm_b200_ctx *ctx, float *out_dev, const float *in_dev, int w, int h);
+/* ITMViewBuilder::ComputeNormalAndWeights (Engine/ITMViewBuilder.h:30; computeNormalAndWeight :59-114): view->depthNormal
+ * (Vector4f) and view->depthUncertainty (sigma_z) of settings.modelSensorNoise.  Interior pixels only, like the reference. */
+int itm_b200_compute_normal_and_weights(itm_b200_ctx *ctx, float *normal_out_dev, float *sigma_z_out_dev, const float *depth_dev, int w,
+                                        int h, const float intrinsics[4]);
+
 /* ITMTracker::TrackCamera (Engine/ITMTracker.h:26) for the depth ICP tracker: builds the depth
  * pyramid from depth_dev and runs the whole Levenberg-Marquardt loop on the device; ts->pose_d
  * is updated.  The map/pose fields of *ts are the tracker's inputs. */

@@ -17,6 +17,8 @@
 //       (ITMLib/Engine/ITMMeshingEngine.h:15-30)
 //   ITMDepthTracker (TrackCamera + ComputeGandH)                       -> ITMDepthTracker_B200
 //       (ITMLib/Engine/ITMDepthTracker.h:24-66)
+//   ITMWeightedICPTracker (ComputeGandH under the reference's own loop) -> ITMWeightedICPTracker_B200
+//       (ITMLib/Engine/ITMWeightedICPTracker.h:23-68)
 //   ITMLowLevelEngine::FilterSubsampleWithHoles(float)                 -> ITMLowLevelEngine_B200
 //       (ITMLib/Engine/ITMLowLevelEngine.h:16-34)
 //   ITMViewBuilder::UpdateView / ConvertDepthAffineToFloat             -> ITMViewBuilder_B200
@@ -41,6 +43,7 @@
 #include "ITMLib/Engine/ITMSceneReconstructionEngine.h"
 #include "ITMLib/Engine/ITMSwappingEngine.h"
 #include "ITMLib/Engine/ITMViewBuilder.h"
+#include "ITMLib/Engine/ITMWeightedICPTracker.h"
 #include "ITMLib/Engine/ITMVisualisationEngine.h"
 #include "ITMLib/Objects/ITMRenderState_VH.h"
 #include "ITMLib/Utils/ITMLibSettings.h"
@@ -398,24 +401,51 @@ class ITMViewBuilder_B200 : public ITMViewBuilder {
                    "ConvertDepthAffineToFloat");
   }
 
+  void DepthFiltering(ITMFloatImage *image_out, const ITMFloatImage *image_in) {
+    itm_b200_check(itm_b200_depth_filtering(c->ctx, image_out->GetData(MEMORYDEVICE_CUDA), image_in->GetData(MEMORYDEVICE_CUDA), image_in->noDims.x,
+                                            image_in->noDims.y),
+                   "DepthFiltering");
+  }
+
+  void ComputeNormalAndWeights(ITMFloat4Image *normal_out, ITMFloatImage *sigmaZ_out, const ITMFloatImage *depth_in, Vector4f intrinsic) {
+    const float intr[4] = {intrinsic.x, intrinsic.y, intrinsic.z, intrinsic.w};
+    itm_b200_check(itm_b200_compute_normal_and_weights(c->ctx, (float *)normal_out->GetData(MEMORYDEVICE_CUDA), sigmaZ_out->GetData(MEMORYDEVICE_CUDA),
+                                                       depth_in->GetData(MEMORYDEVICE_CUDA), depth_in->noDims.x, depth_in->noDims.y, intr),
+                   "ComputeNormalAndWeights");
+  }
+
   // same sequence as ITMViewBuilder_CPU::UpdateView (ITMViewBuilder_CPU.cpp:14-64) with the images in HBM
   void UpdateView(ITMView **view_ptr, ITMUChar4Image *rgbImage, ITMShortImage *rawDepthImage, bool useBilateralFilter, bool modelSensorNoise = false) {
-    if (useBilateralFilter || modelSensorNoise) DIEWITHEXCEPTION("libitm_b200: bilateral filter / sensor-noise model not provided");
     if (*view_ptr == NULL) {
       *view_ptr = new ITMView(calib, rgbImage->noDims, rawDepthImage->noDims, true);
       if (this->shortImage != NULL) delete this->shortImage;
       this->shortImage = new ITMShortImage(rawDepthImage->noDims, true, true);
+      if (this->floatImage != NULL) delete this->floatImage;
+      this->floatImage = new ITMFloatImage(rawDepthImage->noDims, true, true);
+      if (modelSensorNoise) {
+        (*view_ptr)->depthNormal = new ITMFloat4Image(rawDepthImage->noDims, true, true);
+        (*view_ptr)->depthUncertainty = new ITMFloatImage(rawDepthImage->noDims, true, true);
+      }
     }
     ITMView *view = *view_ptr;
     view->rgb->SetFrom(rgbImage, ORUtils::MemoryBlock<Vector4u>::CPU_TO_CUDA);
     this->shortImage->SetFrom(rawDepthImage, ORUtils::MemoryBlock<short>::CPU_TO_CUDA);
     if (view->calib->disparityCalib.type != ITMDisparityCalib::TRAFO_AFFINE) DIEWITHEXCEPTION("libitm_b200: only TRAFO_AFFINE depth is provided");
     this->ConvertDepthAffineToFloat(view->depth, this->shortImage, view->calib->disparityCalib.params);
+    if (useBilateralFilter) {
+      // 5 steps of bilateral filtering
+      this->DepthFiltering(this->floatImage, view->depth);
+      this->DepthFiltering(view->depth, this->floatImage);
+      this->DepthFiltering(this->floatImage, view->depth);
+      this->DepthFiltering(view->depth, this->floatImage);
+      this->DepthFiltering(this->floatImage, view->depth);
+      view->depth->SetFrom(this->floatImage, ORUtils::MemoryBlock<float>::CUDA_TO_CUDA);
+    }
+    if (modelSensorNoise)
+      this->ComputeNormalAndWeights(view->depthNormal, view->depthUncertainty, view->depth, view->calib->intrinsics_d.projectionParamsSimple.all);
   }
 
   void ConvertDisparityToDepth(ITMFloatImage *, const ITMShortImage *, const ITMIntrinsics *, Vector2f) { DIEWITHEXCEPTION("libitm_b200: ConvertDisparityToDepth not provided"); }
-  void DepthFiltering(ITMFloatImage *, const ITMFloatImage *) { DIEWITHEXCEPTION("libitm_b200: DepthFiltering not provided"); }
-  void ComputeNormalAndWeights(ITMFloat4Image *, ITMFloatImage *, const ITMFloatImage *, Vector4f) { DIEWITHEXCEPTION("libitm_b200: ComputeNormalAndWeights not provided"); }
   void UpdateView(ITMView **, ITMUChar4Image *, ITMFloatImage *) { DIEWITHEXCEPTION("libitm_b200: UpdateView(float depth) not provided"); }
   void UpdateView(ITMView **, ITMUChar4Image *, ITMShortImage *, bool, ITMIMUMeasurement *) { DIEWITHEXCEPTION("libitm_b200: UpdateView(imu) not provided"); }
 };
@@ -461,6 +491,38 @@ class ITMDepthTracker_B200 : public ITMDepthTracker {
                                             &noValid),
                    "ComputeGandH");
     // stride 6 for 3- and 6-parameter iterations alike (ITMDepthTracker_CPU.cpp:72-73)
+    for (int i = 0; i < 36; ++i) hessian[i] = h36[i];
+    return noValid;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+/// ITMWeightedICPTracker (TRACKER_WICP): the reference's own Gauss-Newton loop, pyramid and weight pyramid
+/// (ITMWeightedICPTracker.cpp:58-192, over ITMLowLevelEngine_B200::FilterSubsampleWithHoles) with every evaluation on the device.
+class ITMWeightedICPTracker_B200 : public ITMWeightedICPTracker {
+  ITMB200Context *c;
+
+ public:
+  ITMWeightedICPTracker_B200(Vector2i imgSize, TrackerIterationType *trackingRegime, int noHierarchyLevels, int noICPRunTillLevel, float distThresh,
+                             float terminationThreshold, const ITMLowLevelEngine *lowLevelEngine, ITMB200Context *context)
+      : ITMWeightedICPTracker(imgSize, trackingRegime, noHierarchyLevels, noICPRunTillLevel, distThresh, terminationThreshold, lowLevelEngine,
+                              MEMORYDEVICE_CUDA),
+        c(context) {}
+
+ protected:
+  int ComputeGandH(float &f, float *nabla, float *hessian, Matrix4f approxInvPose) {
+    const Vector4f &vk = viewHierarchyLevel->intrinsics, &sk = sceneHierarchyLevel->intrinsics;
+    const float viewIntr[4] = {vk.x, vk.y, vk.z, vk.w}, sceneIntr[4] = {sk.x, sk.y, sk.z, sk.w};
+    const Vector2i viewSize = viewHierarchyLevel->depth->noDims, sceneSize = sceneHierarchyLevel->pointsMap->noDims;
+    int noValid = 0;
+    float h36[36];
+    itm_b200_check(itm_b200_compute_g_and_h_weighted(c->ctx, viewHierarchyLevel->depth->GetData(MEMORYDEVICE_CUDA),
+                                                     weightHierarchyLevel->depth->GetData(MEMORYDEVICE_CUDA), viewSize.x, viewSize.y, viewIntr,
+                                                     (const float *)sceneHierarchyLevel->pointsMap->GetData(MEMORYDEVICE_CUDA),
+                                                     (const float *)sceneHierarchyLevel->normalsMap->GetData(MEMORYDEVICE_CUDA), sceneSize.x,
+                                                     sceneSize.y, sceneIntr, approxInvPose.m, scenePose.m, distThresh[levelId], (int)iterationType,
+                                                     &f, nabla, h36, &noValid),
+                   "ComputeGandH (weighted)");
     for (int i = 0; i < 36; ++i) hessian[i] = h36[i];
     return noValid;
   }

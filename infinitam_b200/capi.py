@@ -111,7 +111,7 @@ SYMBOLS = [
     "itm_b200_forward_render", "itm_b200_find_visible_blocks", "itm_b200_find_surface", "itm_b200_render_image",
     "itm_b200_engine_get_image", "itm_b200_mesh_scene", "itm_b200_write_stl", "itm_b200_write_obj",
     "itm_b200_engine_mesh_scene", "itm_b200_engine_save_scene_to_mesh",
-    "itm_b200_take_cuda_error", "itm_b200_swap_in_select", "itm_b200_swap_in_apply", "itm_b200_swap_out",
+    "itm_b200_take_cuda_error", "itm_b200_compute_g_and_h_weighted", "itm_b200_depth_filtering", "itm_b200_compute_normal_and_weights", "itm_b200_swap_in_select", "itm_b200_swap_in_apply", "itm_b200_swap_out",
 ]
 
 _lib = None
@@ -163,6 +163,10 @@ def load():
     lib.itm_b200_filter_subsample_with_holes.argtypes = [vp, vp, vp, C.c_int, C.c_int]
     lib.itm_b200_compute_g_and_h.argtypes = [vp, vp, C.c_int, C.c_int, f32p, vp, vp, C.c_int, C.c_int, f32p, f32p, f32p,
                                              C.c_float, C.c_int, f32p, f32p, f32p, i32p]
+    lib.itm_b200_compute_g_and_h_weighted.argtypes = [vp, vp, vp, C.c_int, C.c_int, f32p, vp, vp, C.c_int, C.c_int, f32p, f32p, f32p,
+                                                      C.c_float, C.c_int, f32p, f32p, f32p, i32p]
+    lib.itm_b200_depth_filtering.argtypes = [vp, vp, vp, C.c_int, C.c_int]
+    lib.itm_b200_compute_normal_and_weights.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, f32p]
     lib.itm_b200_track_camera.argtypes = [vp, vp, C.POINTER(TrackingState)]
     lib.itm_b200_engine_create.argtypes = [C.POINTER(Params), C.POINTER(vp)]
     lib.itm_b200_engine_create_sharded.argtypes = [C.POINTER(Params), C.POINTER(Shard), C.POINTER(vp)]

@@ -288,6 +288,7 @@ ViewParams rs_view(const itm_b200_ctx *c, const itm_b200_render_state *rs, const
 IcpLevelArgs make_level_args(const itm_b200_ctx *c, int l, const float *depth) {
   const LevelCfg &L = c->levels[l];
   IcpLevelArgs lv;
+  lv.weight = nullptr;
   lv.depth = depth;
   lv.w = L.w; lv.h = L.h;
   lv.fx = L.fx; lv.fy = L.fy; lv.cx = L.cx; lv.cy = L.cy;
@@ -776,7 +777,7 @@ int itm_b200_filter_subsample_with_holes(itm_b200_ctx *c, float *out_dev, const 
   return ITM_B200_OK;
 }
 
-int itm_b200_compute_g_and_h(itm_b200_ctx *c, const float *level_depth_dev, int w, int h, const float view_intrinsics[4],
+static int compute_g_and_h_common(itm_b200_ctx *c, const float *level_weight_dev, const float *level_depth_dev, int w, int h, const float view_intrinsics[4],
                              const float *points_map_dev, const float *normals_map_dev, int scene_w, int scene_h,
                              const float scene_intrinsics[4], const float approx_inv_pose[16], const float scene_pose[16], float dist_thresh,
                              int iteration_type, float *f, float nabla[6], float hessian[36], int *no_valid_points) {
@@ -799,6 +800,7 @@ int itm_b200_compute_g_and_h(itm_b200_ctx *c, const float *level_depth_dev, int 
   a.ctaCounter = c->icpCounter;
   a.terminationThreshold = c->p.depth_tracker_termination_threshold;
   IcpLevelArgs lv;
+  lv.weight = level_weight_dev;
   lv.depth = level_depth_dev;
   lv.w = w; lv.h = h;
   lv.fx = view_intrinsics[0]; lv.fy = view_intrinsics[1]; lv.cx = view_intrinsics[2]; lv.cy = view_intrinsics[3];
@@ -814,6 +816,43 @@ int itm_b200_compute_g_and_h(itm_b200_ctx *c, const float *level_depth_dev, int 
   if (f) *f = out[1];
   if (nabla) memcpy(nabla, out + 2, 6 * sizeof(float));
   if (hessian) memcpy(hessian, out + 8, 36 * sizeof(float));
+  return ITM_B200_OK;
+}
+
+int itm_b200_compute_g_and_h(itm_b200_ctx *c, const float *level_depth_dev, int w, int h, const float view_intrinsics[4],
+                             const float *points_map_dev, const float *normals_map_dev, int scene_w, int scene_h,
+                             const float scene_intrinsics[4], const float approx_inv_pose[16], const float scene_pose[16], float dist_thresh,
+                             int iteration_type, float *f, float nabla[6], float hessian[36], int *no_valid_points) {
+  return compute_g_and_h_common(c, nullptr, level_depth_dev, w, h, view_intrinsics, points_map_dev, normals_map_dev, scene_w, scene_h,
+                                scene_intrinsics, approx_inv_pose, scene_pose, dist_thresh, iteration_type, f, nabla, hessian, no_valid_points);
+}
+
+int itm_b200_compute_g_and_h_weighted(itm_b200_ctx *c, const float *level_depth_dev, const float *level_weight_dev, int w, int h,
+                                      const float view_intrinsics[4], const float *points_map_dev, const float *normals_map_dev, int scene_w,
+                                      int scene_h, const float scene_intrinsics[4], const float approx_inv_pose[16],
+                                      const float scene_pose[16], float dist_thresh, int iteration_type, float *f, float nabla[6],
+                                      float hessian[36], int *no_valid_points) {
+  if (!level_weight_dev) return fail(ITM_B200_EINVAL, "NULL argument");
+  return compute_g_and_h_common(c, level_weight_dev, level_depth_dev, w, h, view_intrinsics, points_map_dev, normals_map_dev, scene_w, scene_h,
+                                scene_intrinsics, approx_inv_pose, scene_pose, dist_thresh, iteration_type, f, nabla, hessian, no_valid_points);
+}
+
+int itm_b200_depth_filtering(itm_b200_ctx *c, float *out_dev, const float *in_dev, int w, int h) {
+  if (!c || !out_dev || !in_dev) return fail(ITM_B200_EINVAL, "NULL argument");
+  launch_filter_depth(out_dev, in_dev, w, h, c->stream);
+  g_launches += 1;
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  return ITM_B200_OK;
+}
+
+int itm_b200_compute_normal_and_weights(itm_b200_ctx *c, float *normal_out_dev, float *sigma_z_out_dev, const float *depth_dev, int w, int h,
+                                        const float intrinsics[4]) {
+  if (!c || !normal_out_dev || !sigma_z_out_dev || !depth_dev || !intrinsics) return fail(ITM_B200_EINVAL, "NULL argument");
+  launch_normal_weight(normal_out_dev, sigma_z_out_dev, depth_dev, w, h, intrinsics, c->stream);
+  g_launches += 1;
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
   return ITM_B200_OK;
 }
 

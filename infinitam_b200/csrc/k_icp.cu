@@ -65,10 +65,12 @@ struct IcpConsts {
   float scenePose[16];
 };
 
-template <bool shortIteration, bool rotationOnly>
+// weighted: computePerPointGH_wICP (ITMLib/Engine/DeviceAgnostic/ITMWeightedICPTracker.h:9-105) - the interpolated normal is
+// scaled by localWeight AFTER b has been taken with the unscaled one
+template <bool shortIteration, bool rotationOnly, bool weighted = false>
 __device__ __forceinline__ bool per_point_Ab(float *A, float &b, int x, int y, float depth, const IcpLevelArgs &lv, const ViewParams &sv,
                                              const IcpConsts &c, const float4 *__restrict__ pointsMap,
-                                             const float4 *__restrict__ normalsMap) {
+                                             const float4 *__restrict__ normalsMap, float localWeight = 1.0f) {
   if (depth <= 1e-8f) return false;
   float tx = depth * (((float)x - lv.cx) / lv.fx);
   float ty = depth * (((float)y - lv.cy) / lv.fy);
@@ -92,6 +94,7 @@ __device__ __forceinline__ bool per_point_Ab(float *A, float &b, int x, int y, f
   float nx, ny, nz, nw;
   bilinear_holes(normalsMap, u, v, sv.W, nx, ny, nz, nw);
   b = nx * dx + ny * dy + nz * dz;
+  if (weighted) { nx *= localWeight; ny *= localWeight; nz *= localWeight; }
   if (shortIteration) {
     if (rotationOnly) {
       A[0] = +wz * ny - wy * nz;
@@ -111,7 +114,7 @@ __device__ __forceinline__ bool per_point_Ab(float *A, float &b, int x, int y, f
 
 // Sums this CTA's share of one evaluation and writes it to partialOut[0..NV).  All threads take part.
 // Layout of a partial: [n, sum b^2, nabla(noPara), hessian lower triangle(noParaSQ)].
-template <bool shortIteration, bool rotationOnly>
+template <bool shortIteration, bool rotationOnly, bool weighted = false>
 __device__ __forceinline__ void eval_to_partial(const IcpLevelArgs &lv, const ViewParams &sv, const IcpConsts &c,
                                                 const float4 *__restrict__ pointsMap, const float4 *__restrict__ normalsMap,
                                                 double (*sPart)[ICP_NVALS], double *__restrict__ partialOut, int nCtas) {
@@ -125,9 +128,15 @@ __device__ __forceinline__ void eval_to_partial(const IcpLevelArgs &lv, const Vi
   for (int i = blockIdx.x * ICP_THREADS + threadIdx.x; i < n; i += nCtas * ICP_THREADS) {
     const int y = i / lv.w, x = i - y * lv.w;
     float A[noPara], b;
-    if (per_point_Ab<shortIteration, rotationOnly>(A, b, x, y, __ldg(lv.depth + i), lv, sv, c, pointsMap, normalsMap)) {
+    float localWeight = 1.0f;
+    if (weighted) {
+      // ITMWeightedICPTracker_CPU.cpp:46: minSigmaZ / sigma_z * 0.5 + 0.5, minSigmaZ = 0.0012
+      const float sz = __ldg(lv.weight + i);
+      localWeight = sz > 0 ? 0.0012f / sz * 0.5f + 0.5f : 0.0f;
+    }
+    if (per_point_Ab<shortIteration, rotationOnly, weighted>(A, b, x, y, __ldg(lv.depth + i), lv, sv, c, pointsMap, normalsMap, localWeight)) {
       acc[0] += 1.0f;
-      acc[1] += b * b;
+      acc[1] += weighted ? b * b * localWeight * localWeight : b * b;
 #pragma unroll
       for (int r = 0, counter = 0; r < noPara; r++) {
         acc[2 + r] += b * A[r];
@@ -659,7 +668,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_CTAS_PER_SM) k_icp_track(Trac
 }
 
 // Stand-alone evaluation at poseIn (16 floats, device): leaves ComputeGandH's results in out44.
-template <bool shortIteration, bool rotationOnly>
+template <bool shortIteration, bool rotationOnly, bool weighted = false>
 __global__ void __launch_bounds__(ICP_THREADS) k_icp_eval_single(IcpArgs a, IcpLevelArgs lv, float *__restrict__ out44,
                                                                  const float *__restrict__ poseIn) {
   constexpr int noPara = shortIteration ? 3 : 6;
@@ -670,7 +679,7 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_eval_single(IcpArgs a, IcpL
   if (threadIdx.x < 16) c.approxInvPose[threadIdx.x] = poseIn[threadIdx.x];
   if (threadIdx.x >= 32 && threadIdx.x < 48) c.scenePose[threadIdx.x - 32] = a.st->scenePose[threadIdx.x - 32];
   __syncthreads();
-  eval_to_partial<shortIteration, rotationOnly>(lv, a.sceneVp, c, reinterpret_cast<const float4 *>(a.pointsMap),
+  eval_to_partial<shortIteration, rotationOnly, weighted>(lv, a.sceneVp, c, reinterpret_cast<const float4 *>(a.pointsMap),
                                                 reinterpret_cast<const float4 *>(a.normalsMap), sPart,
                                                 a.partials + (size_t)blockIdx.x * ICP_NVALS, gridDim.x);
   __threadfence();
@@ -766,6 +775,15 @@ void launch_icp_eval_single(const IcpArgs &a, const IcpLevelArgs &lv, float *out
   int ctas = (n + ICP_THREADS - 1) / ICP_THREADS;
   if (ctas > icp_max_ctas()) ctas = icp_max_ctas();
   if (ctas < 1) ctas = 1;
+  if (lv.weight) {
+    switch (lv.iterationType) {
+      case ITM_ITER_ROTATION: k_icp_eval_single<true, true, true><<<ctas, ICP_THREADS, 0, s>>>(a, lv, out44, poseIn); break;
+      case ITM_ITER_TRANSLATION: k_icp_eval_single<true, false, true><<<ctas, ICP_THREADS, 0, s>>>(a, lv, out44, poseIn); break;
+      case ITM_ITER_BOTH: k_icp_eval_single<false, false, true><<<ctas, ICP_THREADS, 0, s>>>(a, lv, out44, poseIn); break;
+      default: break;
+    }
+    return;
+  }
   switch (lv.iterationType) {
     case ITM_ITER_ROTATION:
       k_icp_eval_single<true, true><<<ctas, ICP_THREADS, 0, s>>>(a, lv, out44, poseIn);

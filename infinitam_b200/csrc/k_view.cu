@@ -136,9 +136,91 @@ __global__ void k_subsample_holes(float *__restrict__ out, const float *__restri
   out[x + y * wOut] = subsample4(__ldg(p), __ldg(p + 1), __ldg(p + wIn), __ldg(p + wIn + 1));
 }
 
+// filterDepth (ITMLib/Engine/DeviceAgnostic/ITMViewBuilder.h:31-56): 5x5 bilateral filter with the Kinect noise model as range
+// sigma; interior pixels only, the 2-pixel border stays 0 (DepthFiltering clears the output first, ITMViewBuilder_CPU.cpp:116-128)
+#define ITM_MEAN_SIGMA_L 1.2232f
+__global__ void __launch_bounds__(256) k_filter_depth(float *__restrict__ out, const float *__restrict__ in, int W, int H) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= W || y >= H) return;
+  if (x < 2 || y < 2 || x >= W - 2 || y >= H - 2) {
+    out[x + y * W] = 0.0f;
+    return;
+  }
+  const float z = __ldg(in + x + y * W);
+  if (z < 0.0f) {
+    out[x + y * W] = -1.0f;
+    return;
+  }
+  const float sigma_z = 1.0f / (0.0012f + 0.0019f * (z - 0.4f) * (z - 0.4f) + 0.0001f / sqrtf(z) * 0.25f);
+  float final_depth = 0.0f, w_sum = 0.0f;
+#pragma unroll
+  for (int i = -2; i <= 2; i++) {
+#pragma unroll
+    for (int j = -2; j <= 2; j++) {
+      const float tmpz = __ldg(in + (x + j) + (y + i) * W);
+      if (tmpz < 0.0f) continue;
+      float dz = (tmpz - z);
+      dz *= dz;
+      const float w = expf(-0.5f * ((float)(abs(i) + abs(j)) * ITM_MEAN_SIGMA_L * ITM_MEAN_SIGMA_L + dz * sigma_z * sigma_z));
+      w_sum += w;
+      final_depth += w * tmpz;
+    }
+  }
+  out[x + y * W] = final_depth / w_sum;
+}
+
+// computeNormalAndWeight (ITMViewBuilder.h:59-114): normal from the 4-neighbourhood of the unprojected depth and the
+// depth uncertainty sigma_z of the Kinect noise model; interior pixels only (ComputeNormalAndWeights, ..._CPU.cpp:130-143),
+// everything else keeps its previous content
+__global__ void __launch_bounds__(256) k_normal_weight(float4 *__restrict__ normalOut, float *__restrict__ sigmaOut,
+                                                       const float *__restrict__ depth, int W, int H, float4 intr) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x < 2 || y < 2 || x >= W - 2 || y >= H - 2) return;
+  const int idx = x + y * W;
+  const float z = __ldg(depth + idx);
+  const float zxp = __ldg(depth + idx + 1), zyp = __ldg(depth + idx + W), zxm = __ldg(depth + idx - 1), zym = __ldg(depth + idx - W);
+  if (z < 0.0f || zxp <= 0 || zyp <= 0 || zxm <= 0 || zym <= 0) {
+    normalOut[idx].w = -1.0f;
+    sigmaOut[idx] = -1.0f;
+    return;
+  }
+  // "unprojected" exactly as the reference writes it: z * (u - c) * f (it multiplies by the focal length)
+  const float fx = (float)x, fy = (float)y;
+  const float xp1x = zxp * ((fx + 1.0f) - intr.z) * intr.x, xp1y = zxp * (fy - intr.w) * intr.y;
+  const float xm1x = zxm * ((fx - 1.0f) - intr.z) * intr.x, xm1y = zxm * (fy - intr.w) * intr.y;
+  const float yp1x = zyp * (fx - intr.z) * intr.x, yp1y = zyp * ((fy + 1.0f) - intr.w) * intr.y;
+  const float ym1x = zym * (fx - intr.z) * intr.x, ym1y = zym * ((fy - 1.0f) - intr.w) * intr.y;
+  const float dxx = xp1x - xm1x, dxy = xp1y - xm1y, dxz = zxp - zxm;
+  const float dyx = yp1x - ym1x, dyy = yp1y - ym1y, dyz = zyp - zym;
+  float nx = (dxy * dyz - dxz * dyy);
+  float ny = (dxz * dyx - dxx * dyz);
+  float nz = (dxx * dyy - dxy * dyx);
+  if (nx == 0.0f && ny == 0 && nz == 0) {
+    normalOut[idx].w = -1.0f;
+    sigmaOut[idx] = -1.0f;
+    return;
+  }
+  const float norm = 1.0f / sqrtf(nx * nx + ny * ny + nz * nz);
+  nx *= norm; ny *= norm; nz *= norm;
+  normalOut[idx] = make_float4(nx, ny, nz, 1.0f);
+  const float theta = acosf(nz);
+  const float theta_diff = theta / (3.1415926535897932384626433832795f * 0.5f - theta);
+  sigmaOut[idx] = (0.0012f + 0.0019f * (z - 0.4f) * (z - 0.4f) + 0.0001f / sqrtf(z) * theta_diff * theta_diff);
+}
+
 }  // namespace
 
 namespace itm {
+
+void launch_filter_depth(float *out, const float *in, int W, int H, cudaStream_t s) {
+  dim3 g((W + 31) / 32, (H + 7) / 8);
+  k_filter_depth<<<g, 256, 0, s>>>(out, in, W, H);
+}
+
+void launch_normal_weight(float *normalOut, float *sigmaOut, const float *depth, int W, int H, const float intr[4], cudaStream_t s) {
+  dim3 g((W + 31) / 32, (H + 7) / 8);
+  k_normal_weight<<<g, 256, 0, s>>>(reinterpret_cast<float4 *>(normalOut), sigmaOut, depth, W, H, make_float4(intr[0], intr[1], intr[2], intr[3]));
+}
 
 void launch_convert_depth(const short *raw, float *out, int n, float a, float b, cudaStream_t s) {
   k_convert_only<<<(n + 255) / 256, 256, 0, s>>>(raw, out, n, a, b);

@@ -75,6 +75,7 @@ struct RenderArgs {
 };
 
 struct IcpLevelArgs {
+  const float *weight;    // weighted ICP only: the level's depth-uncertainty image (weightHierarchy), else NULL
   const float *depth;     // level depth image
   int w, h;
   float fx, fy, cx, cy;   // level intrinsics
@@ -138,6 +139,9 @@ void launch_render_image(const RenderArgs &a, unsigned char *outImage, int type,
 
 void launch_convert_depth(const short *raw, float *out, int n, float a, float b, cudaStream_t s);
 void launch_subsample_holes(float *out, const float *in, int wIn, int hIn, cudaStream_t s);
+// ITMViewBuilder::DepthFiltering / ComputeNormalAndWeights (useBilateralFilter / modelSensorNoise)
+void launch_filter_depth(float *out, const float *in, int W, int H, cudaStream_t s);
+void launch_normal_weight(float *normalOut, float *sigmaOut, const float *depth, int W, int H, const float intr[4], cudaStream_t s);
 // Pose-independent first steps of AllocateSceneFromDepth (mark last frame's visible entries, snapshot the free-list
 // heads) and of CreateExpectedDepths (min/max image initialisation); when given to launch_view_pyramid they are done
 // by the view kernel and the allocate / expected-depth launches skip them (AllocArgs::prologueDone, RenderArgs::minmaxReady).
@@ -163,6 +167,7 @@ __device__ __forceinline__ void icp_bump_epoch(unsigned *epochDev) { *epochDev =
 size_t icp_rows_bytes();
 size_t icp_bcast_bytes();
 // One stand-alone evaluation at poseIn (16 floats, device); [n, f, nabla6, hessian36] left in out44 (device).
+// lv.weight != NULL: ITMWeightedICPTracker's evaluation (per-pixel weight from the depth uncertainty)
 void launch_icp_eval_single(const IcpArgs &a, const IcpLevelArgs &lv, float *out44, const float *poseIn, cudaStream_t s);
 // ITMSwappingEngine (ITMLib/Engine/DeviceSpecific/CPU/ITMSwappingEngine_CPU.cpp); SDF_TRANSFER_BLOCK_NUM = 0x1000
 #define ITM_TRANSFER_BLOCK_NUM 0x1000

@@ -15,9 +15,11 @@ from .ref import HASH_ENTRY_DTYPE
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "_ref", "libitm_adapter.so")
 
-(READ_HASH, READ_VOXELS, READ_VISIBLE_IDS, READ_RAYCAST, READ_POINTS, READ_NORMALS, READ_VISIBLE_TYPES, READ_RAYCAST_IMAGE) = range(8)
+(READ_HASH, READ_VOXELS, READ_VISIBLE_IDS, READ_RAYCAST, READ_POINTS, READ_NORMALS, READ_VISIBLE_TYPES, READ_RAYCAST_IMAGE,
+ READ_DEPTH, READ_DEPTH_UNCERTAINTY, READ_DEPTH_NORMAL) = range(11)
 _DTYPES = {READ_HASH: HASH_ENTRY_DTYPE, READ_VOXELS: np.uint32, READ_VISIBLE_IDS: np.int32, READ_RAYCAST: np.float32,
-           READ_POINTS: np.float32, READ_NORMALS: np.float32, READ_VISIBLE_TYPES: np.uint8, READ_RAYCAST_IMAGE: np.uint8}
+           READ_POINTS: np.float32, READ_NORMALS: np.float32, READ_VISIBLE_TYPES: np.uint8, READ_RAYCAST_IMAGE: np.uint8,
+           READ_DEPTH: np.float32, READ_DEPTH_UNCERTAINTY: np.float32, READ_DEPTH_NORMAL: np.float32}
 
 
 def available() -> bool:
@@ -28,8 +30,11 @@ class AdapterEngine:
     """ITMMainEngine::ProcessFrame composed from reference host objects + the B200 adapter engines."""
 
     def __init__(self, w, h, intr=None, voxel_size=0.005, mu=0.02, max_w=100, vf_min=0.35, vf_max=3.0, device_loop=True,
-                 use_swapping=False):
+                 use_swapping=False, wicp=False, bilateral=False):
         lib = C.CDLL(LIB)
+        lib.adp_set_tracker_wicp.argtypes = [C.c_int, C.c_int]
+        lib.adp_update_view.argtypes = [C.c_void_p, C.c_void_p]
+        lib.adp_wicp_gandh.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         lib.adp_set_use_swapping.argtypes = [C.c_int]
         lib.adp_count_stored.argtypes = [C.c_void_p]
         lib.adp_create.restype = C.c_void_p
@@ -48,8 +53,10 @@ class AdapterEngine:
         s = w / 640.0
         fx, fy, cx, cy = intr if intr is not None else (580.0 * s, 580.0 * s, w / 2.0, h / 2.0)
         lib.adp_set_use_swapping(int(use_swapping))
+        lib.adp_set_tracker_wicp(int(wicp), int(bilateral))
         self.h = lib.adp_create(w, h, fx, fy, cx, cy, voxel_size, mu, max_w, vf_min, vf_max, int(device_loop))
         lib.adp_set_use_swapping(0)
+        lib.adp_set_tracker_wicp(0, 0)
         if not self.h:
             raise RuntimeError("adp_create failed: %s" % lib.adp_last_error().decode())
 
@@ -65,6 +72,19 @@ class AdapterEngine:
 
     def set_use_approximate_raycast(self, on=True):
         self.lib.adp_set_use_approximate_raycast(self.h, int(on))
+
+    def update_view(self, depth_i16):
+        d = np.ascontiguousarray(depth_i16, np.int16)
+        if self.lib.adp_update_view(self.h, d.ctypes.data) != 0:
+            raise RuntimeError("adp_update_view: %s" % self.lib.adp_last_error().decode())
+
+    def wicp_gandh(self, level, approx_inv_pose16):
+        inv = np.ascontiguousarray(approx_inv_pose16, np.float32).reshape(16)
+        out = np.zeros(44, np.float32)
+        n = self.lib.adp_wicp_gandh(self.h, level, inv.ctypes.data, out.ctypes.data)
+        if n < 0:
+            raise RuntimeError("adp_wicp_gandh: %s" % self.lib.adp_last_error().decode())
+        return n, out
 
     @property
     def stored_blocks(self):

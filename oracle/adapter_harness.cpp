@@ -17,8 +17,14 @@
 
 #include <cuda_runtime.h>
 
+// single evaluations of the weighted tracker are driven from outside (SetEvaluationData & co. are private): open the
+// classes up, the layout is unchanged
+#define private public
+#define protected public
 #include "ITMLib/Engine/ITMTrackingController.h"
 #include "itm_b200_adapter.hpp"
+#undef private
+#undef protected
 
 using namespace ITMLib::Engine;
 using namespace ITMLib::Objects;
@@ -37,6 +43,7 @@ struct adp_engine {
   ITMSceneReconstructionEngine_B200<TV, TI> *reco;
   ITMSwappingEngine_B200<TV, TI> *swapper;  // NULL unless created after adp_set_use_swapping(1)
   ITMDepthTracker_B200 *tracker;
+  ITMWeightedICPTracker_B200 *wtracker;  // instead of tracker when created after adp_set_tracker_wicp(1, ..)
   ITMTrackingController *controller;
   ITMTrackingState *trackingState;
   ITMRenderState *renderState;
@@ -52,12 +59,15 @@ struct adp_engine {
 
 static std::string g_err;
 static int g_nextUseSwapping = 0;
+static int g_nextWicp = 0, g_nextBilateral = 0;
 
 extern "C" {
 
 const char *adp_last_error() { return g_err.c_str(); }
 // settings.useSwapping of the engines created from now on (ITMDenseMapper.cpp:16-34, 59-64)
 void adp_set_use_swapping(int on) { g_nextUseSwapping = on; }
+// TRACKER_WICP (+ settings.modelSensorNoise) and settings.useBilateralFilter of the engines created from now on
+void adp_set_tracker_wicp(int on, int bilateral) { g_nextWicp = on; g_nextBilateral = bilateral; }
 
 adp_engine *adp_create(int W, int H, float fx, float fy, float cx, float cy, float voxelSize, float mu, int maxW, float vfMin, float vfMax,
                        int deviceLoop) {
@@ -68,8 +78,9 @@ adp_engine *adp_create(int W, int H, float fx, float fy, float cx, float cy, flo
     e->settings->trackerType = ITMLibSettings::TRACKER_ICP;
     e->settings->useSwapping = g_nextUseSwapping != 0;
     e->settings->useApproximateRaycast = false;
-    e->settings->useBilateralFilter = false;
-    e->settings->modelSensorNoise = false;
+    e->settings->useBilateralFilter = g_nextBilateral != 0;
+    e->settings->modelSensorNoise = g_nextWicp != 0;
+    if (g_nextWicp) e->settings->trackerType = ITMLibSettings::TRACKER_WICP;
     e->settings->sceneParams.voxelSize = voxelSize;
     e->settings->sceneParams.mu = mu;
     e->settings->sceneParams.maxW = maxW;
@@ -90,12 +101,21 @@ adp_engine *adp_create(int W, int H, float fx, float fy, float cx, float cy, flo
     e->reco = new ITMSceneReconstructionEngine_B200<TV, TI>(e->ctx);
     e->renderState = e->vis->CreateRenderState(e->imgSize);
     e->reco->ResetScene(e->scene);
-    e->tracker = new ITMDepthTracker_B200(e->imgSize, e->settings->trackingRegime, e->settings->noHierarchyLevels, e->settings->noICPRunTillLevel,
-                                          e->settings->depthTrackerICPThreshold, e->settings->depthTrackerTerminationThreshold, e->lowLevel, e->ctx);
-    e->tracker->useDeviceLoop = deviceLoop != 0;
-    e->controller = new ITMTrackingController(e->tracker, e->vis, e->lowLevel, e->settings);
+    e->tracker = NULL;
+    e->wtracker = NULL;
+    if (g_nextWicp) {
+      e->wtracker = new ITMWeightedICPTracker_B200(e->imgSize, e->settings->trackingRegime, e->settings->noHierarchyLevels,
+                                                   e->settings->noICPRunTillLevel, e->settings->depthTrackerICPThreshold,
+                                                   e->settings->depthTrackerTerminationThreshold, e->lowLevel, e->ctx);
+    } else {
+      e->tracker = new ITMDepthTracker_B200(e->imgSize, e->settings->trackingRegime, e->settings->noHierarchyLevels, e->settings->noICPRunTillLevel,
+                                            e->settings->depthTrackerICPThreshold, e->settings->depthTrackerTerminationThreshold, e->lowLevel, e->ctx);
+      e->tracker->useDeviceLoop = deviceLoop != 0;
+    }
+    ITMTracker *anyTracker = e->wtracker ? (ITMTracker *)e->wtracker : (ITMTracker *)e->tracker;
+    e->controller = new ITMTrackingController(anyTracker, e->vis, e->lowLevel, e->settings);
     e->trackingState = e->controller->BuildTrackingState(e->imgSize);
-    e->tracker->UpdateInitialPose(e->trackingState);
+    anyTracker->UpdateInitialPose(e->trackingState);
     e->view = NULL;
     e->renderStateFree = NULL;
     e->freeOut = NULL;
@@ -121,7 +141,8 @@ void adp_destroy(adp_engine *e) {
   delete e->meshing;
   delete e->scene;
   delete e->controller;
-  delete e->tracker;
+  if (e->tracker) delete e->tracker;
+  if (e->wtracker) delete e->wtracker;
   delete e->lowLevel;
   delete e->viewBuilder;
   delete e->trackingState;
@@ -205,6 +226,39 @@ int adp_count_stored(adp_engine *e) {
   return n;
 }
 
+// ITMViewBuilder::UpdateView alone (with the engine's filter settings)
+int adp_update_view(adp_engine *e, const short *depth) {
+  try {
+    memcpy(e->rawDepth->GetData(MEMORYDEVICE_CPU), depth, (size_t)e->imgSize.x * e->imgSize.y * sizeof(short));
+    e->viewBuilder->UpdateView(&e->view, e->rgb, e->rawDepth, e->settings->useBilateralFilter, e->settings->modelSensorNoise);
+    return 0;
+  } catch (std::exception &ex) {
+    g_err = ex.what();
+    return -1;
+  }
+}
+
+// one ITMWeightedICPTracker::ComputeGandH at approxInvPose on pyramid level `level` of the current view;
+// out: [0] = noValidPoints, [1] = f, [2..7] = nabla, [8..43] = hessian
+int adp_wicp_gandh(adp_engine *e, int level, const float *approxInvPose, float *out) {
+  try {
+    e->wtracker->SetEvaluationData(e->trackingState, e->view);
+    e->wtracker->PrepareForEvaluation();
+    e->wtracker->SetEvaluationParams(level);
+    Matrix4f inv(approxInvPose);
+    float f = 0.f, nabla[6] = {0, 0, 0, 0, 0, 0}, hess[36];
+    for (int i = 0; i < 36; ++i) hess[i] = 0.f;
+    const int n = e->wtracker->ComputeGandH(f, nabla, hess, inv);
+    out[0] = (float)n; out[1] = f;
+    for (int i = 0; i < 6; ++i) out[2 + i] = nabla[i];
+    for (int i = 0; i < 36; ++i) out[8 + i] = hess[i];
+    return n;
+  } catch (std::exception &ex) {
+    g_err = ex.what();
+    return -1;
+  }
+}
+
 void adp_get_pose(adp_engine *e, float *M16) { memcpy(M16, e->trackingState->pose_d->GetM().m, 64); }
 
 // counters = {noVisibleEntries, lastFreeBlockId, lastFreeExcessListId, age_pointCloud}
@@ -216,7 +270,7 @@ void adp_counters(adp_engine *e, int *c4) {
 }
 
 // which: 0 hash entries, 1 voxel blocks, 2 visible ids, 3 raycast result, 4 points map, 5 normals map, 6 entriesVisibleType,
-// 7 raycastImage
+// 7 raycastImage, 8 view->depth, 9 view->depthUncertainty, 10 view->depthNormal
 long long adp_read(adp_engine *e, int which, void *dst, long long capacity) {
   const size_t P = (size_t)e->imgSize.x * e->imgSize.y;
   const void *src = NULL;
@@ -231,6 +285,9 @@ long long adp_read(adp_engine *e, int which, void *dst, long long capacity) {
     case 5: src = e->trackingState->pointCloud->colours->GetData(MEMORYDEVICE_CUDA); bytes = P * 16; break;
     case 6: src = rs->GetEntriesVisibleType(); bytes = (size_t)ITMVoxelBlockHash::noTotalEntries; break;
     case 7: src = rs->raycastImage->GetData(MEMORYDEVICE_CUDA); bytes = P * 4; break;
+    case 8: src = e->view->depth->GetData(MEMORYDEVICE_CUDA); bytes = P * 4; break;
+    case 9: if (!e->view->depthUncertainty) return -1; src = e->view->depthUncertainty->GetData(MEMORYDEVICE_CUDA); bytes = P * 4; break;
+    case 10: if (!e->view->depthNormal) return -1; src = e->view->depthNormal->GetData(MEMORYDEVICE_CUDA); bytes = P * 16; break;
     default: return -1;
   }
   if ((long long)bytes > capacity) return -(long long)bytes;

@@ -36,9 +36,11 @@ SOURCES = [
     "ITMLib/Objects/ITMPose.cpp",
     "ITMLib/Utils/ITMLibSettings.cpp",
     "ITMLib/Engine/ITMDepthTracker.cpp",
+    "ITMLib/Engine/ITMWeightedICPTracker.cpp",
     "ITMLib/Engine/ITMTrackingController.cpp",
     "ITMLib/Engine/ITMVisualisationEngine.cpp",
     "ITMLib/Engine/DeviceSpecific/CPU/ITMDepthTracker_CPU.cpp",
+    "ITMLib/Engine/DeviceSpecific/CPU/ITMWeightedICPTracker_CPU.cpp",
     "ITMLib/Engine/DeviceSpecific/CPU/ITMLowLevelEngine_CPU.cpp",
     "ITMLib/Engine/DeviceSpecific/CPU/ITMViewBuilder_CPU.cpp",
     "ITMLib/Engine/DeviceSpecific/CPU/ITMSceneReconstructionEngine_CPU.cpp",
@@ -103,6 +105,7 @@ ADAPTER_SOURCES = [
     "ITMLib/Objects/ITMPose.cpp",
     "ITMLib/Utils/ITMLibSettings.cpp",
     "ITMLib/Engine/ITMDepthTracker.cpp",
+    "ITMLib/Engine/ITMWeightedICPTracker.cpp",
     "ITMLib/Engine/ITMTrackingController.cpp",
 ]
 

@@ -103,6 +103,16 @@ def declare_common(lib):
         lib.ref_write_stl.restype = None
         lib.ref_write_obj.argtypes = [C.c_void_p, C.c_char_p]
         lib.ref_write_obj.restype = None
+    if _has(lib, "ref_set_tracker_wicp"):
+        lib.ref_set_tracker_wicp.argtypes = [C.c_int, C.c_int]
+        lib.ref_set_tracker_wicp.restype = None
+        lib.ref_wicp_prepare.argtypes = [C.c_void_p]
+        lib.ref_wicp_prepare.restype = None
+        lib.ref_wicp_gandh.argtypes = [C.c_void_p, C.c_int, _f32p, _f32p]
+        lib.ref_wicp_gandh.restype = C.c_int
+        for name in ("ref_depth_uncertainty", "ref_depth_normal"):
+            getattr(lib, name).argtypes = [C.c_void_p]
+            getattr(lib, name).restype = C.c_void_p
     lib.ref_update_view.argtypes = [C.c_void_p, C.c_void_p]
     lib.ref_update_view.restype = None
     lib.ref_process_frame.argtypes = [C.c_void_p, C.c_void_p]
@@ -167,10 +177,11 @@ class RefEngine:
     """The reference CPU engines composed like ITMMainEngine (ITMLib/Engine/ITMMainEngine.cpp:17-127)."""
 
     def __init__(self, width=640, height=480, intr=None, voxel_size=0.005, mu=0.02, max_w=100, vf_min=0.35,
-                 vf_max=3.0, flavour="parity", use_swapping=False):
+                 vf_max=3.0, flavour="parity", use_swapping=False, wicp=False, bilateral=False):
         from infinitam_b200 import synth  # numpy-only helper
 
         self.use_swapping = use_swapping
+        self.wicp, self.bilateral = wicp, bilateral
         self.W, self.H = width, height
         self.intr = tuple(float(x) for x in (intr or synth.intrinsics_for(width, height)))
         self.voxel_size, self.mu, self.max_w, self.vf_min, self.vf_max = voxel_size, mu, max_w, vf_min, vf_max
@@ -179,10 +190,14 @@ class RefEngine:
 
     def _create(self, flavour):
         self.lib = load(flavour)
+        if self.wicp or self.bilateral:
+            self.lib.ref_set_tracker_wicp(int(self.wicp), int(self.bilateral))
         if self.use_swapping:
             self.lib.ref_set_use_swapping(1)
         with _stdout_to_stderr():  # ITMLibSettings() prints its tracker type on std::cout (ITMLibSettings.cpp:85-86)
             self.h = self.lib.ref_create(self.W, self.H, *self.intr, self.voxel_size, self.mu, self.max_w, self.vf_min, self.vf_max)
+        if self.wicp or self.bilateral:
+            self.lib.ref_set_tracker_wicp(0, 0)
         if self.use_swapping:
             self.lib.ref_set_use_swapping(0)
         c = self.const
@@ -296,6 +311,24 @@ class RefEngine:
     def free_raycast_result(self):
         w, h = self._free_dims
         return _view(self.lib.ref_free_raycast_result(self.h), np.float32, w * h * 4).reshape(h, w, 4)
+
+    # ---- weighted ICP (wicp=True engines) ----------------------------------------------------
+    def wicp_prepare(self):
+        self.lib.ref_wicp_prepare(self.h)
+
+    def wicp_gandh(self, level, approx_inv_pose16):
+        inv = np.ascontiguousarray(approx_inv_pose16, dtype=np.float32).reshape(16)
+        out = np.zeros(44, dtype=np.float32)
+        n = self.lib.ref_wicp_gandh(self.h, level, _fp(inv), _fp(out))
+        return n, out
+
+    @property
+    def depth_uncertainty(self):
+        return self._img(self.lib.ref_depth_uncertainty, np.float32, 1)
+
+    @property
+    def depth_normal(self):
+        return self._img(self.lib.ref_depth_normal, np.float32, 4)
 
     # ---- meshing -----------------------------------------------------------------------
     def mesh_scene(self, whole_buffer=False):

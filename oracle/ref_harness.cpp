@@ -60,6 +60,7 @@ struct ref_engine {
   ITMSceneReconstructionEngine_CPU<TV, TI> *reco;
   ITMSwappingEngine_CPU<TV, TI> *swapper;  // NULL unless created after ref_set_use_swapping(1)
   ITMDepthTracker_CPU *tracker;
+  ITMWeightedICPTracker_CPU *wtracker;  // instead of tracker when created after ref_set_tracker_wicp(1, ..)
   ITMTrackingController *controller;
   ITMTrackingState *trackingState;
   ITMRenderState *renderState;
@@ -79,11 +80,15 @@ static double now_ms() {
 }
 
 static int g_nextUseSwapping = 0;
+static int g_nextWicp = 0, g_nextBilateral = 0;
 
 extern "C" {
 
 // settings.useSwapping of the engines created from now on (ITMLibSettings.cpp:35; ITMDenseMapper.cpp:20,59-64)
 void ref_set_use_swapping(int on) { g_nextUseSwapping = on; }
+// engines created from now on use TRACKER_WICP (ITMWeightedICPTracker_CPU + settings.modelSensorNoise, what
+// ITMLibSettings.cpp:52-57 selects for that tracker type) and, optionally, settings.useBilateralFilter
+void ref_set_tracker_wicp(int on, int bilateral) { g_nextWicp = on; g_nextBilateral = bilateral; }
 
 int ref_const(const char *name) {
   std::string n(name);
@@ -112,8 +117,9 @@ ref_engine *ref_create(int W, int H, float fx, float fy, float cx, float cy,
   e->settings->trackerType = ITMLibSettings::TRACKER_ICP;
   e->settings->useSwapping = g_nextUseSwapping != 0;
   e->settings->useApproximateRaycast = false;
-  e->settings->useBilateralFilter = false;
-  e->settings->modelSensorNoise = false;
+  e->settings->useBilateralFilter = g_nextBilateral != 0;
+  e->settings->modelSensorNoise = g_nextWicp != 0;
+  if (g_nextWicp) e->settings->trackerType = ITMLibSettings::TRACKER_WICP;
   e->settings->sceneParams.voxelSize = voxelSize;
   e->settings->sceneParams.mu = mu;
   e->settings->sceneParams.maxW = maxW;
@@ -133,13 +139,22 @@ ref_engine *ref_create(int W, int H, float fx, float fy, float cx, float cy,
   e->reco = new ITMSceneReconstructionEngine_CPU<TV, TI>();
   e->renderState = e->vis->CreateRenderState(e->imgSize);
   e->reco->ResetScene(e->scene);
-  e->tracker = new ITMDepthTracker_CPU(
-      e->imgSize, e->settings->trackingRegime, e->settings->noHierarchyLevels,
-      e->settings->noICPRunTillLevel, e->settings->depthTrackerICPThreshold,
-      e->settings->depthTrackerTerminationThreshold, e->lowLevel);
-  e->controller = new ITMTrackingController(e->tracker, e->vis, e->lowLevel, e->settings);
+  e->tracker = NULL;
+  e->wtracker = NULL;
+  if (g_nextWicp)
+    e->wtracker = new ITMWeightedICPTracker_CPU(
+        e->imgSize, e->settings->trackingRegime, e->settings->noHierarchyLevels,
+        e->settings->noICPRunTillLevel, e->settings->depthTrackerICPThreshold,
+        e->settings->depthTrackerTerminationThreshold, e->lowLevel);
+  else
+    e->tracker = new ITMDepthTracker_CPU(
+        e->imgSize, e->settings->trackingRegime, e->settings->noHierarchyLevels,
+        e->settings->noICPRunTillLevel, e->settings->depthTrackerICPThreshold,
+        e->settings->depthTrackerTerminationThreshold, e->lowLevel);
+  ITMTracker *anyTracker = e->wtracker ? (ITMTracker *)e->wtracker : (ITMTracker *)e->tracker;
+  e->controller = new ITMTrackingController(anyTracker, e->vis, e->lowLevel, e->settings);
   e->trackingState = e->controller->BuildTrackingState(e->imgSize);
-  e->tracker->UpdateInitialPose(e->trackingState);
+  anyTracker->UpdateInitialPose(e->trackingState);
   e->view = NULL;
   e->renderStateFree = NULL;
   e->freeOut = NULL;
@@ -160,7 +175,8 @@ void ref_destroy(ref_engine *e) {
   if (e->meshing) delete e->meshing;
   delete e->scene;
   delete e->controller;
-  delete e->tracker;
+  if (e->tracker) delete e->tracker;
+  if (e->wtracker) delete e->wtracker;
   delete e->lowLevel;
   delete e->viewBuilder;
   delete e->trackingState;
@@ -181,7 +197,7 @@ void ref_set_rgb(ref_engine *e, const unsigned char *rgba) {
 
 void ref_update_view(ref_engine *e, const short *depth) {
   memcpy(e->rawDepth->GetData(MEMORYDEVICE_CPU), depth, (size_t)e->imgSize.x * e->imgSize.y * sizeof(short));
-  e->viewBuilder->UpdateView(&e->view, e->rgb, e->rawDepth, false, false);
+  e->viewBuilder->UpdateView(&e->view, e->rgb, e->rawDepth, e->settings->useBilateralFilter, e->settings->modelSensorNoise);
 }
 void ref_track(ref_engine *e) { e->controller->Track(e->trackingState, e->view); }
 void ref_allocate(ref_engine *e, int onlyVisible) {
@@ -334,6 +350,25 @@ int ref_icp_gandh(ref_engine *e, int level, const float *approxInvPose, float *o
   for (int i = 0; i < 36; ++i) out[8 + i] = hess[i];
   return n;
 }
+// ---- weighted ICP (TRACKER_WICP engines) ---------------------------------------
+void ref_wicp_prepare(ref_engine *e) {
+  e->wtracker->SetEvaluationData(e->trackingState, e->view);
+  e->wtracker->PrepareForEvaluation();
+}
+int ref_wicp_gandh(ref_engine *e, int level, const float *approxInvPose, float *out) {
+  e->wtracker->SetEvaluationParams(level);
+  Matrix4f inv(approxInvPose);
+  float f = 0.f, nabla[6] = {0, 0, 0, 0, 0, 0}, hess[36];
+  for (int i = 0; i < 36; ++i) hess[i] = 0.f;
+  int n = e->wtracker->ComputeGandH(f, nabla, hess, inv);
+  out[0] = (float)n; out[1] = f;
+  for (int i = 0; i < 6; ++i) out[2 + i] = nabla[i];
+  for (int i = 0; i < 36; ++i) out[8 + i] = hess[i];
+  return n;
+}
+float *ref_depth_uncertainty(ref_engine *e) { return (e->view && e->view->depthUncertainty) ? e->view->depthUncertainty->GetData(MEMORYDEVICE_CPU) : NULL; }
+float *ref_depth_normal(ref_engine *e) { return (e->view && e->view->depthNormal) ? (float *)e->view->depthNormal->GetData(MEMORYDEVICE_CPU) : NULL; }
+
 int ref_pyramid_level(ref_engine *e, int level, float **data, int *w, int *h, float *intrinsics4) {
   ITMTemplatedHierarchyLevel<ITMFloatImage> *l = e->tracker->viewHierarchy->levels[level];
   *data = l->depth->GetData(MEMORYDEVICE_CPU);
