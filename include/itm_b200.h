@@ -81,6 +81,11 @@ typedef struct itm_b200_params {
    * (ITMTrackingController.cpp:11-46) skip the full raycast while the camera stays close to the pose of the last one
    * (ITMTrackingState::TrackerFarFromPointCloud, Objects/ITMTrackingState.h:41-59) and forward-project it instead */
   int use_approximate_raycast;
+  /* 0: the tracker's persistent kernel takes one CTA on every SM (lowest latency for one scene).  n > 0: at most n CTAs,
+   * so that the trackers of several scenes sharing the GPU (BASELINE configs[3]: 8 scenes per GPU, one engine and stream
+   * each) run side by side instead of one after the other - most of a TrackCamera is spent on pyramid levels that occupy
+   * fewer than 40 CTAs anyway.  Changes the summation order of the ICP sums (poses agree to ~1e-6, not bit for bit). */
+  int icp_max_ctas;
 } itm_b200_params;
 #define ITM_B200_VOXEL_S 0
 #define ITM_B200_VOXEL_S_RGB 1

@@ -48,6 +48,7 @@ class Params(C.Structure):
         ("trafo_rgb_to_depth_inv", C.c_float * 16),
         ("use_swapping", C.c_int),
         ("use_approximate_raycast", C.c_int),
+        ("icp_max_ctas", C.c_int),
     ]
 
 

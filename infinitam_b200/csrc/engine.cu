@@ -323,7 +323,7 @@ void enqueue_track(itm_b200_ctx *c, const float *depth0, const float *points, co
     iters[l] = c->levels[l].noIterations;
   }
   const cudaError_t e = launch_icp_track(a, lv, iters, c->nLevels, c->p.no_icp_run_till_level, c->icpRows, c->icpBcast, c->icpEpochDev,
-                                         !epochBumped, s);
+                                         !epochBumped, c->p.icp_max_ctas, s);
   if (e != cudaSuccess) g_lastError = std::string("cooperative launch of the ICP tracker failed: ") + cudaGetErrorString(e);
   g_launches += epochBumped ? 1 : 2;
 }

@@ -738,7 +738,8 @@ int icp_track_grid() {
 __global__ void k_icp_bump(unsigned *epochDev) { icp_bump_epoch(epochDev); }
 
 cudaError_t launch_icp_track(const IcpArgs &a, const IcpLevelArgs *levels, const int *iters, int nLevels, int noIcpLevel,
-                             unsigned long long *rows, unsigned long long *bcast, unsigned *epochDev, bool bumpEpoch, cudaStream_t s) {
+                             unsigned long long *rows, unsigned long long *bcast, unsigned *epochDev, bool bumpEpoch, int gridCap,
+                             cudaStream_t s) {
   TrackArgs t;
   t.a = a;
   for (int l = 0; l < ITM_MAX_LEVELS; ++l) {
@@ -758,7 +759,9 @@ cudaError_t launch_icp_track(const IcpArgs &a, const IcpLevelArgs *levels, const
   t.epochDev = epochDev;
   if (bumpEpoch) k_icp_bump<<<1, 1, 0, s>>>(epochDev);
   void *args[] = {&t};
-  return cudaLaunchCooperativeKernel((const void *)k_icp_track, dim3(icp_track_grid()), dim3(ICP_THREADS), args, 0, s);
+  int grid = icp_track_grid();
+  if (gridCap > 0 && gridCap < grid) grid = gridCap;
+  return cudaLaunchCooperativeKernel((const void *)k_icp_track, dim3(grid), dim3(ICP_THREADS), args, 0, s);
 }
 
 size_t icp_rows_bytes() { return (size_t)icp_max_ctas() * ICP_NVALS * sizeof(unsigned long long); }

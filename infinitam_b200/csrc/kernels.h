@@ -162,7 +162,8 @@ void launch_view_pyramid(const short *raw, float a, float b, float *const *level
 // launch first (false when the frame's view kernel already did, FramePrologue::icpEpoch).  Keeping it on the device
 // makes the launch parameters identical from frame to frame, so a whole frame can be replayed as a CUDA graph.
 cudaError_t launch_icp_track(const IcpArgs &a, const IcpLevelArgs *levels, const int *iters, int nLevels, int noIcpLevel,
-                             unsigned long long *rows, unsigned long long *bcast, unsigned *epochDev, bool bumpEpoch, cudaStream_t s);
+                             unsigned long long *rows, unsigned long long *bcast, unsigned *epochDev, bool bumpEpoch, int gridCap,
+                             cudaStream_t s);  // gridCap > 0: at most that many CTAs (several scenes sharing one GPU)
 __device__ __forceinline__ void icp_bump_epoch(unsigned *epochDev) { *epochDev = (*epochDev % 0x1FFFFFEu) + 1u; }  // 1 .. 2^25 - 2
 size_t icp_rows_bytes();
 size_t icp_bcast_bytes();
