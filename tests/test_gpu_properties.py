@@ -113,3 +113,34 @@ def test_long_free_running_sequence_stays_close_to_reference():
     M = pose.reshape(4, 4).T
     assert np.abs(M[:3, 3] - gt[:3, 3]).max() < 0.03
     eng.close(); o.close()
+
+
+def test_concurrent_scenes_with_capped_tracker_grid():
+    """BASELINE configs[3] on one GPU: several engines (one stream each) fused concurrently with icp_max_ctas so that their
+    persistent tracker kernels co-reside.  Every scene gets the same frames here, so (a) all scenes must end bit-identical
+    to each other - concurrency must not leak between handles - and (b) they must agree with a stand-alone full-grid engine
+    within the pose tolerance (another CTA count = another summation order in the ICP reduction)."""
+    import torch
+    w, h, n, S = 320, 240, 10, 4
+    seq = torch.from_numpy(synth.sequence(n, w, h)).cuda()
+    solo = ITMMainEngine(capi.default_params(w, h))
+    for k in range(n):
+        solo.EnqueueFrameDevice(seq[k].data_ptr())
+    pose_solo, cnt_solo = solo.Sync()
+    p = capi.default_params(w, h)
+    p.icp_max_ctas = 148 // S
+    engs = [ITMMainEngine(p) for _ in range(S)]
+    for k in range(n):
+        for e in engs:
+            e.EnqueueFrameDevice(seq[k].data_ptr())
+    res = [e.Sync() for e in engs]
+    for pose, cnt in res[1:]:
+        assert np.array_equal(pose, res[0][0]) and np.array_equal(cnt, res[0][1])
+    hashes = [e.read(capi.BUF_HASH).tobytes() for e in engs]
+    assert all(hh == hashes[0] for hh in hashes)
+    rot, trans = parity.pose_diff(res[0][0], pose_solo)
+    assert rot <= 1e-4 and trans <= 1e-4, "capped tracker grid drifts from the full grid: %g rad %g m" % (rot, trans)
+    assert abs(int(res[0][1][0]) - int(cnt_solo[0])) <= 0.01 * cnt_solo[0] + 2
+    for e in engs:
+        e.close()
+    solo.close()

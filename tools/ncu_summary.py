@@ -30,7 +30,10 @@ METRICS = OrderedDict([
 ])
 STAGE_OF = {"k_convert_pyramid": "view", "k_icp_track": "track", "k_mark_prev_visible": "allocate", "k_alloc_pixels": "allocate",
             "k_alloc_scan": "allocate", "k_visible_scan": "allocate", "k_integrate": "integrate", "k_minmax_init": "expected_depths",
-            "k_expected_depths": "expected_depths", "k_raycast": "raycast", "k_icp_maps": "icp_maps"}
+            "k_expected_depths": "expected_depths", "k_raycast": "raycast", "k_icp_maps": "icp_maps",
+            # SURVEY 8f rows (not stages of the bench step; listed for the per-kernel table only)
+            "k_fwd_project": None, "k_fwd_gather": None, "k_fwd_cast": None, "k_fwd_shade": None, "k_track_decide": None,
+            "k_find_visible": None, "k_render_image": None, "k_mesh_blocks": None, "k_mesh_scan": None}
 
 
 def to_bytes(v, unit):
@@ -39,10 +42,18 @@ def to_bytes(v, unit):
 
 
 def main():
-    raw, out = sys.argv[1], sys.argv[2]
-    rows = list(csv.reader(open(raw)))
-    hdr, units, data = rows[0], rows[1], rows[2:]
-    idx = {h: i for i, h in enumerate(hdr)}
+    raws, out = sys.argv[1:-1], sys.argv[-1]
+    raw = ", ".join(raws)
+    launches = []
+    for one in raws:
+        rows = list(csv.reader(open(one)))
+        hdr, units, data = rows[0], rows[1], rows[2:]
+        idx = {h: i for i, h in enumerate(hdr)}
+        launches += parse(hdr, units, data, idx)
+    finish(raw, out, launches)
+
+
+def parse(hdr, units, data, idx):
     launches = []
     for d in data:
         name = d[idx["Kernel Name"]]
@@ -61,6 +72,10 @@ def main():
                 f = float(v.replace(",", ""))
                 rec[label] = round(f, 2) if f < 1e6 else int(f)
         launches.append(rec)
+    return launches
+
+
+def finish(raw, out, launches):
     per_kernel = OrderedDict()
     for r in launches:
         per_kernel.setdefault(r["kernel"], []).append(r)
