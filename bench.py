@@ -455,9 +455,13 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     sampler.start()
     sampler.wait_first_sample()
+    # The L2 flush (a 256 MiB fill) is enqueued on the ENGINE's stream right before the frame, and the frame behind it without
+    # a host synchronisation in between: the frame's events then measure device time only - the host's launch latency for an
+    # idle stream (it is part of `e2e`) does not sit between the first time stamp and the first kernel.
+    eng_stream = torch.cuda.ExternalStream(eng.stream(), device=dev)
     for k in range(args.warmup):
-        flush.fill_(k)
-        torch.cuda.synchronize()
+        with torch.cuda.stream(eng_stream):
+            flush.fill_(k)
         eng.EnqueueFrameDevice(frames_dev[k].data_ptr())
         eng.Sync()
     barrier()
@@ -467,8 +471,8 @@ def run_ours(args):
     stage_ms = np.zeros(8)
     n_vis_sum, level_evals = 0, np.zeros(capi.MAX_LEVELS, np.int64)
     for k in range(args.warmup, n):
-        flush.fill_(k & 0xFF)
-        torch.cuda.synchronize()
+        with torch.cuda.stream(eng_stream):
+            flush.fill_(k & 0xFF)
         eng.EnqueueFrameDevice(frames_dev[k].data_ptr())
         _, counters = eng.Sync()
         ms = eng.stage_times()
@@ -542,7 +546,7 @@ def run_ours(args):
             "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "configs[1]: synthetic 640x480 analytic-room sequence, 5 mm voxels, mu=0.02, ITMVoxel_s, depth ICP tracker",
-                       "frames": args.steps, "visible_blocks": n_vis, "icp_evaluations_per_frame": float(ev.sum()), "l2": "flushed between frames (256 MiB write, outside the timed events)",
+                       "frames": args.steps, "visible_blocks": n_vis, "icp_evaluations_per_frame": float(ev.sum()), "l2": "flushed before every frame (256 MiB write on the engine's stream, outside the timed events)",
                        "parallelism": "replicas only: one independent scene per GPU, no collective on the data path",
                        "timing": "per-frame CUDA events on the engine stream, summed; max over ranks"},
             "gvoxel_updates_per_s": world * nv * 512 / (stage_avg["integrate"] * 1e-3) / 1e9 if stage_avg["integrate"] else None,

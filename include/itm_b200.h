@@ -319,6 +319,10 @@ int itm_b200_ipc_free(void *dev_ptr);
 /* rank that integrates the voxel block at block coordinate (x, y, z) */
 int itm_b200_shard_owner_of_block(int x, int y, int z, int world);
 
+/* The cudaStream_t every frame of this engine is enqueued on (borrowed; valid until destroy): lets the host order its own
+ * work - e.g. producing the next depth frame on the device - before or after frames without a host synchronisation. */
+int itm_b200_engine_get_stream(itm_b200_engine *e, void **stream);
+
 /* Same frame, input already resident in HBM, enqueued asynchronously on the engine's stream. */
 int itm_b200_engine_enqueue_frame_dev(itm_b200_engine *e, const short *raw_depth_dev);
 /* Wait for everything enqueued; counters = {noVisibleEntries, lastFreeBlockId,

@@ -1510,6 +1510,12 @@ int itm_b200_engine_process_frame(itm_b200_engine *e, const unsigned char *rgb_h
   return itm_b200_engine_sync(e, pose_out, nullptr);
 }
 
+int itm_b200_engine_get_stream(itm_b200_engine *e, void **stream) {
+  if (!e || !stream) return fail(ITM_B200_EINVAL, "NULL argument");
+  *stream = (void *)e->c->stream;
+  return ITM_B200_OK;
+}
+
 int itm_b200_engine_enqueue_frame_dev(itm_b200_engine *e, const short *raw_depth_dev) {
   if (!e || !raw_depth_dev) return fail(ITM_B200_EINVAL, "NULL argument");
   cudaStream_t s = e->c->stream;

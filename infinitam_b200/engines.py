@@ -99,6 +99,12 @@ class ITMMainEngine:
     def EnqueueFrameDevice(self, raw_depth_dev_ptr: int):
         capi.check(self.lib.itm_b200_engine_enqueue_frame_dev(self.h, C.c_void_p(raw_depth_dev_ptr)))
 
+    def stream(self) -> int:
+        """the cudaStream_t (as an integer) the engine enqueues its frames on, e.g. for torch.cuda.ExternalStream"""
+        p = C.c_void_p()
+        capi.check(self.lib.itm_b200_engine_get_stream(self.h, C.byref(p)))
+        return p.value or 0
+
     def Sync(self):
         pose = np.zeros(16, dtype=np.float32)
         counters = np.zeros(6, dtype=np.int32)
