@@ -68,6 +68,7 @@ struct itm_b200_ctx {
   unsigned long long *scanTickets = nullptr;
   unsigned long long *allocTileState = nullptr;
   unsigned long long *visTileState = nullptr;
+  unsigned long long *otherTileState = nullptr;  // FindVisibleBlocks / swap selection / meshing: 8192-slot tiles, ticket [2]
   double *icpPartials = nullptr;
   unsigned *icpCounter = nullptr;
   unsigned long long *icpRows = nullptr;   // tagged CTA partial sums of k_icp_track
@@ -158,12 +159,17 @@ int ctx_alloc(itm_b200_ctx *c, void *stream) {
   if (maxKey >= 0xFFFFFFFFLL) return fail(ITM_B200_EUNSUPPORTED, "image size x ray-segment steps exceeds the 32-bit allocation key");
   CU(cudaMalloc(&c->allocKey, (size_t)numTiles * 8192 * sizeof(unsigned)));
   CU(cudaMemsetAsync(c->allocKey, 0, (size_t)numTiles * 8192 * sizeof(unsigned), c->stream));
-  CU(cudaMalloc(&c->scanTickets, 2 * sizeof(unsigned long long)));
-  CU(cudaMemsetAsync(c->scanTickets, 0, 2 * sizeof(unsigned long long), c->stream));
-  CU(cudaMalloc(&c->allocTileState, numTiles * sizeof(unsigned long long)));
-  CU(cudaMemsetAsync(c->allocTileState, 0, numTiles * sizeof(unsigned long long), c->stream));
-  CU(cudaMalloc(&c->visTileState, numTiles * sizeof(unsigned long long)));
-  CU(cudaMemsetAsync(c->visTileState, 0, numTiles * sizeof(unsigned long long), c->stream));
+  // every scan kernel family has its own ticket (tile = ticket % its own tile count): [0] allocation scan, [1] visible scan,
+  // [2] the 8192-slot scans of FindVisibleBlocks / swapping / meshing
+  const int allocTiles = (c->sp.nEntries + alloc_scan_tile() - 1) / alloc_scan_tile();
+  CU(cudaMalloc(&c->scanTickets, 3 * sizeof(unsigned long long)));
+  CU(cudaMemsetAsync(c->scanTickets, 0, 3 * sizeof(unsigned long long), c->stream));
+  CU(cudaMalloc(&c->allocTileState, allocTiles * sizeof(unsigned long long)));
+  CU(cudaMemsetAsync(c->allocTileState, 0, allocTiles * sizeof(unsigned long long), c->stream));
+  CU(cudaMalloc(&c->visTileState, allocTiles * sizeof(unsigned long long)));
+  CU(cudaMemsetAsync(c->visTileState, 0, allocTiles * sizeof(unsigned long long), c->stream));
+  CU(cudaMalloc(&c->otherTileState, numTiles * sizeof(unsigned long long)));
+  CU(cudaMemsetAsync(c->otherTileState, 0, numTiles * sizeof(unsigned long long), c->stream));
   CU(cudaMalloc(&c->icpPartials, (size_t)icp_max_ctas() * 32 * sizeof(double)));
   CU(cudaMalloc(&c->icpCounter, sizeof(unsigned)));
   CU(cudaMemsetAsync(c->icpCounter, 0, sizeof(unsigned), c->stream));
@@ -198,6 +204,7 @@ void ctx_free(itm_b200_ctx *c) {
   RELEASE(cudaFree(c->scanTickets));
   RELEASE(cudaFree(c->allocTileState));
   RELEASE(cudaFree(c->visTileState));
+  RELEASE(cudaFree(c->otherTileState));
   RELEASE(cudaFree(c->icpPartials));
   RELEASE(cudaFree(c->icpCounter));
   RELEASE(cudaFree(c->icpRows));
@@ -574,7 +581,7 @@ int itm_b200_find_visible_blocks(itm_b200_ctx *c, const itm_b200_scene *scene, i
   int rc = push_state(c);
   if (rc) return rc;
   launch_find_visible_blocks(scene->hash_entries_dev, rs->visible_entry_ids_dev, c->st, rs_view(c, rs, intrinsics), c->sp, c->sp.nLocal,
-                             c->scanTickets + 1, c->visTileState, c->stream);
+                             c->scanTickets + 2, c->otherTileState, c->stream);
   g_launches += 1;
   rc = pull_state(c);
   if (rc) return rc;
@@ -630,8 +637,8 @@ static SwapArgs swap_args_layer_a(itm_b200_ctx *c, const itm_b200_scene *scene, 
   a.neededIds = sw->needed_entry_ids_dev;
   a.transfer = sw->synced_voxel_blocks_dev;
   a.hasSynced = sw->has_synced_data_dev;
-  a.ticket = c->scanTickets + 1;
-  a.tileState = c->visTileState;
+  a.ticket = c->scanTickets + 2;
+  a.tileState = c->otherTileState;
   a.st = c->st;
   a.sp = c->sp;
   return a;
@@ -706,8 +713,8 @@ static int mesh_scene_common(itm_b200_ctx *c, const void *voxels, const void *ha
   a.noMaxTriangles = no_max_triangles;
   a.st = c->meshSt;
   a.sp = c->sp;
-  a.ticket = c->scanTickets + 1;
-  a.tileState = c->visTileState;
+  a.ticket = c->scanTickets + 2;
+  a.tileState = c->otherTileState;
   launch_mesh_scene(a, c->stream);
   g_launches += 4;
   CU(cudaMemcpyAsync(c->meshHst, c->meshSt, sizeof(FrameState), cudaMemcpyDeviceToHost, c->stream));
@@ -1762,7 +1769,7 @@ int itm_b200_engine_get_image(itm_b200_engine *e, int image_type, const float po
   a.vp.W = out_w; a.vp.H = out_h;
   a.vp.fx = intrinsics[0]; a.vp.fy = intrinsics[1]; a.vp.cx = intrinsics[2]; a.vp.cy = intrinsics[3];
   a.sp = c->sp;
-  launch_find_visible_blocks(e->hash, e->freeVisibleIds, e->stFree, a.vp, c->sp, c->sp.nLocal, c->scanTickets + 1, c->visTileState, s);
+  launch_find_visible_blocks(e->hash, e->freeVisibleIds, e->stFree, a.vp, c->sp, c->sp.nLocal, c->scanTickets + 2, c->otherTileState, s);
   launch_expected_depths(a, s);
   const int type = image_type == ITM_B200_IMAGE_FREECAMERA_COLOUR_FROM_VOLUME ? ITM_B200_RENDER_COLOUR_FROM_VOLUME
                  : image_type == ITM_B200_IMAGE_FREECAMERA_COLOUR_FROM_NORMAL ? ITM_B200_RENDER_COLOUR_FROM_NORMAL

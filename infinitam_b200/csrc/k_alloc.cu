@@ -132,8 +132,10 @@ __global__ void __launch_bounds__(256) k_alloc_pixels(const float *__restrict__ 
   }
 }
 
-#define SCAN_TILE 8192        // slots per CTA
-#define SCAN_PER_THREAD 32    // consecutive slots per thread (256 threads)
+#ifndef SCAN_PER_THREAD
+#define SCAN_PER_THREAD 32    // consecutive slots per thread (256 threads); 8, 16 or 32
+#endif
+#define SCAN_TILE (256 * SCAN_PER_THREAD)  // slots per CTA
 
 // Every thread owns 32 consecutive slots; 1.18 M slots are 144 tiles, i.e. one CTA per SM and a look-back chain of
 // at most 5 warp-wide windows (with 1024-slot tiles the chain was 36 windows long and dominated the kernel).
@@ -289,9 +291,17 @@ __global__ void __launch_bounds__(256) k_visible_scan(const unsigned char *__res
   // 32 type bytes per thread.  entriesVisibleType is caller-owned and exactly nEntries long: the last tile may be ragged.
   unsigned w[SCAN_PER_THREAD / 4];
   if (slot0 + SCAN_PER_THREAD <= sp.nEntries) {
+#if SCAN_PER_THREAD == 32
     const uint4 a = *reinterpret_cast<const uint4 *>(visType + slot0);
     const uint4 b = *reinterpret_cast<const uint4 *>(visType + slot0 + 16);
     w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+#elif SCAN_PER_THREAD == 16
+    const uint4 a = *reinterpret_cast<const uint4 *>(visType + slot0);
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+#else
+    const uint2 a = *reinterpret_cast<const uint2 *>(visType + slot0);
+    w[0] = a.x; w[1] = a.y;
+#endif
   } else {
 #pragma unroll
     for (int i = 0; i < SCAN_PER_THREAD / 4; ++i) {
@@ -377,6 +387,8 @@ __global__ void k_reset_scene(uint32_t *__restrict__ voxels, size_t nVectors, in
 }  // namespace
 
 namespace itm {
+
+int alloc_scan_tile() { return SCAN_TILE; }
 
 int alloc_step_bound(const SceneParams &sp) {
   // noSteps = ceil(2 * |segment| / blockSize); |segment| = 2*mu up to rounding

@@ -94,6 +94,7 @@ struct IcpArgs {
 };
 
 int alloc_step_bound(const SceneParams &sp);
+int alloc_scan_tile();  // slots per CTA of the two allocation scans (their tile-state arrays need one word per tile)
 void launch_reset_scene(void *voxels, int *vbaAllocList, void *table, int *excessAllocList, const SceneParams &sp, cudaStream_t s);
 void launch_allocate(const AllocArgs &a, cudaStream_t s);
 void launch_integrate(const IntegrateArgs &a, cudaStream_t s);
