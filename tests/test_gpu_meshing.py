@@ -92,3 +92,26 @@ def test_adapter_save_scene_to_mesh(tmp_path):
     assert n == o.no_total_triangles and n > 1000
     assert filecmp.cmp(tmp_path / "ref.stl", tmp_path / "adp.stl", shallow=False)
     a.close(); o.close()
+
+
+def test_empty_scene_rows_8f(tmp_path):
+    """edge cases of the 8f rows on a scene that holds nothing: MeshScene yields no triangle (an 84-byte STL: header +
+    count), the free-view rendering is black with an empty visible list, and an all-invalid depth frame leaves it so"""
+    w, h = 160, 120
+    p = capi.default_params(w, h)
+    p.use_approximate_raycast = 1
+    from infinitam_b200.engines import ITMMainEngine
+    eng = ITMMainEngine(p)
+    assert len(eng.UpdateMesh()) == 0
+    eng.ProcessFrame(None, np.zeros((h, w), np.int16))   # no valid pixel
+    eng.ProcessFrame(None, np.full((h, w), -5, np.int16))
+    _, _, st = eng.get_state()
+    assert int(st[0]) == 0 and int(st[1]) == p.sdf_local_block_num - 1, "an empty frame must not allocate"
+    assert len(eng.UpdateMesh()) == 0
+    eng.SaveSceneToMesh(tmp_path / "empty.stl")
+    assert (tmp_path / "empty.stl").stat().st_size == 84
+    K = synth.intrinsics_for(w, h)
+    M = np.eye(4, dtype=np.float32).reshape(16)
+    for t in (capi.IMAGE_FREECAMERA_SHADED, capi.IMAGE_FREECAMERA_COLOUR_FROM_NORMAL, capi.IMAGE_FREECAMERA_COLOUR_FROM_VOLUME, capi.IMAGE_SCENERAYCAST):
+        assert not eng.GetImage(t, M, K).any()
+    eng.close()
