@@ -391,7 +391,9 @@ int itm_b200_engine_icp_stats(itm_b200_engine *e, int evals_per_level[ITM_B200_M
 
 /* Per-stage device times (CUDA events) of the last processed frame in milliseconds:
  * {h2d+view, track, allocate, integrate, expected depths, raycast, icp maps, total}.
- * Enabled by itm_b200_engine_set_profiling(e, 1) (adds event records to the stream). */
+ * Enabled by itm_b200_engine_set_profiling(e, 1) (an event record at every stage boundary: a node between two kernels of the
+ * frame graph each, ~1.5 us apiece).  set_profiling(e, 2) records the frame's start and end only: ms8[7] is then the
+ * frame's device time without those gaps, ms8[0..6] are 0. */
 int itm_b200_engine_set_profiling(itm_b200_engine *e, int on);
 int itm_b200_engine_stage_times(itm_b200_engine *e, float ms8[8]);
 

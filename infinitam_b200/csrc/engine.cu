@@ -958,11 +958,11 @@ struct itm_b200_engine {
   bool externalBuffers = false;  // voxels / raycastResult belong to the caller (sharded engines)
   unsigned barrierSeq = 0;
   // whole-frame CUDA graphs, one per (tracking on/off, profiling on/off); see enqueue_frame
-  cudaGraphExec_t frameGraph[4] = {nullptr, nullptr, nullptr, nullptr};
-  int frameGraphLaunches[4] = {0, 0, 0, 0};
+  cudaGraphExec_t frameGraph[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int frameGraphLaunches[6] = {0, 0, 0, 0, 0, 0};
   bool graphsOff = false;   // swapping / sharded engines, ITM_B200_NO_GRAPH=1, or a failed capture
   bool capturing = false;
-  bool profiling = false;
+  int profiling = 0;  // 0 off, 1 a time stamp at every stage boundary, 2 frame start and end only
   cudaEvent_t ev[9] = {nullptr};
   float stageMs[8] = {0};
   size_t bytes[ITM_B200_BUF_COUNT] = {0};
@@ -1062,7 +1062,7 @@ void engine_free(itm_b200_engine *e) {
   if (e->joinEv) RELEASE(cudaEventDestroy(e->joinEv));
   for (int i = 0; i < 9; ++i)
     if (e->ev[i]) RELEASE(cudaEventDestroy(e->ev[i]));
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 6; ++i)
     if (e->frameGraph[i]) RELEASE(cudaGraphExecDestroy(e->frameGraph[i]));
   if (e->c) {
     ctx_free(e->c);
@@ -1271,6 +1271,7 @@ void stage_shard_barrier(itm_b200_engine *e) {
 // stage-boundary time stamps; inside a stream capture they must become event-record NODES of the graph
 void stamp(itm_b200_engine *e, int i) {
   if (!e->profiling) return;
+  if (e->profiling == 2 && i != 0 && i != 8) return;  // every stamp is a node between two kernels: only the outer ones
   if (e->capturing) cudaEventRecordWithFlags(e->ev[i], e->c->stream, cudaEventRecordExternal);
   else cudaEventRecord(e->ev[i], e->c->stream);
 }
@@ -1321,7 +1322,7 @@ void enqueue_frame(itm_b200_engine *e) {
     enqueue_frame_direct(e);
     return;
   }
-  const int key = (e->agePointCloud != -1 ? 1 : 0) | (e->profiling ? 2 : 0);
+  const int key = (e->agePointCloud != -1 ? 1 : 0) + 2 * e->profiling;
   if (!e->frameGraph[key]) {
     const int ageBefore = e->agePointCloud;
     const unsigned long long launchesBefore = g_launches.load();
@@ -1816,7 +1817,7 @@ int itm_b200_engine_icp_stats(itm_b200_engine *e, int evals_per_level[ITM_B200_M
 
 int itm_b200_engine_set_profiling(itm_b200_engine *e, int on) {
   if (!e) return fail(ITM_B200_EINVAL, "NULL engine");
-  e->profiling = on != 0;
+  e->profiling = on < 0 ? 0 : (on > 2 ? 2 : on);
   return ITM_B200_OK;
 }
 
@@ -1826,8 +1827,11 @@ int itm_b200_engine_stage_times(itm_b200_engine *e, float ms8[8]) {
   // ev[0] frame start, ev[1] after H2D, ev[2] after view, ev[3] track, ev[4] allocate, ev[5] integrate,
   // ev[6] expected depths, ev[7] raycast, ev[8] icp maps
   float t;
-  cudaEventElapsedTime(&t, e->ev[0], e->ev[2]); ms8[0] = t;
-  for (int i = 1; i < 7; ++i) { cudaEventElapsedTime(&t, e->ev[i + 1], e->ev[i + 2]); ms8[i] = t; }
+  for (int i = 0; i < 8; ++i) ms8[i] = 0.0f;
+  if (e->profiling == 1) {
+    cudaEventElapsedTime(&t, e->ev[0], e->ev[2]); ms8[0] = t;
+    for (int i = 1; i < 7; ++i) { cudaEventElapsedTime(&t, e->ev[i + 1], e->ev[i + 2]); ms8[i] = t; }
+  }
   cudaEventElapsedTime(&t, e->ev[0], e->ev[8]); ms8[7] = t;
   return ITM_B200_OK;
 }

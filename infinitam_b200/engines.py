@@ -175,6 +175,7 @@ class ITMMainEngine:
         return n
 
     def set_profiling(self, on=True):
+        """True / 1: a time stamp at every stage boundary; 2: frame start and end only (no event nodes between the kernels)"""
         capi.check(self.lib.itm_b200_engine_set_profiling(self.h, int(on)))
 
     def stage_times(self):
