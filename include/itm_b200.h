@@ -323,7 +323,12 @@ int itm_b200_shard_owner_of_block(int x, int y, int z, int world);
  * work - e.g. producing the next depth frame on the device - before or after frames without a host synchronisation. */
 int itm_b200_engine_get_stream(itm_b200_engine *e, void **stream);
 
-/* Same frame, input already resident in HBM, enqueued asynchronously on the engine's stream. */
+/* Asynchronous device-to-device copy into one of the engine's buffers (ITM_B200_BUF_*), ordered on the engine's stream: e.g. a
+ * depth frame produced on the device placed into ITM_B200_BUF_RAW_DEPTH ahead of itm_b200_engine_enqueue_frame_dev(e, that buffer). */
+int itm_b200_engine_copy_to_buffer_dev(itm_b200_engine *e, int which, const void *src_dev, size_t bytes);
+
+/* Same frame, input already resident in HBM, enqueued asynchronously on the engine's stream.  raw_depth_dev may be the engine's
+ * own ITM_B200_BUF_RAW_DEPTH buffer (no copy then). */
 int itm_b200_engine_enqueue_frame_dev(itm_b200_engine *e, const short *raw_depth_dev);
 /* Wait for everything enqueued; counters = {noVisibleEntries, lastFreeBlockId,
  * lastFreeExcessListId, allocFailures, errorFlags, icpEvaluations of last frame}. */

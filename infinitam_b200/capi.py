@@ -112,7 +112,7 @@ SYMBOLS = [
     "itm_b200_forward_render", "itm_b200_find_visible_blocks", "itm_b200_find_surface", "itm_b200_render_image",
     "itm_b200_engine_get_image", "itm_b200_mesh_scene", "itm_b200_write_stl", "itm_b200_write_obj",
     "itm_b200_engine_mesh_scene", "itm_b200_engine_save_scene_to_mesh",
-    "itm_b200_take_cuda_error", "itm_b200_engine_get_stream", "itm_b200_compute_g_and_h_weighted", "itm_b200_depth_filtering", "itm_b200_compute_normal_and_weights", "itm_b200_swap_in_select", "itm_b200_swap_in_apply", "itm_b200_swap_out",
+    "itm_b200_take_cuda_error", "itm_b200_engine_get_stream", "itm_b200_engine_copy_to_buffer_dev", "itm_b200_compute_g_and_h_weighted", "itm_b200_depth_filtering", "itm_b200_compute_normal_and_weights", "itm_b200_swap_in_select", "itm_b200_swap_in_apply", "itm_b200_swap_out",
 ]
 
 _lib = None
@@ -182,6 +182,7 @@ def load():
     lib.itm_b200_engine_process_frame.argtypes = [vp, vp, vp, f32p]
     lib.itm_b200_engine_enqueue_frame_dev.argtypes = [vp, vp]
     lib.itm_b200_engine_get_stream.argtypes = [vp, C.POINTER(vp)]
+    lib.itm_b200_engine_copy_to_buffer_dev.argtypes = [vp, C.c_int, vp, C.c_size_t]
     lib.itm_b200_engine_sync.argtypes = [vp, f32p, i32p]
     lib.itm_b200_engine_upload_depth.argtypes = [vp, vp]
     lib.itm_b200_engine_run_stage.argtypes = [vp, C.c_int]

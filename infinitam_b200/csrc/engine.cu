@@ -1518,6 +1518,16 @@ int itm_b200_engine_process_frame(itm_b200_engine *e, const unsigned char *rgb_h
   return itm_b200_engine_sync(e, pose_out, nullptr);
 }
 
+int itm_b200_engine_copy_to_buffer_dev(itm_b200_engine *e, int which, const void *src_dev, size_t bytes) {
+  void *p = nullptr;
+  size_t total = 0;
+  int rc = itm_b200_engine_get_buffer(e, which, &p, &total);
+  if (rc) return rc;
+  if (!src_dev || bytes > total) return fail(ITM_B200_EINVAL, "copy_to_buffer_dev: range outside the buffer");
+  CU(cudaMemcpyAsync(p, src_dev, bytes, cudaMemcpyDeviceToDevice, e->c->stream));
+  return ITM_B200_OK;
+}
+
 int itm_b200_engine_get_stream(itm_b200_engine *e, void **stream) {
   if (!e || !stream) return fail(ITM_B200_EINVAL, "NULL argument");
   *stream = (void *)e->c->stream;

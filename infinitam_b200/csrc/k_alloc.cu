@@ -137,8 +137,9 @@ __global__ void __launch_bounds__(256) k_alloc_pixels(const float *__restrict__ 
 #endif
 #define SCAN_TILE (256 * SCAN_PER_THREAD)  // slots per CTA
 
-// Every thread owns 32 consecutive slots; 1.18 M slots are 144 tiles, i.e. one CTA per SM and a look-back chain of
-// at most 5 warp-wide windows (with 1024-slot tiles the chain was 36 windows long and dominated the kernel).
+// Every thread owns SCAN_PER_THREAD consecutive slots; at 32 the 1.18 M slots are 144 tiles, i.e. one CTA per SM (smaller
+// tiles - more CTAs, less serial work per thread - were measured slower).  A tile's offset is the sum of its predecessors'
+// published aggregates (scan_util.cuh).
 __global__ void __launch_bounds__(256) k_alloc_scan(unsigned *__restrict__ allocKey, HashEntry *__restrict__ table,
                                                     unsigned char *__restrict__ visType, const int *__restrict__ vbaAllocList,
                                                     const int *__restrict__ excessAllocList, const float *__restrict__ depth,

@@ -1,4 +1,4 @@
-// Single-pass ordered compaction helpers (decoupled look-back across tiles).
+// Single-pass ordered compaction helpers (tile aggregates published in tagged status words).
 //
 // The reference CPU engine walks all hash slots serially in ascending order and hands out
 // free-list entries / visible-list positions in that order
@@ -19,7 +19,6 @@ namespace itm {
 
 #define SCAN_STATUS_INVALID 0ull
 #define SCAN_STATUS_AGGREGATE 1ull
-#define SCAN_STATUS_PREFIX 2ull
 
 __device__ __forceinline__ unsigned long long scan_pack(unsigned long long status, unsigned epoch, unsigned a, unsigned b) {
   return (status << 62) | ((unsigned long long)(epoch & 0xFFFFFu) << 42) | ((unsigned long long)(a & 0x1FFFFFu) << 21) |

@@ -99,6 +99,12 @@ class ITMMainEngine:
     def EnqueueFrameDevice(self, raw_depth_dev_ptr: int):
         capi.check(self.lib.itm_b200_engine_enqueue_frame_dev(self.h, C.c_void_p(raw_depth_dev_ptr)))
 
+    def PlaceDepthDevice(self, raw_depth_dev_ptr: int):
+        """asynchronous D2D copy of a raw depth frame into the engine's own buffer; returns that buffer's device address (pass
+        it to EnqueueFrameDevice: the frame then starts without a copy)"""
+        capi.check(self.lib.itm_b200_engine_copy_to_buffer_dev(self.h, capi.BUF_RAW_DEPTH, C.c_void_p(raw_depth_dev_ptr), self.W * self.H * 2))
+        return self.buffer_info(capi.BUF_RAW_DEPTH)[0]
+
     def stream(self) -> int:
         """the cudaStream_t (as an integer) the engine enqueues its frames on, e.g. for torch.cuda.ExternalStream"""
         p = C.c_void_p()

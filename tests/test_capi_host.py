@@ -94,3 +94,30 @@ def test_host_pose_helpers_match_oracle():
             lib.itm_b200_compute_delta(_f(g), _f(np.ascontiguousarray(Hm.reshape(36))), short, _f(sc))
             assert np.array_equal(so, sc)
     o.close()
+
+
+def test_write_stl_obj_match_the_reference(tmp_path):
+    """itm_b200_write_stl / _write_obj are host-only entry points: on the triangle array of the reference's own MeshScene they
+    must write the very bytes ITMMesh::WriteSTL / WriteOBJ write (Objects/ITMMesh.h:34-118)"""
+    import filecmp
+
+    import numpy as np
+    import pytest
+
+    from infinitam_b200 import capi, synth
+    from oracle import ref
+    if not ref.available("parity"):
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    o = ref.RefEngine(160, 120)
+    o.process_frame(synth.sequence(1, 160, 120)[0])
+    tri = np.ascontiguousarray(o.mesh_scene()[:20000], dtype=np.float32)
+    o.lib.ref_write_stl(o.h, str(tmp_path / "ref_full.stl").encode())
+    lib = capi.load()
+    full = np.ascontiguousarray(o.mesh_scene(), dtype=np.float32)
+    capi.check(lib.itm_b200_write_stl(str(tmp_path / "ours.stl").encode(), full.ctypes.data, len(full)))
+    assert filecmp.cmp(tmp_path / "ref_full.stl", tmp_path / "ours.stl", shallow=False)
+    o.write_obj(tmp_path / "ref.obj")
+    capi.check(lib.itm_b200_write_obj(str(tmp_path / "ours.obj").encode(), full.ctypes.data, len(full)))
+    assert filecmp.cmp(tmp_path / "ref.obj", tmp_path / "ours.obj", shallow=False)
+    assert len(tri) > 1000
+    o.close()
