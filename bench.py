@@ -514,11 +514,13 @@ def run_ours(args):
         eng.ProcessFrame(rgb_pinned, frames_pinned[k])
     barrier()
     e2e_s = 0.0
+    rgb_addr = rgb_pinned.data_ptr()
+    frame_addr = [frames_pinned[k].data_ptr() for k in range(n)]  # host addresses of the pinned frames
     for k in range(args.warmup, n):
         flush.fill_(k & 0xFF)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        pose = eng.ProcessFrame(rgb_pinned, frames_pinned[k])
+        pose = eng.ProcessFrame(rgb_addr, frame_addr[k])
         e2e_s += time.perf_counter() - t0
     barrier()
     sampler.stop()

@@ -1507,6 +1507,12 @@ int itm_b200_engine_process_frame(itm_b200_engine *e, const unsigned char *rgb_h
   // returns only after view->rgb is complete.
   CU(cudaMemcpyAsync(e->rawDepth, raw_depth_host, P * 2, cudaMemcpyHostToDevice, s));
   if (rgb_host) {
+    // the depth image is on the frame's critical path, the (twice as large) colour image is not: it starts only when the
+    // depth copy has finished, so the two do not share the host link
+    if (e->c->sp.voxelWords != 2) {
+      CU(cudaEventRecord(e->forkEv, s));
+      CU(cudaStreamWaitEvent(e->copyStream, e->forkEv, 0));
+    }
     CU(cudaMemcpyAsync(e->rgb, rgb_host, P * 4, cudaMemcpyHostToDevice, e->copyStream));
     CU(cudaEventRecord(e->rgbDone, e->copyStream));
   }
