@@ -1,7 +1,8 @@
 /* oracle/itm_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
  *
  * A plain-C, single-threaded restatement of the reference's per-frame dense-fusion path
- * (view -> ICP tracking -> allocation -> integration -> expected depths -> raycast -> ICP maps),
+ * (view -> ICP tracking -> allocation -> integration -> expected depths -> raycast -> ICP maps) and of
+ * the rows next to it (ForwardRender / useApproximateRaycast, free-view FindVisibleBlocks + RenderImage, MeshScene),
  * written from the reference's algorithm with run-time pool sizes so that configurations the
  * reference can only reach by editing #defines (BASELINE configs[2]: 2 mm voxels, larger pools)
  * have an oracle too.  Every function cites the reference lines it restates.
@@ -9,7 +10,7 @@
  * Parity status: PINNED.  tests/test_oracle_port.py checks this file stage by stage and bit for
  * bit against the real reference CPU engines (oracle/_ref/libitm_ref.so, built from the unmodified
  * sources by oracle/build_ref.py) when that library is present, and against the golden vectors in
- * tests/golden/ (generated from the real reference by tests/golden/make_golden.py) everywhere.
+ * tests/golden/ (generated from the real reference by tests/golden/make_golden.py and make_golden_8f.py) everywhere.
  *
  * Build: gcc -O2 -ffp-contract=off -fPIC -shared (oracle/build_port.py).  No FMA contraction and no
  * -ffast-math: every float operation is a single IEEE fp32 operation in source order, which is what
@@ -74,6 +75,10 @@ typedef struct port_engine {
   int iters[MAX_LEVELS]; float dist_thresh[MAX_LEVELS];
   /* engine scratch */
   unsigned char *alloc_type; short *block_coords; /* Vector4s per slot */
+  /* ITMRenderState::forwardProjection / fwdProjMissingPoints, ITMMesh, renderState_freeview */
+  V4 *fwd; int *fwd_missing; int n_fwd_missing; int requires_full_rendering; int use_approximate_raycast;
+  float *mesh; int n_mesh;
+  int free_w, free_h; int *free_visible_ids; int free_n_visible; V2 *free_minmax; V4 *free_raycast; unsigned char *free_image;
 } port_engine;
 
 /* ------------------------------------------------------------------------------------------------
@@ -581,23 +586,24 @@ static void scene_integrate(port_engine *e) {
 /* CreateExpectedDepths (DeviceSpecific/CPU/ITMVisualisationEngine_CPU.cpp:94-152) with ProjectSingleBlock and
  * CreateRenderingBlocks (DeviceAgnostic/ITMVisualisationEngine.h:28-90).  The rendering-block list only splits the
  * bounding box into <=16x16 pieces; it is kept (as a counter) for its MAX_RENDERING_BLOCKS cut-off. */
-static void render_expected_depths(port_engine *e) {
+/* for any camera (pose M, intrinsics k = fx fy cx cy), image size and visible list: the live view and the free view share it */
+static void expected_depths_for(const port_engine *e, const float *M, const float *k, int W, int H, const int *visible_ids, int n_visible,
+                                V2 *minmax) {
   const port_params *p = &e->p;
-  const int W = p->width, H = p->height;
   int i, n, corner, x, y, numBlocks = 0;
-  for (i = 0; i < W * H; ++i) { e->minmax[i].x = FAR_AWAY; e->minmax[i].y = VERY_CLOSE; }
-  for (n = 0; n < e->n_visible; ++n) {
-    const HashEntry *h = &e->hash[e->visible_ids[n]];
+  for (i = 0; i < W * H; ++i) { minmax[i].x = FAR_AWAY; minmax[i].y = VERY_CLOSE; }
+  for (n = 0; n < n_visible; ++n) {
+    const HashEntry *h = &e->hash[visible_ids[n]];
     int ulx = W / MINMAX_SUB, uly = H / MINMAX_SUB, lrx = -1, lry = -1, need;
     float zmin = FAR_AWAY, zmax = VERY_CLOSE;
     if (h->ptr < 0) continue;
     for (corner = 0; corner < 8; ++corner) {
       const short tx = (short)(h->x + ((corner & 1) ? 1 : 0)), ty = (short)(h->y + ((corner & 2) ? 1 : 0)), tz = (short)(h->z + ((corner & 4) ? 1 : 0));
       float cx, cy, cz, px, py;
-      m4_apply(e->pose_M, (float)tx * (float)BLOCK * p->voxel_size, (float)ty * (float)BLOCK * p->voxel_size,
+      m4_apply(M, (float)tx * (float)BLOCK * p->voxel_size, (float)ty * (float)BLOCK * p->voxel_size,
                (float)tz * (float)BLOCK * p->voxel_size, 1.0f, &cx, &cy, &cz);
       if (cz < 1e-6) continue;
-      px = (p->fx * cx / cz + p->cx) / MINMAX_SUB; py = (p->fy * cy / cz + p->cy) / MINMAX_SUB;
+      px = (k[0] * cx / cz + k[2]) / MINMAX_SUB; py = (k[1] * cy / cz + k[3]) / MINMAX_SUB;
       if (ulx > floorf(px)) ulx = (int)floorf(px);
       if (lrx < ceilf(px)) lrx = (int)ceilf(px);
       if (uly > floorf(py)) uly = (int)floorf(py);
@@ -616,11 +622,16 @@ static void render_expected_depths(port_engine *e) {
     if (numBlocks + need >= MAX_RENDERING_BLOCKS) continue;
     numBlocks += need;
     for (y = uly; y <= lry; ++y) for (x = ulx; x <= lrx; ++x) {
-      V2 *px2 = &e->minmax[x + y * W];
+      V2 *px2 = &minmax[x + y * W];
       if (px2->x > zmin) px2->x = zmin;
       if (px2->y < zmax) px2->y = zmax;
     }
   }
+}
+
+static void render_expected_depths(port_engine *e) {
+  const float k[4] = {e->p.fx, e->p.fy, e->p.cx, e->p.cy};
+  expected_depths_for(e, e->pose_M, k, e->p.width, e->p.height, e->visible_ids, e->n_visible, e->minmax);
 }
 
 typedef struct { int bx, by, bz, base; } BlockCache; /* ITMVoxelBlockHash::IndexCache, Objects/ITMVoxelBlockHash.h:27-33 */
@@ -670,49 +681,56 @@ static float sdf_trilinear(const port_engine *e, float x, float y, float z, Bloc
   return ((1.0f - cz) * r1 + cz * r2) / 32767.0f;
 }
 
-/* castRay, DeviceAgnostic/ITMVisualisationEngine.h:93-158; GenericRaycast, ITMVisualisationEngine_CPU.cpp:155-188 */
-static void render_raycast(port_engine *e) {
+/* castRay, DeviceAgnostic/ITMVisualisationEngine.h:93-158: one pixel of a camera with inverse pose invM and intrinsics k */
+static void cast_ray(const port_engine *e, int x, int y, V2 mm, const float *invM, const float *k, V4 *out) {
   const port_params *p = &e->p;
-  const int W = p->width, H = p->height;
-  const float oneOverVoxel = 1.0f / p->voxel_size, invfx = 1.0f / p->fx, invfy = 1.0f / p->fy;
+  const float oneOverVoxel = 1.0f / p->voxel_size, invfx = 1.0f / k[0], invfy = 1.0f / k[1];
   const float stepScale = p->mu * oneOverVoxel;
+  float cz, cx, cy, len, lenMax, sx, sy, sz, ex, ey, ez, dx, dy, dz, kn, px, py, pz, sdf = 1.0f, step;
+  int found;
+  BlockCache cache;
+  cache.bx = cache.by = cache.bz = 0x7fffffff; cache.base = -1;
+  cz = mm.x; cx = cz * (((float)x - k[2]) * invfx); cy = cz * (((float)y - k[3]) * invfy);
+  len = sqrtf(cx * cx + cy * cy + cz * cz) * oneOverVoxel;
+  m4_apply(invM, cx, cy, cz, 1.0f, &sx, &sy, &sz); sx *= oneOverVoxel; sy *= oneOverVoxel; sz *= oneOverVoxel;
+  cz = mm.y; cx = cz * (((float)x - k[2]) * invfx); cy = cz * (((float)y - k[3]) * invfy);
+  lenMax = sqrtf(cx * cx + cy * cy + cz * cz) * oneOverVoxel;
+  m4_apply(invM, cx, cy, cz, 1.0f, &ex, &ey, &ez); ex *= oneOverVoxel; ey *= oneOverVoxel; ez *= oneOverVoxel;
+  dx = ex - sx; dy = ey - sy; dz = ez - sz;
+  kn = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+  dx *= kn; dy *= kn; dz *= kn;
+  px = sx; py = sy; pz = sz;
+  while (len < lenMax) {
+    sdf = sdf_nearest(e, px, py, pz, &found, &cache);
+    if (!found) step = BLOCK;
+    else {
+      if (sdf <= 0.1f && sdf >= -0.5f) sdf = sdf_trilinear(e, px, py, pz, &cache);
+      if (sdf <= 0.0f) break;
+      step = (sdf * stepScale < 1.0f) ? 1.0f : sdf * stepScale;
+    }
+    px += step * dx; py += step * dy; pz += step * dz; len += step;
+  }
+  if (sdf <= 0.0f) {
+    step = sdf * stepScale; px += step * dx; py += step * dy; pz += step * dz;
+    sdf = sdf_trilinear(e, px, py, pz, &cache);
+    step = sdf * stepScale; px += step * dx; py += step * dy; pz += step * dz;
+    out->w = 1.0f;
+  } else out->w = 0.0f;
+  out->x = px; out->y = py; out->z = pz;
+}
+
+/* GenericRaycast, ITMVisualisationEngine_CPU.cpp:155-188 */
+static void raycast_for(const port_engine *e, const float *M, const float *k, int W, int H, const V2 *minmax, V4 *out) {
   float invM[16];
   int x, y;
-  m4_inverse(e->pose_M, invM);
-  for (y = 0; y < H; ++y) for (x = 0; x < W; ++x) {
-    const V2 mm = e->minmax[(int)floorf((float)x / MINMAX_SUB) + (int)floorf((float)y / MINMAX_SUB) * W];
-    float cz, cx, cy, len, lenMax, sx, sy, sz, ex, ey, ez, dx, dy, dz, k, px, py, pz, sdf = 1.0f, step;
-    int found;
-    BlockCache cache; V4 *out = &e->raycast[x + y * W];
-    cache.bx = cache.by = cache.bz = 0x7fffffff; cache.base = -1;
-    cz = mm.x; cx = cz * (((float)x - p->cx) * invfx); cy = cz * (((float)y - p->cy) * invfy);
-    len = sqrtf(cx * cx + cy * cy + cz * cz) * oneOverVoxel;
-    m4_apply(invM, cx, cy, cz, 1.0f, &sx, &sy, &sz); sx *= oneOverVoxel; sy *= oneOverVoxel; sz *= oneOverVoxel;
-    cz = mm.y; cx = cz * (((float)x - p->cx) * invfx); cy = cz * (((float)y - p->cy) * invfy);
-    lenMax = sqrtf(cx * cx + cy * cy + cz * cz) * oneOverVoxel;
-    m4_apply(invM, cx, cy, cz, 1.0f, &ex, &ey, &ez); ex *= oneOverVoxel; ey *= oneOverVoxel; ez *= oneOverVoxel;
-    dx = ex - sx; dy = ey - sy; dz = ez - sz;
-    k = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
-    dx *= k; dy *= k; dz *= k;
-    px = sx; py = sy; pz = sz;
-    while (len < lenMax) {
-      sdf = sdf_nearest(e, px, py, pz, &found, &cache);
-      if (!found) step = BLOCK;
-      else {
-        if (sdf <= 0.1f && sdf >= -0.5f) sdf = sdf_trilinear(e, px, py, pz, &cache);
-        if (sdf <= 0.0f) break;
-        step = (sdf * stepScale < 1.0f) ? 1.0f : sdf * stepScale;
-      }
-      px += step * dx; py += step * dy; pz += step * dz; len += step;
-    }
-    if (sdf <= 0.0f) {
-      step = sdf * stepScale; px += step * dx; py += step * dy; pz += step * dz;
-      sdf = sdf_trilinear(e, px, py, pz, &cache);
-      step = sdf * stepScale; px += step * dx; py += step * dy; pz += step * dz;
-      out->w = 1.0f;
-    } else out->w = 0.0f;
-    out->x = px; out->y = py; out->z = pz;
-  }
+  m4_inverse(M, invM);
+  for (y = 0; y < H; ++y) for (x = 0; x < W; ++x)
+    cast_ray(e, x, y, minmax[(int)floorf((float)x / MINMAX_SUB) + (int)floorf((float)y / MINMAX_SUB) * W], invM, k, &out[x + y * W]);
+}
+
+static void render_raycast(port_engine *e) {
+  const float k[4] = {e->p.fx, e->p.fy, e->p.cx, e->p.cy};
+  raycast_for(e, e->pose_M, k, e->p.width, e->p.height, e->minmax, e->raycast);
 }
 
 /* CreateICPMaps_common (ITMVisualisationEngine_CPU.cpp:267-287) + processPixelICP<true> / computeNormalAndAngle<true>
@@ -781,6 +799,314 @@ static void render_icp_maps(port_engine *e) {
  * ---------------------------------------------------------------------------------------------- */
 
 /* ResetScene, ITMSceneReconstructionEngine_CPU.cpp:25-45 */
+/* ------------------------------------------------------------------------------------------------
+ * ForwardRender, free-view rendering, meshing
+ * ---------------------------------------------------------------------------------------------- */
+
+/* computeNormalAndAngle<useSmoothing = true>, DeviceAgnostic/ITMVisualisationEngine.h:192-253 */
+static int normal_from_points(const V4 *img, int x, int y, int W, int H, float vs, const float *light, float *n, float *angle) {
+  V4 xp, yp, xm, ym;
+  float ax = 0, ay = 0, az = 0, bx = 0, by = 0, bz = 0, la, lb, scale;
+  int plus1 = 0;
+  if (y <= 2 || y >= H - 3 || x <= 2 || x >= W - 3) return 0;
+  xp = img[(x + 2) + y * W]; yp = img[x + (y + 2) * W]; xm = img[(x - 2) + y * W]; ym = img[x + (y - 2) * W];
+  if (xp.w <= 0 || yp.w <= 0 || xm.w <= 0 || ym.w <= 0) plus1 = 1;
+  else {
+    ax = xp.x - xm.x; ay = xp.y - xm.y; az = xp.z - xm.z;
+    bx = yp.x - ym.x; by = yp.y - ym.y; bz = yp.z - ym.z;
+    la = ax * ax + ay * ay + az * az; lb = bx * bx + by * by + bz * bz;
+    if (((la < lb) ? lb : la) * vs * vs > (0.15f * 0.15f)) plus1 = 1;
+  }
+  if (plus1) {
+    xp = img[(x + 1) + y * W]; yp = img[x + (y + 1) * W]; xm = img[(x - 1) + y * W]; ym = img[x + (y - 1) * W];
+    ax = xp.x - xm.x; ay = xp.y - xm.y; az = xp.z - xm.z;
+    bx = yp.x - ym.x; by = yp.y - ym.y; bz = yp.z - ym.z;
+    if (xp.w <= 0 || yp.w <= 0 || xm.w <= 0 || ym.w <= 0) return 0;
+  }
+  n[0] = -(ay * bz - az * by); n[1] = -(az * bx - ax * bz); n[2] = -(ax * by - ay * bx);
+  scale = 1.0f / sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+  n[0] *= scale; n[1] *= scale; n[2] *= scale;
+  *angle = n[0] * light[0] + n[1] * light[1] + n[2] * light[2];
+  return (*angle > 0.0) ? 1 : 0;
+}
+
+/* ITMTrackingState::TrackerFarFromPointCloud, Objects/ITMTrackingState.h:41-59 */
+static int tracker_far_from_point_cloud(const port_engine *e) {
+  float ca[3], cb[3], d0, d1, d2;
+  const float *A = e->pose_pc_M, *B = e->pose_M;
+  int r;
+  if (e->age < 0) return 1;
+  if (e->age > 5) return 1;
+  for (r = 0; r < 3; ++r) {
+    ca[r] = -1.0f * (A[r * 4 + 0] * A[12] + A[r * 4 + 1] * A[13] + A[r * 4 + 2] * A[14]);
+    cb[r] = -1.0f * (B[r * 4 + 0] * B[12] + B[r * 4 + 1] * B[13] + B[r * 4 + 2] * B[14]);
+  }
+  d0 = ca[0] - cb[0]; d1 = ca[1] - cb[1]; d2 = ca[2] - cb[2];
+  return (d0 * d0 + d1 * d1 + d2 * d2 > 0.0005f) ? 1 : 0;
+}
+
+/* ForwardRender_common, ITMVisualisationEngine_CPU.cpp:289-354 (forwardProjectPixel, DeviceAgnostic/...VisualisationEngine.h:160-173;
+ * processPixelForwardRender<true> :351-366) */
+static void render_forward(port_engine *e) {
+  const port_params *p = &e->p;
+  const int W = p->width, H = p->height;
+  const float k[4] = {p->fx, p->fy, p->cx, p->cy};
+  float invM[16], light[3];
+  int x, y, n = 0, i;
+  m4_inverse(e->pose_M, invM);
+  light[0] = -invM[8]; light[1] = -invM[9]; light[2] = -invM[10];
+  memset(e->fwd, 0, (size_t)W * H * sizeof(V4));
+  for (y = 0; y < H; y++) for (x = 0; x < W; x++) {
+    const V4 pt = e->raycast[x + y * W];
+    float cx, cy, cz, ix, iy;
+    m4_apply(e->pose_M, pt.x * p->voxel_size, pt.y * p->voxel_size, pt.z * p->voxel_size, 1.0f, &cx, &cy, &cz);
+    ix = k[0] * cx / cz + k[2]; iy = k[1] * cy / cz + k[3];
+    if ((ix < 0) || (ix > W - 1) || (iy < 0) || (iy > H - 1)) continue;
+    if (ix != ix || iy != iy) continue; /* NaN: the reference's float -> int conversion yields a negative index */
+    e->fwd[(int)(ix + 0.5f) + (int)(iy + 0.5f) * W] = pt;
+  }
+  for (y = 0; y < H; y++) for (x = 0; x < W; x++) {
+    const int id = x + y * W;
+    const V4 f = e->fwd[id];
+    const V2 mm = e->minmax[(int)floorf((float)x / MINMAX_SUB) + (int)floorf((float)y / MINMAX_SUB) * W];
+    if ((f.w <= 0) && ((f.x == 0 && f.y == 0 && f.z == 0) || (e->depth[id] >= 0)) && (mm.x < mm.y)) e->fwd_missing[n++] = id;
+  }
+  e->n_fwd_missing = n;
+  for (i = 0; i < n; ++i) {
+    const int id = e->fwd_missing[i];
+    y = id / W; x = id - y * W;
+    cast_ray(e, x, y, e->minmax[(int)floorf((float)x / MINMAX_SUB) + (int)floorf((float)y / MINMAX_SUB) * W], invM, k, &e->fwd[id]);
+  }
+  for (y = 0; y < H; y++) for (x = 0; x < W; x++) {
+    const int id = x + y * W;
+    float nrm[3], angle = 0;
+    unsigned char g = 0;
+    if (e->fwd[id].w > 0.0f && normal_from_points(e->fwd, x, y, W, H, p->voxel_size, light, nrm, &angle)) g = (unsigned char)((0.8f * angle + 0.2f) * 255.0f);
+    e->raycast_image[id * 4 + 0] = g; e->raycast_image[id * 4 + 1] = g; e->raycast_image[id * 4 + 2] = g; e->raycast_image[id * 4 + 3] = g;
+  }
+}
+
+/* FindVisibleBlocks, ITMVisualisationEngine_CPU.cpp:40-77 (checkBlockVisibility<false> with the given camera) */
+static int find_visible_blocks(const port_engine *e, const float *M, const float *k, int W, int H, int *ids) {
+  port_engine cam = *e;  /* block_visible reads pose and intrinsics from the engine: a by-value view with the free camera */
+  int i, n = 0;
+  memcpy(cam.pose_M, M, 64);
+  cam.p.fx = k[0]; cam.p.fy = k[1]; cam.p.cx = k[2]; cam.p.cy = k[3]; cam.p.width = W; cam.p.height = H;
+  for (i = 0; i < e->n_entries; ++i)
+    if (e->hash[i].ptr >= 0 && block_visible(&cam, &e->hash[i])) ids[n++] = i;
+  return n;
+}
+
+/* computeSingleNormalFromSDF, DeviceAgnostic/ITMRepresentationAccess.h:225-337 */
+static void normal_from_sdf(const port_engine *e, float px, float py, float pz, float *r) {
+  const float flx = floorf(px), fly = floorf(py), flz = floorf(pz);
+  const float cx = px - flx, cy = py - fly, cz = pz - flz;
+  const float ncx = 1.0f - cx, ncy = 1.0f - cy, ncz = 1.0f - cz;
+  const int x = (int)flx, y = (int)fly, z = (int)flz;
+  BlockCache c;
+  int f;
+  float fr[4], bk[4], t[4], p1, p2, v1;
+  c.bx = c.by = c.bz = 0x7fffffff; c.base = -1;
+#define S(dx, dy, dz) ((float)voxel_sdf(e, x + (dx), y + (dy), z + (dz), &f, &c))
+  fr[0] = S(0, 0, 0); fr[1] = S(1, 0, 0); fr[2] = S(0, 1, 0); fr[3] = S(1, 1, 0);
+  bk[0] = S(0, 0, 1); bk[1] = S(1, 0, 1); bk[2] = S(0, 1, 1); bk[3] = S(1, 1, 1);
+  p1 = fr[0] * ncy * ncz + fr[2] * cy * ncz + bk[0] * ncy * cz + bk[2] * cy * cz;
+  t[0] = S(-1, 0, 0); t[1] = S(-1, 1, 0); t[2] = S(-1, 0, 1); t[3] = S(-1, 1, 1);
+  p2 = t[0] * ncy * ncz + t[1] * cy * ncz + t[2] * ncy * cz + t[3] * cy * cz;
+  v1 = p1 * cx + p2 * ncx;
+  p1 = fr[1] * ncy * ncz + fr[3] * cy * ncz + bk[1] * ncy * cz + bk[3] * cy * cz;
+  t[0] = S(2, 0, 0); t[1] = S(2, 1, 0); t[2] = S(2, 0, 1); t[3] = S(2, 1, 1);
+  p2 = t[0] * ncy * ncz + t[1] * cy * ncz + t[2] * ncy * cz + t[3] * cy * cz;
+  r[0] = (p1 * ncx + p2 * cx - v1) / 32767.0f;
+  p1 = fr[0] * ncx * ncz + fr[1] * cx * ncz + bk[0] * ncx * cz + bk[1] * cx * cz;
+  t[0] = S(0, -1, 0); t[1] = S(1, -1, 0); t[2] = S(0, -1, 1); t[3] = S(1, -1, 1);
+  p2 = t[0] * ncx * ncz + t[1] * cx * ncz + t[2] * ncx * cz + t[3] * cx * cz;
+  v1 = p1 * cy + p2 * ncy;
+  p1 = fr[2] * ncx * ncz + fr[3] * cx * ncz + bk[2] * ncx * cz + bk[3] * cx * cz;
+  t[0] = S(0, 2, 0); t[1] = S(1, 2, 0); t[2] = S(0, 2, 1); t[3] = S(1, 2, 1);
+  p2 = t[0] * ncx * ncz + t[1] * cx * ncz + t[2] * ncx * cz + t[3] * cx * cz;
+  r[1] = (p1 * ncy + p2 * cy - v1) / 32767.0f;
+  p1 = fr[0] * ncx * ncy + fr[1] * cx * ncy + fr[2] * ncx * cy + fr[3] * cx * cy;
+  t[0] = S(0, 0, -1); t[1] = S(1, 0, -1); t[2] = S(0, 1, -1); t[3] = S(1, 1, -1);
+  p2 = t[0] * ncx * ncy + t[1] * cx * ncy + t[2] * ncx * cy + t[3] * cx * cy;
+  v1 = p1 * cz + p2 * ncz;
+  p1 = bk[0] * ncx * ncy + bk[1] * cx * ncy + bk[2] * ncx * cy + bk[3] * cx * cy;
+  t[0] = S(0, 0, 2); t[1] = S(1, 0, 2); t[2] = S(0, 1, 2); t[3] = S(1, 1, 2);
+  p2 = t[0] * ncx * ncy + t[1] * cx * ncy + t[2] * ncx * cy + t[3] * cx * cy;
+  r[2] = (p1 * ncz + p2 * cz - v1) / 32767.0f;
+#undef S
+}
+
+/* the free-view branch of ITMMainEngine::GetImage (ITMMainEngine.cpp:167-186): FindVisibleBlocks + CreateExpectedDepths +
+ * RenderImage_common (ITMVisualisationEngine_CPU.cpp:191-240; processPixelGrey / processPixelNormal,
+ * DeviceAgnostic/ITMVisualisationEngine.h:368-410).  renderType 0 grey, 2 colour from normal (ITMVoxel_s has no colour: 1 = grey) */
+static void render_free_view(port_engine *e, int renderType, const float *M, const float *k, int W, int H) {
+  float invM[16], light[3];
+  int i;
+  if (e->free_w != W || e->free_h != H) {
+    free(e->free_visible_ids); free(e->free_minmax); free(e->free_raycast); free(e->free_image);
+    e->free_visible_ids = (int *)calloc((size_t)e->n_entries, sizeof(int));
+    e->free_minmax = (V2 *)calloc((size_t)W * H, sizeof(V2));
+    e->free_raycast = (V4 *)calloc((size_t)W * H, sizeof(V4));
+    e->free_image = (unsigned char *)calloc((size_t)W * H, 4);
+    e->free_w = W; e->free_h = H;
+  }
+  e->free_n_visible = find_visible_blocks(e, M, k, W, H, e->free_visible_ids);
+  expected_depths_for(e, M, k, W, H, e->free_visible_ids, e->free_n_visible, e->free_minmax);
+  raycast_for(e, M, k, W, H, e->free_minmax, e->free_raycast);
+  m4_inverse(M, invM);
+  light[0] = -invM[8]; light[1] = -invM[9]; light[2] = -invM[10];
+  for (i = 0; i < W * H; ++i) {
+    const V4 pt = e->free_raycast[i];
+    unsigned char *o = e->free_image + (size_t)i * 4;
+    int found = pt.w > 0;
+    float n[3], angle = 0;
+    if (found) {
+      float scale;
+      normal_from_sdf(e, pt.x, pt.y, pt.z, n);
+      scale = 1.0f / sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+      n[0] *= scale; n[1] *= scale; n[2] *= scale;
+      angle = n[0] * light[0] + n[1] * light[1] + n[2] * light[2];
+      if (!(angle > 0.0)) found = 0;
+    }
+    if (!found) { o[0] = o[1] = o[2] = o[3] = 0; }
+    else if (renderType == 2) {  /* drawPixelNormal leaves the alpha byte as it was */
+      o[0] = (unsigned char)((0.3f + (-n[0] + 1.0f) * 0.35f) * 255.0f);
+      o[1] = (unsigned char)((0.3f + (-n[1] + 1.0f) * 0.35f) * 255.0f);
+      o[2] = (unsigned char)((0.3f + (-n[2] + 1.0f) * 0.35f) * 255.0f);
+    } else {
+      const unsigned char g = (unsigned char)((0.8f * angle + 0.2f) * 255.0f);
+      o[0] = o[1] = o[2] = o[3] = g;
+    }
+  }
+}
+
+/* The marching-cubes case table (the classic Lorensen-Cline / Bourke triangulation the reference uses,
+ * DeviceAgnostic/ITMMeshingEngine.h:9-151), one 64-bit word per case: nibble i = i-th edge index, 0xF terminates. */
+static const unsigned long long MC_CASE[256] = {
+    0xFFFFFFFFFFFFFFFFULL, 0xFFFFFFFFFFFFF380ULL, 0xFFFFFFFFFFFFF910ULL, 0xFFFFFFFFFF189381ULL,
+    0xFFFFFFFFFFFFFA21ULL, 0xFFFFFFFFFFA21380ULL, 0xFFFFFFFFFF920A29ULL, 0xFFFFFFF89A8A2382ULL,
+    0xFFFFFFFFFFFFF2B3ULL, 0xFFFFFFFFFF0B82B0ULL, 0xFFFFFFFFFFB32091ULL, 0xFFFFFFFB89B912B1ULL,
+    0xFFFFFFFFFF3AB1A3ULL, 0xFFFFFFFAB8A801A0ULL, 0xFFFFFFF9AB9B3093ULL, 0xFFFFFFFFFFB8AA89ULL,
+    0xFFFFFFFFFFFFF874ULL, 0xFFFFFFFFFF437034ULL, 0xFFFFFFFFFF748910ULL, 0xFFFFFFF137174914ULL,
+    0xFFFFFFFFFF748A21ULL, 0xFFFFFFFA21403743ULL, 0xFFFFFFF748209A29ULL, 0xFFFF4973727929A2ULL,
+    0xFFFFFFFFFF2B3748ULL, 0xFFFFFFF40242B74BULL, 0xFFFFFFFB32748109ULL, 0xFFFF1292B9B49B74ULL,
+    0xFFFFFFF487AB31A3ULL, 0xFFFF4B7401B41AB1ULL, 0xFFFF30BAB9B09874ULL, 0xFFFFFFFAB99B4B74ULL,
+    0xFFFFFFFFFFFFF459ULL, 0xFFFFFFFFFF380459ULL, 0xFFFFFFFFFF051450ULL, 0xFFFFFFF513538458ULL,
+    0xFFFFFFFFFF459A21ULL, 0xFFFFFFF594A21803ULL, 0xFFFFFFF204245A25ULL, 0xFFFF8434535235A2ULL,
+    0xFFFFFFFFFFB32459ULL, 0xFFFFFFF594B802B0ULL, 0xFFFFFFFB32510450ULL, 0xFFFF584B82852512ULL,
+    0xFFFFFFF45931AB3AULL, 0xFFFFAB81A8180594ULL, 0xFFFF30BAB5B05045ULL, 0xFFFFFFFB8AA85845ULL,
+    0xFFFFFFFFFF975879ULL, 0xFFFFFFF375359039ULL, 0xFFFFFFF751710870ULL, 0xFFFFFFFFFF753351ULL,
+    0xFFFFFFF21A759879ULL, 0xFFFF37503505921AULL, 0xFFFF25A758528208ULL, 0xFFFFFFF7533525A2ULL,
+    0xFFFFFFF2B3987597ULL, 0xFFFFB72029279759ULL, 0xFFFF751871810B32ULL, 0xFFFFFFF51771B12BULL,
+    0xFFFFB3A31A758859ULL, 0xF0ABA010B7905075ULL, 0xF07570805A30B0ABULL, 0xFFFFFFFFFF5B75ABULL,
+    0xFFFFFFFFFFFFF56AULL, 0xFFFFFFFFFF6A5380ULL, 0xFFFFFFFFFF6A5109ULL, 0xFFFFFFF6A5891381ULL,
+    0xFFFFFFFFFF162561ULL, 0xFFFFFFF803621561ULL, 0xFFFFFFF620609569ULL, 0xFFFF823625285895ULL,
+    0xFFFFFFFFFF56AB32ULL, 0xFFFFFFF56A02B80BULL, 0xFFFFFFF6A5B32910ULL, 0xFFFFB892B92916A5ULL,
+    0xFFFFFFF315356B36ULL, 0xFFFF6B51505B0B80ULL, 0xFFFF9505606306B3ULL, 0xFFFFFFF89BB96956ULL,
+    0xFFFFFFFFFF8746A5ULL, 0xFFFFFFFA56374034ULL, 0xFFFFFFF7486A5091ULL, 0xFFFF49737179156AULL,
+    0xFFFFFFF874156216ULL, 0xFFFF743403625521ULL, 0xFFFF620560509748ULL, 0xF962695923497937ULL,
+    0xFFFFFFF56A4872B3ULL, 0xFFFFB720242746A5ULL, 0xFFFF6A5B32874910ULL, 0xF6A54B7B492B9129ULL,
+    0xFFFF6B51535B3748ULL, 0xFB404B7B016B5B15ULL, 0xF74836B630560950ULL, 0xFFFF9B7974B96956ULL,
+    0xFFFFFFFFFFA4694AULL, 0xFFFFFFF380A946A4ULL, 0xFFFFFFF04606A10AULL, 0xFFFFA16468618138ULL,
+    0xFFFFFFF462421941ULL, 0xFFFF462942921803ULL, 0xFFFFFFFFFF624420ULL, 0xFFFFFFF624428238ULL,
+    0xFFFFFFF32B46A94AULL, 0xFFFF6A4A94B82280ULL, 0xFFFFA164606102B3ULL, 0xF1B8B12184A16146ULL,
+    0xFFFF36B319639469ULL, 0xF14641916B0181B8ULL, 0xFFFFFFF4600636B3ULL, 0xFFFFFFFFFF86B846ULL,
+    0xFFFFFFFA98A876A7ULL, 0xFFFFA76A907A0370ULL, 0xFFFF0818717A176AULL, 0xFFFFFFF37117A76AULL,
+    0xFFFF768981861621ULL, 0xF937390976192962ULL, 0xFFFFFFF206607087ULL, 0xFFFFFFFFFF276237ULL,
+    0xFFFF76898A86AB32ULL, 0xF7A9A76790B72702ULL, 0xFB32A767A1871081ULL, 0xFFFF17616A71B12BULL,
+    0xF63136B619768698ULL, 0xFFFFFFFFFF76B190ULL, 0xFFFF06B0B3607087ULL, 0xFFFFFFFFFFFFF6B7ULL,
+    0xFFFFFFFFFFFFFB67ULL, 0xFFFFFFFFFF67B803ULL, 0xFFFFFFFFFF67B910ULL, 0xFFFFFFF67B138918ULL,
+    0xFFFFFFFFFF7B621AULL, 0xFFFFFFF7B6803A21ULL, 0xFFFFFFF7B69A2092ULL, 0xFFFF89A38A3A27B6ULL,
+    0xFFFFFFFFFF726327ULL, 0xFFFFFFF026067807ULL, 0xFFFFFFF910732672ULL, 0xFFFF678891681261ULL,
+    0xFFFFFFF73171A67AULL, 0xFFFF801781A7167AULL, 0xFFFF7A69A0A70730ULL, 0xFFFFFFF9A88A7A67ULL,
+    0xFFFFFFFFFF68B486ULL, 0xFFFFFFF640603B63ULL, 0xFFFFFFF109648B68ULL, 0xFFFF63B139369649ULL,
+    0xFFFFFFF1A28B6486ULL, 0xFFFF640B60B03A21ULL, 0xFFFF9A2920B648B4ULL, 0xF36463B34923A39AULL,
+    0xFFFFFFF264248328ULL, 0xFFFFFFFFFF264240ULL, 0xFFFF834642432091ULL, 0xFFFFFFF642241491ULL,
+    0xFFFF1A6648168318ULL, 0xFFFFFFF40660A01AULL, 0xF39A9303A6834364ULL, 0xFFFFFFFFFF4A649AULL,
+    0xFFFFFFFFFFB67594ULL, 0xFFFFFFF67B594380ULL, 0xFFFFFFFB67045105ULL, 0xFFFF51345343867BULL,
+    0xFFFFFFFB6721A459ULL, 0xFFFF594380A217B6ULL, 0xFFFF204A24A45B67ULL, 0xF67B25A523453843ULL,
+    0xFFFFFFF945267327ULL, 0xFFFF786260680459ULL, 0xFFFF045051673263ULL, 0xF851584812786826ULL,
+    0xFFFF73167161A459ULL, 0xF459078701671A61ULL, 0xFA737A6A305A4A04ULL, 0xFFFFA84A458A7A67ULL,
+    0xFFFFFFF98B9B6596ULL, 0xFFFF590650360B63ULL, 0xFFFFB65510B508B0ULL, 0xFFFFFFF1355363B6ULL,
+    0xFFFF65B8B9B59A21ULL, 0xFA21965690B603B0ULL, 0xF52025A50865B58BULL, 0xFFFF35A3A25363B6ULL,
+    0xFFFF283265825985ULL, 0xFFFFFFF260069659ULL, 0xF826283865081851ULL, 0xFFFFFFFFFF612651ULL,
+    0xF698965683A61631ULL, 0xFFFF06505960A01AULL, 0xFFFFFFFFFFA65830ULL, 0xFFFFFFFFFFFFF65AULL,
+    0xFFFFFFFFFFB57A5BULL, 0xFFFFFFF03857BA5BULL, 0xFFFFFFF091BA57B5ULL, 0xFFFF1381897BA57AULL,
+    0xFFFFFFF15717B21BULL, 0xFFFFB27571721380ULL, 0xFFFF7B2209729579ULL, 0xF289823295B27257ULL,
+    0xFFFFFFF573532A52ULL, 0xFFFF52A578258028ULL, 0xFFFF2A37353A5109ULL, 0xF25752A278129289ULL,
+    0xFFFFFFFFFF573531ULL, 0xFFFFFFF571170780ULL, 0xFFFFFFF735539309ULL, 0xFFFFFFFFFF795789ULL,
+    0xFFFFFFF8BA8A5485ULL, 0xFFFF03BBA50B5405ULL, 0xFFFF54ABA8A48910ULL, 0xF41314943B54A4BAULL,
+    0xFFFF8548B2582152ULL, 0xFB151B2B543B0B40ULL, 0xF58B8545B2950520ULL, 0xFFFFFFFFFF3B2549ULL,
+    0xFFFF483543253A52ULL, 0xFFFFFFF0244252A5ULL, 0xF910854583A532A3ULL, 0xFFFF2492914252A5ULL,
+    0xFFFFFFF153358548ULL, 0xFFFFFFFFFF501540ULL, 0xFFFF530509358548ULL, 0xFFFFFFFFFFFFF549ULL,
+    0xFFFFFFFBA9B947B4ULL, 0xFFFFBA97B9794380ULL, 0xFFFFB470414B1BA1ULL, 0xF4BAB474A1843413ULL,
+    0xFFFF219B294B97B4ULL, 0xF3801B2B197B9479ULL, 0xFFFFFFF04224B47BULL, 0xFFFF42343824B47BULL,
+    0xFFFF947732972A92ULL, 0xF70207872A4797A9ULL, 0xFA040A1A472A3A73ULL, 0xFFFFFFFFFF4782A1ULL,
+    0xFFFFFFF317714194ULL, 0xFFFF178180714194ULL, 0xFFFFFFFFFF347304ULL, 0xFFFFFFFFFFFFF784ULL,
+    0xFFFFFFFFFF8BA8A9ULL, 0xFFFFFFFA9BB93903ULL, 0xFFFFFFFBA88A0A10ULL, 0xFFFFFFFFFFA3BA13ULL,
+    0xFFFFFFF8B99B1B21ULL, 0xFFFF9B2921B93903ULL, 0xFFFFFFFFFFB08B20ULL, 0xFFFFFFFFFFFFFB23ULL,
+    0xFFFFFFF98AA82832ULL, 0xFFFFFFFFFF2902A9ULL, 0xFFFF8A1810A82832ULL, 0xFFFFFFFFFFFFF2A1ULL,
+    0xFFFFFFFFFF819831ULL, 0xFFFFFFFFFFFFF190ULL, 0xFFFFFFFFFFFFF830ULL, 0xFFFFFFFFFFFFFFFFULL,
+};
+
+/* ITMMeshingEngine_CPU::MeshScene, ITMMeshingEngine_CPU.cpp:19-58 (findPointNeighbors / sdfInterp / buildVertList,
+ * DeviceAgnostic/ITMMeshingEngine.h:153-232) */
+static void mesh_scene(port_engine *e) {
+  static const int CX[8] = {0, 1, 1, 0, 0, 1, 1, 0}, CY[8] = {0, 0, 1, 1, 0, 0, 1, 1}, CZ[8] = {0, 0, 0, 0, 1, 1, 1, 1};
+  static const int EA[12] = {0, 1, 2, 3, 4, 5, 6, 7, 0, 1, 2, 3}, EB[12] = {1, 2, 3, 0, 5, 6, 7, 4, 4, 5, 6, 7};
+  const int noMax = e->p.n_local * 32;
+  const float factor = e->p.voxel_size;
+  int entry, x, y, z, n = 0;
+  if (!e->mesh) e->mesh = (float *)malloc((size_t)noMax * 9 * sizeof(float));
+  memset(e->mesh, 0, (size_t)noMax * 9 * sizeof(float));
+  for (entry = 0; entry < e->n_entries; ++entry) {
+    const HashEntry *h = &e->hash[entry];
+    if (h->ptr < 0) continue;
+    for (z = 0; z < BLOCK; z++) for (y = 0; y < BLOCK; y++) for (x = 0; x < BLOCK; x++) {
+      const int gx = h->x * BLOCK + x, gy = h->y * BLOCK + y, gz = h->z * BLOCK + z;
+      float pts[8][3], sdf[8], vert[12][3];
+      unsigned long long tris;
+      int kk, cube = 0, ok = 1, edges = 0;
+      BlockCache c;
+      c.bx = c.by = c.bz = 0x7fffffff; c.base = -1;
+      for (kk = 0; kk < 8; ++kk) {
+        int found;
+        pts[kk][0] = (float)(gx + CX[kk]); pts[kk][1] = (float)(gy + CY[kk]); pts[kk][2] = (float)(gz + CZ[kk]);
+        sdf[kk] = (float)voxel_sdf(e, gx + CX[kk], gy + CY[kk], gz + CZ[kk], &found, &c) / 32767.0f;
+        if (!found || sdf[kk] == 1.0f) { ok = 0; break; }
+      }
+      if (!ok) continue;
+      for (kk = 0; kk < 8; ++kk) if (sdf[kk] < 0) cube |= 1 << kk;
+      tris = MC_CASE[cube];
+      { unsigned long long t = tris; while ((t & 0xF) != 0xF) { edges |= 1 << (int)(t & 0xF); t >>= 4; } }
+      if (edges == 0) continue;
+      for (kk = 0; kk < 12; ++kk) {
+        const float *p1 = pts[EA[kk]], *p2 = pts[EB[kk]];
+        const float v1 = sdf[EA[kk]], v2 = sdf[EB[kk]];
+        if (!(edges & (1 << kk))) continue;
+        if (fabs(0.0f - v1) < 0.00001f) { vert[kk][0] = p1[0]; vert[kk][1] = p1[1]; vert[kk][2] = p1[2]; }
+        else if (fabs(0.0f - v2) < 0.00001f) { vert[kk][0] = p2[0]; vert[kk][1] = p2[1]; vert[kk][2] = p2[2]; }
+        else if (fabs(v1 - v2) < 0.00001f) { vert[kk][0] = p1[0]; vert[kk][1] = p1[1]; vert[kk][2] = p1[2]; }
+        else {
+          const float t = (0.0f - v1) / (v2 - v1);
+          vert[kk][0] = p1[0] + t * (p2[0] - p1[0]); vert[kk][1] = p1[1] + t * (p2[1] - p1[1]); vert[kk][2] = p1[2] + t * (p2[2] - p1[2]);
+        }
+      }
+      while ((tris & 0xF) != 0xF) {
+        float *o = e->mesh + (size_t)n * 9;
+        for (kk = 0; kk < 3; ++kk) {
+          const int ed = (int)((tris >> (4 * kk)) & 0xF);
+          o[kk * 3 + 0] = vert[ed][0] * factor; o[kk * 3 + 1] = vert[ed][1] * factor; o[kk * 3 + 2] = vert[ed][2] * factor;
+        }
+        if (n < noMax - 1) n++;
+        tris >>= 12;
+      }
+    }
+  }
+  e->n_mesh = n;
+}
+
 static void scene_reset(port_engine *e) {
   const size_t nv = (size_t)e->p.n_local * BLOCK3;
   size_t i;
@@ -829,6 +1155,9 @@ port_engine *port_create(const port_params *pp) {
   e->normals = (V4 *)calloc(P, sizeof(V4));
   e->raw = (short *)calloc(P, sizeof(short));
   e->depth = (float *)calloc(P, sizeof(float));
+  e->fwd = (V4 *)calloc(P, sizeof(V4));
+  e->fwd_missing = (int *)calloc(P, sizeof(int));
+  e->requires_full_rendering = 1;
   e->alloc_type = (unsigned char *)calloc((size_t)e->n_entries, 1);
   e->block_coords = (short *)calloc((size_t)e->n_entries * 4, sizeof(short));
   /* ITMRenderState constructor fills the range image with the frustum limits (Objects/ITMRenderState.h:60-72) */
@@ -858,6 +1187,7 @@ void port_destroy(port_engine *e) {
   free(e->voxels); free(e->hash); free(e->vba_list); free(e->excess_list); free(e->visible_ids); free(e->visible_type);
   free(e->minmax); free(e->raycast); free(e->raycast_image); free(e->points); free(e->normals); free(e->raw); free(e->depth);
   free(e->alloc_type); free(e->block_coords);
+  free(e->fwd); free(e->fwd_missing); free(e->mesh); free(e->free_visible_ids); free(e->free_minmax); free(e->free_raycast); free(e->free_image);
   free(e);
 }
 
@@ -866,23 +1196,54 @@ void port_update_view(port_engine *e, const short *depth) {
   view_convert(e);
 }
 /* ITMTrackingController::Track, ITMTrackingController.cpp:11-16 */
-void port_track(port_engine *e) { if (e->age != -1) icp_track(e); }
+/* ITMTrackingController::Track, ITMTrackingController.cpp:11-16 */
+void port_track(port_engine *e) {
+  if (e->age != -1) icp_track(e);
+  e->requires_full_rendering = tracker_far_from_point_cloud(e) || !e->use_approximate_raycast;
+}
 void port_allocate(port_engine *e, int onlyVisible) { scene_allocate(e, onlyVisible); }
 void port_integrate(port_engine *e) { scene_integrate(e); }
 void port_expected_depths(port_engine *e) { render_expected_depths(e); }
 void port_icp_maps(port_engine *e) { render_icp_maps(e); }
 /* ITMMainEngine::ProcessFrame, ITMMainEngine.cpp:111-127 */
+void port_prepare(port_engine *e);
+
 void port_process_frame(port_engine *e, const short *depth) {
   port_update_view(e, depth);
   port_track(e);
   scene_allocate(e, 0);
   scene_integrate(e);
-  render_expected_depths(e);
-  render_icp_maps(e);
+  port_prepare(e);
 }
 
-/* ITMTrackingController::Prepare, ITMTrackingController.cpp:18-46 (ICP tracker, full rendering) */
-void port_prepare(port_engine *e) { render_expected_depths(e); render_icp_maps(e); }
+/* ITMTrackingController::Prepare, ITMTrackingController.cpp:18-46 (depth trackers) */
+void port_prepare(port_engine *e) {
+  render_expected_depths(e);
+  if (e->requires_full_rendering) render_icp_maps(e);
+  else { render_forward(e); e->age++; }
+}
+void port_set_use_approximate_raycast(port_engine *e, int on) { e->use_approximate_raycast = on != 0; }
+int port_requires_full_rendering(port_engine *e) { return e->requires_full_rendering; }
+void port_forward_render(port_engine *e) { render_forward(e); e->age++; }
+float *port_forward_projection(port_engine *e) { return (float *)e->fwd; }
+int *port_fwd_missing_points(port_engine *e) { return e->fwd_missing; }
+int port_no_fwd_missing_points(port_engine *e) { return e->n_fwd_missing; }
+int port_mesh_scene(port_engine *e, float **triangles, int *noMaxTriangles) {
+  mesh_scene(e);
+  *triangles = e->mesh; *noMaxTriangles = e->p.n_local * 32;
+  return e->n_mesh;
+}
+/* free-view image types of ITMMainEngine::GetImage: 3 shaded, 4 colour from volume (= shaded for ITMVoxel_s), 5 colour from normal */
+int port_get_image(port_engine *e, int type, const float *M, const float *k, int w, int h, unsigned char *out) {
+  if (type < 3 || type > 5) return -2;
+  render_free_view(e, type == 5 ? 2 : 0, M, k, w, h);
+  memcpy(out, e->free_image, (size_t)w * h * 4);
+  return 0;
+}
+int *port_free_visible_ids(port_engine *e) { return e->free_visible_ids; }
+int port_free_no_visible(port_engine *e) { return e->free_n_visible; }
+float *port_free_minmax(port_engine *e) { return (float *)e->free_minmax; }
+float *port_free_raycast_result(port_engine *e) { return (float *)e->free_raycast; }
 
 static double now_ms(void) {
   struct timespec ts;

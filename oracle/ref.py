@@ -99,10 +99,11 @@ def declare_common(lib):
     if _has(lib, "ref_mesh_scene"):
         lib.ref_mesh_scene.argtypes = [C.c_void_p, C.POINTER(_f32p), _i32p]
         lib.ref_mesh_scene.restype = C.c_int
-        lib.ref_write_stl.argtypes = [C.c_void_p, C.c_char_p]
-        lib.ref_write_stl.restype = None
-        lib.ref_write_obj.argtypes = [C.c_void_p, C.c_char_p]
-        lib.ref_write_obj.restype = None
+        if _has(lib, "ref_write_stl"):  # the C restatement has no file writers
+            lib.ref_write_stl.argtypes = [C.c_void_p, C.c_char_p]
+            lib.ref_write_stl.restype = None
+            lib.ref_write_obj.argtypes = [C.c_void_p, C.c_char_p]
+            lib.ref_write_obj.restype = None
     if _has(lib, "ref_set_tracker_wicp"):
         lib.ref_set_tracker_wicp.argtypes = [C.c_int, C.c_int]
         lib.ref_set_tracker_wicp.restype = None

@@ -119,3 +119,74 @@ def test_pose_math_matches_reference():
         for x, y in zip(ra, rb):
             assert np.array_equal(x, y)
     a.close(); b.close()
+
+
+# ---- SURVEY 8f rows of the restatement: ForwardRender / useApproximateRaycast, free-view rendering, meshing -----------------
+
+def _free_pose(k):
+    M = np.eye(4, dtype=np.float32)
+    a = np.float32(np.deg2rad(6.0 + 4.0 * k))
+    M[0, 0], M[0, 2], M[2, 0], M[2, 2] = np.cos(a), np.sin(a), -np.sin(a), np.cos(a)
+    M[:3, 3] = [0.1, -0.04 + 0.02 * k, 0.06]
+    return M.T.reshape(16).astype(np.float32)
+
+
+@pytest.mark.skipif(not ref.available("parity"), reason="oracle/_ref not built (needs /root/reference at build time)")
+def test_port_rows_8f_equal_the_reference():
+    """approximate-raycast sequence (the full / approximate decision, forward projection, missing-point list, forward-rendered
+    image), free-view images with their visible lists / ranges / raycasts, and the mesh: bit for bit"""
+    w, h, n = 160, 120, 8
+    seq = synth.sequence(n, w, h, noise=True)
+    r, p = ref.RefEngine(w, h), port.PortEngine(w, h)
+    r.set_use_approximate_raycast(True)
+    p.set_use_approximate_raycast(True)
+    n_fwd = 0
+    for k in range(n):
+        r.process_frame(seq[k])
+        p.process_frame(seq[k])
+        assert np.array_equal(p.pose_M, r.pose_M), "frame %d pose" % k
+        assert p.requires_full_rendering == r.requires_full_rendering and p.age == r.age
+        assert np.array_equal(p.raycast_image, r.raycast_image), "frame %d raycast image" % k
+        if not r.requires_full_rendering:
+            n_fwd += 1
+            assert np.array_equal(p.fwd_missing_points, r.fwd_missing_points)
+            assert np.array_equal(p.forward_projection, r.forward_projection)
+    assert n_fwd >= 2
+    K = np.array(synth.intrinsics_for(w, h), np.float32)
+    for k, t in enumerate((3, 5)):
+        img_r, img_p = r.get_image(t, _free_pose(k), K, w, h), p.get_image(t, _free_pose(k), K, w, h)
+        assert np.array_equal(p.free_visible_ids, r.free_visible_ids)
+        assert np.array_equal(p.free_minmax, r.free_minmax)
+        assert np.array_equal(p.free_raycast_result, r.free_raycast_result)
+        assert img_r.any() and np.array_equal(img_p, img_r), "free-view image type %d" % t
+    tri_r, tri_p = r.mesh_scene(), p.mesh_scene()
+    assert len(tri_r) > 10000 and tri_p.shape == tri_r.shape
+    assert np.array_equal(tri_p.view(np.uint32), tri_r.view(np.uint32))
+    r.close(); p.close()
+
+
+def test_port_rows_8f_reproduce_golden_vectors():
+    """the restatement against tests/golden/ref_rows8f_qqvga.npz (made from the real reference): runs everywhere"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_rows8f_qqvga.npz"))
+    w, h = int(g["W"]), int(g["H"])
+    seq = synth.sequence(1, w, h, noise=True)
+    assert golden_check.crc(seq[0]) == int(g["depth_crc"])
+    p = port.PortEngine(w, h)
+    p.process_frame(seq[0])
+    tri = p.mesh_scene()
+    assert len(tri) == int(g["mesh_n"]) and golden_check.crc(tri) == int(g["mesh_crc"])
+    for k in range(2):
+        img = p.get_image(int(g["free%d_type" % k]), g["free%d_pose" % k], g["free%d_intr" % k], w, h)
+        c = [int(x) for x in g["free%d_crc" % k]]
+        assert len(p.free_visible_ids) == int(g["free%d_nvis" % k])
+        assert [golden_check.crc(p.free_visible_ids), golden_check.crc(p.free_minmax), golden_check.crc(p.free_raycast_result),
+                golden_check.crc(img)] == c
+    p.pose_M = g["fwd_pose"]
+    p.expected_depths()
+    p.forward_render()
+    c = [int(x) for x in g["fwd_crc"]]
+    assert len(p.fwd_missing_points) == int(g["fwd_nmissing"])
+    assert [golden_check.crc(p.forward_projection), golden_check.crc(np.sort(p.fwd_missing_points)), golden_check.crc(p.raycast_image),
+            golden_check.crc(p.minmax)] == c
+    p.close()
