@@ -2,7 +2,8 @@
  *
  * A plain-C, single-threaded restatement of the reference's per-frame dense-fusion path
  * (view -> ICP tracking -> allocation -> integration -> expected depths -> raycast -> ICP maps) and of
- * the rows next to it (ForwardRender / useApproximateRaycast, free-view FindVisibleBlocks + RenderImage, MeshScene),
+ * the rows next to it (ForwardRender / useApproximateRaycast, free-view FindVisibleBlocks + RenderImage, MeshScene,
+ * the weighted ICP tracker with its depth filter and sensor-noise model),
  * written from the reference's algorithm with run-time pool sizes so that configurations the
  * reference can only reach by editing #defines (BASELINE configs[2]: 2 mm voxels, larger pools)
  * have an oracle too.  Every function cites the reference lines it restates.
@@ -32,6 +33,11 @@
 #define MINMAX_SUB 8
 #define MAX_RENDERING_BLOCKS (65536 * 4)
 #define MAX_LEVELS 8
+/* the reference calls exp() / acos() unqualified on float arguments from C++ (DeviceAgnostic/ITMViewBuilder.h:48, 110) */
+#ifndef WICP_EXP
+#define WICP_EXP(x) expf(x)
+#define WICP_ACOS(x) acosf(x)
+#endif
 
 enum { ITER_ROTATION = 1, ITER_TRANSLATION = 2, ITER_BOTH = 3, ITER_NONE = 4 }; /* ITMLibDefines.h:278-283 */
 
@@ -54,6 +60,8 @@ typedef struct {
   int no_icp_run_till_level;
   float icp_dist_thresh, icp_termination;
 } port_params;
+
+static int g_next_wicp = 0, g_next_bilateral = 0;  /* port_set_tracker_wicp */
 
 typedef struct port_engine {
   port_params p;
@@ -78,6 +86,8 @@ typedef struct port_engine {
   /* ITMRenderState::forwardProjection / fwdProjMissingPoints, ITMMesh, renderState_freeview */
   V4 *fwd; int *fwd_missing; int n_fwd_missing; int requires_full_rendering; int use_approximate_raycast;
   float *mesh; int n_mesh;
+  /* TRACKER_WICP: settings.modelSensorNoise / useBilateralFilter, view->depthUncertainty / depthNormal, weight hierarchy */
+  int wicp, bilateral; float *float_tmp; float *sigma; V4 *dnormal; float *level_sigma[MAX_LEVELS];
   int free_w, free_h; int *free_visible_ids; int free_n_visible; V2 *free_minmax; V4 *free_raycast; unsigned char *free_image;
 } port_engine;
 
@@ -262,11 +272,11 @@ static void view_convert(port_engine *e) {
 }
 
 /* filterSubsampleWithHoles, DeviceAgnostic/ITMLowLevelEngine.h:26-47; PrepareForEvaluation, ITMDepthTracker.cpp:62-75 */
-static void view_pyramid(port_engine *e) {
+static void pyramid_of(port_engine *e, float **levels) {
   int l, x, y;
   for (l = 1; l < e->p.n_levels; ++l) {
-    const float *src = e->level_depth[l - 1];
-    float *dst = e->level_depth[l];
+    const float *src = levels[l - 1];
+    float *dst = levels[l];
     const int sw = e->level_w[l - 1], dw = e->level_w[l], dh = e->level_h[l];
     for (y = 0; y < dh; ++y) for (x = 0; x < dw; ++x) {
       float sum = 0.0f, cnt = 0.0f, v;
@@ -277,6 +287,85 @@ static void view_pyramid(port_engine *e) {
       if (cnt > 0) sum /= cnt;
       dst[x + y * dw] = sum;
     }
+  }
+}
+
+static void view_pyramid(port_engine *e) { pyramid_of(e, e->level_depth); }
+
+/* DepthFiltering / filterDepth: ITMViewBuilder_CPU.cpp:116-128, DeviceAgnostic/ITMViewBuilder.h:31-56 */
+static void filter_depth(const port_engine *e, float *out, const float *in) {
+  const int W = e->p.width, H = e->p.height;
+  int x, y, i, j;
+  memset(out, 0, (size_t)W * H * sizeof(float));
+  for (y = 2; y < H - 2; y++) for (x = 2; x < W - 2; x++) {
+    const float z = in[x + y * W];
+    float sigma_z, final_depth = 0.0f, w_sum = 0.0f;
+    if (z < 0.0f) { out[x + y * W] = -1.0f; continue; }
+    sigma_z = 1.0f / (0.0012f + 0.0019f * (z - 0.4f) * (z - 0.4f) + 0.0001f / sqrtf(z) * 0.25f);
+    for (i = -2; i <= 2; i++) for (j = -2; j <= 2; j++) {
+      const float tmpz = in[(x + j) + (y + i) * W];
+      float dz, w;
+      if (tmpz < 0.0f) continue;
+      dz = (tmpz - z); dz *= dz;
+      w = WICP_EXP(-0.5f * ((abs(i) + abs(j)) * 1.2232f * 1.2232f + dz * sigma_z * sigma_z));
+      w_sum += w;
+      final_depth += w * tmpz;
+    }
+    final_depth /= w_sum;
+    out[x + y * W] = final_depth;
+  }
+}
+
+/* ComputeNormalAndWeights / computeNormalAndWeight: ITMViewBuilder_CPU.cpp:130-143, DeviceAgnostic/ITMViewBuilder.h:59-114 */
+static void normal_and_weights(port_engine *e) {
+  const int W = e->p.width, H = e->p.height;
+  const float kx = e->p.fx, ky = e->p.fy, kz = e->p.cx, kw = e->p.cy;
+  int x, y;
+  for (y = 2; y < H - 2; y++) for (x = 2; x < W - 2; x++) {
+    const int idx = x + y * W;
+    const float z = e->depth[idx];
+    float zxp, zyp, zxm, zym, xp1x, xp1y, xm1x, xm1y, yp1x, yp1y, ym1x, ym1y, ax, ay, az, bx, by, bz, nx, ny, nz, norm, theta, td;
+    if (z < 0.0f) { e->dnormal[idx].w = -1.0f; e->sigma[idx] = -1; continue; }
+    zxp = e->depth[idx + 1]; zyp = e->depth[idx + W]; zxm = e->depth[idx - 1]; zym = e->depth[idx - W];
+    if (zxp <= 0 || zyp <= 0 || zxm <= 0 || zym <= 0) { e->dnormal[idx].w = -1.0f; e->sigma[idx] = -1; continue; }
+    xp1x = zxp * ((x + 1.0f) - kz) * kx; xp1y = zxp * (y - kw) * ky;
+    xm1x = zxm * ((x - 1.0f) - kz) * kx; xm1y = zxm * (y - kw) * ky;
+    yp1x = zyp * (x - kz) * kx; yp1y = zyp * ((y + 1.0f) - kw) * ky;
+    ym1x = zym * (x - kz) * kx; ym1y = zym * ((y - 1.0f) - kw) * ky;
+    ax = xp1x - xm1x; ay = xp1y - xm1y; az = zxp - zxm;
+    bx = yp1x - ym1x; by = yp1y - ym1y; bz = zyp - zym;
+    nx = (ay * bz - az * by); ny = (az * bx - ax * bz); nz = (ax * by - ay * bx);
+    if (nx == 0.0f && ny == 0 && nz == 0) { e->dnormal[idx].w = -1.0f; e->sigma[idx] = -1; continue; }
+    norm = 1.0f / sqrtf(nx * nx + ny * ny + nz * nz);
+    nx *= norm; ny *= norm; nz *= norm;
+    e->dnormal[idx].x = nx; e->dnormal[idx].y = ny; e->dnormal[idx].z = nz; e->dnormal[idx].w = 1.0f;
+    theta = WICP_ACOS(nz);
+    td = theta / ((float)3.1415926535897932384626433832795 * 0.5f - theta);
+    e->sigma[idx] = (0.0012f + 0.0019f * (z - 0.4f) * (z - 0.4f) + 0.0001f / sqrtf(z) * td * td);
+  }
+}
+
+/* ITMViewBuilder_CPU::UpdateView's filter part, ITMViewBuilder_CPU.cpp:50-63 */
+static void view_filters(port_engine *e) {
+  const size_t P = (size_t)e->p.width * e->p.height;
+  if (e->bilateral) {
+    if (!e->float_tmp) e->float_tmp = (float *)calloc(P, sizeof(float));
+    filter_depth(e, e->float_tmp, e->depth);
+    filter_depth(e, e->depth, e->float_tmp);
+    filter_depth(e, e->float_tmp, e->depth);
+    filter_depth(e, e->depth, e->float_tmp);
+    filter_depth(e, e->float_tmp, e->depth);
+    memcpy(e->depth, e->float_tmp, P * sizeof(float));
+  }
+  if (e->wicp) {
+    int l;
+    if (!e->sigma) {
+      e->sigma = (float *)calloc(P, sizeof(float));
+      e->dnormal = (V4 *)calloc(P, sizeof(V4));
+      e->level_sigma[0] = e->sigma;
+      for (l = 1; l < e->p.n_levels; ++l) e->level_sigma[l] = (float *)calloc((size_t)e->level_w[l] * e->level_h[l] + 1, sizeof(float));
+    }
+    normal_and_weights(e);
   }
 }
 
@@ -348,6 +437,62 @@ static int icp_evaluate(const port_engine *e, int level, const float *approxInvP
   return nValid;
 }
 
+/* ITMWeightedICPTracker_CPU::ComputeGandH (ITMWeightedICPTracker_CPU.cpp:14-85) + computePerPointGH_wICP
+ * (DeviceAgnostic/ITMWeightedICPTracker.h:9-105): per pixel local sums, then added to the totals (the order matters in fp32) */
+static int wicp_evaluate(const port_engine *e, int level, const float *approxInvPose, float *f, float *nabla, float *hessian) {
+  const int type = e->p.regime[level];
+  const int shortIter = (type == ITER_ROTATION) || (type == ITER_TRANSLATION);
+  const int np = shortIter ? 3 : 6, nh = shortIter ? 6 : 21;
+  const float *depth = e->level_depth[level], *weight = e->level_sigma[level];
+  const int w = e->level_w[level], h = e->level_h[level];
+  const float *vi = e->level_intr[level];
+  const int SW = e->p.width, SH = e->p.height;
+  const float sfx = e->p.fx, sfy = e->p.fy, scx = e->p.cx, scy = e->p.cy;
+  const float thresh = e->dist_thresh[level], minSigmaZ = 0.0012f;
+  float sumH[21], sumN[6], sumF = 0.0f;
+  int nValid = 0, x, y, i, r, c, k;
+  if (type == ITER_NONE) return 0;
+  memset(sumH, 0, sizeof(sumH)); memset(sumN, 0, sizeof(sumN));
+  for (y = 0; y < h; y++) for (x = 0; x < w; x++) {
+    const float d = depth[x + y * w];
+    const float lw = weight[x + y * w] > 0 ? minSigmaZ / weight[x + y * w] * 0.5f + 0.5f : 0.0f;
+    float A[6], b, px, py, pz, qx, qy, qz, rx, ry, rz, u, v, ex, ey, ez, dist, lH[21], lN[6], lF = 0;
+    V4 P, N;
+    for (i = 0; i < np; i++) lN[i] = 0.0f;
+    for (i = 0; i < nh; i++) lH[i] = 0.0f;
+    if (d <= 1e-8f) continue;
+    px = d * (((float)x - vi[2]) / vi[0]); py = d * (((float)y - vi[3]) / vi[1]); pz = d;
+    m4_apply(approxInvPose, px, py, pz, 1.0f, &qx, &qy, &qz);
+    m4_apply(e->pose_pc_M, qx, qy, qz, 1.0f, &rx, &ry, &rz);
+    if (rz <= 0.0f) continue;
+    u = sfx * rx / rz + scx; v = sfy * ry / rz + scy;
+    if (!((u >= 0.0f) && (u <= SW - 2) && (v >= 0.0f) && (v <= SH - 2))) continue;
+    P = bilerp_holes(e->points, u, v, SW);
+    if (P.w < 0.0f) continue;
+    ex = P.x - qx; ey = P.y - qy; ez = P.z - qz;
+    dist = ex * ex + ey * ey + ez * ez;
+    if (dist > thresh) continue;
+    N = bilerp_holes(e->normals, u, v, SW);
+    b = N.x * ex + N.y * ey + N.z * ez;
+    lF += b * b * lw * lw;
+    N.x *= lw; N.y *= lw; N.z *= lw; N.w *= lw;
+    if (shortIter && type == ITER_TRANSLATION) { A[0] = N.x; A[1] = N.y; A[2] = N.z; }
+    else {
+      A[0] = +qz * N.y - qy * N.z; A[1] = -qz * N.x + qx * N.z; A[2] = +qy * N.x - qx * N.y;
+      if (!shortIter) { A[3] = N.x; A[4] = N.y; A[5] = N.z; }
+    }
+    for (r = 0, k = 0; r < np; r++) { lN[r] += b * A[r]; for (c = 0; c <= r; c++, k++) lH[k] += A[r] * A[c]; }
+    nValid++; sumF += lF;
+    for (i = 0; i < np; i++) sumN[i] += lN[i];
+    for (i = 0; i < nh; i++) sumH[i] += lH[i];
+  }
+  for (r = 0, k = 0; r < np; r++) for (c = 0; c <= r; c++, k++) hessian[r + c * 6] = sumH[k];
+  for (r = 0; r < np; ++r) for (c = r + 1; c < np; c++) hessian[r + c * 6] = hessian[c + r * 6];
+  for (i = 0; i < np; ++i) nabla[i] = sumN[i];
+  *f = (nValid > 100) ? sqrtf(sumF) / nValid : 1e5f;
+  return nValid;
+}
+
 /* ITMDepthTracker::ComputeDelta, ITMDepthTracker.cpp:85-102 */
 static void icp_delta(float *step, const float *nabla, const float *hessian, int shortIter) {
   int i, r, c;
@@ -405,6 +550,34 @@ static void icp_track(port_engine *e) {
       icp_delta(step, ngood, A, type != ITER_BOTH);
       icp_apply(inv, step, type, inv);
       /* pose_d->SetInvM(inv); Coerce(); inv = GetInvM()   (ITMPose.cpp:309-326) */
+      m4_inverse(inv, tmpM);
+      se3_log(tmpM, e->pose_params);
+      se3_exp(e->pose_params, e->pose_M);
+      m4_inverse(e->pose_M, inv);
+      for (i = 0; i < 6; i++) stepLen += step[i] * step[i];
+      if (sqrtf(stepLen) / 6 < e->p.icp_termination) break;
+    }
+  }
+}
+
+/* ITMWeightedICPTracker::TrackCamera, ITMWeightedICPTracker.cpp:164-192: plain Gauss-Newton, f_old is never updated */
+static void wicp_track(port_engine *e) {
+  float f_old = 1e10f, f_new, H[36], nabla[6], step[6], inv[16];
+  int level, it, i, nValid;
+  view_pyramid(e);
+  pyramid_of(e, e->level_sigma);
+  m4_inverse(e->pose_M, inv);
+  memset(H, 0, sizeof(H)); memset(nabla, 0, sizeof(nabla));
+  for (level = e->p.n_levels - 1; level >= e->p.no_icp_run_till_level; level--) {
+    const int type = e->p.regime[level];
+    if (type == ITER_NONE) continue;
+    for (it = 0; it < e->iters[level]; it++) {
+      float stepLen = 0.0f, tmpM[16];
+      nValid = wicp_evaluate(e, level, inv, &f_new, nabla, H);
+      if (nValid <= 0) break;
+      if (f_new > f_old) break;
+      icp_delta(step, nabla, H, type != ITER_BOTH);
+      icp_apply(inv, step, type, inv);
       m4_inverse(inv, tmpM);
       se3_log(tmpM, e->pose_params);
       se3_exp(e->pose_params, e->pose_M);
@@ -1158,6 +1331,7 @@ port_engine *port_create(const port_params *pp) {
   e->fwd = (V4 *)calloc(P, sizeof(V4));
   e->fwd_missing = (int *)calloc(P, sizeof(int));
   e->requires_full_rendering = 1;
+  e->wicp = g_next_wicp; e->bilateral = g_next_bilateral;
   e->alloc_type = (unsigned char *)calloc((size_t)e->n_entries, 1);
   e->block_coords = (short *)calloc((size_t)e->n_entries * 4, sizeof(short));
   /* ITMRenderState constructor fills the range image with the frustum limits (Objects/ITMRenderState.h:60-72) */
@@ -1187,6 +1361,8 @@ void port_destroy(port_engine *e) {
   free(e->voxels); free(e->hash); free(e->vba_list); free(e->excess_list); free(e->visible_ids); free(e->visible_type);
   free(e->minmax); free(e->raycast); free(e->raycast_image); free(e->points); free(e->normals); free(e->raw); free(e->depth);
   free(e->alloc_type); free(e->block_coords);
+  free(e->float_tmp); free(e->sigma); free(e->dnormal);
+  if (e->level_sigma[0]) for (l = 1; l < e->p.n_levels; ++l) free(e->level_sigma[l]);
   free(e->fwd); free(e->fwd_missing); free(e->mesh); free(e->free_visible_ids); free(e->free_minmax); free(e->free_raycast); free(e->free_image);
   free(e);
 }
@@ -1194,11 +1370,26 @@ void port_destroy(port_engine *e) {
 void port_update_view(port_engine *e, const short *depth) {
   memcpy(e->raw, depth, (size_t)e->p.width * e->p.height * sizeof(short));
   view_convert(e);
+  view_filters(e);
 }
-/* ITMTrackingController::Track, ITMTrackingController.cpp:11-16 */
+/* engines created from now on: TRACKER_WICP + settings.modelSensorNoise, optionally settings.useBilateralFilter */
+void port_set_tracker_wicp(int on, int bilateral) { g_next_wicp = on; g_next_bilateral = bilateral; }
+void port_wicp_prepare(port_engine *e) { view_pyramid(e); pyramid_of(e, e->level_sigma); }
+int port_wicp_gandh(port_engine *e, int level, const float *approxInvPose, float *out44) {
+  float f = 0, nabla[6] = {0, 0, 0, 0, 0, 0}, H[36];
+  int n, i;
+  memset(H, 0, sizeof(H));
+  n = wicp_evaluate(e, level, approxInvPose, &f, nabla, H);
+  out44[0] = (float)n; out44[1] = f;
+  for (i = 0; i < 6; ++i) out44[2 + i] = nabla[i];
+  for (i = 0; i < 36; ++i) out44[8 + i] = H[i];
+  return n;
+}
+float *port_depth_uncertainty(port_engine *e) { return e->sigma; }
+float *port_depth_normal(port_engine *e) { return (float *)e->dnormal; }
 /* ITMTrackingController::Track, ITMTrackingController.cpp:11-16 */
 void port_track(port_engine *e) {
-  if (e->age != -1) icp_track(e);
+  if (e->age != -1) { if (e->wicp) wicp_track(e); else icp_track(e); }
   e->requires_full_rendering = tracker_far_from_point_cloud(e) || !e->use_approximate_raycast;
 }
 void port_allocate(port_engine *e, int onlyVisible) { scene_allocate(e, onlyVisible); }

@@ -48,10 +48,10 @@ def load(fast=False):
 
 class PortEngine(RefEngine):
     def __init__(self, width=640, height=480, intr=None, voxel_size=0.005, mu=0.02, max_w=100, vf_min=0.35, vf_max=3.0,
-                 n_local=0x10000, n_bucket=0x100000, n_excess=0x20000, fast=False):
+                 n_local=0x10000, n_bucket=0x100000, n_excess=0x20000, fast=False, wicp=False, bilateral=False):
         self.n_local, self.n_bucket, self.n_excess = n_local, n_bucket, n_excess
         self._fast = fast
-        super().__init__(width, height, intr, voxel_size, mu, max_w, vf_min, vf_max)
+        super().__init__(width, height, intr, voxel_size, mu, max_w, vf_min, vf_max, wicp=wicp, bilateral=bilateral)
 
     def _create(self, flavour):
         self.lib = load(self._fast)
@@ -61,7 +61,9 @@ class PortEngine(RefEngine):
         p.voxel_size, p.mu, p.max_w, p.vf_min, p.vf_max = self.voxel_size, self.mu, self.max_w, self.vf_min, self.vf_max
         p.n_local, p.n_bucket, p.n_excess = self.n_local, self.n_bucket, self.n_excess
         self.params = p
+        self.lib.ref_set_tracker_wicp(int(self.wicp), int(self.bilateral))
         self.h = self.lib.ref_create(C.byref(p))
+        self.lib.ref_set_tracker_wicp(0, 0)
 
     def const(self, name):
         return {"SDF_LOCAL_BLOCK_NUM": self.n_local, "SDF_BUCKET_NUM": self.n_bucket, "SDF_EXCESS_LIST_SIZE": self.n_excess,

@@ -190,3 +190,31 @@ def test_port_rows_8f_reproduce_golden_vectors():
     assert [golden_check.crc(p.forward_projection), golden_check.crc(np.sort(p.fwd_missing_points)), golden_check.crc(p.raycast_image),
             golden_check.crc(p.minmax)] == c
     p.close()
+
+
+@pytest.mark.skipif(not ref.available("parity"), reason="oracle/_ref not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("bilateral", [False, True], ids=["sensor-noise-model", "bilateral-filter+sensor-noise-model"])
+def test_port_weighted_icp_equals_the_reference(bilateral):
+    """filterDepth (5 passes), computeNormalAndWeight, the weight pyramid, single weighted evaluations and
+    ITMWeightedICPTracker's Gauss-Newton loop - bit for bit (both sides call glibc's expf / acosf)"""
+    w, h, n = 160, 120, 6
+    seq = synth.sequence(n, w, h, noise=True)
+    r, p = ref.RefEngine(w, h, wicp=True, bilateral=bilateral), port.PortEngine(w, h, wicp=True, bilateral=bilateral)
+    for k in range(n):
+        r.update_view(seq[k])
+        p.update_view(seq[k])
+        assert np.array_equal(p.depth, r.depth), "frame %d filtered depth" % k
+        assert np.array_equal(p.depth_uncertainty, r.depth_uncertainty, equal_nan=True)
+        assert np.array_equal(p.depth_normal, r.depth_normal)
+        if k == 2:
+            r.wicp_prepare(); p.wicp_prepare()
+            inv = r.mat_inv(r.pose_M)
+            for level in range(5):
+                n_r, g_r = r.wicp_gandh(level, inv)
+                n_p, g_p = p.wicp_gandh(level, inv)
+                assert n_r == n_p and np.array_equal(g_r, g_p), "level %d" % level
+        for eng in (r, p):
+            eng.track(); eng.allocate(); eng.integrate(); eng.expected_depths(); eng.icp_maps()
+        assert np.array_equal(p.pose_M, r.pose_M), "frame %d pose" % k
+    assert np.abs(r.pose_M - np.eye(4, dtype=np.float32).reshape(16)).max() > 0.01
+    r.close(); p.close()
