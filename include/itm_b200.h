@@ -86,9 +86,25 @@ typedef struct itm_b200_params {
    * each) run side by side instead of one after the other - most of a TrackCamera is spent on pyramid levels that occupy
    * fewer than 40 CTAs anyway.  Changes the summation order of the ICP sums (poses agree to ~1e-6, not bit for bit). */
   int icp_max_ctas;
+  /* settings.trackerType (ITMLib/Utils/ITMLibSettings.h:40-54).  ITM_B200_TRACKER_ICP: ITMDepthTracker (the default here).
+   * ITM_B200_TRACKER_EXTERNAL: the fork's default (ITMLibSettings.cpp:44) - ITMExternalTracker::TrackCamera is a no-op
+   * (Engine/ITMExternalTracker.cpp:27-30) and the pose comes from outside (Engine/RosPoseSourceEngine.cpp:112-118 writes
+   * trackingState->pose_d before every frame): use itm_b200_engine_process_frame_with_pose / _submit_frame with a pose.
+   * ITM_B200_TRACKER_WICP: ITMWeightedICPTracker (Engine/ITMWeightedICPTracker.cpp:58-192) - bilateral-filtered depth,
+   * sensor-noise weights, plain Gauss-Newton - inside the same device-side loop. */
+  int tracker_type;
+  /* calib.disparityCalib.type (ITMLib/Objects/ITMDisparityCalib.h:24-30): how raw shorts become metres in UpdateView
+   * (ITMViewBuilder_CPU.cpp:38-46).  AFFINE: d * depth_calib_a + depth_calib_b.  KINECT_DISPARITY:
+   * 8 * depth_calib_b * fx / (depth_calib_a - d)  (convertDisparityToDepth, DeviceAgnostic/ITMViewBuilder.h:7-20). */
+  int depth_source;
 } itm_b200_params;
 #define ITM_B200_VOXEL_S 0
 #define ITM_B200_VOXEL_S_RGB 1
+#define ITM_B200_TRACKER_ICP 0
+#define ITM_B200_TRACKER_EXTERNAL 1
+#define ITM_B200_TRACKER_WICP 2
+#define ITM_B200_DEPTH_AFFINE 0
+#define ITM_B200_DEPTH_KINECT_DISPARITY 1
 
 /* Fills *p with the reference's defaults (ICP tracker regime) for a width x height sensor;
  * intrinsics default to ITMIntrinsics() = (580, 580, 320, 240) scaled by width/640. */
@@ -239,6 +255,11 @@ int itm_b200_write_obj(const char *file_name, const float *triangles_host, unsig
 int itm_b200_convert_depth_affine_to_float(itm_b200_ctx *ctx, float *depth_out_dev, const short *depth_in_dev, int w, int h,
                                            float a, float b);
 
+/* ITMViewBuilder::ConvertDisparityToDepth (Engine/ITMViewBuilder.h; convertDisparityToDepth, DeviceAgnostic/ITMViewBuilder.h:7-20):
+ * Kinect raw disparities to metres, depth = 8 * c2 * fx_depth / (c1 - d), non-positive results become -1. */
+int itm_b200_convert_disparity_to_depth(itm_b200_ctx *ctx, float *depth_out_dev, const short *disparity_in_dev, int w, int h,
+                                        float c1, float c2, float fx_depth);
+
 /* ITMLowLevelEngine::FilterSubsampleWithHoles(float) (Engine/ITMLowLevelEngine.h:22) */
 int itm_b200_filter_subsample_with_holes(itm_b200_ctx *ctx, float *out_dev, const float *in_dev, int w_in, int h_in);
 
@@ -292,6 +313,28 @@ int itm_b200_engine_reset(itm_b200_engine *e);
  * after the frame is complete; pose_out (may be NULL) receives trackingState->pose_d->GetM(). */
 int itm_b200_engine_process_frame(itm_b200_engine *e, const unsigned char *rgb_host, const short *raw_depth_host,
                                   float pose_out[16]);
+
+/* The fork's deployment mode (settings.trackerType == TRACKER_EXTERNAL): the pose of this frame comes from outside
+ * (RosPoseSourceEngine.cpp:112-118 does pose_d->SetT / SetR before ProcessFrame) and the frame is fused without ICP
+ * (ITMExternalTracker::TrackCamera is empty, Engine/ITMExternalTracker.cpp:27-30).  pose_M_in = the camera-from-world matrix
+ * pose_d->GetM() (column-major); works with any tracker_type - the tracker is skipped for this frame.  pose_M_in == NULL
+ * keeps the current pose_d (a TRACKER_EXTERNAL engine then simply does not move). */
+int itm_b200_engine_process_frame_with_pose(itm_b200_engine *e, const unsigned char *rgb_host, const short *raw_depth_host,
+                                            const float pose_M_in[16], float pose_out[16]);
+
+/* ---- streaming ProcessFrame ------------------------------------------------------------------------------------
+ * ITMMainEngine::ProcessFrame split into submit and wait so that the upload of frame k+1 and the read-back of frame k's pose
+ * overlap the fusion of frame k: submit copies the (pinned) host images into one of the engine's staging buffers on a copy
+ * stream and enqueues the frame behind it; the frame's last kernel publishes pose + counters into host-mapped memory, which
+ * wait_frame polls - no stream synchronisation, no D2H copy call on the critical path.  Up to ITM_B200_MAX_IN_FLIGHT
+ * frames may be submitted ahead of the oldest one not yet waited for (submit blocks beyond that); the host buffers of a
+ * frame may be reused once its wait_frame returned (or after itm_b200_engine_sync).  Tickets count from 1.
+ * pose_M_in: optional external pose for this frame (see process_frame_with_pose); NULL = track / keep.
+ * counters = {noVisibleEntries, lastFreeBlockId, lastFreeExcessListId, allocFailures, errorFlags, icpEvaluations}. */
+#define ITM_B200_MAX_IN_FLIGHT 4
+int itm_b200_engine_submit_frame(itm_b200_engine *e, const unsigned char *rgb_host, const short *raw_depth_host,
+                                 const float pose_M_in[16], unsigned long long *ticket);
+int itm_b200_engine_wait_frame(itm_b200_engine *e, unsigned long long ticket, float pose_out[16], int counters[6]);
 
 /* ---- work sharding across the GPUs of one NVLink domain (BASELINE configs[2]) --------------------------------
  * One process per GPU.  The index (hash table, free lists, visible list), the pose and all images evolve identically

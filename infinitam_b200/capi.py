@@ -21,6 +21,9 @@ ITER_ROTATION, ITER_TRANSLATION, ITER_BOTH, ITER_NONE = 1, 2, 3, 4
  BUF_PYRAMID_2, BUF_PYRAMID_3, BUF_PYRAMID_4, BUF_RGB, BUF_SWAP_STATES, BUF_FORWARD_PROJECTION, BUF_FWD_MISSING_POINTS,
  BUF_FREEVIEW_VISIBLE_IDS, BUF_FREEVIEW_MINMAX, BUF_FREEVIEW_RAYCAST_RESULT, BUF_FREEVIEW_IMAGE, BUF_COUNT) = range(26)
 VOXEL_S, VOXEL_S_RGB = 0, 1
+TRACKER_ICP, TRACKER_EXTERNAL, TRACKER_WICP = 0, 1, 2
+DEPTH_AFFINE, DEPTH_KINECT_DISPARITY = 0, 1
+MAX_IN_FLIGHT = 4
 
 (STAGE_VIEW, STAGE_TRACK, STAGE_ALLOCATE, STAGE_INTEGRATE, STAGE_EXPECTED_DEPTHS, STAGE_ICP_MAPS, STAGE_SWAP,
  STAGE_FORWARD_RENDER, STAGE_TRACK_DECIDE) = range(9)
@@ -49,6 +52,8 @@ class Params(C.Structure):
         ("use_swapping", C.c_int),
         ("use_approximate_raycast", C.c_int),
         ("icp_max_ctas", C.c_int),
+        ("tracker_type", C.c_int),
+        ("depth_source", C.c_int),
     ]
 
 
@@ -113,6 +118,8 @@ SYMBOLS = [
     "itm_b200_engine_get_image", "itm_b200_mesh_scene", "itm_b200_write_stl", "itm_b200_write_obj",
     "itm_b200_engine_mesh_scene", "itm_b200_engine_save_scene_to_mesh",
     "itm_b200_take_cuda_error", "itm_b200_engine_get_stream", "itm_b200_engine_copy_to_buffer_dev", "itm_b200_compute_g_and_h_weighted", "itm_b200_depth_filtering", "itm_b200_compute_normal_and_weights", "itm_b200_swap_in_select", "itm_b200_swap_in_apply", "itm_b200_swap_out",
+    "itm_b200_convert_disparity_to_depth", "itm_b200_engine_process_frame_with_pose", "itm_b200_engine_submit_frame",
+    "itm_b200_engine_wait_frame",
 ]
 
 _lib = None
@@ -180,6 +187,10 @@ def load():
     lib.itm_b200_engine_destroy.restype = None
     lib.itm_b200_engine_reset.argtypes = [vp]
     lib.itm_b200_engine_process_frame.argtypes = [vp, vp, vp, f32p]
+    lib.itm_b200_engine_process_frame_with_pose.argtypes = [vp, vp, vp, f32p, f32p]
+    lib.itm_b200_engine_submit_frame.argtypes = [vp, vp, vp, f32p, C.POINTER(C.c_ulonglong)]
+    lib.itm_b200_engine_wait_frame.argtypes = [vp, C.c_ulonglong, f32p, i32p]
+    lib.itm_b200_convert_disparity_to_depth.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float]
     lib.itm_b200_engine_enqueue_frame_dev.argtypes = [vp, vp]
     lib.itm_b200_engine_get_stream.argtypes = [vp, C.POINTER(vp)]
     lib.itm_b200_engine_copy_to_buffer_dev.argtypes = [vp, C.c_int, vp, C.c_size_t]

@@ -6,6 +6,7 @@
 // all cross-frame state resident in HBM and no host synchronisation inside a frame.
 #include <atomic>
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -46,6 +47,21 @@ int fail(int code, const std::string &msg) {
       cudaGetLastError();                                                                          \
     }                                                                                              \
   } while (0)
+
+// Every entry point runs on the context's device and leaves the caller's current device as it found it (hosts such as
+// PyTorch switch devices between calls; two engines on different devices may live in one process).
+struct DeviceScope {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceScope(int dev) {
+    if (dev >= 0 && cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceScope() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+#define ON_DEVICE_OF_CTX(c) DeviceScope _deviceScope((c) ? (c)->p.device : -1)
+#define ON_DEVICE_OF_ENGINE(e) DeviceScope _deviceScope(((e) && (e)->c) ? (e)->c->p.device : -1)
 
 struct LevelCfg {
   int w, h;
@@ -101,6 +117,19 @@ int validate_params(const itm_b200_params *p) {
   if (p->no_hierarchy_levels < 1 || p->no_hierarchy_levels > ITM_MAX_LEVELS) return fail(ITM_B200_EINVAL, "no_hierarchy_levels out of range");
   if (!(p->voxel_size > 0) || !(p->mu > 0)) return fail(ITM_B200_EINVAL, "voxel_size and mu must be positive");
   if (p->voxel_type != ITM_B200_VOXEL_S && p->voxel_type != ITM_B200_VOXEL_S_RGB) return fail(ITM_B200_EINVAL, "unknown voxel_type");
+  if (p->no_icp_run_till_level < 0 || p->no_icp_run_till_level >= p->no_hierarchy_levels)
+    return fail(ITM_B200_EINVAL, "no_icp_run_till_level must lie in [0, no_hierarchy_levels)");
+  for (int l = 0; l < p->no_hierarchy_levels; ++l)
+    if (p->tracking_regime[l] < ITM_B200_ITER_ROTATION || p->tracking_regime[l] > ITM_B200_ITER_NONE)
+      return fail(ITM_B200_EINVAL, "tracking_regime[] entries must be ITM_B200_ITER_ROTATION .. ITM_B200_ITER_NONE");
+  // the coarsest pyramid level must still be an image, and the stencils (ICP maps +-2 px, integration [1, W-2]) need room
+  if ((p->width >> (p->no_hierarchy_levels - 1)) < 1 || (p->height >> (p->no_hierarchy_levels - 1)) < 1 || p->width < 8 || p->height < 8)
+    return fail(ITM_B200_EINVAL, "image too small for the pyramid / stencils (at least 8x8 and 1 pixel on the coarsest level)");
+  if (p->tracker_type != ITM_B200_TRACKER_ICP && p->tracker_type != ITM_B200_TRACKER_EXTERNAL && p->tracker_type != ITM_B200_TRACKER_WICP)
+    return fail(ITM_B200_EINVAL, "unknown tracker_type");
+  if (p->depth_source != ITM_B200_DEPTH_AFFINE && p->depth_source != ITM_B200_DEPTH_KINECT_DISPARITY)
+    return fail(ITM_B200_EINVAL, "unknown depth_source");
+  if (p->icp_max_ctas < 0) return fail(ITM_B200_EINVAL, "icp_max_ctas must be >= 0");
   return ITM_B200_OK;
 }
 
@@ -147,7 +176,8 @@ int ctx_alloc(itm_b200_ctx *c, void *stream) {
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) return fail(ITM_B200_ENODEVICE, "no CUDA device available: this library has no CPU fallback");
-  CU(cudaSetDevice(c->p.device));
+  if (c->p.device < 0 || c->p.device >= ndev) return fail(ITM_B200_EINVAL, "params.device is not a visible CUDA device");
+  CU(cudaSetDevice(c->p.device));  // the caller's device is restored by the entry point's DeviceScope
   if (stream) {
     c->stream = (cudaStream_t)stream;
   } else {
@@ -305,8 +335,8 @@ IcpLevelArgs make_level_args(const itm_b200_ctx *c, int l, const float *depth) {
 }
 
 // ITMDepthTracker::TrackCamera: pyramid (unless already built) + LM loop, all enqueued
-void enqueue_track(itm_b200_ctx *c, const float *depth0, const float *points, const float *normals, bool buildPyramid,
-                   bool epochBumped = false) {
+int enqueue_track(itm_b200_ctx *c, const float *depth0, const float *points, const float *normals, bool buildPyramid,
+                  bool epochBumped = false) {
   cudaStream_t s = c->stream;
   if (buildPyramid && c->nLevels > 1) {
     float *lv[ITM_MAX_LEVELS];
@@ -331,8 +361,12 @@ void enqueue_track(itm_b200_ctx *c, const float *depth0, const float *points, co
   }
   const cudaError_t e = launch_icp_track(a, lv, iters, c->nLevels, c->p.no_icp_run_till_level, c->icpRows, c->icpBcast, c->icpEpochDev,
                                          !epochBumped, c->p.icp_max_ctas, s);
-  if (e != cudaSuccess) g_lastError = std::string("cooperative launch of the ICP tracker failed: ") + cudaGetErrorString(e);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(ITM_B200_ECUDA, std::string("cooperative launch of the ICP tracker failed: ") + cudaGetErrorString(e));
+  }
   g_launches += epochBumped ? 1 : 2;
+  return ITM_B200_OK;
 }
 
 }  // namespace
@@ -395,6 +429,7 @@ int itm_b200_ctx_create(const itm_b200_params *params, void *stream, itm_b200_ct
   *out = nullptr;
   int rc = validate_params(params);
   if (rc) return rc;
+  DeviceScope deviceScope(params->device);
   itm_b200_ctx *c = new itm_b200_ctx();
   c->p = *params;
   derive(c);
@@ -410,12 +445,14 @@ int itm_b200_ctx_create(const itm_b200_params *params, void *stream, itm_b200_ct
 }
 
 void itm_b200_ctx_destroy(itm_b200_ctx *ctx) {
+  ON_DEVICE_OF_CTX(ctx);
   if (!ctx) return;
   ctx_free(ctx);
   delete ctx;
 }
 
 int itm_b200_reset_scene(itm_b200_ctx *c, itm_b200_scene *scene) {
+  ON_DEVICE_OF_CTX(c);
   if (!c || !scene) return fail(ITM_B200_EINVAL, "NULL argument");
   launch_reset_scene(scene->voxel_blocks_dev, scene->vba_allocation_list_dev, scene->hash_entries_dev, scene->excess_allocation_list_dev,
                      c->sp, c->stream);
@@ -429,6 +466,7 @@ int itm_b200_reset_scene(itm_b200_ctx *c, itm_b200_scene *scene) {
 
 int itm_b200_allocate_scene_from_depth(itm_b200_ctx *c, itm_b200_scene *scene, itm_b200_render_state *rs, const float *depth_dev,
                                        const float pose_M[16], int only_update_visible_list) {
+  ON_DEVICE_OF_CTX(c);
   if (!c || !scene || !rs || !depth_dev || !pose_M) return fail(ITM_B200_EINVAL, "NULL argument");
   set_pose_host(c->hst, pose_M);
   c->hst->noVisibleEntries = rs->no_visible_entries;
@@ -453,6 +491,7 @@ int itm_b200_allocate_scene_from_depth(itm_b200_ctx *c, itm_b200_scene *scene, i
 
 static int integrate_layer_a(itm_b200_ctx *c, itm_b200_scene *scene, const itm_b200_render_state *rs, const float *depth_dev,
                              const unsigned char *rgb_dev, const float pose_M[16]) {
+  ON_DEVICE_OF_CTX(c);
   if (!c || !scene || !rs || !depth_dev || !pose_M) return fail(ITM_B200_EINVAL, "NULL argument");
   if (c->sp.voxelWords == 2 && !rgb_dev)
     return fail(ITM_B200_EINVAL, "ITMVoxel_s_rgb context: use itm_b200_integrate_into_scene_rgb (needs view->rgb)");
@@ -480,17 +519,20 @@ static int integrate_layer_a(itm_b200_ctx *c, itm_b200_scene *scene, const itm_b
 
 int itm_b200_integrate_into_scene(itm_b200_ctx *c, itm_b200_scene *scene, const itm_b200_render_state *rs, const float *depth_dev,
                                   const float pose_M[16]) {
+  ON_DEVICE_OF_CTX(c);
   return integrate_layer_a(c, scene, rs, depth_dev, nullptr, pose_M);
 }
 
 int itm_b200_integrate_into_scene_rgb(itm_b200_ctx *c, itm_b200_scene *scene, const itm_b200_render_state *rs, const float *depth_dev,
                                       const unsigned char *rgb_dev, const float pose_M[16]) {
+  ON_DEVICE_OF_CTX(c);
   if (!rgb_dev) return fail(ITM_B200_EINVAL, "NULL argument");
   return integrate_layer_a(c, scene, rs, depth_dev, rgb_dev, pose_M);
 }
 
 int itm_b200_create_expected_depths(itm_b200_ctx *c, const itm_b200_scene *scene, itm_b200_render_state *rs, const float pose_M[16],
                                     const float intrinsics[4]) {
+  ON_DEVICE_OF_CTX(c);
   if (!c || !scene || !rs || !pose_M || !intrinsics) return fail(ITM_B200_EINVAL, "NULL argument");
   set_pose_host(c->hst, pose_M);
   c->hst->noVisibleEntries = rs->no_visible_entries;
@@ -513,6 +555,7 @@ int itm_b200_create_expected_depths(itm_b200_ctx *c, const itm_b200_scene *scene
 }
 
 int itm_b200_create_icp_maps(itm_b200_ctx *c, const itm_b200_scene *scene, itm_b200_render_state *rs, itm_b200_tracking_state *ts) {
+  ON_DEVICE_OF_CTX(c);
   if (!c || !scene || !rs || !ts) return fail(ITM_B200_EINVAL, "NULL argument");
   set_pose_host(c->hst, ts->pose_d);
   int rc = push_state(c);
@@ -542,6 +585,7 @@ int itm_b200_create_icp_maps(itm_b200_ctx *c, const itm_b200_scene *scene, itm_b
 
 int itm_b200_forward_render(itm_b200_ctx *c, const itm_b200_scene *scene, itm_b200_render_state *rs, const float *depth_dev,
                             const itm_b200_tracking_state *ts) {
+  ON_DEVICE_OF_CTX(c);
   if (!c || !scene || !rs || !depth_dev || !ts) return fail(ITM_B200_EINVAL, "NULL argument");
   if (!rs->forward_projection_dev || !rs->fwd_proj_missing_points_dev) return fail(ITM_B200_EINVAL, "render state without forward-projection buffers");
   if ((rs->img_width > 0 && rs->img_width != c->vp.W) || (rs->img_height > 0 && rs->img_height != c->vp.H))
@@ -575,6 +619,7 @@ int itm_b200_forward_render(itm_b200_ctx *c, const itm_b200_scene *scene, itm_b2
 
 int itm_b200_find_visible_blocks(itm_b200_ctx *c, const itm_b200_scene *scene, itm_b200_render_state *rs, const float pose_M[16],
                                  const float intrinsics[4]) {
+  ON_DEVICE_OF_CTX(c);
   if (!c || !scene || !rs || !pose_M || !intrinsics) return fail(ITM_B200_EINVAL, "NULL argument");
   set_pose_host(c->hst, pose_M);
   c->hst->errorFlags = 0;
@@ -591,6 +636,7 @@ int itm_b200_find_visible_blocks(itm_b200_ctx *c, const itm_b200_scene *scene, i
 
 static int raycast_layer_a(itm_b200_ctx *c, const itm_b200_scene *scene, itm_b200_render_state *rs, const float pose_M[16],
                            const float intrinsics[4], unsigned char *out_image_dev, int type) {
+  ON_DEVICE_OF_CTX(c);
   if (!c || !scene || !rs || !pose_M || !intrinsics) return fail(ITM_B200_EINVAL, "NULL argument");
   set_pose_host(c->hst, pose_M);
   int rc = push_state(c);
@@ -615,11 +661,13 @@ static int raycast_layer_a(itm_b200_ctx *c, const itm_b200_scene *scene, itm_b20
 
 int itm_b200_find_surface(itm_b200_ctx *c, const itm_b200_scene *scene, itm_b200_render_state *rs, const float pose_M[16],
                           const float intrinsics[4]) {
+  ON_DEVICE_OF_CTX(c);
   return raycast_layer_a(c, scene, rs, pose_M, intrinsics, nullptr, 0);
 }
 
 int itm_b200_render_image(itm_b200_ctx *c, const itm_b200_scene *scene, itm_b200_render_state *rs, const float pose_M[16],
                           const float intrinsics[4], unsigned char *out_image_dev, int type) {
+  ON_DEVICE_OF_CTX(c);
   if (!out_image_dev) return fail(ITM_B200_EINVAL, "NULL argument");
   if (type < 0 || type > 2) return fail(ITM_B200_EINVAL, "unknown RenderImageType");
   return raycast_layer_a(c, scene, rs, pose_M, intrinsics, out_image_dev, type);
@@ -645,6 +693,7 @@ static SwapArgs swap_args_layer_a(itm_b200_ctx *c, const itm_b200_scene *scene, 
 }
 
 int itm_b200_swap_in_select(itm_b200_ctx *c, const itm_b200_scene *scene, const itm_b200_swap_buffers *sw, int *no_needed) {
+  ON_DEVICE_OF_CTX(c);
   if (!c || !scene || !sw || !no_needed) return fail(ITM_B200_EINVAL, "NULL argument");
   if (!scene->swap_states_dev) return fail(ITM_B200_EINVAL, "scene without swap states (scene->useSwapping is off)");
   c->hst->lastFreeBlockId = scene->last_free_block_id;
@@ -659,6 +708,7 @@ int itm_b200_swap_in_select(itm_b200_ctx *c, const itm_b200_scene *scene, const 
 }
 
 int itm_b200_swap_in_apply(itm_b200_ctx *c, itm_b200_scene *scene, const itm_b200_swap_buffers *sw, int no_needed) {
+  ON_DEVICE_OF_CTX(c);
   if (!c || !scene || !sw) return fail(ITM_B200_EINVAL, "NULL argument");
   if (no_needed <= 0) return ITM_B200_OK;
   c->hst->swapCount = no_needed;
@@ -673,6 +723,7 @@ int itm_b200_swap_in_apply(itm_b200_ctx *c, itm_b200_scene *scene, const itm_b20
 }
 
 int itm_b200_swap_out(itm_b200_ctx *c, itm_b200_scene *scene, const itm_b200_render_state *rs, const itm_b200_swap_buffers *sw, int *no_needed) {
+  ON_DEVICE_OF_CTX(c);
   if (!c || !scene || !rs || !sw || !no_needed) return fail(ITM_B200_EINVAL, "NULL argument");
   if (!scene->swap_states_dev) return fail(ITM_B200_EINVAL, "scene without swap states (scene->useSwapping is off)");
   c->hst->lastFreeBlockId = scene->last_free_block_id;
@@ -693,6 +744,7 @@ int itm_b200_swap_out(itm_b200_ctx *c, itm_b200_scene *scene, const itm_b200_ren
 // meshing
 static int mesh_scene_common(itm_b200_ctx *c, const void *voxels, const void *hash, float *triangles_dev, unsigned no_max_triangles,
                              unsigned *no_total_triangles) {
+  ON_DEVICE_OF_CTX(c);
   if (no_max_triangles < 2) return fail(ITM_B200_EINVAL, "mesh capacity too small");
   if (!c->meshBlockList) {
     CU(cudaMalloc(&c->meshBlockList, (size_t)c->sp.nLocal * sizeof(int)));
@@ -726,6 +778,7 @@ static int mesh_scene_common(itm_b200_ctx *c, const void *voxels, const void *ha
 
 int itm_b200_mesh_scene(itm_b200_ctx *c, const itm_b200_scene *scene, float *triangles_dev, unsigned no_max_triangles,
                         unsigned *no_total_triangles) {
+  ON_DEVICE_OF_CTX(c);
   if (!c || !scene || !triangles_dev) return fail(ITM_B200_EINVAL, "NULL argument");
   return mesh_scene_common(c, scene->voxel_blocks_dev, scene->hash_entries_dev, triangles_dev, no_max_triangles, no_total_triangles);
 }
@@ -767,6 +820,7 @@ int itm_b200_write_obj(const char *file_name, const float *t, unsigned n) {
 }
 
 int itm_b200_convert_depth_affine_to_float(itm_b200_ctx *c, float *out_dev, const short *in_dev, int w, int h, float a, float b) {
+  ON_DEVICE_OF_CTX(c);
   if (!c || !out_dev || !in_dev) return fail(ITM_B200_EINVAL, "NULL argument");
   launch_convert_depth(in_dev, out_dev, w * h, a, b, c->stream);
   g_launches += 1;
@@ -775,7 +829,19 @@ int itm_b200_convert_depth_affine_to_float(itm_b200_ctx *c, float *out_dev, cons
   return ITM_B200_OK;
 }
 
+int itm_b200_convert_disparity_to_depth(itm_b200_ctx *c, float *out_dev, const short *in_dev, int w, int h, float c1, float c2, float fx_depth) {
+  ON_DEVICE_OF_CTX(c);
+  if (!c || !out_dev || !in_dev) return fail(ITM_B200_EINVAL, "NULL argument");
+  if (fx_depth == 0.0f) return fail(ITM_B200_EINVAL, "fx_depth must not be 0");
+  launch_convert_depth(in_dev, out_dev, w * h, c1, c2, c->stream, fx_depth);
+  g_launches += 1;
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  return ITM_B200_OK;
+}
+
 int itm_b200_filter_subsample_with_holes(itm_b200_ctx *c, float *out_dev, const float *in_dev, int w_in, int h_in) {
+  ON_DEVICE_OF_CTX(c);
   if (!c || !out_dev || !in_dev) return fail(ITM_B200_EINVAL, "NULL argument");
   launch_subsample_holes(out_dev, in_dev, w_in, h_in, c->stream);
   g_launches += 1;
@@ -788,6 +854,7 @@ static int compute_g_and_h_common(itm_b200_ctx *c, const float *level_weight_dev
                              const float *points_map_dev, const float *normals_map_dev, int scene_w, int scene_h,
                              const float scene_intrinsics[4], const float approx_inv_pose[16], const float scene_pose[16], float dist_thresh,
                              int iteration_type, float *f, float nabla[6], float hessian[36], int *no_valid_points) {
+  ON_DEVICE_OF_CTX(c);
   if (!c || !level_depth_dev || !points_map_dev || !normals_map_dev) return fail(ITM_B200_EINVAL, "NULL argument");
   if (iteration_type == ITM_ITER_NONE) {
     if (no_valid_points) *no_valid_points = 0;
@@ -830,6 +897,7 @@ int itm_b200_compute_g_and_h(itm_b200_ctx *c, const float *level_depth_dev, int 
                              const float *points_map_dev, const float *normals_map_dev, int scene_w, int scene_h,
                              const float scene_intrinsics[4], const float approx_inv_pose[16], const float scene_pose[16], float dist_thresh,
                              int iteration_type, float *f, float nabla[6], float hessian[36], int *no_valid_points) {
+  ON_DEVICE_OF_CTX(c);
   return compute_g_and_h_common(c, nullptr, level_depth_dev, w, h, view_intrinsics, points_map_dev, normals_map_dev, scene_w, scene_h,
                                 scene_intrinsics, approx_inv_pose, scene_pose, dist_thresh, iteration_type, f, nabla, hessian, no_valid_points);
 }
@@ -839,12 +907,14 @@ int itm_b200_compute_g_and_h_weighted(itm_b200_ctx *c, const float *level_depth_
                                       int scene_h, const float scene_intrinsics[4], const float approx_inv_pose[16],
                                       const float scene_pose[16], float dist_thresh, int iteration_type, float *f, float nabla[6],
                                       float hessian[36], int *no_valid_points) {
+  ON_DEVICE_OF_CTX(c);
   if (!level_weight_dev) return fail(ITM_B200_EINVAL, "NULL argument");
   return compute_g_and_h_common(c, level_weight_dev, level_depth_dev, w, h, view_intrinsics, points_map_dev, normals_map_dev, scene_w, scene_h,
                                 scene_intrinsics, approx_inv_pose, scene_pose, dist_thresh, iteration_type, f, nabla, hessian, no_valid_points);
 }
 
 int itm_b200_depth_filtering(itm_b200_ctx *c, float *out_dev, const float *in_dev, int w, int h) {
+  ON_DEVICE_OF_CTX(c);
   if (!c || !out_dev || !in_dev) return fail(ITM_B200_EINVAL, "NULL argument");
   launch_filter_depth(out_dev, in_dev, w, h, c->stream);
   g_launches += 1;
@@ -855,6 +925,7 @@ int itm_b200_depth_filtering(itm_b200_ctx *c, float *out_dev, const float *in_de
 
 int itm_b200_compute_normal_and_weights(itm_b200_ctx *c, float *normal_out_dev, float *sigma_z_out_dev, const float *depth_dev, int w, int h,
                                         const float intrinsics[4]) {
+  ON_DEVICE_OF_CTX(c);
   if (!c || !normal_out_dev || !sigma_z_out_dev || !depth_dev || !intrinsics) return fail(ITM_B200_EINVAL, "NULL argument");
   launch_normal_weight(normal_out_dev, sigma_z_out_dev, depth_dev, w, h, intrinsics, c->stream);
   g_launches += 1;
@@ -864,12 +935,14 @@ int itm_b200_compute_normal_and_weights(itm_b200_ctx *c, float *normal_out_dev, 
 }
 
 int itm_b200_track_camera(itm_b200_ctx *c, const float *depth_dev, itm_b200_tracking_state *ts) {
+  ON_DEVICE_OF_CTX(c);
   if (!c || !depth_dev || !ts) return fail(ITM_B200_EINVAL, "NULL argument");
   set_pose_host(c->hst, ts->pose_d);
   memcpy(c->hst->scenePose, ts->pose_point_cloud, 64);
   int rc = push_state(c);
   if (rc) return rc;
-  enqueue_track(c, depth_dev, ts->points_map_dev, ts->normals_map_dev, true);
+  rc = enqueue_track(c, depth_dev, ts->points_map_dev, ts->normals_map_dev, true);
+  if (rc) return rc;
   rc = pull_state(c);
   if (rc) return rc;
   memcpy(ts->pose_d, c->hst->M_d, 64);
@@ -962,6 +1035,21 @@ struct itm_b200_engine {
   int frameGraphLaunches[6] = {0, 0, 0, 0, 0, 0};
   bool graphsOff = false;   // swapping / sharded engines, ITM_B200_NO_GRAPH=1, or a failed capture
   bool capturing = false;
+  // external pose (TRACKER_EXTERNAL / process_frame_with_pose): pinned staging ring for {M_d, invM_d, poseParams}
+  float *poseStage = nullptr;          // [ITM_RESULT_RING][38]
+  unsigned poseStageNext = 0;
+  bool skipTrackThisFrame = false;
+  // streaming API (submit_frame / wait_frame)
+  FrameResult *resultRing = nullptr;     // pinned + mapped host memory, ITM_RESULT_RING slots
+  FrameResult *resultRingDev = nullptr;  // its device address
+  unsigned long long deviceFrameNo = 0;  // frames whose ICP-map kernel has been enqueued (= FrameState::frameNo once they ran)
+  unsigned long long waitedFrameNo = 0;  // highest ticket handed back by wait_frame / drained by sync
+  FrameResult saved[ITM_RESULT_RING];    // results collected early because their ring slot was about to be reused
+  short *rawDepthStage[ITM_B200_MAX_IN_FLIGHT] = {nullptr};
+  unsigned char *rgbStage[ITM_B200_MAX_IN_FLIGHT] = {nullptr};  // colour voxels only (integration reads view->rgb)
+  cudaEvent_t h2dDone[ITM_B200_MAX_IN_FLIGHT] = {nullptr};
+  cudaEvent_t stageFree[ITM_B200_MAX_IN_FLIGHT] = {nullptr};
+  unsigned long long submitCount = 0;
   int profiling = 0;  // 0 off, 1 a time stamp at every stage boundary, 2 frame start and end only
   cudaEvent_t ev[9] = {nullptr};
   float stageMs[8] = {0};
@@ -998,6 +1086,10 @@ int engine_alloc(itm_b200_engine *e) {
   e->overlapExpectedDepths = !c->p.use_swapping && e->shard.world == 1 && getenv("ITM_B200_OVERLAP") != nullptr;
   CU(cudaMalloc(&e->depth, P * 4));
   for (int i = 0; i < 9; ++i) CU(cudaEventCreate(&e->ev[i]));
+  CU(cudaMallocHost(&e->poseStage, ITM_RESULT_RING * 38 * sizeof(float)));
+  CU(cudaHostAlloc(&e->resultRing, ITM_RESULT_RING * sizeof(FrameResult), cudaHostAllocMapped));
+  memset(e->resultRing, 0, ITM_RESULT_RING * sizeof(FrameResult));
+  CU(cudaHostGetDevicePointer(&e->resultRingDev, e->resultRing, 0));
   if (c->p.use_swapping) {
     const size_t blockBytes = (size_t)ITM_BLOCK_SIZE3 * 4 * c->sp.voxelWords;
     const int numTiles = (c->sp.nEntries + 8191) / 8192;
@@ -1048,6 +1140,14 @@ void engine_free(itm_b200_engine *e) {
   RELEASE(cudaFree(e->freeVisibleIds)); RELEASE(cudaFree(e->freeMinmax)); RELEASE(cudaFree(e->freeRaycastResult)); RELEASE(cudaFree(e->freeImage));
   if (e->hstFree) RELEASE(cudaFreeHost(e->hstFree));
   if (e->imageHost) RELEASE(cudaFreeHost(e->imageHost));
+  if (e->poseStage) RELEASE(cudaFreeHost(e->poseStage));
+  if (e->resultRing) RELEASE(cudaFreeHost(e->resultRing));
+  for (int i = 0; i < ITM_B200_MAX_IN_FLIGHT; ++i) {
+    RELEASE(cudaFree(e->rawDepthStage[i]));
+    RELEASE(cudaFree(e->rgbStage[i]));
+    if (e->h2dDone[i]) RELEASE(cudaEventDestroy(e->h2dDone[i]));
+    if (e->stageFree[i]) RELEASE(cudaEventDestroy(e->stageFree[i]));
+  }
   RELEASE(cudaFree(e->meshTriangles));
   RELEASE(cudaFree(e->swapStates)); RELEASE(cudaFree(e->neededIds)); RELEASE(cudaFree(e->transfer)); RELEASE(cudaFree(e->hasSynced));
   RELEASE(cudaFree(e->swapTileState)); RELEASE(cudaFree(e->swapTicket));
@@ -1097,6 +1197,10 @@ int engine_reset(itm_b200_engine *e) {
   int rc = push_state(c);
   if (rc) return rc;
   e->agePointCloud = -1;
+  e->deviceFrameNo = 0;
+  e->waitedFrameNo = 0;
+  if (e->resultRing) memset(e->resultRing, 0, ITM_RESULT_RING * sizeof(FrameResult));
+  memset(e->saved, 0, sizeof(e->saved));
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaGetLastError());
   return ITM_B200_OK;
@@ -1111,7 +1215,7 @@ void stage_view(itm_b200_engine *e, bool withPrologue) {
   for (int l = 1; l < c->nLevels; ++l) lv[l] = c->pyramid[l];
   FramePrologue pro{c->st, e->visibleIds, e->visType, reinterpret_cast<float2 *>(e->minmax), c->vp.W * c->vp.H, c->icpEpochDev};
   launch_view_pyramid(e->rawDepth, c->p.depth_calib_a, c->p.depth_calib_b, lv, c->vp.W, c->vp.H, c->nLevels, c->stream,
-                      withPrologue ? &pro : nullptr);
+                      withPrologue ? &pro : nullptr, c->p.depth_source == ITM_B200_DEPTH_KINECT_DISPARITY ? c->p.fx : 0.0f);
   e->prologueDone = withPrologue;
   g_launches += 1 + (c->nLevels > 5 ? c->nLevels - 5 : 0);
 }
@@ -1124,11 +1228,19 @@ void stage_track_decide(itm_b200_engine *e) {
   g_launches += 1;
 }
 
-void stage_track(itm_b200_engine *e) {
+// does this frame run the ICP tracker?  Not before the first point cloud exists (ITMTrackingController.cpp:13), not with
+// ITMExternalTracker (its TrackCamera is empty) and not when the caller supplied the frame's pose
+bool frame_tracks(const itm_b200_engine *e) {
+  return e->agePointCloud != -1 && e->c->p.tracker_type != ITM_B200_TRACKER_EXTERNAL && !e->skipTrackThisFrame;
+}
+
+int stage_track(itm_b200_engine *e) {
   // ITMTrackingController::Track (ITMTrackingController.cpp:11-16)
   // in a whole frame the view kernel has already advanced the tracker's launch number (FramePrologue)
-  if (e->agePointCloud != -1) enqueue_track(e->c, e->depth, e->points, e->normals, false, e->prologueDone);
+  int rc = ITM_B200_OK;
+  if (frame_tracks(e)) rc = enqueue_track(e->c, e->depth, e->points, e->normals, false, e->prologueDone);
   stage_track_decide(e);
+  return rc;
 }
 
 void stage_allocate(itm_b200_engine *e) {
@@ -1170,6 +1282,7 @@ RenderArgs engine_render_args(itm_b200_engine *e) {
   a.raycastImage = e->raycastImage;
   a.minmaxReady = 0;
   a.gated = c->p.use_approximate_raycast ? 1 : 0;
+  a.resultRing = e->resultRingDev;
   a.st = c->st;
   a.vp = c->vp;
   a.sp = c->sp;
@@ -1192,6 +1305,7 @@ void stage_icp_maps(itm_b200_engine *e) {
   // pose_pointCloud <- pose_d happens inside the kernel (FrameState::scenePose)
   launch_icp_maps(engine_render_args(e), e->c->stream);
   g_launches += 1;
+  if (!e->capturing) e->deviceFrameNo++;  // the kernel advances FrameState::frameNo
   // the device copy (FrameState::agePointCloud, updated by the kernels) is the authoritative one; the host only needs to
   // know whether a point cloud exists at all (Track's "age != -1" test)
   if (e->agePointCloud == -1) e->agePointCloud = -2;
@@ -1276,11 +1390,13 @@ void stamp(itm_b200_engine *e, int i) {
   else cudaEventRecord(e->ev[i], e->c->stream);
 }
 
-void enqueue_frame_direct(itm_b200_engine *e) {
+int enqueue_frame_direct(itm_b200_engine *e) {
+  int rc = ITM_B200_OK;
   stamp(e, 1);
   stage_view(e, true);
   stamp(e, 2);
-  stage_track(e);
+  rc = stage_track(e);
+  if (rc) return rc;
   stamp(e, 3);
   stage_allocate(e);
   stamp(e, 4);
@@ -1297,7 +1413,10 @@ void enqueue_frame_direct(itm_b200_engine *e) {
   } else {
     stage_integrate(e);
     stage_shard_barrier(e);  // every rank's share of the voxel updates has landed in every copy
-    if (e->swapStates) stage_swap(e);
+    if (e->swapStates) {
+      rc = stage_swap(e);  // the one stage with the host in the loop: a failed copy must not go unnoticed
+      if (rc) return rc;
+    }
     stamp(e, 5);
     stage_expected_depths(e);
     stamp(e, 6);
@@ -1308,6 +1427,7 @@ void enqueue_frame_direct(itm_b200_engine *e) {
   stamp(e, 7);
   stage_icp_maps(e);
   stamp(e, 8);
+  return ITM_B200_OK;
 }
 
 // One ProcessFrame = ~12 launches of 3..100 us each, all with launch parameters that never change (everything that varies
@@ -1316,13 +1436,10 @@ void enqueue_frame_direct(itm_b200_engine *e) {
 // scheduling on the device.  Two things do differ between frames and select the graph: whether the tracker runs (not on
 // the very first frame) and whether stage time stamps are wanted.  Engines whose frame needs the host in the middle
 // (swapping) or peers (sharding) keep the direct path.
-void enqueue_frame(itm_b200_engine *e) {
+int enqueue_frame(itm_b200_engine *e) {
   cudaStream_t s = e->c->stream;
-  if (e->graphsOff) {
-    enqueue_frame_direct(e);
-    return;
-  }
-  const int key = (e->agePointCloud != -1 ? 1 : 0) + 2 * e->profiling;
+  if (e->graphsOff) return enqueue_frame_direct(e);
+  const int key = (frame_tracks(e) ? 1 : 0) + 2 * e->profiling;
   if (!e->frameGraph[key]) {
     const int ageBefore = e->agePointCloud;
     const unsigned long long launchesBefore = g_launches.load();
@@ -1330,9 +1447,9 @@ void enqueue_frame(itm_b200_engine *e) {
     bool ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) == cudaSuccess;
     if (ok) {
       e->capturing = true;
-      enqueue_frame_direct(e);
+      const int rc = enqueue_frame_direct(e);
       e->capturing = false;
-      ok = cudaStreamEndCapture(s, &graph) == cudaSuccess && graph != nullptr;
+      ok = cudaStreamEndCapture(s, &graph) == cudaSuccess && graph != nullptr && rc == ITM_B200_OK;
     }
     // the capture recorded the frame but ran nothing: undo its host-side bookkeeping
     e->frameGraphLaunches[key] = (int)(g_launches.load() - launchesBefore);
@@ -1345,20 +1462,64 @@ void enqueue_frame(itm_b200_engine *e) {
       cudaGetLastError();
       e->frameGraph[key] = nullptr;
       e->graphsOff = true;
-      enqueue_frame_direct(e);
-      return;
+      return enqueue_frame_direct(e);
     }
   }
   if (cudaGraphLaunch(e->frameGraph[key], s) != cudaSuccess) {
     cudaGetLastError();
     e->graphsOff = true;
-    enqueue_frame_direct(e);
-    return;
+    return enqueue_frame_direct(e);
   }
   g_launches += (unsigned long long)e->frameGraphLaunches[key];
+  e->deviceFrameNo++;
   // what stage_icp_maps does on the host (ITMTrackingController::Prepare :35-37)
   if (e->agePointCloud == -1) e->agePointCloud = -2;
   else e->agePointCloud = 0;
+  return ITM_B200_OK;
+}
+
+// trackingState->pose_d->SetM(M) for the coming frame, stream-ordered: {M_d, invM_d, poseParams} are the first 38 floats
+// of FrameState.  The staging slot is pinned and only reused ITM_RESULT_RING frames later.
+int enqueue_pose(itm_b200_engine *e, const float *M) {
+  static_assert(offsetof(FrameState, M_d) == 0 && offsetof(FrameState, invM_d) == 64 && offsetof(FrameState, poseParams) == 128,
+                "pose block of FrameState");
+  FrameState tmp;
+  set_pose_host(&tmp, M);
+  float *slot = e->poseStage + (size_t)(e->poseStageNext++ % ITM_RESULT_RING) * 38;
+  memcpy(slot, tmp.M_d, 64);
+  memcpy(slot + 16, tmp.invM_d, 64);
+  memcpy(slot + 32, tmp.poseParams, 24);
+  CU(cudaMemcpyAsync(e->c->st, slot, 38 * sizeof(float), cudaMemcpyHostToDevice, e->c->stream));
+  return ITM_B200_OK;
+}
+
+// result of frame `ticket` out of the host-mapped ring (or the early-collected copy): polls, no CUDA synchronisation
+int collect_result(itm_b200_engine *e, unsigned long long ticket, FrameResult *out) {
+  if (ticket == 0 || ticket > e->deviceFrameNo) return fail(ITM_B200_EINVAL, "wait_frame: no such frame has been submitted");
+  if (ticket + ITM_RESULT_RING <= e->deviceFrameNo && e->saved[ticket % ITM_RESULT_RING].seq != ticket)
+    return fail(ITM_B200_EINVAL, "wait_frame: the result of that frame has been overwritten");
+  if (e->saved[ticket % ITM_RESULT_RING].seq == ticket) {
+    *out = e->saved[ticket % ITM_RESULT_RING];
+    return ITM_B200_OK;
+  }
+  volatile FrameResult *slot = e->resultRing + (ticket % ITM_RESULT_RING);
+  unsigned long long spins = 0;
+  while (true) {
+    const unsigned long long seq = *reinterpret_cast<volatile unsigned long long *>(&slot->seq);
+    if (seq == ticket) break;
+    if ((++spins & 0xFFFF) == 0) {
+      // a faulted or finished stream never publishes: do not spin forever
+      const cudaError_t q = cudaStreamQuery(e->c->stream);
+      if (q != cudaErrorNotReady) {
+        if (q != cudaSuccess) return fail(ITM_B200_ECUDA, std::string("wait_frame: ") + cudaGetErrorString(q));
+        if (*reinterpret_cast<volatile unsigned long long *>(&slot->seq) == ticket) break;
+        return fail(ITM_B200_ECUDA, "wait_frame: the stream drained without publishing the frame");
+      }
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  memcpy(out, const_cast<FrameResult *>(slot), sizeof(FrameResult));
+  return ITM_B200_OK;
 }
 
 }  // namespace
@@ -1371,6 +1532,7 @@ int itm_b200_engine_create(const itm_b200_params *params, itm_b200_engine **out)
   itm_b200_ctx *c = nullptr;
   int rc = itm_b200_ctx_create(params, nullptr, &c);
   if (rc) return rc;
+  DeviceScope deviceScope(params->device);
   itm_b200_engine *e = new itm_b200_engine();
   e->c = c;
   memset(&e->shard, 0, sizeof(e->shard));
@@ -1400,6 +1562,7 @@ int itm_b200_engine_create_sharded(const itm_b200_params *params, const itm_b200
   itm_b200_ctx *c = nullptr;
   int rc = itm_b200_ctx_create(params, shard->stream, &c);
   if (rc) return rc;
+  DeviceScope deviceScope(params->device);
   itm_b200_engine *e = new itm_b200_engine();
   e->c = c;
   e->graphsOff = true;
@@ -1461,17 +1624,20 @@ int itm_b200_shard_owner_of_block(int x, int y, int z, int world) {
 }
 
 void itm_b200_engine_destroy(itm_b200_engine *e) {
+  ON_DEVICE_OF_ENGINE(e);
   if (!e) return;
   engine_free(e);
   delete e;
 }
 
 int itm_b200_engine_reset(itm_b200_engine *e) {
+  ON_DEVICE_OF_ENGINE(e);
   if (!e) return fail(ITM_B200_EINVAL, "NULL engine");
   return engine_reset(e);
 }
 
 int itm_b200_engine_upload_depth(itm_b200_engine *e, const short *raw_depth_host) {
+  ON_DEVICE_OF_ENGINE(e);
   if (!e || !raw_depth_host) return fail(ITM_B200_EINVAL, "NULL argument");
   const size_t P = (size_t)e->c->vp.W * e->c->vp.H;
   CU(cudaMemcpyAsync(e->rawDepth, raw_depth_host, P * 2, cudaMemcpyHostToDevice, e->c->stream));
@@ -1480,9 +1646,11 @@ int itm_b200_engine_upload_depth(itm_b200_engine *e, const short *raw_depth_host
 }
 
 int itm_b200_engine_sync(itm_b200_engine *e, float pose_out[16], int counters[6]) {
+  ON_DEVICE_OF_ENGINE(e);
   if (!e) return fail(ITM_B200_EINVAL, "NULL engine");
   int rc = pull_state(e->c);
   if (rc) return rc;
+  e->waitedFrameNo = e->deviceFrameNo;
   const FrameState *h = e->c->hst;
   if (pose_out) memcpy(pose_out, h->M_d, 64);
   if (counters) {
@@ -1497,7 +1665,8 @@ int itm_b200_engine_sync(itm_b200_engine *e, float pose_out[16], int counters[6]
   return ITM_B200_OK;
 }
 
-int itm_b200_engine_process_frame(itm_b200_engine *e, const unsigned char *rgb_host, const short *raw_depth_host, float pose_out[16]) {
+static int process_frame_impl(itm_b200_engine *e, const unsigned char *rgb_host, const short *raw_depth_host, const float *pose_M_in,
+                              bool external, float pose_out[16]) {
   if (!e || !raw_depth_host) return fail(ITM_B200_EINVAL, "NULL argument");
   cudaStream_t s = e->c->stream;
   const size_t P = (size_t)e->c->vp.W * e->c->vp.H;
@@ -1519,12 +1688,95 @@ int itm_b200_engine_process_frame(itm_b200_engine *e, const unsigned char *rgb_h
   // colour voxels read view->rgb during integration: then the frame waits for it up front
   if (rgb_host && e->c->sp.voxelWords == 2) CU(cudaStreamWaitEvent(s, e->rgbDone, 0));
   e->haveView = true;
-  enqueue_frame(e);
+  int rc = ITM_B200_OK;
+  if (pose_M_in) rc = enqueue_pose(e, pose_M_in);
+  if (rc) return rc;
+  e->skipTrackThisFrame = external;
+  rc = enqueue_frame(e);
+  e->skipTrackThisFrame = false;
+  if (rc) return rc;
   if (rgb_host && e->c->sp.voxelWords != 2) CU(cudaStreamWaitEvent(s, e->rgbDone, 0));
   return itm_b200_engine_sync(e, pose_out, nullptr);
 }
 
+int itm_b200_engine_process_frame(itm_b200_engine *e, const unsigned char *rgb_host, const short *raw_depth_host, float pose_out[16]) {
+  ON_DEVICE_OF_ENGINE(e);
+  return process_frame_impl(e, rgb_host, raw_depth_host, nullptr, false, pose_out);
+}
+
+int itm_b200_engine_process_frame_with_pose(itm_b200_engine *e, const unsigned char *rgb_host, const short *raw_depth_host,
+                                            const float pose_M_in[16], float pose_out[16]) {
+  ON_DEVICE_OF_ENGINE(e);
+  return process_frame_impl(e, rgb_host, raw_depth_host, pose_M_in, true, pose_out);
+}
+
+int itm_b200_engine_submit_frame(itm_b200_engine *e, const unsigned char *rgb_host, const short *raw_depth_host,
+                                 const float pose_M_in[16], unsigned long long *ticket) {
+  ON_DEVICE_OF_ENGINE(e);
+  if (!e || !raw_depth_host || !ticket) return fail(ITM_B200_EINVAL, "NULL argument");
+  if (e->swapStates || e->shard.world > 1) return fail(ITM_B200_EUNSUPPORTED, "submit_frame: swapping / sharded engines use process_frame");
+  itm_b200_ctx *c = e->c;
+  cudaStream_t s = c->stream;
+  const size_t P = (size_t)c->vp.W * c->vp.H;
+  const bool colour = c->sp.voxelWords == 2;
+  // back-pressure: at most ITM_B200_MAX_IN_FLIGHT frames between the oldest one not yet waited for and this one
+  const unsigned long long f = e->deviceFrameNo + 1;
+  if (f > ITM_B200_MAX_IN_FLIGHT && f - ITM_B200_MAX_IN_FLIGHT > e->waitedFrameNo) {
+    const unsigned long long old = f - ITM_B200_MAX_IN_FLIGHT;
+    FrameResult r;
+    int rc = collect_result(e, old, &r);
+    if (rc) return rc;
+    e->saved[old % ITM_RESULT_RING] = r;
+  }
+  const int slot = (int)(e->submitCount++ % ITM_B200_MAX_IN_FLIGHT);
+  if (!e->rawDepthStage[slot]) {
+    CU(cudaMalloc(&e->rawDepthStage[slot], P * 2));
+    if (colour) CU(cudaMalloc(&e->rgbStage[slot], P * 4));
+    CU(cudaEventCreateWithFlags(&e->h2dDone[slot], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&e->stageFree[slot], cudaEventDisableTiming));
+    CU(cudaEventRecord(e->stageFree[slot], s));
+  }
+  // upload on the copy stream into this frame's staging slot (free once the frame that used it last has copied it out) ...
+  CU(cudaStreamWaitEvent(e->copyStream, e->stageFree[slot], 0));
+  CU(cudaMemcpyAsync(e->rawDepthStage[slot], raw_depth_host, P * 2, cudaMemcpyHostToDevice, e->copyStream));
+  if (rgb_host && colour) CU(cudaMemcpyAsync(e->rgbStage[slot], rgb_host, P * 4, cudaMemcpyHostToDevice, e->copyStream));
+  CU(cudaEventRecord(e->h2dDone[slot], e->copyStream));
+  // view->rgb of a depth-only scene is read by nothing on the device: it goes straight to its place, behind the depth image
+  if (rgb_host && !colour) CU(cudaMemcpyAsync(e->rgb, rgb_host, P * 4, cudaMemcpyHostToDevice, e->copyStream));
+  // ... and on the frame stream: staging slot -> view, then the frame
+  stamp(e, 0);
+  CU(cudaStreamWaitEvent(s, e->h2dDone[slot], 0));
+  CU(cudaMemcpyAsync(e->rawDepth, e->rawDepthStage[slot], P * 2, cudaMemcpyDeviceToDevice, s));
+  if (rgb_host && colour) CU(cudaMemcpyAsync(e->rgb, e->rgbStage[slot], P * 4, cudaMemcpyDeviceToDevice, s));
+  CU(cudaEventRecord(e->stageFree[slot], s));
+  e->haveView = true;
+  int rc = ITM_B200_OK;
+  if (pose_M_in) rc = enqueue_pose(e, pose_M_in);
+  if (rc) return rc;
+  e->skipTrackThisFrame = pose_M_in != nullptr;
+  rc = enqueue_frame(e);
+  e->skipTrackThisFrame = false;
+  if (rc) return rc;
+  *ticket = e->deviceFrameNo;
+  return ITM_B200_OK;
+}
+
+int itm_b200_engine_wait_frame(itm_b200_engine *e, unsigned long long ticket, float pose_out[16], int counters[6]) {
+  ON_DEVICE_OF_ENGINE(e);
+  if (!e) return fail(ITM_B200_EINVAL, "NULL engine");
+  FrameResult r;
+  int rc = collect_result(e, ticket, &r);
+  if (rc) return rc;
+  if (ticket > e->waitedFrameNo) e->waitedFrameNo = ticket;
+  if (pose_out) memcpy(pose_out, r.M_d, 64);
+  if (counters) memcpy(counters, r.counters, sizeof(r.counters));
+  for (int l = 0; l < ITM_MAX_LEVELS; ++l) e->c->hst->icp.levelEvals[l] = r.levelEvals[l];
+  if (r.counters[4] & 1) return fail(ITM_B200_EUNSUPPORTED, "allocation ray segment longer than the supported step bound");
+  return ITM_B200_OK;
+}
+
 int itm_b200_engine_copy_to_buffer_dev(itm_b200_engine *e, int which, const void *src_dev, size_t bytes) {
+  ON_DEVICE_OF_ENGINE(e);
   void *p = nullptr;
   size_t total = 0;
   int rc = itm_b200_engine_get_buffer(e, which, &p, &total);
@@ -1535,28 +1787,32 @@ int itm_b200_engine_copy_to_buffer_dev(itm_b200_engine *e, int which, const void
 }
 
 int itm_b200_engine_get_stream(itm_b200_engine *e, void **stream) {
+  ON_DEVICE_OF_ENGINE(e);
   if (!e || !stream) return fail(ITM_B200_EINVAL, "NULL argument");
   *stream = (void *)e->c->stream;
   return ITM_B200_OK;
 }
 
 int itm_b200_engine_enqueue_frame_dev(itm_b200_engine *e, const short *raw_depth_dev) {
+  ON_DEVICE_OF_ENGINE(e);
   if (!e || !raw_depth_dev) return fail(ITM_B200_EINVAL, "NULL argument");
   cudaStream_t s = e->c->stream;
   const size_t P = (size_t)e->c->vp.W * e->c->vp.H;
   stamp(e, 0);
   if (raw_depth_dev != e->rawDepth) CU(cudaMemcpyAsync(e->rawDepth, raw_depth_dev, P * 2, cudaMemcpyDeviceToDevice, s));
   e->haveView = true;
-  enqueue_frame(e);
+  const int rc = enqueue_frame(e);
+  if (rc) return rc;
   CU(cudaGetLastError());
   return ITM_B200_OK;
 }
 
 int itm_b200_engine_run_stage(itm_b200_engine *e, int stage) {
+  ON_DEVICE_OF_ENGINE(e);
   if (!e) return fail(ITM_B200_EINVAL, "NULL engine");
   switch (stage) {
     case 0: stage_view(e, false); break;
-    case 1: stage_track(e); break;
+    case 1: { int rc = stage_track(e); if (rc) return rc; } break;
     case 2: stage_allocate(e); break;
     case 3: stage_integrate(e); stage_shard_barrier(e); break;
     case 6: if (!e->swapStates) return fail(ITM_B200_EINVAL, "engine was created without use_swapping"); { int rc = stage_swap(e); if (rc) return rc; } break;
@@ -1577,6 +1833,7 @@ int itm_b200_engine_run_stage(itm_b200_engine *e, int stage) {
 }
 
 int itm_b200_engine_get_buffer(itm_b200_engine *e, int which, void **dev_ptr, size_t *bytes) {
+  ON_DEVICE_OF_ENGINE(e);
   if (!e || !dev_ptr) return fail(ITM_B200_EINVAL, "NULL argument");
   void *p = nullptr;
   switch (which) {
@@ -1611,6 +1868,7 @@ int itm_b200_engine_get_buffer(itm_b200_engine *e, int which, void **dev_ptr, si
 }
 
 int itm_b200_engine_read_buffer(itm_b200_engine *e, int which, void *host_dst, size_t bytes, size_t offset) {
+  ON_DEVICE_OF_ENGINE(e);
   void *p = nullptr;
   size_t total = 0;
   int rc = itm_b200_engine_get_buffer(e, which, &p, &total);
@@ -1622,6 +1880,7 @@ int itm_b200_engine_read_buffer(itm_b200_engine *e, int which, void *host_dst, s
 }
 
 int itm_b200_engine_write_buffer(itm_b200_engine *e, int which, const void *host_src, size_t bytes, size_t offset) {
+  ON_DEVICE_OF_ENGINE(e);
   void *p = nullptr;
   size_t total = 0;
   int rc = itm_b200_engine_get_buffer(e, which, &p, &total);
@@ -1634,6 +1893,7 @@ int itm_b200_engine_write_buffer(itm_b200_engine *e, int which, const void *host
 
 int itm_b200_engine_global_cache(itm_b200_engine *e, const unsigned char **has_stored_data, const void **stored_voxel_blocks,
                                  int *swapped_in, int *swapped_out) {
+  ON_DEVICE_OF_ENGINE(e);
   if (!e) return fail(ITM_B200_EINVAL, "NULL engine");
   if (!e->swapStates) return fail(ITM_B200_EINVAL, "engine was created without use_swapping");
   if (has_stored_data) *has_stored_data = e->hasStoredData;
@@ -1644,6 +1904,7 @@ int itm_b200_engine_global_cache(itm_b200_engine *e, const unsigned char **has_s
 }
 
 int itm_b200_engine_get_state(itm_b200_engine *e, float pose_d[16], float pose_point_cloud[16], int state6[6]) {
+  ON_DEVICE_OF_ENGINE(e);
   if (!e) return fail(ITM_B200_EINVAL, "NULL engine");
   int rc = pull_state(e->c);
   if (rc) return rc;
@@ -1662,6 +1923,7 @@ int itm_b200_engine_get_state(itm_b200_engine *e, float pose_d[16], float pose_p
 }
 
 int itm_b200_engine_set_state(itm_b200_engine *e, const float pose_d[16], const float pose_point_cloud[16], const int state6[6]) {
+  ON_DEVICE_OF_ENGINE(e);
   if (!e) return fail(ITM_B200_EINVAL, "NULL engine");
   int rc = pull_state(e->c);
   if (rc) return rc;
@@ -1717,6 +1979,7 @@ static void depth_to_uchar4(unsigned char *dst, const float *src, size_t n) {
 
 int itm_b200_engine_get_image(itm_b200_engine *e, int image_type, const float pose_M[16], const float intrinsics[4],
                               unsigned char *out_host, int out_w, int out_h) {
+  ON_DEVICE_OF_ENGINE(e);
   if (!e || !out_host || out_w <= 0 || out_h <= 0) return fail(ITM_B200_EINVAL, "NULL argument");
   if (!e->haveView) return ITM_B200_OK;  // "if (view == NULL) return;"
   itm_b200_ctx *c = e->c;
@@ -1800,6 +2063,7 @@ int itm_b200_engine_get_image(itm_b200_engine *e, int image_type, const float po
 }
 
 int itm_b200_engine_mesh_scene(itm_b200_engine *e, float *triangles_host, unsigned capacity_triangles, unsigned *no_total_triangles) {
+  ON_DEVICE_OF_ENGINE(e);
   if (!e) return fail(ITM_B200_EINVAL, "NULL engine");
   itm_b200_ctx *c = e->c;
   const unsigned noMax = (unsigned)c->sp.nLocal * 32u;  // ITMMesh::noMaxTriangles (Objects/ITMMesh.h:22)
@@ -1816,6 +2080,7 @@ int itm_b200_engine_mesh_scene(itm_b200_engine *e, float *triangles_host, unsign
 }
 
 int itm_b200_engine_save_scene_to_mesh(itm_b200_engine *e, const char *file_name) {
+  ON_DEVICE_OF_ENGINE(e);
   if (!e || !file_name) return fail(ITM_B200_EINVAL, "NULL argument");
   unsigned n = 0;
   int rc = itm_b200_engine_mesh_scene(e, nullptr, 0, &n);
@@ -1826,18 +2091,21 @@ int itm_b200_engine_save_scene_to_mesh(itm_b200_engine *e, const char *file_name
 }
 
 int itm_b200_engine_icp_stats(itm_b200_engine *e, int evals_per_level[ITM_B200_MAX_LEVELS]) {
+  ON_DEVICE_OF_ENGINE(e);
   if (!e || !evals_per_level) return fail(ITM_B200_EINVAL, "NULL argument");
   for (int l = 0; l < ITM_B200_MAX_LEVELS; ++l) evals_per_level[l] = e->c->hst->icp.levelEvals[l];
   return ITM_B200_OK;
 }
 
 int itm_b200_engine_set_profiling(itm_b200_engine *e, int on) {
+  ON_DEVICE_OF_ENGINE(e);
   if (!e) return fail(ITM_B200_EINVAL, "NULL engine");
   e->profiling = on < 0 ? 0 : (on > 2 ? 2 : on);
   return ITM_B200_OK;
 }
 
 int itm_b200_engine_stage_times(itm_b200_engine *e, float ms8[8]) {
+  ON_DEVICE_OF_ENGINE(e);
   if (!e || !ms8) return fail(ITM_B200_EINVAL, "NULL argument");
   if (!e->profiling) return fail(ITM_B200_EINVAL, "profiling is off");
   // ev[0] frame start, ev[1] after H2D, ev[2] after view, ev[3] track, ev[4] allocate, ev[5] integrate,

@@ -318,6 +318,11 @@ __device__ __forceinline__ unsigned long long gtimer() {
 // so no fence, no arrival counter and no second round trip for the data are needed.
 #define ICP_RING 128  // broadcast slots per launch (>= the largest possible number of evaluations, 72 for 8 levels)
 #define ICP_BCAST_WORDS 20  // 16 pose words + 1 flag word, padded
+// Row words are rewritten at every evaluation, so their tag carries the evaluation number next to the (truncated) launch
+// epoch: a CTA that is waited for wrote its row in this very launch, and the previous content is at most one launch old,
+// so 25 epoch bits cannot alias.  Broadcast slot k is written once per launch (by evaluation k) but slots beyond a launch's
+// last evaluation keep older content indefinitely: their tag is the full 32-bit epoch (never 0), which only repeats after
+// 2^32 - 1 launches of slots that are rewritten by every launch reaching them.
 __device__ __forceinline__ unsigned icp_tag(unsigned epoch, int evalNo) { return (epoch << 7) | (unsigned)(evalNo + 1); }
 __device__ __forceinline__ void word_st(unsigned long long *p, unsigned payload, unsigned tag) {
   const unsigned long long v = ((unsigned long long)tag << 32) | payload;
@@ -569,7 +574,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_CTAS_PER_SM) k_icp_track(Trac
   __shared__ double sPart[ICP_THREADS / 32][ICP_NVALS];
   __shared__ float sSums[ICP_NVALS];
   __shared__ LmShared L;
-  __shared__ unsigned sFlags;
+  __shared__ unsigned sFlags[2];  // double buffered by evaluation parity: a warp may run one evaluation ahead of a reader
   __shared__ IcpLevelArgs sLv;
   __shared__ ViewParams sSv;
   FrameState *st = t.a.st;
@@ -631,25 +636,25 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_CTAS_PER_SM) k_icp_track(Trac
                                        : lm_update<6>(L, sSums, type, level, it == 0, t.a.terminationThreshold);
           TRACE(evalNo, 4);
           TRACE_VAL(evalNo, 6, level);
-          sFlags = (conv || it == nIters - 1) ? 1u : 0u;
+          sFlags[evalNo & 1] = (conv || it == nIters - 1) ? 1u : 0u;
         }
         __syncthreads();
         if (threadIdx.x < 16) {
           const float v = L.approxInvPose[threadIdx.x];
           c.approxInvPose[threadIdx.x] = v;
-          word_st(slot + threadIdx.x, __float_as_uint(v), tag);
+          word_st(slot + threadIdx.x, __float_as_uint(v), epoch);
         } else if (threadIdx.x == 16) {
-          word_st(slot + 16, sFlags, tag);
+          word_st(slot + 16, sFlags[evalNo & 1], epoch);
         }
       } else if (threadIdx.x < 17) {
         unsigned long long w;
-        while ((unsigned)((w = word_ld(slot + threadIdx.x)) >> 32) != tag) { /* spin */ }
+        while ((unsigned)((w = word_ld(slot + threadIdx.x)) >> 32) != epoch) { /* spin */ }
         if (threadIdx.x < 16) c.approxInvPose[threadIdx.x] = __uint_as_float((unsigned)w);
-        else sFlags = (unsigned)w;
+        else sFlags[evalNo & 1] = (unsigned)w;
       }
       __syncthreads();
       if (master && threadIdx.x == 0) { TRACE(evalNo, 5); }
-      if (sFlags & 1u) { ++evalNo; break; }
+      if (sFlags[evalNo & 1] & 1u) { ++evalNo; break; }
     }
   }
   if (master && threadIdx.x == 0) {
@@ -722,10 +727,11 @@ void launch_set_pose(FrameState *st, cudaStream_t s) { k_set_pose<<<1, 1, 0, s>>
 
 // grid for the persistent tracker: as many CTAs as can be co-resident, capped at 2 per SM
 int icp_track_grid() {
-  static int grid = 0;
-  if (grid) return grid;
+  static int gridOf[64] = {0};  // per device
   int dev = 0, sms = 0, perSm = 0;
   cudaGetDevice(&dev);
+  int &grid = gridOf[dev & 63];
+  if (grid) return grid;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_icp_track, ICP_THREADS, 0);
   if (perSm > ICP_CTAS_PER_SM) perSm = ICP_CTAS_PER_SM;

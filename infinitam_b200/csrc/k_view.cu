@@ -19,6 +19,19 @@ __device__ __forceinline__ float convert_affine(short d, float a, float b) {
   return ((d <= 0) || (d > 32000)) ? -1.0f : (float)d * a + b;
 }
 
+// convertDisparityToDepth (ITMViewBuilder.h:7-20): Kinect raw disparity, depth = 8 * c2 * fx / (c1 - d)
+__device__ __forceinline__ float convert_disparity(short d, float c1, float c2, float fxDepth) {
+  const float disparity_tmp = c1 - (float)d;
+  float depth;
+  if (disparity_tmp == 0) depth = 0.0f;
+  else depth = 8.0f * c2 * fxDepth / disparity_tmp;
+  return (depth > 0) ? depth : -1.0f;
+}
+// fxDisparity != 0 selects the Kinect disparity conversion with (a, b) = disparityCalib.params
+__device__ __forceinline__ float convert_raw(short d, float a, float b, float fxDisparity) {
+  return fxDisparity != 0.0f ? convert_disparity(d, a, b, fxDisparity) : convert_affine(d, a, b);
+}
+
 // mean of the >0 entries of a 2x2 quad, accumulation order (0,0) (1,0) (0,1) (1,1)
 __device__ __forceinline__ float subsample4(float p00, float p10, float p01, float p11) {
   float out = 0.0f, n = 0.0f;
@@ -39,7 +52,7 @@ struct PyramidArgs {
 
 // One CTA (256 threads) per 32x32 full-res tile.  raw may be NULL (then level 0 is
 // taken as already converted and only the pyramid is built).
-__global__ void __launch_bounds__(256) k_convert_pyramid(const short *__restrict__ raw, float a, float b, PyramidArgs args) {
+__global__ void __launch_bounds__(256) k_convert_pyramid(const short *__restrict__ raw, float a, float b, float fxDisparity, PyramidArgs args) {
   __shared__ float s0[32][33];
   __shared__ float s1[16][17];
   __shared__ float s2[8][9];
@@ -82,7 +95,7 @@ __global__ void __launch_bounds__(256) k_convert_pyramid(const short *__restrict
     float v = 0.0f;
     if (x < W && y < H) {
       if (raw) {
-        v = convert_affine(__ldg(raw + x + y * W), a, b);
+        v = convert_raw(__ldg(raw + x + y * W), a, b, fxDisparity);
         out0[x + y * W] = v;
       } else {
         v = out0[x + y * W];
@@ -124,9 +137,9 @@ __global__ void __launch_bounds__(256) k_convert_pyramid(const short *__restrict
 }
 
 // stand-alone pieces for the stage-level C ABI
-__global__ void k_convert_only(const short *__restrict__ raw, float *__restrict__ out, int n, float a, float b) {
+__global__ void k_convert_only(const short *__restrict__ raw, float *__restrict__ out, int n, float a, float b, float fxDisparity) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = convert_affine(__ldg(raw + i), a, b);
+  if (i < n) out[i] = convert_raw(__ldg(raw + i), a, b, fxDisparity);
 }
 
 __global__ void k_subsample_holes(float *__restrict__ out, const float *__restrict__ in, int wOut, int hOut, int wIn) {
@@ -222,8 +235,8 @@ void launch_normal_weight(float *normalOut, float *sigmaOut, const float *depth,
   k_normal_weight<<<g, 256, 0, s>>>(reinterpret_cast<float4 *>(normalOut), sigmaOut, depth, W, H, make_float4(intr[0], intr[1], intr[2], intr[3]));
 }
 
-void launch_convert_depth(const short *raw, float *out, int n, float a, float b, cudaStream_t s) {
-  k_convert_only<<<(n + 255) / 256, 256, 0, s>>>(raw, out, n, a, b);
+void launch_convert_depth(const short *raw, float *out, int n, float a, float b, cudaStream_t s, float fxDisparity) {
+  k_convert_only<<<(n + 255) / 256, 256, 0, s>>>(raw, out, n, a, b, fxDisparity);
 }
 
 void launch_subsample_holes(float *out, const float *in, int wIn, int hIn, cudaStream_t s) {
@@ -236,7 +249,7 @@ void launch_subsample_holes(float *out, const float *in, int wIn, int hIn, cudaS
 // the tracker's view hierarchy.  Falls back to per-level launches above 5 levels or when a
 // level's children would straddle tiles (never for even dims >= level count).
 void launch_view_pyramid(const short *raw, float a, float b, float *const *levels, int W, int H, int nLevels, cudaStream_t s,
-                         const FramePrologue *prologue) {
+                         const FramePrologue *prologue, float fxDisparity) {
   PyramidArgs args;
   if (prologue) args.pro = *prologue;
   else args.pro = FramePrologue{nullptr, nullptr, nullptr, nullptr, 0, nullptr};
@@ -251,7 +264,7 @@ void launch_view_pyramid(const short *raw, float a, float b, float *const *level
   const int fused = nLevels < 5 ? nLevels : 5;
   args.nLevels = fused;
   dim3 g((W + 31) / 32, (H + 31) / 32);
-  k_convert_pyramid<<<g, 256, 0, s>>>(raw, a, b, args);
+  k_convert_pyramid<<<g, 256, 0, s>>>(raw, a, b, fxDisparity, args);
   for (int l = fused; l < nLevels; ++l) launch_subsample_holes(levels[l], levels[l - 1], args.w[l - 1], args.h[l - 1], s);
 }
 

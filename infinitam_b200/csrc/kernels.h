@@ -69,6 +69,7 @@ struct RenderArgs {
   unsigned char *raycastImage;  // Vector4u[W*H]
   int minmaxReady;      // the min/max image is already initialised (FramePrologue)
   int gated;            // useApproximateRaycast engines: raycast / ICP maps run only when st->requiresFullRendering
+  FrameResult *resultRing;  // host-mapped ring of ITM_RESULT_RING slots the ICP-map kernel publishes pose + counters into (or NULL)
   FrameState *st;
   ViewParams vp;
   SceneParams sp;
@@ -138,7 +139,8 @@ void launch_mesh_scene(const MeshArgs &a, cudaStream_t s);
 // from volume, 2 colour from normal
 void launch_render_image(const RenderArgs &a, unsigned char *outImage, int type, cudaStream_t s);
 
-void launch_convert_depth(const short *raw, float *out, int n, float a, float b, cudaStream_t s);
+// fxDisparity != 0: Kinect disparity conversion 8 * b * fxDisparity / (a - raw) instead of the affine raw * a + b
+void launch_convert_depth(const short *raw, float *out, int n, float a, float b, cudaStream_t s, float fxDisparity = 0.0f);
 void launch_subsample_holes(float *out, const float *in, int wIn, int hIn, cudaStream_t s);
 // ITMViewBuilder::DepthFiltering / ComputeNormalAndWeights (useBilateralFilter / modelSensorNoise)
 void launch_filter_depth(float *out, const float *in, int W, int H, cudaStream_t s);
@@ -155,7 +157,7 @@ struct FramePrologue {
   unsigned *icpEpoch;       // NULL: not bumped here (launch_icp_track then bumps it with a launch of its own)
 };
 void launch_view_pyramid(const short *raw, float a, float b, float *const *levels, int W, int H, int nLevels, cudaStream_t s,
-                         const FramePrologue *prologue = nullptr);
+                         const FramePrologue *prologue = nullptr, float fxDisparity = 0.0f);
 
 // The whole ITMDepthTracker::TrackCamera LM loop as ONE persistent cooperative kernel (levels[l], iters[l] for
 // l < nLevels).  rows / bcast: zero-initialised scratch of icp_rows_bytes() / icp_bcast_bytes().  epochDev: the launch
@@ -165,7 +167,10 @@ void launch_view_pyramid(const short *raw, float a, float b, float *const *level
 cudaError_t launch_icp_track(const IcpArgs &a, const IcpLevelArgs *levels, const int *iters, int nLevels, int noIcpLevel,
                              unsigned long long *rows, unsigned long long *bcast, unsigned *epochDev, bool bumpEpoch, int gridCap,
                              cudaStream_t s);  // gridCap > 0: at most that many CTAs (several scenes sharing one GPU)
-__device__ __forceinline__ void icp_bump_epoch(unsigned *epochDev) { *epochDev = (*epochDev % 0x1FFFFFEu) + 1u; }  // 1 .. 2^25 - 2
+__device__ __forceinline__ void icp_bump_epoch(unsigned *epochDev) {  // 1 .. 2^32 - 1, never 0 (the scratch starts zeroed)
+  const unsigned n = *epochDev + 1u;
+  *epochDev = n ? n : 1u;
+}
 size_t icp_rows_bytes();
 size_t icp_bcast_bytes();
 // One stand-alone evaluation at poseIn (16 floats, device); [n, f, nabla6, hessian36] left in out44 (device).

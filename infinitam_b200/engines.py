@@ -71,6 +71,32 @@ class ITMMainEngine:
         capi.check(self.lib.itm_b200_engine_process_frame(self.h, _addr(rgbImage), _addr(rawDepthImage), _f32p(pose)))
         return pose
 
+    def ProcessFrameWithPose(self, rgbImage, rawDepthImage, pose_M):
+        """The fork's TRACKER_EXTERNAL mode: trackingState->pose_d is set from outside (RosPoseSourceEngine.cpp:112-118,
+        pose_d->SetM semantics) and the frame is fused without ICP (ITMExternalTracker.cpp:27-30).  pose_M: column-major 16
+        floats or None (keep the current pose)."""
+        pose = np.zeros(16, dtype=np.float32)
+        m = None if pose_M is None else np.ascontiguousarray(pose_M, np.float32).reshape(16)
+        capi.check(self.lib.itm_b200_engine_process_frame_with_pose(self.h, _addr(rgbImage), _addr(rawDepthImage),
+                                                                    None if m is None else _f32p(m), _f32p(pose)))
+        return pose
+
+    def SubmitFrame(self, rgbImage, rawDepthImage, pose_M=None) -> int:
+        """Streaming ProcessFrame, first half: upload (copy stream) + frame enqueued; returns the frame's ticket.  The host
+        images must be pinned and stay untouched until WaitFrame(ticket) returned."""
+        t = C.c_ulonglong()
+        m = None if pose_M is None else np.ascontiguousarray(pose_M, np.float32).reshape(16)
+        capi.check(self.lib.itm_b200_engine_submit_frame(self.h, _addr(rgbImage), _addr(rawDepthImage),
+                                                         None if m is None else _f32p(m), C.byref(t)))
+        return t.value
+
+    def WaitFrame(self, ticket: int):
+        """second half: (pose_d->GetM(), counters) of that frame, polled from host-mapped memory"""
+        pose = np.zeros(16, dtype=np.float32)
+        counters = np.zeros(6, dtype=np.int32)
+        capi.check(self.lib.itm_b200_engine_wait_frame(self.h, C.c_ulonglong(ticket), _f32p(pose), _i32p(counters)))
+        return pose, counters
+
     def GetImage(self, getImageType: int, pose=None, intrinsics=None, width: int | None = None, height: int | None = None):
         """ITMMainEngine::GetImage (ITMMainEngine.cpp:134-192): returns the (h, w, 4) uint8 image.  pose (column-major
         16 floats, pose->GetM()) and intrinsics (fx, fy, cx, cy) are needed by the FREECAMERA types only."""

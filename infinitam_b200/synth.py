@@ -24,6 +24,7 @@ Only numpy is used; nothing here is on the product path.
 from __future__ import annotations
 
 import math
+import os
 
 import numpy as np
 
@@ -111,6 +112,16 @@ def sequence(n_frames: int, width: int = 640, height: int = 480, noise: bool = F
     """(n_frames, height, width) int16, C-contiguous."""
     out = np.empty((n_frames, height, width), dtype=np.int16)
     intr = intrinsics_for(width, height)
-    for i in range(n_frames):
+
+    def one(i):
         out[i] = render_depth(start + i, width, height, intr, noise)
+
+    workers = min(n_frames, os.cpu_count() or 1, 32)
+    if workers > 1:  # numpy releases the GIL inside its array loops: frames render in parallel, results are unchanged
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=workers) as ex:
+            list(ex.map(one, range(n_frames)))
+    else:
+        for i in range(n_frames):
+            one(i)
     return out

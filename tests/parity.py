@@ -20,6 +20,11 @@ TOL_POSE = 1e-4
 
 
 def make_cuda_engine(oracle) -> ITMMainEngine:
+    return ITMMainEngine(cuda_params(oracle))
+
+
+def cuda_params(oracle):
+    """itm_b200_params matching the oracle engine's configuration"""
     p = capi.default_params(oracle.W, oracle.H)
     p.fx, p.fy, p.cx, p.cy = oracle.intr
     p.voxel_size, p.mu, p.max_w = oracle.voxel_size, oracle.mu, oracle.max_w
@@ -28,7 +33,24 @@ def make_cuda_engine(oracle) -> ITMMainEngine:
     p.rgb_fx, p.rgb_fy, p.rgb_cx, p.rgb_cy = oracle.intr
     if oracle.const("sizeof_voxel") == 8:
         p.voxel_type = capi.VOXEL_S_RGB
-    return ITMMainEngine(p)
+    return p
+
+
+def assert_scene_equal(oracle, eng: ITMMainEngine):
+    """free-running comparison of the persistent state: counters, hash table, free lists, visible list bit exact, voxels
+    within 1 LSB (returns the number of voxels whose sdf / weight differ at all)"""
+    _, _, st = eng.get_state()
+    c = oracle.counters
+    assert list(st[:3]) == [int(x) for x in c], "counters differ: gpu %s ref %s" % (st[:3], c)
+    assert hash_equal(eng.read(capi.BUF_HASH), oracle.hash_entries), "hash table differs"
+    n_vis = int(c[0])
+    assert np.array_equal(eng.read(capi.BUF_VISIBLE_IDS)[:n_vis], oracle.visible_ids[:n_vis]), "visible list differs"
+    assert np.array_equal(eng.read(capi.BUF_VISIBLE_TYPES), oracle.visible_types), "entriesVisibleType differs"
+    assert np.array_equal(eng.read(capi.BUF_VBA_ALLOC_LIST), oracle.vba_alloc_list)
+    assert np.array_equal(eng.read(capi.BUF_EXCESS_ALLOC_LIST), oracle.excess_alloc_list)
+    ds, dw, ns, nw = voxel_diff(eng.read(capi.BUF_VOXELS), oracle.voxels)
+    assert ds <= 1 and dw <= 1, "voxels differ by more than 1 LSB: sdf %d w %d" % (ds, dw)
+    return ns, nw
 
 
 def push_scene(oracle, eng: ITMMainEngine):
