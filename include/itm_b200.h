@@ -336,22 +336,32 @@ int itm_b200_engine_submit_frame(itm_b200_engine *e, const unsigned char *rgb_ho
                                  const float pose_M_in[16], unsigned long long *ticket);
 int itm_b200_engine_wait_frame(itm_b200_engine *e, unsigned long long ticket, float pose_out[16], int counters[6]);
 
-/* ---- work sharding across the GPUs of one NVLink domain (BASELINE configs[2]) --------------------------------
- * One process per GPU.  The index (hash table, free lists, visible list), the pose and all images evolve identically
- * on every rank (same deterministic kernels on the same broadcast depth frame); the voxel payload and the raycast
- * image are replicated as well, but every rank integrates only the voxel blocks it owns (by block coordinate,
- * itm_b200_shard_owner_of_block) and casts only its share of the image tiles, storing the results into EVERY rank's copy
- * through NVLink peer pointers, with a cross-GPU barrier after each of the two stages.  The results are bit-identical to
- * a single-GPU engine.  The three shared buffers per rank are allocated with itm_b200_ipc_alloc, their handles exchanged
- * by the host (torch.distributed all_gather in infinitam_b200/multi.py) and opened with itm_b200_ipc_open. */
+/* ---- spatial sharding of ONE scene across the GPUs of one NVLink domain (BASELINE configs[2]) ----------
+ * One process per GPU; rank 0's raw depth frame is broadcast to all (NCCL, by the host: infinitam_b200/multi.py).
+ *   - The index - hash-table positions and chain links, excess list, visible list, pose, images - is replicated: every rank runs
+ *     the same deterministic allocation on the same frame, so it is identical on every rank and identical to a single GPU.
+ *   - The voxel payload is partitioned by block coordinate: slabs of `thickness_blocks` blocks along `axis`, rank r owning
+ *     [origin_block + r * thickness, origin_block + (r + 1) * thickness) (the first / last rank open-ended).  A block's voxels
+ *     exist only where it is RESIDENT: on its owner and, as a one-block halo for the trilinear taps of the ray cast, on the
+ *     neighbouring slab's rank.  Elsewhere its hash entry carries ptr = -1.  params.sdf_local_block_num is the pool PER RANK,
+ *     so the scene a box can hold grows with the number of GPUs.
+ *   - Every rank integrates its resident blocks, renders expected depths and casts all rays against them; the per-rank
+ *     partial raycast images are composed per pixel by nearest hit, each rank pulling the peers' tiles that contain hits
+ *     through NVLink peer pointers after one cross-GPU barrier.  ICP maps and the tracker run replicated on the composed
+ *     image: all ranks compute the identical pose, so neither a pose broadcast nor a G/H all-reduce is needed.
+ * The peer-visible buffers (two partial images of width*height*16 bytes, two tile-flag arrays of ceil(w/16)*ceil(h/8) bytes,
+ * ITM_B200_MAX_SHARDS barrier words) are allocated with itm_b200_ipc_alloc, their handles exchanged by the host
+ * (torch.distributed all_gather in infinitam_b200/multi.py) and opened with itm_b200_ipc_open. */
 #define ITM_B200_MAX_SHARDS 8
 #define ITM_B200_IPC_HANDLE_BYTES 64
 typedef struct itm_b200_shard {
   int rank, world;
-  void *voxel_blocks_dev[ITM_B200_MAX_SHARDS];   /* ITMVoxel_s[local*512] of every rank ([rank] = the local one) */
-  void *raycast_result_dev[ITM_B200_MAX_SHARDS]; /* Vector4f[w*h] of every rank */
-  void *barrier_flags_dev[ITM_B200_MAX_SHARDS];  /* unsigned[ITM_B200_MAX_SHARDS] of every rank, zero-initialised */
-  void *stream;                                  /* cudaStream_t the frames are enqueued on (NULL: a private one) */
+  int axis;                                           /* 0 = x, 1 = y, 2 = z (block coordinates) */
+  int origin_block, thickness_blocks;
+  void *partial_raycast_dev[2][ITM_B200_MAX_SHARDS];  /* Vector4f[w*h] per frame parity and rank ([..][rank] = the local one) */
+  void *tile_hit_dev[2][ITM_B200_MAX_SHARDS];         /* unsigned char[tiles] per frame parity and rank */
+  void *barrier_flags_dev[ITM_B200_MAX_SHARDS];       /* unsigned[ITM_B200_MAX_SHARDS] of every rank, zero-initialised */
+  void *stream;                                       /* cudaStream_t the frames are enqueued on (NULL: a private one) */
 } itm_b200_shard;
 int itm_b200_engine_create_sharded(const itm_b200_params *params, const itm_b200_shard *shard, itm_b200_engine **out);
 /* cudaMalloc + zero fill + cudaIpcGetMemHandle / cudaIpcOpenMemHandle (peer access enabled lazily) / close / free */
@@ -359,8 +369,9 @@ int itm_b200_ipc_alloc(size_t bytes, void **dev_ptr, unsigned char handle[ITM_B2
 int itm_b200_ipc_open(const unsigned char handle[ITM_B200_IPC_HANDLE_BYTES], void **dev_ptr);
 int itm_b200_ipc_close(void *dev_ptr);
 int itm_b200_ipc_free(void *dev_ptr);
-/* rank that integrates the voxel block at block coordinate (x, y, z) */
-int itm_b200_shard_owner_of_block(int x, int y, int z, int world);
+/* rank that owns the voxel block at block coordinate (x, y, z); itm_b200_shard_block_resident: 1 if `rank` keeps its payload */
+int itm_b200_shard_owner_of_block(int x, int y, int z, int world, int axis, int origin_block, int thickness_blocks);
+int itm_b200_shard_block_resident(int x, int y, int z, int rank, int world, int axis, int origin_block, int thickness_blocks);
 
 /* The cudaStream_t every frame of this engine is enqueued on (borrowed; valid until destroy): lets the host order its own
  * work - e.g. producing the next depth frame on the device - before or after frames without a host synchronisation. */

@@ -96,7 +96,8 @@ IPC_HANDLE_BYTES = 64
 class Shard(C.Structure):
     _fields_ = [
         ("rank", C.c_int), ("world", C.c_int),
-        ("voxel_blocks_dev", C.c_void_p * MAX_SHARDS), ("raycast_result_dev", C.c_void_p * MAX_SHARDS),
+        ("axis", C.c_int), ("origin_block", C.c_int), ("thickness_blocks", C.c_int),
+        ("partial_raycast_dev", (C.c_void_p * MAX_SHARDS) * 2), ("tile_hit_dev", (C.c_void_p * MAX_SHARDS) * 2),
         ("barrier_flags_dev", C.c_void_p * MAX_SHARDS), ("stream", C.c_void_p),
     ]
 
@@ -119,7 +120,7 @@ SYMBOLS = [
     "itm_b200_engine_mesh_scene", "itm_b200_engine_save_scene_to_mesh",
     "itm_b200_take_cuda_error", "itm_b200_engine_get_stream", "itm_b200_engine_copy_to_buffer_dev", "itm_b200_compute_g_and_h_weighted", "itm_b200_depth_filtering", "itm_b200_compute_normal_and_weights", "itm_b200_swap_in_select", "itm_b200_swap_in_apply", "itm_b200_swap_out",
     "itm_b200_convert_disparity_to_depth", "itm_b200_engine_process_frame_with_pose", "itm_b200_engine_submit_frame",
-    "itm_b200_engine_wait_frame",
+    "itm_b200_engine_wait_frame", "itm_b200_shard_block_resident",
 ]
 
 _lib = None
@@ -182,7 +183,8 @@ def load():
     lib.itm_b200_ipc_open.argtypes = [C.c_char_p, C.POINTER(vp)]
     lib.itm_b200_ipc_close.argtypes = [vp]
     lib.itm_b200_ipc_free.argtypes = [vp]
-    lib.itm_b200_shard_owner_of_block.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.itm_b200_shard_owner_of_block.argtypes = [C.c_int] * 7
+    lib.itm_b200_shard_block_resident.argtypes = [C.c_int] * 8
     lib.itm_b200_engine_destroy.argtypes = [vp]
     lib.itm_b200_engine_destroy.restype = None
     lib.itm_b200_engine_reset.argtypes = [vp]

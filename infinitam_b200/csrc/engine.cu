@@ -302,6 +302,8 @@ AllocArgs make_alloc_args(itm_b200_ctx *c, const float *depth, void *hash, const
   a.onlyUpdateVisibleList = onlyVisible;
   a.swapStates = nullptr;
   a.prologueDone = 0;
+  memset(&a.shard, 0, sizeof(a.shard));
+  a.shard.world = 1;
   return a;
 }
 
@@ -429,6 +431,14 @@ int itm_b200_ctx_create(const itm_b200_params *params, void *stream, itm_b200_ct
   *out = nullptr;
   int rc = validate_params(params);
   if (rc) return rc;
+  {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+      cudaGetLastError();
+      return fail(ITM_B200_ENODEVICE, "no CUDA device available: this library has no CPU fallback");
+    }
+    if (params->device < 0 || params->device >= ndev) return fail(ITM_B200_EINVAL, "params.device is not a visible CUDA device");
+  }
   DeviceScope deviceScope(params->device);
   itm_b200_ctx *c = new itm_b200_ctx();
   c->p = *params;
@@ -500,8 +510,6 @@ static int integrate_layer_a(itm_b200_ctx *c, itm_b200_scene *scene, const itm_b
   int rc = push_state(c);
   if (rc) return rc;
   IntegrateArgs a;
-  memset(&a.shard, 0, sizeof(a.shard));
-  a.shard.world = 1;
   fill_integrate_calib(c, a, rgb_dev);
   a.depth = depth_dev;
   a.voxels = scene->voxel_blocks_dev;
@@ -1248,6 +1256,7 @@ void stage_allocate(itm_b200_engine *e) {
   AllocArgs a = make_alloc_args(c, e->depth, e->hash, e->vbaAllocList, e->excessAllocList, e->visibleIds, e->visType, 0);
   a.prologueDone = e->prologueDone ? 1 : 0;
   a.swapStates = e->swapStates;
+  a.shard = e->shard;
   launch_allocate(a, c->stream);
   g_launches += e->prologueDone ? 3 : 4;
 }
@@ -1255,7 +1264,6 @@ void stage_allocate(itm_b200_engine *e) {
 void stage_integrate(itm_b200_engine *e) {
   itm_b200_ctx *c = e->c;
   IntegrateArgs a;
-  a.shard = e->shard;
   fill_integrate_calib(c, a, e->rgb);
   a.depth = e->depth;
   a.voxels = e->voxels;
@@ -1296,9 +1304,17 @@ void stage_expected_depths(itm_b200_engine *e, cudaStream_t stream = nullptr) {
   g_launches += e->prologueDone ? 1 : 2;
   e->prologueDone = false;  // both consumers have run
 }
+void stage_shard_barrier(itm_b200_engine *e);
 void stage_raycast(itm_b200_engine *e) {
-  launch_raycast(engine_render_args(e), e->c->stream);
+  const RenderArgs a = engine_render_args(e);
+  launch_raycast(a, e->c->stream);
   g_launches += 1;
+  if (e->shard.world > 1) {
+    // every rank's partial image and tile flags are complete and visible, then: nearest hit per pixel
+    stage_shard_barrier(e);
+    launch_raycast_compose(a, e->c->stream);
+    g_launches += 1;
+  }
 }
 void stage_icp_maps(itm_b200_engine *e) {
   // CreateICPMaps + the bookkeeping of ITMTrackingController::Prepare (:33-39); the copy
@@ -1412,7 +1428,6 @@ int enqueue_frame_direct(itm_b200_engine *e) {
     stamp(e, 6);  // "expected depths" = what is left of it after the integration has finished
   } else {
     stage_integrate(e);
-    stage_shard_barrier(e);  // every rank's share of the voxel updates has landed in every copy
     if (e->swapStates) {
       rc = stage_swap(e);  // the one stage with the host in the loop: a failed copy must not go unnoticed
       if (rc) return rc;
@@ -1422,7 +1437,6 @@ int enqueue_frame_direct(itm_b200_engine *e) {
     stamp(e, 6);
   }
   stage_raycast(e);
-  stage_shard_barrier(e);  // ... and every rank's tiles of the raycast image
   if (e->c->p.use_approximate_raycast) stage_forward_render(e, true);
   stamp(e, 7);
   stage_icp_maps(e);
@@ -1556,9 +1570,12 @@ int itm_b200_engine_create_sharded(const itm_b200_params *params, const itm_b200
     return fail(ITM_B200_EINVAL, "rank / world out of range (at most 8 ranks)");
   if (params && (params->voxel_type != ITM_B200_VOXEL_S || params->use_swapping || params->use_approximate_raycast))
     return fail(ITM_B200_EUNSUPPORTED, "sharded engines support ITMVoxel_s without swapping and approximate raycast only");
+  if (shard->axis < 0 || shard->axis > 2 || shard->thickness_blocks < 2)
+    return fail(ITM_B200_EINVAL, "shard axis must be 0..2 and the slab thickness at least 2 blocks");
   for (int r = 0; r < shard->world; ++r)
-    if (!shard->voxel_blocks_dev[r] || !shard->raycast_result_dev[r] || !shard->barrier_flags_dev[r])
-      return fail(ITM_B200_EINVAL, "every rank's voxel, raycast and flag buffer must be given");
+    for (int q = 0; q < 2; ++q)
+      if (!shard->partial_raycast_dev[q][r] || !shard->tile_hit_dev[q][r] || !shard->barrier_flags_dev[r])
+        return fail(ITM_B200_EINVAL, "every rank's partial-image, tile-flag and barrier buffers must be given");
   itm_b200_ctx *c = nullptr;
   int rc = itm_b200_ctx_create(params, shard->stream, &c);
   if (rc) return rc;
@@ -1566,17 +1583,19 @@ int itm_b200_engine_create_sharded(const itm_b200_params *params, const itm_b200
   itm_b200_engine *e = new itm_b200_engine();
   e->c = c;
   e->graphsOff = true;
-  e->externalBuffers = true;
   memset(&e->shard, 0, sizeof(e->shard));
   e->shard.rank = shard->rank;
   e->shard.world = shard->world;
+  e->shard.axis = shard->axis;
+  e->shard.origin = shard->origin_block;
+  e->shard.thickness = shard->thickness_blocks;
   for (int r = 0; r < shard->world; ++r) {
-    e->shard.voxels[r] = shard->voxel_blocks_dev[r];
-    e->shard.raycast[r] = shard->raycast_result_dev[r];
+    for (int q = 0; q < 2; ++q) {
+      e->shard.partial[q][r] = (float4 *)shard->partial_raycast_dev[q][r];
+      e->shard.tileHit[q][r] = (unsigned char *)shard->tile_hit_dev[q][r];
+    }
     e->shard.flags[r] = (unsigned *)shard->barrier_flags_dev[r];
   }
-  e->voxels = shard->voxel_blocks_dev[shard->rank];
-  e->raycastResult = (float *)shard->raycast_result_dev[shard->rank];
   rc = engine_alloc(e);
   if (!rc) rc = engine_reset(e);  // every rank resets its own copy of the replicated state
   if (rc) {
@@ -1618,9 +1637,18 @@ int itm_b200_ipc_free(void *dev_ptr) {
   return ITM_B200_OK;
 }
 
-int itm_b200_shard_owner_of_block(int x, int y, int z, int world) {
-  if (world < 1) return fail(ITM_B200_EINVAL, "world must be >= 1");
-  return shard_owner_of_block(x, y, z, world);
+int itm_b200_shard_owner_of_block(int x, int y, int z, int world, int axis, int origin_block, int thickness_blocks) {
+  if (world < 1 || thickness_blocks < 1 || axis < 0 || axis > 2) return fail(ITM_B200_EINVAL, "world and thickness must be >= 1, axis 0..2");
+  return shard_owner_of_block(x, y, z, world, axis, origin_block, thickness_blocks);
+}
+
+int itm_b200_shard_block_resident(int x, int y, int z, int rank, int world, int axis, int origin_block, int thickness_blocks) {
+  if (world < 1 || thickness_blocks < 1 || axis < 0 || axis > 2 || rank < 0 || rank >= world)
+    return fail(ITM_B200_EINVAL, "world and thickness must be >= 1, axis 0..2, rank in [0, world)");
+  ShardInfo sh;
+  memset(&sh, 0, sizeof(sh));
+  sh.rank = rank; sh.world = world; sh.axis = axis; sh.origin = origin_block; sh.thickness = thickness_blocks;
+  return shard_block_resident(x, y, z, sh) ? 1 : 0;
 }
 
 void itm_b200_engine_destroy(itm_b200_engine *e) {
@@ -1814,14 +1842,14 @@ int itm_b200_engine_run_stage(itm_b200_engine *e, int stage) {
     case 0: stage_view(e, false); break;
     case 1: { int rc = stage_track(e); if (rc) return rc; } break;
     case 2: stage_allocate(e); break;
-    case 3: stage_integrate(e); stage_shard_barrier(e); break;
+    case 3: stage_integrate(e); break;
     case 6: if (!e->swapStates) return fail(ITM_B200_EINVAL, "engine was created without use_swapping"); { int rc = stage_swap(e); if (rc) return rc; } break;
     case 4: stage_expected_depths(e); break;
     case 5: {
       // teacher forced: the full rendering is wanted, whatever the last decision was
       const int approx = e->c->p.use_approximate_raycast;
       e->c->p.use_approximate_raycast = 0;
-      stage_raycast(e); stage_shard_barrier(e); stage_icp_maps(e);
+      stage_raycast(e); stage_icp_maps(e);
       e->c->p.use_approximate_raycast = approx;
       break;
     }

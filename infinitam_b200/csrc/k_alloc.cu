@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(256) k_alloc_scan(unsigned *__restrict__ alloc
                                                     FrameState *st, ViewParams vp, SceneParams sp, float oneOverVoxelSize,
                                                     int stepBound, int doAllocate, unsigned long long *ticket,
                                                     unsigned long long *tileState, int numTiles,
-                                                    const int *__restrict__ prevVisibleIds, int useSwapping) {
+                                                    const int *__restrict__ prevVisibleIds, int useSwapping, const itm::ShardInfo sh) {
   __shared__ unsigned sWarp[8];
   __shared__ unsigned sTotal;
   __shared__ unsigned sExA, sExB;
@@ -248,10 +248,28 @@ __global__ void __launch_bounds__(256) k_alloc_scan(unsigned *__restrict__ alloc
     for (int i = 0; i < step; ++i) { px += r.dx; py += r.dy; pz += r.dz; }
     int bx, by, bz;
     block_of(px, py, pz, bx, by, bz);
-    const int vbaIdx = baseVba - rankA;
+    int vbaIdx = baseVba - rankA;
     rankA++;
+    int newPtr;
+    if (sh.world > 1) {
+      // Sharded scene: the entry is created on every rank (the index is replicated), the voxel block only where the block
+      // is resident; elsewhere ptr = -1 (allocated, payload not here).  Local block numbers come from a local counter - their
+      // order is of no consequence, no result depends on where in the local pool a block lives.
+      if (shard_block_resident(bx, by, bz, sh)) {
+        vbaIdx = atomicSub(&st->lastFreeBlockId, 1);
+        if (vbaIdx < 0) atomicAdd(&st->lastFreeBlockId, 1);
+        newPtr = vbaIdx >= 0 ? vbaAllocList[vbaIdx] : -1;
+        if (vbaIdx < 0) atomicAdd(&st->allocFailures, 1);
+        vbaIdx = 0;  // the entry itself is always created
+      } else {
+        newPtr = -1;
+        vbaIdx = 0;
+      }
+    } else {
+      newPtr = vbaIdx >= 0 ? vbaAllocList[vbaIdx] : -1;
+    }
     if (t1) {
-      if (vbaIdx >= 0) store_entry(table, slot, bx, by, bz, 0, vbaAllocList[vbaIdx]);
+      if (vbaIdx >= 0) store_entry(table, slot, bx, by, bz, 0, newPtr);
       else atomicAdd(&st->allocFailures, 1);
     } else {
       const int exlIdx = baseExl - rankB;
@@ -259,7 +277,7 @@ __global__ void __launch_bounds__(256) k_alloc_scan(unsigned *__restrict__ alloc
       if (vbaIdx >= 0 && exlIdx >= 0) {
         const int exlOffset = excessAllocList[exlIdx];
         table[slot].offset = exlOffset + 1;
-        store_entry(table, sp.nBuckets + exlOffset, bx, by, bz, 0, vbaAllocList[vbaIdx]);
+        store_entry(table, sp.nBuckets + exlOffset, bx, by, bz, 0, newPtr);
         visType[sp.nBuckets + exlOffset] = 1;
       } else {
         atomicAdd(&st->allocFailures, 1);
@@ -415,7 +433,7 @@ void launch_allocate(const AllocArgs &a, cudaStream_t s) {
   const int numTiles = (a.sp.nEntries + SCAN_TILE - 1) / SCAN_TILE;
   k_alloc_scan<<<numTiles, 256, 0, s>>>(a.allocKey, table, a.visType, a.vbaAllocList, a.excessAllocList, a.depth, a.st, a.vp, a.sp,
                                         oneOverVoxelSize, stepBound, a.onlyUpdateVisibleList ? 0 : 1, a.scanTickets, a.allocTileState, numTiles, a.visibleIds,
-                                        (a.swapStates && !a.onlyUpdateVisibleList) ? 1 : 0);
+                                        (a.swapStates && !a.onlyUpdateVisibleList) ? 1 : 0, a.shard);
   k_visible_scan<<<numTiles, 256, 0, s>>>(a.visType, a.visibleIds, a.st, a.sp, a.visibleCapacity, a.scanTickets + 1,
                                           a.visTileState, numTiles, a.onlyUpdateVisibleList ? nullptr : a.swapStates, table, a.vbaAllocList);
 }

@@ -7,20 +7,43 @@ namespace itm {
 
 #define ITM_MAX_SHARDS 8
 
-// Work sharding across GPUs of one NVLink domain (DESIGN.md "Multi-GPU").  The index (hash table, free lists, visible
-// list) is replicated and evolves identically on every rank; the voxel payload and the raycast image are replicated too,
-// but each rank computes only its share and stores the results into every rank's copy through peer pointers.
+// Spatial sharding of ONE scene across the GPUs of an NVLink domain (DESIGN.md "Multi-GPU").
+//  * The INDEX (hash table positions / offsets, excess list, visible list, pose, images) is replicated: every rank runs the
+//    same deterministic allocation on the same broadcast depth frame, so positions and chain links are identical everywhere
+//    and identical to a single-GPU run.
+//  * The voxel PAYLOAD is not: a block's voxels exist only on the ranks where the block is RESIDENT - its owner (slab of
+//    block coordinates along one axis) and, for the one-block halo the trilinear taps / normals of a ray cast need, the
+//    neighbouring slab's rank.  Everywhere else the entry carries ptr = -1, the reference's own "allocated, but the payload
+//    is not in active memory" state (ITMHashEntry::ptr, ITMLibDefines.h:78-81), which every kernel already honours.
+//  * Each rank integrates its resident blocks (halo blocks redundantly: integration is a pure function of block, depth
+//    and pose), renders expected depths and casts ALL rays against its resident blocks only, reports a hit only when the
+//    surface point lies in a block it OWNS, and the per-rank partial images are composed per pixel by nearest hit
+//    (k_raycast_compose pulls the peers' tiles that contain hits over NVLink).  ICP maps and the tracker then run
+//    replicated on the composed image - no pose broadcast, no G/H all-reduce is needed for the ranks to stay in step.
 struct ShardInfo {
-  int rank, world;                    // world == 1: single GPU, peer arrays unused
-  void *voxels[ITM_MAX_SHARDS];       // every rank's voxel block array (entry [rank] is the local one)
-  void *raycast[ITM_MAX_SHARDS];      // every rank's raycastResult image
+  int rank, world;                    // world == 1: single GPU, everything below unused
+  int axis;                           // 0 / 1 / 2: block coordinate the slabs are cut along
+  int origin, thickness;              // owner = clamp((coord - origin) / thickness, 0, world - 1)   (floor division)
+  float4 *partial[2][ITM_MAX_SHARDS];        // per frame parity: every rank's partial raycast image ([rank] = the local one)
+  unsigned char *tileHit[2][ITM_MAX_SHARDS]; // ... and its per-tile "contains a hit" flags (16x8-pixel tiles, raster order)
   unsigned *flags[ITM_MAX_SHARDS];    // every rank's barrier words: flags[r][src] = last barrier number src has reached
 };
 
-// block coordinate -> owning rank (any deterministic function of the coordinate works; this one mixes all three axes)
-__host__ __device__ __forceinline__ int shard_owner_of_block(int x, int y, int z, int world) {
-  const unsigned h = ((unsigned)x * 73856093u) ^ ((unsigned)y * 19349669u) ^ ((unsigned)z * 83492791u);
-  return (int)((h >> 7) % (unsigned)world);
+__host__ __device__ __forceinline__ int shard_floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+// rank that owns the voxel block at block coordinate (x, y, z)
+__host__ __device__ __forceinline__ int shard_owner_of_block(int x, int y, int z, int world, int axis, int origin, int thickness) {
+  const int c = axis == 0 ? x : (axis == 1 ? y : z);
+  int o = shard_floor_div(c - origin, thickness);
+  return o < 0 ? 0 : (o >= world ? world - 1 : o);
+}
+// is the block's payload kept on `rank`?  (owned, or within one block of the rank's slab)
+__host__ __device__ __forceinline__ bool shard_block_resident(int x, int y, int z, const ShardInfo &sh) {
+  if (sh.world <= 1) return true;
+  const int c = sh.axis == 0 ? x : (sh.axis == 1 ? y : z);
+  const int lo = sh.origin + sh.rank * sh.thickness, hi = lo + sh.thickness;  // owned: [lo, hi), open-ended for the outer ranks
+  const bool aboveLo = sh.rank == 0 || c >= lo - 1;
+  const bool belowHi = sh.rank == sh.world - 1 || c < hi + 1;
+  return aboveLo && belowHi;
 }
 
 struct AllocArgs {
@@ -41,10 +64,10 @@ struct AllocArgs {
   int onlyUpdateVisibleList;
   unsigned char *swapStates;     // ITMHashSwapState[nEntries] when the scene swaps (scene->useSwapping), else NULL
   int prologueDone;              // the marking pass already ran (FramePrologue)
+  ShardInfo shard;               // world > 1: only resident blocks get a voxel block (local free list), the others ptr = -1
 };
 
 struct IntegrateArgs {
-  ShardInfo shard;
   const unsigned char *rgb;   // view->rgb, Vector4u[W*H] (ITMVoxel_s_rgb only)
   float rgbIntr[4];           // intrinsics_rgb (fx, fy, cx, cy)
   float calibInv[16];         // trafo_rgb_to_depth.calib_inv
@@ -101,6 +124,8 @@ void launch_allocate(const AllocArgs &a, cudaStream_t s);
 void launch_integrate(const IntegrateArgs &a, cudaStream_t s);
 void launch_expected_depths(const RenderArgs &a, cudaStream_t s);
 void launch_raycast(const RenderArgs &a, cudaStream_t s);
+// sharded engines: per-pixel nearest hit over every rank's partial image -> a.raycastResult (after the cross-GPU barrier)
+void launch_raycast_compose(const RenderArgs &a, cudaStream_t s);
 void launch_icp_maps(const RenderArgs &a, cudaStream_t s);
 
 // ForwardRender (useApproximateRaycast): render.raycastResult is projected into forwardProjection at render.st's pose,

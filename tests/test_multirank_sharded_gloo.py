@@ -1,5 +1,6 @@
-"""CPU (gloo, world_size 2): host-side logic of the sharded mode - ownership functions agree with the library, every
-block / raycast tile has exactly one owner, IPC handle exchange returns every rank's bytes in rank order."""
+"""CPU (gloo, world_size 2): host-side logic of the sharded mode - ownership / residency functions agree with the library,
+every block has exactly one owner and is resident on its owner plus at most one neighbour, IPC handle exchange returns
+every rank's bytes in rank order."""
 import os
 import socket
 import sys
@@ -28,19 +29,24 @@ def _worker(rank, world, port, q):
     ok = len(got) == world and all(got[r] == bytes([r * 16 + i for i in range(3)]) * 64 for r in range(world))
     lib = capi.load()
     owned = 0
-    for x in range(-6, 6):
-        for y in range(-6, 6):
-            for z in range(-6, 6):
-                o = multi.owner_of_block(x, y, z, world)
-                ok = ok and o == lib.itm_b200_shard_owner_of_block(x, y, z, world) and 0 <= o < world
+    axis, origin, thick = multi.slab_layout(world, 0.005, extent_m=(-0.24, 0.24))  # 12 blocks of 4 cm -> 6 per rank
+    ok = ok and (axis, origin, thick) == (0, -6, 6)
+    for x in range(-8, 8):
+        for y in range(-2, 2):
+            for z in range(-2, 2):
+                o = multi.owner_of_block(x, y, z, world, axis, origin, thick)
+                ok = ok and o == lib.itm_b200_shard_owner_of_block(x, y, z, world, axis, origin, thick) and 0 <= o < world
+                res = [multi.block_resident(x, y, z, r, world, axis, origin, thick) for r in range(world)]
+                ok = ok and res == [bool(lib.itm_b200_shard_block_resident(x, y, z, r, world, axis, origin, thick)) for r in range(world)]
+                ok = ok and res[o] and 1 <= sum(res) <= 2  # on the owner, plus the neighbour for the boundary layer
+                ok = ok and (sum(res) == 2) == (x in (-1, 0))  # ... which is exactly the two block layers at the cut
                 owned += o == rank
-    tiles = [multi.owner_of_raycast_tile(tx, ty, 80, world) for ty in range(90) for tx in range(80)]
-    ok = ok and abs(tiles.count(rank) - len(tiles) / world) <= 1
+    n_blocks = 16 * 4 * 4
     import torch
     t = torch.tensor([owned])
     dist.all_reduce(t)
-    ok = ok and int(t[0]) == 12 ** 3  # every block has exactly one owner
-    ok = ok and abs(owned - 12 ** 3 / world) < 0.15 * 12 ** 3  # ... and the split is roughly even
+    ok = ok and int(t[0]) == n_blocks  # every block has exactly one owner
+    ok = ok and owned == n_blocks // world  # ... and this symmetric range splits evenly
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 

@@ -11,6 +11,11 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 6
 W, H = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (640, 480)
 extras = "extras" in sys.argv
 p = capi.default_params(W, H)
+for a in sys.argv:  # voxel=0.002 pool=0x80000 (BASELINE configs[2] shape)
+    if a.startswith("voxel="):
+        p.voxel_size = float(a[6:])
+    if a.startswith("pool="):
+        p.sdf_local_block_num = int(a[5:], 0)
 if extras:
     p.use_approximate_raycast = 1
 eng = ITMMainEngine(p)

@@ -4,9 +4,14 @@
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
       tools/sharded_run.py [--check] [--frames K] [--size 1280x720] [--voxel 0.002] [--pool 0x80000]
 
---check: every rank also runs a private single-GPU engine on the same frames and compares pose, hash table, voxel
-blocks, visible list and ICP maps BITWISE after every frame (the sharded run must equal the single-GPU run).
-Without --check: timing (device time per frame, max over ranks), L2 flushed between frames."""
+--check: every rank also runs a private single-GPU engine on the same frames and compares after every frame
+  pass A (poses supplied, TRACKER_EXTERNAL on both sides, so that nothing but the sharding differs):
+    * hash-table positions and chain links, excess free list, visible list: bit-identical;
+    * ptr >= 0 exactly where the block is resident on this rank (owner + one-block halo), -1 elsewhere;
+    * every resident block's voxels: bit-identical to the single GPU's block;
+    * composed raycast image vs the single GPU's: hit-mask mismatches and the largest point difference in metres;
+  pass B (free-running ICP on both sides): per-frame pose difference.
+Without --check: timing (device time per frame incl. the NCCL depth broadcast, max over ranks), L2 flushed between frames."""
 import argparse
 import json
 import os
@@ -14,14 +19,19 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
-from infinitam_b200 import capi, synth  # noqa: E402
+from infinitam_b200 import capi, multi, synth  # noqa: E402
 from infinitam_b200.engines import ITMMainEngine  # noqa: E402
-from infinitam_b200.multi import ShardedEngine  # noqa: E402
+from infinitam_b200.multi import ShardedEngine, compare_scene  # noqa: E402
+
+
+def gt_pose(k):
+    return np.ascontiguousarray(synth.ground_truth_pose(k).astype(np.float32).T).reshape(16)
 
 
 def main():
@@ -31,7 +41,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--size", default="1280x720")
     ap.add_argument("--voxel", type=float, default=0.002)
-    ap.add_argument("--pool", default="0x80000", help="SDF_LOCAL_BLOCK_NUM")
+    ap.add_argument("--pool", default="0x80000", help="SDF_LOCAL_BLOCK_NUM per rank")
+    ap.add_argument("--single-pool", default=None, help="pool of the single-GPU engine of --check (default: --pool)")
+    ap.add_argument("--out", default=None, help="write the JSON summary (rank 0) to this file")
     args = ap.parse_args()
     W, H = (int(x) for x in args.size.split("x"))
     rank, local_rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -46,26 +58,46 @@ def main():
     # default stream has handle 0 (= "make a private one" for the C ABI), so use an explicit stream
     tstream = torch.cuda.Stream()
     torch.cuda.set_stream(tstream)
-    eng = ShardedEngine(p, stream=tstream.cuda_stream)
     ok = True
+    summary = {"mode": "sharded", "n_gpus": world, "size": args.size, "voxel": args.voxel, "pool_per_rank": int(args.pool, 0)}
     if args.check:
-        single = ITMMainEngine(p)
-        for k in range(n):
-            eng.EnqueueFrame(seq[k] if rank == 0 else None)
-            pose_s, cnt_s = eng.Sync()
-            single.EnqueueFrameDevice(seq[k].data_ptr())
-            pose_1, cnt_1 = single.Sync()
-            same = {"pose": np.array_equal(pose_s, pose_1), "counters": np.array_equal(cnt_s[:3], cnt_1[:3])}
-            for name, buf in (("hash", capi.BUF_HASH), ("voxels", capi.BUF_VOXELS), ("visible", capi.BUF_VISIBLE_IDS),
-                              ("raycast", capi.BUF_RAYCAST_RESULT), ("points", capi.BUF_POINTS), ("normals", capi.BUF_NORMALS)):
-                a, b = eng.engine.read(buf), single.read(buf)
-                if name == "visible":
-                    a, b = a[: cnt_s[0]], b[: cnt_1[0]]
-                same[name] = a.tobytes() == b.tobytes()
-            ok = ok and all(same.values())
-            print("rank %d frame %d nvis %d %s" % (rank, k, cnt_s[0], "BITWISE EQUAL to single GPU" if all(same.values()) else "DIFFERS: %s" % same), flush=True)
-        single.close()
+        import copy
+        import parity
+        p1 = copy.copy(p)
+        p1.sdf_local_block_num = int(args.single_pool or args.pool, 0)
+        frames_out = []
+        for tracker, label in ((capi.TRACKER_EXTERNAL, "A: poses supplied"), (capi.TRACKER_ICP, "B: free-running ICP")):
+            ps, pq = copy.copy(p), copy.copy(p1)
+            ps.tracker_type = pq.tracker_type = tracker
+            eng = ShardedEngine(ps, stream=tstream.cuda_stream)
+            single = ITMMainEngine(pq)
+            for k in range(n):
+                if tracker == capi.TRACKER_EXTERNAL:
+                    eng.engine.set_state(pose_d=gt_pose(k))
+                    single.set_state(pose_d=gt_pose(k))
+                eng.EnqueueFrame(seq[k] if rank == 0 else None)
+                pose_s, cnt_s = eng.Sync()
+                single.EnqueueFrameDevice(seq[k].data_ptr())
+                pose_1, cnt_1 = single.Sync()
+                rot, trans = parity.pose_diff(pose_s, pose_1)
+                rec = {"pass": label, "frame": k, "rank": rank, "pose_rot_rad": rot, "pose_trans_m": trans,
+                       "alloc_failures": [int(cnt_s[3]), int(cnt_1[3])]}
+                if tracker == capi.TRACKER_EXTERNAL:
+                    rec.update(compare_scene(eng.engine, single, rank, world, eng.layout, args.voxel))
+                    good = (rec["hash_pos_offset_equal"] and rec["visible_list_equal"] and rec["excess_counter_equal"] and rec["residency_matches_ptr"]
+                            and rec["resident_voxel_blocks_equal"] and rec["raycast_hit_mismatch"] <= 1e-3 * max(1, rec["raycast_hits_single"])
+                            and rec["raycast_over_1e-4_m"] <= 1e-3 * max(1, rec["raycast_hits_single"]))
+                else:
+                    good = rot <= 1e-4 and trans <= 1e-4
+                rec["ok"] = bool(good)
+                ok = ok and good
+                frames_out.append(rec)
+                print(json.dumps(rec), flush=True)
+            single.close()
+            eng.close()
+        summary["check"] = frames_out if rank == 0 else None
     else:
+        eng = ShardedEngine(p, stream=tstream.cuda_stream)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
         eng.engine.set_profiling(True)
         tot, stages, cnt = 0.0, np.zeros(8), None
@@ -84,18 +116,23 @@ def main():
                 tot += e0.elapsed_time(e1)
         t = torch.tensor([tot], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        if rank == 0:
-            m = n - args.warmup
-            names = ["view", "track", "allocate", "integrate+barrier", "expected_depths", "raycast+barrier", "icp_maps", "total"]
-            print(json.dumps({"mode": "sharded", "n_gpus": world, "size": args.size, "voxel": args.voxel, "frames": m,
-                              "frames_per_s": m / (float(t[0]) * 1e-3), "ms_per_frame": float(t[0]) / m, "visible_blocks": int(cnt[0]),
-                              "stage_us_rank0": {a: round(1e3 * v / m, 1) for a, v in zip(names, stages)},
-                              "note": "total = CUDA events around NCCL depth broadcast + frame, max over ranks; stage times are rank 0's"}), flush=True)
-    eng.close()
+        m = n - args.warmup
+        names = ["view", "track", "allocate", "integrate", "expected_depths", "raycast+barrier+compose", "icp_maps", "total"]
+        summary.update({"frames": m, "frames_per_s": m / (float(t[0]) * 1e-3), "ms_per_frame": float(t[0]) / m, "visible_blocks": int(cnt[0]),
+                        "free_blocks_used_rank0": int(p.sdf_local_block_num - 1 - cnt[1]), "alloc_failures_rank0": int(cnt[3]),
+                        "stage_us_rank0": {a: round(1e3 * v / m, 1) for a, v in zip(names, stages)},
+                        "note": "total = CUDA events around NCCL depth broadcast + frame, max over ranks; stage times are rank 0's"})
+        eng.close()
     ok_t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
+    summary["ok"] = bool(int(ok_t[0]) == 1)
+    if rank == 0:
+        print(json.dumps({k: v for k, v in summary.items() if k != "check"}), flush=True)
+        if args.out:
+            with open(args.out, "w") as f:
+                json.dump(summary, f)
     dist.destroy_process_group()
-    sys.exit(0 if int(ok_t[0]) == 1 else 1)
+    sys.exit(0 if summary["ok"] else 1)
 
 
 if __name__ == "__main__":
