@@ -97,6 +97,9 @@ typedef struct itm_b200_params {
    * (ITMViewBuilder_CPU.cpp:38-46).  AFFINE: d * depth_calib_a + depth_calib_b.  KINECT_DISPARITY:
    * 8 * depth_calib_b * fx / (depth_calib_a - d)  (convertDisparityToDepth, DeviceAgnostic/ITMViewBuilder.h:7-20). */
   int depth_source;
+  /* settings.useBilateralFilter (ITMLibSettings.cpp:41, off by default): UpdateView runs five passes of the 5x5 bilateral depth
+   * filter (ITMViewBuilder_CPU.cpp:50-59).  settings.modelSensorNoise is implied by ITM_B200_TRACKER_WICP (ITMLibSettings.cpp:51-53). */
+  int use_bilateral_filter;
 } itm_b200_params;
 #define ITM_B200_VOXEL_S 0
 #define ITM_B200_VOXEL_S_RGB 1
@@ -296,6 +299,11 @@ int itm_b200_compute_normal_and_weights(itm_b200_ctx *ctx, float *normal_out_dev
  * is updated.  The map/pose fields of *ts are the tracker's inputs. */
 int itm_b200_track_camera(itm_b200_ctx *ctx, const float *depth_dev, itm_b200_tracking_state *ts);
 
+/* ITMWeightedICPTracker::TrackCamera (Engine/ITMWeightedICPTracker.cpp:164-192) with the whole Gauss-Newton loop on the device:
+ * depth pyramid from depth_dev, weight pyramid from depth_uncertainty_dev (view->depthUncertainty), per-pixel weights, no host
+ * round trip per evaluation.  ts->pose_d is updated. */
+int itm_b200_track_camera_weighted(itm_b200_ctx *ctx, const float *depth_dev, const float *depth_uncertainty_dev, itm_b200_tracking_state *ts);
+
 /* ===================================================================================== *
  *  Layer B - ITMMainEngine: owns scene, render state, tracking state and view in HBM    *
  *  and runs ProcessFrame (ITMLib/Engine/ITMMainEngine.cpp:111-127) without host syncs.  *
@@ -455,6 +463,10 @@ int itm_b200_engine_icp_stats(itm_b200_engine *e, int evals_per_level[ITM_B200_M
  * frame's device time without those gaps, ms8[0..6] are 0. */
 int itm_b200_engine_set_profiling(itm_b200_engine *e, int on);
 int itm_b200_engine_stage_times(itm_b200_engine *e, float ms8[8]);
+
+/* Sharded engines with set_profiling(1): device time of the last frame's partial ray cast, of the wait at the cross-GPU barrier
+ * (= how far behind the slowest rank was) and of the nearest-hit composition (NVLink peer reads), in milliseconds. */
+int itm_b200_engine_shard_times(itm_b200_engine *e, float ms3[3]);
 
 /* ---- host-side pose arithmetic (no GPU needed; used by the adapter and by tests) ---------- */
 /* Matrix4f::inv (ORUtils/Matrix.h:162-218) */

@@ -430,8 +430,16 @@ class ITMViewBuilder_B200 : public ITMViewBuilder {
     ITMView *view = *view_ptr;
     view->rgb->SetFrom(rgbImage, ORUtils::MemoryBlock<Vector4u>::CPU_TO_CUDA);
     this->shortImage->SetFrom(rawDepthImage, ORUtils::MemoryBlock<short>::CPU_TO_CUDA);
-    if (view->calib->disparityCalib.type != ITMDisparityCalib::TRAFO_AFFINE) DIEWITHEXCEPTION("libitm_b200: only TRAFO_AFFINE depth is provided");
-    this->ConvertDepthAffineToFloat(view->depth, this->shortImage, view->calib->disparityCalib.params);
+    switch (view->calib->disparityCalib.type) {  // ITMViewBuilder_CPU.cpp:38-48
+      case ITMDisparityCalib::TRAFO_KINECT:
+        this->ConvertDisparityToDepth(view->depth, this->shortImage, &(view->calib->intrinsics_d), view->calib->disparityCalib.params);
+        break;
+      case ITMDisparityCalib::TRAFO_AFFINE:
+        this->ConvertDepthAffineToFloat(view->depth, this->shortImage, view->calib->disparityCalib.params);
+        break;
+      default:
+        break;
+    }
     if (useBilateralFilter) {
       // 5 steps of bilateral filtering
       this->DepthFiltering(this->floatImage, view->depth);
@@ -445,7 +453,13 @@ class ITMViewBuilder_B200 : public ITMViewBuilder {
       this->ComputeNormalAndWeights(view->depthNormal, view->depthUncertainty, view->depth, view->calib->intrinsics_d.projectionParamsSimple.all);
   }
 
-  void ConvertDisparityToDepth(ITMFloatImage *, const ITMShortImage *, const ITMIntrinsics *, Vector2f) { DIEWITHEXCEPTION("libitm_b200: ConvertDisparityToDepth not provided"); }
+  // ITMViewBuilder_CPU.cpp:78-90: fx_depth = depthIntrinsics->projectionParamsSimple.fx
+  void ConvertDisparityToDepth(ITMFloatImage *depth_out, const ITMShortImage *depth_in, const ITMIntrinsics *depthIntrinsics, Vector2f disparityCalibParams) {
+    itm_b200_check(itm_b200_convert_disparity_to_depth(c->ctx, depth_out->GetData(MEMORYDEVICE_CUDA), depth_in->GetData(MEMORYDEVICE_CUDA),
+                                                       depth_in->noDims.x, depth_in->noDims.y, disparityCalibParams.x, disparityCalibParams.y,
+                                                       depthIntrinsics->projectionParamsSimple.fx),
+                   "ConvertDisparityToDepth");
+  }
   void UpdateView(ITMView **, ITMUChar4Image *, ITMFloatImage *) { DIEWITHEXCEPTION("libitm_b200: UpdateView(float depth) not provided"); }
   void UpdateView(ITMView **, ITMUChar4Image *, ITMShortImage *, bool, ITMIMUMeasurement *) { DIEWITHEXCEPTION("libitm_b200: UpdateView(imu) not provided"); }
 };
@@ -508,6 +522,23 @@ class ITMWeightedICPTracker_B200 : public ITMWeightedICPTracker {
       : ITMWeightedICPTracker(imgSize, trackingRegime, noHierarchyLevels, noICPRunTillLevel, distThresh, terminationThreshold, lowLevelEngine,
                               MEMORYDEVICE_CUDA),
         c(context) {}
+
+  /// true (default): the whole Gauss-Newton loop runs on the device (itm_b200_track_camera_weighted, no host round trip per
+  /// evaluation); false: the reference's own host loop (ITMWeightedICPTracker.cpp:164-192) over ComputeGandH below
+  bool useDeviceLoop = true;
+
+  void TrackCamera(ITMTrackingState *trackingState, const ITMView *view) {
+    if (!useDeviceLoop) {
+      ITMWeightedICPTracker::TrackCamera(trackingState, view);
+      return;
+    }
+    itm_b200_tracking_state t = b200_detail::tracking_state_view(trackingState);
+    itm_b200_check(itm_b200_track_camera_weighted(c->ctx, view->depth->GetData(MEMORYDEVICE_CUDA), view->depthUncertainty->GetData(MEMORYDEVICE_CUDA), &t),
+                   "TrackCamera (weighted)");
+    Matrix4f M;
+    for (int i = 0; i < 16; ++i) M.m[i] = t.pose_d[i];
+    trackingState->pose_d->SetM(M);
+  }
 
  protected:
   int ComputeGandH(float &f, float *nabla, float *hessian, Matrix4f approxInvPose) {

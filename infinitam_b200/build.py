@@ -13,7 +13,10 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libitm_b200.so")
+# ITM_B200_VARIANT=name builds an experimental variant next to the product library (libitm_b200_<name>.so, objects in
+# build_<name>/) with the extra defines of ITM_B200_DEFINES; tools select it with ITM_B200_LIB (capi.load)
+VARIANT = os.environ.get("ITM_B200_VARIANT", "")
+LIB = os.path.join(HERE, "libitm_b200%s.so" % ("_" + VARIANT if VARIANT else ""))
 SOURCES = ["engine.cu", "k_view.cu", "k_alloc.cu", "k_integrate.cu", "k_render.cu", "k_vis.cu", "k_mesh.cu", "k_icp.cu", "k_swap.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 EXTRA = os.environ.get("ITM_B200_DEFINES", "").split()  # e.g. -DITM_ICP_TRACE for tools/icp_trace.py
@@ -34,7 +37,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     headers.append(os.path.join(HERE, "..", "include", "itm_b200.h"))
     headers.append(os.path.abspath(__file__))
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" + ("_" + VARIANT if VARIANT else ""))
     os.makedirs(objdir, exist_ok=True)
     jobs = []
     for src in SOURCES:

@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libitm_b200.so")
+# ITM_B200_LIB: an experimental variant built by ITM_B200_VARIANT=... python -m infinitam_b200.build (A/B measurements only)
+LIB_PATH = os.environ.get("ITM_B200_LIB") or os.path.join(HERE, "libitm_b200.so")
 
 MAX_LEVELS = 8
 OK, EINVAL, ECUDA, ENODEVICE, EUNSUPPORTED = 0, -1, -2, -3, -4
@@ -54,6 +55,7 @@ class Params(C.Structure):
         ("icp_max_ctas", C.c_int),
         ("tracker_type", C.c_int),
         ("depth_source", C.c_int),
+        ("use_bilateral_filter", C.c_int),
     ]
 
 
@@ -120,7 +122,7 @@ SYMBOLS = [
     "itm_b200_engine_mesh_scene", "itm_b200_engine_save_scene_to_mesh",
     "itm_b200_take_cuda_error", "itm_b200_engine_get_stream", "itm_b200_engine_copy_to_buffer_dev", "itm_b200_compute_g_and_h_weighted", "itm_b200_depth_filtering", "itm_b200_compute_normal_and_weights", "itm_b200_swap_in_select", "itm_b200_swap_in_apply", "itm_b200_swap_out",
     "itm_b200_convert_disparity_to_depth", "itm_b200_engine_process_frame_with_pose", "itm_b200_engine_submit_frame",
-    "itm_b200_engine_wait_frame", "itm_b200_shard_block_resident",
+    "itm_b200_engine_wait_frame", "itm_b200_shard_block_resident", "itm_b200_engine_shard_times", "itm_b200_track_camera_weighted",
 ]
 
 _lib = None
@@ -177,6 +179,7 @@ def load():
     lib.itm_b200_depth_filtering.argtypes = [vp, vp, vp, C.c_int, C.c_int]
     lib.itm_b200_compute_normal_and_weights.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, f32p]
     lib.itm_b200_track_camera.argtypes = [vp, vp, C.POINTER(TrackingState)]
+    lib.itm_b200_track_camera_weighted.argtypes = [vp, vp, vp, C.POINTER(TrackingState)]
     lib.itm_b200_engine_create.argtypes = [C.POINTER(Params), C.POINTER(vp)]
     lib.itm_b200_engine_create_sharded.argtypes = [C.POINTER(Params), C.POINTER(Shard), C.POINTER(vp)]
     lib.itm_b200_ipc_alloc.argtypes = [C.c_size_t, C.POINTER(vp), C.c_char_p]
@@ -208,6 +211,7 @@ def load():
     lib.itm_b200_engine_icp_stats.argtypes = [vp, i32p]
     lib.itm_b200_engine_set_profiling.argtypes = [vp, C.c_int]
     lib.itm_b200_engine_stage_times.argtypes = [vp, f32p]
+    lib.itm_b200_engine_shard_times.argtypes = [vp, f32p]
     lib.itm_b200_mat4_inv.argtypes = [f32p, f32p]
     lib.itm_b200_pose_from_inv_m_coerced.argtypes = [f32p, f32p, f32p, f32p]
     lib.itm_b200_compute_delta.argtypes = [f32p, f32p, C.c_int, f32p]

@@ -102,6 +102,7 @@ struct itm_b200_ctx {
   FrameState *st = nullptr;    // device
   FrameState *hst = nullptr;   // pinned host mirror
   float *pyramid[ITM_MAX_LEVELS] = {nullptr};  // levels 1.. (level 0 is the caller's depth image)
+  float *weightPyramid[ITM_MAX_LEVELS] = {nullptr};  // TRACKER_WICP: levels 1.. of the depth-uncertainty hierarchy (allocated on first use)
   LevelCfg levels[ITM_MAX_LEVELS];
   int nLevels = 0;
 };
@@ -248,6 +249,7 @@ void ctx_free(itm_b200_ctx *c) {
   RELEASE(cudaFree(c->st));
   if (c->hst) RELEASE(cudaFreeHost(c->hst));
   for (int l = 1; l < ITM_MAX_LEVELS; ++l) RELEASE(cudaFree(c->pyramid[l]));
+  for (int l = 1; l < ITM_MAX_LEVELS; ++l) RELEASE(cudaFree(c->weightPyramid[l]));
   if (c->ownStream && c->stream) RELEASE(cudaStreamDestroy(c->stream));
 }
 
@@ -304,6 +306,7 @@ AllocArgs make_alloc_args(itm_b200_ctx *c, const float *depth, void *hash, const
   a.prologueDone = 0;
   memset(&a.shard, 0, sizeof(a.shard));
   a.shard.world = 1;
+  a.residentVisibleIds = nullptr;
   return a;
 }
 
@@ -337,13 +340,33 @@ IcpLevelArgs make_level_args(const itm_b200_ctx *c, int l, const float *depth) {
 }
 
 // ITMDepthTracker::TrackCamera: pyramid (unless already built) + LM loop, all enqueued
+int ensure_weight_pyramid(itm_b200_ctx *c) {
+  for (int l = 1; l < c->nLevels; ++l) {
+    if (c->weightPyramid[l]) continue;
+    const size_t n = (size_t)c->levels[l].w * c->levels[l].h;
+    CU(cudaMalloc(&c->weightPyramid[l], (n ? n : 1) * sizeof(float)));
+  }
+  return ITM_B200_OK;
+}
+
+// weight0 != NULL: ITMWeightedICPTracker (weight hierarchy from view->depthUncertainty, Gauss-Newton)
 int enqueue_track(itm_b200_ctx *c, const float *depth0, const float *points, const float *normals, bool buildPyramid,
-                  bool epochBumped = false) {
+                  bool epochBumped = false, const float *weight0 = nullptr) {
   cudaStream_t s = c->stream;
   if (buildPyramid && c->nLevels > 1) {
     float *lv[ITM_MAX_LEVELS];
     lv[0] = const_cast<float *>(depth0);
     for (int l = 1; l < c->nLevels; ++l) lv[l] = c->pyramid[l];
+    launch_view_pyramid(nullptr, 0.f, 0.f, lv, c->vp.W, c->vp.H, c->nLevels, s);
+    g_launches += 1 + (c->nLevels > 5 ? c->nLevels - 5 : 0);
+  }
+  if (weight0 && c->nLevels > 1) {
+    // PrepareForEvaluation's second hierarchy (ITMWeightedICPTracker.cpp:84-85): the same hole-aware subsampling of sigma_z
+    int rc = ensure_weight_pyramid(c);
+    if (rc) return rc;
+    float *lv[ITM_MAX_LEVELS];
+    lv[0] = const_cast<float *>(weight0);
+    for (int l = 1; l < c->nLevels; ++l) lv[l] = c->weightPyramid[l];
     launch_view_pyramid(nullptr, 0.f, 0.f, lv, c->vp.W, c->vp.H, c->nLevels, s);
     g_launches += 1 + (c->nLevels > 5 ? c->nLevels - 5 : 0);
   }
@@ -359,10 +382,11 @@ int enqueue_track(itm_b200_ctx *c, const float *depth0, const float *points, con
   int iters[ITM_MAX_LEVELS];
   for (int l = 0; l < c->nLevels; ++l) {
     lv[l] = make_level_args(c, l, l == 0 ? depth0 : c->pyramid[l]);
+    if (weight0) lv[l].weight = l == 0 ? weight0 : c->weightPyramid[l];
     iters[l] = c->levels[l].noIterations;
   }
   const cudaError_t e = launch_icp_track(a, lv, iters, c->nLevels, c->p.no_icp_run_till_level, c->icpRows, c->icpBcast, c->icpEpochDev,
-                                         !epochBumped, c->p.icp_max_ctas, s);
+                                         !epochBumped, c->p.icp_max_ctas, s, weight0 != nullptr);
   if (e != cudaSuccess) {
     cudaGetLastError();
     return fail(ITM_B200_ECUDA, std::string("cooperative launch of the ICP tracker failed: ") + cudaGetErrorString(e));
@@ -510,6 +534,7 @@ static int integrate_layer_a(itm_b200_ctx *c, itm_b200_scene *scene, const itm_b
   int rc = push_state(c);
   if (rc) return rc;
   IntegrateArgs a;
+  a.residentList = 0;
   fill_integrate_calib(c, a, rgb_dev);
   a.depth = depth_dev;
   a.voxels = scene->voxel_blocks_dev;
@@ -957,6 +982,21 @@ int itm_b200_track_camera(itm_b200_ctx *c, const float *depth_dev, itm_b200_trac
   return ITM_B200_OK;
 }
 
+int itm_b200_track_camera_weighted(itm_b200_ctx *c, const float *depth_dev, const float *depth_uncertainty_dev, itm_b200_tracking_state *ts) {
+  ON_DEVICE_OF_CTX(c);
+  if (!c || !depth_dev || !depth_uncertainty_dev || !ts) return fail(ITM_B200_EINVAL, "NULL argument");
+  set_pose_host(c->hst, ts->pose_d);
+  memcpy(c->hst->scenePose, ts->pose_point_cloud, 64);
+  int rc = push_state(c);
+  if (rc) return rc;
+  rc = enqueue_track(c, depth_dev, ts->points_map_dev, ts->normals_map_dev, true, false, depth_uncertainty_dev);
+  if (rc) return rc;
+  rc = pull_state(c);
+  if (rc) return rc;
+  memcpy(ts->pose_d, c->hst->M_d, 64);
+  return ITM_B200_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // host pose helpers
 int itm_b200_mat4_inv(const float m[16], float out[16]) { return mat4_inv(m, out) ? ITM_B200_OK : ITM_B200_EINVAL; }
@@ -985,6 +1025,7 @@ struct itm_b200_engine {
   int *vbaAllocList = nullptr;
   int *excessAllocList = nullptr;
   // render state
+  int *residentVisibleIds = nullptr;  // sharded scenes: visible entries whose block is resident on this rank
   int *visibleIds = nullptr;
   unsigned char *visType = nullptr;
   float *minmax = nullptr;
@@ -1019,6 +1060,8 @@ struct itm_b200_engine {
   cudaEvent_t forkEv = nullptr, joinEv = nullptr;
   bool overlapExpectedDepths = false;
   float *depth = nullptr;
+  // TRACKER_WICP / useBilateralFilter: ITMViewBuilder's floatImage, view->depthNormal, view->depthUncertainty
+  float *floatImage = nullptr, *depthNormal = nullptr, *depthUncertainty = nullptr;
   int agePointCloud = -1;  // host copy; its evolution does not depend on device results
   bool haveView = false;      // a frame has been given to the engine (ITMMainEngine::view != NULL)
   bool prologueDone = false;  // this frame's view kernel already did the FramePrologue chores
@@ -1060,6 +1103,7 @@ struct itm_b200_engine {
   unsigned long long submitCount = 0;
   int profiling = 0;  // 0 off, 1 a time stamp at every stage boundary, 2 frame start and end only
   cudaEvent_t ev[9] = {nullptr};
+  cudaEvent_t shardEv[4] = {nullptr};  // sharded + profiling: before the march, after it, after the barrier, after the composition
   float stageMs[8] = {0};
   size_t bytes[ITM_B200_BUF_COUNT] = {0};
 };
@@ -1073,7 +1117,10 @@ int engine_alloc(itm_b200_engine *e) {
   CU(cudaMalloc(&e->hash, (size_t)c->sp.nEntries * 16));
   CU(cudaMalloc(&e->vbaAllocList, (size_t)c->sp.nLocal * 4));
   CU(cudaMalloc(&e->excessAllocList, (size_t)c->sp.nExcess * 4));
-  CU(cudaMalloc(&e->visibleIds, (size_t)c->sp.nLocal * 4));
+  // the visible list of a sharded scene lists the whole scene's visible entries, not just this rank's pool
+  const size_t visCap = (size_t)c->sp.nLocal * (e->shard.world > 1 ? e->shard.world : 1);
+  CU(cudaMalloc(&e->visibleIds, visCap * 4));
+  if (e->shard.world > 1) CU(cudaMalloc(&e->residentVisibleIds, (size_t)c->sp.nLocal * 4));
   CU(cudaMalloc(&e->visType, (size_t)((c->sp.nEntries + 8191) / 8192) * 8192));
   CU(cudaMalloc(&e->minmax, P * 8));
   if (!e->externalBuffers) CU(cudaMalloc(&e->raycastResult, P * 16));
@@ -1093,7 +1140,16 @@ int engine_alloc(itm_b200_engine *e) {
   CU(cudaEventCreateWithFlags(&e->joinEv, cudaEventDisableTiming));
   e->overlapExpectedDepths = !c->p.use_swapping && e->shard.world == 1 && getenv("ITM_B200_OVERLAP") != nullptr;
   CU(cudaMalloc(&e->depth, P * 4));
+  if (c->p.use_bilateral_filter) CU(cudaMalloc(&e->floatImage, P * 4));
+  if (c->p.tracker_type == ITM_B200_TRACKER_WICP) {
+    CU(cudaMalloc(&e->depthNormal, P * 16));
+    CU(cudaMalloc(&e->depthUncertainty, P * 4));
+    int rcw = ensure_weight_pyramid(c);
+    if (rcw) return rcw;
+  }
   for (int i = 0; i < 9; ++i) CU(cudaEventCreate(&e->ev[i]));
+  if (e->shard.world > 1)
+    for (int i = 0; i < 4; ++i) CU(cudaEventCreate(&e->shardEv[i]));
   CU(cudaMallocHost(&e->poseStage, ITM_RESULT_RING * 38 * sizeof(float)));
   CU(cudaHostAlloc(&e->resultRing, ITM_RESULT_RING * sizeof(FrameResult), cudaHostAllocMapped));
   memset(e->resultRing, 0, ITM_RESULT_RING * sizeof(FrameResult));
@@ -1122,7 +1178,7 @@ int engine_alloc(itm_b200_engine *e) {
   e->bytes[ITM_B200_BUF_HASH] = (size_t)c->sp.nEntries * 16;
   e->bytes[ITM_B200_BUF_VBA_ALLOC_LIST] = (size_t)c->sp.nLocal * 4;
   e->bytes[ITM_B200_BUF_EXCESS_ALLOC_LIST] = (size_t)c->sp.nExcess * 4;
-  e->bytes[ITM_B200_BUF_VISIBLE_IDS] = (size_t)c->sp.nLocal * 4;
+  e->bytes[ITM_B200_BUF_VISIBLE_IDS] = visCap * 4;
   e->bytes[ITM_B200_BUF_VISIBLE_TYPES] = (size_t)c->sp.nEntries;
   e->bytes[ITM_B200_BUF_DEPTH] = P * 4;
   e->bytes[ITM_B200_BUF_MINMAX] = P * 8;
@@ -1141,9 +1197,10 @@ int engine_alloc(itm_b200_engine *e) {
 void engine_free(itm_b200_engine *e) {
   if (!e->externalBuffers) { RELEASE(cudaFree(e->voxels)); RELEASE(cudaFree(e->raycastResult)); }
   RELEASE(cudaFree(e->hash)); RELEASE(cudaFree(e->vbaAllocList)); RELEASE(cudaFree(e->excessAllocList));
-  RELEASE(cudaFree(e->visibleIds)); RELEASE(cudaFree(e->visType)); RELEASE(cudaFree(e->minmax));
+  RELEASE(cudaFree(e->visibleIds)); RELEASE(cudaFree(e->residentVisibleIds)); RELEASE(cudaFree(e->visType)); RELEASE(cudaFree(e->minmax));
   RELEASE(cudaFree(e->raycastImage)); RELEASE(cudaFree(e->points)); RELEASE(cudaFree(e->normals)); RELEASE(cudaFree(e->rawDepth));
   RELEASE(cudaFree(e->rgb)); RELEASE(cudaFree(e->depth));
+  RELEASE(cudaFree(e->floatImage)); RELEASE(cudaFree(e->depthNormal)); RELEASE(cudaFree(e->depthUncertainty));
   RELEASE(cudaFree(e->forwardProjection)); RELEASE(cudaFree(e->fwdMissing)); RELEASE(cudaFree(e->stFree));
   RELEASE(cudaFree(e->freeVisibleIds)); RELEASE(cudaFree(e->freeMinmax)); RELEASE(cudaFree(e->freeRaycastResult)); RELEASE(cudaFree(e->freeImage));
   if (e->hstFree) RELEASE(cudaFreeHost(e->hstFree));
@@ -1170,6 +1227,8 @@ void engine_free(itm_b200_engine *e) {
   if (e->joinEv) RELEASE(cudaEventDestroy(e->joinEv));
   for (int i = 0; i < 9; ++i)
     if (e->ev[i]) RELEASE(cudaEventDestroy(e->ev[i]));
+  for (int i = 0; i < 4; ++i)
+    if (e->shardEv[i]) RELEASE(cudaEventDestroy(e->shardEv[i]));
   for (int i = 0; i < 6; ++i)
     if (e->frameGraph[i]) RELEASE(cudaGraphExecDestroy(e->frameGraph[i]));
   if (e->c) {
@@ -1185,7 +1244,7 @@ int engine_reset(itm_b200_engine *e) {
   g_launches += 1;
   // MemoryBlock constructors clear their memory (ORUtils/MemoryBlock.h:88-110)
   CU(cudaMemsetAsync(e->visType, 0, (size_t)((c->sp.nEntries + 8191) / 8192) * 8192, c->stream));
-  CU(cudaMemsetAsync(e->visibleIds, 0, (size_t)c->sp.nLocal * 4, c->stream));
+  CU(cudaMemsetAsync(e->visibleIds, 0, (size_t)c->sp.nLocal * 4 * (e->shard.world > 1 ? e->shard.world : 1), c->stream));
   CU(cudaMemsetAsync(e->raycastResult, 0, P * 16, c->stream));
   CU(cudaMemsetAsync(e->raycastImage, 0, P * 4, c->stream));
   CU(cudaMemsetAsync(e->forwardProjection, 0, P * 16, c->stream));
@@ -1196,6 +1255,9 @@ int engine_reset(itm_b200_engine *e) {
   CU(cudaMemsetAsync(e->minmax, 0, P * 8, c->stream));
   CU(cudaMemsetAsync(e->depth, 0, P * 4, c->stream));
   CU(cudaMemsetAsync(e->rgb, 0, P * 4, c->stream));
+  if (e->floatImage) CU(cudaMemsetAsync(e->floatImage, 0, P * 4, c->stream));
+  if (e->depthNormal) CU(cudaMemsetAsync(e->depthNormal, 0, P * 16, c->stream));
+  if (e->depthUncertainty) CU(cudaMemsetAsync(e->depthUncertainty, 0, P * 4, c->stream));
   CU(cudaMemsetAsync(c->allocKey, 0, (size_t)((c->sp.nEntries + 8191) / 8192) * 8192 * sizeof(unsigned), c->stream));
   if (e->swapStates) {
     CU(cudaMemsetAsync(e->swapStates, 0, (size_t)((c->sp.nEntries + 8191) / 8192) * 8192, c->stream));
@@ -1222,10 +1284,36 @@ void stage_view(itm_b200_engine *e, bool withPrologue) {
   lv[0] = e->depth;
   for (int l = 1; l < c->nLevels; ++l) lv[l] = c->pyramid[l];
   FramePrologue pro{c->st, e->visibleIds, e->visType, reinterpret_cast<float2 *>(e->minmax), c->vp.W * c->vp.H, c->icpEpochDev};
-  launch_view_pyramid(e->rawDepth, c->p.depth_calib_a, c->p.depth_calib_b, lv, c->vp.W, c->vp.H, c->nLevels, c->stream,
-                      withPrologue ? &pro : nullptr, c->p.depth_source == ITM_B200_DEPTH_KINECT_DISPARITY ? c->p.fx : 0.0f);
+  const float fxDisparity = c->p.depth_source == ITM_B200_DEPTH_KINECT_DISPARITY ? c->p.fx : 0.0f;
+  const bool wicp = c->p.tracker_type == ITM_B200_TRACKER_WICP;
+  if (!c->p.use_bilateral_filter && !wicp) {
+    launch_view_pyramid(e->rawDepth, c->p.depth_calib_a, c->p.depth_calib_b, lv, c->vp.W, c->vp.H, c->nLevels, c->stream,
+                        withPrologue ? &pro : nullptr, fxDisparity);
+    g_launches += 1 + (c->nLevels > 5 ? c->nLevels - 5 : 0);
+  } else {
+    // ITMViewBuilder::UpdateView with useBilateralFilter / modelSensorNoise (ITMViewBuilder_CPU.cpp:38-63): conversion, five
+    // filter passes, normals + sigma_z; then the tracker's two hierarchies (depth here, sigma_z in enqueue_track)
+    const int W = c->vp.W, H = c->vp.H;
+    launch_convert_depth(e->rawDepth, e->depth, W * H, c->p.depth_calib_a, c->p.depth_calib_b, c->stream, fxDisparity);
+    g_launches += 1;
+    if (c->p.use_bilateral_filter) {
+      launch_filter_depth(e->floatImage, e->depth, W, H, c->stream);
+      launch_filter_depth(e->depth, e->floatImage, W, H, c->stream);
+      launch_filter_depth(e->floatImage, e->depth, W, H, c->stream);
+      launch_filter_depth(e->depth, e->floatImage, W, H, c->stream);
+      launch_filter_depth(e->floatImage, e->depth, W, H, c->stream);
+      cudaMemcpyAsync(e->depth, e->floatImage, (size_t)W * H * 4, cudaMemcpyDeviceToDevice, c->stream);
+      g_launches += 5;
+    }
+    if (wicp) {
+      const float intr[4] = {c->vp.fx, c->vp.fy, c->vp.cx, c->vp.cy};
+      launch_normal_weight(e->depthNormal, e->depthUncertainty, e->depth, W, H, intr, c->stream);
+      g_launches += 1;
+    }
+    launch_view_pyramid(nullptr, 0.f, 0.f, lv, W, H, c->nLevels, c->stream, withPrologue ? &pro : nullptr);
+    g_launches += 1 + (c->nLevels > 5 ? c->nLevels - 5 : 0);
+  }
   e->prologueDone = withPrologue;
-  g_launches += 1 + (c->nLevels > 5 ? c->nLevels - 5 : 0);
 }
 
 // trackingState->requiresFullRendering (ITMTrackingController.cpp:15).  Without useApproximateRaycast it is always true and
@@ -1246,7 +1334,9 @@ int stage_track(itm_b200_engine *e) {
   // ITMTrackingController::Track (ITMTrackingController.cpp:11-16)
   // in a whole frame the view kernel has already advanced the tracker's launch number (FramePrologue)
   int rc = ITM_B200_OK;
-  if (frame_tracks(e)) rc = enqueue_track(e->c, e->depth, e->points, e->normals, false, e->prologueDone);
+  if (frame_tracks(e))
+    rc = enqueue_track(e->c, e->depth, e->points, e->normals, false, e->prologueDone,
+                       e->c->p.tracker_type == ITM_B200_TRACKER_WICP ? e->depthUncertainty : nullptr);
   stage_track_decide(e);
   return rc;
 }
@@ -1257,6 +1347,8 @@ void stage_allocate(itm_b200_engine *e) {
   a.prologueDone = e->prologueDone ? 1 : 0;
   a.swapStates = e->swapStates;
   a.shard = e->shard;
+  a.residentVisibleIds = e->residentVisibleIds;
+  if (e->shard.world > 1) a.visibleCapacity = c->sp.nLocal * e->shard.world;
   launch_allocate(a, c->stream);
   g_launches += e->prologueDone ? 3 : 4;
 }
@@ -1268,7 +1360,8 @@ void stage_integrate(itm_b200_engine *e) {
   a.depth = e->depth;
   a.voxels = e->voxels;
   a.hashTable = e->hash;
-  a.visibleIds = e->visibleIds;
+  a.visibleIds = e->residentVisibleIds ? e->residentVisibleIds : e->visibleIds;
+  a.residentList = e->residentVisibleIds ? 1 : 0;
   a.st = c->st;
   a.vp = c->vp;
   a.sp = c->sp;
@@ -1289,6 +1382,7 @@ RenderArgs engine_render_args(itm_b200_engine *e) {
   a.normalsMap = e->normals;
   a.raycastImage = e->raycastImage;
   a.minmaxReady = 0;
+  a.residentList = 0;
   a.gated = c->p.use_approximate_raycast ? 1 : 0;
   a.resultRing = e->resultRingDev;
   a.st = c->st;
@@ -1299,6 +1393,10 @@ RenderArgs engine_render_args(itm_b200_engine *e) {
 
 void stage_expected_depths(itm_b200_engine *e, cudaStream_t stream = nullptr) {
   RenderArgs a = engine_render_args(e);
+  if (e->residentVisibleIds) {
+    a.visibleIds = e->residentVisibleIds;
+    a.residentList = 1;
+  }
   a.minmaxReady = e->prologueDone ? 1 : 0;
   launch_expected_depths(a, stream ? stream : e->c->stream);
   g_launches += e->prologueDone ? 1 : 2;
@@ -1307,13 +1405,18 @@ void stage_expected_depths(itm_b200_engine *e, cudaStream_t stream = nullptr) {
 void stage_shard_barrier(itm_b200_engine *e);
 void stage_raycast(itm_b200_engine *e) {
   const RenderArgs a = engine_render_args(e);
+  const bool stamps = e->shard.world > 1 && e->profiling == 1;
+  if (stamps) cudaEventRecord(e->shardEv[0], e->c->stream);
   launch_raycast(a, e->c->stream);
   g_launches += 1;
   if (e->shard.world > 1) {
     // every rank's partial image and tile flags are complete and visible, then: nearest hit per pixel
+    if (stamps) cudaEventRecord(e->shardEv[1], e->c->stream);
     stage_shard_barrier(e);
+    if (stamps) cudaEventRecord(e->shardEv[2], e->c->stream);
     launch_raycast_compose(a, e->c->stream);
     g_launches += 1;
+    if (stamps) cudaEventRecord(e->shardEv[3], e->c->stream);
   }
 }
 void stage_icp_maps(itm_b200_engine *e) {
@@ -2129,6 +2232,14 @@ int itm_b200_engine_set_profiling(itm_b200_engine *e, int on) {
   ON_DEVICE_OF_ENGINE(e);
   if (!e) return fail(ITM_B200_EINVAL, "NULL engine");
   e->profiling = on < 0 ? 0 : (on > 2 ? 2 : on);
+  return ITM_B200_OK;
+}
+
+int itm_b200_engine_shard_times(itm_b200_engine *e, float ms3[3]) {
+  ON_DEVICE_OF_ENGINE(e);
+  if (!e || !ms3) return fail(ITM_B200_EINVAL, "NULL argument");
+  if (e->shard.world <= 1 || e->profiling != 1) return fail(ITM_B200_EINVAL, "needs a sharded engine with set_profiling(1)");
+  for (int i = 0; i < 3; ++i) CU(cudaEventElapsedTime(&ms3[i], e->shardEv[i], e->shardEv[i + 1]));
   return ITM_B200_OK;
 }
 

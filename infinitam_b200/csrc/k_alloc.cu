@@ -218,7 +218,9 @@ __global__ void __launch_bounds__(256) k_alloc_scan(unsigned *__restrict__ alloc
       sExB = exB;
       if (tile == numTiles - 1) {
         // counters always count down by the number of requests, successful or not (:186, :204-205)
-        st->lastFreeBlockId = st->allocBaseBlockId - (int)(exA + (sTotal & 0xFFFFu));
+        // (sharded engines pop their local free list once per RESIDENT block, in the loop below; the number of all requests is
+        // not what their pool loses)
+        if (sh.world <= 1) st->lastFreeBlockId = st->allocBaseBlockId - (int)(exA + (sTotal & 0xFFFFu));
         st->lastFreeExcessId = st->allocBaseExcessId - (int)(exB + (sTotal >> 16));
         st->reallocBaseBlockId = st->lastFreeBlockId;
       }
@@ -293,7 +295,7 @@ __global__ void __launch_bounds__(256) k_visible_scan(const unsigned char *__res
                                                       int *__restrict__ visibleIds, FrameState *st, SceneParams sp,
                                                       int visibleCapacity, unsigned long long *ticket, unsigned long long *tileState,
                                                       int numTiles, unsigned char *__restrict__ swapStates, HashEntry *__restrict__ table,
-                                                      const int *__restrict__ vbaAllocList) {
+                                                      const int *__restrict__ vbaAllocList, int *__restrict__ residentIds) {
   __shared__ unsigned sWarp[8];
   __shared__ unsigned sTotal;
   __shared__ unsigned sExA, sExB;
@@ -351,7 +353,17 @@ __global__ void __launch_bounds__(256) k_visible_scan(const unsigned char *__res
       if (table[slot0 + j].ptr == -1) reallocMask |= 1u << j;
     }
   }
-  const unsigned excl = block_exclusive_scan_256(cnt | ((unsigned)__popc(reallocMask) << 16), sWarp, &sTotal);
+  // sharded scenes (never swapping): the second count of the scan ranks the visible entries whose block is resident here
+  unsigned residentMask = 0;
+  if (residentIds) {
+    unsigned m = liveMask;
+    while (m) {
+      const int j = __ffs(m) - 1;
+      m &= m - 1;
+      if (table[slot0 + j].ptr >= 0) residentMask |= 1u << j;
+    }
+  }
+  const unsigned excl = block_exclusive_scan_256(cnt | ((unsigned)__popc(reallocMask | residentMask) << 16), sWarp, &sTotal);
   __syncthreads();
   if (threadIdx.x < 32) {
     unsigned exA, exB;
@@ -367,6 +379,7 @@ __global__ void __launch_bounds__(256) k_visible_scan(const unsigned char *__res
         }
         st->noVisibleEntries = total;
         if (swapStates) st->lastFreeBlockId = st->reallocBaseBlockId - (int)(exB + (sTotal >> 16));
+        if (residentIds) st->noResidentVisible = min((int)(exB + (sTotal >> 16)), sp.nLocal);
       }
     }
   }
@@ -378,6 +391,15 @@ __global__ void __launch_bounds__(256) k_visible_scan(const unsigned char *__res
     liveMask &= liveMask - 1;
     if (pos < visibleCapacity) visibleIds[pos] = slot0 + j;
     pos++;
+  }
+  if (residentMask) {
+    int posB = (int)(sExB + (excl >> 16));
+    while (residentMask) {
+      const int j = __ffs(residentMask) - 1;
+      residentMask &= residentMask - 1;
+      if (posB < sp.nLocal) residentIds[posB] = slot0 + j;
+      posB++;
+    }
   }
   if (reallocMask) {
     int vbaIdx = st->reallocBaseBlockId - (int)(sExB + (excl >> 16));
@@ -435,7 +457,8 @@ void launch_allocate(const AllocArgs &a, cudaStream_t s) {
                                         oneOverVoxelSize, stepBound, a.onlyUpdateVisibleList ? 0 : 1, a.scanTickets, a.allocTileState, numTiles, a.visibleIds,
                                         (a.swapStates && !a.onlyUpdateVisibleList) ? 1 : 0, a.shard);
   k_visible_scan<<<numTiles, 256, 0, s>>>(a.visType, a.visibleIds, a.st, a.sp, a.visibleCapacity, a.scanTickets + 1,
-                                          a.visTileState, numTiles, a.onlyUpdateVisibleList ? nullptr : a.swapStates, table, a.vbaAllocList);
+                                          a.visTileState, numTiles, a.onlyUpdateVisibleList ? nullptr : a.swapStates, table, a.vbaAllocList,
+                                          a.shard.world > 1 ? a.residentVisibleIds : nullptr);
 }
 
 }  // namespace itm

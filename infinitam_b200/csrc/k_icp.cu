@@ -298,6 +298,50 @@ __device__ __noinline__ bool lm_update(LmShared &L, const float *sSums, int iter
   return icp_has_converged(step, terminationThreshold);
 }
 
+// One iteration of ITMWeightedICPTracker::TrackCamera (ITMWeightedICPTracker.cpp:164-192): plain Gauss-Newton on the raw
+// sums (no division by the point count, no damping, no step rejection - f_old stays at its initial 1e10).  Returns true when
+// the level's loop ends (no valid points, f_new > f_old, or HasConverged).
+template <int noPara>
+__device__ __noinline__ bool gn_update(LmShared &L, const float *sSums, int iterationType, int level, float terminationThreshold) {
+  const int noValid = (int)sSums[0];
+  const float fNew = (noValid > 100) ? sqrtf(sSums[1]) / (float)noValid : 1e5f;
+  L.evalCount++;
+  L.levelEvals[level]++;
+  if (noValid <= 0) return true;
+  if (fNew > 1e10f) return true;
+  float H[36], nabla[6];
+#pragma unroll
+  for (int i = 0; i < 36; ++i) H[i] = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) nabla[i] = 0.0f;
+#pragma unroll
+  for (int r = 0, counter = 0; r < noPara; r++) {
+#pragma unroll
+    for (int c = 0; c <= r; c++, counter++) {
+      const float h = sSums[2 + noPara + counter];
+      H[r + c * 6] = h;
+      H[c + r * 6] = h;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < noPara; ++r) nabla[r] = sSums[2 + r];
+  float approxInvPose[16], M_d[16], params[6], step[6];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) approxInvPose[i] = L.approxInvPose[i];
+  icp_compute_delta(step, nabla, H, noPara == 3);
+  icp_apply_delta(approxInvPose, step, iterationType, approxInvPose);
+  pose_set_invM_coerce(approxInvPose, M_d, params);
+  mat4_inv(M_d, approxInvPose);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    L.M_d[i] = M_d[i];
+    L.approxInvPose[i] = approxInvPose[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) L.params[i] = params[i];
+  return icp_has_converged(step, terminationThreshold);
+}
+
 #ifdef ITM_ICP_TRACE
 __device__ unsigned long long g_icpTrace[64 * 8];
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -388,8 +432,10 @@ __device__ __forceinline__ float bilerp(float a, float b, float c, float d, floa
 }
 
 // rest of computePerPointGH_Depth_Ab (ITMDepthTracker.h:40-77) and the accumulation of ComputeGandH (..._CPU.cpp:60-66)
-template <bool shortIteration, bool rotationOnly, int NV>
-__device__ __forceinline__ void icp_accumulate(float *acc, const IcpPixel &q, IcpTaps &t, float distThresh, const float4 *__restrict__ normalsMap, int W) {
+// weighted (computePerPointGH_wICP, ITMWeightedICPTracker.h:66-69): sum b^2 w^2, and the normal is scaled by w after b was taken
+template <bool shortIteration, bool rotationOnly, int NV, bool weighted = false>
+__device__ __forceinline__ void icp_accumulate(float *acc, const IcpPixel &q, IcpTaps &t, float distThresh, const float4 *__restrict__ normalsMap, int W,
+                                               float localWeight = 1.0f) {
   constexpr int noPara = shortIteration ? 3 : 6;
   if (!q.inside) return;
   if (t.p[0].w < 0 || t.p[1].w < 0 || t.p[2].w < 0 || t.p[3].w < 0) return;
@@ -418,6 +464,7 @@ __device__ __forceinline__ void icp_accumulate(float *acc, const IcpPixel &q, Ic
     nz = bilerp(t.n[0].z, t.n[1].z, t.n[2].z, t.n[3].z, fx, fy);
   }
   const float b = nx * dx + ny * dy + nz * dz;
+  if (weighted) { nx *= localWeight; ny *= localWeight; nz *= localWeight; }
   float A[noPara];
   if (shortIteration) {
     if (rotationOnly) {
@@ -434,7 +481,7 @@ __device__ __forceinline__ void icp_accumulate(float *acc, const IcpPixel &q, Ic
     A[3] = nx; A[4] = ny; A[5] = nz;
   }
   acc[0] += 1.0f;
-  acc[1] += b * b;
+  acc[1] += weighted ? b * b * localWeight * localWeight : b * b;
 #pragma unroll
   for (int r = 0, counter = 0; r < noPara; r++) {
     acc[2 + r] += b * A[r];
@@ -476,7 +523,7 @@ __device__ __forceinline__ float warp_transpose_reduce(const float *acc) {
 
 // This CTA's share of one evaluation, pixels two at a time so that 16 gathers are in flight per thread; the CTA sum
 // (fp32 per thread and warp, fp64 across the 8 warps) is published as tagged words in rowOut[0..32).
-template <bool shortIteration, bool rotationOnly>
+template <bool shortIteration, bool rotationOnly, bool weighted = false>
 __device__ __forceinline__ void eval_to_row(const IcpLevelArgs &lv, const ViewParams &sv, const IcpConsts &c,
                                             const float4 *__restrict__ pointsMap, const float4 *__restrict__ normalsMap,
                                             double (*sPart)[ICP_NVALS], unsigned long long *rowOut, unsigned tag, int nCtas) {
@@ -508,9 +555,15 @@ __device__ __forceinline__ void eval_to_row(const IcpLevelArgs &lv, const ViewPa
     IcpPixel q1;
     const int y1 = i / lv.w;
     icp_project(q1, i - y1 * lv.w, y1, __ldg(lv.depth + i), lv, sv, c);
+    float localWeight = 1.0f;
+    if (weighted) {
+      // ITMWeightedICPTracker_CPU.cpp:46: minSigmaZ / sigma_z * 0.5 + 0.5, minSigmaZ = 0.0012
+      const float sz = __ldg(lv.weight + i);
+      localWeight = sz > 0 ? 0.0012f / sz * 0.5f + 0.5f : 0.0f;
+    }
     IcpTaps t1;
     icp_gather(t1, q1, pointsMap, normalsMap, sv.W);
-    icp_accumulate<shortIteration, rotationOnly, NV>(acc, q1, t1, lv.distThresh, normalsMap, sv.W);
+    icp_accumulate<shortIteration, rotationOnly, NV, weighted>(acc, q1, t1, lv.distThresh, normalsMap, sv.W, localWeight);
   }
 #endif
   const float tot = warp_transpose_reduce<NV>(acc);  // lane l: warp total of value l
@@ -569,6 +622,8 @@ __device__ __forceinline__ void gather_rows(const unsigned long long *rows, int 
 // broadcasts the next pose together with the "level finished" flag in slot evalNo of the ring; everybody (active or
 // not) follows the ring, so all CTAs walk the same sequence of levels and iterations.
 // (A fixed master keeps the long straight-line LM code warm in one SM's instruction cache.)
+// WICP: ITMWeightedICPTracker (per-pixel weights from the depth uncertainty, Gauss-Newton) instead of ITMDepthTracker (LM).
+template <bool WICP>
 __global__ void __launch_bounds__(ICP_THREADS, ICP_CTAS_PER_SM) k_icp_track(TrackArgs t) {
   __shared__ IcpConsts c;
   __shared__ double sPart[ICP_THREADS / 32][ICP_NVALS];
@@ -622,9 +677,9 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_CTAS_PER_SM) k_icp_track(Trac
       if (blockIdx.x < nActive) {
         if (master && threadIdx.x == 0) { TRACE(evalNo, 0); }
         unsigned long long *myRow = t.rows + (size_t)blockIdx.x * ICP_NVALS;
-        if (type == ITM_ITER_ROTATION) eval_to_row<true, true>(lv, sSv, c, pointsMap, normalsMap, sPart, myRow, tag, nActive);
-        else if (type == ITM_ITER_TRANSLATION) eval_to_row<true, false>(lv, sSv, c, pointsMap, normalsMap, sPart, myRow, tag, nActive);
-        else eval_to_row<false, false>(lv, sSv, c, pointsMap, normalsMap, sPart, myRow, tag, nActive);
+        if (type == ITM_ITER_ROTATION) eval_to_row<true, true, WICP>(lv, sSv, c, pointsMap, normalsMap, sPart, myRow, tag, nActive);
+        else if (type == ITM_ITER_TRANSLATION) eval_to_row<true, false, WICP>(lv, sSv, c, pointsMap, normalsMap, sPart, myRow, tag, nActive);
+        else eval_to_row<false, false, WICP>(lv, sSv, c, pointsMap, normalsMap, sPart, myRow, tag, nActive);
       }
       unsigned long long *slot = t.bcast + (size_t)(evalNo & (ICP_RING - 1)) * ICP_BCAST_WORDS;
       if (master) {
@@ -632,8 +687,10 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_CTAS_PER_SM) k_icp_track(Trac
         gather_rows(t.rows, nActive, tag, sPart, sSums);
         if (threadIdx.x == 0) {
           TRACE(evalNo, 3);
-          const bool conv = (NV == 11) ? lm_update<3>(L, sSums, type, level, it == 0, t.a.terminationThreshold)
-                                       : lm_update<6>(L, sSums, type, level, it == 0, t.a.terminationThreshold);
+          bool conv;
+          if (WICP) conv = (NV == 11) ? gn_update<3>(L, sSums, type, level, t.a.terminationThreshold) : gn_update<6>(L, sSums, type, level, t.a.terminationThreshold);
+          else conv = (NV == 11) ? lm_update<3>(L, sSums, type, level, it == 0, t.a.terminationThreshold)
+                                 : lm_update<6>(L, sSums, type, level, it == 0, t.a.terminationThreshold);
           TRACE(evalNo, 4);
           TRACE_VAL(evalNo, 6, level);
           sFlags[evalNo & 1] = (conv || it == nIters - 1) ? 1u : 0u;
@@ -733,7 +790,7 @@ int icp_track_grid() {
   int &grid = gridOf[dev & 63];
   if (grid) return grid;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_icp_track, ICP_THREADS, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_icp_track<false>, ICP_THREADS, 0);
   if (perSm > ICP_CTAS_PER_SM) perSm = ICP_CTAS_PER_SM;
   if (perSm < 1) perSm = 1;
   grid = sms * perSm;
@@ -745,7 +802,7 @@ __global__ void k_icp_bump(unsigned *epochDev) { icp_bump_epoch(epochDev); }
 
 cudaError_t launch_icp_track(const IcpArgs &a, const IcpLevelArgs *levels, const int *iters, int nLevels, int noIcpLevel,
                              unsigned long long *rows, unsigned long long *bcast, unsigned *epochDev, bool bumpEpoch, int gridCap,
-                             cudaStream_t s) {
+                             cudaStream_t s, bool weighted) {
   TrackArgs t;
   t.a = a;
   for (int l = 0; l < ITM_MAX_LEVELS; ++l) {
@@ -767,7 +824,8 @@ cudaError_t launch_icp_track(const IcpArgs &a, const IcpLevelArgs *levels, const
   void *args[] = {&t};
   int grid = icp_track_grid();
   if (gridCap > 0 && gridCap < grid) grid = gridCap;
-  return cudaLaunchCooperativeKernel((const void *)k_icp_track, dim3(grid), dim3(ICP_THREADS), args, 0, s);
+  return cudaLaunchCooperativeKernel(weighted ? (const void *)k_icp_track<true> : (const void *)k_icp_track<false>, dim3(grid), dim3(ICP_THREADS),
+                                     args, 0, s);
 }
 
 size_t icp_rows_bytes() { return (size_t)icp_max_ctas() * ICP_NVALS * sizeof(unsigned long long); }

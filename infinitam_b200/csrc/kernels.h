@@ -65,9 +65,11 @@ struct AllocArgs {
   unsigned char *swapStates;     // ITMHashSwapState[nEntries] when the scene swaps (scene->useSwapping), else NULL
   int prologueDone;              // the marking pass already ran (FramePrologue)
   ShardInfo shard;               // world > 1: only resident blocks get a voxel block (local free list), the others ptr = -1
+  int *residentVisibleIds;       // sharded scenes: the visible entries with ptr >= 0, ascending (st->noResidentVisible); else NULL
 };
 
 struct IntegrateArgs {
+  int residentList;           // visibleIds is the resident-visible list: its length is st->noResidentVisible
   const unsigned char *rgb;   // view->rgb, Vector4u[W*H] (ITMVoxel_s_rgb only)
   float rgbIntr[4];           // intrinsics_rgb (fx, fy, cx, cy)
   float calibInv[16];         // trafo_rgb_to_depth.calib_inv
@@ -91,6 +93,7 @@ struct RenderArgs {
   float *normalsMap;    // Vector4f[W*H]
   unsigned char *raycastImage;  // Vector4u[W*H]
   int minmaxReady;      // the min/max image is already initialised (FramePrologue)
+  int residentList;     // visibleIds is the resident-visible list of a sharded scene (length st->noResidentVisible)
   int gated;            // useApproximateRaycast engines: raycast / ICP maps run only when st->requiresFullRendering
   FrameResult *resultRing;  // host-mapped ring of ITM_RESULT_RING slots the ICP-map kernel publishes pose + counters into (or NULL)
   FrameState *st;
@@ -191,7 +194,8 @@ void launch_view_pyramid(const short *raw, float a, float b, float *const *level
 // makes the launch parameters identical from frame to frame, so a whole frame can be replayed as a CUDA graph.
 cudaError_t launch_icp_track(const IcpArgs &a, const IcpLevelArgs *levels, const int *iters, int nLevels, int noIcpLevel,
                              unsigned long long *rows, unsigned long long *bcast, unsigned *epochDev, bool bumpEpoch, int gridCap,
-                             cudaStream_t s);  // gridCap > 0: at most that many CTAs (several scenes sharing one GPU)
+                             cudaStream_t s, bool weighted = false);  // gridCap > 0: at most that many CTAs (several scenes sharing one GPU)
+// weighted: ITMWeightedICPTracker - levels[l].weight = the level of the depth-uncertainty pyramid, Gauss-Newton instead of LM
 __device__ __forceinline__ void icp_bump_epoch(unsigned *epochDev) {  // 1 .. 2^32 - 1, never 0 (the scratch starts zeroed)
   const unsigned n = *epochDev + 1u;
   *epochDev = n ? n : 1u;

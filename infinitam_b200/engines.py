@@ -210,6 +210,12 @@ class ITMMainEngine:
         """True / 1: a time stamp at every stage boundary; 2: frame start and end only (no event nodes between the kernels)"""
         capi.check(self.lib.itm_b200_engine_set_profiling(self.h, int(on)))
 
+    def shard_times(self):
+        """sharded engine, profiling 1: (partial ray cast, barrier wait, composition) of the last frame in ms"""
+        ms = np.zeros(3, np.float32)
+        capi.check(self.lib.itm_b200_engine_shard_times(self.h, _f32p(ms)))
+        return ms
+
     def stage_times(self):
         ms = np.zeros(8, np.float32)
         capi.check(self.lib.itm_b200_engine_stage_times(self.h, _f32p(ms)))

@@ -181,7 +181,11 @@ def compare_frame(oracle, eng: ITMMainEngine, depth_i16, frame_no, report=None, 
     oracle.integrate()
     eng.RunStage(capi.STAGE_INTEGRATE)
     v_gpu = eng.read(capi.BUF_VOXELS)
-    ds, dw, ns, nw = voxel_diff(v_gpu, oracle.voxels)
+    v_ref = oracle.voxels
+    if v_gpu.dtype == np.uint32 and np.array_equal(v_gpu & np.uint32(0x00FFFFFF), v_ref & np.uint32(0x00FFFFFF)):
+        ds, dw, ns, nw = 0, 0, 0, 0  # identical up to the padding byte: skip the element-wise differences (33 M voxels)
+    else:
+        ds, dw, ns, nw = voxel_diff(v_gpu, v_ref)
     r["voxel_max_dsdf"], r["voxel_max_dw"], r["voxel_n_dsdf"], r["voxel_n_dw"] = ds, dw, ns, nw
     check(ds <= 1 and dw <= 1, "voxels differ by more than 1 LSB: sdf %d w %d" % (ds, dw))
     if v_gpu.dtype == np.uint64:

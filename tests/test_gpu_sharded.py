@@ -24,6 +24,21 @@ def _gpu_count():
         return 0
 
 
+def _json_objects(text):
+    """every JSON object in `text` (the ranks' lines may interleave)"""
+    dec, out, i = json.JSONDecoder(), [], 0
+    while True:
+        i = text.find("{", i)
+        if i < 0:
+            return out
+        try:
+            obj, end = dec.raw_decode(text, i)
+            out.append(obj)
+            i = end
+        except json.JSONDecodeError:
+            i += 1
+
+
 def _run(extra, nproc=2):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -37,7 +52,7 @@ def _run(extra, nproc=2):
 def test_two_rank_sharded_scene_matches_single_gpu():
     r = _run(["--check", "--frames", "8", "--size", "320x240", "--voxel", "0.005", "--pool", "0x10000"])
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-3000:]
-    recs = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{") and '"frame"' in l]
+    recs = [x for x in _json_objects(r.stdout) if "frame" in x]
     assert len(recs) == 2 * 2 * 8 and all(x["ok"] for x in recs)
     a = [x for x in recs if x["pass"].startswith("A")]
     # the payload really is partitioned: no rank holds every block, together they hold all of them
@@ -51,8 +66,8 @@ def test_two_ranks_hold_a_scene_that_overflows_one_pool():
     """per-rank pool of 0x1400 blocks: one GPU runs out (allocation failures), two GPUs hold the scene without any"""
     r = _run(["--frames", "4", "--warmup", "1", "--size", "320x240", "--voxel", "0.005", "--pool", "0x1400"])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    two = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    two = [x for x in _json_objects(r.stdout) if "alloc_failures_rank0" in x][-1]
     one = _run(["--frames", "4", "--warmup", "1", "--size", "320x240", "--voxel", "0.005", "--pool", "0x1400"], nproc=1)
     assert one.returncode == 0, one.stdout[-3000:] + one.stderr[-3000:]
-    one = json.loads([l for l in one.stdout.splitlines() if l.startswith("{")][-1])
+    one = [x for x in _json_objects(one.stdout) if "alloc_failures_rank0" in x][-1]
     assert one["alloc_failures_rank0"] > 0 and two["alloc_failures_rank0"] == 0

@@ -47,3 +47,14 @@ def test_small_voxels_teacher_forced():
     """2.5 mm voxels: ray segments span several blocks (more steps per pixel, more hash collisions)."""
     rows = _run(320, 240, 3, voxel_size=0.0025)
     assert all(r["hash_equal"] and r["visible_equal"] for r in rows)
+
+
+def test_vga_100_frames_teacher_forced():
+    """the whole BASELINE sequence (100 frames, 640x480, 5 mm): late-sequence states - longer excess chains, re-visited blocks
+    at w = maxW, 8 k visible blocks - are compared at full size, every stage of every frame against the real reference"""
+    rows = _run(640, 480, 100)
+    assert all(r["hash_equal"] and r["visible_equal"] and r["view_equal"] and r["minmax_equal"] for r in rows)
+    assert max(r["voxel_max_dsdf"] for r in rows) <= 1 and max(r["voxel_max_dw"] for r in rows) <= 1
+    assert max(r["raycast_hit_mismatch"] for r in rows) == 0 and max(r["raycast_max_diff_m"] for r in rows) <= 1e-4
+    assert max(r["pose_rot_rad"] for r in rows) <= 1e-4 and max(r["pose_trans_m"] for r in rows) <= 1e-4
+    assert rows[-1]["counters_ref"][0] > 7500  # the late frames really are the heavy ones

@@ -114,3 +114,31 @@ def test_weighted_icp_free_running(bilateral):
     moved = np.abs(o.pose_M - np.eye(4, dtype=np.float32).T.reshape(16)).max()
     assert moved > 0.02, "the tracker was supposed to follow the camera (moved %g)" % moved
     a.close(); o.close()
+
+
+@needs_libs
+@pytest.mark.parametrize("bilateral", [False, True], ids=["wicp", "wicp+bilateral-filter"])
+def test_weighted_icp_in_the_device_loop_layer_b(bilateral):
+    """TRACKER_WICP inside Layer B (no host round trip per evaluation: bilateral filter, sigma_z, both pyramids and the whole
+    Gauss-Newton loop are enqueued with the frame) against the reference CPU engines, free running"""
+    from infinitam_b200 import capi
+    w, h, n = 320, 240, 8
+    seq = synth.sequence(n, w, h)
+    o = ref.RefEngine(w, h, wicp=True, bilateral=bilateral)
+    p = parity.cuda_params(o)
+    p.tracker_type = capi.TRACKER_WICP
+    p.use_bilateral_filter = 1 if bilateral else 0
+    from infinitam_b200.engines import ITMMainEngine
+    eng = ITMMainEngine(p)
+    tol = 5e-4 if bilateral else 1e-4
+    for k in range(n):
+        o.process_frame(seq[k])
+        pose = eng.ProcessFrame(None, seq[k])
+        rot, trans = parity.pose_diff(pose, o.pose_M)
+        assert rot <= tol and trans <= tol, "frame %d pose differs: %g rad %g m" % (k, rot, trans)
+        if k > 0:
+            assert int(eng.icp_stats().sum()) >= 5  # every level evaluated at least once
+    _, _, st = eng.get_state()
+    assert abs(int(st[0]) - int(o.counters[0])) <= 0.01 * o.counters[0] + 2
+    eng.close()
+    o.close()

@@ -100,7 +100,7 @@ def main():
         eng = ShardedEngine(p, stream=tstream.cuda_stream)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
         eng.engine.set_profiling(True)
-        tot, stages, cnt = 0.0, np.zeros(8), None
+        tot, stages, cnt, sh3 = 0.0, np.zeros(8), None, np.zeros(3)
         for k in range(n):
             flush.fill_(k & 0xFF)
             torch.cuda.synchronize()
@@ -113,15 +113,22 @@ def main():
             _, cnt = eng.Sync()
             if k >= args.warmup:
                 stages += eng.engine.stage_times()
+                if world > 1:
+                    sh3 += eng.engine.shard_times()
                 tot += e0.elapsed_time(e1)
         t = torch.tensor([tot], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         m = n - args.warmup
+        per_rank = torch.tensor(list(stages) + list(sh3) + [float(p.sdf_local_block_num - 1 - cnt[1])], dtype=torch.float64, device="cuda")
+        gathered = [torch.empty_like(per_rank) for _ in range(world)]
+        dist.all_gather(gathered, per_rank)
         names = ["view", "track", "allocate", "integrate", "expected_depths", "raycast+barrier+compose", "icp_maps", "total"]
         summary.update({"frames": m, "frames_per_s": m / (float(t[0]) * 1e-3), "ms_per_frame": float(t[0]) / m, "visible_blocks": int(cnt[0]),
                         "free_blocks_used_rank0": int(p.sdf_local_block_num - 1 - cnt[1]), "alloc_failures_rank0": int(cnt[3]),
-                        "stage_us_rank0": {a: round(1e3 * v / m, 1) for a, v in zip(names, stages)},
-                        "note": "total = CUDA events around NCCL depth broadcast + frame, max over ranks; stage times are rank 0's"})
+                        "stage_us_per_rank": [{a: round(1e3 * float(v) / m, 1) for a, v in zip(names + ["partial_raycast", "barrier_wait", "compose"], g[:11])}
+                                              for g in gathered],
+                        "voxel_blocks_in_use_per_rank": [int(g[11]) for g in gathered],
+                        "note": "total = CUDA events around NCCL depth broadcast + frame, max over ranks"})
         eng.close()
     ok_t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
