@@ -18,6 +18,8 @@
 //     on the pose kept in FrameState, and releases the barrier; the others spin on the generation.
 //   * HasConverged() simply ends the level's loop - nothing is launched for skipped iterations.
 // k_icp_eval_single is the stand-alone evaluation behind the stage-level ComputeGandH entry point.
+#include <cstdlib>
+
 #include "itm_common.cuh"
 #include "kernels.h"
 #include "pose_math.cuh"
@@ -33,13 +35,13 @@ using namespace itm;
 #define ICP_CTAS_PER_SM 1
 #endif
 #define ICP_MAX_CTAS (148 * ICP_CTAS_PER_SM)
+#ifndef ICP_CHUNKS_PER_CTA
+#define ICP_CHUNKS_PER_CTA 2
+#endif
 #define ICP_NVALS 32  // 1 count + 1 f + 6 nabla + 21 hessian, padded
 #ifndef ICP_EARLY_NORMALS
-#define ICP_EARLY_NORMALS 0  // 1: issue the normal-map taps together with the point-map taps (more registers)
-#endif
-#ifndef ICP_BATCH
-#define ICP_BATCH 1   // pixels whose gathers a thread keeps in flight together (2 spills registers: slower)
-#endif
+#define ICP_EARLY_NORMALS 0  // issue the normal-map taps together with the point-map taps: 0 never, 1 always (the 29-value
+#endif                       // evaluation then spills), 2 in the short (rotation- / translation-only) evaluations
 
 __device__ __forceinline__ bool bilinear_holes(const float4 *__restrict__ src, float px, float py, int W, float &rx, float &ry,
                                                float &rz, float &rw) {
@@ -197,94 +199,65 @@ __device__ __forceinline__ void reduce_partials(const double *__restrict__ parti
   }
 }
 
+#ifdef ITM_ICP_TRACE
+__device__ unsigned long long g_icpTrace[64 * 32];
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define TRACE(slot, idx) if ((slot) < 64) g_icpTrace[(slot) * 32 + (idx)] = gtimer()
+#define TRACE_VAL(slot, idx, v) if ((slot) < 64) g_icpTrace[(slot) * 32 + (idx)] = (unsigned long long)(v)
+#ifndef ICP_TRACE_THREAD
+#define ICP_TRACE_THREAD 44
+#endif
+#define TRACE0(slot, idx) if (blockIdx.x == 0 && threadIdx.x == ICP_TRACE_THREAD) { TRACE(slot, idx); }
+__device__ __forceinline__ unsigned long long gtimer_after(float dep) {  // timestamp taken once dep is available
+  unsigned long long t;
+  asm volatile("{ .reg .f32 d; mov.f32 d, %1; mov.u64 %0, %globaltimer; }" : "=l"(t) : "f"(dep));
+  return t;
+}
+#define TRACE_DEP(slot, idx, dep) if (blockIdx.x == 0 && threadIdx.x == ICP_TRACE_THREAD && (slot) < 64) g_icpTrace[(slot) * 32 + (idx)] = gtimer_after(dep)
+__device__ unsigned long long g_icpCtaTrace[64 * 160 * 2];  // [evaluation][CTA]{pose received, row stored}
+#define TRACE_CTA(slot, idx) if ((slot) < 64 && threadIdx.x == 0) g_icpCtaTrace[((slot) * 160 + blockIdx.x) * 2 + (idx)] = gtimer()
+#else
+#define TRACE_CTA(slot, idx)
+#define TRACE_DEP(slot, idx, dep)
+#define TRACE(slot, idx)
+#define TRACE_VAL(slot, idx, v)
+#define TRACE0(slot, idx)
+#endif
+
 // Levenberg-Marquardt state of one TrackCamera call; lives in the master CTA's shared memory.
 struct LmShared {
   float M_d[16], params[6];           // trackingState->pose_d
   float approxInvPose[16];
   float lastGoodM[16], lastGoodParams[6];
   float Hgood[36], ngood[6];
+  float step[6];
   float fOld, lambda;
   int evalCount;
   int levelEvals[ITM_MAX_LEVELS];
 };
 
-// The LM bookkeeping of one iteration, ITMDepthTracker.cpp:167-197.  Run by one thread; noPara is a template
-// parameter so that every array index is static and the 6x6 system lives in registers.  Returns HasConverged().
-template <int noPara>
-__device__ __noinline__ bool lm_update(LmShared &L, const float *sSums, int iterationType, int level, bool firstIterOfLevel, float terminationThreshold) {
-  float M_d[16], params[6], approxInvPose[16];
+// Second half of one tracker iteration, the same for every parameter count and for both trackers (kept out of line so that
+// its instructions are fetched once, not once per caller: the first call of each caller in a launch runs from a cold
+// instruction cache): ApplyDelta, pose_d->SetInvM + Coerce, approxInvPose = pose_d->GetInvM(), HasConverged
+// (ITMDepthTracker.cpp:190-196).  In: L.approxInvPose (the pose the step applies to), L.step.  Out: L.M_d, L.params, L.approxInvPose.
+#ifndef ICP_LM_FINISH_ATTR
+#define ICP_LM_FINISH_ATTR __noinline__
+#endif
+__device__ ICP_LM_FINISH_ATTR bool lm_finish(LmShared &L, int iterationType, float terminationThreshold, int traceSlot) {
+  float approxInvPose[16], M_d[16], params[6], step[6];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) M_d[i] = L.M_d[i];
+  for (int i = 0; i < 16; ++i) approxInvPose[i] = L.approxInvPose[i];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) params[i] = L.params[i];
-  float fOld = L.fOld, lambda = L.lambda;
-  if (firstIterOfLevel) {
-    // approxInvPose = pose_d->GetInvM(); lastKnownGoodPose(*pose_d); f_old = 1e20f; lambda = 1.0  (:161-165)
-#pragma unroll
-    for (int i = 0; i < 16; ++i) L.lastGoodM[i] = M_d[i];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) L.lastGoodParams[i] = params[i];
-    fOld = 1e20f;
-    lambda = 1.0f;
-  }
-  const int noValid = (int)sSums[0];
-  const float fNew = (noValid > 100) ? sqrtf(sSums[1]) / (float)noValid : 1e5f;
-  L.evalCount++;
-  L.levelEvals[level]++;
-
-  float Hgood[36], ngood[6];
-  if ((noValid <= 0) || (fNew > fOld)) {
-    // revert to the last known good pose (:173-177)
-#pragma unroll
-    for (int i = 0; i < 16; ++i) M_d[i] = L.lastGoodM[i];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) params[i] = L.lastGoodParams[i];
-    mat4_inv(M_d, approxInvPose);
-    lambda *= 10.0f;
-#pragma unroll
-    for (int i = 0; i < 36; ++i) Hgood[i] = L.Hgood[i];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) ngood[i] = L.ngood[i];
-  } else {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) approxInvPose[i] = L.approxInvPose[i];  // == pose_d->GetInvM() on entering a level
-#pragma unroll
-    for (int i = 0; i < 16; ++i) L.lastGoodM[i] = M_d[i];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) L.lastGoodParams[i] = params[i];
-    fOld = fNew;
-    // hessian_good / nabla_good = new / noValidPoints.  Entries outside the noPara block are garbage in
-    // the reference (never read); zero here.
-#pragma unroll
-    for (int i = 0; i < 36; ++i) Hgood[i] = 0.0f;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) ngood[i] = 0.0f;
-#pragma unroll
-    for (int r = 0, counter = 0; r < noPara; r++) {
-#pragma unroll
-      for (int c = 0; c <= r; c++, counter++) {
-        const float h = sSums[2 + noPara + counter] / (float)noValid;
-        Hgood[r + c * 6] = h;
-        Hgood[c + r * 6] = h;
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < noPara; ++r) ngood[r] = sSums[2 + r] / (float)noValid;
-#pragma unroll
-    for (int i = 0; i < 36; ++i) L.Hgood[i] = Hgood[i];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) L.ngood[i] = ngood[i];
-    lambda /= 10.0f;
-  }
-  float A[36];
-#pragma unroll
-  for (int i = 0; i < 36; ++i) A[i] = Hgood[i];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) A[i + i * 6] *= 1.0f + lambda;
-  float step[6];
-  icp_compute_delta(step, ngood, A, noPara == 3);
+  for (int i = 0; i < 6; ++i) step[i] = L.step[i];
+  TRACE(traceSlot, 13);
   icp_apply_delta(approxInvPose, step, iterationType, approxInvPose);
+  TRACE(traceSlot, 14);
   pose_set_invM_coerce(approxInvPose, M_d, params);
+  TRACE(traceSlot, 15);
   mat4_inv(M_d, approxInvPose);
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
@@ -293,9 +266,97 @@ __device__ __noinline__ bool lm_update(LmShared &L, const float *sSums, int iter
   }
 #pragma unroll
   for (int i = 0; i < 6; ++i) L.params[i] = params[i];
+  return icp_has_converged(step, terminationThreshold);
+}
+
+// The LM bookkeeping of one iteration, ITMDepthTracker.cpp:167-197.  Run by one thread; noPara is a template
+// parameter so that every array index is static and the 6x6 system lives in registers.  Returns HasConverged().
+template <int noPara>
+__device__ __noinline__ bool lm_update(LmShared &L, const float *sSums, const float *sMeans, int iterationType, int level, bool firstIterOfLevel,
+                                       float terminationThreshold, int traceSlot) {
+  // (the state lives in shared memory and is touched only where an iteration needs it: this runs on one thread, every
+  // instruction is on the frame's critical path)
+  float fOld = L.fOld, lambda = L.lambda;
+  if (firstIterOfLevel) {
+    // approxInvPose = pose_d->GetInvM(); lastKnownGoodPose(*pose_d); f_old = 1e20f; lambda = 1.0  (:161-165)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) L.lastGoodM[i] = L.M_d[i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) L.lastGoodParams[i] = L.params[i];
+    fOld = 1e20f;
+    lambda = 1.0f;
+  }
+  const int noValid = (int)sSums[0];
+  const float fNew = (noValid > 100) ? sqrtf(sSums[1]) / (float)noValid : 1e5f;
+  L.evalCount++;
+  L.levelEvals[level]++;
+
+  // hessian_good / nabla_good: only the noPara x noPara block is ever read (entries outside it are garbage in the reference)
+  float A[noPara * noPara], ngood[noPara];
+  if ((noValid <= 0) || (fNew > fOld)) {
+    // revert to the last known good pose (:173-177)
+    float M_d[16], inv[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { M_d[i] = L.lastGoodM[i]; L.M_d[i] = M_d[i]; }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) L.params[i] = L.lastGoodParams[i];
+    mat4_inv(M_d, inv);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) L.approxInvPose[i] = inv[i];
+    lambda *= 10.0f;
+#pragma unroll
+    for (int r = 0; r < noPara; ++r) {
+      ngood[r] = L.ngood[r];
+#pragma unroll
+      for (int c = 0; c < noPara; ++c) A[r + c * noPara] = L.Hgood[r + c * 6];
+    }
+  } else {
+    // (L.approxInvPose == pose_d->GetInvM() already: it was set from the very same M_d)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) L.lastGoodM[i] = L.M_d[i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) L.lastGoodParams[i] = L.params[i];
+    fOld = fNew;
+    // hessian_good / nabla_good = new / noValidPoints (the quotients were taken by gather_rows, one per lane)
+#pragma unroll
+    for (int r = 0, counter = 0; r < noPara; r++) {
+#pragma unroll
+      for (int c = 0; c <= r; c++, counter++) {
+        const float h = sMeans[2 + noPara + counter];
+        A[r + c * noPara] = h;
+        A[c + r * noPara] = h;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < noPara; ++r) {
+      ngood[r] = sMeans[2 + r];
+      L.ngood[r] = ngood[r];
+#pragma unroll
+      for (int c = 0; c < noPara; ++c) L.Hgood[r + c * 6] = A[r + c * noPara];
+    }
+    lambda /= 10.0f;
+  }
+#pragma unroll
+  for (int i = 0; i < noPara; ++i) A[i + i * noPara] *= 1.0f + lambda;
+  float step[noPara];
+  TRACE(traceSlot, 12);
+  cholesky_solve<noPara>(A, ngood, step);  // ComputeDelta (:85-102)
+#pragma unroll
+  for (int i = 0; i < 6; ++i) L.step[i] = i < noPara ? step[i < noPara ? i : 0] : 0.0f;
   L.fOld = fOld;
   L.lambda = lambda;
-  return icp_has_converged(step, terminationThreshold);
+#ifdef ITM_ICP_TRACE_WARM  // experiment: how long does the second half take when its code was fetched a moment ago?
+  {
+    float save[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) save[i] = L.approxInvPose[i];
+    lm_finish(L, iterationType, terminationThreshold, 64);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) L.approxInvPose[i] = save[i];
+    TRACE(traceSlot, 21);
+  }
+#endif
+  return lm_finish(L, iterationType, terminationThreshold, traceSlot);
 }
 
 // One iteration of ITMWeightedICPTracker::TrackCamera (ITMWeightedICPTracker.cpp:164-192): plain Gauss-Newton on the raw
@@ -325,36 +386,13 @@ __device__ __noinline__ bool gn_update(LmShared &L, const float *sSums, int iter
   }
 #pragma unroll
   for (int r = 0; r < noPara; ++r) nabla[r] = sSums[2 + r];
-  float approxInvPose[16], M_d[16], params[6], step[6];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) approxInvPose[i] = L.approxInvPose[i];
+  float step[6];
   icp_compute_delta(step, nabla, H, noPara == 3);
-  icp_apply_delta(approxInvPose, step, iterationType, approxInvPose);
-  pose_set_invM_coerce(approxInvPose, M_d, params);
-  mat4_inv(M_d, approxInvPose);
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    L.M_d[i] = M_d[i];
-    L.approxInvPose[i] = approxInvPose[i];
-  }
-#pragma unroll
-  for (int i = 0; i < 6; ++i) L.params[i] = params[i];
-  return icp_has_converged(step, terminationThreshold);
+  for (int i = 0; i < 6; ++i) L.step[i] = step[i];
+  return lm_finish(L, iterationType, terminationThreshold, 64);
 }
 
-#ifdef ITM_ICP_TRACE
-__device__ unsigned long long g_icpTrace[64 * 8];
-__device__ __forceinline__ unsigned long long gtimer() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-#define TRACE(slot, idx) if ((slot) < 64) g_icpTrace[(slot) * 8 + (idx)] = gtimer()
-#define TRACE_VAL(slot, idx, v) if ((slot) < 64) g_icpTrace[(slot) * 8 + (idx)] = (unsigned long long)(v)
-#else
-#define TRACE(slot, idx)
-#define TRACE_VAL(slot, idx, v)
-#endif
 
 // ---- self-validating 64-bit words: [63:32] tag, [31:0] payload ------------------------------------------------
 // Everything that crosses CTAs inside the tracker travels as 8-byte words carrying their own tag (launch epoch and
@@ -386,6 +424,7 @@ struct TrackArgs {
   unsigned long long *rows;   // [maxCtas][32] CTA partial sums (float payload)
   unsigned long long *bcast;  // [ICP_RING][ICP_BCAST_WORDS] pose for the next evaluation + flags
   const unsigned *epochDev;   // launch number (never 0), advanced on the device before this launch
+  int chunksPerCta;           // coarse levels: 32-pixel chunks (warps) per active CTA
 };
 
 // What a thread needs to finish one pixel once the gathers have landed
@@ -395,19 +434,41 @@ struct IcpPixel {
   bool inside;
 };
 
-__device__ __forceinline__ void icp_project(IcpPixel &q, int x, int y, float depth, const IcpLevelArgs &lv, const ViewParams &sv,
-                                            const IcpConsts &c) {
+// what a level's pixels share: refined reciprocals of the level's focal lengths and the multiplier that turns
+// i / w into one IMAD.HI (exact for i * (magic * w - 2^32) < 2^32: any image below 2^24 pixels with w < 2^8.. 2^12)
+struct IcpLevelDerived {
+  float rcpFx, rcpFy;
+  unsigned wMagic;
+  bool focalOk;  // fx, fy far from the exponent limits: the inline division sequence is exact
+};
+__device__ __forceinline__ IcpLevelDerived icp_level_derived(const IcpLevelArgs &lv) {
+  IcpLevelDerived d;
+  const float ax = fabsf(lv.fx), ay = fabsf(lv.fy);
+  d.focalOk = ax > 1e-3f && ax < 1e6f && ay > 1e-3f && ay < 1e6f;
+  d.rcpFx = refined_rcp(d.focalOk ? lv.fx : 1.0f);
+  d.rcpFy = refined_rcp(d.focalOk ? lv.fy : 1.0f);
+  d.wMagic = (unsigned)((0x100000000ull + (unsigned)lv.w - 1) / (unsigned)lv.w);
+  return d;
+}
+
+// first half of computePerPointGH_Depth_Ab (ITMDepthTracker.h:17-38): back-project, move into the world, project into the
+// raycast maps.  The four divisions run the compiler's own IEEE fast-path sequence inline (shared reciprocals); operands
+// outside its comfortable range take the ordinary `/`.
+__device__ __forceinline__ void icp_project(IcpPixel &q, int x, int y, float depth, const IcpLevelArgs &lv, const IcpLevelDerived &ld,
+                                            const ViewParams &sv, const IcpConsts &c) {
   q.inside = false;
   q.u = 0.0f; q.v = 0.0f;
   if (depth <= 1e-8f) return;
-  const float tx = depth * (((float)x - lv.cx) / lv.fx);
-  const float ty = depth * (((float)y - lv.cy) / lv.fy);
+  const float tx = depth * safe_div((float)x - lv.cx, lv.fx, ld.rcpFx, ld.focalOk);
+  const float ty = depth * safe_div((float)y - lv.cy, lv.fy, ld.rcpFy, ld.focalOk);
   mat4_mul_vec4(c.approxInvPose, tx, ty, depth, 1.0f, q.wx, q.wy, q.wz);
   float rx, ry, rz;
   mat4_mul_vec4(c.scenePose, q.wx, q.wy, q.wz, 1.0f, rx, ry, rz);
   if (rz <= 0.0f) return;
-  q.u = sv.fx * rx / rz + sv.cx;
-  q.v = sv.fy * ry / rz + sv.cy;
+  const bool zOk = rz > 1e-3f && rz < 1e4f;
+  const float yz = refined_rcp(zOk ? rz : 1.0f);
+  q.u = safe_div(sv.fx * rx, rz, yz, zOk) + sv.cx;
+  q.v = safe_div(sv.fy * ry, rz, yz, zOk) + sv.cy;
   q.inside = (q.u >= 0.0f) && (q.u <= (float)(sv.W - 2)) && (q.v >= 0.0f) && (q.v <= (float)(sv.H - 2));
 }
 
@@ -416,15 +477,16 @@ struct IcpTaps {
 };
 
 // the 4 + 4 taps of interpolateBilinear_withHoles for points and normals, issued together
+template <bool EARLY>
 __device__ __forceinline__ void icp_gather(IcpTaps &t, const IcpPixel &q, const float4 *__restrict__ pointsMap,
                                            const float4 *__restrict__ normalsMap, int W) {
   if (!q.inside) return;
   const int ix = (short)(int)floorf(q.u), iy = (short)(int)floorf(q.v);
   const int o = ix + iy * W;
   t.p[0] = __ldg(pointsMap + o); t.p[1] = __ldg(pointsMap + o + 1); t.p[2] = __ldg(pointsMap + o + W); t.p[3] = __ldg(pointsMap + o + W + 1);
-#if ICP_EARLY_NORMALS
-  t.n[0] = __ldg(normalsMap + o); t.n[1] = __ldg(normalsMap + o + 1); t.n[2] = __ldg(normalsMap + o + W); t.n[3] = __ldg(normalsMap + o + W + 1);
-#endif
+  if (EARLY) {
+    t.n[0] = __ldg(normalsMap + o); t.n[1] = __ldg(normalsMap + o + 1); t.n[2] = __ldg(normalsMap + o + W); t.n[3] = __ldg(normalsMap + o + W + 1);
+  }
 }
 
 __device__ __forceinline__ float bilerp(float a, float b, float c, float d, float dx, float dy) {
@@ -433,7 +495,7 @@ __device__ __forceinline__ float bilerp(float a, float b, float c, float d, floa
 
 // rest of computePerPointGH_Depth_Ab (ITMDepthTracker.h:40-77) and the accumulation of ComputeGandH (..._CPU.cpp:60-66)
 // weighted (computePerPointGH_wICP, ITMWeightedICPTracker.h:66-69): sum b^2 w^2, and the normal is scaled by w after b was taken
-template <bool shortIteration, bool rotationOnly, int NV, bool weighted = false>
+template <bool shortIteration, bool rotationOnly, int NV, bool weighted, bool EARLY>
 __device__ __forceinline__ void icp_accumulate(float *acc, const IcpPixel &q, IcpTaps &t, float distThresh, const float4 *__restrict__ normalsMap, int W,
                                                float localWeight = 1.0f) {
   constexpr int noPara = shortIteration ? 3 : 6;
@@ -449,12 +511,10 @@ __device__ __forceinline__ void icp_accumulate(float *acc, const IcpPixel &q, Ic
   const float dx = cx - q.wx, dy = cy - q.wy, dz = cz - q.wz;
   const float dist = dx * dx + dy * dy + dz * dz;
   if (dist > distThresh) return;
-#if !ICP_EARLY_NORMALS
-  {
+  if (!EARLY) {
     const int o = ix + iy * W;
     t.n[0] = __ldg(normalsMap + o); t.n[1] = __ldg(normalsMap + o + 1); t.n[2] = __ldg(normalsMap + o + W); t.n[3] = __ldg(normalsMap + o + W + 1);
   }
-#endif
   float nx, ny, nz;
   if (t.n[0].w < 0 || t.n[1].w < 0 || t.n[2].w < 0 || t.n[3].w < 0) {
     nx = 0; ny = 0; nz = 0;  // interpolateBilinear_withHoles returns (0,0,0,-1); the reference does not test it here
@@ -521,12 +581,17 @@ __device__ __forceinline__ float warp_transpose_reduce(const float *acc) {
   return v[0];
 }
 
-// This CTA's share of one evaluation, pixels two at a time so that 16 gathers are in flight per thread; the CTA sum
-// (fp32 per thread and warp, fp64 across the 8 warps) is published as tagged words in rowOut[0..32).
+// This CTA's share of one evaluation.  Pixels are dealt in chunks of 32 consecutive ones (one warp-wide, coalesced depth
+// read); chunk k goes to CTA k mod nActive, warp slot k / nActive, so that a coarse level is spread over many SMs with
+// one or two warps each instead of filling a few SMs: its map taps are 2^level pixels apart (one 128-byte line per lane
+// and tap), and thousands of such line requests from one SM queue up behind each other (measured: 1.2-1.7 us for the
+// four point taps with 16 warps per SM against 0.5 us spread out).  The CTA sum (fp32 per thread and warp, fp64 across the
+// warps) is published as tagged words in rowOut[0..32).
 template <bool shortIteration, bool rotationOnly, bool weighted = false>
-__device__ __forceinline__ void eval_to_row(const IcpLevelArgs &lv, const ViewParams &sv, const IcpConsts &c,
+__device__ __forceinline__ void eval_to_row(const IcpLevelArgs &lv, const IcpLevelDerived &ld, const ViewParams &sv, const IcpConsts &c,
                                             const float4 *__restrict__ pointsMap, const float4 *__restrict__ normalsMap,
-                                            double (*sPart)[ICP_NVALS], unsigned long long *rowOut, unsigned tag, int nCtas) {
+                                            double (*sPart)[ICP_NVALS], unsigned long long *rowOut, unsigned tag, int cta, int nActive,
+                                            int traceSlot) {
   constexpr int noPara = shortIteration ? 3 : 6;
   constexpr int noParaSQ = shortIteration ? 6 : 21;
   constexpr int NV = 2 + noPara + noParaSQ;
@@ -534,27 +599,26 @@ __device__ __forceinline__ void eval_to_row(const IcpLevelArgs &lv, const ViewPa
 #pragma unroll
   for (int i = 0; i < NV; ++i) acc[i] = 0.0f;
   const int n = lv.w * lv.h;
-  const int stride = nCtas * ICP_THREADS;
-#if ICP_BATCH == 2
-  for (int i = blockIdx.x * ICP_THREADS + threadIdx.x; i < n; i += 2 * stride) {
-    const int i2 = i + stride;
-    const bool has2 = i2 < n;
-    const float d1 = __ldg(lv.depth + i), d2 = has2 ? __ldg(lv.depth + i2) : 0.0f;
-    IcpPixel q1, q2;
-    const int y1 = i / lv.w, y2 = i2 / lv.w;
-    icp_project(q1, i - y1 * lv.w, y1, d1, lv, sv, c);
-    icp_project(q2, i2 - y2 * lv.w, y2, d2, lv, sv, c);
-    IcpTaps t1, t2;
-    icp_gather(t1, q1, pointsMap, normalsMap, sv.W);
-    icp_gather(t2, q2, pointsMap, normalsMap, sv.W);
-    icp_accumulate<shortIteration, rotationOnly, NV>(acc, q1, t1, lv.distThresh, normalsMap, sv.W);
-    icp_accumulate<shortIteration, rotationOnly, NV>(acc, q2, t2, lv.distThresh, normalsMap, sv.W);
-  }
-#else
-  for (int i = blockIdx.x * ICP_THREADS + threadIdx.x; i < n; i += stride) {
+  const int nChunks = (n + 31) >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int chStride = nActive * (ICP_THREADS / 32);
+  int ch = cta + warp * nActive;
+  // the depth of a warp's next chunk is fetched while the current one is worked on (fine levels: several chunks per warp)
+  float dNext = (ch < nChunks && ch * 32 + lane < n) ? __ldg(lv.depth + ch * 32 + lane) : 0.0f;
+  for (; ch < nChunks; ch += chStride) {
+    const int i = ch * 32 + lane;
+    if (i >= n) break;
     IcpPixel q1;
-    const int y1 = i / lv.w;
-    icp_project(q1, i - y1 * lv.w, y1, __ldg(lv.depth + i), lv, sv, c);
+    const int y1 = (int)__umulhi((unsigned)i, ld.wMagic);
+    TRACE0(traceSlot, 20);
+    const float d1 = dNext;
+    {
+      const int iN = i + chStride * 32;
+      if (ch + chStride < nChunks && iN < n) dNext = __ldg(lv.depth + iN);
+    }
+    TRACE_DEP(traceSlot, 16, d1);
+    icp_project(q1, i - y1 * lv.w, y1, d1, lv, ld, sv, c);
+    TRACE_DEP(traceSlot, 17, q1.u + q1.v);
     float localWeight = 1.0f;
     if (weighted) {
       // ITMWeightedICPTracker_CPU.cpp:46: minSigmaZ / sigma_z * 0.5 + 0.5, minSigmaZ = 0.0012
@@ -562,14 +626,18 @@ __device__ __forceinline__ void eval_to_row(const IcpLevelArgs &lv, const ViewPa
       localWeight = sz > 0 ? 0.0012f / sz * 0.5f + 0.5f : 0.0f;
     }
     IcpTaps t1;
-    icp_gather(t1, q1, pointsMap, normalsMap, sv.W);
-    icp_accumulate<shortIteration, rotationOnly, NV, weighted>(acc, q1, t1, lv.distThresh, normalsMap, sv.W, localWeight);
+    constexpr bool EARLY = ICP_EARLY_NORMALS == 1 || (ICP_EARLY_NORMALS == 2 && shortIteration);
+    icp_gather<EARLY>(t1, q1, pointsMap, normalsMap, sv.W);
+    if (q1.inside) { TRACE_DEP(traceSlot, 18, t1.p[0].x + t1.p[1].y + t1.p[2].z + t1.p[3].w); }
+    icp_accumulate<shortIteration, rotationOnly, NV, weighted, EARLY>(acc, q1, t1, lv.distThresh, normalsMap, sv.W, localWeight);
+    TRACE_DEP(traceSlot, 19, acc[0] + acc[1] + acc[2] + acc[NV - 1]);
   }
-#endif
+  TRACE0(traceSlot, 8);
   const float tot = warp_transpose_reduce<NV>(acc);  // lane l: warp total of value l
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane < NV) sPart[warp][lane] = (double)tot;
+  TRACE0(traceSlot, 9);
   __syncthreads();
+  TRACE0(traceSlot, 10);
   if (threadIdx.x < ICP_NVALS) {
     double s = 0.0;
     if (threadIdx.x < NV) {
@@ -578,6 +646,8 @@ __device__ __forceinline__ void eval_to_row(const IcpLevelArgs &lv, const ViewPa
     }
     word_st(rowOut + threadIdx.x, __float_as_uint((float)s), tag);
   }
+  TRACE0(traceSlot, 11);
+  TRACE_CTA(traceSlot, 1);
   __syncthreads();  // sPart is reused by the caller
 }
 
@@ -585,26 +655,35 @@ __device__ __forceinline__ void eval_to_row(const IcpLevelArgs &lv, const ViewPa
 // the interleaved per-warp groups, groups ascending) -> sSums[0..32).  Each thread has all of its rows' loads in flight at once.
 #define ICP_GROUPS (ICP_THREADS / 32)
 #define ICP_ROWS_PER_THREAD ((ICP_MAX_CTAS + ICP_GROUPS - 1) / ICP_GROUPS)
-__device__ __forceinline__ void gather_rows(const unsigned long long *rows, int nRows, unsigned tag, double (*sPart)[ICP_NVALS], float *sSums) {
+__device__ __forceinline__ void gather_rows(const unsigned long long *rows, int nRows, unsigned tag, double (*sPart)[ICP_NVALS], float *sSums,
+                                            float *sMeans) {
   const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
   double s = 0.0;
-  constexpr int CH = 10;  // rows in flight per thread
-#pragma unroll 1
-  for (int k0 = 0; k0 < ICP_ROWS_PER_THREAD; k0 += CH) {
-    unsigned long long w[CH];
+  static_assert(ICP_ROWS_PER_THREAD <= 10, "all of a thread's rows are kept in flight together");
+  constexpr int CH = ICP_ROWS_PER_THREAD;
+  unsigned long long w[CH];
+#pragma unroll
+  for (int k = 0; k < CH; ++k) w[k] = 0ull;  // tag 0 is never used
+  // poll every outstanding row in the same round: the loads of one round are independent, so a round costs one L2 round
+  // trip whatever the number of rows still missing (polling row after row cost one trip per late row: up to 3 us)
+  bool pending;
+  do {
 #pragma unroll
     for (int k = 0; k < CH; ++k) {
-      const int r = g + ICP_GROUPS * (k0 + k);
-      w[k] = r < nRows ? word_ld(rows + (size_t)r * ICP_NVALS + lane) : 0ull;
+      const int r = g + ICP_GROUPS * k;
+      if (r < nRows && (unsigned)(w[k] >> 32) != tag) w[k] = word_ld(rows + (size_t)r * ICP_NVALS + lane);
     }
+    pending = false;
 #pragma unroll
     for (int k = 0; k < CH; ++k) {
-      const int r = g + ICP_GROUPS * (k0 + k);
-      if (r < nRows) {
-        while ((unsigned)(w[k] >> 32) != tag) w[k] = word_ld(rows + (size_t)r * ICP_NVALS + lane);
-        s += (double)__uint_as_float((unsigned)w[k]);
-      }
+      const int r = g + ICP_GROUPS * k;
+      pending = pending || (r < nRows && (unsigned)(w[k] >> 32) != tag);
     }
+  } while (pending);
+#pragma unroll
+  for (int k = 0; k < CH; ++k) {
+    const int r = g + ICP_GROUPS * k;
+    if (r < nRows) s += (double)__uint_as_float((unsigned)w[k]);
   }
   sPart[g][lane] = s;
   __syncthreads();
@@ -612,7 +691,12 @@ __device__ __forceinline__ void gather_rows(const unsigned long long *rows, int 
     double t = 0.0;
 #pragma unroll
     for (int q = 0; q < ICP_THREADS / 32; ++q) t += sPart[q][threadIdx.x];
-    sSums[threadIdx.x] = (float)t;
+    const float v = (float)t;
+    sSums[threadIdx.x] = v;
+    // hessian / noValidPoints and nabla / noValidPoints of the LM loop (ITMDepthTracker.cpp:181-182), one quotient per lane
+    // instead of 27 dependent-issue divisions on the thread that runs the update
+    const float cnt = (float)(int)__shfl_sync(0xffffffffu, v, 0);
+    sMeans[threadIdx.x] = v / cnt;
   }
   __syncthreads();
 }
@@ -627,8 +711,9 @@ template <bool WICP>
 __global__ void __launch_bounds__(ICP_THREADS, ICP_CTAS_PER_SM) k_icp_track(TrackArgs t) {
   __shared__ IcpConsts c;
   __shared__ double sPart[ICP_THREADS / 32][ICP_NVALS];
-  __shared__ float sSums[ICP_NVALS];
+  __shared__ float sSums[ICP_NVALS], sMeans[ICP_NVALS];
   __shared__ LmShared L;
+  __shared__ IcpLevelDerived sLd;
   __shared__ unsigned sFlags[2];  // double buffered by evaluation parity: a warp may run one evaluation ahead of a reader
   __shared__ IcpLevelArgs sLv;
   __shared__ ViewParams sSv;
@@ -636,7 +721,10 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_CTAS_PER_SM) k_icp_track(Trac
   const float4 *pointsMap = reinterpret_cast<const float4 *>(t.a.pointsMap);
   const float4 *normalsMap = reinterpret_cast<const float4 *>(t.a.normalsMap);
   const int nCtas = gridDim.x;
+  // (a master that evaluates no pixels - polling from the start of an evaluation, its instruction caches holding the update
+  // code only - was measured: 86.1 against 84.4 us per frame, the 148th evaluating CTA is worth more)
   const bool master = blockIdx.x == 0;
+  const int evalCta = (int)blockIdx.x;
 
   if (master && threadIdx.x == 0) { TRACE(63, 0); }
   if (threadIdx.x < 16) {
@@ -665,37 +753,46 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_CTAS_PER_SM) k_icp_track(Trac
     const int type = t.lv[level].iterationType;
     if (type == ITM_ITER_NONE) continue;
     __syncthreads();
-    if (threadIdx.x == 0) { sLv = t.lv[level]; sSv = t.a.sceneVp; }
+    if (threadIdx.x == 0) { sLv = t.lv[level]; sSv = t.a.sceneVp; sLd = icp_level_derived(t.lv[level]); }
     __syncthreads();
     const IcpLevelArgs &lv = sLv;
-    // coarse levels have fewer pixels than the grid has threads: only the first nActive CTAs evaluate
-    const int nActive = min(nCtas, (lv.w * lv.h + ICP_THREADS - 1) / ICP_THREADS);
+    // coarse levels have fewer 32-pixel chunks than the grid has warps: the first nActive CTAs evaluate, with about
+    // chunksPerCta warps each (see eval_to_row)
+    const int nChunks = (lv.w * lv.h + 31) >> 5;
+    const int nActive = max(1, min(nCtas, (nChunks + t.chunksPerCta - 1) / t.chunksPerCta));
     const int NV = (type == ITM_ITER_BOTH) ? 29 : 11;
     const int nIters = t.iters[level];
     for (int it = 0; it < nIters; ++it, ++evalNo) {
       const unsigned tag = icp_tag(epoch, evalNo);
-      if (blockIdx.x < nActive) {
-        if (master && threadIdx.x == 0) { TRACE(evalNo, 0); }
-        unsigned long long *myRow = t.rows + (size_t)blockIdx.x * ICP_NVALS;
-        if (type == ITM_ITER_ROTATION) eval_to_row<true, true, WICP>(lv, sSv, c, pointsMap, normalsMap, sPart, myRow, tag, nActive);
-        else if (type == ITM_ITER_TRANSLATION) eval_to_row<true, false, WICP>(lv, sSv, c, pointsMap, normalsMap, sPart, myRow, tag, nActive);
-        else eval_to_row<false, false, WICP>(lv, sSv, c, pointsMap, normalsMap, sPart, myRow, tag, nActive);
+      if (master && threadIdx.x == 0) { TRACE(evalNo, 0); }
+      if (evalCta >= 0 && evalCta < nActive) {
+        TRACE_CTA(evalNo, 0);
+        unsigned long long *myRow = t.rows + (size_t)evalCta * ICP_NVALS;
+        if (type == ITM_ITER_ROTATION) eval_to_row<true, true, WICP>(lv, sLd, sSv, c, pointsMap, normalsMap, sPart, myRow, tag, evalCta, nActive, evalNo);
+        else if (type == ITM_ITER_TRANSLATION) eval_to_row<true, false, WICP>(lv, sLd, sSv, c, pointsMap, normalsMap, sPart, myRow, tag, evalCta, nActive, evalNo);
+        else eval_to_row<false, false, WICP>(lv, sLd, sSv, c, pointsMap, normalsMap, sPart, myRow, tag, evalCta, nActive, evalNo);
       }
       unsigned long long *slot = t.bcast + (size_t)(evalNo & (ICP_RING - 1)) * ICP_BCAST_WORDS;
       if (master) {
         if (threadIdx.x == 0) { TRACE(evalNo, 1); }
-        gather_rows(t.rows, nActive, tag, sPart, sSums);
+        gather_rows(t.rows, nActive, tag, sPart, sSums, sMeans);
         if (threadIdx.x == 0) {
           TRACE(evalNo, 3);
           bool conv;
           if (WICP) conv = (NV == 11) ? gn_update<3>(L, sSums, type, level, t.a.terminationThreshold) : gn_update<6>(L, sSums, type, level, t.a.terminationThreshold);
-          else conv = (NV == 11) ? lm_update<3>(L, sSums, type, level, it == 0, t.a.terminationThreshold)
-                                 : lm_update<6>(L, sSums, type, level, it == 0, t.a.terminationThreshold);
+          else conv = (NV == 11) ? lm_update<3>(L, sSums, sMeans, type, level, it == 0, t.a.terminationThreshold, evalNo)
+                                 : lm_update<6>(L, sSums, sMeans, type, level, it == 0, t.a.terminationThreshold, evalNo);
           TRACE(evalNo, 4);
           TRACE_VAL(evalNo, 6, level);
           sFlags[evalNo & 1] = (conv || it == nIters - 1) ? 1u : 0u;
         }
-        __syncthreads();
+      }
+      unsigned long long w = 0ull;
+      if (!master && threadIdx.x < 17) {
+        while ((unsigned)((w = word_ld(slot + threadIdx.x)) >> 32) != epoch) { /* spin */ }
+      }
+      __syncthreads();  // the update is done (master) / every warp has finished reading the old pose (dry run)
+      if (master) {
         if (threadIdx.x < 16) {
           const float v = L.approxInvPose[threadIdx.x];
           c.approxInvPose[threadIdx.x] = v;
@@ -703,11 +800,10 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_CTAS_PER_SM) k_icp_track(Trac
         } else if (threadIdx.x == 16) {
           word_st(slot + 16, sFlags[evalNo & 1], epoch);
         }
-      } else if (threadIdx.x < 17) {
-        unsigned long long w;
-        while ((unsigned)((w = word_ld(slot + threadIdx.x)) >> 32) != epoch) { /* spin */ }
-        if (threadIdx.x < 16) c.approxInvPose[threadIdx.x] = __uint_as_float((unsigned)w);
-        else sFlags[evalNo & 1] = (unsigned)w;
+      } else if (threadIdx.x < 16) {
+        c.approxInvPose[threadIdx.x] = __uint_as_float((unsigned)w);
+      } else if (threadIdx.x == 16) {
+        sFlags[evalNo & 1] = (unsigned)w;
       }
       __syncthreads();
       if (master && threadIdx.x == 0) { TRACE(evalNo, 5); }
@@ -820,6 +916,13 @@ cudaError_t launch_icp_track(const IcpArgs &a, const IcpLevelArgs *levels, const
   t.rows = rows;
   t.bcast = bcast;
   t.epochDev = epochDev;
+  static int chunks = 0;  // ITM_B200_ICP_CHUNKS: A/B measurements
+  if (!chunks) {
+    const char *e = getenv("ITM_B200_ICP_CHUNKS");
+    chunks = e ? atoi(e) : ICP_CHUNKS_PER_CTA;
+    if (chunks < 1 || chunks > ICP_THREADS / 32) chunks = ICP_CHUNKS_PER_CTA;
+  }
+  t.chunksPerCta = chunks;
   if (bumpEpoch) k_icp_bump<<<1, 1, 0, s>>>(epochDev);
   void *args[] = {&t};
   int grid = icp_track_grid();
@@ -832,8 +935,11 @@ size_t icp_rows_bytes() { return (size_t)icp_max_ctas() * ICP_NVALS * sizeof(uns
 size_t icp_bcast_bytes() { return (size_t)ICP_RING * ICP_BCAST_WORDS * sizeof(unsigned long long); }
 
 #ifdef ITM_ICP_TRACE
-extern "C" int itm_b200_debug_icp_trace(unsigned long long *out512) {
-  return (int)cudaMemcpyFromSymbol(out512, g_icpTrace, sizeof(unsigned long long) * 512);
+extern "C" int itm_b200_debug_icp_cta_trace(unsigned long long *out) {
+  return (int)cudaMemcpyFromSymbol(out, g_icpCtaTrace, sizeof(unsigned long long) * 64 * 160 * 2);
+}
+extern "C" int itm_b200_debug_icp_trace(unsigned long long *out2048) {
+  return (int)cudaMemcpyFromSymbol(out2048, g_icpTrace, sizeof(unsigned long long) * 2048);
 }
 #endif
 
