@@ -82,6 +82,8 @@ __global__ void __launch_bounds__(256) k_alloc_pixels(const float *__restrict__ 
                                                       unsigned char *__restrict__ visType, unsigned *__restrict__ allocKey,
                                                       FrameState *st, ViewParams vp, SceneParams sp, float oneOverVoxelSize,
                                                       int stepBound) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float sInvM[16];
   if (threadIdx.x < 16) sInvM[threadIdx.x] = st->invM_d[threadIdx.x];
   __syncthreads();
@@ -154,6 +156,8 @@ __global__ void __launch_bounds__(256) k_alloc_scan(unsigned *__restrict__ alloc
   __shared__ unsigned sEpoch;
   __shared__ float sInvM[16];
   __shared__ float sM[16];
+  pdl_wait();
+  pdl_trigger();
   if (threadIdx.x == 0) {
     const unsigned long long t = atomicAdd(ticket, 1ull);
     sTile = (int)(t % (unsigned long long)numTiles);
@@ -301,6 +305,8 @@ __global__ void __launch_bounds__(256) k_visible_scan(const unsigned char *__res
   __shared__ unsigned sExA, sExB;
   __shared__ int sTile;
   __shared__ unsigned sEpoch;
+  pdl_wait();
+  pdl_trigger();
   if (threadIdx.x == 0) {
     const unsigned long long t = atomicAdd(ticket, 1ull);
     sTile = (int)(t % (unsigned long long)numTiles);
@@ -451,14 +457,14 @@ void launch_allocate(const AllocArgs &a, cudaStream_t s) {
   HashEntry *table = reinterpret_cast<HashEntry *>(a.hashTable);
   if (!a.prologueDone) k_mark_prev_visible<<<64, 256, 0, s>>>(a.visibleIds, a.visType, a.st);
   dim3 g((a.vp.W + 31) / 32, (a.vp.H + 7) / 8);
-  k_alloc_pixels<<<g, 256, 0, s>>>(a.depth, table, a.visType, a.allocKey, a.st, a.vp, a.sp, oneOverVoxelSize, stepBound);
+  launch_pdl(k_alloc_pixels, g, dim3(256), s, a.depth, (const HashEntry *)table, a.visType, a.allocKey, a.st, a.vp, a.sp, oneOverVoxelSize, stepBound);
   const int numTiles = (a.sp.nEntries + SCAN_TILE - 1) / SCAN_TILE;
-  k_alloc_scan<<<numTiles, 256, 0, s>>>(a.allocKey, table, a.visType, a.vbaAllocList, a.excessAllocList, a.depth, a.st, a.vp, a.sp,
-                                        oneOverVoxelSize, stepBound, a.onlyUpdateVisibleList ? 0 : 1, a.scanTickets, a.allocTileState, numTiles, a.visibleIds,
-                                        (a.swapStates && !a.onlyUpdateVisibleList) ? 1 : 0, a.shard);
-  k_visible_scan<<<numTiles, 256, 0, s>>>(a.visType, a.visibleIds, a.st, a.sp, a.visibleCapacity, a.scanTickets + 1,
-                                          a.visTileState, numTiles, a.onlyUpdateVisibleList ? nullptr : a.swapStates, table, a.vbaAllocList,
-                                          a.shard.world > 1 ? a.residentVisibleIds : nullptr);
+  launch_pdl(k_alloc_scan, dim3(numTiles), dim3(256), s, a.allocKey, table, a.visType, (const int *)a.vbaAllocList, (const int *)a.excessAllocList,
+             (const float *)a.depth, a.st, a.vp, a.sp, oneOverVoxelSize, stepBound, a.onlyUpdateVisibleList ? 0 : 1, a.scanTickets, a.allocTileState,
+             numTiles, (const int *)a.visibleIds, (a.swapStates && !a.onlyUpdateVisibleList) ? 1 : 0, a.shard);
+  launch_pdl(k_visible_scan, dim3(numTiles), dim3(256), s, (const unsigned char *)a.visType, a.visibleIds, a.st, a.sp, a.visibleCapacity,
+             a.scanTickets + 1, a.visTileState, numTiles, a.onlyUpdateVisibleList ? (unsigned char *)nullptr : a.swapStates, table,
+             (const int *)a.vbaAllocList, a.shard.world > 1 ? a.residentVisibleIds : (int *)nullptr);
 }
 
 }  // namespace itm

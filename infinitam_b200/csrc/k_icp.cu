@@ -721,6 +721,7 @@ __global__ void __launch_bounds__(ICP_THREADS, ICP_CTAS_PER_SM) k_icp_track(Trac
   const float4 *pointsMap = reinterpret_cast<const float4 *>(t.a.pointsMap);
   const float4 *normalsMap = reinterpret_cast<const float4 *>(t.a.normalsMap);
   const int nCtas = gridDim.x;
+  pdl_wait();  // (launched cooperatively, without programmatic serialisation: a no-op that keeps the chain's rule)
   // (a master that evaluates no pixels - polling from the start of an evaluation, its instruction caches holding the update
   // code only - was measured: 86.1 against 84.4 us per frame, the 148th evaluating CTA is worth more)
   const bool master = blockIdx.x == 0;

@@ -57,6 +57,8 @@ __global__ void __launch_bounds__(256) k_convert_pyramid(const short *__restrict
   __shared__ float s1[16][17];
   __shared__ float s2[8][9];
   __shared__ float s3[4][5];
+  pdl_wait();
+  pdl_trigger();
   const int W = args.w[0], H = args.h[0];
   const int tx0 = blockIdx.x * 32, ty0 = blockIdx.y * 32;
   const int tid = threadIdx.x;
@@ -264,7 +266,7 @@ void launch_view_pyramid(const short *raw, float a, float b, float *const *level
   const int fused = nLevels < 5 ? nLevels : 5;
   args.nLevels = fused;
   dim3 g((W + 31) / 32, (H + 31) / 32);
-  k_convert_pyramid<<<g, 256, 0, s>>>(raw, a, b, fxDisparity, args);
+  launch_pdl(k_convert_pyramid, g, dim3(256), s, raw, a, b, fxDisparity, args);
   for (int l = fused; l < nLevels; ++l) launch_subsample_holes(levels[l], levels[l - 1], args.w[l - 1], args.h[l - 1], s);
 }
 

@@ -3,7 +3,36 @@
 #include <cuda_runtime.h>
 #include "itm_common.cuh"
 
+#include <cstdlib>
+#include <utility>
+
 namespace itm {
+
+// Launch of a kernel that belongs to a frame's chain: with programmatic stream serialisation the kernel's CTAs may be placed
+// while its predecessor in the stream drains (itm_common.cuh, pdl_wait / pdl_trigger; a stream capture turns this into a
+// programmatic edge of the frame graph).  ITM_B200_PDL=0 launches plainly (A/B measurements).
+inline bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char *e = getenv("ITM_B200_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 #define ITM_MAX_SHARDS 8
 
