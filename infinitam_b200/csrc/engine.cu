@@ -81,6 +81,7 @@ struct itm_b200_ctx {
   bool ownStream = false;
   // scratch
   unsigned *allocKey = nullptr;
+  AllocLists allocLists = {};
   unsigned long long *scanTickets = nullptr;
   unsigned long long *allocTileState = nullptr;
   unsigned long long *visTileState = nullptr;
@@ -199,6 +200,21 @@ int ctx_alloc(itm_b200_ctx *c, void *stream) {
   CU(cudaMemsetAsync(c->allocTileState, 0, allocTiles * sizeof(unsigned long long), c->stream));
   CU(cudaMalloc(&c->visTileState, allocTiles * sizeof(unsigned long long)));
   CU(cudaMemsetAsync(c->visTileState, 0, allocTiles * sizeof(unsigned long long), c->stream));
+  {
+    AllocLists &L = c->allocLists;
+    L.numBins = (c->sp.nEntries + ITM_ALLOC_BIN - 1) / ITM_ALLOC_BIN;
+    const size_t nWords = (size_t)L.numBins * ITM_ALLOC_BIN / 32;
+    CU(cudaMalloc(&L.claimBits, nWords * sizeof(unsigned)));
+    CU(cudaMemsetAsync(L.claimBits, 0, nWords * sizeof(unsigned), c->stream));
+    CU(cudaMalloc(&L.reqList, (size_t)L.numBins * ITM_ALLOC_BIN * sizeof(int)));
+    CU(cudaMalloc(&L.newVisList, (size_t)L.numBins * ITM_ALLOC_BIN * sizeof(int)));
+    CU(cudaMalloc(&L.prevCopy, (size_t)(c->sp.nLocal + 32) * sizeof(int)));
+    CU(cudaMalloc(&L.prevKeep, (size_t)(c->sp.nLocal + 32)));
+    CU(cudaMalloc(&L.binCounts, (size_t)5 * L.numBins * sizeof(int)));
+    CU(cudaMemsetAsync(L.binCounts, 0, (size_t)5 * L.numBins * sizeof(int), c->stream));
+    CU(cudaMalloc(&L.done, sizeof(int)));
+    CU(cudaMemsetAsync(L.done, 0, sizeof(int), c->stream));
+  }
   CU(cudaMalloc(&c->otherTileState, numTiles * sizeof(unsigned long long)));
   CU(cudaMemsetAsync(c->otherTileState, 0, numTiles * sizeof(unsigned long long), c->stream));
   CU(cudaMalloc(&c->icpPartials, (size_t)icp_max_ctas() * 32 * sizeof(double)));
@@ -232,6 +248,13 @@ int ctx_alloc(itm_b200_ctx *c, void *stream) {
 void ctx_free(itm_b200_ctx *c) {
   if (!c) return;
   RELEASE(cudaFree(c->allocKey));
+  RELEASE(cudaFree(c->allocLists.claimBits));
+  RELEASE(cudaFree(c->allocLists.reqList));
+  RELEASE(cudaFree(c->allocLists.newVisList));
+  RELEASE(cudaFree(c->allocLists.prevCopy));
+  RELEASE(cudaFree(c->allocLists.prevKeep));
+  RELEASE(cudaFree(c->allocLists.binCounts));
+  RELEASE(cudaFree(c->allocLists.done));
   RELEASE(cudaFree(c->scanTickets));
   RELEASE(cudaFree(c->allocTileState));
   RELEASE(cudaFree(c->visTileState));
@@ -295,6 +318,7 @@ AllocArgs make_alloc_args(itm_b200_ctx *c, const float *depth, void *hash, const
   a.visType = visType;
   a.visibleCapacity = c->sp.nLocal;
   a.allocKey = c->allocKey;
+  a.lists = c->allocLists;
   a.scanTickets = c->scanTickets;
   a.allocTileState = c->allocTileState;
   a.visTileState = c->visTileState;
@@ -1283,7 +1307,9 @@ void stage_view(itm_b200_engine *e, bool withPrologue) {
   float *lv[ITM_MAX_LEVELS];
   lv[0] = e->depth;
   for (int l = 1; l < c->nLevels; ++l) lv[l] = c->pyramid[l];
-  FramePrologue pro{c->st, e->visibleIds, e->visType, reinterpret_cast<float2 *>(e->minmax), c->vp.W * c->vp.H, c->icpEpochDev};
+  FramePrologue pro{c->st, e->visibleIds, e->visType, reinterpret_cast<float2 *>(e->minmax), c->vp.W * c->vp.H, c->icpEpochDev,
+                    alloc_uses_lists(c->allocLists, false, e->swapStates != nullptr, e->shard.world, c->vp.W * c->vp.H, c->sp.nEntries)
+                        ? c->allocLists.claimBits : nullptr};
   const float fxDisparity = c->p.depth_source == ITM_B200_DEPTH_KINECT_DISPARITY ? c->p.fx : 0.0f;
   const bool wicp = c->p.tracker_type == ITM_B200_TRACKER_WICP;
   if (!c->p.use_bilateral_filter && !wicp) {

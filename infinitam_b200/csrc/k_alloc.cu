@@ -18,8 +18,14 @@
 //   3. k_visible_scan: same scan machinery over entriesVisibleType; visibleEntryIDs come out
 //      in ascending slot order like the reference's.  (The frustum re-check of last frame's entries
 //      runs one thread per entry at the start of k_alloc_scan.)
+//   2'/3'. Where the frame touches fewer table slots than the table has (kernels.h, alloc_uses_lists), steps 2 and 3 work on
+//      compact per-bin lists of the requested and the newly visible slots instead of walking all slots (k_alloc_assign,
+//      k_visible_merge, "Compact lists" below) - same results.
 // No counter is read back by the host; the free-list heads and the visible count live in
 // FrameState.
+#include <cstdlib>
+#include <cstring>
+
 #include "itm_common.cuh"
 #include "kernels.h"
 #include "scan_util.cuh"
@@ -69,19 +75,50 @@ __device__ __forceinline__ void block_of(float px, float py, float pz, int &bx, 
 
 // marks last frame's visible entries as "3" (:159-160) and snapshots the free-list heads the
 // allocation scan will count down from
-__global__ void k_mark_prev_visible(const int *__restrict__ visibleIds, unsigned char *__restrict__ visType, FrameState *st) {
+__global__ void k_mark_prev_visible(const int *__restrict__ visibleIds, unsigned char *__restrict__ visType, FrameState *st,
+                                    unsigned *__restrict__ claimBits) {
   const int n = st->noVisibleEntries;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     st->allocBaseBlockId = st->lastFreeBlockId;
     st->allocBaseExcessId = st->lastFreeExcessId;
   }
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) visType[visibleIds[i]] = 3;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int id = visibleIds[i];
+    visType[id] = 3;
+    if (claimBits) atomicOr(claimBits + (id >> 5), 1u << (id & 31));  // list-based allocation: "was visible when the frame began"
+  }
 }
 
+// LISTS (compact lists, see k_alloc_assign): besides the keys, the pass leaves per bin of ITM_ALLOC_BIN slots the list of slots
+// that were requested and the list of slots that became visible.  "Became visible" = not in last frame's list: the marking
+// pass that sets those entries' type to 3 also sets their claim bit, so a slot whose bit is still clear when this pass
+// touches it is new - the threads that see it clear race for the bit and the one winner lists the slot.  The bit is
+// tested through L1 (the array is 147 KB, every SM keeps its part): a stale line only costs a lost race.  (Deciding by
+// reading the slot's visible type before overwriting it was measured at 100 us: every store evicts the line the next
+// thread's load needs.)
+__device__ __forceinline__ bool claim_slot(unsigned *claimBits, int slot) {
+  unsigned *w = claimBits + (slot >> 5);
+  const unsigned bit = 1u << (slot & 31);
+  if (*w & bit) return false;        // through L1: set since the marking pass for nearly every slot a ray touches
+  if (__ldcg(w) & bit) return false; // a new slot: most of the few hundred threads that touch it find it taken here
+  return !(atomicOr(w, bit) & bit);
+}
+__device__ __forceinline__ void push_bin(int *list, int *counts, int slot, int value) {
+  const int bin = slot / ITM_ALLOC_BIN;
+  const int i = atomicAdd(counts + bin, 1);
+  if (i < ITM_ALLOC_BIN) list[(size_t)bin * ITM_ALLOC_BIN + i] = value;
+}
+template <bool LISTS>
+__device__ __forceinline__ void mark_visible(unsigned char *visType, int slot, unsigned char type, const itm::AllocLists &L) {
+  visType[slot] = type;
+  if (LISTS && claim_slot(L.claimBits, slot)) push_bin(L.newVisList, L.binCounts + 2 * L.numBins, slot, slot);
+}
+
+template <bool LISTS>
 __global__ void __launch_bounds__(256) k_alloc_pixels(const float *__restrict__ depth, const HashEntry *__restrict__ table,
                                                       unsigned char *__restrict__ visType, unsigned *__restrict__ allocKey,
                                                       FrameState *st, ViewParams vp, SceneParams sp, float oneOverVoxelSize,
-                                                      int stepBound) {
+                                                      int stepBound, const itm::AllocLists L) {
   pdl_wait();
   pdl_trigger();
   __shared__ float sInvM[16];
@@ -108,7 +145,7 @@ __global__ void __launch_bounds__(256) k_alloc_pixels(const float *__restrict__ 
     HashEntry e = load_entry(table, hashIdx);
     bool isFound = false;
     if (e.px == bx && e.py == by && e.pz == bz && e.ptr >= -1) {
-      visType[hashIdx] = (e.ptr == -1) ? 2 : 1;
+      mark_visible<LISTS>(visType, hashIdx, (e.ptr == -1) ? 2 : 1, L);
       isFound = true;
     }
     if (!isFound) {
@@ -118,7 +155,7 @@ __global__ void __launch_bounds__(256) k_alloc_pixels(const float *__restrict__ 
           hashIdx = sp.nBuckets + e.offset - 1;
           e = load_entry(table, hashIdx);
           if (e.px == bx && e.py == by && e.pz == bz && e.ptr >= -1) {
-            visType[hashIdx] = (e.ptr == -1) ? 2 : 1;
+            mark_visible<LISTS>(visType, hashIdx, (e.ptr == -1) ? 2 : 1, L);
             isFound = true;
             break;
           }
@@ -126,8 +163,12 @@ __global__ void __launch_bounds__(256) k_alloc_pixels(const float *__restrict__ 
         isExcess = true;
       }
       if (!isFound) {
-        atomicMax(allocKey + hashIdx, (unsigned)locId * (unsigned)stepBound + (unsigned)i + 1u);
-        if (!isExcess) visType[hashIdx] = 1;
+        const unsigned old = atomicMax(allocKey + hashIdx, (unsigned)locId * (unsigned)stepBound + (unsigned)i + 1u);
+        if (LISTS && old == 0) {  // the slot's first request of this frame
+          push_bin(L.reqList, L.binCounts, hashIdx, isExcess ? (hashIdx | (int)0x80000000) : hashIdx);
+          if (isExcess) atomicAdd(L.binCounts + L.numBins + hashIdx / ITM_ALLOC_BIN, 1);
+        }
+        if (!isExcess) mark_visible<LISTS>(visType, hashIdx, 1, L);
       }
     }
     px += r.dx; py += r.dy; pz += r.dz;
@@ -418,6 +459,300 @@ __global__ void __launch_bounds__(256) k_visible_scan(const unsigned char *__res
   }
 }
 
+// =====================================================================================================================
+// Compact lists.  The two ordered scans above walk all ~1.18 M slots every frame to rank a few hundred requests and a few
+// thousand visible entries; their cost is the chain of dependent, mostly cold memory round trips of two whole-table
+// kernels.  The reference's order - ascending slot index - can be had from what the per-pixel pass already knows:
+//   * the slots are cut into bins of ITM_ALLOC_BIN consecutive slots (144 bins for the default table, one CTA each);
+//     k_alloc_pixels<true> drops every requested slot and every newly visible slot into its bin's list;
+//   * k_alloc_assign: rank of a request = requests in lower bins (a 144-term sum) + requests of its own bin with a lower
+//     slot (a handful); the winner's block coordinate is recomputed from its key and the entry filled exactly as above.
+//     The same kernel re-checks last frame's visible entries that no ray touched (grid-wide, one thread per entry), copies
+//     the list aside and counts, per bin, its entries and the ones that stay;
+//   * k_visible_merge: last frame's list is ascending already, so the new list is the merge of its kept entries with the
+//     sorted newly-visible slots: position = kept + new entries in lower bins, + kept entries of the own bin below, + new
+//     entries of the own bin below.
+// Results (hash table, free-list heads, entriesVisibleType, visibleEntryIDs) are bit-identical to the scans'.  Engines that
+// swap, shard, or only update the visible list keep the scans (their second ranking rides on the same pass there).
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// sum of counts[0..bin) and of all numBins counts, by warp 0 of the CTA; results in out[0], out[1] (shared)
+__device__ __forceinline__ void bin_prefix(const int *__restrict__ counts, int numBins, int bin, int *out) {
+  if (threadIdx.x < 32) {
+    int lo = 0, all = 0;
+    for (int b = threadIdx.x; b < numBins; b += 32) {
+      const int c = min(__ldcg(counts + b), ITM_ALLOC_BIN);
+      all += c;
+      if (b < bin) lo += c;
+    }
+    lo = warp_sum(lo);
+    all = warp_sum(all);
+    if (threadIdx.x == 0) { out[0] = lo; out[1] = all; }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_alloc_assign(unsigned *__restrict__ allocKey, HashEntry *__restrict__ table,
+                                                      unsigned char *__restrict__ visType, const int *__restrict__ vbaAllocList,
+                                                      const int *__restrict__ excessAllocList, const float *__restrict__ depth,
+                                                      FrameState *st, ViewParams vp, SceneParams sp, float oneOverVoxelSize,
+                                                      int stepBound, const int *__restrict__ prevVisibleIds, const itm::AllocLists L) {
+  __shared__ float sInvM[16];
+  __shared__ float sM[16];
+  __shared__ int sReq[2], sEx[2];
+  pdl_wait();
+  pdl_trigger();
+  if (threadIdx.x < 16) sInvM[threadIdx.x] = st->invM_d[threadIdx.x];
+  if (threadIdx.x >= 32 && threadIdx.x < 48) sM[threadIdx.x - 32] = st->M_d[threadIdx.x - 32];
+  const int bin = blockIdx.x, numBins = L.numBins;
+  int *cntReq = L.binCounts, *cntEx = L.binCounts + numBins, *cntNew = L.binCounts + 2 * numBins;
+  int *cntPrev = L.binCounts + 3 * numBins, *cntKept = L.binCounts + 4 * numBins;
+  bin_prefix(cntReq, numBins, bin, sReq);
+  __syncthreads();
+  if (threadIdx.x < 32) {  // (excess-list requests: a second pass of the same warp)
+    int lo = 0, all = 0;
+    for (int b = threadIdx.x; b < numBins; b += 32) {
+      const int c = __ldcg(cntEx + b);
+      all += c;
+      if (b < bin) lo += c;
+    }
+    lo = warp_sum(lo);
+    all = warp_sum(all);
+    if (threadIdx.x == 0) { sEx[0] = lo; sEx[1] = all; }
+  }
+  __syncthreads();
+
+  // ---- last frame's visible entries: frustum re-check of the untouched ones (..._CPU.cpp:236-247), copy, per-bin counts
+  {
+    const int nPrev = st->noVisibleEntries;
+    const int nThreads = gridDim.x * blockDim.x;
+    for (int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < nPrev; i0 += nThreads) {
+      const int i = i0 + (threadIdx.x & 31);
+      bool keep = false;
+      int b = -1;
+      if (i < nPrev) {
+        const int id = __ldg(prevVisibleIds + i);
+        unsigned char t = visType[id];
+        if (t == 3) {
+          const HashEntry e = load_entry(table, id);
+          if (!block_visible(sM, e.px, e.py, e.pz, sp.voxelSize, vp)) {
+            visType[id] = 0;
+            t = 0;
+          }
+        }
+        keep = t != 0;
+        b = id / ITM_ALLOC_BIN;
+        L.prevCopy[i] = id;
+        L.prevKeep[i] = keep ? 1 : 0;
+      }
+      // one atomic per (warp, bin): the list is ascending, a warp's 32 entries fall into one or two bins
+      const unsigned same = __match_any_sync(0xffffffffu, b);
+      const unsigned kept = __ballot_sync(0xffffffffu, keep);
+      if (b >= 0 && (threadIdx.x & 31) == __ffs(same) - 1) {
+        atomicAdd(cntPrev + b, __popc(same));
+        const int k = __popc(same & kept);
+        if (k) atomicAdd(cntKept + b, k);
+      }
+    }
+  }
+
+  // ---- this bin's requests
+  const int nReq = min(__ldcg(cntReq + bin), ITM_ALLOC_BIN);
+  const int *__restrict__ myList = L.reqList + (size_t)bin * ITM_ALLOC_BIN;
+  const int baseVba = st->allocBaseBlockId, baseExl = st->allocBaseExcessId;
+  if (bin == numBins - 1 && threadIdx.x == 0) {
+    // counters always count down by the number of requests, successful or not (:186, :204-205)
+    st->lastFreeBlockId = baseVba - sReq[1];
+    st->lastFreeExcessId = baseExl - sEx[1];
+    st->reallocBaseBlockId = st->lastFreeBlockId;
+  }
+  for (int r = threadIdx.x; r < nReq; r += blockDim.x) {
+    const int mine = __ldcg(myList + r);
+    const int slot = mine & 0x7fffffff;
+    const bool t2 = mine < 0;
+    int rankA = sReq[0], rankB = sEx[0];
+    for (int j = 0; j < nReq; ++j) {
+      const int v = __ldcg(myList + j);
+      const bool less = (v & 0x7fffffff) < slot;
+      rankA += less ? 1 : 0;
+      rankB += (less && v < 0) ? 1 : 0;
+    }
+    const unsigned keyRaw = allocKey[slot];
+    allocKey[slot] = 0;  // leave the array clean for the next frame
+    // recompute the winning request's block coordinate from its (pixel, step) key
+    const unsigned key = keyRaw - 1u;
+    const int locId = (int)(key / (unsigned)stepBound), step = (int)(key % (unsigned)stepBound);
+    const int y = locId / vp.W, x = locId - y * vp.W;
+    RaySegment rs;
+    make_ray_segment(rs, __ldg(depth + locId), x, y, sInvM, 1.0f / vp.fx, 1.0f / vp.fy, vp.cx, vp.cy, sp.mu, oneOverVoxelSize, sp.vfMin,
+                     sp.vfMax);
+    float px = rs.px, py = rs.py, pz = rs.pz;
+    for (int i = 0; i < step; ++i) { px += rs.dx; py += rs.dy; pz += rs.dz; }
+    int bx, by, bz;
+    block_of(px, py, pz, bx, by, bz);
+    const int vbaIdx = baseVba - rankA;
+    const int newPtr = vbaIdx >= 0 ? vbaAllocList[vbaIdx] : -1;
+    if (!t2) {
+      if (vbaIdx >= 0) store_entry(table, slot, bx, by, bz, 0, newPtr);
+      else atomicAdd(&st->allocFailures, 1);
+    } else {
+      const int exlIdx = baseExl - rankB;
+      if (vbaIdx >= 0 && exlIdx >= 0) {
+        const int exlOffset = excessAllocList[exlIdx];
+        table[slot].offset = exlOffset + 1;
+        const int newSlot = sp.nBuckets + exlOffset;
+        store_entry(table, newSlot, bx, by, bz, 0, newPtr);
+        visType[newSlot] = 1;
+        push_bin(L.newVisList, cntNew, newSlot, newSlot);
+      } else {
+        atomicAdd(&st->allocFailures, 1);
+      }
+    }
+  }
+}
+
+// exclusive scan of one value per thread over the CTA (256 threads); *total = the CTA's sum.  sTmp: 8 ints of shared memory
+__device__ __forceinline__ int cta_exclusive_scan(int v, int *sTmp, int &total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int n = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += n;
+  }
+  __syncthreads();  // sTmp of the previous call has been consumed
+  if (lane == 31) sTmp[warp] = inc;
+  __syncthreads();
+  int base = 0;
+  total = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    const int t = sTmp[w];
+    if (w < warp) base += t;
+    total += t;
+  }
+  return base + inc - v;
+}
+
+// index of the first element of the ascending run a[0..n) that is >= key
+__device__ __forceinline__ int lower_bound_ldg(const int *__restrict__ a, int n, int key) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(a + mid) < key) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256) k_visible_merge(int *__restrict__ visibleIds, FrameState *st, int visibleCapacity,
+                                                       const itm::AllocLists L) {
+  __shared__ int sNew[2], sKept[2], sPrev[2];
+  __shared__ int sTmp[8];
+  __shared__ bool sLast;
+  // per bin: newAt[b] (16 bit, two per word) = new slots whose place is right before previous entry b;
+  // keptBefore[b] = kept previous entries of this bin with an index below b
+  __shared__ unsigned sNewAt[ITM_ALLOC_BIN / 2 + 2];
+  __shared__ unsigned short sKeptBefore[ITM_ALLOC_BIN + 2];
+  pdl_wait();
+  pdl_trigger();
+  const int bin = blockIdx.x, numBins = L.numBins;
+  int *cntNew = L.binCounts + 2 * numBins, *cntPrev = L.binCounts + 3 * numBins, *cntKept = L.binCounts + 4 * numBins;
+  bin_prefix(cntNew, numBins, bin, sNew);
+  if (threadIdx.x >= 32 && threadIdx.x < 64) {
+    int lo = 0, all = 0, plo = 0;
+    for (int b = threadIdx.x - 32; b < numBins; b += 32) {
+      const int c = __ldcg(cntKept + b), p = __ldcg(cntPrev + b);
+      all += c;
+      if (b < bin) { lo += c; plo += p; }
+    }
+    lo = warp_sum(lo);
+    all = warp_sum(all);
+    plo = warp_sum(plo);
+    if (threadIdx.x == 32) { sKept[0] = lo; sKept[1] = all; sPrev[0] = plo; }
+  }
+  const int nNew = min(__ldcg(cntNew + bin), ITM_ALLOC_BIN);
+  const int nPrevBin = min(__ldcg(cntPrev + bin), ITM_ALLOC_BIN);  // (a bin holds at most ITM_ALLOC_BIN distinct slots)
+  for (int i = threadIdx.x; i < ITM_ALLOC_BIN / 2 + 2; i += 256) sNewAt[i] = 0;
+  __syncthreads();
+  // every count this CTA needs has been read: the last CTA to get here clears them for the next frame
+  if (threadIdx.x == 0) {
+    __threadfence();
+    sLast = atomicAdd(L.done, 1) == (int)gridDim.x - 1;
+  }
+  const int *__restrict__ newList = L.newVisList + (size_t)bin * ITM_ALLOC_BIN;
+  const int *__restrict__ prevIds = L.prevCopy + sPrev[0];
+  const unsigned char *__restrict__ prevKeep = L.prevKeep + sPrev[0];
+  const int outBase = sKept[0] + sNew[0];
+  if (bin == 0 && threadIdx.x == 0) {
+    int total = sKept[1] + sNew[1];
+    if (total > visibleCapacity) {
+      atomicOr(&st->errorFlags, 2);
+      total = visibleCapacity;
+    }
+    st->noVisibleEntries = total;
+  }
+  // (1) where in the previous run does each new slot belong?
+  for (int k = threadIdx.x; k < nNew; k += 256) {
+    const int b = lower_bound_ldg(prevIds, nPrevBin, __ldg(newList + k));
+    atomicAdd(&sNewAt[b >> 1], 1u << (16 * (b & 1)));
+  }
+  __syncthreads();
+  // (2) the kept previous entries: position = kept entries below + new slots below, both running sums over the run
+  int keptRun = 0, newRun = 0;  // totals of the earlier rounds (the same in every thread)
+  for (int j0 = 0; j0 < nPrevBin; j0 += 1024) {   // 4 consecutive entries per thread and round
+    int id[4], keep[4], at[4];
+    int keptMine = 0, newMine = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int j = j0 + threadIdx.x * 4 + q;
+      const bool valid = j < nPrevBin;
+      id[q] = valid ? __ldg(prevIds + j) : 0;
+      keep[q] = (valid && __ldg(prevKeep + j) != 0) ? 1 : 0;
+      at[q] = valid ? (int)((sNewAt[j >> 1] >> (16 * (j & 1))) & 0xFFFFu) : 0;
+      keptMine += keep[q];
+      newMine += at[q];
+    }
+    int keptTotal, newTotal;
+    int keptEx = keptRun + cta_exclusive_scan(keptMine, sTmp, keptTotal);
+    int newEx = newRun + cta_exclusive_scan(newMine, sTmp, newTotal);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int j = j0 + threadIdx.x * 4 + q;
+      if (j < nPrevBin) sKeptBefore[j] = (unsigned short)keptEx;
+      newEx += at[q];  // new slots placed before entry j are below it
+      if (keep[q]) {
+        const int pos = outBase + keptEx + newEx;
+        if (pos < visibleCapacity) visibleIds[pos] = id[q];
+      }
+      keptEx += keep[q];
+    }
+    keptRun += keptTotal;
+    newRun += newTotal;
+  }
+  if (threadIdx.x == 0) sKeptBefore[nPrevBin] = (unsigned short)keptRun;
+  __syncthreads();
+  // (3) the new slots: kept previous entries below + new slots below
+  for (int k = threadIdx.x; k < nNew; k += 256) {
+    const int slot = __ldg(newList + k);
+    const int b = lower_bound_ldg(prevIds, nPrevBin, slot);
+    int below = (int)sKeptBefore[b];
+    for (int q = 0; q < nNew; ++q) below += (__ldg(newList + q) < slot) ? 1 : 0;
+    const int pos = outBase + below;
+    if (pos < visibleCapacity) visibleIds[pos] = slot;
+  }
+  __syncthreads();
+  if (sLast) {
+    for (int i = threadIdx.x; i < 5 * numBins; i += 256) L.binCounts[i] = 0;
+    if (threadIdx.x == 0) *L.done = 0;
+  }
+  // the claim bits are this frame's only (the per-pixel pass is long over): every CTA clears its bin's
+  unsigned *bits = L.claimBits + (size_t)bin * (ITM_ALLOC_BIN / 32);
+  for (int i = threadIdx.x; i < ITM_ALLOC_BIN / 32; i += 256) bits[i] = 0;
+}
+
 // ResetScene, ITMSceneReconstructionEngine_CPU.cpp:25-45
 __global__ void k_reset_scene(uint32_t *__restrict__ voxels, size_t nVectors, int *__restrict__ vbaAllocList, int nLocal,
                               HashEntry *__restrict__ table, int nEntries, int *__restrict__ excessAllocList, int nExcess,
@@ -455,9 +790,20 @@ void launch_allocate(const AllocArgs &a, cudaStream_t s) {
   const float oneOverVoxelSize = 1.0f / (a.sp.voxelSize * ITM_BLOCK_SIZE);
   const int stepBound = alloc_step_bound(a.sp);
   HashEntry *table = reinterpret_cast<HashEntry *>(a.hashTable);
-  if (!a.prologueDone) k_mark_prev_visible<<<64, 256, 0, s>>>(a.visibleIds, a.visType, a.st);
+  const bool lists = alloc_uses_lists(a.lists, a.onlyUpdateVisibleList != 0, a.swapStates != nullptr, a.shard.world, a.vp.W * a.vp.H, a.sp.nEntries);
+  if (!a.prologueDone) k_mark_prev_visible<<<64, 256, 0, s>>>(a.visibleIds, a.visType, a.st, lists ? a.lists.claimBits : nullptr);
   dim3 g((a.vp.W + 31) / 32, (a.vp.H + 7) / 8);
-  launch_pdl(k_alloc_pixels, g, dim3(256), s, a.depth, (const HashEntry *)table, a.visType, a.allocKey, a.st, a.vp, a.sp, oneOverVoxelSize, stepBound);
+  if (lists) {
+    launch_pdl(k_alloc_pixels<true>, g, dim3(256), s, a.depth, (const HashEntry *)table, a.visType, a.allocKey, a.st, a.vp, a.sp, oneOverVoxelSize,
+               stepBound, a.lists);
+    launch_pdl(k_alloc_assign, dim3(a.lists.numBins), dim3(256), s, a.allocKey, table, a.visType, (const int *)a.vbaAllocList,
+               (const int *)a.excessAllocList, (const float *)a.depth, a.st, a.vp, a.sp, oneOverVoxelSize, stepBound, (const int *)a.visibleIds,
+               a.lists);
+    launch_pdl(k_visible_merge, dim3(a.lists.numBins), dim3(256), s, a.visibleIds, a.st, a.visibleCapacity, a.lists);
+    return;
+  }
+  launch_pdl(k_alloc_pixels<false>, g, dim3(256), s, a.depth, (const HashEntry *)table, a.visType, a.allocKey, a.st, a.vp, a.sp, oneOverVoxelSize,
+             stepBound, a.lists);
   const int numTiles = (a.sp.nEntries + SCAN_TILE - 1) / SCAN_TILE;
   launch_pdl(k_alloc_scan, dim3(numTiles), dim3(256), s, a.allocKey, table, a.visType, (const int *)a.vbaAllocList, (const int *)a.excessAllocList,
              (const float *)a.depth, a.st, a.vp, a.sp, oneOverVoxelSize, stepBound, a.onlyUpdateVisibleList ? 0 : 1, a.scanTickets, a.allocTileState,

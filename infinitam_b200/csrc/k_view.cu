@@ -78,7 +78,11 @@ __global__ void __launch_bounds__(256) k_convert_pyramid(const short *__restrict
         st->allocBaseExcessId = st->lastFreeExcessId;
       }
       const int n = st->noVisibleEntries;
-      for (int i = gtid; i < n; i += nThreads) args.pro.visType[__ldg(args.pro.visibleIds + i)] = 3;
+      for (int i = gtid; i < n; i += nThreads) {
+        const int id = __ldg(args.pro.visibleIds + i);
+        args.pro.visType[id] = 3;
+        if (args.pro.claimBits) atomicOr(args.pro.claimBits + (id >> 5), 1u << (id & 31));
+      }
     }
     if (args.pro.icpEpoch && gtid == 0) itm::icp_bump_epoch(args.pro.icpEpoch);
     if (args.pro.minmax) {
@@ -254,7 +258,7 @@ void launch_view_pyramid(const short *raw, float a, float b, float *const *level
                          const FramePrologue *prologue, float fxDisparity) {
   PyramidArgs args;
   if (prologue) args.pro = *prologue;
-  else args.pro = FramePrologue{nullptr, nullptr, nullptr, nullptr, 0, nullptr};
+  else args.pro = FramePrologue{nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr};
   int w = W, h = H;
   for (int l = 0; l < ITM_MAX_LEVELS; ++l) {
     args.level[l] = l < nLevels ? levels[l] : nullptr;

@@ -75,7 +75,36 @@ __host__ __device__ __forceinline__ bool shard_block_resident(int x, int y, int 
   return aboveLo && belowHi;
 }
 
+// Scratch of the list-based allocation (k_alloc.cu, "compact lists"): empty / zero between frames.  The hash slots are cut
+// into bins of ITM_ALLOC_BIN consecutive slots; a bin's lists hold at most one item per slot, so ITM_ALLOC_BIN items each.
+#define ITM_ALLOC_BIN 8192
+struct AllocLists {
+  unsigned *claimBits;      // one bit per hash slot: a thread of this frame's per-pixel pass has taken care of its visible type
+  int *reqList;             // [bins][ITM_ALLOC_BIN] slots that received an allocation request this frame (bit 31: excess-list request)
+  int *newVisList;          // [bins][ITM_ALLOC_BIN] slots that became visible this frame
+  int *prevCopy;            // [visibleCapacity] last frame's visible list (ascending)
+  unsigned char *prevKeep;  // [visibleCapacity] 1 = that entry stays in the list
+  int *binCounts;           // [5][bins]: requests, excess-list requests, newly visible, previous entries, kept previous entries
+  int *done;                // CTAs of the merge kernel that have read the counts (the last one clears them)
+  int numBins;
+};
+
+// Does an allocation pass with these properties take the list-based kernels (else the whole-table scans)?  The lists cost
+// per ray-segment step that touches the table (a claim-bit test each), the scans per hash slot: the lists win while
+// pixels x ~3 steps stay below the number of slots (measured on B200: 640x480 / 1.18 M slots 33.3 -> 29.4 us, 1280x720
+// 51.9 -> 56.0 us).  ITM_B200_ALLOC=scan / lists forces one of them (A/B measurements).
+inline bool alloc_uses_lists(const AllocLists &l, bool onlyUpdateVisibleList, bool swapping, int world, int pixels, int nEntries) {
+  static int force = -1;
+  if (force < 0) {
+    const char *e = getenv("ITM_B200_ALLOC");
+    force = !e ? 0 : (e[0] == 's' ? 1 : (e[0] == 'l' ? 2 : 0));
+  }
+  if (!l.claimBits || force == 1 || onlyUpdateVisibleList || swapping || world > 1) return false;
+  return force == 2 || 3ll * pixels < (long long)nEntries;
+}
+
 struct AllocArgs {
+  AllocLists lists;              // claimBits == NULL: always the full-table scans
   const float *depth;            // view->depth, float metres
   void *hashTable;               // ITMHashEntry[nEntries]
   const int *vbaAllocList;       // ITMLocalVBA allocation list
@@ -212,6 +241,7 @@ struct FramePrologue {
   float2 *minmax;           // NULL: no min/max initialisation
   int minmaxPixels;
   unsigned *icpEpoch;       // NULL: not bumped here (launch_icp_track then bumps it with a launch of its own)
+  unsigned *claimBits;      // list-based allocation (AllocLists): the marked entries' claim bits are set; NULL: scans
 };
 void launch_view_pyramid(const short *raw, float a, float b, float *const *levels, int W, int H, int nLevels, cudaStream_t s,
                          const FramePrologue *prologue = nullptr, float fxDisparity = 0.0f);
