@@ -244,7 +244,7 @@ def _alg_bytes(P, E, nv, ev, voxel_bytes=4):
     }
 
 
-KERNELS = {"view": "k_convert_pyramid", "track": "k_icp_track", "allocate": "k_alloc_pixels+k_alloc_scan+k_visible_scan",
+KERNELS = {"view": "k_convert_pyramid", "track": "k_icp_track", "allocate": "k_alloc_pixels+k_alloc_assign+k_visible_merge (compact lists; 1280x720 and swapping / sharded engines: k_alloc_pixels+k_alloc_scan+k_visible_scan)",
            "integrate": "k_integrate_cols", "expected_depths": "k_expected_depths", "raycast": "k_raycast", "icp_maps": "k_icp_maps"}
 STAGES = ["view", "track", "allocate", "integrate", "expected_depths", "raycast", "icp_maps", "total"]
 

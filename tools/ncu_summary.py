@@ -29,7 +29,7 @@ METRICS = OrderedDict([
     ("gpu__compute_memory_throughput.avg.pct_of_peak_sustained_elapsed", "mem_tput_pct"),
 ])
 STAGE_OF = {"k_convert_pyramid": "view", "k_icp_track": "track", "k_mark_prev_visible": "allocate", "k_alloc_pixels": "allocate",
-            "k_alloc_scan": "allocate", "k_visible_scan": "allocate", "k_integrate": "integrate", "k_minmax_init": "expected_depths",
+            "k_alloc_scan": "allocate", "k_visible_scan": "allocate", "k_alloc_assign": "allocate", "k_visible_merge": "allocate", "k_integrate": "integrate", "k_minmax_init": "expected_depths",
             "k_expected_depths": "expected_depths", "k_raycast": "raycast", "k_icp_maps": "icp_maps",
             # SURVEY 8f rows (not stages of the bench step; listed for the per-kernel table only)
             "k_fwd_project": None, "k_fwd_gather": None, "k_fwd_cast": None, "k_fwd_shade": None, "k_track_decide": None,
