@@ -1886,12 +1886,15 @@ int itm_b200_engine_submit_frame(itm_b200_engine *e, const unsigned char *rgb_ho
     e->saved[old % ITM_RESULT_RING] = r;
   }
   const int slot = (int)(e->submitCount++ % ITM_B200_MAX_IN_FLIGHT);
-  if (!e->rawDepthStage[slot]) {
-    CU(cudaMalloc(&e->rawDepthStage[slot], P * 2));
-    if (colour) CU(cudaMalloc(&e->rgbStage[slot], P * 4));
-    CU(cudaEventCreateWithFlags(&e->h2dDone[slot], cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&e->stageFree[slot], cudaEventDisableTiming));
-    CU(cudaEventRecord(e->stageFree[slot], s));
+  if (!e->rawDepthStage[0]) {
+    // all staging slots at the first submit: cudaMalloc synchronises the device, it must not recur while frames are in flight
+    for (int i = 0; i < ITM_B200_MAX_IN_FLIGHT; ++i) {
+      CU(cudaMalloc(&e->rawDepthStage[i], P * 2));
+      if (colour) CU(cudaMalloc(&e->rgbStage[i], P * 4));
+      CU(cudaEventCreateWithFlags(&e->h2dDone[i], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&e->stageFree[i], cudaEventDisableTiming));
+      CU(cudaEventRecord(e->stageFree[i], s));
+    }
   }
   // upload on the copy stream into this frame's staging slot (free once the frame that used it last has copied it out) ...
   CU(cudaStreamWaitEvent(e->copyStream, e->stageFree[slot], 0));
