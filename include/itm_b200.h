@@ -121,6 +121,12 @@ unsigned long long itm_b200_launch_count(void);
 /* the CUDA runtime's pending (non-sticky) error code of the calling thread, cleared by this call; 0 = none.  No entry point
  * of the library leaves one behind (hosts such as PyTorch that share the CUDA runtime would trip over it). */
 int itm_b200_take_cuda_error(void);
+/* Which kernels AllocateSceneFromDepth uses (ITMSceneReconstructionEngine_CPU.cpp:117-291; both give the identical hash table,
+ * free lists, entriesVisibleType and visibleEntryIDs): 0 = automatic (compact per-bin lists where a frame touches fewer hash
+ * slots than the table has, else two ordered whole-table scans), 1 = always the scans, 2 = the lists wherever they apply
+ * (not for swapping / sharded engines or onlyUpdateVisibleList).  Process-wide; takes effect for engines created afterwards.
+ * Returns the previous mode, or a negative error.  For A/B measurements and tests. */
+int itm_b200_set_alloc_mode(int mode);
 
 /* ===================================================================================== *
  *  Layer A - one function per engine method, on caller-owned device buffers.            *

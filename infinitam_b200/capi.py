@@ -123,6 +123,7 @@ SYMBOLS = [
     "itm_b200_take_cuda_error", "itm_b200_engine_get_stream", "itm_b200_engine_copy_to_buffer_dev", "itm_b200_compute_g_and_h_weighted", "itm_b200_depth_filtering", "itm_b200_compute_normal_and_weights", "itm_b200_swap_in_select", "itm_b200_swap_in_apply", "itm_b200_swap_out",
     "itm_b200_convert_disparity_to_depth", "itm_b200_engine_process_frame_with_pose", "itm_b200_engine_submit_frame",
     "itm_b200_engine_wait_frame", "itm_b200_shard_block_resident", "itm_b200_engine_shard_times", "itm_b200_track_camera_weighted",
+    "itm_b200_set_alloc_mode",
 ]
 
 _lib = None
@@ -228,3 +229,14 @@ def default_params(width=640, height=480) -> Params:
     p = Params()
     load().itm_b200_default_params(C.byref(p), width, height)
     return p
+
+
+def set_alloc_mode(mode):
+    """itm_b200_set_alloc_mode: 0 automatic, 1 ordered scans, 2 compact lists; returns the previous mode."""
+    lib = load()
+    lib.itm_b200_set_alloc_mode.argtypes = [C.c_int]
+    lib.itm_b200_set_alloc_mode.restype = C.c_int
+    prev = lib.itm_b200_set_alloc_mode(int(mode))
+    if prev < 0:
+        raise ItmError(prev, lib.itm_b200_last_error().decode())
+    return prev

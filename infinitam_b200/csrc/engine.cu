@@ -470,6 +470,13 @@ int itm_b200_device_count(void) {
 
 unsigned long long itm_b200_launch_count(void) { return g_launches.load(); }
 
+int itm_b200_set_alloc_mode(int mode) {
+  if (mode < 0 || mode > 2) return fail(ITM_B200_EINVAL, "alloc mode must be 0 (automatic), 1 (scans) or 2 (lists)");
+  const int prev = alloc_mode();
+  alloc_mode() = mode;
+  return prev;
+}
+
 // the CUDA runtime's pending (non-sticky) error of the calling thread, cleared by the call; 0 = none.  Every entry point
 // of this library is meant to leave none behind - tests check that.
 int itm_b200_take_cuda_error(void) { return (int)cudaGetLastError(); }

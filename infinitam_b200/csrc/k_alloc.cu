@@ -772,6 +772,15 @@ namespace itm {
 
 int alloc_scan_tile() { return SCAN_TILE; }
 
+int &alloc_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char *e = getenv("ITM_B200_ALLOC");
+    mode = !e ? 0 : (e[0] == 's' ? 1 : (e[0] == 'l' ? 2 : 0));
+  }
+  return mode;
+}
+
 int alloc_step_bound(const SceneParams &sp) {
   // noSteps = ceil(2 * |segment| / blockSize); |segment| = 2*mu up to rounding
   const float len = 2.0f * sp.mu / (sp.voxelSize * (float)ITM_BLOCK_SIZE);

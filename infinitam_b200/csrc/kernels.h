@@ -93,12 +93,9 @@ struct AllocLists {
 // per ray-segment step that touches the table (a claim-bit test each), the scans per hash slot: the lists win while
 // pixels x ~3 steps stay below the number of slots (measured on B200: 640x480 / 1.18 M slots 33.3 -> 29.4 us, 1280x720
 // 51.9 -> 56.0 us).  ITM_B200_ALLOC=scan / lists forces one of them (A/B measurements).
+int &alloc_mode();  // 0 automatic, 1 scans, 2 lists wherever they apply (itm_b200_set_alloc_mode; initial value from ITM_B200_ALLOC)
 inline bool alloc_uses_lists(const AllocLists &l, bool onlyUpdateVisibleList, bool swapping, int world, int pixels, int nEntries) {
-  static int force = -1;
-  if (force < 0) {
-    const char *e = getenv("ITM_B200_ALLOC");
-    force = !e ? 0 : (e[0] == 's' ? 1 : (e[0] == 'l' ? 2 : 0));
-  }
+  const int force = alloc_mode();
   if (!l.claimBits || force == 1 || onlyUpdateVisibleList || swapping || world > 1) return false;
   return force == 2 || 3ll * pixels < (long long)nEntries;
 }

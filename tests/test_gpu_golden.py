@@ -37,7 +37,15 @@ def test_cuda_free_running_reproduces_golden_vectors():
     eng.close()
 
 
-def test_cuda_teacher_forced_against_port_with_runtime_pools():
+@pytest.fixture(params=[1, 2], ids=["ordered-scans", "compact-lists"])
+def alloc_mode(request):
+    """both implementations of AllocateSceneFromDepth (itm_b200_set_alloc_mode) must give the reference's table bit for bit"""
+    prev = capi.set_alloc_mode(request.param)
+    yield request.param
+    capi.set_alloc_mode(prev)
+
+
+def test_cuda_teacher_forced_against_port_with_runtime_pools(alloc_mode):
     """small pools (4096 blocks, 2^15 buckets): many bucket collisions -> excess-list allocation is exercised heavily"""
     o = port.PortEngine(320, 240, n_local=0x2000, n_bucket=0x4000, n_excess=0x2000)
     eng = parity.make_cuda_engine(o)
@@ -48,7 +56,7 @@ def test_cuda_teacher_forced_against_port_with_runtime_pools():
     eng.close(); o.close()
 
 
-def test_cuda_pool_exhaustion_matches_oracle():
+def test_cuda_pool_exhaustion_matches_oracle(alloc_mode):
     """the voxel-block pool and the excess list both run dry while the camera moves; the reference keeps decrementing its
     counters and silently skips the blocks (ITMSceneReconstructionEngine_CPU.cpp:187-189, :206) - so must we"""
     o = port.PortEngine(320, 240, n_local=7168, n_bucket=0x4000, n_excess=1600)
@@ -58,6 +66,33 @@ def test_cuda_pool_exhaustion_matches_oracle():
     assert rows[-1]["counters_ref"][1] < 0 and rows[-1]["counters_ref"][2] < 0, "both pools were supposed to be exhausted"
     assert max(r["counters_ref"][0] for r in rows) <= 7168
     eng.close(); o.close()
+
+
+def test_cuda_allocation_lists_equal_scans_free_running():
+    """40 free-running 640x480 frames, once with each allocation implementation: identical hash table, free-list heads,
+    entriesVisibleType, visible list and pose after every tenth frame (the camera sweeps, so entries leave and re-enter
+    the list and the excess list grows)"""
+    seq = synth.sequence(40, 640, 480)
+    snaps = []
+    for mode in (1, 2):
+        prev = capi.set_alloc_mode(mode)
+        try:
+            eng = ITMMainEngine(width=640, height=480)
+            got = []
+            for k in range(40):
+                eng.ProcessFrame(None, seq[k])
+                if k % 10 == 9:
+                    pose, _, st = eng.get_state()
+                    n = int(st[0])
+                    got.append((pose.copy(), st[:3].copy(), eng.read(capi.BUF_HASH).copy(), eng.read(capi.BUF_VISIBLE_IDS)[:n].copy(),
+                                eng.read(capi.BUF_VISIBLE_TYPES).copy()))
+            eng.close()
+        finally:
+            capi.set_alloc_mode(prev)
+        snaps.append(got)
+    for a, b in zip(*snaps):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
 
 
 def test_cuda_hd_2mm_teacher_forced_against_port():
