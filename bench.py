@@ -447,7 +447,7 @@ def c5_record(torch, dev, local_rank, peak, peak_kind, n_frames=44, warm=4):
                 stage += eng.stage_times()
                 nvis.append(int(eng.Sync()[1][0]))
                 if swapping:
-                    _, _, a, b = eng.global_cache()
+                    a, b = eng.swap_counts()
                     n_in += a
                     n_out += b
         m = n_frames - warm
@@ -460,7 +460,7 @@ def c5_record(torch, dev, local_rank, peak, peak_kind, n_frames=44, warm=4):
                     "visible_blocks_mean": nv, "stage_ms": stage_avg}
         if swapping:
             out[key].update({"blocks_swapped_in": n_in, "blocks_swapped_out": n_out,
-                             "note": "stage_ms.integrate includes the swap-in / swap-out stage (host in the loop)"})
+                             "note": "stage_ms.integrate includes the swap-in / swap-out stage: the kernels move blocks to / from the host-mapped cache pool themselves, the frame stays one CUDA graph"})
         else:
             out[key]["roofline_integrate_rgb"] = {"kernel": "k_integrate_rgb", "bound": "hbm", "algorithmic_bytes": int(alg_int), "avg_launch_ms": ms,
                                                   "achieved": alg_int / (ms * 1e-3) / 1e9 if ms else None, "peak": peak, "unit": "GB/s",

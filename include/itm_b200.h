@@ -100,6 +100,12 @@ typedef struct itm_b200_params {
   /* settings.useBilateralFilter (ITMLibSettings.cpp:41, off by default): UpdateView runs five passes of the 5x5 bilateral depth
    * filter (ITMViewBuilder_CPU.cpp:50-59).  settings.modelSensorNoise is implied by ITM_B200_TRACKER_WICP (ITMLibSettings.cpp:51-53). */
   int use_bilateral_filter;
+  /* Layer B with use_swapping: the global cache (ITMGlobalCache, ITMLib/Objects/ITMGlobalCache.h:21-36 - room for every hash
+   * entry's block in the reference, 2.4 / 4.8 GB) is a pool of this many voxel blocks in host-mapped pinned memory that the
+   * swapping kernels read and write directly over PCIe, with a per-entry slot index on the device; a block gets its slot the
+   * first time it is swapped out.  0 = 4 x sdf_local_block_num (at most one per hash entry).  A full pool sets error flag 4
+   * (the block's data is then lost, the reference never runs out). */
+  int swap_cache_blocks;
 } itm_b200_params;
 #define ITM_B200_VOXEL_S 0
 #define ITM_B200_VOXEL_S_RGB 1
@@ -428,7 +434,10 @@ int itm_b200_engine_read_buffer(itm_b200_engine *e, int which, void *host_dst, s
 int itm_b200_engine_write_buffer(itm_b200_engine *e, int which, const void *host_src, size_t bytes, size_t offset);
 
 /* ITMGlobalCache of a swapping engine (host memory, borrowed): hasStoredData[bucket+excess] and the stored voxel
- * blocks (ITMLib/Objects/ITMGlobalCache.h:21-36).  *swapped_in / *swapped_out: entries moved by the last frame. */
+ * blocks (ITMLib/Objects/ITMGlobalCache.h:21-36).  *swapped_in / *swapped_out: entries moved by the last frame.
+ * The engine keeps the cache as a pool in host-mapped memory (params.swap_cache_blocks); this call waits for the pending
+ * frames and materialises the reference's dense layout from it (for inspection and tests - not a per-frame call).  With
+ * has_stored_data == stored_voxel_blocks == NULL only the two counts are fetched. */
 int itm_b200_engine_global_cache(itm_b200_engine *e, const unsigned char **has_stored_data, const void **stored_voxel_blocks,
                                  int *swapped_in, int *swapped_out);
 

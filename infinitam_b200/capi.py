@@ -56,6 +56,7 @@ class Params(C.Structure):
         ("tracker_type", C.c_int),
         ("depth_source", C.c_int),
         ("use_bilateral_filter", C.c_int),
+        ("swap_cache_blocks", C.c_int),
     ]
 
 

@@ -753,6 +753,7 @@ static SwapArgs swap_args_layer_a(itm_b200_ctx *c, const itm_b200_scene *scene, 
   a.tileState = c->otherTileState;
   a.st = c->st;
   a.sp = c->sp;
+  a.cachePool = nullptr; a.cacheSlot = nullptr; a.cacheCount = nullptr; a.cachePoolBlocks = 0; a.movedCounts = nullptr;
   return a;
 }
 
@@ -1102,11 +1103,17 @@ struct itm_b200_engine {
   int *neededIds = nullptr;                 // device
   void *transfer = nullptr;                 // device, syncedVoxelBlocks
   unsigned char *hasSynced = nullptr;       // device
-  int *neededIdsHost = nullptr;             // pinned
-  void *transferHost = nullptr;             // pinned
-  unsigned char *hasSyncedHost = nullptr;   // pinned
+  // the global cache: a pool of voxel blocks in host-mapped pinned memory (the swapping kernels move blocks themselves)
+  char *cachePool = nullptr;                // host address
+  void *cachePoolDev = nullptr;             // the same memory as the device sees it
+  int cachePoolBlocks = 0;
+  int *cacheSlot = nullptr;                 // device, [nEntries]: pool slot of an entry's stored block, -1 = none (hasStoredData)
+  int *cacheCount = nullptr;                // device: slots handed out
+  int *movedCounts = nullptr;               // device: [0] swapped in, [1] swapped out by the last frame
+  // ITMGlobalCache's dense view, materialised by itm_b200_engine_global_cache only
   unsigned char *hasStoredData = nullptr;   // host, [nEntries]
   char *storedVoxelBlocks = nullptr;        // host, [nEntries] blocks (allocated lazily by the OS)
+  int *cacheSlotHost = nullptr;
   unsigned long long *swapTileState = nullptr;
   unsigned long long *swapTicket = nullptr;
   int lastSwappedIn = 0, lastSwappedOut = 0;
@@ -1192,16 +1199,21 @@ int engine_alloc(itm_b200_engine *e) {
     CU(cudaMalloc(&e->neededIds, ITM_TRANSFER_BLOCK_NUM * sizeof(int)));
     CU(cudaMalloc(&e->transfer, ITM_TRANSFER_BLOCK_NUM * blockBytes));
     CU(cudaMalloc(&e->hasSynced, ITM_TRANSFER_BLOCK_NUM));
-    CU(cudaMallocHost(&e->neededIdsHost, ITM_TRANSFER_BLOCK_NUM * sizeof(int)));
-    CU(cudaMallocHost(&e->transferHost, ITM_TRANSFER_BLOCK_NUM * blockBytes));
-    CU(cudaMallocHost(&e->hasSyncedHost, ITM_TRANSFER_BLOCK_NUM));
+    long long poolBlocks = c->p.swap_cache_blocks > 0 ? c->p.swap_cache_blocks : 4ll * c->sp.nLocal;
+    if (poolBlocks > c->sp.nEntries) poolBlocks = c->sp.nEntries;
+    e->cachePoolBlocks = (int)poolBlocks;
+    CU(cudaHostAlloc(&e->cachePool, (size_t)poolBlocks * blockBytes, cudaHostAllocMapped));
+    CU(cudaHostGetDevicePointer(&e->cachePoolDev, e->cachePool, 0));
+    CU(cudaMalloc(&e->cacheSlot, (size_t)c->sp.nEntries * sizeof(int)));
+    CU(cudaMemset(e->cacheSlot, 0xFF, (size_t)c->sp.nEntries * sizeof(int)));
+    CU(cudaMalloc(&e->cacheCount, sizeof(int)));
+    CU(cudaMemset(e->cacheCount, 0, sizeof(int)));
+    CU(cudaMalloc(&e->movedCounts, 2 * sizeof(int)));
+    CU(cudaMemset(e->movedCounts, 0, 2 * sizeof(int)));
     CU(cudaMalloc(&e->swapTileState, numTiles * sizeof(unsigned long long)));
     CU(cudaMemset(e->swapTileState, 0, numTiles * sizeof(unsigned long long)));
     CU(cudaMalloc(&e->swapTicket, sizeof(unsigned long long)));
     CU(cudaMemset(e->swapTicket, 0, sizeof(unsigned long long)));
-    e->hasStoredData = (unsigned char *)calloc(c->sp.nEntries, 1);
-    e->storedVoxelBlocks = (char *)malloc((size_t)c->sp.nEntries * blockBytes);
-    if (!e->hasStoredData || !e->storedVoxelBlocks) return fail(ITM_B200_ECUDA, "host memory for the global cache");
     e->bytes[ITM_B200_BUF_SWAP_STATES] = (size_t)c->sp.nEntries;
   }
   e->bytes[ITM_B200_BUF_VOXELS] = (size_t)c->sp.nLocal * ITM_BLOCK_SIZE3 * 4 * c->sp.voxelWords;
@@ -1247,10 +1259,9 @@ void engine_free(itm_b200_engine *e) {
   RELEASE(cudaFree(e->meshTriangles));
   RELEASE(cudaFree(e->swapStates)); RELEASE(cudaFree(e->neededIds)); RELEASE(cudaFree(e->transfer)); RELEASE(cudaFree(e->hasSynced));
   RELEASE(cudaFree(e->swapTileState)); RELEASE(cudaFree(e->swapTicket));
-  if (e->neededIdsHost) RELEASE(cudaFreeHost(e->neededIdsHost));
-  if (e->transferHost) RELEASE(cudaFreeHost(e->transferHost));
-  if (e->hasSyncedHost) RELEASE(cudaFreeHost(e->hasSyncedHost));
-  free(e->hasStoredData); free(e->storedVoxelBlocks);
+  if (e->cachePool) RELEASE(cudaFreeHost(e->cachePool));
+  RELEASE(cudaFree(e->cacheSlot)); RELEASE(cudaFree(e->cacheCount)); RELEASE(cudaFree(e->movedCounts));
+  free(e->hasStoredData); free(e->storedVoxelBlocks); free(e->cacheSlotHost);
   if (e->copyStream) RELEASE(cudaStreamDestroy(e->copyStream));
   if (e->rgbDone) RELEASE(cudaEventDestroy(e->rgbDone));
   if (e->sideStream) RELEASE(cudaStreamDestroy(e->sideStream));
@@ -1292,7 +1303,9 @@ int engine_reset(itm_b200_engine *e) {
   CU(cudaMemsetAsync(c->allocKey, 0, (size_t)((c->sp.nEntries + 8191) / 8192) * 8192 * sizeof(unsigned), c->stream));
   if (e->swapStates) {
     CU(cudaMemsetAsync(e->swapStates, 0, (size_t)((c->sp.nEntries + 8191) / 8192) * 8192, c->stream));
-    memset(e->hasStoredData, 0, c->sp.nEntries);
+    CU(cudaMemsetAsync(e->cacheSlot, 0xFF, (size_t)c->sp.nEntries * sizeof(int), c->stream));
+    CU(cudaMemsetAsync(e->cacheCount, 0, sizeof(int), c->stream));
+    CU(cudaMemsetAsync(e->movedCounts, 0, 2 * sizeof(int), c->stream));
   }
   host_state_init(c->hst, c->sp);
   int rc = push_state(c);
@@ -1479,51 +1492,22 @@ void stage_forward_render(itm_b200_engine *e, bool gated) {
 
 // ITMSwappingEngine::IntegrateGlobalIntoLocal + SaveToGlobalMemory (ITMDenseMapper.cpp:59-64).  Unlike the rest of the
 // frame this needs the host in the loop (the global cache is host memory): two list read-backs and the block transfers.
+// ITMSwappingEngine::IntegrateGlobalIntoLocal + SaveToGlobalMemory (ITMDenseMapper.cpp:59-64) without the host: ordered
+// selection, then the kernels combine from / copy to the host-mapped cache pool themselves (k_swap.cu)
 int stage_swap(itm_b200_engine *e) {
   itm_b200_ctx *c = e->c;
   cudaStream_t s = c->stream;
-  const size_t blockBytes = (size_t)ITM_BLOCK_SIZE3 * 4 * c->sp.voxelWords;
   SwapArgs a;
   a.voxels = e->voxels; a.hashTable = e->hash; a.vbaAllocList = e->vbaAllocList; a.visType = e->visType; a.swapStates = e->swapStates;
   a.neededIds = e->neededIds; a.transfer = e->transfer; a.hasSynced = e->hasSynced; a.ticket = e->swapTicket; a.tileState = e->swapTileState;
   a.st = c->st; a.sp = c->sp;
-  // ---- host -> active memory (ITMSwappingEngine_CPU.cpp:69-104)
-  launch_swap_select(a, 0, s);
-  g_launches += 1;
-  CU(cudaMemcpyAsync(e->neededIdsHost, e->neededIds, ITM_TRANSFER_BLOCK_NUM * sizeof(int), cudaMemcpyDeviceToHost, s));
-  int rc = pull_state(c);
-  if (rc) return rc;
-  const int nIn = c->hst->swapCount;
-  for (int i = 0; i < nIn; ++i) {  // LoadFromGlobalMemory (:47-60)
-    const int id = e->neededIdsHost[i];
-    e->hasSyncedHost[i] = e->hasStoredData[id];
-    if (e->hasStoredData[id]) memcpy((char *)e->transferHost + (size_t)i * blockBytes, e->storedVoxelBlocks + (size_t)id * blockBytes, blockBytes);
-  }
-  if (nIn > 0) {
-    CU(cudaMemcpyAsync(e->hasSynced, e->hasSyncedHost, nIn, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(e->transfer, e->transferHost, (size_t)nIn * blockBytes, cudaMemcpyHostToDevice, s));
-    launch_swap_in_apply(a, s);
-    g_launches += 1;
-  }
-  // ---- active memory -> host (:107-176)
-  launch_swap_select(a, 1, s);
-  launch_swap_out_apply(a, s);
-  g_launches += 2;
-  CU(cudaMemcpyAsync(e->neededIdsHost, e->neededIds, ITM_TRANSFER_BLOCK_NUM * sizeof(int), cudaMemcpyDeviceToHost, s));
-  rc = pull_state(c);
-  if (rc) return rc;
-  const int nOut = c->hst->swapCount;
-  if (nOut > 0) {
-    CU(cudaMemcpyAsync(e->transferHost, e->transfer, (size_t)nOut * blockBytes, cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    for (int i = 0; i < nOut; ++i) {  // SetStoredData (:168-174)
-      const int id = e->neededIdsHost[i];
-      e->hasStoredData[id] = 1;
-      memcpy(e->storedVoxelBlocks + (size_t)id * blockBytes, (char *)e->transferHost + (size_t)i * blockBytes, blockBytes);
-    }
-  }
-  e->lastSwappedIn = nIn;
-  e->lastSwappedOut = nOut;
+  a.cachePool = e->cachePoolDev; a.cacheSlot = e->cacheSlot; a.cacheCount = e->cacheCount; a.cachePoolBlocks = e->cachePoolBlocks;
+  a.movedCounts = e->movedCounts;
+  launch_swap_select(a, 0, s);   // host -> active memory (ITMSwappingEngine_CPU.cpp:69-104)
+  launch_swap_in_direct(a, s);
+  launch_swap_select(a, 1, s);   // active memory -> host (:107-176)
+  launch_swap_out_direct(a, s);
+  g_launches += 4;
   return ITM_B200_OK;
 }
 
@@ -1687,7 +1671,7 @@ int itm_b200_engine_create(const itm_b200_params *params, itm_b200_engine **out)
   e->c = c;
   memset(&e->shard, 0, sizeof(e->shard));
   e->shard.world = 1;
-  e->graphsOff = params->use_swapping != 0 || getenv("ITM_B200_NO_GRAPH") != nullptr;
+  e->graphsOff = getenv("ITM_B200_NO_GRAPH") != nullptr;
   rc = engine_alloc(e);
   if (!rc) rc = engine_reset(e);
   if (rc) {
@@ -2063,6 +2047,33 @@ int itm_b200_engine_global_cache(itm_b200_engine *e, const unsigned char **has_s
   ON_DEVICE_OF_ENGINE(e);
   if (!e) return fail(ITM_B200_EINVAL, "NULL engine");
   if (!e->swapStates) return fail(ITM_B200_EINVAL, "engine was created without use_swapping");
+  itm_b200_ctx *c = e->c;
+  const size_t blockBytes = (size_t)ITM_BLOCK_SIZE3 * 4 * c->sp.voxelWords;
+  int moved[2] = {0, 0};
+  if (!has_stored_data && !stored_voxel_blocks) {  // the counts only
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpy(moved, e->movedCounts, sizeof(moved), cudaMemcpyDeviceToHost));
+    if (swapped_in) *swapped_in = moved[0];
+    if (swapped_out) *swapped_out = moved[1];
+    return ITM_B200_OK;
+  }
+  if (!e->hasStoredData) {
+    e->hasStoredData = (unsigned char *)calloc(c->sp.nEntries, 1);
+    e->storedVoxelBlocks = (char *)malloc((size_t)c->sp.nEntries * blockBytes);  // touched only where a block is stored
+    e->cacheSlotHost = (int *)malloc((size_t)c->sp.nEntries * sizeof(int));
+    if (!e->hasStoredData || !e->storedVoxelBlocks || !e->cacheSlotHost) return fail(ITM_B200_ECUDA, "host memory for the global cache view");
+  }
+  // the dense ITMGlobalCache view of the pool: every pending frame has to be through with it first
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaMemcpy(e->cacheSlotHost, e->cacheSlot, (size_t)c->sp.nEntries * sizeof(int), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(moved, e->movedCounts, sizeof(moved), cudaMemcpyDeviceToHost));
+  for (int id = 0; id < c->sp.nEntries; ++id) {
+    const int slot = e->cacheSlotHost[id];
+    e->hasStoredData[id] = slot >= 0 ? 1 : 0;
+    if (slot >= 0) memcpy(e->storedVoxelBlocks + (size_t)id * blockBytes, e->cachePool + (size_t)slot * blockBytes, blockBytes);
+  }
+  e->lastSwappedIn = moved[0];
+  e->lastSwappedOut = moved[1];
   if (has_stored_data) *has_stored_data = e->hasStoredData;
   if (stored_voxel_blocks) *stored_voxel_blocks = e->storedVoxelBlocks;
   if (swapped_in) *swapped_in = e->lastSwappedIn;

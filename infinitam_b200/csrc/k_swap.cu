@@ -176,6 +176,100 @@ __global__ void __launch_bounds__(256) k_swap_out_apply(uint32_t *__restrict__ v
   }
 }
 
+// ---- Layer B: the global cache is a pool in host-mapped pinned memory; the kernels move blocks to / from it themselves
+// (16-byte accesses over PCIe), so a swapping frame has no host round trip and sits in the frame graph like any other.
+
+// IntegrateGlobalIntoLocal (:69-104): LoadFromGlobalMemory's copy and the combine loop in one pass
+__global__ void __launch_bounds__(256) k_swap_in_direct(uint32_t *__restrict__ voxels, const HashEntry *__restrict__ table,
+                                                        unsigned char *__restrict__ swapStates, const int *__restrict__ neededIds,
+                                                        const uint32_t *__restrict__ pool, const int *__restrict__ cacheSlot,
+                                                        const FrameState *__restrict__ st, int voxelWords, int maxW, int *movedCounts) {
+  const int n = st->swapCount;
+  if (blockIdx.x == 0 && threadIdx.x == 0) movedCounts[0] = n;
+  for (int i = blockIdx.x; i < n; i += gridDim.x) {
+    const int id = neededIds[i];
+    const int slot = cacheSlot[id];   // hasStoredData[id]
+    const int ptr = table[id].ptr;
+    if (slot >= 0 && ptr >= 0) {
+      uint32_t *dst = voxels + (size_t)ptr * ITM_BLOCK_SIZE3 * voxelWords;
+      const uint32_t *src = pool + (size_t)slot * ITM_BLOCK_SIZE3 * voxelWords;
+      if (voxelWords == 1) {
+        // 512 words: two per thread, one 8-byte read from the host each
+        const uint2 sv = *reinterpret_cast<const uint2 *>(src + 2 * threadIdx.x);
+        uint2 dv = *reinterpret_cast<uint2 *>(dst + 2 * threadIdx.x);
+        dv.x = combine_depth(sv.x, dv.x, maxW);
+        dv.y = combine_depth(sv.y, dv.y, maxW);
+        *reinterpret_cast<uint2 *>(dst + 2 * threadIdx.x) = dv;
+      } else {
+        // 512 two-word voxels: two voxels (16 bytes) per thread
+        const uint4 sv = *reinterpret_cast<const uint4 *>(src + 4 * threadIdx.x);
+        uint4 dv = *reinterpret_cast<uint4 *>(dst + 4 * threadIdx.x);
+        dv.x = combine_depth(sv.x, dv.x, maxW);
+        combine_colour(sv.x, sv.y, dv.x, dv.y, maxW);
+        dv.z = combine_depth(sv.z, dv.z, maxW);
+        combine_colour(sv.z, sv.w, dv.z, dv.w, maxW);
+        *reinterpret_cast<uint4 *>(dst + 4 * threadIdx.x) = dv;
+      }
+    }
+    if (threadIdx.x == 0) swapStates[id] = 2;
+  }
+}
+
+// SaveToGlobalMemory (:107-176): the copy goes straight to the entry's pool slot (SetStoredData), handed out on first use
+__global__ void __launch_bounds__(256) k_swap_out_direct(uint32_t *__restrict__ voxels, HashEntry *__restrict__ table,
+                                                         unsigned char *__restrict__ swapStates, const int *__restrict__ neededIds,
+                                                         uint32_t *__restrict__ pool, int *__restrict__ cacheSlot, int *cacheCount,
+                                                         int poolBlocks, int *__restrict__ vbaAllocList, FrameState *st, int voxelWords,
+                                                         int nBuckets, int *movedCounts) {
+  __shared__ int sSlot;
+  const int n = st->swapCount;
+  const int base = st->swapBaseBlockId;  // noAllocatedVoxelEntries at the start of the loop
+  if (blockIdx.x == 0 && threadIdx.x == 0) movedCounts[1] = n;
+  for (int i = blockIdx.x; i < n; i += gridDim.x) {
+    const int id = neededIds[i];
+    const int ptr = table[id].ptr;
+    if (threadIdx.x == 0) {
+      int slot = cacheSlot[id];
+      if (slot < 0) {
+        slot = atomicAdd(cacheCount, 1);
+        if (slot >= poolBlocks) {
+          atomicOr(&st->errorFlags, 4);
+          slot = -1;
+        } else {
+          cacheSlot[id] = slot;
+        }
+      }
+      sSlot = slot;
+    }
+    __syncthreads();
+    const int slot = sSlot;
+    uint32_t *blk = voxels + (size_t)ptr * ITM_BLOCK_SIZE3 * voxelWords;
+    const int vbaIdx = base + i;
+    const bool release = vbaIdx < nBuckets - 1;
+    const int words = ITM_BLOCK_SIZE3 * voxelWords;
+    for (int w4 = threadIdx.x * 4; w4 < words; w4 += 256 * 4) {
+      const uint4 v = *reinterpret_cast<const uint4 *>(blk + w4);
+      if (slot >= 0) *reinterpret_cast<uint4 *>(pool + (size_t)slot * words + w4) = v;
+      // TVoxel(): sdf = 32767, everything else 0
+      if (release)
+        *reinterpret_cast<uint4 *>(blk + w4) = voxelWords == 1 ? make_uint4(0x7FFFu, 0x7FFFu, 0x7FFFu, 0x7FFFu) : make_uint4(0x7FFFu, 0u, 0x7FFFu, 0u);
+    }
+    __syncthreads();  // everybody has read table[id].ptr and sSlot before they change
+    if (threadIdx.x == 0) {
+      swapStates[id] = 0;
+      if (release) {
+        vbaAllocList[vbaIdx + 1] = ptr;
+        table[id].ptr = -1;
+      }
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    int released = n;
+    if (base + released > nBuckets - 1) released = (nBuckets - 1 - base) > 0 ? (nBuckets - 1 - base) : 0;
+    st->lastFreeBlockId = base + released;
+  }
+}
+
 }  // namespace
 
 namespace itm {
@@ -196,6 +290,18 @@ void launch_swap_out_apply(const SwapArgs &a, cudaStream_t s) {
   k_swap_out_apply<<<148 * 4, 256, 0, s>>>(reinterpret_cast<uint32_t *>(a.voxels), reinterpret_cast<HashEntry *>(a.hashTable), a.swapStates,
                                            a.neededIds, reinterpret_cast<uint32_t *>(a.transfer), a.vbaAllocList, a.st, a.sp.voxelWords,
                                            a.sp.nBuckets);
+}
+
+void launch_swap_in_direct(const SwapArgs &a, cudaStream_t s) {
+  k_swap_in_direct<<<148 * 4, 256, 0, s>>>(reinterpret_cast<uint32_t *>(a.voxels), reinterpret_cast<const HashEntry *>(a.hashTable), a.swapStates,
+                                           a.neededIds, reinterpret_cast<const uint32_t *>(a.cachePool), a.cacheSlot, a.st, a.sp.voxelWords,
+                                           a.sp.maxW, a.movedCounts);
+}
+
+void launch_swap_out_direct(const SwapArgs &a, cudaStream_t s) {
+  k_swap_out_direct<<<148 * 4, 256, 0, s>>>(reinterpret_cast<uint32_t *>(a.voxels), reinterpret_cast<HashEntry *>(a.hashTable), a.swapStates,
+                                            a.neededIds, reinterpret_cast<uint32_t *>(a.cachePool), a.cacheSlot, a.cacheCount, a.cachePoolBlocks,
+                                            a.vbaAllocList, a.st, a.sp.voxelWords, a.sp.nBuckets, a.movedCounts);
 }
 
 }  // namespace itm

@@ -276,12 +276,21 @@ struct SwapArgs {
   unsigned long long *tileState;
   FrameState *st;
   SceneParams sp;
+  // Layer B's global cache: a pool of blocks in host-mapped pinned memory + the slot of every hash entry (-1: nothing stored)
+  void *cachePool;
+  int *cacheSlot;
+  int *cacheCount;                  // slots handed out so far
+  int cachePoolBlocks;
+  int *movedCounts;                 // [0] entries combined from the cache, [1] entries moved to the cache by the last frame
 };
 // ordered selection of the first ITM_TRANSFER_BLOCK_NUM entries (ascending slot order) that need swapping in (mode 0:
 // state 1) or can be swapped out (mode 1: state 2, resident, not visible); st->swapCount = how many
 void launch_swap_select(const SwapArgs &a, int mode, cudaStream_t s);
 void launch_swap_in_apply(const SwapArgs &a, cudaStream_t s);   // IntegrateGlobalIntoLocal's combine loop
 void launch_swap_out_apply(const SwapArgs &a, cudaStream_t s);  // SaveToGlobalMemory's device part
+// the same two steps against the host-mapped cache pool: no transfer buffer, no host in the loop (Layer B)
+void launch_swap_in_direct(const SwapArgs &a, cudaStream_t s);
+void launch_swap_out_direct(const SwapArgs &a, cudaStream_t s);
 
 // all ranks meet: returns (on the stream) once every rank has enqueued barrier number seq after its own prior work
 void launch_shard_barrier(const ShardInfo &sh, unsigned seq, cudaStream_t s);

@@ -188,6 +188,12 @@ class ITMMainEngine:
         capi.check(self.lib.itm_b200_engine_set_state(
             self.h, None if p is None else _f32p(p), None if q is None else _f32p(q), None if s is None else _i32p(s)))
 
+    def swap_counts(self):
+        """(swapped_in, swapped_out) of the last frame of a swapping engine"""
+        n_in, n_out = C.c_int(0), C.c_int(0)
+        capi.check(self.lib.itm_b200_engine_global_cache(self.h, None, None, C.byref(n_in), C.byref(n_out)))
+        return n_in.value, n_out.value
+
     def global_cache(self):
         """(hasStoredData uint8[entries], storedVoxelBlocks words[entries, 512], swapped_in, swapped_out) of a swapping engine -
         numpy views onto the engine's host memory"""
