@@ -152,6 +152,20 @@ def _pose_list(m):
 # ======================================================================================================================
 # reference arm
 
+class _c_stdout_to_stderr:
+    """The reference's ITMLibSettings constructor prints its tracker type on the C++ stdout; this process's stdout carries
+    one JSON line and nothing else, so file descriptor 1 points at stderr while a reference object is constructed."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def _reference_engine():
     from oracle import ref
 
@@ -161,7 +175,8 @@ def _reference_engine():
         return port.PortEngine(W, H), "port", 1, "C restatement, serial"
     cores = (os.cpu_count() or 1) if flavour == "fast" else 1
     os.environ["OMP_NUM_THREADS"] = str(cores)  # torchrun exports OMP_NUM_THREADS=1; libgomp reads it when the library loads
-    eng = ref.RefEngine(W, H, flavour=flavour)
+    with _c_stdout_to_stderr():
+        eng = ref.RefEngine(W, H, flavour=flavour)
     _omp_threads(cores)
     return eng, "reference", cores, "%s build (-O3 -mavx2 -mfma%s)" % (flavour, " -fopenmp" if flavour == "fast" else "")
 
@@ -655,7 +670,8 @@ def next_rows_sample(params, frames_dev, frames_np, n_frames=30):
         from oracle import ref
         flavour = "fast" if ref.available("fast") else ("parity" if ref.available("parity") else None)
         if flavour:
-            o = ref.RefEngine(W, H, flavour=flavour)
+            with _c_stdout_to_stderr():
+                o = ref.RefEngine(W, H, flavour=flavour)
             o.set_use_approximate_raycast(True)
             m = min(n, 12)
             for k in range(3):
