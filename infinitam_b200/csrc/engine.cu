@@ -132,6 +132,7 @@ int validate_params(const itm_b200_params *p) {
   if (p->depth_source != ITM_B200_DEPTH_AFFINE && p->depth_source != ITM_B200_DEPTH_KINECT_DISPARITY)
     return fail(ITM_B200_EINVAL, "unknown depth_source");
   if (p->icp_max_ctas < 0) return fail(ITM_B200_EINVAL, "icp_max_ctas must be >= 0");
+  if (p->swap_cache_blocks < 0) return fail(ITM_B200_EINVAL, "swap_cache_blocks must be >= 0");
   return ITM_B200_OK;
 }
 

@@ -435,19 +435,22 @@ struct IcpPixel {
 };
 
 // what a level's pixels share: refined reciprocals of the level's focal lengths and the multiplier that turns
-// i / w into one IMAD.HI (exact for i * (magic * w - 2^32) < 2^32: any image below 2^24 pixels with w < 2^8.. 2^12)
+// i / w into one IMAD.HI: magic = ceil(2^32 / w) is exact for every i with i * (magic * w - 2^32) < 2^32, which
+// w * w * h < 2^32 guarantees (1280x720: 1.2e9); wMagic = 0 (larger images, w = 1) means "divide"
 struct IcpLevelDerived {
   float rcpFx, rcpFy;
   unsigned wMagic;
   bool focalOk;  // fx, fy far from the exponent limits: the inline division sequence is exact
 };
+__device__ __forceinline__ int icp_row_of(int i, int w, unsigned wMagic) { return wMagic ? (int)__umulhi((unsigned)i, wMagic) : i / w; }
 __device__ __forceinline__ IcpLevelDerived icp_level_derived(const IcpLevelArgs &lv) {
   IcpLevelDerived d;
   const float ax = fabsf(lv.fx), ay = fabsf(lv.fy);
   d.focalOk = ax > 1e-3f && ax < 1e6f && ay > 1e-3f && ay < 1e6f;
   d.rcpFx = refined_rcp(d.focalOk ? lv.fx : 1.0f);
   d.rcpFy = refined_rcp(d.focalOk ? lv.fy : 1.0f);
-  d.wMagic = (unsigned)((0x100000000ull + (unsigned)lv.w - 1) / (unsigned)lv.w);
+  const bool magicOk = lv.w > 1 && (unsigned long long)lv.w * (unsigned long long)lv.w * (unsigned long long)lv.h < 0x100000000ull;
+  d.wMagic = magicOk ? (unsigned)((0x100000000ull + (unsigned)lv.w - 1) / (unsigned)lv.w) : 0u;
   return d;
 }
 
@@ -609,7 +612,7 @@ __device__ __forceinline__ void eval_to_row(const IcpLevelArgs &lv, const IcpLev
     const int i = ch * 32 + lane;
     if (i >= n) break;
     IcpPixel q1;
-    const int y1 = (int)__umulhi((unsigned)i, ld.wMagic);
+    const int y1 = icp_row_of(i, lv.w, ld.wMagic);
     TRACE0(traceSlot, 20);
     const float d1 = dNext;
     {

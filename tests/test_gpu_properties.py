@@ -100,6 +100,21 @@ def test_ragged_image_sizes():
         eng.close(); o.close()
 
 
+def test_tiny_image_runs():
+    """24x16: the coarsest pyramid level is a single pixel, the next one 3x2 - fewer pixels than a warp, far fewer than the
+    100 valid points the tracker wants.  The frame must go through (first frame bit-equal to the oracle: no tracking yet; the
+    later poses are whatever a singular system gives in either implementation)."""
+    o = port.PortEngine(24, 16)
+    eng = parity.make_cuda_engine(o)
+    seq = synth.sequence(3, 24, 16)
+    parity.compare_frame(o, eng, seq[0], 0, strict=True)
+    for k in (1, 2):
+        eng.ProcessFrame(None, seq[k])
+    _, counters = eng.Sync()
+    assert int(counters[4]) == 0  # no error flags
+    eng.close(); o.close()
+
+
 def test_long_free_running_sequence_stays_close_to_reference():
     """30 frames without teacher forcing: the trajectories may drift apart (ICP is chaotic in its rounding) but must stay
     within 2 mm / 2 mrad, and both must stay near the ground truth"""
