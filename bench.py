@@ -514,7 +514,7 @@ def sharded_c3_record(torch, dist, dev, local_rank, world, rank, n_frames=14, wa
         pe.tracker_type = p1.tracker_type = capi.TRACKER_EXTERNAL
         eng = ShardedEngine(pe, stream=tstream.cuda_stream)
         single = ITMMainEngine(p1)
-        worst = {"raycast_hit_mismatch": 0, "raycast_max_diff_m": 0.0, "raycast_over_1e-4_m": 0}
+        worst = {"raycast_hit_mismatch": 0, "raycast_max_diff_m": 0.0, "raycast_over_1e-4_m": 0, "raycast_unresolved_px": 0, "raycast_px_differing": 0}
         ok = True
         rec = {}
         for k in range(check_frames):
@@ -578,7 +578,8 @@ def sharded_c3_record(torch, dist, dev, local_rank, world, rank, n_frames=14, wa
     import parity
     rot, trans = parity.pose_diff(pose_s, pose_1)
     t = torch.tensor([tot, 0.0 if ok else 1.0, float(worst["raycast_hit_mismatch"]), worst["raycast_max_diff_m"], float(worst["raycast_over_1e-4_m"]),
-                      rot, trans, float(blocks_used), float(rec.get("owned_blocks", 0))], dtype=torch.float64, device=dev)
+                      rot, trans, float(blocks_used), float(rec.get("owned_blocks", 0)), float(worst["raycast_unresolved_px"]),
+                      float(worst["raycast_px_differing"])], dtype=torch.float64, device=dev)
     allr = [torch.empty_like(t) for _ in range(world)]
     dist.all_gather(allr, t)
     allr = torch.stack(allr).cpu().numpy()
@@ -587,7 +588,10 @@ def sharded_c3_record(torch, dist, dev, local_rank, world, rank, n_frames=14, wa
     out.update({"slab_layout": {"axis": layout[0], "origin_block": layout[1], "thickness_blocks": layout[2]},
                 "index_and_resident_voxels_bit_identical_to_single_gpu": bool(allr[:, 1].max() == 0.0), "checked_frames": check_frames,
                 "composed_raycast_vs_single_gpu": {"hit_mask_mismatch_px_max": int(allr[:, 2].max()), "max_point_diff_m": float(allr[:, 3].max()),
-                                                   "px_over_1e-4_m_max": int(allr[:, 4].max()), "pixels": w * h},
+                                                   "px_over_1e-4_m_max": int(allr[:, 4].max()), "pixels": w * h,
+                                                   "unresolved_px_max": int(allr[:, 9].max()), "px_differing_bitwise_max": int(allr[:, 10].max()),
+                                                   "note": "a pixel is unresolved when no rank could march its ray completely on its own voxels "
+                                                           "(reported as a miss); every other pixel is bit-identical to the single GPU's"},
                 "free_running_pose_diff_after_%d_frames" % n: {"rot_rad": float(allr[:, 5].max()), "trans_m": float(allr[:, 6].max())},
                 "voxel_blocks_in_use_per_rank": [int(x) for x in allr[:, 7]], "owned_blocks_per_rank_frame_%d" % (check_frames - 1): [int(x) for x in allr[:, 8]],
                 "frames": m, "frames_per_s": m / (tot_max * 1e-3), "ms_per_frame": tot_max / m,
@@ -595,7 +599,7 @@ def sharded_c3_record(torch, dist, dev, local_rank, world, rank, n_frames=14, wa
                 "gvoxel_updates_per_s_all_ranks": (nvis / m) * 512 / (stages[3] / ms * 1e-3) / 1e9 if stages[3] else None,
                 "stage_us_rank0": {a: round(1e3 * v / ms, 1) for a, v in zip(names + ["partial_raycast", "barrier_wait", "compose"], list(stages) + list(sh3))},
                 "collectives": "NCCL broadcast of the raw depth frame (1.8 MB) from rank 0; one flag barrier + peer reads of the partial raycast tiles "
-                               "that contain hits (NVLink); ICP maps and tracker replicated (no pose broadcast / G-H all-reduce needed)",
+                               "a rank could not complete itself (NVLink); ICP maps and tracker replicated (no pose broadcast / G-H all-reduce needed)",
                 "timing": "CUDA events around NCCL depth broadcast + frame on the shared stream, L2 flushed, max over ranks"})
     return out
 

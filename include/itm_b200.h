@@ -482,6 +482,10 @@ int itm_b200_engine_stage_times(itm_b200_engine *e, float ms8[8]);
 /* Sharded engines with set_profiling(1): device time of the last frame's partial ray cast, of the wait at the cross-GPU barrier
  * (= how far behind the slowest rank was) and of the nearest-hit composition (NVLink peer reads), in milliseconds. */
 int itm_b200_engine_shard_times(itm_b200_engine *e, float ms3[3]);
+/* Sharded engines: pixels of the last frame's composed raycast whose ray no rank could march completely on its own voxels
+ * (it passes through allocated blocks of two slabs beyond the one-block halo); they are reported as misses.  Every other
+ * pixel of the composed image - hit or miss - is bit-identical to a single GPU's.  Waits for the pending frames. */
+int itm_b200_engine_shard_unresolved(itm_b200_engine *e, int *pixels);
 
 /* ---- host-side pose arithmetic (no GPU needed; used by the adapter and by tests) ---------- */
 /* Matrix4f::inv (ORUtils/Matrix.h:162-218) */

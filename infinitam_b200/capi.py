@@ -124,7 +124,7 @@ SYMBOLS = [
     "itm_b200_take_cuda_error", "itm_b200_engine_get_stream", "itm_b200_engine_copy_to_buffer_dev", "itm_b200_compute_g_and_h_weighted", "itm_b200_depth_filtering", "itm_b200_compute_normal_and_weights", "itm_b200_swap_in_select", "itm_b200_swap_in_apply", "itm_b200_swap_out",
     "itm_b200_convert_disparity_to_depth", "itm_b200_engine_process_frame_with_pose", "itm_b200_engine_submit_frame",
     "itm_b200_engine_wait_frame", "itm_b200_shard_block_resident", "itm_b200_engine_shard_times", "itm_b200_track_camera_weighted",
-    "itm_b200_set_alloc_mode",
+    "itm_b200_set_alloc_mode", "itm_b200_engine_shard_unresolved",
 ]
 
 _lib = None

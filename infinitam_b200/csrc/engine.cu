@@ -1440,10 +1440,8 @@ RenderArgs engine_render_args(itm_b200_engine *e) {
 
 void stage_expected_depths(itm_b200_engine *e, cudaStream_t stream = nullptr) {
   RenderArgs a = engine_render_args(e);
-  if (e->residentVisibleIds) {
-    a.visibleIds = e->residentVisibleIds;
-    a.residentList = 1;
-  }
+  // (a sharded scene renders the expected depths from ALL visible blocks - the index is replicated - so that every rank
+  // marches the very ranges a single GPU would: launch_expected_depths accepts ptr = -1 entries there)
   a.minmaxReady = e->prologueDone ? 1 : 0;
   launch_expected_depths(a, stream ? stream : e->c->stream);
   g_launches += e->prologueDone ? 1 : 2;
@@ -2288,6 +2286,17 @@ int itm_b200_engine_shard_times(itm_b200_engine *e, float ms3[3]) {
   if (!e || !ms3) return fail(ITM_B200_EINVAL, "NULL argument");
   if (e->shard.world <= 1 || e->profiling != 1) return fail(ITM_B200_EINVAL, "needs a sharded engine with set_profiling(1)");
   for (int i = 0; i < 3; ++i) CU(cudaEventElapsedTime(&ms3[i], e->shardEv[i], e->shardEv[i + 1]));
+  return ITM_B200_OK;
+}
+
+int itm_b200_engine_shard_unresolved(itm_b200_engine *e, int *pixels) {
+  ON_DEVICE_OF_ENGINE(e);
+  if (!e || !pixels) return fail(ITM_B200_EINVAL, "NULL argument");
+  if (e->shard.world <= 1) return fail(ITM_B200_EINVAL, "needs a sharded engine");
+  int rc = pull_state(e->c);
+  if (rc) return rc;
+  // the frame that incremented frameNo to its current value composed with parity (frameNo - 1) & 1
+  *pixels = e->c->hst->shardUnresolved[(e->c->hst->frameNo - 1) & 1];
   return ITM_B200_OK;
 }
 

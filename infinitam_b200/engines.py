@@ -222,6 +222,12 @@ class ITMMainEngine:
         capi.check(self.lib.itm_b200_engine_shard_times(self.h, _f32p(ms)))
         return ms
 
+    def shard_unresolved(self):
+        """sharded engine: pixels of the last composed raycast that no rank could march completely (reported as misses)"""
+        n = C.c_int(0)
+        capi.check(self.lib.itm_b200_engine_shard_unresolved(self.h, C.byref(n)))
+        return n.value
+
     def stage_times(self):
         ms = np.zeros(8, np.float32)
         capi.check(self.lib.itm_b200_engine_stage_times(self.h, _f32p(ms)))

@@ -133,6 +133,10 @@ def compare_scene(eng, single, rank, world, layout, voxel_size):
     r["raycast_max_diff_m"] = float(d.max())
     r["raycast_over_1e-4_m"] = int((d > 1e-4).sum())
     r["raycast_bit_equal_px"] = float(np.mean(np.all(rs[both] == r1[both], axis=1))) if both.any() else 1.0
+    # pixels no rank could march completely are reported as misses and counted by the engine; every other pixel - hit or miss -
+    # must be the single GPU's bits
+    r["raycast_unresolved_px"] = int(eng.shard_unresolved())
+    r["raycast_px_differing"] = int(np.any(rs.view(np.uint32) != r1.view(np.uint32), axis=2).sum())
     ps, p1 = eng.read(capi.BUF_POINTS).reshape(H, W, 4), single.read(capi.BUF_POINTS).reshape(H, W, 4)
     r["icp_point_validity_mismatch"] = int(((ps[..., 3] > 0) != (p1[..., 3] > 0)).sum())
     return r

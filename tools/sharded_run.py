@@ -85,8 +85,11 @@ def main():
                 if tracker == capi.TRACKER_EXTERNAL:
                     rec.update(compare_scene(eng.engine, single, rank, world, eng.layout, args.voxel))
                     good = (rec["hash_pos_offset_equal"] and rec["visible_list_equal"] and rec["excess_counter_equal"] and rec["residency_matches_ptr"]
-                            and rec["resident_voxel_blocks_equal"] and rec["raycast_hit_mismatch"] <= 1e-3 * max(1, rec["raycast_hits_single"])
-                            and rec["raycast_over_1e-4_m"] <= 1e-3 * max(1, rec["raycast_hits_single"]))
+                            and rec["resident_voxel_blocks_equal"]
+                            # every pixel some rank could march completely is bit-identical to the single GPU's; the others
+                            # (counted by the engine, reported as misses) must stay rare
+                            and rec["raycast_px_differing"] <= rec["raycast_unresolved_px"] and rec["raycast_max_diff_m"] == 0.0
+                            and rec["raycast_unresolved_px"] <= 2e-2 * max(1, rec["raycast_hits_single"]))
                 else:
                     good = rot <= 1e-4 and trans <= 1e-4
                 rec["ok"] = bool(good)
