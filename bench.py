@@ -525,7 +525,7 @@ def sharded_c3_record(torch, dist, dev, local_rank, world, rank, n_frames=14, wa
             eng.Sync()
             single.EnqueueFrameDevice(seq[k].data_ptr())
             single.Sync()
-            rec = compare_scene(eng.engine, single, rank, world, eng.layout, 0.002)
+            rec = compare_scene(eng.engine, single, rank, world, eng.layout, 0.002, eng.halo)
             ok = ok and rec["hash_pos_offset_equal"] and rec["visible_list_equal"] and rec["residency_matches_ptr"] and rec["resident_voxel_blocks_equal"]
             for key in worst:
                 worst[key] = max(worst[key], rec[key])

@@ -382,6 +382,10 @@ typedef struct itm_b200_shard {
   void *tile_hit_dev[2][ITM_B200_MAX_SHARDS];         /* unsigned char[tiles] per frame parity and rank */
   void *barrier_flags_dev[ITM_B200_MAX_SHARDS];       /* unsigned[ITM_B200_MAX_SHARDS] of every rank, zero-initialised */
   void *stream;                                       /* cudaStream_t the frames are enqueued on (NULL: a private one) */
+  int halo_blocks;                                    /* blocks beyond its slab a rank keeps resident (and integrates redundantly); 0 = 1.
+                                                       * A ray can be marched by a rank as long as every allocated block it samples is
+                                                       * resident there: a wider halo leaves fewer pixels that no rank can complete
+                                                       * (itm_b200_engine_shard_unresolved) at the price of more redundant integration */
 } itm_b200_shard;
 int itm_b200_engine_create_sharded(const itm_b200_params *params, const itm_b200_shard *shard, itm_b200_engine **out);
 /* cudaMalloc + zero fill + cudaIpcGetMemHandle / cudaIpcOpenMemHandle (peer access enabled lazily) / close / free */
@@ -391,7 +395,8 @@ int itm_b200_ipc_close(void *dev_ptr);
 int itm_b200_ipc_free(void *dev_ptr);
 /* rank that owns the voxel block at block coordinate (x, y, z); itm_b200_shard_block_resident: 1 if `rank` keeps its payload */
 int itm_b200_shard_owner_of_block(int x, int y, int z, int world, int axis, int origin_block, int thickness_blocks);
-int itm_b200_shard_block_resident(int x, int y, int z, int rank, int world, int axis, int origin_block, int thickness_blocks);
+int itm_b200_shard_block_resident(int x, int y, int z, int rank, int world, int axis, int origin_block, int thickness_blocks);  /* halo 1 */
+int itm_b200_shard_block_resident_halo(int x, int y, int z, int rank, int world, int axis, int origin_block, int thickness_blocks, int halo_blocks);
 
 /* The cudaStream_t every frame of this engine is enqueued on (borrowed; valid until destroy): lets the host order its own
  * work - e.g. producing the next depth frame on the device - before or after frames without a host synchronisation. */

@@ -102,6 +102,7 @@ class Shard(C.Structure):
         ("axis", C.c_int), ("origin_block", C.c_int), ("thickness_blocks", C.c_int),
         ("partial_raycast_dev", (C.c_void_p * MAX_SHARDS) * 2), ("tile_hit_dev", (C.c_void_p * MAX_SHARDS) * 2),
         ("barrier_flags_dev", C.c_void_p * MAX_SHARDS), ("stream", C.c_void_p),
+        ("halo_blocks", C.c_int),
     ]
 
 
@@ -124,7 +125,7 @@ SYMBOLS = [
     "itm_b200_take_cuda_error", "itm_b200_engine_get_stream", "itm_b200_engine_copy_to_buffer_dev", "itm_b200_compute_g_and_h_weighted", "itm_b200_depth_filtering", "itm_b200_compute_normal_and_weights", "itm_b200_swap_in_select", "itm_b200_swap_in_apply", "itm_b200_swap_out",
     "itm_b200_convert_disparity_to_depth", "itm_b200_engine_process_frame_with_pose", "itm_b200_engine_submit_frame",
     "itm_b200_engine_wait_frame", "itm_b200_shard_block_resident", "itm_b200_engine_shard_times", "itm_b200_track_camera_weighted",
-    "itm_b200_set_alloc_mode", "itm_b200_engine_shard_unresolved",
+    "itm_b200_set_alloc_mode", "itm_b200_engine_shard_unresolved", "itm_b200_shard_block_resident_halo",
 ]
 
 _lib = None

@@ -1708,6 +1708,7 @@ int itm_b200_engine_create_sharded(const itm_b200_params *params, const itm_b200
   e->shard.axis = shard->axis;
   e->shard.origin = shard->origin_block;
   e->shard.thickness = shard->thickness_blocks;
+  e->shard.halo = shard->halo_blocks > 0 ? shard->halo_blocks : 1;
   for (int r = 0; r < shard->world; ++r) {
     for (int q = 0; q < 2; ++q) {
       e->shard.partial[q][r] = (float4 *)shard->partial_raycast_dev[q][r];
@@ -1762,11 +1763,15 @@ int itm_b200_shard_owner_of_block(int x, int y, int z, int world, int axis, int 
 }
 
 int itm_b200_shard_block_resident(int x, int y, int z, int rank, int world, int axis, int origin_block, int thickness_blocks) {
-  if (world < 1 || thickness_blocks < 1 || axis < 0 || axis > 2 || rank < 0 || rank >= world)
+  return itm_b200_shard_block_resident_halo(x, y, z, rank, world, axis, origin_block, thickness_blocks, 1);
+}
+
+int itm_b200_shard_block_resident_halo(int x, int y, int z, int rank, int world, int axis, int origin_block, int thickness_blocks, int halo_blocks) {
+  if (world < 1 || thickness_blocks < 1 || axis < 0 || axis > 2 || rank < 0 || rank >= world || halo_blocks < 1)
     return fail(ITM_B200_EINVAL, "world and thickness must be >= 1, axis 0..2, rank in [0, world)");
   ShardInfo sh;
   memset(&sh, 0, sizeof(sh));
-  sh.rank = rank; sh.world = world; sh.axis = axis; sh.origin = origin_block; sh.thickness = thickness_blocks;
+  sh.rank = rank; sh.world = world; sh.axis = axis; sh.origin = origin_block; sh.thickness = thickness_blocks; sh.halo = halo_blocks;
   return shard_block_resident(x, y, z, sh) ? 1 : 0;
 }
 

@@ -53,6 +53,7 @@ struct ShardInfo {
   int rank, world;                    // world == 1: single GPU, everything below unused
   int axis;                           // 0 / 1 / 2: block coordinate the slabs are cut along
   int origin, thickness;              // owner = clamp((coord - origin) / thickness, 0, world - 1)   (floor division)
+  int halo;                           // blocks beyond its slab a rank keeps resident (>= 1)
   float4 *partial[2][ITM_MAX_SHARDS];        // per frame parity: every rank's partial raycast image ([rank] = the local one)
   unsigned char *tileHit[2][ITM_MAX_SHARDS]; // ... and its per-tile "contains a hit" flags (16x8-pixel tiles, raster order)
   unsigned *flags[ITM_MAX_SHARDS];    // every rank's barrier words: flags[r][src] = last barrier number src has reached
@@ -70,8 +71,8 @@ __host__ __device__ __forceinline__ bool shard_block_resident(int x, int y, int 
   if (sh.world <= 1) return true;
   const int c = sh.axis == 0 ? x : (sh.axis == 1 ? y : z);
   const int lo = sh.origin + sh.rank * sh.thickness, hi = lo + sh.thickness;  // owned: [lo, hi), open-ended for the outer ranks
-  const bool aboveLo = sh.rank == 0 || c >= lo - 1;
-  const bool belowHi = sh.rank == sh.world - 1 || c < hi + 1;
+  const bool aboveLo = sh.rank == 0 || c >= lo - sh.halo;
+  const bool belowHi = sh.rank == sh.world - 1 || c < hi + sh.halo;
   return aboveLo && belowHi;
 }
 

@@ -83,7 +83,7 @@ def main():
                 rec = {"pass": label, "frame": k, "rank": rank, "pose_rot_rad": rot, "pose_trans_m": trans,
                        "alloc_failures": [int(cnt_s[3]), int(cnt_1[3])]}
                 if tracker == capi.TRACKER_EXTERNAL:
-                    rec.update(compare_scene(eng.engine, single, rank, world, eng.layout, args.voxel))
+                    rec.update(compare_scene(eng.engine, single, rank, world, eng.layout, args.voxel, eng.halo))
                     good = (rec["hash_pos_offset_equal"] and rec["visible_list_equal"] and rec["excess_counter_equal"] and rec["residency_matches_ptr"]
                             and rec["resident_voxel_blocks_equal"]
                             # every pixel some rank could march completely is bit-identical to the single GPU's; the others
