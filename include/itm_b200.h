@@ -388,6 +388,14 @@ typedef struct itm_b200_shard {
                                                        * (itm_b200_engine_shard_unresolved) at the price of more redundant integration */
 } itm_b200_shard;
 int itm_b200_engine_create_sharded(const itm_b200_params *params, const itm_b200_shard *shard, itm_b200_engine **out);
+/* Optional second step (all ranks, before the first frame): IPC handles of this rank's voxel pool and hash table, to be opened by
+ * the peers (itm_b200_ipc_open) and handed to their engines with shard_attach ([rank] is ignored).  With peers attached, the
+ * rays no rank can march completely on its own voxels are marched once more after the composition, reading the blocks held
+ * elsewhere from their owners over NVLink - the composed raycast image is then the single GPU's in every pixel.  Without,
+ * those pixels are reported as misses (itm_b200_engine_shard_unresolved counts them either way). */
+int itm_b200_engine_shard_export(itm_b200_engine *e, unsigned char voxels_handle[ITM_B200_IPC_HANDLE_BYTES],
+                                 unsigned char hash_handle[ITM_B200_IPC_HANDLE_BYTES]);
+int itm_b200_engine_shard_attach(itm_b200_engine *e, void *const peer_voxels_dev[ITM_B200_MAX_SHARDS], void *const peer_hash_dev[ITM_B200_MAX_SHARDS]);
 /* cudaMalloc + zero fill + cudaIpcGetMemHandle / cudaIpcOpenMemHandle (peer access enabled lazily) / close / free */
 int itm_b200_ipc_alloc(size_t bytes, void **dev_ptr, unsigned char handle[ITM_B200_IPC_HANDLE_BYTES]);
 int itm_b200_ipc_open(const unsigned char handle[ITM_B200_IPC_HANDLE_BYTES], void **dev_ptr);

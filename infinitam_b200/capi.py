@@ -126,6 +126,7 @@ SYMBOLS = [
     "itm_b200_convert_disparity_to_depth", "itm_b200_engine_process_frame_with_pose", "itm_b200_engine_submit_frame",
     "itm_b200_engine_wait_frame", "itm_b200_shard_block_resident", "itm_b200_engine_shard_times", "itm_b200_track_camera_weighted",
     "itm_b200_set_alloc_mode", "itm_b200_engine_shard_unresolved", "itm_b200_shard_block_resident_halo",
+    "itm_b200_engine_shard_export", "itm_b200_engine_shard_attach",
 ]
 
 _lib = None

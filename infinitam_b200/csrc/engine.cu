@@ -1242,6 +1242,7 @@ void engine_free(itm_b200_engine *e) {
   if (!e->externalBuffers) { RELEASE(cudaFree(e->voxels)); RELEASE(cudaFree(e->raycastResult)); }
   RELEASE(cudaFree(e->hash)); RELEASE(cudaFree(e->vbaAllocList)); RELEASE(cudaFree(e->excessAllocList));
   RELEASE(cudaFree(e->visibleIds)); RELEASE(cudaFree(e->residentVisibleIds)); RELEASE(cudaFree(e->visType)); RELEASE(cudaFree(e->minmax));
+  RELEASE(cudaFree(e->shard.unresolvedList));
   RELEASE(cudaFree(e->raycastImage)); RELEASE(cudaFree(e->points)); RELEASE(cudaFree(e->normals)); RELEASE(cudaFree(e->rawDepth));
   RELEASE(cudaFree(e->rgb)); RELEASE(cudaFree(e->depth));
   RELEASE(cudaFree(e->floatImage)); RELEASE(cudaFree(e->depthNormal)); RELEASE(cudaFree(e->depthUncertainty));
@@ -1412,6 +1413,11 @@ void stage_integrate(itm_b200_engine *e) {
   a.st = c->st;
   a.vp = c->vp;
   a.sp = c->sp;
+  // sharded scene with attached peers: nobody may still be reading this rank's voxels for the previous frame's fallback rays
+  if (e->shard.world > 1 && e->shard.unresolvedList && e->barrierSeq > 0) {
+    launch_shard_wait_readers(e->shard, e->barrierSeq, c->stream);
+    g_launches += 1;
+  }
   launch_integrate(a, c->stream);
   g_launches += 1;
 }
@@ -1461,6 +1467,10 @@ void stage_raycast(itm_b200_engine *e) {
     if (stamps) cudaEventRecord(e->shardEv[2], e->c->stream);
     launch_raycast_compose(a, e->c->stream);
     g_launches += 1;
+    if (e->shard.unresolvedList) {  // peers attached: the rays no rank could complete, with peer reads
+      launch_raycast_fallback(a, e->barrierSeq, e->c->stream);
+      g_launches += 1;
+    }
     if (stamps) cudaEventRecord(e->shardEv[3], e->c->stream);
   }
 }
@@ -1724,6 +1734,34 @@ int itm_b200_engine_create_sharded(const itm_b200_params *params, const itm_b200
     return rc;
   }
   *out = e;
+  return ITM_B200_OK;
+}
+
+int itm_b200_engine_shard_export(itm_b200_engine *e, unsigned char voxels_handle[ITM_B200_IPC_HANDLE_BYTES],
+                                 unsigned char hash_handle[ITM_B200_IPC_HANDLE_BYTES]) {
+  ON_DEVICE_OF_ENGINE(e);
+  if (!e || !voxels_handle || !hash_handle) return fail(ITM_B200_EINVAL, "NULL argument");
+  if (e->shard.world <= 1) return fail(ITM_B200_EINVAL, "needs a sharded engine");
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, e->voxels));
+  memset(voxels_handle, 0, ITM_B200_IPC_HANDLE_BYTES);
+  memcpy(voxels_handle, &h, sizeof(h));
+  CU(cudaIpcGetMemHandle(&h, e->hash));
+  memset(hash_handle, 0, ITM_B200_IPC_HANDLE_BYTES);
+  memcpy(hash_handle, &h, sizeof(h));
+  return ITM_B200_OK;
+}
+
+int itm_b200_engine_shard_attach(itm_b200_engine *e, void *const peer_voxels_dev[ITM_B200_MAX_SHARDS], void *const peer_hash_dev[ITM_B200_MAX_SHARDS]) {
+  ON_DEVICE_OF_ENGINE(e);
+  if (!e || !peer_voxels_dev || !peer_hash_dev) return fail(ITM_B200_EINVAL, "NULL argument");
+  if (e->shard.world <= 1) return fail(ITM_B200_EINVAL, "needs a sharded engine");
+  for (int r = 0; r < e->shard.world; ++r) {
+    if (r != e->shard.rank && (!peer_voxels_dev[r] || !peer_hash_dev[r])) return fail(ITM_B200_EINVAL, "every peer's voxel pool and hash table must be given");
+    e->shard.peerVoxels[r] = r == e->shard.rank ? (const uint32_t *)e->voxels : (const uint32_t *)peer_voxels_dev[r];
+    e->shard.peerTable[r] = r == e->shard.rank ? (const HashEntry *)e->hash : (const HashEntry *)peer_hash_dev[r];
+  }
+  if (!e->shard.unresolvedList) CU(cudaMalloc(&e->shard.unresolvedList, (size_t)e->c->vp.W * e->c->vp.H * sizeof(int)));
   return ITM_B200_OK;
 }
 

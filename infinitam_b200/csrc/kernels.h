@@ -57,6 +57,12 @@ struct ShardInfo {
   float4 *partial[2][ITM_MAX_SHARDS];        // per frame parity: every rank's partial raycast image ([rank] = the local one)
   unsigned char *tileHit[2][ITM_MAX_SHARDS]; // ... and its per-tile "contains a hit" flags (16x8-pixel tiles, raster order)
   unsigned *flags[ITM_MAX_SHARDS];    // every rank's barrier words: flags[r][src] = last barrier number src has reached
+                                      // (flags[r][16 + src]: the frame up to which src is through with reading peers' voxels)
+  // set by itm_b200_engine_shard_attach (else NULL: rays no rank can complete stay misses): every rank's voxel pool and hash
+  // table ([rank] = the local ones), and this rank's list of unresolved pixels
+  const uint32_t *peerVoxels[ITM_MAX_SHARDS];
+  const HashEntry *peerTable[ITM_MAX_SHARDS];
+  int *unresolvedList;
 };
 
 __host__ __device__ __forceinline__ int shard_floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
@@ -295,6 +301,10 @@ void launch_swap_out_direct(const SwapArgs &a, cudaStream_t s);
 
 // all ranks meet: returns (on the stream) once every rank has enqueued barrier number seq after its own prior work
 void launch_shard_barrier(const ShardInfo &sh, unsigned seq, cudaStream_t s);
+// rays no rank could complete, marched with peer reads of the blocks held elsewhere (needs the peers of shard_attach), then the
+// "through with the peers' voxels" signal; launch_shard_wait_readers: before a rank's next integration overwrites voxels
+void launch_raycast_fallback(const RenderArgs &a, unsigned seq, cudaStream_t s);
+void launch_shard_wait_readers(const ShardInfo &sh, unsigned seq, cudaStream_t s);
 int icp_max_ctas();
 int icp_track_grid();
 int integrate_grid();

@@ -209,6 +209,24 @@ class ShardedEngine:
         self.engine = ITMMainEngine.__new__(ITMMainEngine)
         self.engine.lib, self.engine.params, self.engine.W, self.engine.H, self.engine.h = self.lib, params, W, H, h
         self._raw = torch.empty((H, W), dtype=torch.int16, device=torch.device("cuda", torch.cuda.current_device()))
+        # every rank's voxel pool and hash table, peer-visible: the few rays no rank can march on its own voxels read the
+        # blocks held elsewhere from their owners (ITM_B200_SHARD_PEERS=0: they stay misses)
+        import os
+        self.peers = os.environ.get("ITM_B200_SHARD_PEERS", "1") != "0"
+        if self.peers:
+            hv, hh = C.create_string_buffer(capi.IPC_HANDLE_BYTES), C.create_string_buffer(capi.IPC_HANDLE_BYTES)
+            capi.check(self.lib.itm_b200_engine_shard_export(h, hv, hh))
+            peers = exchange_handles(hv.raw + hh.raw)
+            pv, ph = (C.c_void_p * capi.MAX_SHARDS)(), (C.c_void_p * capi.MAX_SHARDS)()
+            for r in range(self.world):
+                if r == self.rank:
+                    continue
+                for arr, off in ((pv, 0), (ph, capi.IPC_HANDLE_BYTES)):
+                    q = C.c_void_p()
+                    capi.check(self.lib.itm_b200_ipc_open(peers[r][off:off + capi.IPC_HANDLE_BYTES], C.byref(q)))
+                    self._opened.append(q)
+                    arr[r] = q.value
+            capi.check(self.lib.itm_b200_engine_shard_attach(h, pv, ph))
         dist.barrier()  # nobody reads a peer's buffers before that peer exists
 
     def EnqueueFrame(self, raw_depth_dev=None):

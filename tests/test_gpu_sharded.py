@@ -62,6 +62,22 @@ def test_two_rank_sharded_scene_matches_single_gpu():
 
 
 @pytest.mark.skipif(_gpu_count() < 2, reason="needs two GPUs with peer access")
+def test_slabs_across_the_viewing_direction_still_give_the_single_gpu_raycast():
+    """slabs cut along z (the viewing direction), 40 blocks thick: a few percent of the rays pass through allocated blocks of both
+    slabs, so that neither rank can march them on its own voxels - they are marched with peer reads over NVLink.  The composed
+    raycast image must be the single GPU's in every pixel, and the free-running poses identical."""
+    r = _run(["--check", "--frames", "6", "--size", "320x240", "--voxel", "0.005", "--pool", "0x10000", "--layout", "2,0,40"])
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-3000:]
+    recs = [x for x in _json_objects(r.stdout) if "frame" in x]
+    assert len(recs) == 2 * 2 * 6 and all(x["ok"] for x in recs)
+    a = [x for x in recs if x["pass"].startswith("A")]
+    assert max(x["raycast_unresolved_px"] for x in a) > 500, "the layout was meant to produce rays that cross slabs"
+    assert all(x["raycast_px_differing"] == 0 and x["raycast_hit_mismatch"] == 0 for x in a)
+    b = [x for x in recs if x["pass"].startswith("B")]
+    assert all(x["pose_rot_rad"] == 0.0 and x["pose_trans_m"] == 0.0 for x in b)
+
+
+@pytest.mark.skipif(_gpu_count() < 2, reason="needs two GPUs with peer access")
 def test_two_ranks_hold_a_scene_that_overflows_one_pool():
     """per-rank pool of 0x1400 blocks: one GPU runs out (allocation failures), two GPUs hold the scene without any"""
     r = _run(["--frames", "4", "--warmup", "1", "--size", "320x240", "--voxel", "0.005", "--pool", "0x1400"])
