@@ -1243,6 +1243,7 @@ void engine_free(itm_b200_engine *e) {
   RELEASE(cudaFree(e->hash)); RELEASE(cudaFree(e->vbaAllocList)); RELEASE(cudaFree(e->excessAllocList));
   RELEASE(cudaFree(e->visibleIds)); RELEASE(cudaFree(e->residentVisibleIds)); RELEASE(cudaFree(e->visType)); RELEASE(cudaFree(e->minmax));
   RELEASE(cudaFree(e->shard.unresolvedList));
+  RELEASE(cudaFree(e->shard.remotePtr));
   RELEASE(cudaFree(e->raycastImage)); RELEASE(cudaFree(e->points)); RELEASE(cudaFree(e->normals)); RELEASE(cudaFree(e->rawDepth));
   RELEASE(cudaFree(e->rgb)); RELEASE(cudaFree(e->depth));
   RELEASE(cudaFree(e->floatImage)); RELEASE(cudaFree(e->depthNormal)); RELEASE(cudaFree(e->depthUncertainty));
@@ -1286,6 +1287,7 @@ int engine_reset(itm_b200_engine *e) {
   const size_t P = (size_t)c->vp.W * c->vp.H;
   launch_reset_scene(e->voxels, e->vbaAllocList, e->hash, e->excessAllocList, c->sp, c->stream);
   g_launches += 1;
+  if (e->shard.remotePtr) CU(cudaMemsetAsync(e->shard.remotePtr, 0xFF, (size_t)c->sp.nEntries * sizeof(int), c->stream));
   // MemoryBlock constructors clear their memory (ORUtils/MemoryBlock.h:88-110)
   CU(cudaMemsetAsync(e->visType, 0, (size_t)((c->sp.nEntries + 8191) / 8192) * 8192, c->stream));
   CU(cudaMemsetAsync(e->visibleIds, 0, (size_t)c->sp.nLocal * 4 * (e->shard.world > 1 ? e->shard.world : 1), c->stream));
@@ -1761,7 +1763,11 @@ int itm_b200_engine_shard_attach(itm_b200_engine *e, void *const peer_voxels_dev
     e->shard.peerVoxels[r] = r == e->shard.rank ? (const uint32_t *)e->voxels : (const uint32_t *)peer_voxels_dev[r];
     e->shard.peerTable[r] = r == e->shard.rank ? (const HashEntry *)e->hash : (const HashEntry *)peer_hash_dev[r];
   }
-  if (!e->shard.unresolvedList) CU(cudaMalloc(&e->shard.unresolvedList, (size_t)e->c->vp.W * e->c->vp.H * sizeof(int)));
+  if (!e->shard.unresolvedList) {
+    CU(cudaMalloc(&e->shard.unresolvedList, (size_t)e->c->vp.W * e->c->vp.H * sizeof(int)));
+    CU(cudaMalloc(&e->shard.remotePtr, (size_t)e->c->sp.nEntries * sizeof(int)));
+    CU(cudaMemset(e->shard.remotePtr, 0xFF, (size_t)e->c->sp.nEntries * sizeof(int)));
+  }
   return ITM_B200_OK;
 }
 

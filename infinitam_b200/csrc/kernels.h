@@ -63,6 +63,7 @@ struct ShardInfo {
   const uint32_t *peerVoxels[ITM_MAX_SHARDS];
   const HashEntry *peerTable[ITM_MAX_SHARDS];
   int *unresolvedList;
+  int *remotePtr;                     // [nEntries] the owner's block number of an entry held elsewhere, once it has been looked up (-1: not yet)
 };
 
 __host__ __device__ __forceinline__ int shard_floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }

@@ -149,7 +149,7 @@ class ShardedEngine:
     own GPU.  The voxel payload is partitioned (slabs of block coordinates, see slab_layout), the per-rank partial raycast
     images are composed inside the frame by peer reads over NVLink; there is no other collective."""
 
-    def __init__(self, params, stream=None, layout=None, halo=None):
+    def __init__(self, params, stream=None, layout=None, halo=None, peers=None):
         """stream: raw cudaStream_t handle shared with torch (torch.cuda.Stream().cuda_stream, made current), so that the
         NCCL broadcast and the engine's kernels are ordered on one stream.  Must not be the legacy default stream (0).
         layout: (axis, origin_block, thickness_blocks); default: the synthetic room's x extent cut into world slabs.
@@ -212,7 +212,7 @@ class ShardedEngine:
         # every rank's voxel pool and hash table, peer-visible: the few rays no rank can march on its own voxels read the
         # blocks held elsewhere from their owners (ITM_B200_SHARD_PEERS=0: they stay misses)
         import os
-        self.peers = os.environ.get("ITM_B200_SHARD_PEERS", "1") != "0"
+        self.peers = (bool(peers) if peers is not None else os.environ.get("ITM_B200_SHARD_PEERS", "1") != "0") and self.world > 1
         if self.peers:
             hv, hh = C.create_string_buffer(capi.IPC_HANDLE_BYTES), C.create_string_buffer(capi.IPC_HANDLE_BYTES)
             capi.check(self.lib.itm_b200_engine_shard_export(h, hv, hh))
