@@ -365,10 +365,14 @@ int itm_b200_engine_wait_frame(itm_b200_engine *e, unsigned long long ticket, fl
  *     exist only where it is RESIDENT: on its owner and, as a one-block halo for the trilinear taps of the ray cast, on the
  *     neighbouring slab's rank.  Elsewhere its hash entry carries ptr = -1.  params.sdf_local_block_num is the pool PER RANK,
  *     so the scene a box can hold grows with the number of GPUs.
- *   - Every rank integrates its resident blocks, renders expected depths and casts all rays against them; the per-rank
- *     partial raycast images are composed per pixel by nearest hit, each rank pulling the peers' tiles that contain hits
- *     through NVLink peer pointers after one cross-GPU barrier.  ICP maps and the tracker run replicated on the composed
- *     image: all ranks compute the identical pose, so neither a pose broadcast nor a G/H all-reduce is needed.
+ *   - Every rank integrates its resident blocks, renders the expected depths from all visible blocks (their positions are in
+ *     the replicated index) and marches every ray over the range a single GPU would, noting whether a sample or trilinear tap
+ *     fell into a block held elsewhere.  A ray that never met one has seen exactly what a single GPU holds: its result - hit
+ *     or miss - is the single-GPU result bit for bit.  After one cross-GPU barrier every rank composes the full image from
+ *     such complete results, pulling through NVLink peer pointers the tiles it could not complete itself; rays no rank could
+ *     complete are marched once more with peer reads of the voxels held elsewhere (shard_export / shard_attach below).  ICP maps
+ *     and the tracker run replicated on the composed image - which is the single GPU's - so all ranks compute the identical
+ *     pose and neither a pose broadcast nor a G/H all-reduce is needed.
  * The peer-visible buffers (two partial images of width*height*16 bytes, two tile-flag arrays of ceil(w/16)*ceil(h/8) bytes,
  * ITM_B200_MAX_SHARDS barrier words) are allocated with itm_b200_ipc_alloc, their handles exchanged by the host
  * (torch.distributed all_gather in infinitam_b200/multi.py) and opened with itm_b200_ipc_open. */

@@ -45,9 +45,10 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, c
 //    neighbouring slab's rank.  Everywhere else the entry carries ptr = -1, the reference's own "allocated, but the payload
 //    is not in active memory" state (ITMHashEntry::ptr, ITMLibDefines.h:78-81), which every kernel already honours.
 //  * Each rank integrates its resident blocks (halo blocks redundantly: integration is a pure function of block, depth
-//    and pose), renders expected depths and casts ALL rays against its resident blocks only, reports a hit only when the
-//    surface point lies in a block it OWNS, and the per-rank partial images are composed per pixel by nearest hit
-//    (k_raycast_compose pulls the peers' tiles that contain hits over NVLink).  ICP maps and the tracker then run
+//    and pose), renders the expected depths from ALL visible blocks and marches ALL rays over those ranges with its own voxels
+//    (k_raycast_sharded).  A ray that never sampled a block held elsewhere is complete: its result is the single GPU's, bit for
+//    bit.  k_raycast_compose takes any complete result per pixel (pulling peers' tiles over NVLink), k_raycast_fallback marches
+//    the rays no rank could complete with peer reads of the voxels held elsewhere.  ICP maps and the tracker then run
 //    replicated on the composed image - no pose broadcast, no G/H all-reduce is needed for the ranks to stay in step.
 struct ShardInfo {
   int rank, world;                    // world == 1: single GPU, everything below unused
