@@ -208,6 +208,16 @@ int itm_b200_create_expected_depths(itm_b200_ctx *ctx, const itm_b200_scene *sce
 int itm_b200_create_icp_maps(itm_b200_ctx *ctx, const itm_b200_scene *scene, itm_b200_render_state *rs,
                              itm_b200_tracking_state *ts);
 
+/* IITMVisualisationEngine::CreatePointCloud (Engine/ITMVisualisationEngine.h:62-63; CPU reference
+ * ITMVisualisationEngine_CPU.cpp:242-264 and RenderPointCloud :424-462), the colour tracker's model of the scene: rays are
+ * cast with inv_M = ts->pose_d->GetInvM() * view->calib->trafo_rgb_to_depth.calib (the caller's product, used as it is) and
+ * the colour camera's intrinsics into rs->raycast_result, rs->raycast_image is shaded, and every pixel that kept its point
+ * (with skip_points: of the odd columns of the odd rows) appends, in raster order, location = point in metres (w = 1) to
+ * ts->points_map_dev and the interpolated voxel colour (w = 1; all zero for voxels without colour) to ts->normals_map_dev.
+ * *no_total_points = pointCloud->noTotalPoints; ts->pose_point_cloud = ts->pose_d. */
+int itm_b200_create_point_cloud(itm_b200_ctx *ctx, const itm_b200_scene *scene, itm_b200_render_state *rs, itm_b200_tracking_state *ts,
+                                const float inv_M[16], const float intrinsics_rgb[4], int skip_points, int *no_total_points);
+
 /* IITMVisualisationEngine::ForwardRender (Engine/ITMVisualisationEngine.h:73-74; CPU reference
  * ITMVisualisationEngine_CPU.cpp:289-354): rs->raycast_result (the last full raycast) is projected to ts->pose_d into
  * rs->forward_projection, pixels left without a point are ray cast, rs->raycast_image is shaded from the result.
@@ -463,6 +473,16 @@ int itm_b200_engine_global_cache(itm_b200_engine *e, const unsigned char **has_s
  * noFwdProjMissingPoints} (set_state ignores the last two). */
 int itm_b200_engine_get_state(itm_b200_engine *e, float pose_d[16], float pose_point_cloud[16], int state6[6]);
 int itm_b200_engine_set_state(itm_b200_engine *e, const float pose_d[16], const float pose_point_cloud[16], const int state6[6]);
+
+/* What ITMTrackingController::Prepare does for TRACKER_COLOR (Engine/ITMTrackingController.cpp:22-28): CreateExpectedDepths
+ * at pose_rgb = trafo_rgb_to_depth.calib_inv * pose_d with the colour camera's intrinsics, then CreatePointCloud (see
+ * itm_b200_create_point_cloud).  Here it is a query: it renders into buffers of its own and leaves the live render and
+ * tracking state - the depth tracker's maps - untouched.  trafo_rgb_to_depth: ITMExtrinsics::calib (column-major 4x4), NULL =
+ * identity; intrinsics_rgb: NULL = the depth camera's.  locations_host / colours_host: Vector4f[capacity_points] or NULL;
+ * image_host: Vector4u[w*h] (the shaded raycast) or NULL.  *no_total_points is the full count even if fewer were copied. */
+int itm_b200_engine_create_point_cloud(itm_b200_engine *e, const float trafo_rgb_to_depth[16], const float intrinsics_rgb[4], int skip_points,
+                                       float *locations_host, float *colours_host, int capacity_points, unsigned char *image_host,
+                                       int *no_total_points);
 
 /* ITMMainEngine::GetImage (ITMLib/Engine/ITMMainEngine.cpp:134-192).  image_type is ITMMainEngine::GetImageType
  * (Engine/ITMMainEngine.h:78-87).  out_host receives Vector4u[out_w * out_h]; for the ORIGINAL_* / SCENERAYCAST types

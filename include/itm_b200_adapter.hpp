@@ -340,8 +340,21 @@ class ITMVisualisationEngine_B200<TVoxel, ITMVoxelBlockHash> : public ITMVisuali
     itm_b200_check(itm_b200_find_surface(c->ctx, &s, &r, pose->GetM().m, intr), "FindSurface");
   }
 
-  // the colour tracker's point cloud (TRACKER_COLOR) is outside the depth-ICP fusion path (out of scope)
-  void CreatePointCloud(const ITMView *, ITMTrackingState *, ITMRenderState *, bool) const { DIEWITHEXCEPTION("libitm_b200: CreatePointCloud not provided"); }
+  // the colour tracker's model of the scene (ITMTrackingController.cpp:22-28 calls it for TRACKER_COLOR)
+  void CreatePointCloud(const ITMView *view, ITMTrackingState *trackingState, ITMRenderState *renderState, bool skipPoints) const {
+    itm_b200_scene s = b200_detail::scene_view(const_cast<Scene *>(this->scene));
+    itm_b200_render_state r = b200_detail::render_state_view((ITMRenderState_VH *)renderState);
+    r.img_width = renderState->raycastResult->noDims.x;  // CreatePointCloud_common: imgSize = raycastResult->noDims
+    r.img_height = renderState->raycastResult->noDims.y;
+    itm_b200_tracking_state t = b200_detail::tracking_state_view(trackingState);
+    const Matrix4f invM = trackingState->pose_d->GetInvM() * view->calib->trafo_rgb_to_depth.calib;  // ITMVisualisationEngine_CPU.cpp:247
+    const Vector4f &k = view->calib->intrinsics_rgb.projectionParamsSimple.all;
+    const float intr[4] = {k.x, k.y, k.z, k.w};
+    int noTotalPoints = 0;
+    itm_b200_check(itm_b200_create_point_cloud(c->ctx, &s, &r, &t, invM.m, intr, skipPoints ? 1 : 0, &noTotalPoints), "CreatePointCloud");
+    trackingState->pose_pointCloud->SetFrom(trackingState->pose_d);
+    trackingState->pointCloud->noTotalPoints = noTotalPoints;
+  }
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -86,6 +86,8 @@ struct itm_b200_ctx {
   unsigned long long *allocTileState = nullptr;
   unsigned long long *visTileState = nullptr;
   unsigned long long *otherTileState = nullptr;  // FindVisibleBlocks / swap selection / meshing: 8192-slot tiles, ticket [2]
+  unsigned long long *pcTileState = nullptr;     // CreatePointCloud: pcTiles 8192-pixel tiles + their ticket, made on first use
+  int pcTiles = 0;
   double *icpPartials = nullptr;
   unsigned *icpCounter = nullptr;
   unsigned long long *icpRows = nullptr;   // tagged CTA partial sums of k_icp_track
@@ -260,6 +262,7 @@ void ctx_free(itm_b200_ctx *c) {
   RELEASE(cudaFree(c->allocTileState));
   RELEASE(cudaFree(c->visTileState));
   RELEASE(cudaFree(c->otherTileState));
+  RELEASE(cudaFree(c->pcTileState));
   RELEASE(cudaFree(c->icpPartials));
   RELEASE(cudaFree(c->icpCounter));
   RELEASE(cudaFree(c->icpRows));
@@ -644,6 +647,56 @@ int itm_b200_create_icp_maps(itm_b200_ctx *c, const itm_b200_scene *scene, itm_b
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaGetLastError());
   // trackingState->pose_pointCloud->SetFrom(trackingState->pose_d)  (ITMVisualisationEngine_CPU.cpp:273)
+  memcpy(ts->pose_point_cloud, ts->pose_d, 64);
+  return ITM_B200_OK;
+}
+
+// scan state of CreatePointCloud for a W x H image (kept until an image of another size comes along)
+static int point_cloud_scan_state(itm_b200_ctx *c, int W, int H) {
+  const int tiles = point_cloud_tiles(W, H);
+  if (tiles == c->pcTiles) return ITM_B200_OK;
+  CU(cudaStreamSynchronize(c->stream));
+  cudaFree(c->pcTileState);
+  c->pcTileState = nullptr;
+  c->pcTiles = 0;
+  CU(cudaMalloc(&c->pcTileState, (size_t)(tiles + 1) * sizeof(unsigned long long)));
+  CU(cudaMemsetAsync(c->pcTileState, 0, (size_t)(tiles + 1) * sizeof(unsigned long long), c->stream));
+  c->pcTiles = tiles;
+  return ITM_B200_OK;
+}
+
+int itm_b200_create_point_cloud(itm_b200_ctx *c, const itm_b200_scene *scene, itm_b200_render_state *rs, itm_b200_tracking_state *ts,
+                                const float inv_M[16], const float intrinsics[4], int skip_points, int *no_total_points) {
+  ON_DEVICE_OF_CTX(c);
+  if (!c || !scene || !rs || !ts || !inv_M || !intrinsics || !no_total_points) return fail(ITM_B200_EINVAL, "NULL argument");
+  if (!ts->points_map_dev || !ts->normals_map_dev || !rs->raycast_image_dev || !rs->raycast_result_dev)
+    return fail(ITM_B200_EINVAL, "CreatePointCloud needs the point cloud's locations / colours and the render state's images");
+  // the caller's product pose_d->GetInvM() * trafo_rgb_to_depth.calib is used as it is (castRay and the light direction
+  // read nothing else); M_d is only kept consistent with it
+  memcpy(c->hst->invM_d, inv_M, 64);
+  mat4_inv(inv_M, c->hst->M_d);
+  int rc = push_state(c);
+  if (rc) return rc;
+  RenderArgs a;
+  memset(&a, 0, sizeof(a));
+  a.shard.world = 1;
+  a.voxels = scene->voxel_blocks_dev;
+  a.hashTable = scene->hash_entries_dev;
+  a.minmax = rs->rendering_range_image_dev;
+  a.raycastResult = rs->raycast_result_dev;
+  a.raycastImage = rs->raycast_image_dev;
+  a.st = c->st;
+  a.vp = rs_view(c, rs, intrinsics);
+  a.sp = c->sp;
+  rc = point_cloud_scan_state(c, a.vp.W, a.vp.H);
+  if (rc) return rc;
+  launch_render_image(a, rs->raycast_image_dev, ITM_B200_RENDER_SHADED_GREYSCALE, c->stream);
+  launch_point_cloud(a, skip_points, ts->points_map_dev, ts->normals_map_dev, c->pcTileState, c->pcTiles, c->stream);
+  g_launches += 2;
+  rc = pull_state(c);
+  if (rc) return rc;
+  *no_total_points = c->hst->noTotalPoints;
+  // trackingState->pose_pointCloud->SetFrom(trackingState->pose_d)  (ITMVisualisationEngine_CPU.cpp:250)
   memcpy(ts->pose_point_cloud, ts->pose_d, 64);
   return ITM_B200_OK;
 }
@@ -1075,6 +1128,11 @@ struct itm_b200_engine {
   FrameState *stFree = nullptr;    // device: pose + visible count of the free-view camera
   FrameState *hstFree = nullptr;   // pinned
   float *meshTriangles = nullptr;      // device ITMMesh::triangles (noMaxTriangles), allocated by the first UpdateMesh
+  float *cloudLocations = nullptr;     // CreatePointCloud query: Vector4f[W*H] each, sensor-sized render buffers of its own
+  float *cloudColours = nullptr;
+  float *cloudMinmax = nullptr;
+  float *cloudRaycastResult = nullptr;
+  unsigned char *cloudImage = nullptr;
   unsigned char *imageHost = nullptr;  // pinned staging for GetImage
   size_t imageHostBytes = 0;
   // tracking state
@@ -1249,6 +1307,8 @@ void engine_free(itm_b200_engine *e) {
   RELEASE(cudaFree(e->floatImage)); RELEASE(cudaFree(e->depthNormal)); RELEASE(cudaFree(e->depthUncertainty));
   RELEASE(cudaFree(e->forwardProjection)); RELEASE(cudaFree(e->fwdMissing)); RELEASE(cudaFree(e->stFree));
   RELEASE(cudaFree(e->freeVisibleIds)); RELEASE(cudaFree(e->freeMinmax)); RELEASE(cudaFree(e->freeRaycastResult)); RELEASE(cudaFree(e->freeImage));
+  RELEASE(cudaFree(e->cloudLocations)); RELEASE(cudaFree(e->cloudColours)); RELEASE(cudaFree(e->cloudMinmax));
+  RELEASE(cudaFree(e->cloudRaycastResult)); RELEASE(cudaFree(e->cloudImage));
   if (e->hstFree) RELEASE(cudaFreeHost(e->hstFree));
   if (e->imageHost) RELEASE(cudaFreeHost(e->imageHost));
   if (e->poseStage) RELEASE(cudaFreeHost(e->poseStage));
@@ -2285,6 +2345,76 @@ int itm_b200_engine_get_image(itm_b200_engine *e, int image_type, const float po
   CU(cudaMemcpyAsync(out_host, e->freeImage, N * 4, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
   CU(cudaGetLastError());
+  return ITM_B200_OK;
+}
+
+int itm_b200_engine_create_point_cloud(itm_b200_engine *e, const float trafo_rgb_to_depth[16], const float intrinsics_rgb[4], int skip_points,
+                                       float *locations_host, float *colours_host, int capacity_points, unsigned char *image_host,
+                                       int *no_total_points) {
+  ON_DEVICE_OF_ENGINE(e);
+  if (!e || !no_total_points) return fail(ITM_B200_EINVAL, "NULL argument");
+  if ((locations_host || colours_host) && capacity_points < 0) return fail(ITM_B200_EINVAL, "capacity_points must not be negative");
+  itm_b200_ctx *c = e->c;
+  if (e->shard.world > 1) return fail(ITM_B200_EINVAL, "CreatePointCloud is not provided for sharded scenes");
+  cudaStream_t s = c->stream;
+  const size_t P = (size_t)c->vp.W * c->vp.H;
+  if (!e->cloudLocations) {
+    CU(cudaMalloc(&e->cloudLocations, P * 16));
+    CU(cudaMalloc(&e->cloudColours, P * 16));
+    CU(cudaMalloc(&e->cloudMinmax, P * 8));  // full-size allocation like ITMRenderState::renderingRangeImage
+    CU(cudaMalloc(&e->cloudRaycastResult, P * 16));
+    CU(cudaMalloc(&e->cloudImage, P * 4));
+  }
+  int rc = pull_state(c);  // the tracked pose and the visible list's length
+  if (rc) return rc;
+  e->waitedFrameNo = e->deviceFrameNo;
+  // ITMExtrinsics::SetFrom (Objects/ITMExtrinsics.h:32-42): calib_inv = [R^T | -R^T t], the translation accumulated by subtraction
+  float calib[16], calibInv[16];
+  if (trafo_rgb_to_depth) memcpy(calib, trafo_rgb_to_depth, 64);
+  else for (int i = 0; i < 16; ++i) calib[i] = (i % 5 == 0) ? 1.0f : 0.0f;
+  for (int i = 0; i < 16; ++i) calibInv[i] = (i % 5 == 0) ? 1.0f : 0.0f;
+  for (int r = 0; r < 3; ++r)
+    for (int col = 0; col < 3; ++col) calibInv[r + 4 * col] = calib[col + 4 * r];
+  for (int r = 0; r < 3; ++r) {
+    float d = 0.0f;
+    for (int col = 0; col < 3; ++col) d -= calib[col + 4 * r] * calib[col + 4 * 3];
+    calibInv[r + 4 * 3] = d;
+  }
+  // Prepare (ITMTrackingController.cpp:24-26): pose_rgb = calib_inv * pose_d->GetM() for the ray ranges;
+  // CreatePointCloud_common (ITMVisualisationEngine_CPU.cpp:247): invM = pose_d->GetInvM() * calib for the rays
+  memset(e->hstFree, 0, sizeof(FrameState));
+  mat4_mul(calibInv, c->hst->M_d, e->hstFree->M_d);
+  mat4_mul(c->hst->invM_d, calib, e->hstFree->invM_d);
+  e->hstFree->noVisibleEntries = c->hst->noVisibleEntries;
+  CU(cudaMemcpyAsync(e->stFree, e->hstFree, sizeof(FrameState), cudaMemcpyHostToDevice, s));
+  RenderArgs a;
+  memset(&a, 0, sizeof(a));
+  a.shard.world = 1;
+  a.voxels = e->voxels;
+  a.hashTable = e->hash;
+  a.visibleIds = e->visibleIds;
+  a.minmax = e->cloudMinmax;
+  a.raycastResult = e->cloudRaycastResult;
+  a.raycastImage = e->cloudImage;
+  a.st = e->stFree;
+  a.vp = c->vp;
+  if (intrinsics_rgb) { a.vp.fx = intrinsics_rgb[0]; a.vp.fy = intrinsics_rgb[1]; a.vp.cx = intrinsics_rgb[2]; a.vp.cy = intrinsics_rgb[3]; }
+  a.sp = c->sp;
+  rc = point_cloud_scan_state(c, a.vp.W, a.vp.H);
+  if (rc) return rc;
+  launch_expected_depths(a, s);
+  launch_render_image(a, e->cloudImage, ITM_B200_RENDER_SHADED_GREYSCALE, s);
+  launch_point_cloud(a, skip_points, e->cloudLocations, e->cloudColours, c->pcTileState, c->pcTiles, s);
+  g_launches += 4;
+  CU(cudaMemcpyAsync(e->hstFree, e->stFree, sizeof(FrameState), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  CU(cudaGetLastError());
+  const int n = e->hstFree->noTotalPoints;
+  *no_total_points = n;
+  const size_t k = (size_t)(n < capacity_points ? n : capacity_points);
+  if (locations_host && k) CU(cudaMemcpy(locations_host, e->cloudLocations, k * 16, cudaMemcpyDeviceToHost));
+  if (colours_host && k) CU(cudaMemcpy(colours_host, e->cloudColours, k * 16, cudaMemcpyDeviceToHost));
+  if (image_host) CU(cudaMemcpy(image_host, e->cloudImage, P * 4, cudaMemcpyDeviceToHost));
   return ITM_B200_OK;
 }
 

@@ -356,6 +356,95 @@ __global__ void __launch_bounds__(128) k_render_image(const void *__restrict__ v
   outImage[locId] = out;
 }
 
+
+// ---------------------------------------------------------------- CreatePointCloud
+
+// RenderPointCloud (ITMVisualisationEngine_CPU.cpp:424-462) once k_render_image (grey) has shaded `image` from the same
+// rays: a pixel carries a point iff its grey value is non-zero (drawPixelGrey writes >= 51 wherever
+// computeNormalAndAngle kept the point, everything else is cleared), and with skipPoints only odd columns of odd rows
+// count.  The serial loop numbers the points in raster order; here 8192-pixel tiles do that with one look-back scan, then
+// every kept pixel writes location = point * voxelSize (w = 1) and colour = the interpolated voxel colour (w = 1;
+// all zero for voxels without colour) at its rank.
+template <int VW>
+__global__ void __launch_bounds__(256) k_point_cloud(const void *__restrict__ voxels, const void *__restrict__ table,
+                                                     const float4 *__restrict__ pointsRay, const uchar4 *__restrict__ image,
+                                                     float4 *__restrict__ locations, float4 *__restrict__ colours, FrameState *st,
+                                                     ViewParams vp, SceneParams sp, int skipPoints, unsigned long long *ticket,
+                                                     unsigned long long *tileState, int numTiles) {
+  __shared__ unsigned sWarp[8];
+  __shared__ unsigned sTotal;
+  __shared__ unsigned sExA;
+  __shared__ int sTile;
+  __shared__ unsigned sEpoch;
+  __shared__ unsigned sBallot[8][VIS_PER_THREAD];
+  if (threadIdx.x == 0) {
+    const unsigned long long t = atomicAdd(ticket, 1ull);
+    sTile = (int)(t % (unsigned long long)numTiles);
+    sEpoch = (unsigned)((t / (unsigned long long)numTiles + 1ull) & 0xFFFFFull);
+  }
+  __syncthreads();
+  const int tile = sTile;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nPixels = vp.W * vp.H;
+  const int warpPix0 = tile * VIS_TILE + warp * (32 * VIS_PER_THREAD);
+  unsigned cnt = 0;
+#pragma unroll 1
+  for (int i = 0; i < VIS_PER_THREAD; ++i) {
+    const int pix = warpPix0 + i * 32 + lane;
+    bool keep = false;
+    if (pix < nPixels) {
+      keep = __ldg(&image[pix]).w != 0;
+      if (skipPoints) {
+        const int y = pix / vp.W, x = pix - y * vp.W;
+        if ((x % 2 == 0) || (y % 2 == 0)) keep = false;
+      }
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) sBallot[warp][i] = b;
+    cnt += __popc(b);
+  }
+  if (lane == 0) sWarp[warp] = cnt;
+  __syncthreads();
+  unsigned warpBase = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    const unsigned s = sWarp[w];
+    if (w < warp) warpBase += s;
+    tot += s;
+  }
+  if (threadIdx.x == 0) sTotal = tot;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    unsigned exA, exB;
+    scan_lookback(tileState, tile, sEpoch, sTotal, 0u, exA, exB);
+    if (threadIdx.x == 0) {
+      sExA = exA;
+      if (tile == numTiles - 1) st->noTotalPoints = (int)(exA + sTotal);
+    }
+  }
+  __syncthreads();
+  if (cnt == 0) return;
+  VoxelReader<VW> rd;
+  rd.init(voxels, table, sp.nBuckets, sp.hashMask);
+  int pos = (int)(sExA + warpBase);
+  for (int i = 0; i < VIS_PER_THREAD; ++i) {
+    const unsigned b = sBallot[warp][i];
+    if ((b >> lane) & 1u) {
+      const int p = pos + __popc(b & ((1u << lane) - 1u));
+      const float4 pt = __ldg(&pointsRay[warpPix0 + i * 32 + lane]);
+      float4 clr = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      if constexpr (VW == 2) {
+        // readFromSDF_color4u_interpolated returns (r, g, b, 255) / 255, and "tmp /= tmp.w" divides by 1
+        colour_interpolated(rd, pt.x, pt.y, pt.z, clr.x, clr.y, clr.z);
+        clr.w = 1.0f;
+      }
+      colours[p] = clr;
+      locations[p] = make_float4(pt.x * sp.voxelSize, pt.y * sp.voxelSize, pt.z * sp.voxelSize, 1.0f);
+    }
+    pos += __popc(b);
+  }
+}
+
 }  // namespace
 
 namespace itm {
@@ -391,6 +480,21 @@ void launch_render_image(const RenderArgs &a, unsigned char *outImage, int type,
   else
     k_render_image<1><<<g, 128, 0, s>>>(a.voxels, a.hashTable, reinterpret_cast<const float2 *>(a.minmax), reinterpret_cast<float4 *>(a.raycastResult),
                                         reinterpret_cast<uchar4 *>(outImage), a.st, a.vp, a.sp, type);
+}
+
+int point_cloud_tiles(int W, int H) { return (W * H + VIS_TILE - 1) / VIS_TILE; }
+
+void launch_point_cloud(const RenderArgs &a, int skipPoints, float *locations, float *colours, unsigned long long *tileState,
+                        int numTiles, cudaStream_t s) {
+  // tileState[numTiles] is the ticket counter of this tile count
+  const float4 *rays = reinterpret_cast<const float4 *>(a.raycastResult);
+  const uchar4 *img = reinterpret_cast<const uchar4 *>(a.raycastImage);
+  if (a.sp.voxelWords == 2)
+    k_point_cloud<2><<<numTiles, 256, 0, s>>>(a.voxels, a.hashTable, rays, img, reinterpret_cast<float4 *>(locations), reinterpret_cast<float4 *>(colours),
+                                              a.st, a.vp, a.sp, skipPoints, tileState + numTiles, tileState, numTiles);
+  else
+    k_point_cloud<1><<<numTiles, 256, 0, s>>>(a.voxels, a.hashTable, rays, img, reinterpret_cast<float4 *>(locations), reinterpret_cast<float4 *>(colours),
+                                              a.st, a.vp, a.sp, skipPoints, tileState + numTiles, tileState, numTiles);
 }
 
 }  // namespace itm

@@ -230,6 +230,12 @@ void launch_mesh_scene(const MeshArgs &a, cudaStream_t s);
 // RenderImage: raycast at st's pose into a.raycastResult and shade into outImage (Vector4u[W*H]); type 0 grey, 1 colour
 // from volume, 2 colour from normal
 void launch_render_image(const RenderArgs &a, unsigned char *outImage, int type, cudaStream_t s);
+// RenderPointCloud's compaction over a.raycastResult / a.raycastImage (grey, from launch_render_image): points in raster
+// order into locations / colours, their number into a.st->noTotalPoints.  tileState: point_cloud_tiles(W, H) + 1 zeroed
+// words that stay with this tile count (the last one is the ticket counter).
+int point_cloud_tiles(int W, int H);
+void launch_point_cloud(const RenderArgs &a, int skipPoints, float *locations, float *colours, unsigned long long *tileState,
+                        int numTiles, cudaStream_t s);
 
 // fxDisparity != 0: Kinect disparity conversion 8 * b * fxDisparity / (a - raw) instead of the affine raw * a + b
 void launch_convert_depth(const short *raw, float *out, int n, float a, float b, cudaStream_t s, float fxDisparity = 0.0f);

@@ -108,6 +108,23 @@ class ITMMainEngine:
                                                       None if k is None else _f32p(k), out.ctypes.data, w, h))
         return out
 
+    def CreatePointCloud(self, trafo_rgb_to_depth=None, intrinsics_rgb=None, skipPoints: bool = False, with_image: bool = False):
+        """The TRACKER_COLOR branch of ITMTrackingController::Prepare (ITMTrackingController.cpp:22-28) as a query:
+        CreateExpectedDepths at the colour camera's pose + IITMVisualisationEngine::CreatePointCloud.  Returns
+        (locations[n, 4], colours[n, 4]) (+ the (h, w, 4) shaded raycast with with_image); the live maps stay untouched."""
+        T = None if trafo_rgb_to_depth is None else np.ascontiguousarray(trafo_rgb_to_depth, np.float32).reshape(16)
+        k = None if intrinsics_rgb is None else np.ascontiguousarray(intrinsics_rgb, np.float32).reshape(4)
+        n = C.c_int()
+        cap = self.W * self.H
+        loc = np.zeros((cap, 4), dtype=np.float32)
+        clr = np.zeros((cap, 4), dtype=np.float32)
+        img = np.zeros((self.H, self.W, 4), dtype=np.uint8) if with_image else None
+        capi.check(self.lib.itm_b200_engine_create_point_cloud(self.h, None if T is None else _f32p(T), None if k is None else _f32p(k),
+                                                               1 if skipPoints else 0, loc.ctypes.data, clr.ctypes.data, cap,
+                                                               None if img is None else img.ctypes.data, C.byref(n)))
+        out = (loc[: n.value].copy(), clr[: n.value].copy())
+        return out + (img,) if with_image else out
+
     def UpdateMesh(self):
         """ITMMainEngine::UpdateMesh (ITMMainEngine.cpp:97-101): marching cubes over the scene; returns the (n, 9) float32
         triangle array (p0, p1, p2 per row) in the reference's order"""

@@ -91,6 +91,15 @@ class AdapterEngine:
         """number of voxel blocks parked in the reference's host-side ITMGlobalCache"""
         return self.lib.adp_count_stored(self.h)
 
+    def create_point_cloud(self, trafo_rgb_to_depth=None, skip_points=False):
+        """Prepare()'s TRACKER_COLOR branch through the adapter: (locations[n, 4], colours[n, 4])"""
+        self.lib.adp_create_point_cloud.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        T = None if trafo_rgb_to_depth is None else np.ascontiguousarray(trafo_rgb_to_depth, dtype=np.float32).reshape(16)
+        n = self.lib.adp_create_point_cloud(self.h, None if T is None else T.ctypes.data, 1 if skip_points else 0)
+        if n < 0:
+            raise RuntimeError("adp_create_point_cloud: %s" % self.lib.adp_last_error().decode())
+        return self.read(READ_POINTS).reshape(-1, 4)[:n].copy(), self.read(READ_NORMALS).reshape(-1, 4)[:n].copy()
+
     def save_scene_to_mesh(self, path):
         self.lib.adp_save_scene_to_mesh.argtypes = [C.c_void_p, C.c_char_p]
         n = self.lib.adp_save_scene_to_mesh(self.h, str(path).encode())

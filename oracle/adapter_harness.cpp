@@ -205,6 +205,22 @@ int adp_get_free_image(adp_engine *e, int renderType, const float *poseM16, cons
   }
 }
 
+// the TRACKER_COLOR branch of ITMTrackingController::Prepare (ITMTrackingController.cpp:22-28) through the adapter's
+// visualisation engine; locations / colours come back with adp_read(4 / 5).  Returns noTotalPoints.
+int adp_create_point_cloud(adp_engine *e, const float *trafo16, int skipPoints) {
+  try {
+    if (e->view == NULL) return -1;
+    if (trafo16) { Matrix4f T(trafo16); e->calib.trafo_rgb_to_depth.SetFrom(T); e->view->calib->trafo_rgb_to_depth.SetFrom(T); }  // the view holds a copy
+    ITMPose pose_rgb(e->view->calib->trafo_rgb_to_depth.calib_inv * e->trackingState->pose_d->GetM());
+    e->vis->CreateExpectedDepths(&pose_rgb, &(e->view->calib->intrinsics_rgb), e->renderState);
+    e->vis->CreatePointCloud(e->view, e->trackingState, e->renderState, skipPoints != 0);
+    return e->trackingState->pointCloud->noTotalPoints;
+  } catch (std::exception &ex) {
+    g_err = ex.what();
+    return -1;
+  }
+}
+
 // ITMMainEngine::SaveSceneToMesh (ITMMainEngine.cpp:103-109): MeshScene into a CUDA ITMMesh, then the reference's own WriteSTL
 int adp_save_scene_to_mesh(adp_engine *e, const char *fileName) {
   try {

@@ -96,6 +96,9 @@ def declare_common(lib):
             getattr(lib, name).restype = C.c_void_p
         lib.ref_get_image.argtypes = [C.c_void_p, C.c_int, _f32p, _f32p, C.c_int, C.c_int, C.c_void_p]
         lib.ref_get_image.restype = C.c_int
+    if _has(lib, "ref_create_point_cloud"):
+        lib.ref_create_point_cloud.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        lib.ref_create_point_cloud.restype = C.c_int
     if _has(lib, "ref_mesh_scene"):
         lib.ref_mesh_scene.argtypes = [C.c_void_p, C.POINTER(_f32p), _i32p]
         lib.ref_mesh_scene.restype = C.c_int
@@ -287,6 +290,14 @@ class RefEngine:
     def fwd_missing_points(self):
         n = self.lib.ref_no_fwd_missing_points(self.h)
         return _view(self.lib.ref_fwd_missing_points(self.h), np.int32, self.W * self.H)[:n]
+
+    def create_point_cloud(self, trafo_rgb_to_depth=None, skip_points=False):
+        """Prepare()'s TRACKER_COLOR branch: (locations[n, 4], colours[n, 4]); overwrites the ICP maps and the render state"""
+        T = None if trafo_rgb_to_depth is None else np.ascontiguousarray(trafo_rgb_to_depth, dtype=np.float32).reshape(16)
+        n = self.lib.ref_create_point_cloud(self.h, None if T is None else T.ctypes.data, 1 if skip_points else 0)
+        if n < 0:
+            raise RuntimeError("ref_create_point_cloud: no view yet")
+        return self.points.reshape(-1, 4)[:n].copy(), self.normals.reshape(-1, 4)[:n].copy()
 
     def get_image(self, image_type, pose_M=None, intr=None, width=None, height=None):
         """ITMMainEngine::GetImage; returns (h, w, 4) uint8 or None when there is no view yet"""

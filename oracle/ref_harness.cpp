@@ -291,6 +291,18 @@ int ref_free_no_visible(ref_engine *e) { return e->renderStateFree ? ((ITMRender
 float *ref_free_minmax(ref_engine *e) { return e->renderStateFree ? (float *)e->renderStateFree->renderingRangeImage->GetData(MEMORYDEVICE_CPU) : NULL; }
 float *ref_free_raycast_result(ref_engine *e) { return e->renderStateFree ? (float *)e->renderStateFree->raycastResult->GetData(MEMORYDEVICE_CPU) : NULL; }
 
+// What ITMTrackingController::Prepare does for TRACKER_COLOR (ITMTrackingController.cpp:22-28): expected depths at the colour
+// camera's pose, then CreatePointCloud into trackingState->pointCloud (read it back with ref_points / ref_normals).
+// trafo16 = ITMExtrinsics::calib to install first (NULL keeps the current one).  Returns noTotalPoints.
+int ref_create_point_cloud(ref_engine *e, const float *trafo16, int skipPoints) {
+  if (e->view == NULL) return -1;
+  if (trafo16) { Matrix4f T(trafo16); e->calib.trafo_rgb_to_depth.SetFrom(T); e->view->calib->trafo_rgb_to_depth.SetFrom(T); }  // the view holds a copy
+  ITMPose pose_rgb(e->view->calib->trafo_rgb_to_depth.calib_inv * e->trackingState->pose_d->GetM());
+  e->vis->CreateExpectedDepths(&pose_rgb, &(e->view->calib->intrinsics_rgb), e->renderState);
+  e->vis->CreatePointCloud(e->view, e->trackingState, e->renderState, skipPoints != 0);
+  return e->trackingState->pointCloud->noTotalPoints;
+}
+
 // ITMMainEngine::UpdateMesh (ITMMainEngine.cpp:97-101): returns noTotalTriangles; *triangles = ITMMesh::Triangle array
 int ref_mesh_scene(ref_engine *e, float **triangles, int *noMaxTriangles) {
   if (!e->mesh) { e->mesh = new ITMMesh(MEMORYDEVICE_CPU); e->meshing = new ITMMeshingEngine_CPU<TV, TI>(); }

@@ -88,6 +88,18 @@ def test_adapter_approximate_raycast_and_free_view():
         img_o = o.get_image(3 if rt == 0 else 5, M, o.intr, w, h)
         bad = np.count_nonzero(np.abs(img_a.astype(np.int32) - img_o.astype(np.int32)).max(axis=2) > 1)
         assert img_o.any() and bad <= 0.002 * w * h, "free-view type %d: %d pixels differ" % (rt, bad)
+    # the colour tracker's Prepare branch (CreateExpectedDepths at the colour camera + CreatePointCloud) through the adapter;
+    # the two scenes agree to the free-running tolerance only, so compare counts and the clouds as sets
+    T = np.eye(4, dtype=np.float32)
+    T[:3, 3] = [0.025, -0.01, 0.005]  # ITMExtrinsics::calib of the colour camera, column-major below
+    T = np.ascontiguousarray(T.T).reshape(16)
+    for skip in (False, True):
+        loc_a, clr_a = a.create_point_cloud(T, skip)
+        loc_o, clr_o = o.create_point_cloud(T, skip)
+        assert len(loc_o) > 2000 and abs(len(loc_a) - len(loc_o)) <= 0.002 * len(loc_o), "point cloud sizes: %d vs %d" % (len(loc_a), len(loc_o))
+        assert np.all(loc_a[:, 3] == 1.0) and not clr_a.any()
+        assert np.abs(loc_a[:, :3].mean(axis=0) - loc_o[:, :3].mean(axis=0)).max() <= 1e-3
+        assert np.abs(loc_a[:, :3].min(axis=0) - loc_o[:, :3].min(axis=0)).max() <= 2e-2
     a.close(); o.close()
 
 

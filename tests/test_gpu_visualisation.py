@@ -161,3 +161,52 @@ def test_get_image_colour_from_volume():
     parity.push_scene(o, eng)
     _check_get_image(o, eng, w, h, colour=True)
     eng.close(); o.close()
+
+
+def _rgb_to_depth_trafo():
+    """a small colour-to-depth extrinsic calibration (ITMExtrinsics::calib, column-major): 2 degrees about y, a few cm"""
+    a = np.deg2rad(2.0)
+    T = np.eye(4, dtype=np.float32)
+    T[0, 0], T[0, 2], T[2, 0], T[2, 2] = np.cos(a), np.sin(a), -np.sin(a), np.cos(a)
+    T[:3, 3] = [0.025, -0.01, 0.005]
+    return np.ascontiguousarray(T.T).reshape(16)
+
+
+@pytest.mark.parametrize("flavour", ["parity", "rgb"])
+def test_create_point_cloud_equals_the_reference(flavour):
+    """IITMVisualisationEngine::CreatePointCloud as ITMTrackingController::Prepare calls it for TRACKER_COLOR
+    (ITMTrackingController.cpp:22-28): expected depths at the colour camera's pose, raycast through
+    invM_d * trafo_rgb_to_depth, shaded image, points and interpolated voxel colours compacted in raster order - with
+    and without skipPoints, for plain and colour voxels, on the reference's own scene (teacher forced)."""
+    if not ref.available(flavour):
+        pytest.skip("oracle/_ref library for flavour %r not built" % flavour)
+    w, h, n = 320, 240, 4
+    seq = synth.sequence(n, w, h)
+    o = ref.RefEngine(w, h, flavour=flavour)
+    eng = parity.make_cuda_engine(o)
+    if flavour == "rgb":
+        yy, xx = np.mgrid[0:h, 0:w]
+        rgb = np.stack([(xx * 3) % 256, (yy * 5) % 256, ((xx // 16 + yy // 16) % 2) * 200 + 20, np.full_like(xx, 255)], axis=-1).astype(np.uint8)
+        o.set_rgb(rgb)
+        eng.write(capi.BUF_RGB, rgb)
+    for k in range(n):
+        parity.compare_frame(o, eng, seq[k], k, strict=True)
+    parity.push_scene(o, eng)
+    maps_before = (eng.read(capi.BUF_POINTS).copy(), eng.read(capi.BUF_NORMALS).copy(), eng.read(capi.BUF_RAYCAST_RESULT).copy())
+    for T in (None, _rgb_to_depth_trafo()):
+        for skip in (False, True):
+            loc_a, clr_a, img_a = eng.CreatePointCloud(T, None, skip, with_image=True)
+            loc_o, clr_o = o.create_point_cloud(T, skip_points=skip)
+            assert len(loc_o) > (2000 if skip else 10000), "the reference found too few points for a meaningful check"
+            assert len(loc_a) == len(loc_o), "noTotalPoints: %d vs %d" % (len(loc_a), len(loc_o))
+            assert np.array_equal(img_a, o.raycast_image), "shaded raycast differs"
+            assert np.array_equal(loc_a, loc_o), "locations differ"
+            assert np.array_equal(clr_a, clr_o), "colours differ (max %g)" % np.abs(clr_a - clr_o).max()
+            if flavour == "rgb":
+                assert clr_o[:, :3].max() > 0.1 and np.all(clr_o[:, 3] == 1.0)
+            else:
+                assert not clr_o.any()
+    # a query: the depth tracker's maps and the live raycast are untouched
+    assert np.array_equal(maps_before[0], eng.read(capi.BUF_POINTS)) and np.array_equal(maps_before[1], eng.read(capi.BUF_NORMALS))
+    assert np.array_equal(maps_before[2], eng.read(capi.BUF_RAYCAST_RESULT))
+    eng.close(); o.close()
