@@ -288,6 +288,17 @@ int itm_b200_convert_disparity_to_depth(itm_b200_ctx *ctx, float *depth_out_dev,
 /* ITMLowLevelEngine::FilterSubsampleWithHoles(float) (Engine/ITMLowLevelEngine.h:22) */
 int itm_b200_filter_subsample_with_holes(itm_b200_ctx *ctx, float *out_dev, const float *in_dev, int w_in, int h_in);
 
+/* The rest of ITMLowLevelEngine (Engine/ITMLowLevelEngine.h:14-27; CPU reference DeviceSpecific/CPU/ITMLowLevelEngine_CPU.cpp:12-108,
+ * DeviceAgnostic/ITMLowLevelEngine.h): image helpers only the colour / Ren trackers call.  CopyImage copies `bytes` =
+ * image_in->dataSize * sizeof(T); the subsamplers write (w_in / 2) x (h_in / 2) pixels; GradientX / GradientY write Vector4s
+ * (short4) - interior pixels get the 3x3 Sobel / 8 of the colour channels and w = 255, and like the reference only the
+ * first w*h*sizeof(Vector3s) bytes of the output are cleared beforehand. */
+int itm_b200_copy_image(itm_b200_ctx *ctx, void *out_dev, const void *in_dev, size_t bytes);
+int itm_b200_filter_subsample_rgba(itm_b200_ctx *ctx, unsigned char *out_dev, const unsigned char *in_dev, int w_in, int h_in);
+int itm_b200_filter_subsample_with_holes_float4(itm_b200_ctx *ctx, float *out_dev, const float *in_dev, int w_in, int h_in);
+int itm_b200_gradient_x(itm_b200_ctx *ctx, short *grad_dev, const unsigned char *image_dev, int w, int h);
+int itm_b200_gradient_y(itm_b200_ctx *ctx, short *grad_dev, const unsigned char *image_dev, int w, int h);
+
 /* ITMDepthTracker::ComputeGandH (Engine/ITMDepthTracker.h:56): one evaluation of the
  * point-to-plane error at approx_inv_pose.  hessian is the full 6x6 (column-major, r + c*6) as
  * the reference returns it; returns noValidPoints through *no_valid_points. */

@@ -391,14 +391,42 @@ class ITMLowLevelEngine_B200 : public ITMLowLevelEngine {
                    "FilterSubsampleWithHoles");
   }
 
-  // colour-tracker helpers: not on the depth-ICP path
-  void CopyImage(ITMUChar4Image *, const ITMUChar4Image *) const { DIEWITHEXCEPTION("libitm_b200: CopyImage not provided"); }
-  void CopyImage(ITMFloatImage *, const ITMFloatImage *) const { DIEWITHEXCEPTION("libitm_b200: CopyImage not provided"); }
-  void CopyImage(ITMFloat4Image *, const ITMFloat4Image *) const { DIEWITHEXCEPTION("libitm_b200: CopyImage not provided"); }
-  void FilterSubsample(ITMUChar4Image *, const ITMUChar4Image *) const { DIEWITHEXCEPTION("libitm_b200: FilterSubsample not provided"); }
-  void FilterSubsampleWithHoles(ITMFloat4Image *, const ITMFloat4Image *) const { DIEWITHEXCEPTION("libitm_b200: FilterSubsampleWithHoles(float4) not provided"); }
-  void GradientX(ITMShort4Image *, const ITMUChar4Image *) const { DIEWITHEXCEPTION("libitm_b200: GradientX not provided"); }
-  void GradientY(ITMShort4Image *, const ITMUChar4Image *) const { DIEWITHEXCEPTION("libitm_b200: GradientY not provided"); }
+  // the helpers only the colour / Ren trackers call (ITMLowLevelEngine_CPU.cpp:12-108), images in HBM
+  void CopyImage(ITMUChar4Image *image_out, const ITMUChar4Image *image_in) const {
+    itm_b200_check(itm_b200_copy_image(c->ctx, image_out->GetData(MEMORYDEVICE_CUDA), image_in->GetData(MEMORYDEVICE_CUDA),
+                                       image_in->dataSize * sizeof(Vector4u)), "CopyImage");
+  }
+  void CopyImage(ITMFloatImage *image_out, const ITMFloatImage *image_in) const {
+    itm_b200_check(itm_b200_copy_image(c->ctx, image_out->GetData(MEMORYDEVICE_CUDA), image_in->GetData(MEMORYDEVICE_CUDA),
+                                       image_in->dataSize * sizeof(float)), "CopyImage");
+  }
+  void CopyImage(ITMFloat4Image *image_out, const ITMFloat4Image *image_in) const {
+    itm_b200_check(itm_b200_copy_image(c->ctx, image_out->GetData(MEMORYDEVICE_CUDA), image_in->GetData(MEMORYDEVICE_CUDA),
+                                       image_in->dataSize * sizeof(Vector4f)), "CopyImage");
+  }
+  void FilterSubsample(ITMUChar4Image *image_out, const ITMUChar4Image *image_in) const {
+    const Vector2i in = image_in->noDims;
+    image_out->ChangeDims(Vector2i(in.x / 2, in.y / 2));
+    itm_b200_check(itm_b200_filter_subsample_rgba(c->ctx, (unsigned char *)image_out->GetData(MEMORYDEVICE_CUDA),
+                                                  (const unsigned char *)image_in->GetData(MEMORYDEVICE_CUDA), in.x, in.y), "FilterSubsample");
+  }
+  void FilterSubsampleWithHoles(ITMFloat4Image *image_out, const ITMFloat4Image *image_in) const {
+    const Vector2i in = image_in->noDims;
+    image_out->ChangeDims(Vector2i(in.x / 2, in.y / 2));
+    itm_b200_check(itm_b200_filter_subsample_with_holes_float4(c->ctx, (float *)image_out->GetData(MEMORYDEVICE_CUDA),
+                                                               (const float *)image_in->GetData(MEMORYDEVICE_CUDA), in.x, in.y),
+                   "FilterSubsampleWithHoles");
+  }
+  void GradientX(ITMShort4Image *grad_out, const ITMUChar4Image *image_in) const {
+    grad_out->ChangeDims(image_in->noDims);
+    itm_b200_check(itm_b200_gradient_x(c->ctx, (short *)grad_out->GetData(MEMORYDEVICE_CUDA), (const unsigned char *)image_in->GetData(MEMORYDEVICE_CUDA),
+                                       image_in->noDims.x, image_in->noDims.y), "GradientX");
+  }
+  void GradientY(ITMShort4Image *grad_out, const ITMUChar4Image *image_in) const {
+    grad_out->ChangeDims(image_in->noDims);
+    itm_b200_check(itm_b200_gradient_y(c->ctx, (short *)grad_out->GetData(MEMORYDEVICE_CUDA), (const unsigned char *)image_in->GetData(MEMORYDEVICE_CUDA),
+                                       image_in->noDims.x, image_in->noDims.y), "GradientY");
+  }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -473,8 +501,24 @@ class ITMViewBuilder_B200 : public ITMViewBuilder {
                                                        depthIntrinsics->projectionParamsSimple.fx),
                    "ConvertDisparityToDepth");
   }
-  void UpdateView(ITMView **, ITMUChar4Image *, ITMFloatImage *) { DIEWITHEXCEPTION("libitm_b200: UpdateView(float depth) not provided"); }
-  void UpdateView(ITMView **, ITMUChar4Image *, ITMShortImage *, bool, ITMIMUMeasurement *) { DIEWITHEXCEPTION("libitm_b200: UpdateView(imu) not provided"); }
+  // ITMViewBuilder_CPU.cpp:66-75: the caller has already filled the view's own host images; only the upload happens here
+  void UpdateView(ITMView **view_ptr, ITMUChar4Image *rgbImage, ITMFloatImage *depthImage) {
+    if (*view_ptr == NULL) *view_ptr = new ITMView(calib, rgbImage->noDims, depthImage->noDims, true);
+    (*view_ptr)->rgb->UpdateDeviceFromHost();
+    (*view_ptr)->depth->UpdateDeviceFromHost();
+  }
+  // ITMViewBuilder_CPU.cpp:77-92: a view that also carries the IMU measurement, then the plain update
+  void UpdateView(ITMView **view_ptr, ITMUChar4Image *rgbImage, ITMShortImage *depthImage, bool useBilateralFilter, ITMIMUMeasurement *imuMeasurement) {
+    if (*view_ptr == NULL) {
+      *view_ptr = new ITMViewIMU(calib, rgbImage->noDims, depthImage->noDims, true);
+      if (this->shortImage != NULL) delete this->shortImage;
+      this->shortImage = new ITMShortImage(depthImage->noDims, true, true);
+      if (this->floatImage != NULL) delete this->floatImage;
+      this->floatImage = new ITMFloatImage(depthImage->noDims, true, true);
+    }
+    ((ITMViewIMU *)(*view_ptr))->imu->SetFrom(imuMeasurement);
+    this->UpdateView(view_ptr, rgbImage, depthImage, useBilateralFilter);
+  }
 };
 
 // ---------------------------------------------------------------------------------------------

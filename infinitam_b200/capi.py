@@ -120,7 +120,8 @@ SYMBOLS = [
     "itm_b200_engine_set_state", "itm_b200_engine_icp_stats", "itm_b200_engine_set_profiling", "itm_b200_engine_stage_times",
     "itm_b200_mat4_inv", "itm_b200_pose_from_inv_m_coerced", "itm_b200_compute_delta",
     "itm_b200_forward_render", "itm_b200_find_visible_blocks", "itm_b200_find_surface", "itm_b200_render_image",
-    "itm_b200_engine_get_image", "itm_b200_create_point_cloud", "itm_b200_engine_create_point_cloud", "itm_b200_mesh_scene", "itm_b200_write_stl", "itm_b200_write_obj",
+    "itm_b200_engine_get_image", "itm_b200_create_point_cloud", "itm_b200_engine_create_point_cloud", "itm_b200_copy_image",
+    "itm_b200_filter_subsample_rgba", "itm_b200_filter_subsample_with_holes_float4", "itm_b200_gradient_x", "itm_b200_gradient_y", "itm_b200_mesh_scene", "itm_b200_write_stl", "itm_b200_write_obj",
     "itm_b200_engine_mesh_scene", "itm_b200_engine_save_scene_to_mesh",
     "itm_b200_take_cuda_error", "itm_b200_engine_get_stream", "itm_b200_engine_copy_to_buffer_dev", "itm_b200_compute_g_and_h_weighted", "itm_b200_depth_filtering", "itm_b200_compute_normal_and_weights", "itm_b200_swap_in_select", "itm_b200_swap_in_apply", "itm_b200_swap_out",
     "itm_b200_convert_disparity_to_depth", "itm_b200_engine_process_frame_with_pose", "itm_b200_engine_submit_frame",
@@ -166,6 +167,9 @@ def load():
     lib.itm_b200_find_surface.argtypes = [vp, C.POINTER(Scene), C.POINTER(RenderState), f32p, f32p]
     lib.itm_b200_render_image.argtypes = [vp, C.POINTER(Scene), C.POINTER(RenderState), f32p, f32p, vp, C.c_int]
     lib.itm_b200_engine_get_image.argtypes = [vp, C.c_int, f32p, f32p, vp, C.c_int, C.c_int]
+    lib.itm_b200_copy_image.argtypes = [vp, vp, vp, C.c_size_t]
+    for name in ("itm_b200_filter_subsample_rgba", "itm_b200_filter_subsample_with_holes_float4", "itm_b200_gradient_x", "itm_b200_gradient_y"):
+        getattr(lib, name).argtypes = [vp, vp, vp, C.c_int, C.c_int]
     lib.itm_b200_create_point_cloud.argtypes = [vp, C.POINTER(Scene), C.POINTER(RenderState), C.POINTER(TrackingState), f32p, f32p,
                                                 C.c_int, C.POINTER(C.c_int)]
     lib.itm_b200_engine_create_point_cloud.argtypes = [vp, f32p, f32p, C.c_int, vp, vp, C.c_int, vp, C.POINTER(C.c_int)]

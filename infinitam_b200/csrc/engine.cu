@@ -969,6 +969,49 @@ int itm_b200_filter_subsample_with_holes(itm_b200_ctx *c, float *out_dev, const 
   return ITM_B200_OK;
 }
 
+int itm_b200_copy_image(itm_b200_ctx *c, void *out_dev, const void *in_dev, size_t bytes) {
+  ON_DEVICE_OF_CTX(c);
+  if (!c || !out_dev || !in_dev) return fail(ITM_B200_EINVAL, "NULL argument");
+  CU(cudaMemcpyAsync(out_dev, in_dev, bytes, cudaMemcpyDeviceToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return ITM_B200_OK;
+}
+
+int itm_b200_filter_subsample_rgba(itm_b200_ctx *c, unsigned char *out_dev, const unsigned char *in_dev, int w_in, int h_in) {
+  ON_DEVICE_OF_CTX(c);
+  if (!c || !out_dev || !in_dev) return fail(ITM_B200_EINVAL, "NULL argument");
+  if (w_in < 2 || h_in < 2) return ITM_B200_OK;  // newDims has a zero: the reference's loops do nothing
+  launch_subsample_rgba(out_dev, in_dev, w_in, h_in, c->stream);
+  g_launches += 1;
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  return ITM_B200_OK;
+}
+
+int itm_b200_filter_subsample_with_holes_float4(itm_b200_ctx *c, float *out_dev, const float *in_dev, int w_in, int h_in) {
+  ON_DEVICE_OF_CTX(c);
+  if (!c || !out_dev || !in_dev) return fail(ITM_B200_EINVAL, "NULL argument");
+  if (w_in < 2 || h_in < 2) return ITM_B200_OK;
+  launch_subsample_holes4(out_dev, in_dev, w_in, h_in, c->stream);
+  g_launches += 1;
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  return ITM_B200_OK;
+}
+
+static int gradient_common(itm_b200_ctx *c, short *grad_dev, const unsigned char *image_dev, int w, int h, int alongX) {
+  ON_DEVICE_OF_CTX(c);
+  if (!c || !grad_dev || !image_dev) return fail(ITM_B200_EINVAL, "NULL argument");
+  if (w <= 0 || h <= 0) return fail(ITM_B200_EINVAL, "image size must be positive");
+  CU(launch_gradient(grad_dev, image_dev, w, h, alongX, c->stream));
+  g_launches += 1;
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  return ITM_B200_OK;
+}
+int itm_b200_gradient_x(itm_b200_ctx *c, short *grad_dev, const unsigned char *image_dev, int w, int h) { return gradient_common(c, grad_dev, image_dev, w, h, 1); }
+int itm_b200_gradient_y(itm_b200_ctx *c, short *grad_dev, const unsigned char *image_dev, int w, int h) { return gradient_common(c, grad_dev, image_dev, w, h, 0); }
+
 static int compute_g_and_h_common(itm_b200_ctx *c, const float *level_weight_dev, const float *level_depth_dev, int w, int h, const float view_intrinsics[4],
                              const float *points_map_dev, const float *normals_map_dev, int scene_w, int scene_h,
                              const float scene_intrinsics[4], const float approx_inv_pose[16], const float scene_pose[16], float dist_thresh,

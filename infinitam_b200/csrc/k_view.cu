@@ -155,6 +155,58 @@ __global__ void k_subsample_holes(float *__restrict__ out, const float *__restri
   out[x + y * wOut] = subsample4(__ldg(p), __ldg(p + 1), __ldg(p + wIn), __ldg(p + wIn + 1));
 }
 
+// ---- the image helpers of ITMLowLevelEngine that only the colour / Ren trackers call (DeviceAgnostic/ITMLowLevelEngine.h) ----
+
+// filterSubsample (:7-24): 2x2 box on uchar4, integer mean
+__global__ void k_subsample_rgba(uchar4 *__restrict__ out, const uchar4 *__restrict__ in, int wOut, int hOut, int wIn) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= wOut || y >= hOut) return;
+  const uchar4 *p = in + 2 * x + 2 * y * wIn;
+  const uchar4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + wIn), d = __ldg(p + wIn + 1);
+  out[x + y * wOut] = make_uchar4((unsigned char)(((int)a.x + b.x + c.x + d.x) / 4), (unsigned char)(((int)a.y + b.y + c.y + d.y) / 4),
+                                  (unsigned char)(((int)a.z + b.z + c.z + d.z) / 4), (unsigned char)(((int)a.w + b.w + c.w + d.w) / 4));
+}
+
+// filterSubsampleWithHoles for Vector4f (:49-72): mean of the taps with w >= 0 (all four components, w included), in tap
+// order; (0, 0, 0, -1) if there is none
+__global__ void k_subsample_holes4(float4 *__restrict__ out, const float4 *__restrict__ in, int wOut, int hOut, int wIn) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= wOut || y >= hOut) return;
+  const float4 *p = in + 2 * x + 2 * y * wIn;
+  const float4 t[4] = {__ldg(p), __ldg(p + 1), __ldg(p + wIn), __ldg(p + wIn + 1)};
+  float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  float good = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (t[k].w >= 0) {
+      acc.x += t[k].x; acc.y += t[k].y; acc.z += t[k].z; acc.w += t[k].w;
+      good += 1.0f;
+    }
+  if (good > 0) { acc.x /= good; acc.y /= good; acc.z /= good; acc.w /= good; }
+  else acc.w = -1.0f;
+  out[x + y * wOut] = acc;
+}
+
+// gradientX / gradientY (:74-124): 3x3 Sobel on the colour channels, integer arithmetic, / 8 truncating; w = 255.  Only
+// interior pixels are written: the reference driver clears the first W*H*sizeof(Vector3s) bytes of the Vector4s image
+// beforehand (ITMLowLevelEngine_CPU.cpp:87,101), i.e. border pixels in its last quarter keep what they held - the
+// launcher does the same.
+template <bool ALONG_X>
+__global__ void k_gradient(short4 *__restrict__ grad, const uchar4 *__restrict__ image, int W, int H) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x < 1 || y < 1 || x >= W - 1 || y >= H - 1) return;
+  int dx[3], dy[3], dz[3];
+#pragma unroll
+  for (int k = -1; k <= 1; ++k) {
+    const uchar4 hi = ALONG_X ? __ldg(image + (x + 1) + (y + k) * W) : __ldg(image + (x + k) + (y + 1) * W);
+    const uchar4 lo = ALONG_X ? __ldg(image + (x - 1) + (y + k) * W) : __ldg(image + (x + k) + (y - 1) * W);
+    // each difference is stored in a short before it is combined (no truncation: |difference| <= 255)
+    dx[k + 1] = (int)hi.x - (int)lo.x; dy[k + 1] = (int)hi.y - (int)lo.y; dz[k + 1] = (int)hi.z - (int)lo.z;
+  }
+  grad[x + y * W] = make_short4((short)((dx[0] + 2 * dx[1] + dx[2]) / 8), (short)((dy[0] + 2 * dy[1] + dy[2]) / 8),
+                                (short)((dz[0] + 2 * dz[1] + dz[2]) / 8), (short)((2 * 255 + 2 * (2 * 255) + 2 * 255) / 8));
+}
+
 // filterDepth (ITMLib/Engine/DeviceAgnostic/ITMViewBuilder.h:31-56): 5x5 bilateral filter with the Kinect noise model as range
 // sigma; interior pixels only, the 2-pixel border stays 0 (DepthFiltering clears the output first, ITMViewBuilder_CPU.cpp:116-128)
 #define ITM_MEAN_SIGMA_L 1.2232f
@@ -249,6 +301,27 @@ void launch_subsample_holes(float *out, const float *in, int wIn, int hIn, cudaS
   const int wOut = wIn / 2, hOut = hIn / 2;
   dim3 b(32, 8), g((wOut + 31) / 32, (hOut + 7) / 8);
   k_subsample_holes<<<g, b, 0, s>>>(out, in, wOut, hOut, wIn);
+}
+
+void launch_subsample_rgba(unsigned char *out, const unsigned char *in, int wIn, int hIn, cudaStream_t s) {
+  const int wOut = wIn / 2, hOut = hIn / 2;
+  dim3 b(32, 8), g((wOut + 31) / 32, (hOut + 7) / 8);
+  k_subsample_rgba<<<g, b, 0, s>>>(reinterpret_cast<uchar4 *>(out), reinterpret_cast<const uchar4 *>(in), wOut, hOut, wIn);
+}
+
+void launch_subsample_holes4(float *out, const float *in, int wIn, int hIn, cudaStream_t s) {
+  const int wOut = wIn / 2, hOut = hIn / 2;
+  dim3 b(32, 8), g((wOut + 31) / 32, (hOut + 7) / 8);
+  k_subsample_holes4<<<g, b, 0, s>>>(reinterpret_cast<float4 *>(out), reinterpret_cast<const float4 *>(in), wOut, hOut, wIn);
+}
+
+cudaError_t launch_gradient(short *grad, const unsigned char *image, int W, int H, int alongX, cudaStream_t s) {
+  const cudaError_t e = cudaMemsetAsync(grad, 0, (size_t)W * H * 6, s);  // sizeof(Vector3s), like the reference driver
+  if (e != cudaSuccess) return e;
+  dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
+  if (alongX) k_gradient<true><<<g, b, 0, s>>>(reinterpret_cast<short4 *>(grad), reinterpret_cast<const uchar4 *>(image), W, H);
+  else k_gradient<false><<<g, b, 0, s>>>(reinterpret_cast<short4 *>(grad), reinterpret_cast<const uchar4 *>(image), W, H);
+  return cudaSuccess;
 }
 
 // Fused conversion + pyramid.  levels[0] is the full-resolution float depth; levels 1.. are

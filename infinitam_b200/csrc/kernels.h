@@ -240,6 +240,11 @@ void launch_point_cloud(const RenderArgs &a, int skipPoints, float *locations, f
 // fxDisparity != 0: Kinect disparity conversion 8 * b * fxDisparity / (a - raw) instead of the affine raw * a + b
 void launch_convert_depth(const short *raw, float *out, int n, float a, float b, cudaStream_t s, float fxDisparity = 0.0f);
 void launch_subsample_holes(float *out, const float *in, int wIn, int hIn, cudaStream_t s);
+// ITMLowLevelEngine's remaining image helpers (colour / Ren trackers): FilterSubsample(uchar4), FilterSubsampleWithHoles(Vector4f),
+// GradientX / GradientY (Vector4s out; clears the first W*H*6 bytes like the reference driver, writes interior pixels)
+void launch_subsample_rgba(unsigned char *out, const unsigned char *in, int wIn, int hIn, cudaStream_t s);
+void launch_subsample_holes4(float *out, const float *in, int wIn, int hIn, cudaStream_t s);
+cudaError_t launch_gradient(short *grad, const unsigned char *image, int W, int H, int alongX, cudaStream_t s);
 // ITMViewBuilder::DepthFiltering / ComputeNormalAndWeights (useBilateralFilter / modelSensorNoise)
 void launch_filter_depth(float *out, const float *in, int W, int H, cudaStream_t s);
 void launch_normal_weight(float *normalOut, float *sigmaOut, const float *depth, int W, int H, const float intr[4], cudaStream_t s);

@@ -100,6 +100,28 @@ class AdapterEngine:
             raise RuntimeError("adp_create_point_cloud: %s" % self.lib.adp_last_error().decode())
         return self.read(READ_POINTS).reshape(-1, 4)[:n].copy(), self.read(READ_NORMALS).reshape(-1, 4)[:n].copy()
 
+    def low_level(self, op, image, prefill=0):
+        """the same helper through ITMLowLevelEngine_B200 (see oracle.ref.RefEngine.low_level)"""
+        from oracle.ref import _low_level
+        self.lib.adp_low_level.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        self.lib.adp_low_level.restype = C.c_longlong
+        try:
+            return _low_level(self.lib.adp_low_level, self.h, op, image, prefill)
+        except RuntimeError as ex:
+            raise RuntimeError("%s: %s" % (ex, self.lib.adp_last_error().decode()))
+
+    def update_view_variants(self, depth_f32, raw_depth_i16):
+        """ITMViewBuilder_B200::UpdateView(rgb, float depth) and UpdateView(rgb, short depth, filter, imu) on fresh views:
+        returns (device depth after the float variant, device depth after the IMU variant)"""
+        self.lib.adp_update_view_variants.argtypes = [C.c_void_p] * 5
+        d = np.ascontiguousarray(depth_f32, np.float32)
+        r = np.ascontiguousarray(raw_depth_i16, np.int16)
+        o1, o2 = np.zeros_like(d), np.zeros_like(d)
+        rc = self.lib.adp_update_view_variants(self.h, d.ctypes.data, o1.ctypes.data, r.ctypes.data, o2.ctypes.data)
+        if rc != 0:
+            raise RuntimeError("adp_update_view_variants: rc %d %s" % (rc, self.lib.adp_last_error().decode()))
+        return o1, o2
+
     def save_scene_to_mesh(self, path):
         self.lib.adp_save_scene_to_mesh.argtypes = [C.c_void_p, C.c_char_p]
         n = self.lib.adp_save_scene_to_mesh(self.h, str(path).encode())

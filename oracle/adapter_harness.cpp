@@ -221,6 +221,74 @@ int adp_create_point_cloud(adp_engine *e, const float *trafo16, int skipPoints) 
   }
 }
 
+// the same helpers through ITMLowLevelEngine_B200 (images in HBM); see ref_low_level in ref_harness.cpp for the contract
+long long adp_low_level(adp_engine *e, int op, const void *in, int w, int h, void *out, int prefillByte) {
+  try {
+    const Vector2i dims(w, h), half(w / 2, h / 2);
+    const size_t P = (size_t)w * h, Q = (size_t)half.x * half.y;
+    if (op == 2) {
+      ITMFloat4Image src(dims, true, true), dst(half, true, true);
+      memcpy(src.GetData(MEMORYDEVICE_CPU), in, P * 16);
+      src.UpdateDeviceFromHost();
+      dst.Clear((unsigned char)prefillByte);
+      e->lowLevel->FilterSubsampleWithHoles(&dst, &src);
+      dst.UpdateHostFromDevice();
+      memcpy(out, dst.GetData(MEMORYDEVICE_CPU), Q * 16);
+      return (long long)(Q * 16);
+    }
+    ITMUChar4Image src(dims, true, true);
+    memcpy(src.GetData(MEMORYDEVICE_CPU), in, P * 4);
+    src.UpdateDeviceFromHost();
+    if (op == 0 || op == 1) {
+      ITMUChar4Image dst(op == 0 ? dims : half, true, true);
+      dst.Clear((unsigned char)prefillByte);
+      if (op == 0) e->lowLevel->CopyImage(&dst, &src); else e->lowLevel->FilterSubsample(&dst, &src);
+      dst.UpdateHostFromDevice();
+      const size_t bytes = (op == 0 ? P : Q) * 4;
+      memcpy(out, dst.GetData(MEMORYDEVICE_CPU), bytes);
+      return (long long)bytes;
+    }
+    ITMShort4Image grad(dims, true, true);
+    grad.Clear((unsigned char)prefillByte);
+    if (op == 3) e->lowLevel->GradientX(&grad, &src); else e->lowLevel->GradientY(&grad, &src);
+    grad.UpdateHostFromDevice();
+    memcpy(out, grad.GetData(MEMORYDEVICE_CPU), P * 8);
+    return (long long)(P * 8);
+  } catch (std::exception &ex) {
+    g_err = ex.what();
+    return -1;
+  }
+}
+
+// ITMViewBuilder::UpdateView(view, rgb, float depth): the view's own host images are filled first, the call uploads them;
+// returns the device depth back in depthOut.  Then the IMU variant on a fresh view: returns 0 if the measurement arrived.
+int adp_update_view_variants(adp_engine *e, const float *depth, float *depthOut, const short *rawDepth, float *imuDepthOut) {
+  try {
+    const size_t P = (size_t)e->imgSize.x * e->imgSize.y;
+    ITMFloatImage fimg(e->imgSize, true, false);
+    ITMView *v = NULL;
+    ITMViewBuilder_B200 vb(&e->calib, e->ctx);
+    vb.UpdateView(&v, e->rgb, &fimg);  // creates the view
+    memcpy(v->depth->GetData(MEMORYDEVICE_CPU), depth, P * 4);
+    vb.UpdateView(&v, e->rgb, &fimg);
+    if (cudaMemcpy(depthOut, v->depth->GetData(MEMORYDEVICE_CUDA), P * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+    delete v;
+    ITMView *vi = NULL;
+    ITMIMUMeasurement imu;
+    imu.R.setIdentity();
+    imu.R.m[1] = 0.25f;
+    memcpy(e->rawDepth->GetData(MEMORYDEVICE_CPU), rawDepth, P * sizeof(short));
+    vb.UpdateView(&vi, e->rgb, e->rawDepth, false, &imu);
+    const bool ok = ((ITMViewIMU *)vi)->imu->R.m[1] == 0.25f;
+    if (cudaMemcpy(imuDepthOut, vi->depth->GetData(MEMORYDEVICE_CUDA), P * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+    delete vi;
+    return ok ? 0 : 1;
+  } catch (std::exception &ex) {
+    g_err = ex.what();
+    return -1;
+  }
+}
+
 // ITMMainEngine::SaveSceneToMesh (ITMMainEngine.cpp:103-109): MeshScene into a CUDA ITMMesh, then the reference's own WriteSTL
 int adp_save_scene_to_mesh(adp_engine *e, const char *fileName) {
   try {

@@ -99,6 +99,9 @@ def declare_common(lib):
     if _has(lib, "ref_create_point_cloud"):
         lib.ref_create_point_cloud.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         lib.ref_create_point_cloud.restype = C.c_int
+    if _has(lib, "ref_low_level"):
+        lib.ref_low_level.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        lib.ref_low_level.restype = C.c_longlong
     if _has(lib, "ref_mesh_scene"):
         lib.ref_mesh_scene.argtypes = [C.c_void_p, C.POINTER(_f32p), _i32p]
         lib.ref_mesh_scene.restype = C.c_int
@@ -148,6 +151,22 @@ def declare_common(lib):
     lib.ref_get_counters.argtypes = [C.c_void_p, _i32p]
     lib.ref_set_counters.argtypes = [C.c_void_p, _i32p]
     return lib
+
+
+def _low_level(fn, handle, op, image, prefill):
+    h, w = image.shape[:2]
+    src = np.ascontiguousarray(image, dtype=np.float32 if op == 2 else np.uint8)
+    assert src.shape == (h, w, 4)
+    if op in (1, 2):
+        out = np.zeros((h // 2, w // 2, 4), dtype=src.dtype)
+    elif op == 0:
+        out = np.zeros((h, w, 4), dtype=np.uint8)
+    else:
+        out = np.zeros((h, w, 4), dtype=np.int16)
+    n = fn(handle, int(op), src.ctypes.data, w, h, out.ctypes.data, int(prefill))
+    if n != out.nbytes:
+        raise RuntimeError("low_level(%d) returned %d, expected %d bytes" % (op, n, out.nbytes))
+    return out
 
 
 def _fp(a):
@@ -298,6 +317,11 @@ class RefEngine:
         if n < 0:
             raise RuntimeError("ref_create_point_cloud: no view yet")
         return self.points.reshape(-1, 4)[:n].copy(), self.normals.reshape(-1, 4)[:n].copy()
+
+    def low_level(self, op, image, prefill=0):
+        """ITMLowLevelEngine_CPU helper `op` (0 CopyImage, 1 FilterSubsample, 2 FilterSubsampleWithHoles(Vector4f), 3 GradientX,
+        4 GradientY) on an (h, w, 4) image; returns the output image (uint8 / float32 / int16, 4 channels)"""
+        return _low_level(self.lib.ref_low_level, self.h, op, image, prefill)
 
     def get_image(self, image_type, pose_M=None, intr=None, width=None, height=None):
         """ITMMainEngine::GetImage; returns (h, w, 4) uint8 or None when there is no view yet"""

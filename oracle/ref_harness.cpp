@@ -303,6 +303,38 @@ int ref_create_point_cloud(ref_engine *e, const float *trafo16, int skipPoints) 
   return e->trackingState->pointCloud->noTotalPoints;
 }
 
+// ITMLowLevelEngine's colour-tracker helpers on caller data (ITMLowLevelEngine_CPU.cpp:12-108).
+// op: 0 CopyImage(uchar4), 1 FilterSubsample(uchar4), 2 FilterSubsampleWithHoles(Vector4f), 3 GradientX, 4 GradientY.
+// in: w*h input pixels; out: the output image's pixels (ops 1, 2: (w/2)*(h/2)); the output image is filled with
+// prefillByte first (the gradient drivers clear only part of it).  Returns the number of output bytes.
+long long ref_low_level(ref_engine *e, int op, const void *in, int w, int h, void *out, int prefillByte) {
+  const Vector2i dims(w, h), half(w / 2, h / 2);
+  const size_t P = (size_t)w * h, Q = (size_t)half.x * half.y;
+  if (op == 2) {
+    ITMFloat4Image src(dims, true, false), dst(half, true, false);
+    memcpy(src.GetData(MEMORYDEVICE_CPU), in, P * 16);
+    dst.Clear((unsigned char)prefillByte);
+    e->lowLevel->FilterSubsampleWithHoles(&dst, &src);
+    memcpy(out, dst.GetData(MEMORYDEVICE_CPU), Q * 16);
+    return (long long)(Q * 16);
+  }
+  ITMUChar4Image src(dims, true, false);
+  memcpy(src.GetData(MEMORYDEVICE_CPU), in, P * 4);
+  if (op == 0 || op == 1) {
+    ITMUChar4Image dst(op == 0 ? dims : half, true, false);
+    dst.Clear((unsigned char)prefillByte);
+    if (op == 0) e->lowLevel->CopyImage(&dst, &src); else e->lowLevel->FilterSubsample(&dst, &src);
+    const size_t bytes = (op == 0 ? P : Q) * 4;
+    memcpy(out, dst.GetData(MEMORYDEVICE_CPU), bytes);
+    return (long long)bytes;
+  }
+  ITMShort4Image grad(dims, true, false);
+  grad.Clear((unsigned char)prefillByte);
+  if (op == 3) e->lowLevel->GradientX(&grad, &src); else e->lowLevel->GradientY(&grad, &src);
+  memcpy(out, grad.GetData(MEMORYDEVICE_CPU), P * 8);
+  return (long long)(P * 8);
+}
+
 // ITMMainEngine::UpdateMesh (ITMMainEngine.cpp:97-101): returns noTotalTriangles; *triangles = ITMMesh::Triangle array
 int ref_mesh_scene(ref_engine *e, float **triangles, int *noMaxTriangles) {
   if (!e->mesh) { e->mesh = new ITMMesh(MEMORYDEVICE_CPU); e->meshing = new ITMMeshingEngine_CPU<TV, TI>(); }

@@ -127,3 +127,30 @@ def test_adapter_swapping_engine():
     ca, co = a.counters, o.counters
     assert abs(int(ca[1]) - int(co[1])) <= 0.02 * (o.n_local - co[1]) + 2
     a.close(); o.close()
+
+
+@needs_libs
+def test_adapter_low_level_helpers_and_view_variants():
+    """The rest of ITMLowLevelEngine (CopyImage, FilterSubsample, FilterSubsampleWithHoles(Vector4f), GradientX / GradientY:
+    ITMLowLevelEngine_CPU.cpp:12-108) and of ITMViewBuilder (float-depth and IMU UpdateView) through the adapter, bit for bit
+    against the reference CPU engine - including the gradient drivers' partial clear of the output image."""
+    w, h = 322, 242  # newDims = 161 x 121: odd sizes inside the 2x2 quads' reach
+    rng = np.random.default_rng(7)
+    o = ref.RefEngine(w, h)
+    a = adapter.AdapterEngine(w, h, intr=o.intr)
+    rgba = rng.integers(0, 256, size=(h, w, 4), dtype=np.uint8)
+    f4 = rng.normal(size=(h, w, 4)).astype(np.float32)
+    f4[..., 3] = np.where(rng.random((h, w)) < 0.3, -1.0, 1.0)  # holes
+    f4[:40, :40, 3] = -1.0  # whole quads without a valid tap
+    for op, img in ((0, rgba), (1, rgba), (2, f4), (3, rgba), (4, rgba)):
+        got, want = a.low_level(op, img, prefill=0x5A), o.low_level(op, img, prefill=0x5A)
+        assert got.shape == want.shape and np.array_equal(got.view(np.uint8), want.view(np.uint8)), "ITMLowLevelEngine helper %d differs" % op
+    g = o.low_level(3, rgba, prefill=0x5A)
+    assert np.all(g[1:-1, 1:-1, 3] == 255) and np.all(g[-1, :, 0] == 0x5A5A) and np.all(g[0, :, 0] == 0)  # the reference's partial clear
+    depth = np.where(rng.random((h, w)) < 0.1, -1.0, rng.uniform(0.5, 3.0, (h, w))).astype(np.float32)
+    raw = rng.integers(0, 4000, size=(h, w)).astype(np.int16)
+    d_float, d_imu = a.update_view_variants(depth, raw)
+    assert np.array_equal(d_float, depth)
+    o.update_view(raw)
+    assert np.array_equal(d_imu, o.depth)
+    a.close(); o.close()
