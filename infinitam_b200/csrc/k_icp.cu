@@ -258,7 +258,7 @@ __device__ ICP_LM_FINISH_ATTR bool lm_finish(LmShared &L, int iterationType, flo
   TRACE(traceSlot, 14);
   pose_set_invM_coerce(approxInvPose, M_d, params);
   TRACE(traceSlot, 15);
-  mat4_inv(M_d, approxInvPose);
+  mat4_inv_pose(M_d, approxInvPose);
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     L.M_d[i] = M_d[i];
@@ -300,7 +300,7 @@ __device__ __noinline__ bool lm_update(LmShared &L, const float *sSums, const fl
     for (int i = 0; i < 16; ++i) { M_d[i] = L.lastGoodM[i]; L.M_d[i] = M_d[i]; }
 #pragma unroll
     for (int i = 0; i < 6; ++i) L.params[i] = L.lastGoodParams[i];
-    mat4_inv(M_d, inv);
+    mat4_inv_pose(M_d, inv);
 #pragma unroll
     for (int i = 0; i < 16; ++i) L.approxInvPose[i] = inv[i];
     lambda *= 10.0f;

@@ -78,6 +78,43 @@ PM_HD bool mat4_inv(const float *m, float *dst) {
   return true;
 }
 
+// mat4_inv for a matrix whose bottom row is exactly (0, 0, 0, 1) - every pose the tracker handles.  In the cofactor
+// formula above the products with that row are x * 0 (= +-0, dropped here: adding a zero changes nothing) and x * 1
+// (= x), so what remains is the same arithmetic on the same operands in the same order: bit-identical results for
+// finite inputs (only the sign of a zero may differ) at well under half the instructions - this runs on one thread in
+// the middle of the tracker's serial chain.  Falls back to the general routine for any other bottom row.
+PM_HD bool mat4_inv_pose(const float *m, float *dst) {
+  if (!(m[3] == 0.0f && m[7] == 0.0f && m[11] == 0.0f && m[15] == 1.0f)) return mat4_inv(m, dst);
+  // rows of m (the general routine's transposed copy): a = src[0..3], b = src[4..7], c = src[8..11]
+  const float a0 = m[0], a1 = m[4], a2 = m[8], a3 = m[12];
+  const float b0 = m[1], b1 = m[5], b2 = m[9], b3 = m[13];
+  const float c0 = m[2], c1 = m[6], c2 = m[10], c3 = m[14];
+  dst[0] = c2 * b1 - c1 * b2;
+  dst[1] = c0 * b2 - c2 * b0;
+  dst[2] = c1 * b0 - c0 * b1;
+  dst[3] = 0.0f;
+  const float det = a0 * dst[0] + a1 * dst[1] + a2 * dst[2];
+  if (det == 0.0f) return false;
+  dst[4] = c1 * a2 - c2 * a1;
+  dst[5] = c2 * a0 - c0 * a2;
+  dst[6] = c0 * a1 - c1 * a0;
+  dst[7] = 0.0f;
+  const float t0 = a2 * b3, t1 = a3 * b2, t2 = a1 * b3, t3 = a3 * b1, t4 = a1 * b2, t5 = a2 * b1;
+  const float t6 = a0 * b3, t7 = a3 * b0, t8 = a0 * b2, t9 = a2 * b0, t10 = a0 * b1, t11 = a1 * b0;
+  dst[8] = t4 - t5;
+  dst[9] = t9 - t8;
+  dst[10] = t10 - t11;
+  dst[11] = 0.0f;
+  dst[12] = (t2 * c2 + t5 * c3 + t1 * c1) - (t4 * c3 + t0 * c1 + t3 * c2);
+  dst[13] = (t8 * c3 + t0 * c0 + t7 * c2) - (t6 * c2 + t9 * c3 + t1 * c0);
+  dst[14] = (t6 * c1 + t11 * c3 + t3 * c0) - (t10 * c3 + t2 * c0 + t7 * c1);
+  dst[15] = (t10 * c2 + t4 * c0 + t9 * c1) - (t8 * c1 + t11 * c2 + t5 * c0);
+  const float s = 1 / det;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) dst[i] *= s;
+  return true;
+}
+
 // r = lhs * rhs, column-major; each element accumulated from 0 in k order like the reference
 PM_HD void mat4_mul(const float *lhs, const float *rhs, float *r) {
 #pragma unroll
@@ -130,8 +167,14 @@ PM_HD void pose_params_to_M(const float *p, float *M) {
       B = 0.5f - 0.25f * one_6th * theta_sq;
     } else {
       float inv_theta = 1.0f / theta;
-      A = sinf(theta) * inv_theta;
-      B = (1.0f - cosf(theta)) * (inv_theta * inv_theta);
+      float sn, cs;
+#ifdef __CUDA_ARCH__
+      sincosf(theta, &sn, &cs);  // one argument reduction for both (same values as sinf / cosf)
+#else
+      sn = sinf(theta); cs = cosf(theta);
+#endif
+      A = sn * inv_theta;
+      B = (1.0f - cs) * (inv_theta * inv_theta);
       C = (1.0f - A) * (inv_theta * inv_theta);
     }
     float cross2[3];
@@ -246,7 +289,7 @@ PM_HD void pose_M_to_params(const float *M, float *p) {
 // pose_d->SetInvM(invM); pose_d->Coerce();  (ITMPose.cpp:316-326)
 PM_HD void pose_set_invM_coerce(const float *invM, float *M, float *params) {
   float Mtmp[16];
-  mat4_inv(invM, Mtmp);
+  mat4_inv_pose(invM, Mtmp);
   // SetInvM -> SetParamsFromModelView, then Coerce: SetParamsFromModelView once more on the same M (a pure
   // function of M, so one evaluation gives the identical params), then SetModelViewFromParams
   pose_M_to_params(Mtmp, params);
