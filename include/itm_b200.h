@@ -142,7 +142,11 @@ int itm_b200_set_alloc_mode(int mode);
 
 typedef struct itm_b200_ctx itm_b200_ctx;
 
-/* stream: a cudaStream_t (or NULL for a private stream).  */
+/* stream: the cudaStream_t every call of this context runs on, or NULL for a private NON-BLOCKING stream.  A private stream
+ * does not wait for work the caller still has in flight elsewhere - not even on the legacy default stream (an asynchronous
+ * cudaMemset of an input buffer, a kernel that produces the depth image): synchronise before calling, or pass the stream
+ * that work is on.  Code written against the legacy default stream, like ITMLib's host objects, passes cudaStreamLegacy
+ * ((void *)0x1), which is what include/itm_b200_adapter.hpp does. */
 int itm_b200_ctx_create(const itm_b200_params *params, void *stream, itm_b200_ctx **out);
 void itm_b200_ctx_destroy(itm_b200_ctx *ctx);
 

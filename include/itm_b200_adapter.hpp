@@ -96,7 +96,9 @@ class ITMB200Context {
     params.depth_tracker_icp_threshold = settings->depthTrackerICPThreshold;
     params.depth_tracker_termination_threshold = settings->depthTrackerTerminationThreshold;
     params.device = device;
-    itm_b200_check(itm_b200_ctx_create(&params, NULL, &ctx), "itm_b200_ctx_create");
+    // ITMLib's host objects work on the legacy default stream (cudaMemset in MemoryBlock::Clear, blocking cudaMemcpy); the
+    // engines run on that stream too, so that they are ordered after whatever the host code still has in flight there
+    itm_b200_check(itm_b200_ctx_create(&params, (void *)cudaStreamLegacy, &ctx), "itm_b200_ctx_create");
   }
   ~ITMB200Context() { itm_b200_ctx_destroy(ctx); }
 
