@@ -71,6 +71,7 @@ def test_stage_functions_on_caller_buffers():
     seq = synth.sequence(3, W, H)
     for k in range(3):
         raw.copy_(_dev(seq[k]))
+        torch.cuda.synchronize()  # the context has a stream of its own (include/itm_b200.h: itm_b200_ctx_create)
         o.update_view(seq[k])
         capi.check(lib.itm_b200_convert_depth_affine_to_float(ctx, depth.data_ptr(), raw.data_ptr(), W, H, 0.001, 0.0))
         assert np.array_equal(_host(depth, np.float32, (H, W)), o.depth)
