@@ -63,6 +63,7 @@ def test_stage_functions_on_caller_buffers():
         ts.pose_point_cloud[i] = ident[i]
     ts.age_point_cloud = -1
 
+    torch.cuda.synchronize()
     capi.check(lib.itm_b200_reset_scene(ctx, C.byref(scene)))
     assert (scene.last_free_block_id, scene.last_free_excess_list_id) == (o.n_local - 1, o.n_excess - 1)
     assert np.array_equal(_host(vba, np.int32), o.vba_alloc_list)
