@@ -669,7 +669,7 @@ int itm_b200_create_point_cloud(itm_b200_ctx *c, const itm_b200_scene *scene, it
                                 const float inv_M[16], const float intrinsics[4], int skip_points, int *no_total_points) {
   ON_DEVICE_OF_CTX(c);
   if (!c || !scene || !rs || !ts || !inv_M || !intrinsics || !no_total_points) return fail(ITM_B200_EINVAL, "NULL argument");
-  if (!ts->points_map_dev || !ts->normals_map_dev || !rs->raycast_image_dev || !rs->raycast_result_dev)
+  if (!ts->points_map_dev || !ts->normals_map_dev || !rs->raycast_image_dev || !rs->raycast_result_dev || !rs->rendering_range_image_dev)
     return fail(ITM_B200_EINVAL, "CreatePointCloud needs the point cloud's locations / colours and the render state's images");
   // the caller's product pose_d->GetInvM() * trafo_rgb_to_depth.calib is used as it is (castRay and the light direction
   // read nothing else); M_d is only kept consistent with it
