@@ -1132,7 +1132,7 @@ int itm_b200_mat4_inv(const float m[16], float out[16]) { return mat4_inv(m, out
 
 int itm_b200_pose_from_inv_m_coerced(const float inv_m[16], float m_out[16], float inv_out[16], float params_out[6]) {
   pose_set_invM_coerce(inv_m, m_out, params_out);
-  mat4_inv(m_out, inv_out);
+  mat4_inv_pose(m_out, inv_out);  // the routines the tracker's device loop runs (tests/test_capi_host.py pins them to the reference)
   return ITM_B200_OK;
 }
 

@@ -72,7 +72,7 @@ def test_host_pose_helpers_match_oracle():
     lib = capi.load()
     o = port.PortEngine(64, 48)
     rng = np.random.default_rng(3)
-    for _ in range(200):
+    for _ in range(2000):
         p6 = np.concatenate([rng.normal(0, 0.3, 3), rng.normal(0, 0.5, 3)]).astype(np.float32)
         M = np.zeros(16, np.float32)
         o.lib.ref_pose_from_params(_f(p6), _f(M))
