@@ -147,3 +147,53 @@ def test_cuda_rows_8f_reproduce_golden_vectors():
     assert golden_check.crc(fp) == c[0], "forward projection differs"
     assert golden_check.crc(eng.read_image(capi.BUF_RAYCAST_IMAGE, 4)) == c[2], "forward-rendered image differs"
     eng.close()
+
+
+def test_cuda_point_cloud_and_low_level_helpers_reproduce_golden_vectors():
+    """CreatePointCloud (the TRACKER_COLOR branch of ITMTrackingController::Prepare) and the colour-tracker helpers of
+    ITMLowLevelEngine against tests/golden/ref_cloud_lowlevel_qqvga.npz (made from the real reference by
+    tests/golden/make_golden_cloud.py) - exact, and independent of oracle/_ref being present."""
+    import ctypes as C
+    import os
+    import sys
+    torch = pytest.importorskip("torch")
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden_cloud as mk
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_cloud_lowlevel_qqvga.npz"))
+    W, H = int(g["W"]), int(g["H"])
+    seq = synth.sequence(1, W, H, noise=True)
+    assert golden_check.crc(seq[0]) == int(g["depth_crc"]), "synthetic generator no longer reproduces the golden input"
+    eng = ITMMainEngine(width=W, height=H)
+    eng.ProcessFrame(None, seq[0])
+    for k in range(4):
+        T = g["trafo"] if int(g["cloud%d_use_trafo" % k]) else None
+        loc, clr, img = eng.CreatePointCloud(T, None, bool(int(g["cloud%d_skip" % k])), with_image=True)
+        assert len(loc) == int(g["cloud%d_n" % k]), "noTotalPoints %d, golden %d" % (len(loc), int(g["cloud%d_n" % k]))
+        assert np.array_equal(loc[:16], g["cloud%d_head" % k])
+        assert [golden_check.crc(loc), golden_check.crc(clr), golden_check.crc(img)] == [int(x) for x in g["cloud%d_crc" % k]]
+    eng.close()
+    # ---- ITMLowLevelEngine helpers through Layer A on caller-owned buffers
+    LW, LH, prefill = int(g["LW"]), int(g["LH"]), int(g["prefill"])
+    rgba, f4 = mk.lowlevel_inputs()
+    assert [golden_check.crc(rgba), golden_check.crc(f4)] == [int(x) for x in g["lowlevel_in_crc"]], "numpy no longer reproduces the golden input"
+    lib = capi.load()
+    p = capi.default_params(W, H)
+    ctx = C.c_void_p()
+    capi.check(lib.itm_b200_ctx_create(C.byref(p), None, C.byref(ctx)))
+    d_rgba = torch.from_numpy(rgba.reshape(-1)).cuda()
+    d_f4 = torch.from_numpy(f4.reshape(-1)).cuda()
+    half = (LH // 2) * (LW // 2)
+    outs = [torch.full((LH * LW * 4,), prefill, dtype=torch.uint8, device="cuda"),   # CopyImage
+            torch.full((half * 4,), prefill, dtype=torch.uint8, device="cuda"),      # FilterSubsample
+            torch.full((half * 16,), prefill, dtype=torch.uint8, device="cuda"),     # FilterSubsampleWithHoles(Vector4f)
+            torch.full((LH * LW * 8,), prefill, dtype=torch.uint8, device="cuda"),   # GradientX (Vector4s)
+            torch.full((LH * LW * 8,), prefill, dtype=torch.uint8, device="cuda")]   # GradientY
+    torch.cuda.synchronize()
+    capi.check(lib.itm_b200_copy_image(ctx, outs[0].data_ptr(), d_rgba.data_ptr(), LH * LW * 4))
+    capi.check(lib.itm_b200_filter_subsample_rgba(ctx, outs[1].data_ptr(), d_rgba.data_ptr(), LW, LH))
+    capi.check(lib.itm_b200_filter_subsample_with_holes_float4(ctx, outs[2].data_ptr(), d_f4.data_ptr(), LW, LH))
+    capi.check(lib.itm_b200_gradient_x(ctx, outs[3].data_ptr(), d_rgba.data_ptr(), LW, LH))
+    capi.check(lib.itm_b200_gradient_y(ctx, outs[4].data_ptr(), d_rgba.data_ptr(), LW, LH))
+    got = [golden_check.crc(o.cpu().numpy()) for o in outs]
+    assert got == [int(x) for x in g["lowlevel_crc"]], "low-level helper outputs differ from the golden vectors: %s" % (got,)
+    lib.itm_b200_ctx_destroy(ctx)
