@@ -89,6 +89,7 @@ typedef struct port_engine {
   /* TRACKER_WICP: settings.modelSensorNoise / useBilateralFilter, view->depthUncertainty / depthNormal, weight hierarchy */
   int wicp, bilateral; float *float_tmp; float *sigma; V4 *dnormal; float *level_sigma[MAX_LEVELS];
   int free_w, free_h; int *free_visible_ids; int free_n_visible; V2 *free_minmax; V4 *free_raycast; unsigned char *free_image;
+  float trafo_rgb_to_depth[16]; /* ITMRGBDCalib::trafo_rgb_to_depth.calib (identity unless port_create_point_cloud installs one) */
 } port_engine;
 
 /* ------------------------------------------------------------------------------------------------
@@ -893,12 +894,15 @@ static void cast_ray(const port_engine *e, int x, int y, V2 mm, const float *inv
 }
 
 /* GenericRaycast, ITMVisualisationEngine_CPU.cpp:155-188 */
-static void raycast_for(const port_engine *e, const float *M, const float *k, int W, int H, const V2 *minmax, V4 *out) {
-  float invM[16];
+static void raycast_with_inverse(const port_engine *e, const float *invM, const float *k, int W, int H, const V2 *minmax, V4 *out) {
   int x, y;
-  m4_inverse(M, invM);
   for (y = 0; y < H; ++y) for (x = 0; x < W; ++x)
     cast_ray(e, x, y, minmax[(int)floorf((float)x / MINMAX_SUB) + (int)floorf((float)y / MINMAX_SUB) * W], invM, k, &out[x + y * W]);
+}
+static void raycast_for(const port_engine *e, const float *M, const float *k, int W, int H, const V2 *minmax, V4 *out) {
+  float invM[16];
+  m4_inverse(M, invM);
+  raycast_with_inverse(e, invM, k, W, H, minmax, out);
 }
 
 static void render_raycast(port_engine *e) {
@@ -1154,6 +1158,111 @@ static void render_free_view(port_engine *e, int renderType, const float *M, con
   }
 }
 
+/* The TRACKER_COLOR branch of ITMTrackingController::Prepare (ITMTrackingController.cpp:22-28): CreateExpectedDepths at
+ * pose_rgb = trafo_rgb_to_depth.calib_inv * pose_d, then CreatePointCloud_common + RenderPointCloud
+ * (ITMVisualisationEngine_CPU.cpp:242-264, 424-462) with invM = pose_d^-1 * trafo_rgb_to_depth.calib; the colour camera has the
+ * depth camera's intrinsics here.  calib_inv as ITMExtrinsics::SetFrom builds it (Objects/ITMExtrinsics.h:32-42).  ITMVoxel_s
+ * has no colour: VoxelColorReader<false> returns zeros.  Points land in e->points, colours in e->normals (the point cloud's
+ * two images); returns noTotalPoints. */
+static int render_point_cloud(port_engine *e, int skipPoints) {
+  const port_params *p = &e->p;
+  const int W = p->width, H = p->height;
+  const float k[4] = {p->fx, p->fy, p->cx, p->cy};
+  const float *T = e->trafo_rgb_to_depth;
+  float Tinv[16], pose_rgb[16], invPose[16], invM[16], light[3];
+  int r, c, x, y, n = 0;
+  for (r = 0; r < 16; ++r) Tinv[r] = (r % 5 == 0) ? 1.0f : 0.0f;
+  for (r = 0; r < 3; ++r) for (c = 0; c < 3; ++c) Tinv[r + 4 * c] = T[c + 4 * r];
+  for (r = 0; r < 3; ++r) {
+    float d = 0.0f;
+    for (c = 0; c < 3; ++c) d -= T[c + 4 * r] * T[c + 4 * 3];
+    Tinv[r + 4 * 3] = d;
+  }
+  m4_product(Tinv, e->pose_M, pose_rgb);
+  expected_depths_for(e, pose_rgb, k, W, H, e->visible_ids, e->n_visible, e->minmax);
+  m4_inverse(e->pose_M, invPose);
+  m4_product(invPose, T, invM);
+  raycast_with_inverse(e, invM, k, W, H, e->minmax, e->raycast);
+  memcpy(e->pose_pc_M, e->pose_M, sizeof(e->pose_pc_M));
+  light[0] = -invM[8]; light[1] = -invM[9]; light[2] = -invM[10];
+  for (y = 0; y < H; ++y) for (x = 0; x < W; ++x) {
+    const int i = x + y * W;
+    const V4 pt = e->raycast[i];
+    unsigned char *o = e->raycast_image + (size_t)i * 4;
+    int found = pt.w > 0;
+    if (found) {
+      float nrm[3], scale, angle;
+      normal_from_sdf(e, pt.x, pt.y, pt.z, nrm);
+      scale = 1.0f / sqrtf(nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2]);
+      angle = nrm[0] * scale * light[0] + nrm[1] * scale * light[1] + nrm[2] * scale * light[2];
+      if (!(angle > 0.0)) found = 0;
+      else o[0] = o[1] = o[2] = o[3] = (unsigned char)((0.8f * angle + 0.2f) * 255.0f);
+    }
+    if (!found) { o[0] = o[1] = o[2] = o[3] = 0; }
+    if (skipPoints && ((x % 2 == 0) || (y % 2 == 0))) found = 0;
+    if (found) {
+      V4 zero = {0.0f, 0.0f, 0.0f, 0.0f}, loc;
+      e->normals[n] = zero;
+      loc.x = pt.x * p->voxel_size; loc.y = pt.y * p->voxel_size; loc.z = pt.z * p->voxel_size; loc.w = 1.0f;
+      e->points[n] = loc;
+      n++;
+    }
+  }
+  return n;
+}
+
+/* ITMLowLevelEngine_CPU's colour-tracker helpers (ITMLowLevelEngine_CPU.cpp:12-108; filterSubsample, filterSubsampleWithHoles
+ * for Vector4f, gradientX / gradientY: DeviceAgnostic/ITMLowLevelEngine.h:7-124).  op: 0 CopyImage, 1 FilterSubsample,
+ * 2 FilterSubsampleWithHoles(Vector4f), 3 GradientX, 4 GradientY; `out` is filled with prefillByte first (the gradient drivers
+ * clear only the first w*h*sizeof(Vector3s) bytes of their Vector4s image).  Returns the number of output bytes. */
+static long long low_level(int op, const void *in, int w, int h, void *out, int prefillByte) {
+  const int w2 = w / 2, h2 = h / 2;
+  int x, y, ch, j;
+  if (op == 0) { memcpy(out, in, (size_t)w * h * 4); return (long long)w * h * 4; }
+  if (op == 1) {
+    const unsigned char *s = (const unsigned char *)in;
+    unsigned char *d = (unsigned char *)out;
+    for (y = 0; y < h2; ++y) for (x = 0; x < w2; ++x) for (ch = 0; ch < 4; ++ch) {
+      const int a = s[((2 * x) + (2 * y) * w) * 4 + ch], b = s[((2 * x + 1) + (2 * y) * w) * 4 + ch];
+      const int c = s[((2 * x) + (2 * y + 1) * w) * 4 + ch], e4 = s[((2 * x + 1) + (2 * y + 1) * w) * 4 + ch];
+      d[(x + y * w2) * 4 + ch] = (unsigned char)((a + b + c + e4) / 4);
+    }
+    return (long long)w2 * h2 * 4;
+  }
+  if (op == 2) {
+    const V4 *s = (const V4 *)in;
+    V4 *d = (V4 *)out;
+    for (y = 0; y < h2; ++y) for (x = 0; x < w2; ++x) {
+      const V4 tap[4] = {s[(2 * x) + (2 * y) * w], s[(2 * x + 1) + (2 * y) * w], s[(2 * x) + (2 * y + 1) * w], s[(2 * x + 1) + (2 * y + 1) * w]};
+      V4 acc = {0.0f, 0.0f, 0.0f, 0.0f};
+      float good = 0.0f;
+      for (j = 0; j < 4; ++j) if (tap[j].w >= 0) { acc.x += tap[j].x; acc.y += tap[j].y; acc.z += tap[j].z; acc.w += tap[j].w; good++; }
+      if (good > 0) { acc.x /= good; acc.y /= good; acc.z /= good; acc.w /= good; } else acc.w = -1.0f;
+      d[x + y * w2] = acc;
+    }
+    return (long long)w2 * h2 * 16;
+  }
+  {
+    const unsigned char *s = (const unsigned char *)in;
+    short *g = (short *)out;
+    memset(out, prefillByte, (size_t)w * h * 8);
+    memset(out, 0, (size_t)w * h * 6);
+    for (y = 1; y < h - 1; ++y) for (x = 1; x < w - 1; ++x) {
+      for (ch = 0; ch < 3; ++ch) {
+        short d3[3];
+        for (j = -1; j <= 1; ++j) {
+          const int hi = (op == 3) ? s[((x + 1) + (y + j) * w) * 4 + ch] : s[((x + j) + (y + 1) * w) * 4 + ch];
+          const int lo = (op == 3) ? s[((x - 1) + (y + j) * w) * 4 + ch] : s[((x + j) + (y - 1) * w) * 4 + ch];
+          d3[j + 1] = (short)(hi - lo);
+        }
+        g[(x + y * w) * 4 + ch] = (short)((d3[0] + 2 * d3[1] + d3[2]) / 8);
+      }
+      g[(x + y * w) * 4 + 3] = (short)((2 * 255 + 2 * (2 * 255) + 2 * 255) / 8);
+    }
+    return (long long)w * h * 8;
+  }
+}
+
 /* The marching-cubes case table (the classic Lorensen-Cline / Bourke triangulation the reference uses,
  * DeviceAgnostic/ITMMeshingEngine.h:9-151), one 64-bit word per case: nibble i = i-th edge index, 0xF terminates. */
 static const unsigned long long MC_CASE[256] = {
@@ -1337,6 +1446,7 @@ port_engine *port_create(const port_params *pp) {
   /* ITMRenderState constructor fills the range image with the frustum limits (Objects/ITMRenderState.h:60-72) */
   { size_t i; for (i = 0; i < P; ++i) { e->minmax[i].x = pp->vf_min; e->minmax[i].y = pp->vf_max; } }
   memcpy(e->pose_M, ident, sizeof(ident)); memcpy(e->pose_pc_M, ident, sizeof(ident));
+  memcpy(e->trafo_rgb_to_depth, ident, sizeof(ident));
   e->age = -1;
   /* hierarchy: ITMDepthTracker constructor (ITMDepthTracker.cpp:11-36), intrinsics halving (:62-75) */
   w = pp->width; h = pp->height; fx = pp->fx; fy = pp->fy; cx = pp->cx; cy = pp->cy;
@@ -1430,6 +1540,15 @@ int port_get_image(port_engine *e, int type, const float *M, const float *k, int
   render_free_view(e, type == 5 ? 2 : 0, M, k, w, h);
   memcpy(out, e->free_image, (size_t)w * h * 4);
   return 0;
+}
+int port_create_point_cloud(port_engine *e, const float *trafo16, int skipPoints) {
+  if (trafo16) memcpy(e->trafo_rgb_to_depth, trafo16, 64);
+  return render_point_cloud(e, skipPoints);
+}
+long long port_low_level(port_engine *e, int op, const void *in, int w, int h, void *out, int prefillByte) {
+  (void)e;
+  if (op != 3 && op != 4) memset(out, prefillByte, op == 0 ? (size_t)w * h * 4 : op == 1 ? (size_t)(w / 2) * (h / 2) * 4 : (size_t)(w / 2) * (h / 2) * 16);
+  return low_level(op, in, w, h, out, prefillByte);
 }
 int *port_free_visible_ids(port_engine *e) { return e->free_visible_ids; }
 int port_free_no_visible(port_engine *e) { return e->free_n_visible; }

@@ -218,3 +218,30 @@ def test_port_weighted_icp_equals_the_reference(bilateral):
         assert np.array_equal(p.pose_M, r.pose_M), "frame %d pose" % k
     assert np.abs(r.pose_M - np.eye(4, dtype=np.float32).reshape(16)).max() > 0.01
     r.close(); p.close()
+
+
+def test_port_point_cloud_and_low_level_helpers_reproduce_golden_vectors():
+    """the restatement's CreatePointCloud (TRACKER_COLOR branch of Prepare) and ITMLowLevelEngine helpers against
+    tests/golden/ref_cloud_lowlevel_qqvga.npz (made from the real reference by tests/golden/make_golden_cloud.py): runs everywhere"""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden_cloud as mk
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_cloud_lowlevel_qqvga.npz"))
+    w, h = int(g["W"]), int(g["H"])
+    seq = synth.sequence(1, w, h, noise=True)
+    assert golden_check.crc(seq[0]) == int(g["depth_crc"])
+    p = port.PortEngine(w, h)
+    p.process_frame(seq[0])
+    ident = np.eye(4, dtype=np.float32).reshape(16)
+    for k in range(4):
+        T = g["trafo"] if int(g["cloud%d_use_trafo" % k]) else ident
+        loc, clr = p.create_point_cloud(T, skip_points=bool(int(g["cloud%d_skip" % k])))
+        assert len(loc) == int(g["cloud%d_n" % k])
+        assert np.array_equal(loc[:16], g["cloud%d_head" % k])
+        assert [golden_check.crc(loc), golden_check.crc(clr), golden_check.crc(p.raycast_image)] == [int(x) for x in g["cloud%d_crc" % k]]
+    rgba, f4 = mk.lowlevel_inputs()
+    assert [golden_check.crc(rgba), golden_check.crc(f4)] == [int(x) for x in g["lowlevel_in_crc"]]
+    got = [golden_check.crc(p.low_level(op, f4 if op == 2 else rgba, prefill=int(g["prefill"]))) for op in range(5)]
+    assert got == [int(x) for x in g["lowlevel_crc"]]
+    p.close()
